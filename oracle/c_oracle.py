@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of oracle/mpc_oracle.c (the plain-C CPU oracle).
+
+Importers: tests/, __graft_entry__.smoke(), bench.py cpu_baseline / --impl reference.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmpc_oracle.so")
+
+CTRL_ZERO, CTRL_CONSTANT, CTRL_TANGENTIAL, CTRL_SEQUENCE = 0, 1, 2, 3
+
+
+class OrcParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in ("MU", "R_E", "J2", "G0", "ISP", "S", "R0", "RHO", "C_D", "RHO_ATM")] + \
+               [("include_J2", ctypes.c_int), ("include_drag", ctypes.c_int)]
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "mpc_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libmpc_oracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        dp = ctypes.POINTER(ctypes.c_double)
+        ip = ctypes.POINTER(ctypes.c_int)
+        _lib.orc_discretize_rk4.argtypes = [dp, dp, dp, ctypes.POINTER(OrcParams), ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, dp, ip, ctypes.c_int]
+        _lib.orc_discretize_rk4.restype = ctypes.c_int
+        _lib.orc_propagate_rk4.argtypes = [dp, dp, ctypes.POINTER(OrcParams), ctypes.c_int, dp, dp, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           dp, dp, ip, ctypes.c_int]
+        _lib.orc_propagate_rk4.restype = ctypes.c_int
+        _lib.orc_max_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.983e-13):
+    return OrcParams(const.MU, const.R_E, const.J2, const.G0, const.ISP, const.S, const.R0, const.RHO,
+                     c_d, rho_atm, int(include_J2), int(include_drag))
+
+
+def max_threads():
+    return lib().orc_max_threads()
+
+
+def discretize_batch(x, u, tf, const, include_J2=False, n_sub=100, nthreads=0):
+    """x [N,7,K], u [N,3,K], tf scalar or [N] -> (A[N,K-1,7,7], B_kp[N,K-1,7,3], B_kn, Sigma[N,7,K-1], xi[N,7,K-1], status)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    N, _, K = x.shape
+    tf = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    out = np.zeros((N, K - 1, 105))
+    status = np.zeros(N * (K - 1), dtype=np.int32)
+    p = make_params(const, include_J2)
+    lib().orc_discretize_rk4(_dp(x), _dp(u), _dp(tf), ctypes.byref(p), N, K, n_sub, _dp(out),
+                             status.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), nthreads)
+    A = out[:, :, 0:49].reshape(N, K - 1, 7, 7)
+    Bp = out[:, :, 49:70].reshape(N, K - 1, 7, 3)
+    Bn = out[:, :, 70:91].reshape(N, K - 1, 7, 3)
+    S = out[:, :, 91:98].transpose(0, 2, 1)
+    X = out[:, :, 98:105].transpose(0, 2, 1)
+    return A, Bp, Bn, S, X, status.reshape(N, K - 1)
+
+
+def propagate_batch(y0, tf, const, kind=CTRL_ZERO, cparams=(0.0, 0.0, 0.0), table=None, end_tau=1.0,
+                    include_drag=True, include_J2=True, T=100, n_sub=10, nthreads=0):
+    """y0 [N,7] -> (y[N,7,T], u[N,3,T], status[N]); samples at linspace(0,1,T)."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    N = y0.shape[0]
+    tf = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    cp = np.ascontiguousarray(np.resize(np.asarray(cparams, dtype=np.float64), 3))
+    Ku, per_sat = 0, 0
+    if table is not None:
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        Ku = table.shape[-1]
+        per_sat = int(table.ndim == 3)
+    y = np.zeros((N, 7, T))
+    uo = np.zeros((N, 3, T))
+    status = np.zeros(N, dtype=np.int32)
+    p = make_params(const, include_J2, include_drag)
+    lib().orc_propagate_rk4(_dp(y0), _dp(tf), ctypes.byref(p), kind, _dp(cp), _dp(table), Ku, per_sat,
+                            float(end_tau), N, T, n_sub, _dp(y), _dp(uo),
+                            status.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), nthreads)
+    return y, uo, status

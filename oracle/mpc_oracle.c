@@ -1,0 +1,384 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- plain-C CPU oracle for the batched SCvx discretize / propagate
+ * hot path.  It checks the CUDA kernels (tests/, __graft_entry__.smoke) and is the timed
+ * "port" CPU baseline in bench.py; the product library never links or calls it.
+ *
+ * What it restates (file:line under /root/reference):
+ *   - dynamics f                      simulator.py:115-161
+ *   - Jacobians A = tf*Dxf, B = tf*Duf linearize_discretize.py:119-183, :186-215
+ *   - residual xi, Sigma              linearize_discretize.py:218-254
+ *   - augmented IVP  [Phi;x]' = [A Phi; f]    linearize_discretize.py:262-290
+ *   - FOH input interpolation         linearize_discretize.py:294-315
+ *   - quadrature: inverse of Phi at every node, lambda weights, trapezoid rule, final
+ *     left-multiply by Phi(tau_{k+1})  linearize_discretize.py:52-80
+ *   - controller laws                 control.py:20-29, 47-53, 66-84, 104-143
+ *   - propagation over tau in [0,1]   simulator.py:164-189
+ *
+ * Deliberately the *naive dense* formulation (56-vector classical RK4, dense 7x7 products,
+ * Gauss-Jordan inverse with partial pivoting, the reference's literal J2 Jacobian) so that it
+ * is independent of the structure-exploiting CUDA kernels it checks.
+ *
+ * The time integrator is fixed-step classical RK4 with n_sub steps per interval and the
+ * trapezoid rule on the n_sub+1 step nodes -- the reference's `use_uniform_steps=True,
+ * integrator_steps=n_sub+1` node set (linearize_discretize.py:27-28,47-48), with scipy's
+ * adaptive RK45 + dense output replaced by RK4 on those nodes.  Pinned against the reference
+ * through tests/golden (tests/test_oracle_golden.py): <= 1e-8 norm-relative.
+ */
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    double MU, R_E, J2, G0, ISP, S, R0, RHO; /* satellite_scale.py:42-44 */
+    double C_D, RHO_ATM;                     /* constants.py:7, simulator.py:112 */
+    int include_J2, include_drag;
+} orc_params;
+
+enum { ORC_CTRL_ZERO = 0, ORC_CTRL_CONSTANT = 1, ORC_CTRL_TANGENTIAL = 2, ORC_CTRL_SEQUENCE = 3 };
+
+static double norm3(const double *a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+
+/* f / tf : simulator.py:130-160 */
+static int dyn(const double *y, const double *u, const orc_params *p, int drag, int j2, double *dy)
+{
+    const double *r = y, *v = y + 3;
+    double m = y[6];
+    if (!(m > 0.0)) return 1;
+    double rn = norm3(r);
+    double g = -p->MU / (rn * rn * rn);
+    for (int i = 0; i < 3; ++i) {
+        dy[i] = v[i];
+        dy[3 + i] = g * r[i] + u[i] / m;
+    }
+    if (drag) {
+        double vn = norm3(v);
+        double c = -0.5 * p->C_D * p->S * (1.0 / m) * (p->RHO_ATM / p->RHO) * vn;
+        for (int i = 0; i < 3; ++i) dy[3 + i] += c * v[i];
+    }
+    if (j2) {
+        double q = 5.0 * (r[2] / rn) * (r[2] / rn);
+        double k = 1.5 * p->J2 * p->MU * p->R_E * p->R_E / pow(rn, 5);
+        dy[3] += k * (q - 1.0) * r[0];
+        dy[4] += k * (q - 1.0) * r[1];
+        dy[5] += k * (q - 3.0) * r[2];
+    }
+    dy[6] = -norm3(u) / (p->G0 * p->ISP);
+    return 0;
+}
+
+/* Dxf (7x7 row-major), linearize_discretize.py:134-179 without the (unusable) drag branch */
+static void dxf(const double *x, const double *u, const orc_params *p, int j2, double *D)
+{
+    memset(D, 0, 49 * sizeof(double));
+    const double *r = x;
+    double m = x[6];
+    double rn = norm3(r), rn2 = rn * rn;
+    double c3 = -p->MU / (rn2 * rn), c5 = 3.0 * p->MU / (rn2 * rn2 * rn);
+    for (int i = 0; i < 3; ++i) {
+        D[i * 7 + 3 + i] = 1.0;
+        for (int j = 0; j < 3; ++j) D[(3 + i) * 7 + j] = (i == j ? c3 : 0.0) + c5 * r[i] * r[j];
+        D[(3 + i) * 7 + 6] = -u[i] / (m * m);
+    }
+    if (j2) {
+        double kJ2 = 1.5 * p->J2 * p->MU * p->R_E * p->R_E;
+        double zz = (r[2] / rn) * (r[2] / rn);
+        double gd[3] = {5 * zz - 1, 5 * zz - 1, 5 * zz - 3};
+        double ddr[3];
+        for (int j = 0; j < 3; ++j) ddr[j] = 5 * r[2] * r[2] * (-2 * r[j] / (rn2 * rn2));
+        ddr[2] += (5 / rn2) * 2 * r[2];
+        double rn5 = rn2 * rn2 * rn, rn7 = rn5 * rn2;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                D[(3 + i) * 7 + j] += kJ2 * gd[i] * r[i] * (-5 * r[j] / rn7) + kJ2 / rn5 * r[i] * ddr[j]
+                                      + (i == j ? kJ2 / rn5 * gd[i] : 0.0);
+    }
+}
+
+/* Duf (7x3 row-major), linearize_discretize.py:200-212 */
+static void duf(const double *x, const double *u, const orc_params *p, double *D)
+{
+    memset(D, 0, 21 * sizeof(double));
+    double m = x[6];
+    for (int i = 0; i < 3; ++i) D[(3 + i) * 3 + i] = 1.0 / m;
+    double nT = norm3(u);
+    if (nT > 2.220446049250313e-16)
+        for (int j = 0; j < 3; ++j) D[6 * 3 + j] = -u[j] / (p->G0 * p->ISP * nT);
+}
+
+/* augmented RHS, y = [Phi row-major (49), x (7)]; linearize_discretize.py:262-290 */
+static int aug_rhs(const double *y, const double *u, double tf, const orc_params *p, int j2, double *dy)
+{
+    double D[49], f[7];
+    dxf(y + 49, u, p, j2, D);
+    if (dyn(y + 49, u, p, 0, j2, f)) return 1;
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) {
+            double s = 0.0;
+            for (int l = 0; l < 7; ++l) s += D[i * 7 + l] * y[l * 7 + j];
+            dy[i * 7 + j] = tf * s;
+        }
+    for (int i = 0; i < 7; ++i) dy[49 + i] = tf * f[i];
+    return 0;
+}
+
+static int inv7(const double *M, double *Inv)
+{
+    double a[7][14];
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) {
+            a[i][j] = M[i * 7 + j];
+            a[i][7 + j] = (i == j);
+        }
+    for (int c = 0; c < 7; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 7; ++r)
+            if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+        if (a[piv][c] == 0.0) return 1;
+        if (piv != c)
+            for (int j = 0; j < 14; ++j) {
+                double t = a[c][j];
+                a[c][j] = a[piv][j];
+                a[piv][j] = t;
+            }
+        double d = 1.0 / a[c][c];
+        for (int j = 0; j < 14; ++j) a[c][j] *= d;
+        for (int r = 0; r < 7; ++r)
+            if (r != c) {
+                double f = a[r][c];
+                if (f != 0.0)
+                    for (int j = 0; j < 14; ++j) a[r][j] -= f * a[c][j];
+            }
+    }
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) Inv[i * 7 + j] = a[i][7 + j];
+    return 0;
+}
+
+/* One interval; out = A(49) B_kp(21) B_kn(21) Sigma(7) xi(7); linearize_discretize.py:8-82.
+ * u0/u1 are the FOH end points of this interval (u is linear inside one interval, :305-315). */
+static int interval(const double *xk, const double *u0, const double *u1, double tf, double dtau, int n_sub,
+                    const orc_params *p, int j2, double *out)
+{
+    double y[56], k1[56], k2[56], k3[56], k4[56], yt[56];
+    memset(y, 0, sizeof y);
+    for (int i = 0; i < 7; ++i) {
+        y[i * 7 + i] = 1.0;
+        y[49 + i] = xk[i];
+    }
+    double accBp[21] = {0}, accBn[21] = {0}, accS[7] = {0}, accX[7] = {0};
+    double h = dtau / n_sub;
+    for (int n = 0; n <= n_sub; ++n) {
+        double lam_p = (double)n / n_sub, lam_n = 1.0 - lam_p;
+        double un[3];
+        for (int i = 0; i < 3; ++i) un[i] = lam_n * u0[i] + lam_p * u1[i];
+        /* node terms, :63-75 */
+        double Pinv[49], Bm[21], Dx[49], sig[7], xi[7];
+        const double *xs = y + 49;
+        if (inv7(y, Pinv)) return 3;
+        duf(xs, un, p, Bm);
+        for (int i = 0; i < 21; ++i) Bm[i] *= tf;
+        if (dyn(xs, un, p, 0, j2, sig)) return 1;
+        dxf(xs, un, p, j2, Dx);
+        for (int i = 0; i < 7; ++i) {
+            double s = 0.0;
+            for (int l = 0; l < 7; ++l) s += tf * Dx[i * 7 + l] * xs[l];
+            for (int l = 0; l < 3; ++l) s += Bm[i * 3 + l] * un[l];
+            xi[i] = -s;
+        }
+        double w = (n == 0 || n == n_sub) ? 0.5 * h : h; /* uniform-node trapezoid, :77-80 */
+        for (int i = 0; i < 7; ++i) {
+            double ss = 0.0, sx = 0.0;
+            for (int l = 0; l < 7; ++l) {
+                ss += Pinv[i * 7 + l] * sig[l];
+                sx += Pinv[i * 7 + l] * xi[l];
+            }
+            accS[i] += w * ss;
+            accX[i] += w * sx;
+            for (int j = 0; j < 3; ++j) {
+                double sb = 0.0;
+                for (int l = 0; l < 7; ++l) sb += Pinv[i * 7 + l] * Bm[l * 3 + j];
+                accBp[i * 3 + j] += w * lam_p * sb;
+                accBn[i * 3 + j] += w * lam_n * sb;
+            }
+        }
+        if (n == n_sub) break;
+        /* classical RK4 step on the 56-vector */
+        double um[3], ue[3];
+        double lm = (n + 0.5) / n_sub, le = (n + 1.0) / n_sub;
+        for (int i = 0; i < 3; ++i) {
+            um[i] = (1.0 - lm) * u0[i] + lm * u1[i];
+            ue[i] = (1.0 - le) * u0[i] + le * u1[i];
+        }
+        if (aug_rhs(y, un, tf, p, j2, k1)) return 1;
+        for (int i = 0; i < 56; ++i) yt[i] = y[i] + 0.5 * h * k1[i];
+        if (aug_rhs(yt, um, tf, p, j2, k2)) return 1;
+        for (int i = 0; i < 56; ++i) yt[i] = y[i] + 0.5 * h * k2[i];
+        if (aug_rhs(yt, um, tf, p, j2, k3)) return 1;
+        for (int i = 0; i < 56; ++i) yt[i] = y[i] + h * k3[i];
+        if (aug_rhs(yt, ue, tf, p, j2, k4)) return 1;
+        for (int i = 0; i < 56; ++i) y[i] += h / 6.0 * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
+    }
+    memcpy(out, y, 49 * sizeof(double));
+    for (int i = 0; i < 7; ++i) {
+        double ss = 0.0, sx = 0.0;
+        for (int l = 0; l < 7; ++l) {
+            ss += y[i * 7 + l] * accS[l];
+            sx += y[i * 7 + l] * accX[l];
+        }
+        out[91 + i] = ss;
+        out[98 + i] = sx;
+        for (int j = 0; j < 3; ++j) {
+            double sp = 0.0, sn = 0.0;
+            for (int l = 0; l < 7; ++l) {
+                sp += y[i * 7 + l] * accBp[l * 3 + j];
+                sn += y[i * 7 + l] * accBn[l * 3 + j];
+            }
+            out[49 + i * 3 + j] = sp;
+            out[70 + i * 3 + j] = sn;
+        }
+    }
+    for (int i = 0; i < 105; ++i)
+        if (!isfinite(out[i])) return 2;
+    return 0;
+}
+
+/*
+ * Batched discretization.  x [N][7][K], u [N][3][K], tf [N]; out [N][K-1][105]
+ * (A row-major 49 | B_kp 21 | B_kn 21 | Sigma 7 | xi 7); status [N*(K-1)].
+ * nthreads <= 0: all OpenMP threads.  Returns the number of failed intervals.
+ */
+int orc_discretize_rk4(const double *x, const double *u, const double *tf, const orc_params *p, int N, int K,
+                       int n_sub, double *out, int *status, int nthreads)
+{
+    long total = (long)N * (K - 1);
+    int bad = 0;
+    if (K < 2 || N < 1) return 0;
+    double dtau = 1.0 / (K - 1);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (long i = 0; i < total; ++i) {
+        int s = (int)(i / (K - 1)), k = (int)(i % (K - 1));
+        double xk[7], u0[3], u1[3];
+        for (int c = 0; c < 7; ++c) xk[c] = x[((long)s * 7 + c) * K + k];
+        for (int c = 0; c < 3; ++c) {
+            u0[c] = u[((long)s * 3 + c) * K + k];
+            u1[c] = u[((long)s * 3 + c) * K + k + 1];
+        }
+        int st = interval(xk, u0, u1, tf[s], dtau, n_sub, p, p->include_J2, out + i * 105);
+        if (status) status[i] = st;
+        bad += (st != 0);
+    }
+    return bad;
+}
+
+/* controller laws, control.py:20-29,47-53,66-84,104-143 */
+static void ctrl_eval(int kind, const double *cp, const double *tab, int Ku, double end_tau, const double *x,
+                      double tau, double *u)
+{
+    u[0] = u[1] = u[2] = 0.0;
+    if (kind == ORC_CTRL_CONSTANT) {
+        u[0] = cp[0];
+        u[1] = cp[1];
+        u[2] = cp[2];
+    } else if (kind == ORC_CTRL_TANGENTIAL) {
+        const double *r = x, *v = x + 3;
+        double rn = norm3(r);
+        double rh[3] = {r[0] / rn, r[1] / rn, r[2] / rn};
+        double h[3] = {r[1] * v[2] - r[2] * v[1], r[2] * v[0] - r[0] * v[2], r[0] * v[1] - r[1] * v[0]};
+        double hn = norm3(h);
+        double hh[3] = {h[0] / hn, h[1] / hn, h[2] / hn};
+        u[0] = cp[0] * (hh[1] * rh[2] - hh[2] * rh[1]);
+        u[1] = cp[0] * (hh[2] * rh[0] - hh[0] * rh[2]);
+        u[2] = cp[0] * (hh[0] * rh[1] - hh[1] * rh[0]);
+    } else if (kind == ORC_CTRL_SEQUENCE) {
+        if (tau <= end_tau) {
+            double t = tau / end_tau;
+            if (t == 1.0) {
+                for (int c = 0; c < 3; ++c) u[c] = tab[c * Ku + Ku - 1];
+            } else {
+                double dt = 1.0 / (Ku - 1);
+                int k = (int)floor(t / dt);
+                if (k > Ku - 2) k = Ku - 2;
+                double lo = (double)k / (Ku - 1), hi = (double)(k + 1) / (Ku - 1);
+                double ln = (hi - t) / (hi - lo), lp = (t - lo) / (hi - lo);
+                for (int c = 0; c < 3; ++c) u[c] = ln * tab[c * Ku + k] + lp * tab[c * Ku + k + 1];
+            }
+        }
+    }
+}
+
+static int prop_rhs(const double *y, double tau, double tf, const orc_params *p, int kind, const double *cp,
+                    const double *tab, int Ku, double end_tau, double *dy)
+{
+    double u[3];
+    ctrl_eval(kind, cp, tab, Ku, end_tau, y, tau, u);
+    if (dyn(y, u, p, p->include_drag, p->include_J2, dy)) return 1;
+    for (int i = 0; i < 7; ++i) dy[i] *= tf;
+    return 0;
+}
+
+/*
+ * Batched propagation.  y0 [N][7], tf [N]; samples at tau_j = j/(T-1) with n_sub RK4 steps between
+ * samples; y [N][7][T], u_out [N][3][T] (= extract_uk, linearize_discretize.py:393-411).
+ * ctrl_tab: [N][3][Ku] when tab_per_sat, else [3][Ku].
+ */
+int orc_propagate_rk4(const double *y0, const double *tf, const orc_params *p, int kind, const double *cp,
+                      const double *ctrl_tab, int Ku, int tab_per_sat, double end_tau, int N, int T, int n_sub,
+                      double *y, double *u_out, int *status, int nthreads)
+{
+    int bad = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int s = 0; s < N; ++s) {
+        const double *tab = ctrl_tab ? ctrl_tab + (tab_per_sat ? (long)s * 3 * Ku : 0) : 0;
+        double x[7], k1[7], k2[7], k3[7], k4[7], xt[7], us[3];
+        int st = 0;
+        for (int c = 0; c < 7; ++c) x[c] = y0[s * 7 + c];
+        double h = (T > 1) ? 1.0 / ((double)(T - 1) * n_sub) : 0.0;
+        for (int j = 0; j < T && !st; ++j) {
+            double tau_j = (T > 1) ? (double)j / (T - 1) : 0.0;
+            for (int c = 0; c < 7; ++c) y[((long)s * 7 + c) * T + j] = x[c];
+            if (u_out) {
+                ctrl_eval(kind, cp, tab, Ku, end_tau, x, tau_j, us);
+                for (int c = 0; c < 3; ++c) u_out[((long)s * 3 + c) * T + j] = us[c];
+            }
+            if (j == T - 1) break;
+            for (int n = 0; n < n_sub; ++n) {
+                /* step end points computed from integers so the last one is exactly tau_{j+1}
+                 * (and exactly 1.0 at the end of the run, as solve_ivp clips to t_bound) */
+                double tau_n = (T > 1) ? (double)(j + 1) / (T - 1) : 0.0;
+                double t0 = (n == 0) ? tau_j : tau_j + n * h;
+                double t1 = (n == n_sub - 1) ? tau_n : tau_j + (n + 1) * h;
+                double tm = 0.5 * (t0 + t1);
+                st |= prop_rhs(x, t0, tf[s], p, kind, cp, tab, Ku, end_tau, k1);
+                for (int c = 0; c < 7; ++c) xt[c] = x[c] + 0.5 * h * k1[c];
+                st |= prop_rhs(xt, tm, tf[s], p, kind, cp, tab, Ku, end_tau, k2);
+                for (int c = 0; c < 7; ++c) xt[c] = x[c] + 0.5 * h * k2[c];
+                st |= prop_rhs(xt, tm, tf[s], p, kind, cp, tab, Ku, end_tau, k3);
+                for (int c = 0; c < 7; ++c) xt[c] = x[c] + h * k3[c];
+                st |= prop_rhs(xt, t1, tf[s], p, kind, cp, tab, Ku, end_tau, k4);
+                if (st) break;
+                for (int c = 0; c < 7; ++c) x[c] += h / 6.0 * (k1[c] + 2.0 * k2[c] + 2.0 * k3[c] + k4[c]);
+            }
+        }
+        if (status) status[s] = st;
+        bad += (st != 0);
+    }
+    return bad;
+}
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,182 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference).
+
+Run in the build container only:  python tests/golden/make_golden.py
+The reference pins no numeric result of its own on this path (its tests only plot),
+so these fixtures -- outputs of the reference itself on its own test scenarios -- are
+what pins oracle/ and, through it, the CUDA path.  Scenario sources are cited inline.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle.refshim import load_reference  # noqa: E402
+
+R = load_reference()
+F = R.Simulator.satellite_dynamics
+
+# Hubble state, ref: test_discretizer.py:17-21
+R_INIT = np.array([5371.4806, -4133.1393, 1399.9594]) * 1000
+V_INIT = np.array([4.6921, 4.9848, -3.2752]) * 1000
+M_INIT = 12200.0
+
+
+def const_vec(c):
+    return np.array([c.MU, c.R_E, c.J2, c.G0, c.ISP, c.S, c.R0, c.RHO])
+
+
+def disc(const, x, u, tf, uniform, J2=False, steps=101, ks=None):
+    d = R.Discretizer(const, include_J2=J2)
+    d.use_uniform_steps = uniform
+    d.integrator_steps = steps
+    if ks is None:
+        return d.discretize(F, x, u, tf)
+    # in-process per-interval call (name-mangled privates, ref: linearize_discretize.py:115-116,357-358)
+    K = x.shape[1]
+    d._Discretizer__tau = np.linspace(0, 1, K)
+    d._Discretizer__u = u
+    opts = dict(use_uniform_steps=uniform, integrator_steps=steps, ivp_max_step=d.ivp_max_step, ivp_solver=d.ivp_solver)
+    funcs = dict(dPhi_gen=d.dPhi_gen, f=F, u_func=d.u_func, B_func=d.B_func, Sigma_func=d.Sigma_func, xi_func=d.xi_func)
+    res = [R.get_matrices(opts, funcs, tf, d._Discretizer__tau, x, k) for k in ks]
+    return (np.stack([r[0] for r in res]), np.stack([r[1] for r in res]), np.stack([r[2] for r in res]),
+            np.column_stack([r[3] for r in res]), np.column_stack([r[4] for r in res]))
+
+
+def pack(prefix, out):
+    names = ["A_k", "B_kp", "B_kn", "Sigma_k", "xi_k"]
+    return {f"{prefix}_{n}": o for n, o in zip(names, out)}
+
+
+def main():
+    sat = R.Satellite(R_INIT, V_INIT, M_INIT)
+    scale = R.SatelliteScale(sat=sat)
+    const = scale.get_normalized_constants()
+    g = {"const": const_vec(const), "x0_dim": sat.get_state_vector(),
+         "scale": np.array([scale._r0, scale._s0, scale._v0, scale._a0, scale._m0, scale._T0, scale._mu0])}
+    T_init = np.array([0.44, 0.7, 1.0])
+
+    # --- D0: ref test_discretizer.py:30-54 (K=2, DIMENSIONAL x with normalized constants, tf=1)
+    x = np.column_stack([sat.get_state_vector()] * 2)
+    u = np.column_stack([T_init] * 2)
+    g.update(d0_x=x, d0_u=u, d0_tf=1.0)
+    g.update(pack("d0_def", disc(const, x, u, 1, False)))
+    g.update(pack("d0_uni", disc(const, x, u, 1, True)))
+
+    # --- D1: ref test_discretizer.py:57-85 (K=3 identical columns, tf=0.1)
+    xn = scale.normalize_state(sat.get_state_vector())
+    x = np.column_stack([xn] * 3)
+    u = np.column_stack([T_init] * 3)
+    g.update(d1_x=x, d1_u=u, d1_tf=0.1)
+    g.update(pack("d1_def", disc(const, x, u, 0.1, False)))
+    g.update(pack("d1_uni", disc(const, x, u, 0.1, True)))
+
+    # --- D2: ref test_discretizer.py:88-117 (constant thrust, tf=1, base_res=100 -> K=100)
+    sim = R.Simulator(sats=[sat], controller=R.ConstantThrustController([sat], T_init), scale=scale,
+                      base_res=100, include_drag=False, include_J2=False)
+    sim.run(tf=1)
+    x = sim.sim_data[sat.id]
+    K = x.shape[1]
+    u = np.tile(T_init.reshape(3, 1), (1, K))
+    out = disc(const, x, u, 1, True)
+    # The test's own u is np.tile(T_init,(3,K)) (:103): shape (3,3K) whose COLUMNS cycle through
+    # [.44]*3,[.7]*3,[1.]*3 -- not the constant thrust the trajectory was flown with.  The reference
+    # accepts it (u_FOH uses u's own column count for its grid, :308-315); keep it as a fixture of the
+    # "u on a different grid than x" behaviour.
+    uq = np.tile(T_init, (3, K))
+    g.update(d2q_u=uq, d2q_ks=np.array([0, 50, 98]))
+    g.update(pack("d2q_uni", disc(const, x, uq, 1, True, ks=[0, 50, 98])))
+    g.update(d2_x=x, d2_u=u, d2_tf=1.0, d2_t=sim.sim_time[sat.id])
+    g.update(pack("d2_uni", out))
+
+    # --- D3: ref test_discretizer.py:120-150 (tangential 0.5, tf=2 -> K=200); also the MPC seed (control.py:178-180)
+    c = R.ConstantTangentialThrustController([sat], 0.5)
+    sim = R.Simulator(sats=[sat], controller=c, scale=scale, base_res=100, include_drag=False, include_J2=False)
+    sim.run(tf=2)
+    x = sim.sim_data[sat.id]
+    t = sim.sim_time[sat.id]
+    u = R.Discretizer.extract_uk(x, t, c)
+    g.update(d3_x=x, d3_u=u, d3_tf=2.0, d3_t=t)
+    g.update(pack("d3_def", disc(const, x, u, 2, False)))
+    g.update(pack("d3_uni", disc(const, x, u, 2, True)))
+    ks = list(range(0, 199, 10))
+    g["d3_j2_ks"] = np.array(ks)
+    g.update(pack("d3_j2_uni", disc(const, x, u, 2, True, J2=True, ks=ks)))
+    g.update(pack("d3_j2_def", disc(const, x, u, 2, False, J2=True, ks=ks)))
+    g["d3_n21_ks"] = np.array(ks)
+    g.update(pack("d3_n21_uni", disc(const, x, u, 2, True, steps=21, ks=ks)))
+
+    # --- D4: BASELINE config 1 (single satellite, K=50): tangential 0.5, tf=0.5, base_res=100
+    sim = R.Simulator(sats=[sat], controller=c, scale=scale, base_res=100, include_drag=False, include_J2=False)
+    sim.run(tf=0.5)
+    x = sim.sim_data[sat.id]
+    t = sim.sim_time[sat.id]
+    u = R.Discretizer.extract_uk(x, t, c)
+    g.update(d4_x=x, d4_u=u, d4_tf=0.5, d4_t=t)
+    g.update(pack("d4_def", disc(const, x, u, 0.5, False)))
+    g.update(pack("d4_uni", disc(const, x, u, 0.5, True)))
+    np.savez(os.path.join(HERE, "discretize.npz"), **g)
+
+    # ------------------------------------------------------------------ propagation
+    p = {"const": const_vec(const), "x0_dim": sat.get_state_vector()}
+    # P0: ref test_simulator.py:17-33 (5-orbit coast, default drag+J2)
+    s = R.Satellite(R_INIT, V_INIT, M_INIT)
+    sim = R.Simulator(sats=[s], scale=scale)
+    sim.run(tf=5)
+    p.update(p0_y=sim.sim_data[s.id], p0_t=sim.sim_time[s.id], p0_tf=5.0)
+    # P1: tangential 0.5, tf=2, no drag / no J2 (test_discretizer.py:120-131)
+    s = R.Satellite(R_INIT, V_INIT, M_INIT)
+    sim = R.Simulator(sats=[s], controller=c, scale=scale, base_res=100, include_drag=False, include_J2=False)
+    sim.run(tf=2)
+    p.update(p1_y=sim.sim_data[s.id], p1_t=sim.sim_time[s.id], p1_tf=2.0, p1_mag=0.5,
+             p1_u=R.Discretizer.extract_uk(sim.sim_data[s.id], sim.sim_time[s.id], c))
+    # P2: constant thrust [0,0,0.1], drag+J2 (test_simulator.py:175-188, shortened to 3 orbits)
+    s = R.Satellite(R_INIT, V_INIT, M_INIT)
+    sim = R.Simulator(sats=[s], controller=R.ConstantThrustController(thrust=np.array([0., 0., 0.1])), scale=scale)
+    sim.run(tf=3)
+    p.update(p2_y=sim.sim_data[s.id], p2_t=sim.sim_time[s.id], p2_tf=3.0, p2_thrust=np.array([0., 0., 0.1]))
+    # P3: three perturbed satellites v0*(1+0.1*rand) (test_simulator.py:36-55), one scale from sat 0
+    rng = np.random.default_rng(20240531)
+    fac = 1 + 0.1 * rng.random(3)
+    sats = [R.Satellite(R_INIT, V_INIT * f, M_INIT) for f in fac]
+    sc3 = R.SatelliteScale(sat=sats[0])
+    sim = R.Simulator(sats=sats, scale=sc3)
+    sim.run(tf=5)
+    p.update(p3_fac=fac, p3_const=const_vec(sc3.get_normalized_constants()),
+             p3_y0_dim=np.stack([q.get_state_vector() for q in sats]),
+             p3_y=np.stack([sim.sim_data[q.id] for q in sats]), p3_t=sim.sim_time[sats[0].id], p3_tf=5.0)
+    # P4: tangential 0.1 with drag+J2 (test_simulator.py:190-203), 2 orbits
+    s = R.Satellite(R_INIT, V_INIT, M_INIT)
+    c01 = R.ConstantTangentialThrustController(tangential_thrust=0.1)
+    sim = R.Simulator(sats=[s], controller=c01, scale=scale)
+    sim.run(tf=2)
+    p.update(p4_y=sim.sim_data[s.id], p4_t=sim.sim_time[s.id], p4_tf=2.0, p4_mag=0.1)
+    # P5: SequenceController (control.py:86-143) -- table shorter than the run (end_tau = 0.75)
+    kk = 30
+    tt = np.linspace(0, 1, kk)
+    u_tab = np.vstack([0.3 * np.cos(2 * np.pi * tt), 0.4 * np.sin(3 * tt) + 0.1, 0.05 * (tt - 0.5)])
+    s = R.Satellite(R_INIT, V_INIT, M_INIT)
+    cs = R.SequenceController(u=u_tab, tf_u=1.5, tf_sim=2.0)
+    sim = R.Simulator(sats=[s], controller=cs, scale=scale, base_res=60, include_drag=False, include_J2=False)
+    sim.run(tf=2)
+    p.update(p5_y=sim.sim_data[s.id], p5_t=sim.sim_time[s.id], p5_tf=2.0, p5_u_tab=u_tab, p5_tf_u=1.5,
+             p5_u=R.Discretizer.extract_uk(sim.sim_data[s.id], sim.sim_time[s.id], cs))
+    # P6: run_segments bookkeeping, two satellites, tangential 0.5, tf=3 in 4 segments (test_simulator.py:149-173)
+    s1 = R.Satellite(R_INIT, V_INIT, M_INIT)
+    s2 = R.Satellite(R_INIT, V_INIT * 1.1, M_INIT)
+    cc = R.ConstantTangentialThrustController(sats=[s1, s2], tangential_thrust=0.5)
+    sim = R.Simulator(sats=[s1, s2], scale=scale, base_res=100, controller=cc)
+    sim.run_segments(tf=3, num_segments=4)
+    p.update(p6_y=np.stack([sim.sim_data[s1.id], sim.sim_data[s2.id]]),
+             p6_t=np.stack([sim.sim_time[s1.id], sim.sim_time[s2.id]]),
+             p6_final_dim=np.stack([s1.get_state_vector(), s2.get_state_vector()]))
+    np.savez(os.path.join(HERE, "propagate.npz"), **p)
+    for f in ("discretize.npz", "propagate.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
