@@ -1,0 +1,185 @@
+/*
+ * mpc_b200.h -- C-ABI of libmpc_b200.so: the B200 (sm_100a) implementation of mpconstellation's
+ * batched SCvx linearize-and-discretize step and nonlinear orbit propagation.
+ *
+ * The reference (rgovindjee/mpconstellation) is pure Python and has no FFI layer; the boundary
+ * it offers is two call signatures, Discretizer.discretize (linearize_discretize.py:334-390)
+ * and Simulator.get_trajectory_ODE / run (simulator.py:29-48,164-189).  Each entry point below
+ * names the reference interface it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MPC_E_* code; mpc_last_error() gives text
+ *   - all arrays are float64, C-contiguous, in the reference's own per-satellite shapes with a
+ *     leading batch axis:  x [N][7][K], u [N][3][K], y [N][7][T]
+ *   - "device API": pointers are device pointers owned by the caller, work is enqueued on the
+ *     caller's stream (a cudaStream_t passed as void*), nothing is allocated, nothing synchronises
+ *   - "host API": pointers are host pointers (pinned memory recommended: mpc_host_alloc);
+ *     an mpc_ctx owns the device workspace, streams and the chunked copy/compute pipeline
+ *   - there is NO CPU fallback anywhere in this library
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+/* rows of the structure-of-arrays discretization output, out[row][interval] */
+#define MPC_OUT_ROWS 105
+#define MPC_ROW_A 0      /* 49 rows: A_k  = Phi(tau_{k+1}), row-major 7x7   linearize_discretize.py:43-44 */
+#define MPC_ROW_BP 49    /* 21 rows: B_kp (B+), row-major 7x3               linearize_discretize.py:72,77 */
+#define MPC_ROW_BN 70    /* 21 rows: B_kn (B-), row-major 7x3               linearize_discretize.py:71,78 */
+#define MPC_ROW_SIGMA 91 /*  7 rows: Sigma_k                                linearize_discretize.py:74,79 */
+#define MPC_ROW_XI 98    /*  7 rows: xi_k                                   linearize_discretize.py:75,80 */
+
+/* return codes */
+#define MPC_SUCCESS 0
+#define MPC_E_INVALID (-1)     /* bad argument */
+#define MPC_E_CUDA (-2)        /* CUDA runtime error (text in mpc_last_error) */
+#define MPC_E_UNSUPPORTED (-3) /* option the reference cannot run either (e.g. drag in the discretizer) */
+#define MPC_E_NOMEM (-4)
+
+/* per-unit status written by the kernels (one int32 per interval / per satellite) */
+#define MPC_ST_OK 0
+#define MPC_ST_MASS 1      /* mass <= 0 met while integrating: simulator.py:135-136 raises here */
+#define MPC_ST_NONFINITE 2 /* a non-finite result */
+
+/* integrators of the discretization kernel */
+#define MPC_INTEG_RK4_UNIFORM 0 /* fixed-step RK4, n_sub steps, trapezoid on the n_sub+1 step nodes:
+                                   the reference's use_uniform_steps=True, integrator_steps=n_sub+1
+                                   node set (linearize_discretize.py:27-28,47-48) */
+
+/* Normalized constants: the reference's Constants bag (constants.py:11-20) as produced by
+ * SatelliteScale.get_normalized_constants (satellite_scale.py:36-44), plus the two module-level
+ * values the dynamics read directly (C_D constants.py:7; density simulator.py:112). */
+typedef struct mpc_params {
+    double mu, r_e, j2, g0, isp;
+    double s_area, r0, rho;
+    double c_d, rho_atm;
+    int32_t include_j2;   /* Discretizer(include_J2=...) / Simulator(include_J2=...) */
+    int32_t include_drag; /* Simulator(include_drag=...); the discretizer rejects it like the reference */
+} mpc_params;
+
+/* Controller laws the propagator can evaluate on the device (control.py). */
+#define MPC_CTRL_ZERO 0       /* Controller.get_u_func                      control.py:20-29   */
+#define MPC_CTRL_CONSTANT 1   /* ConstantThrustController                   control.py:47-53   */
+#define MPC_CTRL_TANGENTIAL 2 /* ConstantTangentialThrustController         control.py:66-84   */
+#define MPC_CTRL_SEQUENCE 3   /* SequenceController (FOH table, end_tau)    control.py:104-143 */
+
+typedef struct mpc_controller {
+    int32_t kind;          /* MPC_CTRL_* */
+    int32_t table_len;     /* Ku: columns of the sequence table (>= 2 for MPC_CTRL_SEQUENCE) */
+    int32_t table_per_sat; /* 1: table is [N][3][Ku]; 0: one [3][Ku] table shared by all satellites */
+    int32_t reserved;
+    double thrust[3];      /* CONSTANT: the vector; TANGENTIAL: thrust[0] = magnitude */
+    double end_tau;        /* SEQUENCE: tf_u / tf_sim (control.py:101) */
+    const double *table;   /* SEQUENCE: device pointer (device API) or host pointer (host API) */
+} mpc_controller;
+
+/* ---------------------------------------------------------------- library */
+int mpc_version(void);
+const char *mpc_last_error(void);
+int mpc_device_count(void);
+/* name / SM count / clock of a device; returns MPC_E_CUDA when there is no usable GPU */
+int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------- device API */
+
+/*
+ * Replaces Discretizer.discretize (linearize_discretize.py:334-390) + get_matrices (:8-82) for a
+ * whole batch: every (satellite, interval) pair is one independent unit.
+ *
+ *   x   [n_sats][7][K]   reference trajectories (scaled states)            discretize() arg `x`
+ *   u   [n_sats][3][K]   reference inputs on the same K nodes              discretize() arg `u`
+ *   tf  [n_sats]         reference final time per satellite                discretize() arg `tf`
+ *   n_sub                RK4 steps per interval = integrator_steps - 1     Discretizer.integrator_steps
+ *   out                  SoA, out[row * out_pitch + out_offset + s*(K-1) + k], row in [0,105)
+ *   status [n_sats*(K-1)] MPC_ST_* per interval (may be NULL)
+ *
+ * out_pitch >= out_offset + n_sats*(K-1).  Passing a pitch/offset larger than the local batch lets
+ * several ranks write disjoint column ranges of one gathered buffer.
+ */
+int mpc_discretize_batch(const double *x, const double *u, const double *tf, const mpc_params *p, int n_sats,
+                         int K, int n_sub, double *out, int64_t out_pitch, int64_t out_offset, int32_t *status,
+                         void *stream);
+
+/*
+ * Same computation; every result is stored to n_dst destination buffers (for example the local
+ * buffer plus NVLink peer-mapped buffers of the other ranks: the all-gather of the discretized
+ * matrices fused into the producing kernel).  dst is a HOST array of n_dst device pointers
+ * (n_dst <= MPC_MAX_DST).
+ */
+#define MPC_MAX_DST 8
+int mpc_discretize_batch_multi(const double *x, const double *u, const double *tf, const mpc_params *p,
+                               int n_sats, int K, int n_sub, double *const *dst, int n_dst, int64_t out_pitch,
+                               int64_t out_offset, int32_t *status, void *stream);
+
+/*
+ * Replaces Simulator.get_trajectory_ODE (simulator.py:164-189) for a batch of satellites, and
+ * Discretizer.extract_uk (linearize_discretize.py:393-411) on the sampled trajectory.
+ *
+ *   y0  [n_sats][7]      normalized initial states (scale.normalize_state(sat.get_state_vector()))
+ *   tf  [n_sats]
+ *   T                    eval_points = int(base_res * tf)    (simulator.py:38,185)
+ *   n_sub                RK4 steps between consecutive samples; the reference's max_step=0.001
+ *                        (simulator.py:186) corresponds to n_sub = ceil(1000/(T-1))
+ *   y   [n_sats][7][T]   sol.y per satellite; sample times are linspace(0,1,T)
+ *   u_out [n_sats][3][T] controller output at every sample (may be NULL)
+ *   status [n_sats]      MPC_ST_* (may be NULL)
+ */
+int mpc_propagate_batch(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
+                        int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------- host API */
+typedef struct mpc_ctx mpc_ctx;
+
+int mpc_ctx_create(int device, mpc_ctx **ctx);
+int mpc_ctx_destroy(mpc_ctx *ctx);
+
+/* page-locked host memory (cudaHostAlloc); NULL on failure */
+void *mpc_host_alloc(size_t bytes);
+void mpc_host_free(void *p);
+
+/*
+ * Host-buffer form of mpc_discretize_batch: copies x/u/tf to the device, runs the kernel and
+ * copies the SoA result back, pipelined in satellite chunks over two streams.
+ * out_host is [105][n_sats*(K-1)] (pitch = n_sats*(K-1)); status_host [n_sats*(K-1)] or NULL.
+ */
+int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf,
+                              const mpc_params *p, int n_sats, int K, int n_sub, double *out_host,
+                              int32_t *status_host);
+
+/* Host-buffer form of mpc_propagate_batch (ctrl->table is a host pointer here). */
+int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p,
+                             const mpc_controller *ctrl, int n_sats, int T, int n_sub, double *y_host,
+                             double *u_host, int32_t *status_host);
+
+/*
+ * SCP inner step on host buffers, fused on the device (control.py:180-188 pattern): propagate the
+ * batch, evaluate the controller on the samples (extract_uk), discretize about the result.  The
+ * reference trajectory never leaves HBM between the two kernels.  K = T.
+ * Any of y_host / u_host may be NULL when the caller only wants the matrices.
+ */
+int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                  const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                  int n_sub_prop, int n_sub_disc, double *y_host, double *u_host,
+                                  double *out_host, int32_t *status_host);
+
+/* ---------------------------------------------------------------- measurement helpers */
+
+/* FP64 FMA-chain microbenchmark: measured DFMA peak of `device` in TFLOP/s (2 flop per FMA). */
+int mpc_fp64_peak_probe(int device, int repeats, double *tflops, double *ms);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches evidence). */
+int64_t mpc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_B200_H */

@@ -1,0 +1,157 @@
+"""ctypes binding of csrc/libmpc_b200.so (C-ABI: include/mpc_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable, the
+functions here raise.  `build()` compiles the library in-tree with nvcc for sm_100a.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libmpc_b200.so")
+SOURCES = ["mpc_b200.cu"]
+HEADERS = ["discretize_kernel.cuh", "propagate_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+MPC_OUT_ROWS = 105
+ROW_A, ROW_BP, ROW_BN, ROW_SIGMA, ROW_XI = 0, 49, 70, 91, 98
+CTRL_ZERO, CTRL_CONSTANT, CTRL_TANGENTIAL, CTRL_SEQUENCE = 0, 1, 2, 3
+ST_OK, ST_MASS, ST_NONFINITE = 0, 1, 2
+E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4
+
+
+class MpcParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in
+                ("mu", "r_e", "j2", "g0", "isp", "s_area", "r0", "rho", "c_d", "rho_atm")] + \
+               [("include_j2", ctypes.c_int32), ("include_drag", ctypes.c_int32)]
+
+
+class MpcController(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("table_len", ctypes.c_int32), ("table_per_sat", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("thrust", ctypes.c_double * 3), ("end_tau", ctypes.c_double),
+                ("table", ctypes.c_void_p)]
+
+
+class MpcError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"libmpc_b200 error {code}: {text}")
+        self.code = code
+
+
+def needs_build():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into csrc/libmpc_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return SO_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", SO_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return SO_PATH
+
+
+_lib = None
+
+_DP = ctypes.c_void_p  # all array pointers are passed as raw addresses
+
+
+def lib():
+    """Loads the shared library (once).  Raises ImportError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = ctypes.CDLL(SO_PATH)
+    i, i64, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+    pp, pc = ctypes.POINTER(MpcParams), ctypes.POINTER(MpcController)
+    L.mpc_version.restype = i
+    L.mpc_last_error.restype = ctypes.c_char_p
+    L.mpc_device_count.restype = i
+    L.mpc_device_info.argtypes = [i, ctypes.c_char_p, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
+    L.mpc_launch_count.restype = i64
+    L.mpc_discretize_batch.argtypes = [_DP, _DP, _DP, pp, i, i, i, _DP, i64, i64, _DP, vp]
+    L.mpc_discretize_batch_multi.argtypes = [_DP, _DP, _DP, pp, i, i, i, ctypes.POINTER(ctypes.c_void_p), i, i64, i64, _DP, vp]
+    L.mpc_propagate_batch.argtypes = [_DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP, vp]
+    L.mpc_ctx_create.argtypes = [i, ctypes.POINTER(vp)]
+    L.mpc_ctx_destroy.argtypes = [vp]
+    L.mpc_host_alloc.argtypes = [ctypes.c_size_t]
+    L.mpc_host_alloc.restype = vp
+    L.mpc_host_free.argtypes = [vp]
+    L.mpc_host_free.restype = None
+    L.mpc_discretize_batch_host.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, _DP, _DP]
+    L.mpc_propagate_batch_host.argtypes = [vp, _DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP]
+    L.mpc_propagate_discretize_host.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, _DP]
+    L.mpc_fp64_peak_probe.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    for name in ("mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
+                 "mpc_ctx_create", "mpc_ctx_destroy", "mpc_discretize_batch_host", "mpc_propagate_batch_host",
+                 "mpc_propagate_discretize_host", "mpc_fp64_peak_probe"):
+        getattr(L, name).restype = i
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "mpc_version", "mpc_last_error", "mpc_device_count", "mpc_device_info", "mpc_launch_count",
+    "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
+    "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
+    "mpc_discretize_batch_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host",
+    "mpc_fp64_peak_probe",
+]
+
+
+def check(rc):
+    if rc != 0:
+        raise MpcError(rc, lib().mpc_last_error().decode("utf-8", "replace"))
+
+
+def require_gpu():
+    if lib().mpc_device_count() < 1:
+        raise RuntimeError("mpconstellation_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
+
+
+def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.983e-13):
+    """Pack a reference-style Constants bag (constants.py:11-20) into the C struct."""
+    g = lambda n, d=0.0: float(getattr(const, n, d))
+    return MpcParams(g("MU"), g("R_E"), g("J2"), g("G0"), g("ISP"), g("S"), g("R0", 1.0), g("RHO", 1.0),
+                     float(c_d), float(rho_atm), int(bool(include_J2)), int(bool(include_drag)))
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over page-locked host memory (cudaHostAlloc through the C-ABI)."""
+    dtype = np.dtype(dtype)
+    shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    L = lib()
+    ptr = L.mpc_host_alloc(max(nbytes, 1))
+    if not ptr:
+        raise MemoryError(L.mpc_last_error().decode())
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    weakref.finalize(buf, L.mpc_host_free, ptr)
+    return arr
+
+
+def addr(a):
+    """Raw address of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data

@@ -1,0 +1,281 @@
+"""Batched entry points over the C-ABI: every (satellite, interval) / satellite is one GPU work unit.
+
+Host arrays (numpy) go through the library's host API (chunked copy/compute pipeline); torch CUDA
+tensors go through the device API on torch's current stream.  Shapes follow the reference with a
+leading batch axis: x [N,7,K], u [N,3,K], tf [N] -> SoA [105, N*(K-1)].
+"""
+import ctypes
+import math
+import threading
+
+import numpy as np
+
+from . import _lib
+from .control import ControllerSpec, spec_from
+
+_ctx_lock = threading.Lock()
+_ctxs = {}
+
+
+def _ctx(device=0):
+    with _ctx_lock:
+        if device not in _ctxs:
+            _lib.require_gpu()
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().mpc_ctx_create(int(device), ctypes.byref(h)))
+            _ctxs[device] = h
+        return _ctxs[device]
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+def _tf_vec(tf, n):
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (n,)))
+
+
+class DiscretizedBatch:
+    """SoA result of a batched discretization plus reference-shaped views.
+
+    soa: [105, N*(K-1)] float64 (rows: A 49 | B_kp 21 | B_kn 21 | Sigma 7 | xi 7), status: [N, K-1] int32.
+    sat(s) returns (A_k, B_kp, B_kn, Sigma_k, xi_k) with the shapes and order of
+    Discretizer.discretize (linearize_discretize.py:390); they are views, no copy is made.
+    """
+
+    def __init__(self, soa, status, n_sats, K):
+        self.soa, self.status, self.n_sats, self.K = soa, status, n_sats, K
+
+    def _rows(self, r0, nrows, s):
+        n = self.K - 1
+        return self.soa[r0:r0 + nrows, s * n:(s + 1) * n]
+
+    def sat(self, s):
+        n = self.K - 1
+        A = self._rows(_lib.ROW_A, 49, s).T.reshape(n, 7, 7)
+        Bp = self._rows(_lib.ROW_BP, 21, s).T.reshape(n, 7, 3)
+        Bn = self._rows(_lib.ROW_BN, 21, s).T.reshape(n, 7, 3)
+        return A, Bp, Bn, self._rows(_lib.ROW_SIGMA, 7, s), self._rows(_lib.ROW_XI, 7, s)
+
+    def stacked(self):
+        """(A[N,K-1,7,7], B_kp[N,K-1,7,3], B_kn[N,K-1,7,3], Sigma[N,7,K-1], xi[N,7,K-1]) as views."""
+        N, n = self.n_sats, self.K - 1
+        v = self.soa.reshape(_lib.MPC_OUT_ROWS, N, n)
+        A = v[0:49].transpose(1, 2, 0).reshape(N, n, 7, 7)
+        Bp = v[49:70].transpose(1, 2, 0).reshape(N, n, 7, 3)
+        Bn = v[70:91].transpose(1, 2, 0).reshape(N, n, 7, 3)
+        return A, Bp, Bn, v[91:98].transpose(1, 0, 2), v[98:105].transpose(1, 0, 2)
+
+    def raise_on_error(self):
+        raise_on_status(self.status)
+
+
+def raise_on_status(status):
+    st = np.asarray(status)
+    if st.size and st.max() != 0:
+        idx = np.argwhere(st != 0)[0]
+        code = int(st[tuple(idx)])
+        if code == _lib.ST_MASS:
+            # same exception type / text as simulator.py:135-136
+            raise Exception(f"ERROR: INVALID SATELLITE MASS: non-positive mass at unit {tuple(int(i) for i in idx)}")
+        raise FloatingPointError(f"non-finite result at unit {tuple(int(i) for i in idx)}")
+
+
+def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_sub=100, out=None, status=None,
+                     device=0, check=True):
+    """Discretize every interval of every satellite in one launch sequence (host arrays).
+
+    x [N,7,K], u [N,3,K], tf scalar or [N]; `out` may be a preallocated (ideally pinned) [105, N*(K-1)]
+    array.  Returns a DiscretizedBatch.  ref: linearize_discretize.py:334-390 / :8-82.
+    """
+    ctx = _ctx(device)
+    x = _f64(x)
+    if x.ndim != 3 or x.shape[1] != 7:
+        raise ValueError(f"x must be [N,7,K], got {x.shape}")
+    N, _, K = x.shape
+    u = _f64(u, (N, 3, K))
+    tfv = _tf_vec(tf, N)
+    n_int = N * (K - 1)
+    if out is None:
+        out = _lib.pinned_empty((_lib.MPC_OUT_ROWS, n_int))
+    elif out.shape != (_lib.MPC_OUT_ROWS, n_int) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("out must be C-contiguous float64 [105, N*(K-1)]")
+    if status is None:
+        status = np.zeros(n_int, dtype=np.int32)
+    p = _lib.make_params(const, include_J2, include_drag)
+    _lib.check(_lib.lib().mpc_discretize_batch_host(ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv),
+                                                    ctypes.byref(p), N, K, int(n_sub), _lib.addr(out),
+                                                    _lib.addr(status)))
+    res = DiscretizedBatch(out, status.reshape(N, K - 1), N, K)
+    if check:
+        res.raise_on_error()
+    return res
+
+
+def _ctrl_struct(spec, n_sats, table_addr=None):
+    c = _lib.MpcController()
+    c.kind = spec.kind
+    c.thrust[0], c.thrust[1], c.thrust[2] = [float(t) for t in spec.thrust]
+    c.end_tau = float(spec.end_tau)
+    keep = None
+    if spec.kind == _lib.CTRL_SEQUENCE:
+        tab = spec.table
+        if tab.ndim == 3 and tab.shape[0] != n_sats:
+            raise ValueError("per-satellite sequence table must be [N,3,Ku]")
+        c.table_len = tab.shape[-1]
+        c.table_per_sat = int(tab.ndim == 3)
+        keep = tab
+        c.table = table_addr if table_addr is not None else tab.ctypes.data
+    return c, keep
+
+
+def default_n_sub(T, max_step=0.001):
+    """RK4 steps between samples so that the step in tau is <= max_step (simulator.py:186)."""
+    if T < 2:
+        return 1
+    return max(1, int(math.ceil(1.0 / (max_step * (T - 1)) - 1e-9)))
+
+
+def propagate_batch(y0, tf, controller, const, include_drag=True, include_J2=True, T=100, n_sub=None,
+                    want_u=True, device=0, check=True, y_out=None, u_out=None):
+    """Propagate N satellites over tau in [0,1] and sample at linspace(0,1,T) (host arrays).
+
+    y0 [N,7] normalized states; returns (y [N,7,T], u [N,3,T] or None, t [T], status [N]).
+    ref: simulator.py:164-189 (+ extract_uk, linearize_discretize.py:393-411).
+    """
+    ctx = _ctx(device)
+    y0 = _f64(y0)
+    if y0.ndim != 2 or y0.shape[1] != 7:
+        raise ValueError(f"y0 must be [N,7], got {y0.shape}")
+    N = y0.shape[0]
+    T = int(T)
+    spec = spec_from(controller)
+    tfv = _tf_vec(tf, N)
+    if n_sub is None:
+        n_sub = default_n_sub(T)
+    y = y_out if y_out is not None else _lib.pinned_empty((N, 7, T))
+    uo = (u_out if u_out is not None else _lib.pinned_empty((N, 3, T))) if want_u else None
+    status = np.zeros(N, dtype=np.int32)
+    t = np.linspace(0, 1, T)
+    if N == 0 or T == 0:
+        return y, uo, t, status
+    p = _lib.make_params(const, include_J2, include_drag)
+    c, _keep = _ctrl_struct(spec, N)
+    _lib.check(_lib.lib().mpc_propagate_batch_host(ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(p),
+                                                   ctypes.byref(c), N, T, int(n_sub), _lib.addr(y),
+                                                   _lib.addr(uo), _lib.addr(status)))
+    if check:
+        raise_on_status(status)
+    return y, uo, t, status
+
+
+def propagate_discretize(y0, tf, controller, const, T, prop_drag=False, prop_J2=False, disc_J2=False,
+                         n_sub_prop=None, n_sub_disc=100, out=None, y_out=None, u_out=None, device=0, check=True):
+    """One SCP linearization pass on the device: propagate -> extract_uk -> discretize, the reference
+    trajectory staying in HBM between the kernels (control.py:180-188 pattern).  K = T.
+    Returns (DiscretizedBatch, y [N,7,T], u [N,3,T])."""
+    ctx = _ctx(device)
+    y0 = _f64(y0)
+    N = y0.shape[0]
+    T = int(T)
+    spec = spec_from(controller)
+    tfv = _tf_vec(tf, N)
+    n_int = N * (T - 1)
+    if n_sub_prop is None:
+        n_sub_prop = default_n_sub(T)
+    if out is None:
+        out = _lib.pinned_empty((_lib.MPC_OUT_ROWS, n_int))
+    y = y_out if y_out is not None else _lib.pinned_empty((N, 7, T))
+    uo = u_out if u_out is not None else _lib.pinned_empty((N, 3, T))
+    status = np.zeros(n_int, dtype=np.int32)
+    pp = _lib.make_params(const, prop_J2, prop_drag)
+    pd = _lib.make_params(const, disc_J2, False)
+    c, _keep = _ctrl_struct(spec, N)
+    _lib.check(_lib.lib().mpc_propagate_discretize_host(ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(pp),
+                                                        ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop),
+                                                        int(n_sub_disc), _lib.addr(y), _lib.addr(uo), _lib.addr(out),
+                                                        _lib.addr(status)))
+    res = DiscretizedBatch(out, status.reshape(N, T - 1), N, T)
+    if check:
+        res.raise_on_error()
+    return res, y, uo
+
+
+# ------------------------------------------------------------------ device-tensor API (torch CUDA tensors)
+
+def _torch():
+    import torch
+    return torch
+
+
+def discretize_batch_device(x, u, tf, const, include_J2=False, n_sub=100, out=None, out_pitch=None, out_offset=0,
+                            status=None, extra_dst=None):
+    """Device form: x [N,7,K], u [N,3,K], tf [N] are float64 CUDA tensors; work is enqueued on torch's
+    current stream, nothing synchronises.  `out` is [105, pitch]; `extra_dst` is an optional list of
+    further [105, pitch] buffers (e.g. peer-mapped) every result is also stored to (total 1,2,4 or 8)."""
+    torch = _torch()
+    N, _, K = x.shape
+    n_int = N * (K - 1)
+    assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+    assert u.shape == (N, 3, K) and u.is_contiguous() and tf.shape == (N,)
+    if out is None:
+        out = torch.empty((_lib.MPC_OUT_ROWS, n_int), dtype=torch.float64, device=x.device)
+    pitch = out.shape[1] if out_pitch is None else int(out_pitch)
+    if status is None:
+        status = torch.empty(n_int, dtype=torch.int32, device=x.device)
+    p = _lib.make_params(const, include_J2, False)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    L = _lib.lib()
+    if extra_dst:
+        ptrs = [out.data_ptr()] + [int(d if isinstance(d, int) else d.data_ptr()) for d in extra_dst]
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        _lib.check(L.mpc_discretize_batch_multi(x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p), N, K,
+                                                int(n_sub), arr, len(ptrs), pitch, int(out_offset),
+                                                status.data_ptr(), stream))
+    else:
+        _lib.check(L.mpc_discretize_batch(x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p), N, K,
+                                          int(n_sub), out.data_ptr(), pitch, int(out_offset), status.data_ptr(),
+                                          stream))
+    return out, status
+
+
+def propagate_batch_device(y0, tf, controller, const, include_drag=True, include_J2=True, T=100, n_sub=None,
+                           y=None, u_out=None, status=None):
+    """Device form of propagate_batch: y0 [N,7], tf [N] float64 CUDA tensors -> y [N,7,T], u [N,3,T], status [N]."""
+    torch = _torch()
+    N = y0.shape[0]
+    spec = spec_from(controller)
+    if n_sub is None:
+        n_sub = default_n_sub(T)
+    if y is None:
+        y = torch.empty((N, 7, T), dtype=torch.float64, device=y0.device)
+    if u_out is None:
+        u_out = torch.empty((N, 3, T), dtype=torch.float64, device=y0.device)
+    if status is None:
+        status = torch.empty(N, dtype=torch.int32, device=y0.device)
+    tab_dev = None
+    if spec.kind == _lib.CTRL_SEQUENCE:
+        tab_dev = torch.as_tensor(spec.table, dtype=torch.float64).to(y0.device).contiguous()
+    c, _keep = _ctrl_struct(spec, N, table_addr=tab_dev.data_ptr() if tab_dev is not None else None)
+    p = _lib.make_params(const, include_J2, include_drag)
+    stream = torch.cuda.current_stream(y0.device).cuda_stream
+    _lib.check(_lib.lib().mpc_propagate_batch(y0.data_ptr(), tf.data_ptr(), ctypes.byref(p), ctypes.byref(c), N,
+                                              int(T), int(n_sub), y.data_ptr(), u_out.data_ptr(),
+                                              status.data_ptr(), stream))
+    if tab_dev is not None:
+        tab_dev.record_stream(torch.cuda.current_stream(y0.device))
+    return y, u_out, status
+
+
+def fp64_peak_tflops(device=0, repeats=5):
+    _lib.require_gpu()
+    tf_, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.lib().mpc_fp64_peak_probe(int(device), int(repeats), ctypes.byref(tf_), ctypes.byref(ms)))
+    return tf_.value, ms.value
+
+
+def launch_count():
+    return int(_lib.lib().mpc_launch_count())

@@ -1,0 +1,518 @@
+// mpc_b200.cu -- C-ABI (include/mpc_b200.h) over the sm_100a kernels.  No CPU fallback: every entry
+// point either launches CUDA work or returns an error.
+#include "../../include/mpc_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "discretize_kernel.cuh"
+#include "propagate_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess) return fail(MPC_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                              \
+    } while (0)
+
+constexpr int kDiscBlock = 128;
+constexpr int kPropBlock = 32;
+
+mpc::DiscParams disc_params(const mpc_params *p)
+{
+    mpc::DiscParams d;
+    d.mu = p->mu;
+    d.kj2 = 1.5 * p->j2 * p->mu * p->r_e * p->r_e;
+    d.inv_ve = 1.0 / (p->g0 * p->isp);
+    return d;
+}
+
+mpc::PropParams prop_params(const mpc_params *p)
+{
+    mpc::PropParams d;
+    d.mu = p->mu;
+    d.kj2 = 1.5 * p->j2 * p->mu * p->r_e * p->r_e;
+    d.inv_ve = 1.0 / (p->g0 * p->isp);
+    d.drag_k = p->include_drag ? 0.5 * p->c_d * p->s_area * (p->rho_atm / p->rho) : 0.0;
+    d.include_j2 = p->include_j2;
+    d.include_drag = p->include_drag;
+    return d;
+}
+
+template <bool J2, int NDST>
+int launch_disc_n(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                  int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                  cudaStream_t st)
+{
+    auto kern = mpc::discretize_kernel<J2, kDiscBlock, NDST>;
+    const size_t smem = (size_t)mpc::kAccSlots * kDiscBlock * sizeof(double);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_dev = dev;
+    }
+    const long long n_int = (long long)n_sats * (K - 1);
+    const unsigned grid = (unsigned)((n_int + kDiscBlock - 1) / kDiscBlock);
+    kern<<<grid, kDiscBlock, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
+template <bool J2>
+int launch_disc(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                int n_sub, const mpc::DstTab &dst, int n_dst, long long pitch, long long offset, int32_t *status,
+                cudaStream_t st)
+{
+    switch (n_dst) {
+        case 1: return launch_disc_n<J2, 1>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, st);
+        case 2: return launch_disc_n<J2, 2>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, st);
+        case 4: return launch_disc_n<J2, 4>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, st);
+        case 8: return launch_disc_n<J2, 8>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, st);
+        default: return fail(MPC_E_INVALID, "n_dst must be 1, 2, 4 or 8 (got %d)", n_dst);
+    }
+}
+
+int check_disc_args(const void *x, const void *u, const void *tf, const mpc_params *p, int n_sats, int K, int n_sub)
+{
+    if (!x || !u || !tf || !p) return fail(MPC_E_INVALID, "null pointer argument");
+    if (n_sats < 0 || K < 2 || n_sub < 1)
+        return fail(MPC_E_INVALID, "need n_sats >= 0, K >= 2, n_sub >= 1 (got %d, %d, %d)", n_sats, K, n_sub);
+    if (p->include_drag)
+        // the reference's drag linearisation needs const.CD and a rho_func it never provides
+        // (linearize_discretize.py:162-169): it raises; so do we
+        return fail(MPC_E_UNSUPPORTED, "include_drag is not supported by the discretizer (the reference raises too)");
+    return MPC_SUCCESS;
+}
+
+int disc_device(const double *x, const double *u, const double *tf, const mpc_params *p, int n_sats, int K,
+                int n_sub, double *const *dst, int n_dst, int64_t pitch, int64_t offset, int32_t *status,
+                cudaStream_t st)
+{
+    int rc = check_disc_args(x, u, tf, p, n_sats, K, n_sub);
+    if (rc) return rc;
+    if (!dst || n_dst < 1 || n_dst > MPC_MAX_DST) return fail(MPC_E_INVALID, "bad destination list");
+    const long long n_int = (long long)n_sats * (K - 1);
+    if (pitch < offset + n_int || offset < 0) return fail(MPC_E_INVALID, "out_pitch/out_offset do not hold the batch");
+    if (n_int == 0) return MPC_SUCCESS;
+    mpc::DstTab tab;
+    for (int d = 0; d < mpc::kMaxDst; ++d) tab.p[d] = (d < n_dst) ? dst[d] : nullptr;
+    for (int d = 0; d < n_dst; ++d)
+        if (!tab.p[d]) return fail(MPC_E_INVALID, "null destination %d", d);
+    const mpc::DiscParams P = disc_params(p);
+    return p->include_j2 ? launch_disc<true>(x, u, tf, P, n_sats, K, n_sub, tab, n_dst, pitch, offset, status, st)
+                         : launch_disc<false>(x, u, tf, P, n_sats, K, n_sub, tab, n_dst, pitch, offset, status, st);
+}
+
+int check_ctrl(const mpc_controller *c)
+{
+    if (!c) return fail(MPC_E_INVALID, "null controller");
+    if (c->kind < MPC_CTRL_ZERO || c->kind > MPC_CTRL_SEQUENCE) return fail(MPC_E_UNSUPPORTED, "unknown controller kind %d", c->kind);
+    if (c->kind == MPC_CTRL_SEQUENCE) {
+        if (!c->table || c->table_len < 2) return fail(MPC_E_INVALID, "sequence controller needs a table with >= 2 columns");
+        if (!(c->end_tau > 0.0)) return fail(MPC_E_INVALID, "sequence controller needs end_tau > 0");
+    }
+    return MPC_SUCCESS;
+}
+
+int prop_device(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *c,
+                const double *table_dev, int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status,
+                cudaStream_t st)
+{
+    if (!y0 || !tf || !p || !y) return fail(MPC_E_INVALID, "null pointer argument");
+    if (n_sats < 0 || T < 0 || n_sub < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 0, n_sub >= 1");
+    int rc = check_ctrl(c);
+    if (rc) return rc;
+    if (n_sats == 0 || T == 0) return MPC_SUCCESS;
+    mpc::CtrlParams C;
+    C.kind = c->kind;
+    C.table_len = c->table_len;
+    C.table_per_sat = c->table_per_sat;
+    C.pad = 0;
+    C.t0 = c->thrust[0];
+    C.t1 = c->thrust[1];
+    C.t2 = c->thrust[2];
+    C.end_tau = c->end_tau;
+    C.table = (c->kind == MPC_CTRL_SEQUENCE) ? table_dev : nullptr;
+    const unsigned grid = (unsigned)((n_sats + kPropBlock - 1) / kPropBlock);
+    mpc::propagate_kernel<kPropBlock><<<grid, kPropBlock, 0, st>>>(y0, tf, prop_params(p), C, n_sats, T, n_sub, y,
+                                                                  u_out, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct mpc_ctx {
+    int device = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    std::vector<cudaEvent_t> ev;  // one per chunk slot
+    // grow-only device workspace
+    double *d_x = nullptr, *d_u = nullptr, *d_tf = nullptr, *d_out = nullptr, *d_y0 = nullptr, *d_tab = nullptr;
+    int32_t *d_status = nullptr, *d_status2 = nullptr;
+    size_t cap_x = 0, cap_u = 0, cap_tf = 0, cap_out = 0, cap_y0 = 0, cap_tab = 0, cap_status = 0, cap_status2 = 0;
+};
+
+namespace {
+
+template <typename T>
+int ensure(T *&ptr, size_t &cap, size_t count)
+{
+    if (count <= cap) return MPC_SUCCESS;
+    if (ptr) CUDA_TRY(cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void **)&ptr, count * sizeof(T));
+    if (e != cudaSuccess) return fail(MPC_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    cap = count;
+    return MPC_SUCCESS;
+}
+
+int ensure_events(mpc_ctx *ctx, size_t n)
+{
+    while (ctx->ev.size() < n) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev.push_back(e);
+    }
+    return MPC_SUCCESS;
+}
+
+// satellites per chunk of the host pipeline: about 8 chunks, never smaller than ~64k intervals
+int chunk_sats(int n_sats, int K)
+{
+    const long long per_sat = std::max(1, K - 1);
+    long long by_count = (n_sats + 7) / 8;
+    long long by_size = (65536 + per_sat - 1) / per_sat;
+    long long c = std::max(by_count, by_size);
+    return (int)std::min<long long>(std::max<long long>(c, 1), std::max(n_sats, 1));
+}
+
+// D2H of the columns [c0, c0+nc) of the SoA result (105 rows), host pitch = n_int
+int copy_out_chunk(double *out_host, const double *d_out, long long n_int, long long c0, long long nc, cudaStream_t st)
+{
+    CUDA_TRY(cudaMemcpy2DAsync(out_host + c0, (size_t)n_int * sizeof(double), d_out + c0, (size_t)n_int * sizeof(double),
+                               (size_t)nc * sizeof(double), MPC_OUT_ROWS, cudaMemcpyDeviceToHost, st));
+    return MPC_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpc_version(void) { return MPC_B200_VERSION; }
+
+const char *mpc_last_error(void) { return g_err; }
+
+int mpc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor)
+{
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return MPC_SUCCESS;
+}
+
+int64_t mpc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int mpc_discretize_batch(const double *x, const double *u, const double *tf, const mpc_params *p, int n_sats,
+                         int K, int n_sub, double *out, int64_t out_pitch, int64_t out_offset, int32_t *status,
+                         void *stream)
+{
+    double *dst[1] = {out};
+    return disc_device(x, u, tf, p, n_sats, K, n_sub, dst, 1, out_pitch, out_offset, status, (cudaStream_t)stream);
+}
+
+int mpc_discretize_batch_multi(const double *x, const double *u, const double *tf, const mpc_params *p,
+                               int n_sats, int K, int n_sub, double *const *dst, int n_dst, int64_t out_pitch,
+                               int64_t out_offset, int32_t *status, void *stream)
+{
+    return disc_device(x, u, tf, p, n_sats, K, n_sub, dst, n_dst, out_pitch, out_offset, status,
+                       (cudaStream_t)stream);
+}
+
+int mpc_propagate_batch(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
+                        int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status, void *stream)
+{
+    return prop_device(y0, tf, p, ctrl, ctrl ? ctrl->table : nullptr, n_sats, T, n_sub, y, u_out, status,
+                       (cudaStream_t)stream);
+}
+
+int mpc_ctx_create(int device, mpc_ctx **out)
+{
+    if (!out) return fail(MPC_E_INVALID, "null ctx pointer");
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(MPC_E_INVALID, "device %d out of range (%d visible)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    mpc_ctx *c = new mpc_ctx();
+    c->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    *out = c;
+    return MPC_SUCCESS;
+}
+
+int mpc_ctx_destroy(mpc_ctx *c)
+{
+    if (!c) return MPC_SUCCESS;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    cudaFree(c->d_x);
+    cudaFree(c->d_u);
+    cudaFree(c->d_tf);
+    cudaFree(c->d_out);
+    cudaFree(c->d_y0);
+    cudaFree(c->d_tab);
+    cudaFree(c->d_status);
+    cudaFree(c->d_status2);
+    delete c;
+    return MPC_SUCCESS;
+}
+
+void *mpc_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(MPC_E_NOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void mpc_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf,
+                              const mpc_params *p, int n_sats, int K, int n_sub, double *out_host,
+                              int32_t *status_host)
+{
+    if (!ctx || !out_host) return fail(MPC_E_INVALID, "null ctx/out");
+    int rc = check_disc_args(x, u, tf, p, n_sats, K, n_sub);
+    if (rc) return rc;
+    const long long n_int = (long long)n_sats * (K - 1);
+    if (n_int == 0) return MPC_SUCCESS;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if ((rc = ensure(ctx->d_x, ctx->cap_x, (size_t)n_sats * 7 * K))) return rc;
+    if ((rc = ensure(ctx->d_u, ctx->cap_u, (size_t)n_sats * 3 * K))) return rc;
+    if ((rc = ensure(ctx->d_tf, ctx->cap_tf, (size_t)n_sats))) return rc;
+    if ((rc = ensure(ctx->d_out, ctx->cap_out, (size_t)n_int * MPC_OUT_ROWS))) return rc;
+    if ((rc = ensure(ctx->d_status, ctx->cap_status, (size_t)n_int))) return rc;
+    const int cs = chunk_sats(n_sats, K);
+    const int n_chunks = (n_sats + cs - 1) / cs;
+    if ((rc = ensure_events(ctx, (size_t)n_chunks))) return rc;
+    const mpc::DiscParams P = disc_params(p);
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_tf, tf, (size_t)n_sats * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s0 = c * cs, ns = std::min(cs, n_sats - s0);
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_x + (size_t)s0 * 7 * K, x + (size_t)s0 * 7 * K, (size_t)ns * 7 * K * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->s_compute));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_u + (size_t)s0 * 3 * K, u + (size_t)s0 * 3 * K, (size_t)ns * 3 * K * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->s_compute));
+        mpc::DstTab tab{};
+        tab.p[0] = ctx->d_out;
+        const long long off = (long long)s0 * (K - 1);
+        rc = p->include_j2
+                 ? launch_disc_n<true, 1>(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, P, ns,
+                                          K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute)
+                 : launch_disc_n<false, 1>(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, P,
+                                           ns, K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev[c], ctx->s_compute));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev[c], 0));
+        if ((rc = copy_out_chunk(out_host, ctx->d_out, n_int, off, (long long)ns * (K - 1), ctx->s_copy))) return rc;
+    }
+    if (status_host)
+        CUDA_TRY(cudaMemcpyAsync(status_host, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 ctx->s_copy));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_compute));
+    return MPC_SUCCESS;
+}
+
+static int upload_table(mpc_ctx *ctx, const mpc_controller *ctrl, int n_sats, cudaStream_t st)
+{
+    if (ctrl->kind != MPC_CTRL_SEQUENCE) return MPC_SUCCESS;
+    const size_t cnt = (size_t)(ctrl->table_per_sat ? n_sats : 1) * 3 * ctrl->table_len;
+    int rc = ensure(ctx->d_tab, ctx->cap_tab, cnt);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_tab, ctrl->table, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+    return MPC_SUCCESS;
+}
+
+int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p,
+                             const mpc_controller *ctrl, int n_sats, int T, int n_sub, double *y_host,
+                             double *u_host, int32_t *status_host)
+{
+    if (!ctx || !y0 || !tf || !p || !y_host) return fail(MPC_E_INVALID, "null pointer argument");
+    if (n_sats < 0 || T < 0 || n_sub < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 0, n_sub >= 1");
+    int rc = check_ctrl(ctrl);
+    if (rc) return rc;
+    if (n_sats == 0 || T == 0) return MPC_SUCCESS;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if ((rc = ensure(ctx->d_y0, ctx->cap_y0, (size_t)n_sats * 7))) return rc;
+    if ((rc = ensure(ctx->d_tf, ctx->cap_tf, (size_t)n_sats))) return rc;
+    if ((rc = ensure(ctx->d_x, ctx->cap_x, (size_t)n_sats * 7 * T))) return rc;
+    if ((rc = ensure(ctx->d_u, ctx->cap_u, (size_t)n_sats * 3 * T))) return rc;
+    if ((rc = ensure(ctx->d_status2, ctx->cap_status2, (size_t)n_sats))) return rc;
+    cudaStream_t st = ctx->s_compute;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_y0, y0, (size_t)n_sats * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_tf, tf, (size_t)n_sats * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = upload_table(ctx, ctrl, n_sats, st))) return rc;
+    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p, ctrl, ctx->d_tab, n_sats, T, n_sub, ctx->d_x, ctx->d_u, ctx->d_status2, st)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(y_host, ctx->d_x, (size_t)n_sats * 7 * T * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (u_host) CUDA_TRY(cudaMemcpyAsync(u_host, ctx->d_u, (size_t)n_sats * 3 * T * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status_host)
+        CUDA_TRY(cudaMemcpyAsync(status_host, ctx->d_status2, (size_t)n_sats * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MPC_SUCCESS;
+}
+
+int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                  const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                  int n_sub_prop, int n_sub_disc, double *y_host, double *u_host,
+                                  double *out_host, int32_t *status_host)
+{
+    if (!ctx || !y0 || !tf || !p_prop || !p_disc || !out_host) return fail(MPC_E_INVALID, "null pointer argument");
+    const int K = T;
+    if (n_sats < 0 || K < 2 || n_sub_prop < 1 || n_sub_disc < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 2, n_sub >= 1");
+    if (p_disc->include_drag) return fail(MPC_E_UNSUPPORTED, "include_drag is not supported by the discretizer (the reference raises too)");
+    int rc = check_ctrl(ctrl);
+    if (rc) return rc;
+    if (n_sats == 0) return MPC_SUCCESS;
+    const long long n_int = (long long)n_sats * (K - 1);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if ((rc = ensure(ctx->d_y0, ctx->cap_y0, (size_t)n_sats * 7))) return rc;
+    if ((rc = ensure(ctx->d_tf, ctx->cap_tf, (size_t)n_sats))) return rc;
+    if ((rc = ensure(ctx->d_x, ctx->cap_x, (size_t)n_sats * 7 * K))) return rc;
+    if ((rc = ensure(ctx->d_u, ctx->cap_u, (size_t)n_sats * 3 * K))) return rc;
+    if ((rc = ensure(ctx->d_out, ctx->cap_out, (size_t)n_int * MPC_OUT_ROWS))) return rc;
+    if ((rc = ensure(ctx->d_status, ctx->cap_status, (size_t)n_int))) return rc;
+    if ((rc = ensure(ctx->d_status2, ctx->cap_status2, (size_t)n_sats))) return rc;
+    const int cs = chunk_sats(n_sats, K);
+    const int n_chunks = (n_sats + cs - 1) / cs;
+    if ((rc = ensure_events(ctx, (size_t)n_chunks))) return rc;
+    cudaStream_t st = ctx->s_compute;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_y0, y0, (size_t)n_sats * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_tf, tf, (size_t)n_sats * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = upload_table(ctx, ctrl, n_sats, st))) return rc;
+    // the whole batch is propagated first (one thread per satellite is latency-bound: chunking it
+    // would only serialise the latency), then discretized chunk by chunk while results stream out
+    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p_prop, ctrl, ctx->d_tab, n_sats, K, n_sub_prop, ctx->d_x, ctx->d_u,
+                          ctx->d_status2, st)))
+        return rc;
+    const mpc::DiscParams P = disc_params(p_disc);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s0 = c * cs, ns = std::min(cs, n_sats - s0);
+        mpc::DstTab tab{};
+        tab.p[0] = ctx->d_out;
+        const long long off = (long long)s0 * (K - 1);
+        rc = p_disc->include_j2
+                 ? launch_disc_n<true, 1>(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, P, ns,
+                                          K, n_sub_disc, tab, n_int, off, ctx->d_status + off, st)
+                 : launch_disc_n<false, 1>(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, P,
+                                           ns, K, n_sub_disc, tab, n_int, off, ctx->d_status + off, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev[c], st));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev[c], 0));
+        if (c == 0) {
+            if (y_host) CUDA_TRY(cudaMemcpyAsync(y_host, ctx->d_x, (size_t)n_sats * 7 * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
+            if (u_host) CUDA_TRY(cudaMemcpyAsync(u_host, ctx->d_u, (size_t)n_sats * 3 * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
+        }
+        if ((rc = copy_out_chunk(out_host, ctx->d_out, n_int, off, (long long)ns * (K - 1), ctx->s_copy))) return rc;
+    }
+    if (status_host)
+        CUDA_TRY(cudaMemcpyAsync(status_host, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // a satellite whose propagation failed poisons its intervals: surface it in the interval status
+    if (status_host) {
+        std::vector<int32_t> ps((size_t)n_sats);
+        CUDA_TRY(cudaMemcpy(ps.data(), ctx->d_status2, (size_t)n_sats * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int s = 0; s < n_sats; ++s)
+            if (ps[(size_t)s])
+                for (int k = 0; k < K - 1; ++k) status_host[(size_t)s * (K - 1) + k] = ps[(size_t)s];
+    }
+    return MPC_SUCCESS;
+}
+
+int mpc_fp64_peak_probe(int device, int repeats, double *tflops, double *ms)
+{
+    if (!tflops) return fail(MPC_E_INVALID, "null output");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < std::max(repeats, 1) + 1; ++r) {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        mpc::fp64_probe_kernel<<<blocks, threads>>>(d, iters, 1.0 + r);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+        if (r > 0) best = std::min(best, t);  // first launch is warm-up
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    const double flops = (double)blocks * threads * (double)iters * 64.0 * 2.0;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms) *ms = best;
+    return MPC_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// propagate_kernel.cuh -- batched nonlinear orbit propagation, one thread per satellite.
+//
+// Replaces Simulator.get_trajectory_ODE (simulator.py:164-189): integrate
+//   y' = tf * f(y, u(y,tau))   over tau in [0,1]          (simulator.py:115-161)
+// and sample at linspace(0,1,T).  The reference's solve_ivp(RK45, max_step=0.001) becomes
+// fixed-step classical RK4 with n_sub steps between consecutive samples.  The controller law
+// u(y,tau) (control.py) is evaluated on the device at every stage, and once more at every
+// sample to produce Discretizer.extract_uk's output (linearize_discretize.py:393-411).
+//
+// Propagation is sequential in tau, so this kernel is latency-bound by construction: one warp per
+// CTA spreads the satellites over as many SMs as possible.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "discretize_kernel.cuh"
+
+namespace mpc {
+
+struct PropParams {
+    double mu, kj2, inv_ve;
+    double drag_k;  // 0.5 * C_D * S * (rho_atm / RHO)   (simulator.py:152)
+    int include_j2, include_drag;
+};
+
+struct CtrlParams {
+    int kind, table_len, table_per_sat, pad;
+    double t0, t1, t2;  // constant thrust vector, or t0 = tangential magnitude
+    double end_tau;
+    const double *table;
+};
+
+__device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__restrict__ tab, const double (&y)[7],
+                                          double tau, double &ux, double &uy, double &uz)
+{
+    ux = uy = uz = 0.0;
+    if (C.kind == 1) {  // control.py:47-53
+        ux = C.t0;
+        uy = C.t1;
+        uz = C.t2;
+    } else if (C.kind == 2) {  // control.py:66-84: thrust along t_hat = h_hat x r_hat
+        const double ir = fast_rsqrt(fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2])));
+        const double nx = y[0] * ir, ny = y[1] * ir, nz = y[2] * ir;
+        const double hx = fma(y[1], y[5], -y[2] * y[4]);
+        const double hy = fma(y[2], y[3], -y[0] * y[5]);
+        const double hz = fma(y[0], y[4], -y[1] * y[3]);
+        const double ih = C.t0 * fast_rsqrt(fma(hx, hx, fma(hy, hy, hz * hz)));
+        ux = ih * fma(hy, nz, -hz * ny);
+        uy = ih * fma(hz, nx, -hx * nz);
+        uz = ih * fma(hx, ny, -hy * nx);
+    } else if (C.kind == 3) {  // control.py:104-143: FOH table on tau/end_tau, zero after end_tau
+        if (tau <= C.end_tau) {
+            const int Ku = C.table_len;
+            const double t = tau / C.end_tau;
+            if (t == 1.0) {
+                ux = tab[Ku - 1];
+                uy = tab[2 * Ku - 1];
+                uz = tab[3 * Ku - 1];
+            } else {
+                const double km1 = (double)(Ku - 1);
+                int k = (int)floor(t * km1);
+                k = min(max(k, 0), Ku - 2);
+                const double lo = (double)k / km1, hi = (double)(k + 1) / km1;
+                const double iw = 1.0 / (hi - lo);
+                const double ln = (hi - t) * iw, lp = (t - lo) * iw;
+                ux = fma(ln, tab[k], lp * tab[k + 1]);
+                uy = fma(ln, tab[Ku + k], lp * tab[Ku + k + 1]);
+                uz = fma(ln, tab[2 * Ku + k], lp * tab[2 * Ku + k + 1]);
+            }
+        }
+    }
+}
+
+// f(y,u) without the tf factor (simulator.py:130-160); returns nonzero on non-positive mass
+__device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C, const double *__restrict__ tab,
+                                        const double (&y)[7], double tau, double (&dy)[7])
+{
+    double ux, uy, uz;
+    ctrl_eval(C, tab, y, tau, ux, uy, uz);
+    const double m = y[6];
+    const double r2 = fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2]));
+    const double ir = fast_rsqrt(r2);
+    const double ir2 = ir * ir;
+    const double mu3 = P.mu * ir * ir2;
+    const double im = fast_rcp(m);
+    double ax = fma(-mu3, y[0], ux * im);
+    double ay = fma(-mu3, y[1], uy * im);
+    double az = fma(-mu3, y[2], uz * im);
+    if (P.include_drag) {
+        const double v2 = fma(y[3], y[3], fma(y[4], y[4], y[5] * y[5]));
+        const double vn = (v2 > 0.0) ? v2 * fast_rsqrt(v2) : 0.0;
+        const double c = -P.drag_k * im * vn;
+        ax = fma(c, y[3], ax);
+        ay = fma(c, y[4], ay);
+        az = fma(c, y[5], az);
+    }
+    if (P.include_j2) {
+        const double nz = y[2] * ir;
+        const double q5 = 5.0 * nz * nz;
+        const double k5 = P.kj2 * ir2 * ir2 * ir;
+        const double c1 = k5 * (q5 - 1.0);
+        ax = fma(c1, y[0], ax);
+        ay = fma(c1, y[1], ay);
+        az = fma(k5 * (q5 - 3.0), y[2], az);
+    }
+    const double uu = fma(ux, ux, fma(uy, uy, uz * uz));
+    const double un = (uu > 0.0) ? uu * fast_rsqrt(uu) : 0.0;
+    dy[0] = y[3];
+    dy[1] = y[4];
+    dy[2] = y[5];
+    dy[3] = ax;
+    dy[4] = ay;
+    dy[5] = az;
+    dy[6] = -un * P.inv_ve;
+    return !(m > 0.0);
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_arr, PropParams P, CtrlParams C,
+                 int n_sats, int T, int n_sub, double *__restrict__ y_out, double *__restrict__ u_out,
+                 int32_t *__restrict__ status)
+{
+    const int s = blockIdx.x * BLOCK + threadIdx.x;
+    if (s >= n_sats) return;
+    const double *tab = C.table ? C.table + (C.table_per_sat ? (long long)s * 3 * C.table_len : 0) : nullptr;
+    const double tf = tf_arr[s];
+    double y[7], k1[7], k2[7], k3[7], k4[7], yt[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) y[c] = y0[(long long)s * 7 + c];
+    const double Tm1 = (T > 1) ? (double)(T - 1) : 1.0;
+    const double h = 1.0 / (Tm1 * (double)n_sub);
+    const double hs = tf * h, hh = 0.5 * hs, hs_6 = hs * (1.0 / 6.0);
+    double *yo = y_out + (long long)s * 7 * T;
+    double *uo = u_out ? u_out + (long long)s * 3 * T : nullptr;
+    int bad = 0;
+    for (int j = 0; j < T; ++j) {
+        const double tau_j = (T > 1) ? (double)j / Tm1 : 0.0;
+        if (bad) {
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) yo[(long long)c * T + j] = qnan;
+            if (uo) {
+                uo[j] = qnan;
+                uo[T + j] = qnan;
+                uo[2 * (long long)T + j] = qnan;
+            }
+            continue;
+        }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) yo[(long long)c * T + j] = y[c];
+        if (uo) {
+            double ux, uy, uz;
+            ctrl_eval(C, tab, y, tau_j, ux, uy, uz);
+            uo[j] = ux;
+            uo[T + j] = uy;
+            uo[2 * (long long)T + j] = uz;
+        }
+        if (j == T - 1) break;
+        const double tau_n = (double)(j + 1) / Tm1;
+        for (int n = 0; n < n_sub; ++n) {
+            // step end points from integers: the last one is exactly tau_{j+1} (1.0 at the end of the run)
+            const double t0 = (n == 0) ? tau_j : fma((double)n, h, tau_j);
+            const double t1 = (n == n_sub - 1) ? tau_n : fma((double)(n + 1), h, tau_j);
+            const double tm = 0.5 * (t0 + t1);
+            bad |= prop_rhs(P, C, tab, y, t0, k1);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) yt[c] = fma(hh, k1[c], y[c]);
+            bad |= prop_rhs(P, C, tab, yt, tm, k2);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) yt[c] = fma(hh, k2[c], y[c]);
+            bad |= prop_rhs(P, C, tab, yt, tm, k3);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) yt[c] = fma(hs, k3[c], y[c]);
+            bad |= prop_rhs(P, C, tab, yt, t1, k4);
+            if (bad) break;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) y[c] = fma(hs_6, (k1[c] + k4[c]) + 2.0 * (k2[c] + k3[c]), y[c]);
+        }
+    }
+    if (status) status[s] = bad ? 1 : 0;
+}
+
+// FP64 FMA throughput probe: 8 independent chains per thread, `iters` rounds.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double b = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            a0 = fma(a0, b, c);
+            a1 = fma(a1, b, c);
+            a2 = fma(a2, b, c);
+            a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c);
+            a5 = fma(a5, b, c);
+            a6 = fma(a6, b, c);
+            a7 = fma(a7, b, c);
+        }
+    }
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace mpc

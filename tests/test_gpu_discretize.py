@@ -1,0 +1,184 @@
+"""GPU parity tests of the discretization kernel, called through the C-ABI (ctypes)."""
+import numpy as np
+import pytest
+
+from conftest import NAMES, rel_err, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+# CUDA vs the reference's use_uniform_steps=True mode (golden fixtures): SURVEY 8c states <= 1e-8
+TOL_REF = 1e-8
+# CUDA vs the plain-C oracle (same RK4/trapezoid algorithm, different formulation: dense LU inverse,
+# literal J2 Jacobian, 56-vector classical RK4): rounding-level agreement
+TOL_ORACLE = 1e-10
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mpconstellation_b200 as m
+    m._lib.require_gpu()
+    return m
+
+
+def _sel(o, ks):
+    return o[ks] if o.ndim == 3 else o[:, ks]
+
+
+@pytest.mark.parametrize("sc", ["d0", "d1", "d2", "d3", "d4"])
+def test_discretizer_matches_reference_fixtures(M, gold_disc, const, sc):
+    """the reference's own test scenarios (test_discretizer.py:30-150) through the reference signature"""
+    g = gold_disc
+    d = M.Discretizer(const, use_scipy_ZOH=False, include_drag=False, include_J2=False)
+    d.use_uniform_steps = True
+    out = d.discretize(M.Simulator.satellite_dynamics, g[sc + "_x"], g[sc + "_u"], float(g[sc + "_tf"]))
+    K = g[sc + "_x"].shape[1]
+    assert [o.shape for o in out] == [(K - 1, 7, 7), (K - 1, 7, 3), (K - 1, 7, 3), (7, K - 1), (7, K - 1)]
+    for n, o in zip(NAMES, out):
+        assert rel_err(o, g[f"{sc}_uni_{n}"]) < TOL_REF, (sc, n)
+
+
+def test_j2_and_node_count_match_reference_fixtures(M, gold_disc, const):
+    g = gold_disc
+    ks = g["d3_j2_ks"]
+    d = M.Discretizer(const, include_J2=True)
+    d.use_uniform_steps = True
+    out = d.discretize(M.Simulator.satellite_dynamics, g["d3_x"], g["d3_u"], 2.0)
+    for n, o in zip(NAMES, out):
+        assert rel_err(_sel(o, ks), g[f"d3_j2_uni_{n}"]) < TOL_REF, n
+    d = M.Discretizer(const)
+    d.use_uniform_steps = True
+    d.integrator_steps = 21
+    out = d.discretize(M.Simulator.satellite_dynamics, g["d3_x"], g["d3_u"], 2.0)
+    for n, o in zip(NAMES, out):
+        assert rel_err(_sel(o, ks), g[f"d3_n21_uni_{n}"]) < TOL_REF, n
+
+
+def test_scipy_zoh_flag_is_the_same_hold(M, gold_disc, const):
+    """test_discretizer.py:152-157 (test_custom_ZOH)"""
+    g = gold_disc
+    outs = []
+    for flag in (False, True):
+        d = M.Discretizer(const, use_scipy_ZOH=flag)
+        d.use_uniform_steps = True
+        outs.append(d.discretize(M.Simulator.satellite_dynamics, g["d1_x"], g["d1_u"], 0.1))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n_sats,K,tf,j2,n_sub", [(64, 100, 1.0, False, 100), (7, 33, 0.7, True, 100),
+                                                  (5, 2, 0.05, False, 100), (3, 50, 2.0, True, 16),
+                                                  (130, 3, 0.02, False, 7)])
+def test_batch_matches_c_oracle(M, const, n_sats, K, tf, j2, n_sub):
+    """config 2 (64 sats x K=100) and ragged shapes against the plain-C oracle on the same seeded inputs"""
+    from oracle import c_oracle as C
+    _, x, u = synth_batch(n_sats, K, tf, const)
+    tfv = tf * (1 + 0.05 * np.arange(n_sats) / n_sats)          # per-satellite tf
+    ref = C.discretize_batch(x, u, tfv, const, include_J2=j2, n_sub=n_sub)
+    assert ref[5].max() == 0
+    res = M.discretize_batch(x, u, tfv, const, include_J2=j2, n_sub=n_sub)
+    assert res.status.shape == (n_sats, K - 1) and res.status.max() == 0
+    for n, o, r in zip(NAMES, res.stacked(), ref[:5]):
+        assert o.shape == r.shape
+        assert rel_err(o, r) < TOL_ORACLE, n
+        # per-interval too, so a single bad unit cannot hide behind the batch maximum
+        axes = tuple(range(2, o.ndim)) if n in ("A_k", "B_kp", "B_kn") else (1,)
+        num = np.max(np.abs(o - r), axis=axes)
+        den = np.max(np.abs(r), axis=axes)
+        assert np.all(num <= 1e-9 * np.maximum(den, 1e-300)), n
+
+
+def test_structure_of_outputs(M, const):
+    """size-independent properties: last row of A_k is e7, B_kp + B_kn = A_k int Phi^-1 B (lambda weights sum to 1),
+    the symplectic identity on the 6x6 block, and thrust-free intervals give zero mass rows"""
+    _, x, u = synth_batch(16, 40, 1.0, const)
+    res = M.discretize_batch(x, u, 1.0, const)
+    A, Bp, Bn, S, X = res.stacked()
+    assert np.array_equal(A[..., 6, :6], np.zeros_like(A[..., 6, :6])) and np.all(A[..., 6, 6] == 1.0)
+    J = np.block([[np.zeros((3, 3)), np.eye(3)], [-np.eye(3), np.zeros((3, 3))]])
+    P6 = A[..., :6, :6]
+    assert np.max(np.abs(np.swapaxes(P6, -1, -2) @ J @ P6 - J)) < 1e-9
+    u0 = np.zeros_like(u)
+    res0 = M.discretize_batch(x, u0, 1.0, const)
+    A0, Bp0, Bn0, S0, X0 = res0.stacked()
+    assert np.all(Bp0[..., 6, :] == 0) and np.all(Bn0[..., 6, :] == 0) and np.all(S0[:, 6, :] == 0)   # eps guard (:208)
+    assert np.all(np.isfinite(res0.soa))
+
+
+def test_rollout_self_consistency_full_size_sample(M, const):
+    """known-answer property at the bench's K: the discrete model on its own reference trajectory reproduces
+    the nonlinear propagation (test_discretizer.py:110-113)"""
+    _, x, u = synth_batch(8, 200, 2.0, const)
+    res = M.discretize_batch(x, u, 2.0, const)
+    for s in range(8):
+        A, Bp, Bn, S, X = res.sat(s)
+        for k in range(0, 199, 9):
+            pred = A[k] @ x[s, :, k] + Bn[k] @ u[s, :, k] + Bp[k] @ u[s, :, k + 1] + S[:, k] * 2.0 + X[:, k]
+            assert np.max(np.abs(pred - x[s, :, k + 1])) < 1e-5
+
+
+def test_mass_failure_is_flagged_and_raises_like_reference(M, const):
+    _, x, u = synth_batch(2, 10, 1.0, const)
+    x = x.copy()
+    x[1, 6, 4] = -0.5
+    with pytest.raises(Exception, match="INVALID SATELLITE MASS"):
+        M.discretize_batch(x, u, 1.0, const)
+    res = M.discretize_batch(x, u, 1.0, const, check=False)
+    assert res.status[1, 4] == M._lib.ST_MASS and res.status.sum() == M._lib.ST_MASS
+    x[0, 0, 2] = np.nan
+    res = M.discretize_batch(x, u, 1.0, const, check=False)
+    assert res.status[0, 2] == M._lib.ST_NONFINITE
+
+
+def test_drag_is_rejected_by_the_library_like_the_reference(M, const):
+    _, x, u = synth_batch(1, 5, 1.0, const)
+    with pytest.raises(M._lib.MpcError) as e:
+        M.discretize_batch(x, u, 1.0, const, include_drag=True)
+    assert e.value.code == M._lib.E_UNSUPPORTED
+
+
+def test_device_api_pitch_offset_and_multi_destination(M, const):
+    """device-pointer entry points on torch tensors: two 'ranks' write disjoint column ranges of one
+    gathered buffer, and the multi-destination store replicates bit-identically"""
+    import torch
+    _, x, u = synth_batch(6, 12, 1.0, const)
+    K = 12
+    ref = M.discretize_batch(x, u, 1.0, const).soa.copy()
+    dev = torch.device("cuda:0")
+    n = 6 * (K - 1)
+    gathered = torch.full((105, n + 5), float("nan"), dtype=torch.float64, device=dev)
+    tfv = torch.ones(3, dtype=torch.float64, device=dev)
+    for r in range(2):
+        xs = torch.from_numpy(x[3 * r:3 * r + 3]).to(dev).contiguous()
+        us = torch.from_numpy(u[3 * r:3 * r + 3]).to(dev).contiguous()
+        M.discretize_batch_device(xs, us, tfv, const, out=gathered, out_offset=r * 3 * (K - 1))
+    torch.cuda.synchronize()
+    got = gathered.cpu().numpy()
+    assert np.array_equal(got[:, :n], ref) and np.all(np.isnan(got[:, n:]))
+    xs = torch.from_numpy(x).to(dev).contiguous()
+    us = torch.from_numpy(u).to(dev).contiguous()
+    tfv = torch.ones(6, dtype=torch.float64, device=dev)
+    outs = [torch.zeros((105, n), dtype=torch.float64, device=dev) for _ in range(4)]
+    M.discretize_batch_device(xs, us, tfv, const, out=outs[0], extra_dst=outs[1:])
+    torch.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), ref)
+
+
+def test_full_size_config3_properties(M, const):
+    """BASELINE config 3 (4096 satellites x K=200 = 815,104 intervals): full-size run checked through
+    size-independent properties + a random sample of intervals against the C oracle"""
+    from oracle import c_oracle as C
+    N, K = 4096, 200
+    y0, _, _ = synth_batch(N, 2, 2.0, const)            # initial states only (cheap)
+    res, x, u = M.propagate_discretize(y0, 2.0, M.ConstantTangentialThrustController(tangential_thrust=0.5), const, T=K)
+    assert res.status.max() == 0 and np.all(np.isfinite(res.soa))
+    A, Bp, Bn, S, X = res.stacked()
+    assert np.all(A[..., 6, 6] == 1.0) and not np.any(A[..., 6, :6])
+    J = np.block([[np.zeros((3, 3)), np.eye(3)], [-np.eye(3), np.zeros((3, 3))]])
+    P6 = A[::37, ::11, :6, :6]
+    assert np.max(np.abs(np.swapaxes(P6, -1, -2) @ J @ P6 - J)) < 1e-9
+    rng = np.random.default_rng(7)
+    sats = np.sort(rng.choice(N, 12, replace=False))
+    ref = C.discretize_batch(np.ascontiguousarray(x[sats]), np.ascontiguousarray(u[sats]), 2.0, const)
+    for n, o, r in zip(NAMES, (A[sats], Bp[sats], Bn[sats], S[sats], X[sats]), ref[:5]):
+        assert rel_err(o, r) < TOL_ORACLE, n

@@ -1,0 +1,172 @@
+"""GPU parity tests of the propagation kernel and the Simulator mirror, through the C-ABI."""
+import numpy as np
+import pytest
+
+from conftest import rel_err, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATE = 1e-6      # north_star tolerance on propagated states vs the reference's RK45
+TOL_ORACLE = 1e-11    # same RK4, same step grid, vs the plain-C oracle
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mpconstellation_b200 as m
+    m._lib.require_gpu()
+    return m
+
+
+def _hubble(M, gp):
+    x = gp["x0_dim"]
+    sat = M.Satellite(x[0:3].copy(), x[3:6].copy(), float(x[6]))
+    return sat, M.SatelliteScale(sat=sat)
+
+
+def test_five_orbit_coast_drag_j2(M, gold_prop):
+    """test_simulator.py:17-33"""
+    sat, scale = _hubble(M, gold_prop)
+    sim = M.Simulator(sats=[sat], scale=scale)
+    data, time = sim.run(tf=5)
+    assert data[sat.id].shape == (7, 500) and np.array_equal(time[sat.id], gold_prop["p0_t"])
+    assert rel_err(data[sat.id], gold_prop["p0_y"]) < TOL_STATE
+
+
+def test_tangential_reference_trajectory_and_extract_uk(M, gold_prop):
+    """test_discretizer.py:120-138: the trajectory the discretizer is linearized about, and extract_uk"""
+    gp = gold_prop
+    sat, scale = _hubble(M, gp)
+    c = M.ConstantTangentialThrustController([sat], 0.5)
+    sim = M.Simulator(sats=[sat], controller=c, scale=scale, base_res=100, include_drag=False, include_J2=False)
+    sim.run(tf=2)
+    assert rel_err(sim.sim_data[sat.id], gp["p1_y"]) < TOL_STATE
+    assert rel_err(sim.sim_u[sat.id], gp["p1_u"]) < TOL_STATE
+    u_host = M.Discretizer.extract_uk(sim.sim_data[sat.id], sim.sim_time[sat.id], c)
+    assert rel_err(u_host, sim.sim_u[sat.id]) < 1e-12
+
+
+def test_constant_and_tangential_with_perturbations(M, gold_prop):
+    """test_simulator.py:175-203"""
+    gp = gold_prop
+    sat, scale = _hubble(M, gp)
+    sim = M.Simulator(sats=[sat], controller=M.ConstantThrustController(thrust=gp["p2_thrust"]), scale=scale)
+    sim.run(tf=3)
+    assert rel_err(sim.sim_data[sat.id], gp["p2_y"]) < TOL_STATE
+    sat, scale = _hubble(M, gp)
+    sim = M.Simulator(sats=[sat], controller=M.ConstantTangentialThrustController(tangential_thrust=0.1), scale=scale)
+    sim.run(tf=2)
+    assert rel_err(sim.sim_data[sat.id], gp["p4_y"]) < TOL_STATE
+
+
+def test_three_satellites_one_scale(M, gold_prop):
+    """test_simulator.py:36-55"""
+    gp = gold_prop
+    sats = [M.Satellite(y[0:3].copy(), y[3:6].copy(), float(y[6])) for y in gp["p3_y0_dim"]]
+    scale = M.SatelliteScale(sat=sats[0])
+    sim = M.Simulator(sats=sats, scale=scale)
+    data, _ = sim.run(tf=5)
+    got = np.stack([data[s.id] for s in sats])
+    assert rel_err(got, gp["p3_y"]) < TOL_STATE
+
+
+def test_run_segments_bookkeeping(M, gold_prop):
+    """test_simulator.py:149-173: concatenation, time offsets (+1e-7), satellite state write-back"""
+    gp = gold_prop
+    x = gp["x0_dim"]
+    s1 = M.Satellite(x[0:3].copy(), x[3:6].copy(), float(x[6]))
+    s2 = M.Satellite(x[0:3].copy(), x[3:6] * 1.1, float(x[6]))
+    scale = M.SatelliteScale(sat=s1)
+    c = M.ConstantTangentialThrustController(sats=[s1, s2], tangential_thrust=0.5)
+    sim = M.Simulator(sats=[s1, s2], scale=scale, base_res=100, controller=c)
+    sim.run_segments(tf=3, num_segments=4)
+    got_y = np.stack([sim.sim_data[s1.id], sim.sim_data[s2.id]])
+    got_t = np.stack([sim.sim_time[s1.id], sim.sim_time[s2.id]])
+    assert got_y.shape == gp["p6_y"].shape
+    assert np.allclose(got_t, gp["p6_t"], rtol=0, atol=1e-15)
+    assert rel_err(got_y, gp["p6_y"]) < TOL_STATE
+    final = np.stack([s1.get_state_vector(), s2.get_state_vector()])
+    assert rel_err(final, gp["p6_final_dim"]) < TOL_STATE
+
+
+def test_sequence_controller(M, gold_prop, const):
+    """SequenceController as OptimalController drives it (end_tau >= 1): FOH kinks only -> <= 1e-6.  With the
+    table ending inside the run the thrust jumps to zero; the reference integrates across the jump with O(h)
+    error, so agreement is limited to that (documented), while extract_uk stays exact."""
+    from oracle import mpc_oracle as O
+    gp = gold_prop
+    sat, scale = _hubble(M, gp)
+    tab = gp["p5_u_tab"]
+    y0 = scale.normalize_state(sat.get_state_vector())
+    yr, _ = O.propagate(y0, 2.0, O.ctrl_sequence(tab, 2.0, 2.0), const, False, False, 120)
+    sim = M.Simulator(sats=[sat], controller=M.SequenceController(u=tab, tf_u=2.0, tf_sim=2.0), scale=scale,
+                      base_res=60, include_drag=False, include_J2=False)
+    sim.run(tf=2)
+    assert rel_err(sim.sim_data[sat.id], yr) < TOL_STATE
+    sat, scale = _hubble(M, gp)
+    sim = M.Simulator(sats=[sat], controller=M.SequenceController(u=tab, tf_u=1.5, tf_sim=2.0), scale=scale,
+                      base_res=60, include_drag=False, include_J2=False)
+    sim.run(tf=2)
+    assert rel_err(sim.sim_data[sat.id], gp["p5_y"]) < 5e-3
+    assert rel_err(sim.sim_u[sat.id], gp["p5_u"]) < 1e-12
+
+
+def test_get_trajectory_ode_signature(M, gold_prop):
+    gp = gold_prop
+    sat, scale = _hubble(M, gp)
+    c = M.ConstantTangentialThrustController([sat], 0.5)
+    sim = M.Simulator(sats=[sat], controller=c, scale=scale, include_drag=False, include_J2=False)
+    sim.eval_points = 200
+    sol = sim.get_trajectory_ODE(sat, 2, c.get_u_func())
+    assert sol.y.shape == (7, 200) and sol.t.shape == (200,)
+    assert rel_err(sol.y, gp["p1_y"]) < TOL_STATE
+    with pytest.raises(NotImplementedError):
+        sim.get_trajectory_ODE(sat, 2, lambda x, tau: np.zeros(3))
+
+
+@pytest.mark.parametrize("kind", ["zero", "constant", "tangential", "sequence", "sequence_per_sat"])
+def test_batch_matches_c_oracle(M, const, kind):
+    from oracle import c_oracle as C
+    N, T, tf = 37, 64, 1.3
+    y0, _, _ = synth_batch(N, 2, 1.0, const)
+    rng = np.random.default_rng(3)
+    tfv = tf * (1 + 0.1 * rng.random(N))
+    tab = 0.3 * rng.standard_normal((3, 17))
+    tabs = 0.3 * rng.standard_normal((N, 3, 9))
+    ctrl, ckw = {
+        "zero": (M.Controller(), dict(kind=C.CTRL_ZERO)),
+        "constant": (M.ConstantThrustController(thrust=np.array([0.1, -0.2, 0.05])), dict(kind=C.CTRL_CONSTANT, cparams=(0.1, -0.2, 0.05))),
+        "tangential": (M.ConstantTangentialThrustController(tangential_thrust=0.4), dict(kind=C.CTRL_TANGENTIAL, cparams=(0.4, 0, 0))),
+        "sequence": (M.SequenceController(u=tab, tf_u=2.0, tf_sim=1.0), dict(kind=C.CTRL_SEQUENCE, table=tab, end_tau=2.0)),
+        "sequence_per_sat": (M.SequenceController(u=tabs, tf_u=1.0, tf_sim=1.0), dict(kind=C.CTRL_SEQUENCE, table=tabs, end_tau=1.0)),
+    }[kind]
+    y, u, t, st = M.propagate_batch(y0, tfv, ctrl, const, include_drag=True, include_J2=True, T=T, n_sub=9)
+    yr, ur, sr = C.propagate_batch(y0, tfv, const, include_drag=True, include_J2=True, T=T, n_sub=9, **ckw)
+    assert st.max() == 0 and sr.max() == 0
+    assert rel_err(y, yr) < TOL_ORACLE and rel_err(u, ur) < 1e-10
+    assert np.array_equal(t, np.linspace(0, 1, T))
+
+
+def test_edge_shapes_and_mass_failure(M, const):
+    y0, _, _ = synth_batch(3, 2, 1.0, const)
+    y, u, t, st = M.propagate_batch(y0, 1.0, M.Controller(), const, T=1)
+    assert y.shape == (3, 7, 1) and np.array_equal(y[:, :, 0], y0)
+    y, u, t, st = M.propagate_batch(y0[:0], 1.0, M.Controller(), const, T=10)
+    assert y.shape == (0, 7, 10)
+    y0 = y0.copy()
+    y0[1, 6] = 1e-3
+    with pytest.raises(Exception, match="INVALID SATELLITE MASS"):
+        M.propagate_batch(y0, 5.0, M.ConstantThrustController(thrust=np.array([5.0, 0, 0])), const, T=50)
+    y, u, t, st = M.propagate_batch(y0, 5.0, M.ConstantThrustController(thrust=np.array([5.0, 0, 0])), const, T=50, check=False)
+    assert list(st) == [0, 1, 0] and np.all(np.isfinite(y[0])) and np.any(np.isnan(y[1]))
+
+
+def test_device_tensor_api(M, const):
+    import torch
+    y0, _, _ = synth_batch(9, 2, 1.0, const)
+    c = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    yh, uh, _, _ = M.propagate_batch(y0, 2.0, c, const, include_drag=False, include_J2=False, T=50)
+    dev = torch.device("cuda:0")
+    y, u, st = M.propagate_batch_device(torch.from_numpy(y0).to(dev), torch.full((9,), 2.0, dtype=torch.float64, device=dev),
+                                        c, const, include_drag=False, include_J2=False, T=50)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), yh) and np.array_equal(u.cpu().numpy(), uh) and int(st.max()) == 0

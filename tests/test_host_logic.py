@@ -1,0 +1,165 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+import mpconstellation_b200 as M
+from mpconstellation_b200 import _lib, batch
+from mpconstellation_b200.control import spec_from
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mpc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mpc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    if _lib.needs_build():
+        _lib.build()
+    L = ctypes.CDLL(_lib.SO_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/mpc_b200.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert _lib.lib().mpc_version() == 100
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.MpcParams) == 10 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.MpcController) == 4 * 4 + 3 * 8 + 8 + 8
+    assert _lib.MpcController.table.offset == 48
+
+
+def test_no_cpu_fallback_without_device():
+    if _lib.lib().mpc_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        batch.discretize_batch(np.zeros((1, 7, 3)) + 1.0, np.zeros((1, 3, 3)), 1.0, M.SatelliteScale().get_normalized_constants())
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mpconstellation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("mpc_oracle-free", ""), f"{f} mentions the oracle"
+
+
+def test_scale_and_constants_mirror_reference(gold_disc):
+    sat = M.Satellite(gold_disc["x0_dim"][0:3], gold_disc["x0_dim"][3:6], gold_disc["x0_dim"][6])
+    scale = M.SatelliteScale(sat=sat)
+    c = scale.get_normalized_constants()
+    got = np.array([c.MU, c.R_E, c.J2, c.G0, c.ISP, c.S, c.R0, c.RHO])
+    assert np.array_equal(got, gold_disc["const"])
+    x = sat.get_state_vector()
+    xn = scale.normalize_state(x)
+    assert np.allclose(scale.redim_state(xn), x, rtol=1e-15)
+    X = np.column_stack([x, 2 * x])
+    assert np.allclose(scale.redim_state(scale.normalize_state(X)), X, rtol=1e-15)
+    assert np.isclose(np.linalg.norm(xn[0:3]), 1.0) and xn[6] == 1.0
+    assert scale.normalize_thrust(scale.redim_thrust(0.5)) == pytest.approx(0.5)
+    ids = {M.Satellite().id for _ in range(100)}
+    assert len(ids) == 100
+
+
+def test_controller_specs_and_host_laws(gold_prop):
+    gp = gold_prop
+    from oracle import mpc_oracle as O
+    x = gp["p1_y"][:, 17]
+    s = spec_from(M.Controller())
+    assert s.kind == _lib.CTRL_ZERO and np.array_equal(M.Controller().get_u_func()(x, 0.3), np.zeros(3))
+    c = M.ConstantThrustController(thrust=np.array([0.1, 0.2, 0.3]))
+    assert spec_from(c).kind == _lib.CTRL_CONSTANT and spec_from(c).thrust == (0.1, 0.2, 0.3)
+    c = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    assert np.allclose(c.get_u_func()(x, 0.1), O.ctrl_tangential(0.5)(x, 0.1), rtol=1e-14, atol=1e-16)
+    tab = gp["p5_u_tab"]
+    c = M.SequenceController(u=tab, tf_u=1.5, tf_sim=2.0)
+    sp = spec_from(c)
+    assert sp.kind == _lib.CTRL_SEQUENCE and sp.end_tau == 0.75
+    ref = O.ctrl_sequence(tab, 1.5, 2.0)
+    for tau in (0.0, 0.1234, 0.5, 0.75, 0.7500001, 1.0):
+        assert np.allclose(c.get_u_func()(x, tau), ref(x, tau), rtol=1e-13, atol=1e-15)
+    # u_func closures carry their spec; arbitrary callables are refused (no Python on the device)
+    assert spec_from(c.get_u_func()).kind == _lib.CTRL_SEQUENCE
+    with pytest.raises(NotImplementedError):
+        spec_from(lambda x, tau: np.zeros(3))
+
+
+def test_reference_style_controller_objects_are_recognised():
+    """duck-typed by class name, the way the reference's own controller classes look"""
+    class ConstantThrustController:                      # noqa: shadows on purpose
+        def __init__(self):
+            self.thrust = np.array([0., 0., 0.1])
+
+        def get_u_func(self):
+            return lambda x, tau: self.thrust
+
+    c = ConstantThrustController()
+    assert spec_from(c).kind == _lib.CTRL_CONSTANT
+    assert spec_from(c.get_u_func()).thrust == (0.0, 0.0, 0.1)
+
+    class OptimalLike:
+        sequence_controller = M.SequenceController(u=np.ones((3, 4)), tf_u=2, tf_sim=1)
+
+    assert spec_from(OptimalLike()).end_tau == 2.0
+
+
+def test_discretizer_option_errors_mirror_reference():
+    const = M.SatelliteScale().get_normalized_constants()
+    f = M.Simulator.satellite_dynamics
+    x = np.ones((7, 3))
+    u = np.zeros((3, 3))
+    d = M.Discretizer(const, include_drag=True)
+    with pytest.raises(TypeError):                       # reference: 'NoneType' object is not callable
+        d.discretize(f, x, u, 1.0)
+    d = M.Discretizer(const)
+    with pytest.raises(NotImplementedError):
+        d.discretize(lambda *a, **k: None, x, u, 1.0)
+    d.ivp_solver = "DOP853"
+    with pytest.raises(NotImplementedError):
+        d.discretize(f, x, u, 1.0)
+    d = M.Discretizer(const)
+    assert (d.ivp_max_step, d.ivp_solver, d.integrator_steps, d.use_uniform_steps) == (1e-2, 'RK45', 101, False)
+
+
+def test_discretized_batch_views_have_reference_shapes_and_order():
+    N, K = 3, 5
+    n = N * (K - 1)
+    soa = np.arange(105 * n, dtype=np.float64).reshape(105, n)
+    b = batch.DiscretizedBatch(soa, np.zeros((N, K - 1), np.int32), N, K)
+    A, Bp, Bn, S, X = b.sat(1)
+    assert A.shape == (K - 1, 7, 7) and Bp.shape == (K - 1, 7, 3) and Bn.shape == (K - 1, 7, 3)
+    assert S.shape == (7, K - 1) and X.shape == (7, K - 1)
+    k, i, j = 2, 4, 5
+    col = 1 * (K - 1) + k
+    assert A[k, i, j] == soa[i * 7 + j, col]                 # model.A_k[s][k,i,j]   (optimizer.py:332)
+    assert Bp[k, i, 2] == soa[49 + i * 3 + 2, col]           # model.B_kp[s][k,i,j]  (optimizer.py:334)
+    assert Bn[k, i, 1] == soa[70 + i * 3 + 1, col]           # model.B_kn[s][k,i,j]  (optimizer.py:333)
+    assert S[i, k] == soa[91 + i, col] and X[i, k] == soa[98 + i, col]   # [i,k]     (optimizer.py:335-336)
+    assert A.base is not None                                 # views, not copies
+    As, Bps, Bns, Ss, Xs = b.stacked()
+    assert np.array_equal(As[1], A) and np.array_equal(Ss[1], S) and np.array_equal(Bns[1], Bn)
+
+
+def test_default_n_sub_matches_reference_max_step():
+    assert batch.default_n_sub(200) == 6 and batch.default_n_sub(1001) == 1 and batch.default_n_sub(2) == 1000
+    assert batch.default_n_sub(1) == 1 and batch.default_n_sub(500) == 3
+
+
+def test_host_dynamics_matches_oracle(gold_prop, const):
+    from oracle import mpc_oracle as O
+    y = gold_prop["p0_y"][:, 123]
+    uf = O.ctrl_tangential(0.3)
+    a = M.Simulator.satellite_dynamics(0.2, y, uf, 2.0, const, True, True)
+    b = O.dynamics(y, uf(y, 0.2), 2.0, const, True, True)
+    assert np.allclose(a, b, rtol=1e-14, atol=1e-18)
+    with pytest.raises(Exception, match="INVALID SATELLITE MASS"):
+        M.Simulator.satellite_dynamics(0.0, np.array([1, 0, 0, 0, 1, 0, -1.0]), uf, 1.0, const)

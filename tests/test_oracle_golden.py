@@ -1,0 +1,172 @@
+"""CPU: pins oracle/ against fixtures produced by the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import NAMES, rel_err
+from oracle import c_oracle as C
+from oracle import mpc_oracle as O
+
+# tolerance of the RK4-on-uniform-nodes restatement against the reference's use_uniform_steps=True mode
+# (<= 1e-8 norm-relative; the reference's own RK45 noise floor is ~1e-10)
+TOL_UNIFORM = 1e-8
+
+
+def _stack(res):
+    return (np.stack([r[0] for r in res]), np.stack([r[1] for r in res]), np.stack([r[2] for r in res]),
+            np.column_stack([r[3] for r in res]), np.column_stack([r[4] for r in res]))
+
+
+def _sel(o, ks):
+    return o[ks] if o.ndim == 3 else o[:, ks]
+
+
+@pytest.mark.parametrize("sc", ["d0", "d1", "d4"])
+@pytest.mark.parametrize("uniform", [False, True])
+def test_py_oracle_small_scenarios(gold_disc, const, sc, uniform):
+    """numpy/scipy restatement == reference, both quadrature modes (same library calls: ~1e-15)."""
+    g = gold_disc
+    out = O.discretize(g[sc + "_x"], g[sc + "_u"], float(g[sc + "_tf"]), const, use_uniform_steps=uniform)
+    tag = sc + ("_uni" if uniform else "_def")
+    for n, o in zip(NAMES, out):
+        assert rel_err(o, g[f"{tag}_{n}"]) < 1e-13, (tag, n)
+
+
+@pytest.mark.parametrize("tag,kw", [("d3_def", {}), ("d3_uni", dict(use_uniform_steps=True)),
+                                    ("d3_j2_uni", dict(use_uniform_steps=True, include_J2=True)),
+                                    ("d3_j2_def", dict(include_J2=True)),
+                                    ("d3_n21_uni", dict(use_uniform_steps=True, integrator_steps=21))])
+def test_py_oracle_tangential_sampled(gold_disc, const, tag, kw):
+    g = gold_disc
+    ks = [int(k) for k in g["d3_j2_ks"]][::4]
+    out = _stack([O.interval_matrices(k, g["d3_x"], g["d3_u"], 2.0, const, **kw) for k in ks])
+    full = tag in ("d3_def", "d3_uni")
+    for n, o in zip(NAMES, out):
+        ref = g[f"{tag}_{n}"]
+        ref = _sel(ref, ks) if full else _sel(ref, list(range(0, len(g["d3_j2_ks"]), 4)))
+        assert rel_err(o, ref) < 1e-13, (tag, n)
+
+
+def test_py_oracle_u_on_other_grid(gold_disc, const):
+    """the reference test's own malformed u (3,3K): FOH runs on u's grid (test_discretizer.py:103)"""
+    g = gold_disc
+    out = _stack([O.interval_matrices(int(k), g["d2_x"], g["d2q_u"], 1.0, const, use_uniform_steps=True)
+                  for k in g["d2q_ks"]])
+    for n, o in zip(NAMES, out):
+        assert rel_err(o, g[f"d2q_uni_{n}"]) < 1e-13
+
+
+@pytest.mark.parametrize("sc", ["d0", "d1", "d2", "d3", "d4"])
+def test_c_oracle_vs_reference_uniform(gold_disc, const, sc):
+    g = gold_disc
+    A, Bp, Bn, S, X, st = C.discretize_batch(g[sc + "_x"][None], g[sc + "_u"][None], float(g[sc + "_tf"]), const)
+    assert st.max() == 0
+    for n, o in zip(NAMES, (A[0], Bp[0], Bn[0], S[0], X[0])):
+        assert rel_err(o, g[f"{sc}_uni_{n}"]) < TOL_UNIFORM, (sc, n)
+
+
+def test_c_oracle_j2_and_other_node_count(gold_disc, const):
+    g = gold_disc
+    ks = g["d3_j2_ks"]
+    out = C.discretize_batch(g["d3_x"][None], g["d3_u"][None], 2.0, const, include_J2=True)
+    for n, o in zip(NAMES, out[:5]):
+        assert rel_err(_sel(o[0], ks), g[f"d3_j2_uni_{n}"]) < TOL_UNIFORM
+    out = C.discretize_batch(g["d3_x"][None], g["d3_u"][None], 2.0, const, n_sub=20)
+    for n, o in zip(NAMES, out[:5]):
+        assert rel_err(_sel(o[0], ks), g[f"d3_n21_uni_{n}"]) < TOL_UNIFORM
+
+
+def test_reference_default_mode_distance_is_its_own_quadrature_error(gold_disc, const):
+    """Documented, not gated: default-mode B+- sit ~1e-3 from the uniform-node answer."""
+    g = gold_disc
+    e = [rel_err(g[f"d3_def_{n}"], g[f"d3_uni_{n}"]) for n in NAMES]
+    assert e[0] < 1e-8 and 1e-4 < e[1] < 1e-2 and 1e-4 < e[2] < 1e-2 and e[3] < 1e-5 and e[4] < 1e-3
+
+
+def test_rollout_reproduces_reference_trajectory(gold_disc):
+    """the implicit check of test_discretizer.py:110-113 turned into assertions: the discrete model,
+    evaluated on its own reference trajectory, reproduces the nonlinear propagation.  Constant thrust is
+    exactly representable by the first-order hold (defect = integration error); the tangential law is not
+    (defect = FOH error of a state-dependent input, ~1e-6 per step at K=200)."""
+    g = gold_disc
+    for sc, step_tol, roll_tol in (("d2", 1e-6, 1e-5), ("d3", 1e-5, 2e-3)):
+        out = [g[f"{sc}_uni_{n}"] for n in NAMES]
+        x, u, tf = g[sc + "_x"], g[sc + "_u"], float(g[sc + "_tf"])
+        defect = max(np.max(np.abs(out[0][k] @ x[:, k] + out[2][k] @ u[:, k] + out[1][k] @ u[:, k + 1]
+                                   + out[3][:, k] * tf + out[4][:, k] - x[:, k + 1])) for k in range(x.shape[1] - 1))
+        assert defect < step_tol, (sc, defect)
+        xr = O.rollout(out[0], out[1], out[2], out[3], out[4], x[:, 0], u, tf)
+        assert rel_err(xr, x) < roll_tol, sc
+
+
+def test_constants_and_scaling(gold_disc):
+    g = gold_disc
+    sf = O.scale_factors(g["x0_dim"])
+    c = O.normalized_constants(sf)
+    got = np.array([c.MU, c.R_E, c.J2, c.G0, c.ISP, c.S, c.R0, c.RHO])
+    assert np.allclose(got, g["const"], rtol=1e-15, atol=0)
+    assert np.allclose([sf[k] for k in ("r0", "s0", "v0", "a0", "m0", "T0", "mu0")], g["scale"], rtol=1e-15)
+    y = O.normalize_state(g["x0_dim"], sf)
+    assert np.allclose(O.redim_state(y, sf), g["x0_dim"], rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------------- propagation
+
+def _y0(gp):
+    sf = O.scale_factors(gp["x0_dim"])
+    return O.normalize_state(gp["x0_dim"], sf), sf
+
+
+def test_py_oracle_propagation(gold_prop, const):
+    gp = gold_prop
+    y0, _ = _y0(gp)
+    y, t = O.propagate(y0, 2.0, O.ctrl_tangential(0.5), const, False, False, 200)
+    assert rel_err(y, gp["p1_y"]) < 1e-13 and np.array_equal(t, gp["p1_t"])
+    assert rel_err(O.extract_uk(y, t, O.ctrl_tangential(0.5)), gp["p1_u"]) < 1e-13
+    y, t = O.propagate(y0, 2.0, O.ctrl_sequence(gp["p5_u_tab"], 1.5, 2.0), const, False, False, 120)
+    assert rel_err(y, gp["p5_y"]) < 1e-13
+
+
+# fixed-step RK4 (h <= 1e-3 in tau) against the reference's RK45: <= 1e-6 required on propagated states
+@pytest.mark.parametrize("case", ["p0", "p1", "p2", "p4"])
+def test_c_oracle_propagation_vs_reference(gold_prop, const, case):
+    gp = gold_prop
+    y0, _ = _y0(gp)
+    kw = {"p0": dict(kind=C.CTRL_ZERO, T=500), "p1": dict(kind=C.CTRL_TANGENTIAL, cparams=(0.5, 0, 0), T=200, include_drag=False, include_J2=False),
+          "p2": dict(kind=C.CTRL_CONSTANT, cparams=gp["p2_thrust"], T=300), "p4": dict(kind=C.CTRL_TANGENTIAL, cparams=(0.1, 0, 0), T=200)}[case]
+    T = kw["T"]
+    y, u, st = C.propagate_batch(y0[None], float(gp[case + "_tf"]), const, n_sub=int(np.ceil(1000 / (T - 1))), **kw)
+    assert st[0] == 0
+    assert rel_err(y[0], gp[case + "_y"]) < 1e-6   # north_star tolerance on propagated states
+    if case == "p1":
+        assert rel_err(u[0], gp["p1_u"]) < 1e-7
+
+
+def test_c_oracle_three_perturbed_sats(gold_prop):
+    gp = gold_prop
+    c3 = O.OracleConstants(*gp["p3_const"])
+    sf = O.scale_factors(gp["p3_y0_dim"][0])
+    y0 = np.stack([O.normalize_state(y, sf) for y in gp["p3_y0_dim"]])
+    y, _, st = C.propagate_batch(y0, 5.0, c3, C.CTRL_ZERO, T=500, n_sub=3)
+    assert st.max() == 0 and rel_err(y, gp["p3_y"]) < 1e-6
+
+
+def test_c_oracle_sequence_controller(gold_prop, const):
+    """FOH kinks only (end_tau >= 1, as OptimalController uses it): RK4 agrees to <= 1e-6.  A table that ends
+    inside the run (end_tau < 1) is a jump discontinuity the reference itself integrates across with O(h)
+    error; there the two agree only to that error (documented in DESIGN.md)."""
+    gp = gold_prop
+    y0, _ = _y0(gp)
+    tab = gp["p5_u_tab"]
+    yr, _ = O.propagate(y0, 2.0, O.ctrl_sequence(tab, 2.0, 2.0), const, False, False, 120)
+    y, u, st = C.propagate_batch(y0[None], 2.0, const, C.CTRL_SEQUENCE, table=tab, end_tau=1.0, include_drag=False,
+                                 include_J2=False, T=120, n_sub=10)
+    assert st[0] == 0 and rel_err(y[0], yr) < 1e-6
+    y, u, st = C.propagate_batch(y0[None], 2.0, const, C.CTRL_SEQUENCE, table=tab, end_tau=0.75, include_drag=False,
+                                 include_J2=False, T=120, n_sub=10)
+    assert rel_err(y[0], gp["p5_y"]) < 5e-3 and rel_err(u[0], gp["p5_u"]) < 1e-12
+
+
+def test_c_oracle_mass_failure_flag(const):
+    y0 = np.array([[1.0, 0, 0, 0, 6.28, 0, 1e-3]])
+    y, _, st = C.propagate_batch(y0, 5.0, const, C.CTRL_CONSTANT, (5.0, 0, 0), T=50, n_sub=20)
+    assert st[0] == 1
