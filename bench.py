@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- discretized intervals/sec of the batched SCvx linearize-and-discretize hot path.
+
+Workload (BASELINE.json configs[2], the largest single-GPU configuration): 4096 satellites x K=200
+nodes (815,104 intervals), tangential thrust 0.5, tf=2.  One STEP = one SCP linearization pass over the
+batch: propagate every satellite (reference trajectory + extract_uk) then discretize every interval
+(integrator_steps=101: 100 RK4 steps + 101-node trapezoid per interval).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the reference algorithm on the host cores
+
+Under torchrun (N>1) every rank processes its own 4096-satellite shard (weak scaling) and the discretized
+matrices are all-gathered over NCCL/NVLink inside the timed step, as north_star asks.
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, >= 3 warm-up steps, L2 flushed
+between timed steps (256 MiB write), max over ranks, clocks sampled during the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HUBBLE = np.array([5371.4806e3, -4133.1393e3, 1399.9594e3, 4.6921e3, 4.9848e3, -3.2752e3, 12200.0])
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SM x 64 DFMA/clk x 2 flop x 1.965 GHz = 37.2
+
+
+def flops_per_interval(n_sub, include_j2=False):
+    """ALGORITHMIC FP64 work of one interval (FMA = 2 flop, mul/add = 1, rsqrt/rcp = 1), for the algorithm
+    as DESIGN.md states it (structure-exploiting formulation: 42 live Phi entries, symmetric G, symplectic
+    inverse).  Counted per RK4 step / per quadrature node / per interval epilogue; see DESIGN.md section 5."""
+    stage = 62 + (44 if include_j2 else 0)        # r^-3 powers, G (6 unique), a_g, u/m, d=-u/m^2 per RK stage
+    rk4_state = 4 * stage + 2 * 14 + 40           # + 2 thrust interpolations/norms, Nystrom combine of r,v,m
+    rk4_phi = 7 * (4 * 18 + 6 * 2 * 3 + 2 * 9 + 12)   # 7 columns x (4 G*p products + stage positions + combine)
+    node = 36 * 2 + 18 * 4 + 2 * 42 * 2 + 18 + 56 * 2  # e=-Phi6^-1 c, Q=Phi^-1 B, Phi^-1[Sigma xi], G r, 56 accumulators
+    epilogue = 6 * 7 * 8 * 2 + 64
+    return n_sub * (rk4_state + rk4_phi) + (n_sub + 1) * node + epilogue
+
+
+def bytes_per_interval():
+    return 13 * 8 + 105 * 8       # read x_k, u_k, u_k+1; write 105 doubles
+
+
+# ------------------------------------------------------------------------------------------ inputs
+
+def make_constellation(n_sats, seed=20240531):
+    """Hubble state rotated about z by 2*pi*i/N, speed scaled by 1+0.1*U[0,1), one scale from sat 0."""
+    import mpconstellation_b200 as M
+    scale = M.SatelliteScale(x=HUBBLE)
+    const = scale.get_normalized_constants()
+    y = scale.normalize_state(HUBBLE)
+    rng = np.random.default_rng(seed)
+    ang = 2 * np.pi * np.arange(n_sats) / max(n_sats, 1)
+    ca, sa = np.cos(ang), np.sin(ang)
+    f = 1 + 0.1 * rng.random(n_sats)
+    Y = np.tile(y, (n_sats, 1))
+    Y[:, 0], Y[:, 1] = ca * y[0] - sa * y[1], sa * y[0] + ca * y[1]
+    Y[:, 3], Y[:, 4] = (ca * y[3] - sa * y[4]) * f, (sa * y[3] + ca * y[4]) * f
+    Y[:, 5] = y[5] * f
+    return Y, const
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.02):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.reasons, self.max_mhz = period, [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+
+def cpu_port_baseline(n_sats, K, tf, n_sub, budget_s=12.0):
+    """oracle/mpc_oracle.c (plain-C port of the same RK4/trapezoid algorithm, OpenMP over intervals) on a
+    bounded sample of the workload: the first S satellites."""
+    from oracle import c_oracle as C
+    from oracle.mpc_oracle import OracleConstants
+    Y, const_m = make_constellation(n_sats)
+    const = OracleConstants(const_m.MU, const_m.R_E, const_m.J2, const_m.G0, const_m.ISP, const_m.S, const_m.R0, const_m.RHO)
+    cores = C.max_threads()
+    n_prop = max(1, int(np.ceil(1000 / (K - 1))))
+
+    def run(S):
+        t0 = time.perf_counter()
+        x, u, st = C.propagate_batch(Y[:S], tf, const, C.CTRL_TANGENTIAL, (0.5, 0, 0), include_drag=False,
+                                     include_J2=False, T=K, n_sub=n_prop)
+        out = C.discretize_batch(x, u, tf, const, n_sub=n_sub)
+        assert out[5].max() == 0
+        return time.perf_counter() - t0
+    S = min(n_sats, 2 * cores)
+    t = run(S)                                   # calibration (also warms the OpenMP pool)
+    S = int(min(n_sats, max(S, S * budget_s / max(t, 1e-3))))
+    t = run(S)
+    return {"value": S * (K - 1) / t, "unit": "intervals/s", "cores": cores, "kind": "port",
+            "sample": f"first {S} of {n_sats} satellites x {K-1} intervals (propagate + discretize, n_sub={n_sub}), "
+                      f"{t:.1f} s of oracle/mpc_oracle.c with OpenMP"}
+
+
+def reference_arm(args):
+    """--impl reference: the reference ALGORITHM (scipy RK45 + per-node numpy, one process pool over intervals
+    per discretize call, satellites looped serially -- linearize_discretize.py:334-390, optimizer.py:243-249,
+    simulator.py:41-45) restated in oracle/mpc_oracle.py, on all host cores, on a bounded sample per step.
+    The reference itself is pure Python and cannot travel to the GPU box; the restatement makes the same
+    library calls and is pinned to it bit-for-bit by tests/test_oracle_golden.py."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import mpc_oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sats, K, tf = args.sats, args.nodes, args.tf
+    sf = O.scale_factors(HUBBLE)
+    const = O.normalized_constants(sf)
+    Y, _ = make_constellation(n_sats)
+    cores = os.cpu_count() or 1
+    S = args.ref_sats
+    ctrl = O.ctrl_tangential(0.5)
+
+    def step():
+        for s in range(S):
+            x, t = O.propagate(Y[s], tf, ctrl, const, False, False, K)
+            u = O.extract_uk(x, t, ctrl)
+            O.discretize(x, u, tf, const, use_uniform_steps=True, integrator_steps=args.n_sub + 1, processes=cores)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = S * (K - 1) / dt
+    sample = (f"{S} of {n_sats} satellites x {K-1} intervals per step (propagate + discretize, use_uniform_steps=True, "
+              f"integrator_steps={args.n_sub + 1}), mp.Pool({cores}) per discretize call as the reference does")
+    print(json.dumps({
+        "impl": "reference", "metric": "discretized intervals/sec", "value": val, "unit": "intervals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": "intervals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args):
+    return {"workload": f"{args.sats} satellites x K={args.nodes} nodes ({args.sats * (args.nodes - 1)} intervals) per GPU: "
+                        "propagate (tangential thrust 0.5, no drag/J2) + discretize, BASELINE configs[2]",
+            "sats_per_gpu": args.sats, "K": args.nodes, "tf": args.tf, "integrator_steps": args.n_sub + 1,
+            "integrator": "fixed-step RK4, trapezoid on the RK4 nodes", "l2": "flushed between timed steps (256 MiB write)",
+            "parallelism": f"satellites sharded over {args.gpus} GPU(s)" + (", NCCL all-gather of the SoA matrices inside the step" if args.gpus > 1 else "")}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+def gpu_arm(args):
+    import torch
+    import mpconstellation_b200 as M
+    from mpconstellation_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_gpu()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    N, K, tf, n_sub = args.sats, args.nodes, args.tf, args.n_sub
+    n_int = N * (K - 1)
+    Y, const = make_constellation(N * world)
+    Y = Y[rank * N:(rank + 1) * N]
+    ctrl = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+
+    # ---- device-resident step --------------------------------------------------------------------
+    y0 = torch.from_numpy(Y).to(dev)
+    tfd = torch.full((N,), tf, dtype=torch.float64, device=dev)
+    x = torch.empty((N, 7, K), dtype=torch.float64, device=dev)
+    u = torch.empty((N, 3, K), dtype=torch.float64, device=dev)
+    stp = torch.empty(N, dtype=torch.int32, device=dev)
+    std = torch.empty(n_int, dtype=torch.int32, device=dev)
+    n_chunks = args.chunks if world > 1 else 1
+    cs = (N + n_chunks - 1) // n_chunks
+    out = torch.empty((105, n_int), dtype=torch.float64, device=dev)
+    gathered = [torch.empty((world, 105, min(cs, N - c * cs) * (K - 1)), dtype=torch.float64, device=dev)
+                for c in range(n_chunks)] if world > 1 else None
+    outs_c = [torch.empty((105, min(cs, N - c * cs) * (K - 1)), dtype=torch.float64, device=dev)
+              for c in range(n_chunks)] if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    n_prop = M.batch.default_n_sub(K)
+
+    def step(ev=None):
+        M.propagate_batch_device(y0, tfd, ctrl, const, include_drag=False, include_J2=False, T=K, n_sub=n_prop,
+                                 y=x, u_out=u, status=stp)
+        if ev is not None:
+            ev[0].record()
+        if world == 1:
+            M.discretize_batch_device(x, u, tfd, const, n_sub=n_sub, out=out, status=std)
+            if ev is not None:
+                ev[1].record()
+        else:
+            # chunked: all-gather of chunk c on the comm stream overlaps the discretization of chunk c+1
+            cur = torch.cuda.current_stream(dev)
+            for c in range(n_chunks):
+                s0, s1 = c * cs, min(N, (c + 1) * cs)
+                M.discretize_batch_device(x[s0:s1], u[s0:s1], tfd[s0:s1], const, n_sub=n_sub, out=outs_c[c],
+                                          status=std[s0 * (K - 1):s1 * (K - 1)])
+                done = torch.cuda.Event()
+                done.record(cur)
+                comm_stream.wait_event(done)
+                with torch.cuda.stream(comm_stream):
+                    dist.all_gather_into_tensor(gathered[c], outs_c[c])
+            if ev is not None:
+                ev[1].record()
+            cur.wait_stream(comm_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    assert int(stp.max()) == 0 and int(std.max()) == 0, "device status flags set"
+    peak_tflops, _ = M.fp64_peak_tflops(local, repeats=5)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = M.launch_count()
+    step_ms, disc_ms = [], []
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        barrier()
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        e0.record()
+        step((e1, e2))
+        e3.record()
+        torch.cuda.synchronize(dev)
+        step_ms.append(e0.elapsed_time(e3))
+        disc_ms.append(e1.elapsed_time(e2))
+    launches = M.launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = float(np.sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms, float(np.sum(disc_ms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, disc_total = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    else:
+        disc_total = float(np.sum(disc_ms))
+    ms_per_step = total_ms / args.steps
+    value = world * n_int / (ms_per_step * 1e-3)
+    disc_ms_avg = disc_total / args.steps
+
+    # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside the timed region) --
+    y0_h = M.pinned_empty((N, 7))
+    y0_h[:] = Y
+    out_h = M.pinned_empty((105, n_int))
+    y_h = M.pinned_empty((N, 7, K))
+    u_h = M.pinned_empty((N, 3, K))
+    e2e_t = []
+    for i in range(2 + max(3, args.steps // 2)):
+        barrier()
+        t0 = time.perf_counter()
+        res, _, _ = M.propagate_discretize(y0_h, tf, ctrl, const, T=K, n_sub_prop=n_prop, n_sub_disc=n_sub, out=out_h,
+                                           y_out=y_h, u_out=u_h, device=local)
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            e2e_t.append(dt)
+    e2e_s = float(np.mean(e2e_t))
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    # parity spot check inside the bench: device-resident result == host-API result
+    same = bool(np.array_equal(out_h[:, :K - 1], (out if world == 1 else outs_c[0]).cpu().numpy()[:, :K - 1]))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    fl = flops_per_interval(n_sub)
+    achieved_tflops = fl * n_int / (disc_ms_avg * 1e-3) / 1e12
+    cpu = cpu_port_baseline(N, K, tf, n_sub) if not args.no_cpu_baseline else None
+    line = {
+        "metric": "discretized intervals/sec", "value": value, "unit": "intervals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": world * n_int / e2e_s, "unit": "intervals/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(y0_h.nbytes + N * 8),
+                "d2h_bytes_per_step": int(out_h.nbytes + y_h.nbytes + u_h.nbytes + n_int * 4),
+                "api": "mpconstellation_b200.propagate_discretize (C-ABI mpc_propagate_discretize_host), pinned host buffers",
+                "matches_device_path": same},
+        "gpu_launches": int(launches),
+        "kernel": {"discretize_ms": disc_ms_avg, "propagate_ms": ms_per_step - disc_ms_avg if world == 1 else None,
+                   "discretize_intervals_per_s_per_gpu": n_int / (disc_ms_avg * 1e-3)},
+        "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                     "frac": achieved_tflops / peak_tflops, "traffic": None,
+                     "peak_source": "DFMA-chain microbenchmark (mpc_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
+                     "peak_nominal": FP64_NOMINAL_TFLOPS, "flop_per_interval": fl,
+                     "kernel": "mpc::discretize_kernel",
+                     "hbm": {"achieved": bytes_per_interval() * n_int / (disc_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "peak_source": hbm_src, "bytes_per_interval": bytes_per_interval()}},
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sats", type=int, default=4096, help="satellites per GPU")
+    ap.add_argument("--nodes", type=int, default=200, help="K temporal nodes")
+    ap.add_argument("--tf", type=float, default=2.0)
+    ap.add_argument("--n-sub", dest="n_sub", type=int, default=100, help="RK4 steps per interval (integrator_steps-1)")
+    ap.add_argument("--chunks", type=int, default=8, help="compute/all-gather overlap chunks (N>1)")
+    ap.add_argument("--ref-sats", dest="ref_sats", type=int, default=2, help="satellites per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,14 +57,12 @@ __device__ __forceinline__ double fast_rcp(double a)
 
 __device__ __forceinline__ double fast_rsqrt(double a)
 {
-    // reciprocal square root: MUFU.RSQ64H seed (~20 bits) + 2 Newton steps, then one cheap
-    // correction so the result is good to ~1 ulp (a > 0, normal range)
+    // reciprocal square root: MUFU.RSQ64H seed (~20 bits) + 2 Newton steps: relative error
+    // 1.5 e^2 per step -> 2^-40 -> 2^-79, i.e. rounding-limited (a > 0, normal range)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     const double h = 0.5 * a;
     double e = fma(-h * y, y, 0.5);  // 0.5 - 0.5 a y^2
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
     y = fma(y, e, y);
     e = fma(-h * y, y, 0.5);
     y = fma(y, e, y);
@@ -193,7 +191,9 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     const long long n_int = (long long)n_sats * (K - 1);
     const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (gid >= n_int) return;
-    double *acc = acc_smem + threadIdx.x;
+    // volatile: keep the accumulators IN shared memory (the compiler would otherwise promote these
+    // thread-private slots to registers and spill them to local memory, which is write-through to L2)
+    volatile double *acc = acc_smem + threadIdx.x;
 #define ACC(e) acc[(e) * BLOCK]
 
     const int s = (int)(gid / (K - 1));
@@ -362,10 +362,6 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             s4.dy = -qy * i4;
             s4.dz = -qz * i4;
         }
-        // ---- variational columns ----------------------------------------------------------------
-#pragma unroll
-        for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
-        column_step<true>(pr[6], pv[6], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
         // ---- state update -------------------------------------------------------------------------
         {
             const double wx = a2x + a3x, wy = a2y + a3y, wz = a2z + a3z;
@@ -378,6 +374,10 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             vz = fma(hs_6, (sz + wz) + a4z, vz);
             m = fma(hs_6, fma(4.0, mdm, md1) + mde, m);
         }
+        // ---- variational columns ----------------------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
+        column_step<true>(pr[6], pv[6], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
         ux = uex;
         uy = uey;
         uz = uez;

@@ -155,8 +155,8 @@ def test_edge_shapes_and_mass_failure(M, const):
     y0 = y0.copy()
     y0[1, 6] = 1e-3
     with pytest.raises(Exception, match="INVALID SATELLITE MASS"):
-        M.propagate_batch(y0, 5.0, M.ConstantThrustController(thrust=np.array([5.0, 0, 0])), const, T=50)
-    y, u, t, st = M.propagate_batch(y0, 5.0, M.ConstantThrustController(thrust=np.array([5.0, 0, 0])), const, T=50, check=False)
+        M.propagate_batch(y0, 5.0, M.ConstantThrustController(thrust=np.array([0.05, 0, 0])), const, T=50)
+    y, u, t, st = M.propagate_batch(y0, 5.0, M.ConstantThrustController(thrust=np.array([0.05, 0, 0])), const, T=50, check=False)
     assert list(st) == [0, 1, 0] and np.all(np.isfinite(y[0])) and np.any(np.isnan(y[1]))
 
 
