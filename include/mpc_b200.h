@@ -179,6 +179,10 @@ int mpc_fp64_peak_probe(int device, int repeats, double *tflops, double *ms);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches evidence). */
 int64_t mpc_launch_count(void);
 
+/* Experiment knob: selects an alternative block-size / register-cap build of the discretization kernel
+ * (0 = production).  Results are identical; only occupancy differs.  See DESIGN.md, tuning table. */
+int mpc_set_tuning(int variant);
+
 #ifdef __cplusplus
 }
 #endif

@@ -181,8 +181,8 @@ struct DstTab {  // destination buffers of the (optionally multi-destination) So
     double *p[kMaxDst];
 };
 
-template <bool J2, int BLOCK, int NDST>
-__global__ void __launch_bounds__(BLOCK)
+template <bool J2, int BLOCK, int MINB, int NDST>
+__global__ void __launch_bounds__(BLOCK, MINB)
 discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ tf_arr,
                   DiscParams P, int n_sats, int K, int n_sub, DstTab dst, long long pitch, long long offset,
                   int32_t *__restrict__ status)
@@ -253,58 +253,81 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             const double sfrac = (double)n * inv_n;                     // lambda+   (:61)
             const double w = (n == 0 || n == n_sub) ? 0.5 : 1.0;        // trapezoid end weights (:77-80)
             const double ws = w * sfrac;
-            // e = -Phi6^-1 c (c = column 6): e_top[a] = pr[3+a].cv - pv[3+a].cr ; e_bot[a] = pv[a].cr - pr[a].cv
-            double et[3], eb[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                et[a] = fma(pr[3 + a][0], pv[6][0], fma(pr[3 + a][1], pv[6][1], pr[3 + a][2] * pv[6][2]));
-                et[a] = fma(-pv[3 + a][0], pr[6][0], fma(-pv[3 + a][1], pr[6][1], fma(-pv[3 + a][2], pr[6][2], et[a])));
-                eb[a] = fma(pv[a][0], pr[6][0], fma(pv[a][1], pr[6][1], pv[a][2] * pr[6][2]));
-                eb[a] = fma(-pr[a][0], pv[6][0], fma(-pr[a][1], pv[6][1], fma(-pr[a][2], pv[6][2], eb[a])));
-            }
             // Duf = [0; I/m; b^T],  b = -u / (G0 ISP |u|)  (0 when |u| <= eps)      (:200-212)
             const double bs = -P.inv_ve * iun;
             const double b[3] = {bs * ux, bs * uy, bs * uz};
-            // Q = Phi^-1 Duf: rows 0..2: -pr[3+a][j]/m + b_j et[a]; rows 3..5: pr[a][j]/m + b_j eb[a]; row 6: b_j
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const double qt = fma(b[j], et[a], -im * pr[3 + a][j]);
-                    const double qb = fma(b[j], eb[a], im * pr[a][j]);
-                    ACC(a * 3 + j) = fma(w, qt, ACC(a * 3 + j));
-                    ACC(18 + a * 3 + j) = fma(ws, qt, ACC(18 + a * 3 + j));
-                    ACC(9 + a * 3 + j) = fma(w, qb, ACC(9 + a * 3 + j));
-                    ACC(27 + a * 3 + j) = fma(ws, qb, ACC(27 + a * 3 + j));
-                }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                ACC(48 + j) = fma(w, b[j], ACC(48 + j));
-                ACC(51 + j) = fma(ws, b[j], ACC(51 + j));
-            }
             // Sigma = f(tf=1) = [v; a; mdot] (:252-253);  xi' = -[v; G r; mdot_B] with mdot_B the
             // (Duf u) last row, which is 0 under the eps guard
             const double mdb = (iun != 0.0) ? md1 : 0.0;
-            const double wS[7] = {vx, vy, vz, a1x, a1y, a1z, md1};
-            const double wX[7] = {-vx, -vy, -vz, -grx, -gry, -grz, -mdb};
-            // Phi^-1 w = [Phi6^-1 w6 + e wm ; wm];  Phi6^-1 w6: top[a] = pv[3+a].wr - pr[3+a].wv, bot[a] = pr[a].wv - pv[a].wr
+            // Row pairs: column 3+a of Phi gives row a of every Phi^-1 product, column a gives row 3+a
+            //   e = -Phi6^-1 c (c = column 6):  et[a] = pr[3+a].cv - pv[3+a].cr ,  eb[a] = pv[a].cr - pr[a].cv
+            //   Q = Phi^-1 Duf:   row a: -pr[3+a][j]/m + b_j et[a] ;  row 3+a: pr[a][j]/m + b_j eb[a]
+            //   Phi^-1 w = [Phi6^-1 w6 + e wm ; wm] :  row a: pv[3+a].wr - pr[3+a].wv ;  row 3+a: pr[a].wv - pv[a].wr
+            // The 16 accumulators of a row pair are loaded together, updated, stored together (the volatile
+            // accesses keep program order, so grouping them exposes one shared-memory latency per group).
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                double st = fma(pv[3 + a][0], wS[0], fma(pv[3 + a][1], wS[1], fma(pv[3 + a][2], wS[2], et[a] * wS[6])));
-                st = fma(-pr[3 + a][0], wS[3], fma(-pr[3 + a][1], wS[4], fma(-pr[3 + a][2], wS[5], st)));
-                double sb = fma(pr[a][0], wS[3], fma(pr[a][1], wS[4], fma(pr[a][2], wS[5], eb[a] * wS[6])));
-                sb = fma(-pv[a][0], wS[0], fma(-pv[a][1], wS[1], fma(-pv[a][2], wS[2], sb)));
-                ACC(36 + a) = fma(w, st, ACC(36 + a));
-                ACC(39 + a) = fma(w, sb, ACC(39 + a));
-                double xt = fma(pv[3 + a][0], wX[0], fma(pv[3 + a][1], wX[1], fma(pv[3 + a][2], wX[2], et[a] * wX[6])));
-                xt = fma(-pr[3 + a][0], wX[3], fma(-pr[3 + a][1], wX[4], fma(-pr[3 + a][2], wX[5], xt)));
-                double xb = fma(pr[a][0], wX[3], fma(pr[a][1], wX[4], fma(pr[a][2], wX[5], eb[a] * wX[6])));
-                xb = fma(-pv[a][0], wX[0], fma(-pv[a][1], wX[1], fma(-pv[a][2], wX[2], xb)));
-                ACC(42 + a) = fma(w, xt, ACC(42 + a));
-                ACC(45 + a) = fma(w, xb, ACC(45 + a));
+                double A0t[3], A1t[3], A0b[3], A1b[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    A0t[j] = ACC(a * 3 + j);
+                    A1t[j] = ACC(18 + a * 3 + j);
+                    A0b[j] = ACC(9 + a * 3 + j);
+                    A1b[j] = ACC(27 + a * 3 + j);
+                }
+                double ASt = ACC(36 + a), ASb = ACC(39 + a), AXt = ACC(42 + a), AXb = ACC(45 + a);
+                double et = fma(pr[3 + a][0], pv[6][0], fma(pr[3 + a][1], pv[6][1], pr[3 + a][2] * pv[6][2]));
+                et = fma(-pv[3 + a][0], pr[6][0], fma(-pv[3 + a][1], pr[6][1], fma(-pv[3 + a][2], pr[6][2], et)));
+                double eb = fma(pv[a][0], pr[6][0], fma(pv[a][1], pr[6][1], pv[a][2] * pr[6][2]));
+                eb = fma(-pr[a][0], pv[6][0], fma(-pr[a][1], pv[6][1], fma(-pr[a][2], pv[6][2], eb)));
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const double qt = fma(b[j], et, -im * pr[3 + a][j]);
+                    const double qb = fma(b[j], eb, im * pr[a][j]);
+                    A0t[j] = fma(w, qt, A0t[j]);
+                    A1t[j] = fma(ws, qt, A1t[j]);
+                    A0b[j] = fma(w, qb, A0b[j]);
+                    A1b[j] = fma(ws, qb, A1b[j]);
+                }
+                // the v-part of Sigma and xi' differ only in sign: share the dot products with v
+                const double dvt = fma(pv[3 + a][0], vx, fma(pv[3 + a][1], vy, pv[3 + a][2] * vz));
+                const double dvb = fma(pv[a][0], vx, fma(pv[a][1], vy, pv[a][2] * vz));
+                const double st = fma(-pr[3 + a][0], a1x, fma(-pr[3 + a][1], a1y, fma(-pr[3 + a][2], a1z, fma(et, md1, dvt))));
+                const double xt = fma(pr[3 + a][0], grx, fma(pr[3 + a][1], gry, fma(pr[3 + a][2], grz, -fma(et, mdb, dvt))));
+                const double sb = fma(pr[a][0], a1x, fma(pr[a][1], a1y, fma(pr[a][2], a1z, fma(eb, md1, -dvb))));
+                const double xb = fma(-pr[a][0], grx, fma(-pr[a][1], gry, fma(-pr[a][2], grz, fma(-eb, mdb, dvb))));
+                ASt = fma(w, st, ASt);
+                ASb = fma(w, sb, ASb);
+                AXt = fma(w, xt, AXt);
+                AXb = fma(w, xb, AXb);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    ACC(a * 3 + j) = A0t[j];
+                    ACC(18 + a * 3 + j) = A1t[j];
+                    ACC(9 + a * 3 + j) = A0b[j];
+                    ACC(27 + a * 3 + j) = A1b[j];
+                }
+                ACC(36 + a) = ASt;
+                ACC(39 + a) = ASb;
+                ACC(42 + a) = AXt;
+                ACC(45 + a) = AXb;
             }
-            ACC(54) = fma(w, wS[6], ACC(54));
-            ACC(55) = fma(w, wX[6], ACC(55));
+            {   // row 6: Phi^-1 row 6 = e7^T, so the integrands are the last rows of Duf, Sigma, xi'
+                double m0[3], m1[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    m0[j] = ACC(48 + j);
+                    m1[j] = ACC(51 + j);
+                }
+                double mS = ACC(54), mX = ACC(55);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    ACC(48 + j) = fma(w, b[j], m0[j]);
+                    ACC(51 + j) = fma(ws, b[j], m1[j]);
+                }
+                ACC(54) = fma(w, md1, mS);
+                ACC(55) = fma(-w, mdb, mX);
+            }
         }
         if (n == n_sub) break;
 

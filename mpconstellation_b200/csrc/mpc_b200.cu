@@ -59,26 +59,51 @@ mpc::PropParams prop_params(const mpc_params *p)
     return d;
 }
 
-template <bool J2, int NDST>
-int launch_disc_n(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
-                  int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
-                  cudaStream_t st)
+std::atomic<int> g_tuning{0};
+
+template <bool J2, int BLOCK, int MINB, int NDST>
+int launch_disc_cfg(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                    int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                    cudaStream_t st)
 {
-    auto kern = mpc::discretize_kernel<J2, kDiscBlock, NDST>;
-    const size_t smem = (size_t)mpc::kAccSlots * kDiscBlock * sizeof(double);
+    auto kern = mpc::discretize_kernel<J2, BLOCK, MINB, NDST>;
+    const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (configured_dev != dev) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured_dev = dev;
     }
     const long long n_int = (long long)n_sats * (K - 1);
-    const unsigned grid = (unsigned)((n_int + kDiscBlock - 1) / kDiscBlock);
-    kern<<<grid, kDiscBlock, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+    const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
+}
+
+// The production configuration plus the experimental ones mpc_set_tuning() selects (single destination,
+// no J2 only: they exist to measure occupancy / register-cap trade-offs).
+template <bool J2, int NDST>
+int launch_disc_n(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                  int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                  cudaStream_t st)
+{
+#define MPC_ARGS x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, st
+    if (!J2 && NDST == 1) {
+        switch (g_tuning.load(std::memory_order_relaxed)) {
+            case 1: return launch_disc_cfg<false, 64, 5, 1>(MPC_ARGS);
+            case 2: return launch_disc_cfg<false, 64, 6, 1>(MPC_ARGS);
+            case 3: return launch_disc_cfg<false, 32, 9, 1>(MPC_ARGS);
+            case 4: return launch_disc_cfg<false, 64, 4, 1>(MPC_ARGS);
+            case 5: return launch_disc_cfg<false, 32, 11, 1>(MPC_ARGS);
+            default: break;
+        }
+    }
+    return launch_disc_cfg<J2, kDiscBlock, 2, NDST>(MPC_ARGS);
+#undef MPC_ARGS
 }
 
 template <bool J2>
@@ -253,6 +278,13 @@ int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc
 }
 
 int64_t mpc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int mpc_set_tuning(int variant)
+{
+    if (variant < 0 || variant > 5) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);
+    g_tuning.store(variant);
+    return MPC_SUCCESS;
+}
 
 int mpc_discretize_batch(const double *x, const double *u, const double *tf, const mpc_params *p, int n_sats,
                          int K, int n_sub, double *out, int64_t out_pitch, int64_t out_offset, int32_t *status,
