@@ -32,15 +32,19 @@ FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SM x 64 DFMA/clk 
 
 
 def flops_per_interval(n_sub, include_j2=False):
-    """ALGORITHMIC FP64 work of one interval (FMA = 2 flop, mul/add = 1, rsqrt/rcp = 1), for the algorithm
-    as DESIGN.md states it (structure-exploiting formulation: 42 live Phi entries, symmetric G, symplectic
-    inverse).  Counted per RK4 step / per quadrature node / per interval epilogue; see DESIGN.md section 5."""
-    stage = 62 + (44 if include_j2 else 0)        # r^-3 powers, G (6 unique), a_g, u/m, d=-u/m^2 per RK stage
-    rk4_state = 4 * stage + 2 * 14 + 40           # + 2 thrust interpolations/norms, Nystrom combine of r,v,m
-    rk4_phi = 7 * (4 * 18 + 6 * 2 * 3 + 2 * 9 + 12)   # 7 columns x (4 G*p products + stage positions + combine)
-    node = 36 * 2 + 18 * 4 + 2 * 42 * 2 + 18 + 56 * 2  # e=-Phi6^-1 c, Q=Phi^-1 B, Phi^-1[Sigma xi], G r, 56 accumulators
-    epilogue = 6 * 7 * 8 * 2 + 64
-    return n_sub * (rk4_state + rk4_phi) + (n_sub + 1) * node + epilogue
+    """ALGORITHMIC FP64 work of one interval: the arithmetic of the algorithm DESIGN.md section 5 states
+    (42 live Phi entries, symmetric G, Nystrom-form RK4, symplectic inverse, 56 accumulators), FMA = 2 flop,
+    mul/add = 1, MUFU seeds not counted.  One thread does one interval with no recomputation, so this equals
+    the executed DFMA/DMUL/DADD count: per RK4 step + quadrature node 582 FMA + 221 mul + 98 add (J2: 630 /
+    281 / 119), plus ~800 flop for the last node and the Phi_end * [integrals] epilogue.  Cross-checked
+    against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/r01_c: 149.1 kflop)."""
+    per_step = (2 * 630 + 281 + 119) if include_j2 else (2 * 582 + 221 + 98)
+    return n_sub * per_step + 800
+
+
+def fp64_instr_per_interval(n_sub, include_j2=False):
+    """FP64-pipe instructions (DFMA+DMUL+DADD) per interval: the pipe-occupancy view of the same work."""
+    return n_sub * ((630 + 281 + 119) if include_j2 else (582 + 221 + 98)) + 500
 
 
 def bytes_per_interval():
@@ -347,6 +351,8 @@ def gpu_arm(args):
                      "frac": achieved_tflops / peak_tflops, "traffic": None,
                      "peak_source": "DFMA-chain microbenchmark (mpc_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
                      "peak_nominal": FP64_NOMINAL_TFLOPS, "flop_per_interval": fl,
+                     "fp64_pipe_frac": fp64_instr_per_interval(n_sub) * n_int / (disc_ms_avg * 1e-3) / (peak_tflops * 1e12 / 2),
+                     "fp64_pipe_note": "FP64 instructions issued / (measured DFMA issue rate): DMUL/DADD occupy a DFMA slot but count 1 flop",
                      "kernel": "mpc::discretize_kernel",
                      "hbm": {"achieved": bytes_per_interval() * n_int / (disc_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "peak_source": hbm_src, "bytes_per_interval": bytes_per_interval()}},

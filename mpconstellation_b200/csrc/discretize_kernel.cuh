@@ -181,8 +181,8 @@ struct DstTab {  // destination buffers of the (optionally multi-destination) So
     double *p[kMaxDst];
 };
 
-template <bool J2, int BLOCK, int MINB, int NDST>
-__global__ void __launch_bounds__(BLOCK, MINB)
+template <bool J2, int BLOCK, int MAXREG, int NDST>
+__global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG)
 discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ tf_arr,
                   DiscParams P, int n_sats, int K, int n_sub, DstTab dst, long long pitch, long long offset,
                   int32_t *__restrict__ status)
@@ -398,9 +398,10 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             m = fma(hs_6, fma(4.0, mdm, md1) + mde, m);
         }
         // ---- variational columns ----------------------------------------------------------------
+        // the mass column first: its forcing terms d1..d4 are dead for the remaining six columns
+        column_step<true>(pr[6], pv[6], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
 #pragma unroll
         for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
-        column_step<true>(pr[6], pv[6], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
         ux = uex;
         uy = uey;
         uz = uez;

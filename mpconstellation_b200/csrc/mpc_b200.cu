@@ -61,12 +61,12 @@ mpc::PropParams prop_params(const mpc_params *p)
 
 std::atomic<int> g_tuning{0};
 
-template <bool J2, int BLOCK, int MINB, int NDST>
+template <bool J2, int BLOCK, int MAXREG, int NDST>
 int launch_disc_cfg(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                     int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
                     cudaStream_t st)
 {
-    auto kern = mpc::discretize_kernel<J2, BLOCK, MINB, NDST>;
+    auto kern = mpc::discretize_kernel<J2, BLOCK, MAXREG, NDST>;
     const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -94,15 +94,19 @@ int launch_disc_n(const double *x, const double *u, const double *tf, const mpc:
 #define MPC_ARGS x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, st
     if (!J2 && NDST == 1) {
         switch (g_tuning.load(std::memory_order_relaxed)) {
-            case 1: return launch_disc_cfg<false, 64, 5, 1>(MPC_ARGS);
-            case 2: return launch_disc_cfg<false, 64, 6, 1>(MPC_ARGS);
-            case 3: return launch_disc_cfg<false, 32, 9, 1>(MPC_ARGS);
-            case 4: return launch_disc_cfg<false, 64, 4, 1>(MPC_ARGS);
-            case 5: return launch_disc_cfg<false, 32, 11, 1>(MPC_ARGS);
+            case 1: return launch_disc_cfg<false, 32, 224, 1>(MPC_ARGS);   //  9 warps / SM
+            case 2: return launch_disc_cfg<false, 64, 200, 1>(MPC_ARGS);   // 10 warps / SM
+            case 3: return launch_disc_cfg<false, 32, 184, 1>(MPC_ARGS);   // 11 warps / SM
+            case 4: return launch_disc_cfg<false, 64, 168, 1>(MPC_ARGS);   // 12 warps / SM
+            case 5: return launch_disc_cfg<false, 64, 255, 1>(MPC_ARGS);   //  8 warps / SM, smaller CTAs
             default: break;
         }
     }
-    return launch_disc_cfg<J2, kDiscBlock, 2, NDST>(MPC_ARGS);
+    // Small batches (BASELINE configs 1-2: 49 ... 6,336 intervals) cannot fill 148 SMs with 128-thread CTAs:
+    // one-warp CTAs spread them over as many SMs as possible (same code, 224-register build, 9 CTAs/SM).
+    if (NDST == 1 && (long long)n_sats * (K - 1) < 148LL * 9 * 32 * 2)
+        return launch_disc_cfg<J2, 32, 224, 1>(MPC_ARGS);
+    return launch_disc_cfg<J2, kDiscBlock, 255, NDST>(MPC_ARGS);
 #undef MPC_ARGS
 }
 
