@@ -191,7 +191,7 @@ def workload_config(args):
                         "propagate (tangential thrust 0.5, no drag/J2) + discretize, BASELINE configs[2]",
             "sats_per_gpu": args.sats, "K": args.nodes, "tf": args.tf, "integrator_steps": args.n_sub + 1,
             "integrator": "fixed-step RK4, trapezoid on the RK4 nodes", "l2": "flushed between timed steps (256 MiB write)",
-            "parallelism": f"satellites sharded over {args.gpus} GPU(s)" + (", NCCL all-gather of the SoA matrices inside the step" if args.gpus > 1 else "")}
+            "parallelism": f"satellites sharded over {args.gpus} GPU(s)" + (f", all-gather of the SoA matrices inside the step ({args.gather})" if args.gpus > 1 else "")}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -223,16 +223,25 @@ def gpu_arm(args):
     u = torch.empty((N, 3, K), dtype=torch.float64, device=dev)
     stp = torch.empty(N, dtype=torch.int32, device=dev)
     std = torch.empty(n_int, dtype=torch.int32, device=dev)
-    n_chunks = args.chunks if world > 1 else 1
-    cs = (N + n_chunks - 1) // n_chunks
-    out = torch.empty((105, n_int), dtype=torch.float64, device=dev)
-    gathered = [torch.empty((world, 105, min(cs, N - c * cs) * (K - 1)), dtype=torch.float64, device=dev)
-                for c in range(n_chunks)] if world > 1 else None
-    outs_c = [torch.empty((105, min(cs, N - c * cs) * (K - 1)), dtype=torch.float64, device=dev)
-              for c in range(n_chunks)] if world > 1 else None
+    out = torch.empty((105, n_int), dtype=torch.float64, device=dev) if world == 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
     n_prop = M.batch.default_n_sub(K)
+    fused = None
+    gather_mode = "none"
+    if world > 1:
+        from mpconstellation_b200 import distributed as D
+        gather_mode = args.gather
+        if gather_mode == "fused":
+            try:
+                fused = D.FusedGather(N * world, K, device=dev)
+            except Exception as exc:            # no peer mapping on this box: fall back to the NCCL baseline
+                if rank == 0:
+                    print(f"[bench] symmetric memory unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
+                gather_mode = "nccl"
+        if gather_mode == "nccl":
+            local = torch.empty((105, n_int), dtype=torch.float64, device=dev)
+            comm_stream = torch.cuda.Stream(dev)
+            col_chunk = ((N + args.chunks - 1) // args.chunks) * (K - 1)
 
     def step(ev=None):
         M.propagate_batch_device(y0, tfd, ctrl, const, include_drag=False, include_J2=False, T=K, n_sub=n_prop,
@@ -241,23 +250,18 @@ def gpu_arm(args):
             ev[0].record()
         if world == 1:
             M.discretize_batch_device(x, u, tfd, const, n_sub=n_sub, out=out, status=std)
-            if ev is not None:
-                ev[1].record()
+        elif fused is not None:
+            # the kernel stores every result into all ranks' gathered buffers (peer stores over NVLink)
+            fused.discretize(x, u, tfd, const, n_sub=n_sub, barrier=True)
         else:
-            # chunked: all-gather of chunk c on the comm stream overlaps the discretization of chunk c+1
-            cur = torch.cuda.current_stream(dev)
-            for c in range(n_chunks):
-                s0, s1 = c * cs, min(N, (c + 1) * cs)
-                M.discretize_batch_device(x[s0:s1], u[s0:s1], tfd[s0:s1], const, n_sub=n_sub, out=outs_c[c],
-                                          status=std[s0 * (K - 1):s1 * (K - 1)])
-                done = torch.cuda.Event()
-                done.record(cur)
-                comm_stream.wait_event(done)
-                with torch.cuda.stream(comm_stream):
-                    dist.all_gather_into_tensor(gathered[c], outs_c[c])
-            if ev is not None:
-                ev[1].record()
-            cur.wait_stream(comm_stream)
+            def produce(c0, c1):
+                s0, s1 = c0 // (K - 1), c1 // (K - 1)
+                M.discretize_batch_device(x[s0:s1], u[s0:s1], tfd[s0:s1], const, n_sub=n_sub, out=local,
+                                          out_offset=c0, status=std[c0:c1])
+            step.gathered = D.nccl_gather_chunks(local, args.chunks, side_stream=comm_stream, produce=produce,
+                                                 chunk_cols=col_chunk)
+        if ev is not None:
+            ev[1].record()
 
     def barrier():
         if dist is not None:
@@ -267,7 +271,7 @@ def gpu_arm(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    assert int(stp.max()) == 0 and int(std.max()) == 0, "device status flags set"
+    assert int(stp.max()) == 0 and int((fused.status if fused is not None else std).max()) == 0, "device status flags set"
     peak_tflops, _ = M.fp64_peak_tflops(local, repeats=5)
     sampler = ClockSampler(local)
     sampler.start()
@@ -320,7 +324,21 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     # parity spot check inside the bench: device-resident result == host-API result
-    same = bool(np.array_equal(out_h[:, :K - 1], (out if world == 1 else outs_c[0]).cpu().numpy()[:, :K - 1]))
+    if world == 1:
+        dev_cols = out[:, :K - 1]
+    elif fused is not None:
+        dev_cols = fused.buf[:, rank * n_int:rank * n_int + K - 1]
+    else:
+        dev_cols = local[:, :K - 1]
+    same = bool(np.array_equal(out_h[:, :K - 1], dev_cols.cpu().numpy()))
+    gathered_ok = None
+    if fused is not None:
+        # every rank must hold every other rank's block: compare a column of each peer block with its owner
+        probe = torch.stack([fused.buf[:, r * n_int + 7] for r in range(world)])
+        mine = fused.buf[:, rank * n_int + 7].clone()
+        allm = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        gathered_ok = bool(all(torch.equal(probe[r], allm[r]) for r in range(world)))
 
     if rank != 0:
         if dist is not None:
@@ -344,6 +362,8 @@ def gpu_arm(args):
                 "d2h_bytes_per_step": int(out_h.nbytes + y_h.nbytes + u_h.nbytes + n_int * 4),
                 "api": "mpconstellation_b200.propagate_discretize (C-ABI mpc_propagate_discretize_host), pinned host buffers",
                 "matches_device_path": same},
+        "gather": {"mode": gather_mode, "verified": gathered_ok,
+                   "bytes_received_per_rank_per_step": int((world - 1) * n_int * 105 * 8)} if world > 1 else None,
         "gpu_launches": int(launches),
         "kernel": {"discretize_ms": disc_ms_avg, "propagate_ms": ms_per_step - disc_ms_avg if world == 1 else None,
                    "discretize_intervals_per_s_per_gpu": n_int / (disc_ms_avg * 1e-3)},
@@ -375,7 +395,9 @@ def main():
     ap.add_argument("--nodes", type=int, default=200, help="K temporal nodes")
     ap.add_argument("--tf", type=float, default=2.0)
     ap.add_argument("--n-sub", dest="n_sub", type=int, default=100, help="RK4 steps per interval (integrator_steps-1)")
-    ap.add_argument("--chunks", type=int, default=8, help="compute/all-gather overlap chunks (N>1)")
+    ap.add_argument("--chunks", type=int, default=8, help="compute/all-gather overlap chunks (N>1, --gather nccl)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: all-gather by peer stores from inside the kernel (fused) or chunked NCCL all-gather")
     ap.add_argument("--ref-sats", dest="ref_sats", type=int, default=2, help="satellites per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

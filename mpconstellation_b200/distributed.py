@@ -1,13 +1,23 @@
-"""Multi-GPU: satellites sharded over ranks, one all-gather of the discretized matrices.
+"""Multi-GPU: satellites sharded over ranks, the all-gather of the discretized matrices fused into the kernel.
 
 Every (satellite, interval) is independent given the reference trajectory (linearize_discretize.py:31-34),
-so the only exchange step is the one north_star names: the SoA matrices of every shard are gathered to the
-rank(s) driving the optimizer.  One process per GPU (torchrun); `torch.distributed` does the plumbing.
+so the path shards by satellite with no exchange until the end; the one exchange north_star names is the
+all-gather of the SoA matrices to the rank(s) driving the optimizer.  One process per GPU (torchrun);
+`torch.distributed` does the plumbing.
 
-Layout after the gather: rank-major  G[r][row][col]  with  r in [0,world), row in [0,105),
-col = local_sat * (K-1) + k  -- i.e. each rank's SoA block is kept contiguous (what NCCL all-gather
-produces without an extra transpose).  `GatheredDiscretization.sat(s)` hands out the reference-shaped
-views for a GLOBAL satellite index, so optimizer-side code indexes exactly as before (optimizer.py:327-339).
+Two implementations of the exchange:
+
+* `FusedGather` (the product path on NVLink/NVSwitch boxes): every rank owns a symmetric-memory buffer in
+  the FINAL gathered layout  G[row][global column],  global column = global_satellite * (K-1) + k.
+  The discretization kernel of rank r stores each result directly into column range r of EVERY rank's
+  buffer (`mpc_discretize_batch_multi`, peer-mapped pointers): the transfer is spread over the whole
+  compute-bound kernel instead of following it, no staging copy, no separate collective launch.
+  A symmetric-memory barrier closes the step.
+* `nccl_gather_chunks` (baseline / fallback when peer mapping is unavailable): chunked
+  `all_gather_into_tensor` on a side stream, overlapping the gather of chunk c with the compute of chunk c+1.
+
+`GatheredView` hands out the reference-shaped per-satellite views of either result, so optimizer-side code
+indexes exactly as before (optimizer.py:327-339).
 """
 import numpy as np
 
@@ -26,101 +36,132 @@ def shard_range(n_sats, rank, world):
     return s0, min(n_sats, s0 + per)
 
 
-class GatheredDiscretization:
-    """Rank-major gathered SoA blocks: array-like [world, 105, per*(K-1)] (numpy array or CPU/CUDA tensor)."""
+def _np(a):
+    return a if isinstance(a, np.ndarray) else a.detach().cpu().numpy()
 
-    def __init__(self, gathered, n_sats, K, world):
-        self.g, self.n_sats, self.K, self.world = gathered, n_sats, K, world
+
+class GatheredView:
+    """Per-satellite access to a gathered SoA buffer.
+
+    layout "global":  buf[105, n_sats*(K-1)]            (FusedGather)
+    layout "rank":    buf[world, 105, per*(K-1)]        (NCCL all-gather of equal rank blocks)
+    """
+
+    def __init__(self, buf, n_sats, K, world, layout="global"):
+        self.buf, self.n_sats, self.K, self.world, self.layout = buf, n_sats, K, world, layout
         self.per = (n_sats + world - 1) // world
 
-    def locate(self, s):
+    def block(self, s):
         if not 0 <= s < self.n_sats:
             raise IndexError(s)
-        return s // self.per, s % self.per
+        n = self.K - 1
+        if self.layout == "global":
+            return _np(self.buf[:, s * n:(s + 1) * n])
+        r, ls = s // self.per, s % self.per
+        return _np(self.buf[r][:, ls * n:(ls + 1) * n])
 
     def sat(self, s):
-        """(A_k, B_kp, B_kn, Sigma_k, xi_k) of global satellite s, reference shapes/order
-        (linearize_discretize.py:390); numpy views when the gathered buffer is a numpy array."""
-        r, ls = self.locate(s)
+        """(A_k, B_kp, B_kn, Sigma_k, xi_k) of GLOBAL satellite s; shapes/order of linearize_discretize.py:390."""
         n = self.K - 1
-        blk = self.g[r][:, ls * n:(ls + 1) * n]
-        if not isinstance(blk, np.ndarray):
-            blk = blk.cpu().numpy()
+        blk = self.block(s)
         A = blk[_lib.ROW_A:_lib.ROW_A + 49].T.reshape(n, 7, 7)
         Bp = blk[_lib.ROW_BP:_lib.ROW_BP + 21].T.reshape(n, 7, 3)
         Bn = blk[_lib.ROW_BN:_lib.ROW_BN + 21].T.reshape(n, 7, 3)
         return A, Bp, Bn, blk[_lib.ROW_SIGMA:_lib.ROW_SIGMA + 7], blk[_lib.ROW_XI:_lib.ROW_XI + 7]
 
 
-def all_gather_soa(local, group=None, out=None):
-    """All-gather equal-sized local SoA blocks [105, cols] -> [world, 105, cols] (NCCL for CUDA tensors,
-    gloo for CPU tensors).  Ranks with fewer satellites pad their block to the common size first."""
+def _dst_count(world):
+    for n in (1, 2, 4, 8):
+        if world <= n:
+            return n
+    raise ValueError("FusedGather supports up to 8 ranks (one NVSwitch box)")
+
+
+class FusedGather:
+    """All-gather of the discretized matrices by peer stores from inside the discretization kernel."""
+
+    def __init__(self, n_sats_total, K, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = dist.group.WORLD if group is None else group
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_sats, self.K = n_sats_total, K
+        self.pitch = n_sats_total * (K - 1)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.buf = symm_mem.empty((_lib.MPC_OUT_ROWS, self.pitch), dtype=torch.float64, device=self.device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        # own buffer first (it is also the kernel's "local" destination), then the peers, rotated so that the
+        # ranks do not all hammer the same peer at the same time; padded to 1/2/4/8 with the own pointer
+        order = [(self.rank + i) % self.world for i in range(self.world)]
+        self.dst = [ptrs[r] for r in order]
+        while len(self.dst) < _dst_count(self.world):
+            self.dst.append(ptrs[self.rank])
+        self.s0, self.s1 = shard_range(n_sats_total, self.rank, self.world)
+        self.status = torch.zeros(max(1, (self.s1 - self.s0) * (K - 1)), dtype=torch.int32, device=self.device)
+
+    def discretize(self, x, u, tf, const, include_J2=False, n_sub=100, barrier=True):
+        """x [n_local,7,K], u [n_local,3,K], tf [n_local] (this rank's shard_range block, CUDA float64).  Enqueues
+        the kernel on the current stream; with barrier=True also the cross-rank barrier after which every
+        rank's `self.buf` holds all N satellites."""
+        from . import batch
+        assert x.shape[0] == self.s1 - self.s0 and x.shape[2] == self.K
+        if x.shape[0] > 0:
+            batch.discretize_batch_device(x, u, tf, const, include_J2=include_J2, n_sub=n_sub, out=self.buf,
+                                          out_pitch=self.pitch, out_offset=self.s0 * (self.K - 1),
+                                          status=self.status, extra_dst=self.dst[1:])
+        if barrier:
+            self.handle.barrier()
+        return self.buf
+
+    def view(self):
+        return GatheredView(self.buf, self.n_sats, self.K, self.world, layout="global")
+
+
+def nccl_gather_chunks(local, n_chunks, group=None, side_stream=None, produce=None, chunk_cols=None):
+    """Baseline exchange: `local` is this rank's [105, cols] block (equal cols on every rank).  It is gathered
+    in `n_chunks` column chunks (or chunks of exactly `chunk_cols` columns); if `produce(c0, c1)` is given it is called right before chunk [c0,c1) is
+    gathered (that is where the caller launches the kernel for those columns), so gather(c) overlaps
+    produce(c+1).  Returns the list of gathered chunk tensors [world, 105, chunk_cols] and the chunk bounds.
+    Works on CPU tensors with gloo (used by the CPU tests) and CUDA tensors with NCCL."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    if out is None:
-        out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    return out
-
-
-def discretize_sharded(x, u, tf, const, n_sats_total, include_J2=False, n_sub=100, chunks=4, group=None,
-                       local_compute=None):
-    """Discretize this rank's shard and all-gather the result.
-
-    x [n_local,7,K], u [n_local,3,K], tf [n_local]: CUDA float64 tensors holding this rank's contiguous block of
-    satellites (shard_range).  The shard is processed in `chunks` sub-blocks; the all-gather of chunk c runs on
-    a side stream while chunk c+1 is being discretized.  Returns a list of GatheredDiscretization chunks'
-    gathered tensors and a GatheredDiscretization-compatible accessor.
-
-    `local_compute` lets a test substitute the per-chunk compute on a CPU-only box (gloo); the product path
-    leaves it None and runs the CUDA kernel.
-    """
-    import torch
-    import torch.distributed as dist
-    from . import batch
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    per = (n_sats_total + world - 1) // world
-    n_local = x.shape[0]
-    K = x.shape[2]
-    s0, s1 = shard_range(n_sats_total, rank, world)
-    assert n_local == s1 - s0, "x must hold exactly this rank's shard"
-    dev = x.device
-    cuda = dev.type == "cuda"
-    # pad the local block to `per` satellites so every rank contributes the same number of columns
-    local = torch.zeros((_lib.MPC_OUT_ROWS, per * (K - 1)), dtype=torch.float64, device=dev)
-    status = torch.zeros(per * (K - 1), dtype=torch.int32, device=dev)
-    gathered = torch.empty((world, _lib.MPC_OUT_ROWS, per * (K - 1)), dtype=torch.float64, device=dev)
-    csz = max(1, (per + chunks - 1) // chunks)
-    side = torch.cuda.Stream(dev) if cuda else None
-    views = []
-    for c0 in range(0, per, csz):
-        c1 = min(per, c0 + csz)
-        l0, l1 = min(c0, n_local), min(c1, n_local)
-        if l1 > l0:
-            if local_compute is not None:
-                local_compute(x[l0:l1], u[l0:l1], tf[l0:l1], local, l0 * (K - 1), status)
-            else:
-                batch.discretize_batch_device(x[l0:l1], u[l0:l1], tf[l0:l1], const, include_J2=include_J2, n_sub=n_sub,
-                                              out=local, out_offset=l0 * (K - 1), status=status[l0 * (K - 1):l1 * (K - 1)])
-        # gather the column range of this chunk from every rank into gathered[:, :, cols]
-        cols = slice(c0 * (K - 1), c1 * (K - 1))
-        piece = local[:, cols].contiguous()
-        recv = torch.empty((world,) + tuple(piece.shape), dtype=torch.float64, device=dev)
+    cols = local.shape[1]
+    csz = int(chunk_cols) if chunk_cols else max(1, (cols + n_chunks - 1) // n_chunks)
+    cuda = local.is_cuda
+    if cuda and side_stream is None:
+        side_stream = torch.cuda.Stream(local.device)
+    out, bounds = [], []
+    for c0 in range(0, cols, csz):
+        c1 = min(cols, c0 + csz)
+        if produce is not None:
+            produce(c0, c1)
+        piece = local[:, c0:c1].contiguous()
+        recv = torch.empty((world,) + tuple(piece.shape), dtype=local.dtype, device=local.device)
         if cuda:
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
-                dist.all_gather_into_tensor(recv, piece, group=group)
-                gathered[:, :, cols].copy_(recv)
-            piece.record_stream(side)
-            recv.record_stream(side)
+            ev.record(torch.cuda.current_stream(local.device))
+            side_stream.wait_event(ev)
+            with torch.cuda.stream(side_stream):
+                dist.all_gather_into_tensor(recv.view(-1, piece.shape[1]), piece, group=group)
+            piece.record_stream(side_stream)
         else:
-            dist.all_gather_into_tensor(recv, piece, group=group)
-            gathered[:, :, cols].copy_(recv)
-        views.append(recv)
+            dist.all_gather_into_tensor(recv.view(-1, piece.shape[1]), piece, group=group)
+        out.append(recv)
+        bounds.append((c0, c1))
     if cuda:
-        torch.cuda.current_stream(dev).wait_stream(side)
-    return GatheredDiscretization(gathered, n_sats_total, K, world), status
+        torch.cuda.current_stream(local.device).wait_stream(side_stream)
+    return out, bounds
+
+
+def assemble_rank_major(chunks, bounds, world):
+    """[world, 105, cols] from the chunk list of nccl_gather_chunks (a copy; for consumers that want one buffer)."""
+    import torch
+    cols = bounds[-1][1]
+    full = torch.empty((world, chunks[0].shape[1], cols), dtype=chunks[0].dtype, device=chunks[0].device)
+    for t, (c0, c1) in zip(chunks, bounds):
+        full[:, :, c0:c1] = t
+    return full
