@@ -233,13 +233,13 @@ def gpu_arm(args):
         gather_mode = args.gather
         if gather_mode == "fused":
             try:
-                fused = D.FusedGather(N * world, K, device=dev)
+                fused = D.FusedGather(N * world, K, device=dev, mode=args.fused_mode)
             except Exception as exc:            # no peer mapping on this box: fall back to the NCCL baseline
                 if rank == 0:
                     print(f"[bench] symmetric memory unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
                 gather_mode = "nccl"
         if gather_mode == "nccl":
-            local = torch.empty((105, n_int), dtype=torch.float64, device=dev)
+            local_out = torch.empty((105, n_int), dtype=torch.float64, device=dev)
             comm_stream = torch.cuda.Stream(dev)
             col_chunk = ((N + args.chunks - 1) // args.chunks) * (K - 1)
 
@@ -256,9 +256,9 @@ def gpu_arm(args):
         else:
             def produce(c0, c1):
                 s0, s1 = c0 // (K - 1), c1 // (K - 1)
-                M.discretize_batch_device(x[s0:s1], u[s0:s1], tfd[s0:s1], const, n_sub=n_sub, out=local,
+                M.discretize_batch_device(x[s0:s1], u[s0:s1], tfd[s0:s1], const, n_sub=n_sub, out=local_out,
                                           out_offset=c0, status=std[c0:c1])
-            step.gathered = D.nccl_gather_chunks(local, args.chunks, side_stream=comm_stream, produce=produce,
+            step.gathered = D.nccl_gather_chunks(local_out, args.chunks, side_stream=comm_stream, produce=produce,
                                                  chunk_cols=col_chunk)
         if ev is not None:
             ev[1].record()
@@ -329,7 +329,7 @@ def gpu_arm(args):
     elif fused is not None:
         dev_cols = fused.buf[:, rank * n_int:rank * n_int + K - 1]
     else:
-        dev_cols = local[:, :K - 1]
+        dev_cols = local_out[:, :K - 1]
     same = bool(np.array_equal(out_h[:, :K - 1], dev_cols.cpu().numpy()))
     gathered_ok = None
     if fused is not None:
@@ -362,7 +362,7 @@ def gpu_arm(args):
                 "d2h_bytes_per_step": int(out_h.nbytes + y_h.nbytes + u_h.nbytes + n_int * 4),
                 "api": "mpconstellation_b200.propagate_discretize (C-ABI mpc_propagate_discretize_host), pinned host buffers",
                 "matches_device_path": same},
-        "gather": {"mode": gather_mode, "verified": gathered_ok,
+        "gather": {"mode": gather_mode + (":" + args.fused_mode if fused is not None else ""), "verified": gathered_ok,
                    "bytes_received_per_rank_per_step": int((world - 1) * n_int * 105 * 8)} if world > 1 else None,
         "gpu_launches": int(launches),
         "kernel": {"discretize_ms": disc_ms_avg, "propagate_ms": ms_per_step - disc_ms_avg if world == 1 else None,
@@ -396,6 +396,7 @@ def main():
     ap.add_argument("--tf", type=float, default=2.0)
     ap.add_argument("--n-sub", dest="n_sub", type=int, default=100, help="RK4 steps per interval (integrator_steps-1)")
     ap.add_argument("--chunks", type=int, default=8, help="compute/all-gather overlap chunks (N>1, --gather nccl)")
+    ap.add_argument("--fused-mode", dest="fused_mode", default="unicast", choices=["unicast", "multicast"])
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: all-gather by peer stores from inside the kernel (fused) or chunked NCCL all-gather")
     ap.add_argument("--ref-sats", dest="ref_sats", type=int, default=2, help="satellites per step of the reference arm")

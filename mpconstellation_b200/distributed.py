@@ -80,7 +80,10 @@ def _dst_count(world):
 class FusedGather:
     """All-gather of the discretized matrices by peer stores from inside the discretization kernel."""
 
-    def __init__(self, n_sats_total, K, group=None, device=None):
+    def __init__(self, n_sats_total, K, group=None, device=None, mode="unicast"):
+        """mode "unicast": one peer-mapped store per destination rank (works on any P2P-capable box);
+        mode "multicast": one store to the NVSwitch multicast address of the symmetric buffer, replicated by the
+        switch to every rank (NVLS) -- 1/world of the SM store instructions and of the egress traffic."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -99,6 +102,10 @@ class FusedGather:
         self.dst = [ptrs[r] for r in order]
         while len(self.dst) < _dst_count(self.world):
             self.dst.append(ptrs[self.rank])
+        self.mode = mode
+        self.mc_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if mode == "multicast" and not self.mc_ptr:
+            raise RuntimeError("this box / torch build exposes no multicast (NVLS) mapping for symmetric memory")
         self.s0, self.s1 = shard_range(n_sats_total, self.rank, self.world)
         self.status = torch.zeros(max(1, (self.s1 - self.s0) * (K - 1)), dtype=torch.int32, device=self.device)
 
@@ -108,7 +115,15 @@ class FusedGather:
         rank's `self.buf` holds all N satellites."""
         from . import batch
         assert x.shape[0] == self.s1 - self.s0 and x.shape[2] == self.K
-        if x.shape[0] > 0:
+        if x.shape[0] > 0 and self.mode == "multicast":
+            import ctypes
+            import torch
+            p = _lib.make_params(const, include_J2, False)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(_lib.lib().mpc_discretize_batch(x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p),
+                                                       x.shape[0], self.K, int(n_sub), self.mc_ptr, self.pitch,
+                                                       self.s0 * (self.K - 1), self.status.data_ptr(), stream))
+        elif x.shape[0] > 0:
             batch.discretize_batch_device(x, u, tf, const, include_J2=include_J2, n_sub=n_sub, out=self.buf,
                                           out_pitch=self.pitch, out_offset=self.s0 * (self.K - 1),
                                           status=self.status, extra_dst=self.dst[1:])

@@ -44,6 +44,14 @@ v = fg.view()
 A = v.sat(N * world - 1)[0]
 ok_view = np.array_equal(A, full[:49, -(K - 1):].T.reshape(K - 1, 7, 7).cpu().numpy())
 
+t_mc, ok_mc = float("nan"), 1
+try:
+    fm = D.FusedGather(N * world, K, device=dev, mode="multicast")
+    fm.buf.zero_(); torch.cuda.synchronize(); dist.barrier()
+    t_mc = timed(lambda: fm.discretize(x, u, tfd, const))
+    ok_mc = int(torch.equal(fm.buf, full))
+except Exception as exc:
+    if rank == 0: print("multicast unavailable:", exc)
 loc = torch.empty((105, n_int), dtype=torch.float64, device=dev)
 def nccl_step():
     def produce(c0, c1):
@@ -59,10 +67,10 @@ def nccl_plain():
     nccl_plain.res = torch.empty((world * 105, n_int), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(nccl_plain.res, loc)
 t_plain = timed(nccl_plain)
-res = torch.tensor([int(ok_fused), int(ok_view), int(ok_nccl)], device=dev); dist.all_reduce(res, op=dist.ReduceOp.MIN)
+res = torch.tensor([int(ok_fused), int(ok_view), int(ok_nccl), int(ok_mc)], device=dev); dist.all_reduce(res, op=dist.ReduceOp.MIN)
 if rank == 0:
     gb = (world - 1) * n_int * 840 / 1e9
-    print(f"world {world}  N/rank {N}  K {K}: local-only {t_local:.3f} ms | fused peer-store gather {t_fused:.3f} ms | "
+    print(f"world {world}  N/rank {N}  K {K}: local-only {t_local:.3f} ms | fused peer-store gather {t_fused:.3f} ms | fused multicast-store gather {t_mc:.3f} ms | "
           f"NCCL chunked-overlap {t_nccl:.3f} ms | kernel then NCCL all-gather {t_plain:.3f} ms | "
-          f"{gb:.2f} GB received per rank | verified fused/view/nccl = {res.tolist()}")
+          f"{gb:.2f} GB received per rank | verified fused/view/nccl/multicast = {res.tolist()}")
 dist.destroy_process_group()
