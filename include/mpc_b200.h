@@ -49,11 +49,7 @@ extern "C" {
 #define MPC_ST_OK 0
 #define MPC_ST_MASS 1      /* mass <= 0 met while integrating: simulator.py:135-136 raises here */
 #define MPC_ST_NONFINITE 2 /* a non-finite result */
-
-/* integrators of the discretization kernel */
-#define MPC_INTEG_RK4_UNIFORM 0 /* fixed-step RK4, n_sub steps, trapezoid on the n_sub+1 step nodes:
-                                   the reference's use_uniform_steps=True, integrator_steps=n_sub+1
-                                   node set (linearize_discretize.py:27-28,47-48) */
+#define MPC_ST_STEP 3      /* adaptive mode: step size underflow / too many steps (solve_ivp would fail) */
 
 /* Normalized constants: the reference's Constants bag (constants.py:11-20) as produced by
  * SatelliteScale.get_normalized_constants (satellite_scale.py:36-44), plus the two module-level
@@ -121,6 +117,20 @@ int mpc_discretize_batch_multi(const double *x, const double *u, const double *t
                                int64_t out_offset, int32_t *status, void *stream);
 
 /*
+ * The reference's DEFAULT quadrature mode (Discretizer.use_uniform_steps = False, linearize_discretize.py:
+ * 29-30,49-50,109): the nodes of every interval are the steps scipy's solve_ivp(RK45) accepts.  The kernel
+ * replays scipy's step-size controller per interval (Dormand-Prince 5(4), rtol/atol error norm, first-step
+ * heuristic, max_step = Discretizer.ivp_max_step) and applies the non-uniform trapezoid rule on those nodes,
+ * so the matrices match what the unmodified reference hands to the optimizer.  scipy defaults: rtol 1e-3,
+ * atol 1e-6.  n_nodes [n_sats*(K-1)] (may be NULL) receives the node count of every interval (len(sol.t)).
+ * Other arguments as mpc_discretize_batch.
+ */
+int mpc_discretize_batch_adaptive(const double *x, const double *u, const double *tf, const mpc_params *p,
+                                  int n_sats, int K, double rtol, double atol, double max_step, double *out,
+                                  int64_t out_pitch, int64_t out_offset, int32_t *status, int32_t *n_nodes,
+                                  void *stream);
+
+/*
  * Replaces Simulator.get_trajectory_ODE (simulator.py:164-189) for a batch of satellites, and
  * Discretizer.extract_uk (linearize_discretize.py:393-411) on the sampled trajectory.
  *
@@ -154,6 +164,12 @@ void mpc_host_free(void *p);
 int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf,
                               const mpc_params *p, int n_sats, int K, int n_sub, double *out_host,
                               int32_t *status_host);
+
+/* Host-buffer form of mpc_discretize_batch_adaptive. */
+int mpc_discretize_batch_adaptive_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf,
+                                       const mpc_params *p, int n_sats, int K, double rtol, double atol,
+                                       double max_step, double *out_host, int32_t *status_host,
+                                       int32_t *n_nodes_host);
 
 /* Host-buffer form of mpc_propagate_batch (ctrl->table is a host pointer here). */
 int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p,

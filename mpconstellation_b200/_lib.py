@@ -15,14 +15,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libmpc_b200.so")
 SOURCES = ["mpc_b200.cu"]
-HEADERS = ["discretize_kernel.cuh", "propagate_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
+HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "propagate_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
 MPC_OUT_ROWS = 105
 ROW_A, ROW_BP, ROW_BN, ROW_SIGMA, ROW_XI = 0, 49, 70, 91, 98
 CTRL_ZERO, CTRL_CONSTANT, CTRL_TANGENTIAL, CTRL_SEQUENCE = 0, 1, 2, 3
-ST_OK, ST_MASS, ST_NONFINITE = 0, 1, 2
+ST_OK, ST_MASS, ST_NONFINITE, ST_STEP = 0, 1, 2, 3
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4
 
 
@@ -89,6 +89,9 @@ def lib():
     L.mpc_launch_count.restype = i64
     L.mpc_discretize_batch.argtypes = [_DP, _DP, _DP, pp, i, i, i, _DP, i64, i64, _DP, vp]
     L.mpc_discretize_batch_multi.argtypes = [_DP, _DP, _DP, pp, i, i, i, ctypes.POINTER(ctypes.c_void_p), i, i64, i64, _DP, vp]
+    d = ctypes.c_double
+    L.mpc_discretize_batch_adaptive.argtypes = [_DP, _DP, _DP, pp, i, i, d, d, d, _DP, i64, i64, _DP, _DP, vp]
+    L.mpc_discretize_batch_adaptive_host.argtypes = [vp, _DP, _DP, _DP, pp, i, i, d, d, d, _DP, _DP, _DP]
     L.mpc_propagate_batch.argtypes = [_DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP, vp]
     L.mpc_ctx_create.argtypes = [i, ctypes.POINTER(vp)]
     L.mpc_ctx_destroy.argtypes = [vp]
@@ -103,6 +106,7 @@ def lib():
     L.mpc_set_tuning.argtypes = [i]
     L.mpc_set_tuning.restype = i
     for name in ("mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
+                 "mpc_discretize_batch_adaptive", "mpc_discretize_batch_adaptive_host",
                  "mpc_ctx_create", "mpc_ctx_destroy", "mpc_discretize_batch_host", "mpc_propagate_batch_host",
                  "mpc_propagate_discretize_host", "mpc_fp64_peak_probe"):
         getattr(L, name).restype = i
@@ -112,9 +116,9 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "mpc_version", "mpc_last_error", "mpc_device_count", "mpc_device_info", "mpc_launch_count",
-    "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
+    "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_propagate_batch",
     "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
-    "mpc_discretize_batch_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host",
+    "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host",
     "mpc_fp64_peak_probe", "mpc_set_tuning",
 ]
 

@@ -81,15 +81,21 @@ def raise_on_status(status):
         if code == _lib.ST_MASS:
             # same exception type / text as simulator.py:135-136
             raise Exception(f"ERROR: INVALID SATELLITE MASS: non-positive mass at unit {tuple(int(i) for i in idx)}")
+        if code == _lib.ST_STEP:
+            raise RuntimeError(f"adaptive integration failed (step size underflow) at unit {tuple(int(i) for i in idx)}")
         raise FloatingPointError(f"non-finite result at unit {tuple(int(i) for i in idx)}")
 
 
 def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_sub=100, out=None, status=None,
-                     device=0, check=True):
+                     device=0, check=True, adaptive=None):
     """Discretize every interval of every satellite in one launch sequence (host arrays).
 
     x [N,7,K], u [N,3,K], tf scalar or [N]; `out` may be a preallocated (ideally pinned) [105, N*(K-1)]
     array.  Returns a DiscretizedBatch.  ref: linearize_discretize.py:334-390 / :8-82.
+
+    adaptive=None: fixed-step RK4 with n_sub steps, trapezoid on the n_sub+1 step nodes (the reference's
+    use_uniform_steps=True node set).  adaptive=dict(rtol=1e-3, atol=1e-6, max_step=1e-2): the reference's
+    default mode, quadrature on the steps scipy's RK45 controller accepts; the result carries `.n_nodes`.
     """
     ctx = _ctx(device)
     x = _f64(x)
@@ -106,10 +112,19 @@ def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_su
     if status is None:
         status = np.zeros(n_int, dtype=np.int32)
     p = _lib.make_params(const, include_J2, include_drag)
-    _lib.check(_lib.lib().mpc_discretize_batch_host(ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv),
-                                                    ctypes.byref(p), N, K, int(n_sub), _lib.addr(out),
-                                                    _lib.addr(status)))
+    n_nodes = None
+    if adaptive is None:
+        _lib.check(_lib.lib().mpc_discretize_batch_host(ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv),
+                                                        ctypes.byref(p), N, K, int(n_sub), _lib.addr(out),
+                                                        _lib.addr(status)))
+    else:
+        n_nodes = np.zeros(n_int, dtype=np.int32)
+        _lib.check(_lib.lib().mpc_discretize_batch_adaptive_host(
+            ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv), ctypes.byref(p), N, K, float(adaptive.get("rtol", 1e-3)),
+            float(adaptive.get("atol", 1e-6)), float(adaptive.get("max_step", 1e-2)), _lib.addr(out), _lib.addr(status),
+            _lib.addr(n_nodes)))
     res = DiscretizedBatch(out, status.reshape(N, K - 1), N, K)
+    res.n_nodes = None if n_nodes is None else n_nodes.reshape(N, K - 1)
     if check:
         res.raise_on_error()
     return res
@@ -212,7 +227,7 @@ def _torch():
 
 
 def discretize_batch_device(x, u, tf, const, include_J2=False, n_sub=100, out=None, out_pitch=None, out_offset=0,
-                            status=None, extra_dst=None):
+                            status=None, extra_dst=None, adaptive=None, n_nodes=None):
     """Device form: x [N,7,K], u [N,3,K], tf [N] are float64 CUDA tensors; work is enqueued on torch's
     current stream, nothing synchronises.  `out` is [105, pitch]; `extra_dst` is an optional list of
     further [105, pitch] buffers (e.g. peer-mapped) every result is also stored to (total 1,2,4 or 8)."""
@@ -229,7 +244,12 @@ def discretize_batch_device(x, u, tf, const, include_J2=False, n_sub=100, out=No
     p = _lib.make_params(const, include_J2, False)
     stream = torch.cuda.current_stream(x.device).cuda_stream
     L = _lib.lib()
-    if extra_dst:
+    if adaptive is not None:
+        _lib.check(L.mpc_discretize_batch_adaptive(
+            x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p), N, K, float(adaptive.get("rtol", 1e-3)),
+            float(adaptive.get("atol", 1e-6)), float(adaptive.get("max_step", 1e-2)), out.data_ptr(), pitch,
+            int(out_offset), status.data_ptr(), n_nodes.data_ptr() if n_nodes is not None else None, stream))
+    elif extra_dst:
         ptrs = [out.data_ptr()] + [int(d if isinstance(d, int) else d.data_ptr()) for d in extra_dst]
         arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
         _lib.check(L.mpc_discretize_batch_multi(x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p), N, K,

@@ -1,0 +1,362 @@
+// discretize_adaptive_kernel.cuh -- the reference's DEFAULT quadrature mode on the device.
+//
+// With use_uniform_steps=False (linearize_discretize.py:29-30,49-50,109 -- the shipped default, and what
+// control.py:187 uses) the quadrature nodes of an interval are the steps scipy's solve_ivp(RK45) accepted:
+// 4-8 nodes, geometrically growing from Hairer's first-step heuristic.  The matrices handed to the optimizer
+// therefore depend on scipy's step-size controller.  This kernel replays that controller per interval
+// (one thread each): Dormand-Prince 5(4) with local extrapolation, error norm = RMS over all 56 components of
+// err / (atol + rtol*max(|y|,|y_new|)), SAFETY 0.9, step factor clamped to [0.2, 10], first step from
+// select_initial_step, max_step = Discretizer.ivp_max_step, steps clipped to the interval end
+// (scipy 1.18.1: integrate/_ivp/rk.py rk_step / RungeKutta._step_impl / RK45 tableau, common.py
+// select_initial_step / norm).  scipy is a third-party dependency the reference neither vendors nor pins.
+//
+// Same structure as the fixed-step kernel: unscaled system with step hs = tf*h, Phi column by column with the
+// 7 stage matrices G_s shared by all columns, symplectic Phi^-1 at the nodes, non-uniform trapezoid panels
+// (np.trapz with x = sol.t, :77-80).  Per-thread storage in shared memory, [slot][thread]:
+//   0..55 accumulators | 56..97 Phi (buffer 0) | 98..139 Phi (buffer 1) | 140..202 G_s, d_s of the 7 stages
+#pragma once
+#include "discretize_kernel.cuh"
+
+namespace mpc {
+
+constexpr int kAdSlots = 203;
+constexpr int kAdPhi0 = 56, kAdPhi1 = 98, kAdGs = 140;
+
+__device__ __constant__ double kDpA[6][5] = {{0, 0, 0, 0, 0},
+                                             {1.0 / 5, 0, 0, 0, 0},
+                                             {3.0 / 40, 9.0 / 40, 0, 0, 0},
+                                             {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+                                             {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+                                             {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+
+struct AdStage {  // one evaluation of the unscaled dynamics and its linearization
+    double k[7];  // f / tf = [v; a; mdot]
+    Sym3 g;
+    double d[3];
+    double im, iun, un;
+    double ux, uy, uz;
+};
+
+template <bool J2>
+__device__ __forceinline__ int ad_eval(const DiscParams &P, const double (&x)[7], double s, double u0x, double u0y,
+                                       double u0z, double dux, double duy, double duz, AdStage &o)
+{
+    o.ux = fma(s, dux, u0x);
+    o.uy = fma(s, duy, u0y);
+    o.uz = fma(s, duz, u0z);
+    double ax, ay, az;
+    gravity<J2>(P, x[0], x[1], x[2], ax, ay, az, o.g);
+    o.im = fast_rcp(x[6]);
+    const double tx = o.ux * o.im, ty = o.uy * o.im, tz = o.uz * o.im;
+    const double uu = fma(o.ux, o.ux, fma(o.uy, o.uy, o.uz * o.uz));
+    o.iun = (uu > 4.930380657631324e-32) ? fast_rsqrt(uu) : 0.0;
+    o.un = uu * o.iun;
+    o.k[0] = x[3];
+    o.k[1] = x[4];
+    o.k[2] = x[5];
+    o.k[3] = ax + tx;
+    o.k[4] = ay + ty;
+    o.k[5] = az + tz;
+    o.k[6] = -o.un * P.inv_ve;
+    o.d[0] = -tx * o.im;
+    o.d[1] = -ty * o.im;
+    o.d[2] = -tz * o.im;
+    return !(x[6] > 0.0);
+}
+
+#define SM(e) sm[(e) * BLOCK]
+
+template <int BLOCK>
+__device__ __forceinline__ void ad_store_stage(volatile double *sm, int s, const AdStage &st)
+{
+    const int b = kAdGs + s * 9;
+    SM(b + 0) = st.g.xx;
+    SM(b + 1) = st.g.xy;
+    SM(b + 2) = st.g.xz;
+    SM(b + 3) = st.g.yy;
+    SM(b + 4) = st.g.yz;
+    SM(b + 5) = st.g.zz;
+    SM(b + 6) = st.d[0];
+    SM(b + 7) = st.d[1];
+    SM(b + 8) = st.d[2];
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void ad_load_phi(volatile double *sm, int base, double (&pr)[7][3], double (&pv)[7][3])
+{
+#pragma unroll
+    for (int c = 0; c < 7; ++c)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            pr[c][a] = SM(base + c * 6 + a);
+            pv[c][a] = SM(base + c * 6 + 3 + a);
+        }
+}
+
+// node terms at (Phi in buffer `base`, state x, stage st): acc += w * integrands, lambda+ = lam
+template <int BLOCK>
+__device__ __forceinline__ void ad_node(volatile double *sm, int base, const DiscParams &P, const double (&x)[7],
+                                        const AdStage &st, double w, double lam)
+{
+    double pr[7][3], pv[7][3];
+    ad_load_phi<BLOCK>(sm, base, pr, pv);
+    double grx, gry, grz;
+    sym_mul(st.g, x[0], x[1], x[2], grx, gry, grz);
+    node_accumulate<BLOCK>(sm, pr, pv, P, st.im, st.ux, st.uy, st.uz, st.iun, st.k[6], x[3], x[4], x[5], st.k[3],
+                           st.k[4], st.k[5], grx, gry, grz, w, w * lam);
+}
+
+template <bool J2, int BLOCK, int NDST>
+__global__ void __launch_bounds__(BLOCK)
+discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in,
+                           const double *__restrict__ tf_arr, DiscParams P, int n_sats, int K, double rtol, double atol,
+                           double max_step, DstTab dst, long long pitch, long long offset, int32_t *__restrict__ status,
+                           int32_t *__restrict__ n_nodes)
+{
+    extern __shared__ double acc_smem[];
+    const long long n_int = (long long)n_sats * (K - 1);
+    const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (gid >= n_int) return;
+    volatile double *sm = acc_smem + threadIdx.x;
+    const int sat = (int)(gid / (K - 1));
+    const int k = (int)(gid - (long long)sat * (K - 1));
+    const double tf = tf_arr[sat];
+    const double *xs = x_in + ((long long)sat * 7) * K + k;
+    const double *us = u_in + ((long long)sat * 3) * K + k;
+    double x[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) x[c] = xs[(long long)c * K];
+    const double u0x = us[0], u0y = us[K], u0z = us[2 * (long long)K];
+    const double dux = us[1] - u0x, duy = us[K + 1] - u0y, duz = us[2 * (long long)K + 1] - u0z;
+    // tau = np.linspace(0, 1, K) (:356): start + i*step, last point exactly 1
+    const double step = 1.0 / (double)(K - 1);
+    const double t0 = (double)k * step, t1 = (k + 1 == K - 1) ? 1.0 : (double)(k + 1) * step;
+    const double ilen = 1.0 / (t1 - t0);
+
+#pragma unroll 1
+    for (int e = 0; e < kAdSlots; ++e) SM(e) = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) SM(kAdPhi0 + c * 6 + c) = 1.0;  // Phi(tau_k) = I   (:34)
+    int cur = kAdPhi0, nxt = kAdPhi1;
+    int bad = 0, fail = 0, nodes = 1;
+    double t = t0;
+
+    AdStage st0;
+    bad |= ad_eval<J2>(P, x, 0.0, u0x, u0y, u0z, dux, duy, duz, st0);
+    // ---- select_initial_step (common.py); f = tf * k, y0 = [I, x] ------------------------------------------
+    double h_abs;
+    {
+        const double interval_length = fabs(t1 - t0);
+        // d0 = RMS(y0/scale), d1 = RMS(f0/scale), scale = atol + |y0| rtol; Phi(t0) = I: 7 ones, 42 zeros
+        const double s1 = atol + rtol, s0 = atol;
+        double d0sq = 7.0 / (s1 * s1), d1sq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const double sc = atol + fabs(x[i]) * rtol;
+            d0sq += (x[i] / sc) * (x[i] / sc);
+            d1sq += (tf * st0.k[i] / sc) * (tf * st0.k[i] / sc);
+        }
+        // f0 of Phi = tf * A(x0) * I: column c of A.  rows 0..2 = e_{c-3} (c = 3..5), rows 3..5 = G[:,c] (c<3) / d (c=6)
+        // nonzero entries: Phi_r' = I (scale s0: y0 entry is 0), Phi_v' = G (diag on s0... all y0 zeros) and d
+        const double g[9] = {st0.g.xx, st0.g.xy, st0.g.xz, st0.g.xy, st0.g.yy, st0.g.yz, st0.g.xz, st0.g.yz, st0.g.zz};
+        d1sq += 3.0 * (tf / s0) * (tf / s0);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) d1sq += (tf * g[i] / s0) * (tf * g[i] / s0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) d1sq += (tf * st0.d[i] / s0) * (tf * st0.d[i] / s0);
+        const double d0 = sqrt(d0sq / 56.0), d1 = sqrt(d1sq / 56.0);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, interval_length);
+        // y1 = y0 + h0 f0 ; f1 = fun(t0 + h0, y1) ; d2 = RMS((f1 - f0)/scale) / h0
+        const double hs0 = h0 * tf;
+        double x1[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x1[i] = fma(hs0, st0.k[i], x[i]);
+        AdStage stA;
+        bad |= ad_eval<J2>(P, x1, h0 * ilen, u0x, u0y, u0z, dux, duy, duz, stA);
+        double d2sq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const double sc = atol + fabs(x[i]) * rtol;
+            const double df = tf * (stA.k[i] - st0.k[i]) / sc;
+            d2sq += df * df;
+        }
+        // Phi1 = I + hs0 * A0 (columns): p_r = e_c(r) + hs0 * e_{c-3}, p_v = e_{c-3}(v) + hs0 * (G0[:,c] | d0)
+        // f1 = A1 Phi1: rows r: Phi1_v ; rows v: G1 Phi1_r + d1 * Phi1[6][c]
+        const double g1[9] = {stA.g.xx, stA.g.xy, stA.g.xz, stA.g.xy, stA.g.yy, stA.g.yz, stA.g.xz, stA.g.yz, stA.g.zz};
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            double p1r[3], p1v[3], f0r[3], f0v[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                f0r[a] = (c == a + 3) ? 1.0 : 0.0;
+                f0v[a] = (c < 3) ? g[a * 3 + c] : ((c == 6) ? st0.d[a] : 0.0);
+                p1r[a] = ((c == a) ? 1.0 : 0.0) + hs0 * f0r[a];
+                p1v[a] = ((c == a + 3) ? 1.0 : 0.0) + hs0 * f0v[a];
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double f1r = p1v[a];
+                double f1v = g1[a * 3 + 0] * p1r[0] + g1[a * 3 + 1] * p1r[1] + g1[a * 3 + 2] * p1r[2];
+                if (c == 6) f1v += stA.d[a];
+                const double scr = (c == a) ? s1 : s0, scv = (c == a + 3) ? s1 : s0;
+                const double e1 = tf * (f1r - f0r[a]) / scr, e2 = tf * (f1v - f0v[a]) / scv;
+                d2sq += e1 * e1 + e2 * e2;
+            }
+        }
+        const double d2 = sqrt(d2sq / 56.0) / h0;
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+        h_abs = fmin(fmin(100.0 * h0, h1), fmin(interval_length, max_step));
+    }
+
+    // ---- solve_ivp main loop ----------------------------------------------------------------------------------
+    while (t < t1 && !fail) {
+        const double min_step = 10.0 * fabs(nextafter(t, CUDART_INF) - t);
+        if (h_abs > max_step) h_abs = max_step;
+        else if (h_abs < min_step) h_abs = min_step;
+        bool accepted = false, rejected = false;
+        double t_new = t, h = 0.0;
+        double xn[7];
+        AdStage st6;
+        while (!accepted) {
+            if (h_abs < min_step) {
+                fail = 1;
+                break;
+            }
+            t_new = t + h_abs;
+            if (t_new - t1 > 0.0) t_new = t1;
+            h = t_new - t;
+            h_abs = fabs(h);
+            const double hs = h * tf;
+            // -- state stages (registers) ------------------------------------------------------------------------
+            double kx[7][7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) kx[0][i] = st0.k[i];
+            ad_store_stage<BLOCK>(sm, 0, st0);
+            const double cs[6] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
+#pragma unroll
+            for (int s = 1; s < 6; ++s) {
+                double xs_[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    double dy = 0.0;
+#pragma unroll
+                    for (int l = 0; l < s; ++l) dy = fma(kx[l][i], kDpA[s][l], dy);
+                    xs_[i] = fma(dy, hs, x[i]);
+                }
+                AdStage sg;
+                bad |= ad_eval<J2>(P, xs_, (t + cs[s] * h - t0) * ilen, u0x, u0y, u0z, dux, duy, duz, sg);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) kx[s][i] = sg.k[i];
+                ad_store_stage<BLOCK>(sm, s, sg);
+            }
+            const double bw[6] = {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+            const double ew[7] = {-71.0 / 57600, 0.0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                double dy = 0.0;
+#pragma unroll
+                for (int l = 0; l < 6; ++l) dy = fma(kx[l][i], bw[l], dy);
+                xn[i] = fma(hs, dy, x[i]);
+            }
+            bad |= ad_eval<J2>(P, xn, (t + h - t0) * ilen, u0x, u0y, u0z, dux, duy, duz, st6);
+            ad_store_stage<BLOCK>(sm, 6, st6);
+            double esum = 0.0;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                double e = st6.k[i] * ew[6];
+#pragma unroll
+                for (int l = 0; l < 6; ++l) e = fma(kx[l][i], ew[l], e);
+                const double q = e * hs * fast_rcp(atol + fmax(fabs(x[i]), fabs(xn[i])) * rtol);
+                esum = fma(q, q, esum);
+            }
+            // -- Phi columns (shared memory, dynamic loop) --------------------------------------------------------
+#pragma unroll 1
+            for (int c = 0; c < 7; ++c) {
+                const double dflag = (c == 6) ? 1.0 : 0.0;
+                double p[6], kr[7][3], kv[7][3];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) p[i] = SM(cur + c * 6 + i);
+#pragma unroll
+                for (int s = 0; s < 7; ++s) {
+                    double q[6];
+                    if (s == 0) {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) q[i] = p[i];
+                    } else if (s < 6) {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            double dy = 0.0;
+#pragma unroll
+                            for (int l = 0; l < s; ++l) dy = fma((i < 3) ? kr[l][i] : kv[l][i - 3], kDpA[s][l], dy);
+                            q[i] = fma(dy, hs, p[i]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            double dy = 0.0;
+#pragma unroll
+                            for (int l = 0; l < 6; ++l) dy = fma((i < 3) ? kr[l][i] : kv[l][i - 3], bw[l], dy);
+                            q[i] = fma(hs, dy, p[i]);
+                        }
+                        // q is the new column: error estimate and store
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) SM(nxt + c * 6 + i) = q[i];
+                    }
+                    const int b = kAdGs + s * 9;
+                    const double gxx = SM(b), gxy = SM(b + 1), gxz = SM(b + 2), gyy = SM(b + 3), gyz = SM(b + 4), gzz = SM(b + 5);
+                    const double dx = SM(b + 6) * dflag, dy_ = SM(b + 7) * dflag, dz = SM(b + 8) * dflag;
+                    kr[s][0] = q[3];
+                    kr[s][1] = q[4];
+                    kr[s][2] = q[5];
+                    kv[s][0] = fma(gxz, q[2], fma(gxy, q[1], fma(gxx, q[0], dx)));
+                    kv[s][1] = fma(gyz, q[2], fma(gyy, q[1], fma(gxy, q[0], dy_)));
+                    kv[s][2] = fma(gzz, q[2], fma(gyz, q[1], fma(gxz, q[0], dz)));
+                    if (s == 6) {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            double e = 0.0;
+#pragma unroll
+                            for (int l = 0; l < 7; ++l) e = fma((i < 3) ? kr[l][i] : kv[l][i - 3], ew[l], e);
+                            const double qq = e * hs * fast_rcp(atol + fmax(fabs(p[i]), fabs(q[i])) * rtol);
+                            esum = fma(qq, qq, esum);
+                        }
+                    }
+                }
+            }
+            const double err = sqrt(esum * (1.0 / 56.0));
+            if (!(err >= 1.0)) {   // also accepts a NaN error so that a poisoned unit terminates (status flags it)
+                double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+                if (rejected) factor = fmin(1.0, factor);
+                if (!(factor == factor)) factor = 1.0;
+                h_abs *= factor;
+                accepted = true;
+            } else {
+                h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+                rejected = true;
+            }
+        }
+        if (fail) break;
+        // ---- accepted: trapezoid panel [t, t_new] (np.trapz, x = sol.t) ------------------------------------------
+        const double w = 0.5 * (t_new - t);
+        ad_node<BLOCK>(sm, cur, P, x, st0, w, (t - t0) * ilen);
+        ad_node<BLOCK>(sm, nxt, P, xn, st6, w, (t_new - t0) * ilen);
+        const int tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = xn[i];
+        st0 = st6;
+        t = t_new;
+        if (++nodes > 4096) fail = 1;
+    }
+
+    double pr[7][3], pv[7][3];
+    ad_load_phi<BLOCK>(sm, cur, pr, pv);
+    const int nonfinite = epilogue_store<BLOCK, NDST>(sm, pr, pv, tf, 1.0, dst, pitch, offset + gid);
+    if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : (fail ? 3 : 0));
+    if (n_nodes) n_nodes[gid] = nodes;
+}
+#undef SM
+
+}  // namespace mpc

@@ -181,6 +181,165 @@ struct DstTab {  // destination buffers of the (optionally multi-destination) So
     double *p[kMaxDst];
 };
 
+// Quadrature-node accumulation shared by the fixed-step and the adaptive kernel:
+//   acc += w * Phi^-1 [Duf, Sigma, xi']   and   acc1 += w*lambda+ * Phi^-1 Duf      (ws = w * lambda+)
+// with Phi given by its columns (pr, pv), Phi^-1 from the symplectic structure, and the slots laid out as
+// documented at kAccSlots.  linearize_discretize.py:63-75.
+#define ACC(e) acc[(e) * BLOCK]
+template <int BLOCK>
+__device__ __forceinline__ void node_accumulate(volatile double *acc, const double (&pr)[7][3], const double (&pv)[7][3],
+                                                const DiscParams &P, double im, double ux, double uy, double uz,
+                                                double iun, double md1, double vx, double vy, double vz, double a1x,
+                                                double a1y, double a1z, double grx, double gry, double grz, double w,
+                                                double ws)
+{
+    // Duf = [0; I/m; b^T],  b = -u / (G0 ISP |u|)  (0 when |u| <= eps)      (:200-212)
+    const double bs = -P.inv_ve * iun;
+    const double b[3] = {bs * ux, bs * uy, bs * uz};
+    // Sigma = f(tf=1) = [v; a; mdot] (:252-253);  xi' = -[v; G r; mdot_B] with mdot_B the
+    // (Duf u) last row, which is 0 under the eps guard
+    const double mdb = (iun != 0.0) ? md1 : 0.0;
+    // Row pairs: column 3+a of Phi gives row a of every Phi^-1 product, column a gives row 3+a
+    //   e = -Phi6^-1 c (c = column 6):  et[a] = pr[3+a].cv - pv[3+a].cr ,  eb[a] = pv[a].cr - pr[a].cv
+    //   Q = Phi^-1 Duf:   row a: -pr[3+a][j]/m + b_j et[a] ;  row 3+a: pr[a][j]/m + b_j eb[a]
+    //   Phi^-1 w = [Phi6^-1 w6 + e wm ; wm] :  row a: pv[3+a].wr - pr[3+a].wv ;  row 3+a: pr[a].wv - pv[a].wr
+    // The 16 accumulators of a row pair are loaded together, updated, stored together (the volatile
+    // accesses keep program order, so grouping them exposes one shared-memory latency per group).
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double A0t[3], A1t[3], A0b[3], A1b[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            A0t[j] = ACC(a * 3 + j);
+            A1t[j] = ACC(18 + a * 3 + j);
+            A0b[j] = ACC(9 + a * 3 + j);
+            A1b[j] = ACC(27 + a * 3 + j);
+        }
+        double ASt = ACC(36 + a), ASb = ACC(39 + a), AXt = ACC(42 + a), AXb = ACC(45 + a);
+        double et = fma(pr[3 + a][0], pv[6][0], fma(pr[3 + a][1], pv[6][1], pr[3 + a][2] * pv[6][2]));
+        et = fma(-pv[3 + a][0], pr[6][0], fma(-pv[3 + a][1], pr[6][1], fma(-pv[3 + a][2], pr[6][2], et)));
+        double eb = fma(pv[a][0], pr[6][0], fma(pv[a][1], pr[6][1], pv[a][2] * pr[6][2]));
+        eb = fma(-pr[a][0], pv[6][0], fma(-pr[a][1], pv[6][1], fma(-pr[a][2], pv[6][2], eb)));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double qt = fma(b[j], et, -im * pr[3 + a][j]);
+            const double qb = fma(b[j], eb, im * pr[a][j]);
+            A0t[j] = fma(w, qt, A0t[j]);
+            A1t[j] = fma(ws, qt, A1t[j]);
+            A0b[j] = fma(w, qb, A0b[j]);
+            A1b[j] = fma(ws, qb, A1b[j]);
+        }
+        // the v-part of Sigma and xi' differ only in sign: share the dot products with v
+        const double dvt = fma(pv[3 + a][0], vx, fma(pv[3 + a][1], vy, pv[3 + a][2] * vz));
+        const double dvb = fma(pv[a][0], vx, fma(pv[a][1], vy, pv[a][2] * vz));
+        const double st = fma(-pr[3 + a][0], a1x, fma(-pr[3 + a][1], a1y, fma(-pr[3 + a][2], a1z, fma(et, md1, dvt))));
+        const double xt = fma(pr[3 + a][0], grx, fma(pr[3 + a][1], gry, fma(pr[3 + a][2], grz, -fma(et, mdb, dvt))));
+        const double sb = fma(pr[a][0], a1x, fma(pr[a][1], a1y, fma(pr[a][2], a1z, fma(eb, md1, -dvb))));
+        const double xb = fma(-pr[a][0], grx, fma(-pr[a][1], gry, fma(-pr[a][2], grz, fma(-eb, mdb, dvb))));
+        ASt = fma(w, st, ASt);
+        ASb = fma(w, sb, ASb);
+        AXt = fma(w, xt, AXt);
+        AXb = fma(w, xb, AXb);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            ACC(a * 3 + j) = A0t[j];
+            ACC(18 + a * 3 + j) = A1t[j];
+            ACC(9 + a * 3 + j) = A0b[j];
+            ACC(27 + a * 3 + j) = A1b[j];
+        }
+        ACC(36 + a) = ASt;
+        ACC(39 + a) = ASb;
+        ACC(42 + a) = AXt;
+        ACC(45 + a) = AXb;
+    }
+    {   // row 6: Phi^-1 row 6 = e7^T, so the integrands are the last rows of Duf, Sigma, xi'
+        double m0[3], m1[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            m0[j] = ACC(48 + j);
+            m1[j] = ACC(51 + j);
+        }
+        double mS = ACC(54), mX = ACC(55);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            ACC(48 + j) = fma(w, b[j], m0[j]);
+            ACC(51 + j) = fma(ws, b[j], m1[j]);
+        }
+        ACC(54) = fma(w, md1, mS);
+        ACC(55) = fma(-w, mdb, mX);
+    }
+}
+
+// Epilogue shared by both kernels: A_k = Phi_end; [B_kp B_kn Sigma_k xi_k] = Phi_end * integrals, with the
+// integrals scaled by sB (B and xi carry tf, :182,214) / sS (Sigma does not, :252); SoA store to NDST buffers.
+// linearize_discretize.py:43-44,77-80.  Returns nonzero when a stored value is not finite.
+template <int BLOCK, int NDST>
+__device__ __forceinline__ int epilogue_store(volatile double *acc, const double (&pr)[7][3], const double (&pv)[7][3],
+                                              double sB, double sS, const DstTab &dst, long long pitch, long long col)
+{
+    double *dsts[NDST];
+#pragma unroll
+    for (int d = 0; d < NDST; ++d) dsts[d] = dst.p[d];
+    int nonfinite = 0;
+    auto store = [&](int row, double v) {
+        nonfinite |= !(fabs(v) <= 1.79769313486231570e308);
+#pragma unroll
+        for (int d = 0; d < NDST; ++d) dsts[d][(long long)row * pitch + col] = v;
+    };
+    // A_k = Phi_end (row-major 7x7)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            store(a * 7 + c, pr[c][a]);
+            store((a + 3) * 7 + c, pv[c][a]);
+        }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) store(42 + c, (c == 6) ? 1.0 : 0.0);
+    // Bp = sB*I1, Bn = sB*(I0 - I1), Sigma = sS*IS, xi = sB*IX
+    // result row a: sum_c Phi[a][c] I[c][.],  Phi[a][c] = pr[c][a] (a<3) / pv[c][a-3] (a<6); row 6 = I[6][.]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double I[7];
+        if (j < 3) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) I[c] = sB * ACC(18 + c * 3 + j);
+            I[6] = sB * ACC(51 + j);
+        } else if (j < 6) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) I[c] = sB * (ACC(c * 3 + (j - 3)) - ACC(18 + c * 3 + (j - 3)));
+            I[6] = sB * (ACC(48 + (j - 3)) - ACC(51 + (j - 3)));
+        } else if (j == 6) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) I[c] = sS * ACC(36 + c);
+            I[6] = sS * ACC(54);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) I[c] = sB * ACC(42 + c);
+            I[6] = sB * ACC(55);
+        }
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+            double v;
+            if (a < 3) {
+                v = pr[0][a] * I[0];
+#pragma unroll
+                for (int c = 1; c < 7; ++c) v = fma(pr[c][a], I[c], v);
+            } else if (a < 6) {
+                v = pv[0][a - 3] * I[0];
+#pragma unroll
+                for (int c = 1; c < 7; ++c) v = fma(pv[c][a - 3], I[c], v);
+            } else {
+                v = I[6];
+            }
+            const int row = (j < 3) ? (49 + a * 3 + j) : (j < 6) ? (70 + a * 3 + (j - 3)) : (j == 6) ? (91 + a) : (98 + a);
+            store(row, v);
+        }
+    }
+    return nonfinite;
+}
+#undef ACC
+
 template <bool J2, int BLOCK, int MAXREG, int NDST>
 __global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG)
 discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ tf_arr,
@@ -253,81 +412,7 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             const double sfrac = (double)n * inv_n;                     // lambda+   (:61)
             const double w = (n == 0 || n == n_sub) ? 0.5 : 1.0;        // trapezoid end weights (:77-80)
             const double ws = w * sfrac;
-            // Duf = [0; I/m; b^T],  b = -u / (G0 ISP |u|)  (0 when |u| <= eps)      (:200-212)
-            const double bs = -P.inv_ve * iun;
-            const double b[3] = {bs * ux, bs * uy, bs * uz};
-            // Sigma = f(tf=1) = [v; a; mdot] (:252-253);  xi' = -[v; G r; mdot_B] with mdot_B the
-            // (Duf u) last row, which is 0 under the eps guard
-            const double mdb = (iun != 0.0) ? md1 : 0.0;
-            // Row pairs: column 3+a of Phi gives row a of every Phi^-1 product, column a gives row 3+a
-            //   e = -Phi6^-1 c (c = column 6):  et[a] = pr[3+a].cv - pv[3+a].cr ,  eb[a] = pv[a].cr - pr[a].cv
-            //   Q = Phi^-1 Duf:   row a: -pr[3+a][j]/m + b_j et[a] ;  row 3+a: pr[a][j]/m + b_j eb[a]
-            //   Phi^-1 w = [Phi6^-1 w6 + e wm ; wm] :  row a: pv[3+a].wr - pr[3+a].wv ;  row 3+a: pr[a].wv - pv[a].wr
-            // The 16 accumulators of a row pair are loaded together, updated, stored together (the volatile
-            // accesses keep program order, so grouping them exposes one shared-memory latency per group).
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                double A0t[3], A1t[3], A0b[3], A1b[3];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    A0t[j] = ACC(a * 3 + j);
-                    A1t[j] = ACC(18 + a * 3 + j);
-                    A0b[j] = ACC(9 + a * 3 + j);
-                    A1b[j] = ACC(27 + a * 3 + j);
-                }
-                double ASt = ACC(36 + a), ASb = ACC(39 + a), AXt = ACC(42 + a), AXb = ACC(45 + a);
-                double et = fma(pr[3 + a][0], pv[6][0], fma(pr[3 + a][1], pv[6][1], pr[3 + a][2] * pv[6][2]));
-                et = fma(-pv[3 + a][0], pr[6][0], fma(-pv[3 + a][1], pr[6][1], fma(-pv[3 + a][2], pr[6][2], et)));
-                double eb = fma(pv[a][0], pr[6][0], fma(pv[a][1], pr[6][1], pv[a][2] * pr[6][2]));
-                eb = fma(-pr[a][0], pv[6][0], fma(-pr[a][1], pv[6][1], fma(-pr[a][2], pv[6][2], eb)));
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const double qt = fma(b[j], et, -im * pr[3 + a][j]);
-                    const double qb = fma(b[j], eb, im * pr[a][j]);
-                    A0t[j] = fma(w, qt, A0t[j]);
-                    A1t[j] = fma(ws, qt, A1t[j]);
-                    A0b[j] = fma(w, qb, A0b[j]);
-                    A1b[j] = fma(ws, qb, A1b[j]);
-                }
-                // the v-part of Sigma and xi' differ only in sign: share the dot products with v
-                const double dvt = fma(pv[3 + a][0], vx, fma(pv[3 + a][1], vy, pv[3 + a][2] * vz));
-                const double dvb = fma(pv[a][0], vx, fma(pv[a][1], vy, pv[a][2] * vz));
-                const double st = fma(-pr[3 + a][0], a1x, fma(-pr[3 + a][1], a1y, fma(-pr[3 + a][2], a1z, fma(et, md1, dvt))));
-                const double xt = fma(pr[3 + a][0], grx, fma(pr[3 + a][1], gry, fma(pr[3 + a][2], grz, -fma(et, mdb, dvt))));
-                const double sb = fma(pr[a][0], a1x, fma(pr[a][1], a1y, fma(pr[a][2], a1z, fma(eb, md1, -dvb))));
-                const double xb = fma(-pr[a][0], grx, fma(-pr[a][1], gry, fma(-pr[a][2], grz, fma(-eb, mdb, dvb))));
-                ASt = fma(w, st, ASt);
-                ASb = fma(w, sb, ASb);
-                AXt = fma(w, xt, AXt);
-                AXb = fma(w, xb, AXb);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    ACC(a * 3 + j) = A0t[j];
-                    ACC(18 + a * 3 + j) = A1t[j];
-                    ACC(9 + a * 3 + j) = A0b[j];
-                    ACC(27 + a * 3 + j) = A1b[j];
-                }
-                ACC(36 + a) = ASt;
-                ACC(39 + a) = ASb;
-                ACC(42 + a) = AXt;
-                ACC(45 + a) = AXb;
-            }
-            {   // row 6: Phi^-1 row 6 = e7^T, so the integrands are the last rows of Duf, Sigma, xi'
-                double m0[3], m1[3];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    m0[j] = ACC(48 + j);
-                    m1[j] = ACC(51 + j);
-                }
-                double mS = ACC(54), mX = ACC(55);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    ACC(48 + j) = fma(w, b[j], m0[j]);
-                    ACC(51 + j) = fma(ws, b[j], m1[j]);
-                }
-                ACC(54) = fma(w, md1, mS);
-                ACC(55) = fma(-w, mdb, mX);
-            }
+            node_accumulate<BLOCK>(acc, pr, pv, P, im, ux, uy, uz, iun, md1, vx, vy, vz, a1x, a1y, a1z, grx, gry, grz, w, ws);
         }
         if (n == n_sub) break;
 
@@ -410,66 +495,7 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     }
 
     // ---- epilogue: left-multiply by Phi_end, scale by the step, store SoA -----------------------
-    double *dsts[NDST];
-#pragma unroll
-    for (int d = 0; d < NDST; ++d) dsts[d] = dst.p[d];
-    const long long col = offset + gid;
-    int nonfinite = 0;
-    auto store = [&](int row, double v) {
-        nonfinite |= !(fabs(v) <= 1.79769313486231570e308);
-#pragma unroll
-        for (int d = 0; d < NDST; ++d) dsts[d][(long long)row * pitch + col] = v;
-    };
-    // A_k = Phi_end (row-major 7x7)
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            store(a * 7 + c, pr[c][a]);
-            store((a + 3) * 7 + c, pv[c][a]);
-        }
-#pragma unroll
-    for (int c = 0; c < 7; ++c) store(42 + c, (c == 6) ? 1.0 : 0.0);
-    // integrals (h folded in): Bp = hs*I1, Bn = hs*(I0 - I1), Sigma = h*IS, xi = hs*IX
-    // result row a: sum_c Phi[a][c] I[c][.],  Phi[a][c] = pr[c][a] (a<3) / pv[c][a-3] (a<6); row 6 = I[6][.]
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        double I[7];
-        if (j < 3) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) I[c] = hs * ACC(18 + c * 3 + j);
-            I[6] = hs * ACC(51 + j);
-        } else if (j < 6) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) I[c] = hs * (ACC(c * 3 + (j - 3)) - ACC(18 + c * 3 + (j - 3)));
-            I[6] = hs * (ACC(48 + (j - 3)) - ACC(51 + (j - 3)));
-        } else if (j == 6) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) I[c] = h * ACC(36 + c);
-            I[6] = h * ACC(54);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) I[c] = hs * ACC(42 + c);
-            I[6] = hs * ACC(55);
-        }
-#pragma unroll
-        for (int a = 0; a < 7; ++a) {
-            double v;
-            if (a < 3) {
-                v = pr[0][a] * I[0];
-#pragma unroll
-                for (int c = 1; c < 7; ++c) v = fma(pr[c][a], I[c], v);
-            } else if (a < 6) {
-                v = pv[0][a - 3] * I[0];
-#pragma unroll
-                for (int c = 1; c < 7; ++c) v = fma(pv[c][a - 3], I[c], v);
-            } else {
-                v = I[6];
-            }
-            const int row = (j < 3) ? (49 + a * 3 + j) : (j < 6) ? (70 + a * 3 + (j - 3)) : (j == 6) ? (91 + a) : (98 + a);
-            store(row, v);
-        }
-    }
+    const int nonfinite = epilogue_store<BLOCK, NDST>(acc, pr, pv, hs, h, dst, pitch, offset + gid);
     if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : 0);
 #undef ACC
 }

@@ -11,7 +11,10 @@
 #include <cstring>
 #include <vector>
 
+#include <math_constants.h>
+
 #include "discretize_kernel.cuh"
+#include "discretize_adaptive_kernel.cuh"
 #include "propagate_kernel.cuh"
 
 namespace {
@@ -124,6 +127,43 @@ int launch_disc(const double *x, const double *u, const double *tf, const mpc::D
     }
 }
 
+struct AdaptiveOpts {   // scipy solve_ivp(RK45) controls of the reference's default quadrature mode
+    double rtol, atol, max_step;
+    int32_t *n_nodes;
+};
+
+template <bool J2>
+int launch_adaptive(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                    const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                    cudaStream_t st)
+{
+    constexpr int BLOCK = 32;
+    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1>;
+    const size_t smem = (size_t)mpc::kAdSlots * BLOCK * sizeof(double);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured_dev = dev;
+    }
+    const long long n_int = (long long)n_sats * (K - 1);
+    const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, o.rtol, o.atol, o.max_step, dst, pitch, offset, status,
+                                    o.n_nodes);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
+int check_adaptive(double rtol, double atol, double max_step)
+{
+    if (!(rtol > 0.0) || !(atol > 0.0) || !(max_step > 0.0))
+        return fail(MPC_E_INVALID, "adaptive mode needs rtol, atol, max_step > 0 (got %g, %g, %g)", rtol, atol, max_step);
+    return MPC_SUCCESS;
+}
+
 int check_disc_args(const void *x, const void *u, const void *tf, const mpc_params *p, int n_sats, int K, int n_sub)
 {
     if (!x || !u || !tf || !p) return fail(MPC_E_INVALID, "null pointer argument");
@@ -202,7 +242,8 @@ struct mpc_ctx {
     std::vector<cudaEvent_t> ev;  // one per chunk slot
     // grow-only device workspace
     double *d_x = nullptr, *d_u = nullptr, *d_tf = nullptr, *d_out = nullptr, *d_y0 = nullptr, *d_tab = nullptr;
-    int32_t *d_status = nullptr, *d_status2 = nullptr;
+    int32_t *d_status = nullptr, *d_status2 = nullptr, *d_nodes = nullptr;
+    size_t cap_nodes = 0;
     size_t cap_x = 0, cap_u = 0, cap_tf = 0, cap_out = 0, cap_y0 = 0, cap_tab = 0, cap_status = 0, cap_status2 = 0;
 };
 
@@ -306,6 +347,25 @@ int mpc_discretize_batch_multi(const double *x, const double *u, const double *t
                        (cudaStream_t)stream);
 }
 
+int mpc_discretize_batch_adaptive(const double *x, const double *u, const double *tf, const mpc_params *p,
+                                  int n_sats, int K, double rtol, double atol, double max_step, double *out,
+                                  int64_t out_pitch, int64_t out_offset, int32_t *status, int32_t *n_nodes, void *stream)
+{
+    int rc = check_disc_args(x, u, tf, p, n_sats, K, 1);
+    if (rc) return rc;
+    if ((rc = check_adaptive(rtol, atol, max_step))) return rc;
+    if (!out) return fail(MPC_E_INVALID, "null output");
+    const long long n_int = (long long)n_sats * (K - 1);
+    if (out_pitch < out_offset + n_int || out_offset < 0) return fail(MPC_E_INVALID, "out_pitch/out_offset do not hold the batch");
+    if (n_int == 0) return MPC_SUCCESS;
+    mpc::DstTab tab{};
+    tab.p[0] = out;
+    const AdaptiveOpts o{rtol, atol, max_step, n_nodes};
+    const mpc::DiscParams P = disc_params(p);
+    return p->include_j2 ? launch_adaptive<true>(x, u, tf, P, n_sats, K, o, tab, out_pitch, out_offset, status, (cudaStream_t)stream)
+                         : launch_adaptive<false>(x, u, tf, P, n_sats, K, o, tab, out_pitch, out_offset, status, (cudaStream_t)stream);
+}
+
 int mpc_propagate_batch(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
                         int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status, void *stream)
 {
@@ -344,6 +404,7 @@ int mpc_ctx_destroy(mpc_ctx *c)
     cudaFree(c->d_tab);
     cudaFree(c->d_status);
     cudaFree(c->d_status2);
+    cudaFree(c->d_nodes);
     delete c;
     return MPC_SUCCESS;
 }
@@ -364,13 +425,15 @@ void mpc_host_free(void *p)
     if (p) cudaFreeHost(p);
 }
 
-int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf,
-                              const mpc_params *p, int n_sats, int K, int n_sub, double *out_host,
-                              int32_t *status_host)
+// shared body of the two host-buffer discretization entry points (ad == nullptr: fixed-step kernel)
+static int disc_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf, const mpc_params *p, int n_sats,
+                     int K, int n_sub, const AdaptiveOpts *ad, double *out_host, int32_t *status_host,
+                     int32_t *n_nodes_host)
 {
     if (!ctx || !out_host) return fail(MPC_E_INVALID, "null ctx/out");
     int rc = check_disc_args(x, u, tf, p, n_sats, K, n_sub);
     if (rc) return rc;
+    if (ad && (rc = check_adaptive(ad->rtol, ad->atol, ad->max_step))) return rc;
     const long long n_int = (long long)n_sats * (K - 1);
     if (n_int == 0) return MPC_SUCCESS;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -379,6 +442,7 @@ int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, co
     if ((rc = ensure(ctx->d_tf, ctx->cap_tf, (size_t)n_sats))) return rc;
     if ((rc = ensure(ctx->d_out, ctx->cap_out, (size_t)n_int * MPC_OUT_ROWS))) return rc;
     if ((rc = ensure(ctx->d_status, ctx->cap_status, (size_t)n_int))) return rc;
+    if (ad && n_nodes_host && (rc = ensure(ctx->d_nodes, ctx->cap_nodes, (size_t)n_int))) return rc;
     const int cs = chunk_sats(n_sats, K);
     const int n_chunks = (n_sats + cs - 1) / cs;
     if ((rc = ensure_events(ctx, (size_t)n_chunks))) return rc;
@@ -386,18 +450,23 @@ int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, co
     CUDA_TRY(cudaMemcpyAsync(ctx->d_tf, tf, (size_t)n_sats * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
     for (int c = 0; c < n_chunks; ++c) {
         const int s0 = c * cs, ns = std::min(cs, n_sats - s0);
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_x + (size_t)s0 * 7 * K, x + (size_t)s0 * 7 * K, (size_t)ns * 7 * K * sizeof(double),
+        const double *dx = ctx->d_x + (size_t)s0 * 7 * K, *du = ctx->d_u + (size_t)s0 * 3 * K;
+        CUDA_TRY(cudaMemcpyAsync((void *)dx, x + (size_t)s0 * 7 * K, (size_t)ns * 7 * K * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->s_compute));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_u + (size_t)s0 * 3 * K, u + (size_t)s0 * 3 * K, (size_t)ns * 3 * K * sizeof(double),
+        CUDA_TRY(cudaMemcpyAsync((void *)du, u + (size_t)s0 * 3 * K, (size_t)ns * 3 * K * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->s_compute));
         mpc::DstTab tab{};
         tab.p[0] = ctx->d_out;
         const long long off = (long long)s0 * (K - 1);
-        rc = p->include_j2
-                 ? launch_disc_n<true, 1>(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, P, ns,
-                                          K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute)
-                 : launch_disc_n<false, 1>(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, P,
-                                           ns, K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute);
+        if (ad) {
+            AdaptiveOpts o = *ad;
+            o.n_nodes = n_nodes_host ? ctx->d_nodes + off : nullptr;
+            rc = p->include_j2 ? launch_adaptive<true>(dx, du, ctx->d_tf + s0, P, ns, K, o, tab, n_int, off, ctx->d_status + off, ctx->s_compute)
+                               : launch_adaptive<false>(dx, du, ctx->d_tf + s0, P, ns, K, o, tab, n_int, off, ctx->d_status + off, ctx->s_compute);
+        } else {
+            rc = p->include_j2 ? launch_disc_n<true, 1>(dx, du, ctx->d_tf + s0, P, ns, K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute)
+                               : launch_disc_n<false, 1>(dx, du, ctx->d_tf + s0, P, ns, K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute);
+        }
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ctx->ev[c], ctx->s_compute));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev[c], 0));
@@ -406,9 +475,27 @@ int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, co
     if (status_host)
         CUDA_TRY(cudaMemcpyAsync(status_host, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                  ctx->s_copy));
+    if (ad && n_nodes_host)
+        CUDA_TRY(cudaMemcpyAsync(n_nodes_host, ctx->d_nodes, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 ctx->s_copy));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_compute));
     return MPC_SUCCESS;
+}
+
+int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf,
+                              const mpc_params *p, int n_sats, int K, int n_sub, double *out_host,
+                              int32_t *status_host)
+{
+    return disc_host(ctx, x, u, tf, p, n_sats, K, n_sub, nullptr, out_host, status_host, nullptr);
+}
+
+int mpc_discretize_batch_adaptive_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf,
+                                       const mpc_params *p, int n_sats, int K, double rtol, double atol,
+                                       double max_step, double *out_host, int32_t *status_host, int32_t *n_nodes_host)
+{
+    const AdaptiveOpts o{rtol, atol, max_step, nullptr};
+    return disc_host(ctx, x, u, tf, p, n_sats, K, 1, &o, out_host, status_host, n_nodes_host);
 }
 
 static int upload_table(mpc_ctx *ctx, const mpc_controller *ctrl, int n_sats, cudaStream_t st)

@@ -3,8 +3,6 @@
 Constructor, attributes, `discretize(f, x, u, tf)` signature, return order (A_k, B_kp, B_kn, Sigma_k, xi_k)
 and shapes are the reference's, so `optimizer.py:243-249` can hold one of these as `self.d` unchanged.
 """
-import warnings
-
 import numpy as np
 
 from . import batch
@@ -28,8 +26,10 @@ class Discretizer:
         # numerical integration parameters (linearize_discretize.py:108-109)
         self.integrator_steps = 101
         self.use_uniform_steps = False
+        # scipy.integrate.solve_ivp defaults (the reference passes neither, linearize_discretize.py:37-41)
+        self.ivp_rtol = 1e-3
+        self.ivp_atol = 1e-6
         self.device = 0
-        self._warned = False
 
     # -- option handling ---------------------------------------------------------------------------
     def _check_options(self, f):
@@ -49,14 +49,8 @@ class Discretizer:
         if self.ivp_solver != 'RK45':
             raise NotImplementedError(f"ivp_solver={self.ivp_solver!r}: the device integrator is fixed-step RK4 "
                                       "on the reference's node grid (stated against RK45)")
-        if int(self.integrator_steps) < 2:
+        if self.use_uniform_steps and int(self.integrator_steps) < 2:
             raise ValueError("integrator_steps must be >= 2")
-        if not self.use_uniform_steps and not self._warned:
-            warnings.warn("use_uniform_steps=False: quadrature nodes are the uniform integrator_steps grid on "
-                          "the device (the reference's use_uniform_steps=True node set), not scipy's adaptive "
-                          "step sequence; results differ from the reference default by its own quadrature "
-                          "error (see DESIGN.md)", stacklevel=3)
-            self._warned = True
 
     # -- the reference entry point -------------------------------------------------------------------
     def discretize(self, f, x, u, tf):
@@ -81,8 +75,14 @@ class Discretizer:
         if u.shape[-1] != K:
             raise ValueError(f"u has {u.shape[-1]} columns but x has {K}: the device first-order hold needs u on "
                              "the same K nodes as x")
+        # use_uniform_steps=False (the reference default): quadrature on the steps scipy's RK45 controller accepts
+        # (replayed on the device, scipy's default rtol/atol as the reference passes none);
+        # use_uniform_steps=True: fixed-step RK4 on the uniform integrator_steps grid.
+        adaptive = None if self.use_uniform_steps else dict(rtol=self.ivp_rtol, atol=self.ivp_atol,
+                                                            max_step=float(self.ivp_max_step))
         return batch.discretize_batch(x, u, tf, self.const, include_J2=self.include_J2, include_drag=False,
-                                      n_sub=int(self.integrator_steps) - 1, out=out, device=self.device, check=check)
+                                      n_sub=max(1, int(self.integrator_steps) - 1), out=out, device=self.device,
+                                      check=check, adaptive=adaptive)
 
     @staticmethod
     def extract_uk(x_k, tau_k, controller):

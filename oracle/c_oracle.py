@@ -43,6 +43,9 @@ def lib():
                                            ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            dp, dp, ip, ctypes.c_int]
         _lib.orc_propagate_rk4.restype = ctypes.c_int
+        _lib.orc_discretize_rk45.argtypes = [dp, dp, dp, ctypes.POINTER(OrcParams), ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, ip, ip, ctypes.c_int]
+        _lib.orc_discretize_rk45.restype = ctypes.c_int
         _lib.orc_max_threads.restype = ctypes.c_int
     return _lib
 
@@ -77,6 +80,28 @@ def discretize_batch(x, u, tf, const, include_J2=False, n_sub=100, nthreads=0):
     S = out[:, :, 91:98].transpose(0, 2, 1)
     X = out[:, :, 98:105].transpose(0, 2, 1)
     return A, Bp, Bn, S, X, status.reshape(N, K - 1)
+
+
+def discretize_batch_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6, max_step=1e-2, nthreads=0):
+    """The reference's default mode (quadrature on the accepted RK45 steps).  Returns the same tuple as
+    discretize_batch plus the node count per interval."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    N, _, K = x.shape
+    tf = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    out = np.zeros((N, K - 1, 105))
+    status = np.zeros(N * (K - 1), dtype=np.int32)
+    nodes = np.zeros(N * (K - 1), dtype=np.int32)
+    p = make_params(const, include_J2)
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib().orc_discretize_rk45(_dp(x), _dp(u), _dp(tf), ctypes.byref(p), N, K, rtol, atol, max_step, _dp(out),
+                              status.ctypes.data_as(ip), nodes.ctypes.data_as(ip), nthreads)
+    A = out[:, :, 0:49].reshape(N, K - 1, 7, 7)
+    Bp = out[:, :, 49:70].reshape(N, K - 1, 7, 3)
+    Bn = out[:, :, 70:91].reshape(N, K - 1, 7, 3)
+    S = out[:, :, 91:98].transpose(0, 2, 1)
+    X = out[:, :, 98:105].transpose(0, 2, 1)
+    return A, Bp, Bn, S, X, status.reshape(N, K - 1), nodes.reshape(N, K - 1)
 
 
 def propagate_batch(y0, tf, const, kind=CTRL_ZERO, cparams=(0.0, 0.0, 0.0), table=None, end_tau=1.0,

@@ -276,6 +276,237 @@ int orc_discretize_rk4(const double *x, const double *u, const double *tf, const
     return bad;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Adaptive mode: the reference's DEFAULT quadrature (use_uniform_steps=False, linearize_discretize.py:
+ * 29-30,49-50): nodes are the accepted steps of scipy.integrate.solve_ivp(method='RK45', max_step=1e-2,
+ * rtol=1e-3, atol=1e-6).  scipy is a third-party dependency the reference neither vendors nor pins; this
+ * restates its published algorithm (scipy 1.18.1, integrate/_ivp/rk.py: rk_step, RungeKutta._step_impl,
+ * RK45 tableau; integrate/_ivp/common.py: select_initial_step, norm) -- Dormand-Prince 5(4), local
+ * extrapolation, error norm = RMS of err/(atol + rtol*max(|y|,|y_new|)), SAFETY 0.9, factor clamp
+ * [0.2, 10], first step from Hairer's heuristic.
+ */
+#define ORC_MAX_NODES 512
+
+static const double DP_C[6] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
+static const double DP_A[6][5] = {{0, 0, 0, 0, 0},
+                                  {1.0 / 5, 0, 0, 0, 0},
+                                  {3.0 / 40, 9.0 / 40, 0, 0, 0},
+                                  {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+                                  {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+                                  {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+static const double DP_B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+static const double DP_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+
+static double rms56(const double *v)
+{
+    double s = 0.0;
+    for (int i = 0; i < 56; ++i) s += v[i] * v[i];
+    return sqrt(s) / sqrt(56.0);
+}
+
+typedef struct {
+    const double *u0, *u1;
+    double t0, t1, tf;
+    const orc_params *p;
+    int j2;
+} aug_ctx;
+
+static int aug_fun(const aug_ctx *c, double t, const double *y, double *dy)
+{
+    /* FOH inside one interval (linearize_discretize.py:305-315) */
+    double lp = (t - c->t0) / (c->t1 - c->t0), ln = (c->t1 - t) / (c->t1 - c->t0);
+    double u[3];
+    for (int i = 0; i < 3; ++i) u[i] = ln * c->u0[i] + lp * c->u1[i];
+    return aug_rhs(y, u, c->tf, c->p, c->j2, dy);
+}
+
+/* quadrature-node integrands (linearize_discretize.py:63-75) at state y (Phi, x) and time t:
+ * g[0..20] = Phi^-1 B lam+, g[21..41] = Phi^-1 B lam-, g[42..48] = Phi^-1 Sigma, g[49..55] = Phi^-1 xi */
+static int node_integrands(const aug_ctx *c, double t, const double *y, double *g)
+{
+    double lp = (t - c->t0) / (c->t1 - c->t0), ln = (c->t1 - t) / (c->t1 - c->t0);
+    double un[3], Pinv[49], Bm[21], Dx[49], sig[7], xi[7];
+    const double *xs = y + 49;
+    for (int i = 0; i < 3; ++i) un[i] = ln * c->u0[i] + lp * c->u1[i];
+    if (inv7(y, Pinv)) return 3;
+    duf(xs, un, c->p, Bm);
+    for (int i = 0; i < 21; ++i) Bm[i] *= c->tf;
+    if (dyn(xs, un, c->p, 0, c->j2, sig)) return 1;
+    dxf(xs, un, c->p, c->j2, Dx);
+    for (int i = 0; i < 7; ++i) {
+        double s = 0.0;
+        for (int l = 0; l < 7; ++l) s += c->tf * Dx[i * 7 + l] * xs[l];
+        for (int l = 0; l < 3; ++l) s += Bm[i * 3 + l] * un[l];
+        xi[i] = -s;
+    }
+    for (int i = 0; i < 7; ++i) {
+        double ss = 0.0, sx = 0.0;
+        for (int l = 0; l < 7; ++l) {
+            ss += Pinv[i * 7 + l] * sig[l];
+            sx += Pinv[i * 7 + l] * xi[l];
+        }
+        g[42 + i] = ss;
+        g[49 + i] = sx;
+        for (int j = 0; j < 3; ++j) {
+            double sb = 0.0;
+            for (int l = 0; l < 7; ++l) sb += Pinv[i * 7 + l] * Bm[l * 3 + j];
+            g[i * 3 + j] = sb * lp;
+            g[21 + i * 3 + j] = sb * ln;
+        }
+    }
+    return 0;
+}
+
+static int interval_rk45(const double *xk, const double *u0, const double *u1, double tf, double t0, double t1,
+                         double rtol, double atol, double max_step, const orc_params *p, int j2, double *out,
+                         int *n_nodes)
+{
+    aug_ctx c = {u0, u1, t0, t1, tf, p, j2};
+    double y[56], f[56], K[7][56], ynew[56], fnew[56], tmp[56], sc[56];
+    double acc[56] = {0}, gprev[56], gcur[56];
+    memset(y, 0, sizeof y);
+    for (int i = 0; i < 7; ++i) {
+        y[i * 7 + i] = 1.0;
+        y[49 + i] = xk[i];
+    }
+    double t = t0;
+    if (aug_fun(&c, t, y, f)) return 1;
+    /* select_initial_step (common.py) */
+    double h_abs;
+    {
+        double interval_length = fabs(t1 - t0);
+        for (int i = 0; i < 56; ++i) sc[i] = atol + fabs(y[i]) * rtol;
+        for (int i = 0; i < 56; ++i) tmp[i] = y[i] / sc[i];
+        double d0 = rms56(tmp);
+        for (int i = 0; i < 56; ++i) tmp[i] = f[i] / sc[i];
+        double d1 = rms56(tmp);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        if (h0 > interval_length) h0 = interval_length;
+        for (int i = 0; i < 56; ++i) ynew[i] = y[i] + h0 * f[i];
+        if (aug_fun(&c, t + h0, ynew, fnew)) return 1;
+        for (int i = 0; i < 56; ++i) tmp[i] = (fnew[i] - f[i]) / sc[i];
+        double d2 = rms56(tmp) / h0;
+        double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+        h_abs = fmin(fmin(100 * h0, h1), fmin(interval_length, max_step));
+    }
+    int st = node_integrands(&c, t, y, gprev);
+    if (st) return st;
+    int nodes = 1;
+    while (t < t1) {
+        double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
+        if (h_abs > max_step) h_abs = max_step;
+        else if (h_abs < min_step) h_abs = min_step;
+        int accepted = 0, rejected = 0;
+        double t_new = t, h = 0.0;
+        while (!accepted) {
+            if (h_abs < min_step) return 4;
+            h = h_abs;
+            t_new = t + h;
+            if (t_new - t1 > 0) t_new = t1;
+            h = t_new - t;
+            h_abs = fabs(h);
+            /* rk_step (rk.py) */
+            memcpy(K[0], f, sizeof f);
+            for (int s = 1; s < 6; ++s) {
+                for (int i = 0; i < 56; ++i) {
+                    double dy = 0.0;
+                    for (int l = 0; l < s; ++l) dy += K[l][i] * DP_A[s][l];
+                    tmp[i] = y[i] + dy * h;
+                }
+                if (aug_fun(&c, t + DP_C[s] * h, tmp, K[s])) return 1;
+            }
+            for (int i = 0; i < 56; ++i) {
+                double d = 0.0;
+                for (int l = 0; l < 6; ++l) d += K[l][i] * DP_B[l];
+                ynew[i] = y[i] + h * d;
+            }
+            if (aug_fun(&c, t + h, ynew, fnew)) return 1;
+            memcpy(K[6], fnew, sizeof fnew);
+            for (int i = 0; i < 56; ++i) {
+                double e = 0.0;
+                for (int l = 0; l < 7; ++l) e += K[l][i] * DP_E[l];
+                double scale = atol + fmax(fabs(y[i]), fabs(ynew[i])) * rtol;
+                tmp[i] = e * h / scale;
+            }
+            double err = rms56(tmp);
+            if (err < 1.0) {
+                double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+                if (rejected && factor > 1.0) factor = 1.0;
+                h_abs *= factor;
+                accepted = 1;
+            } else {
+                h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+                rejected = 1;
+            }
+        }
+        /* node t_new: trapezoid panel [t, t_new] (np.trapz with x = sol.t, :77-80) */
+        st = node_integrands(&c, t_new, ynew, gcur);
+        if (st) return st;
+        double w = 0.5 * (t_new - t);
+        for (int i = 0; i < 56; ++i) acc[i] += w * (gprev[i] + gcur[i]);
+        memcpy(gprev, gcur, sizeof gcur);
+        memcpy(y, ynew, sizeof y);
+        memcpy(f, fnew, sizeof f);
+        t = t_new;
+        if (++nodes > ORC_MAX_NODES) return 4;
+    }
+    if (n_nodes) *n_nodes = nodes;
+    memcpy(out, y, 49 * sizeof(double));
+    for (int i = 0; i < 7; ++i) {
+        double ss = 0.0, sx = 0.0;
+        for (int l = 0; l < 7; ++l) {
+            ss += y[i * 7 + l] * acc[42 + l];
+            sx += y[i * 7 + l] * acc[49 + l];
+        }
+        out[91 + i] = ss;
+        out[98 + i] = sx;
+        for (int j = 0; j < 3; ++j) {
+            double sp = 0.0, sn = 0.0;
+            for (int l = 0; l < 7; ++l) {
+                sp += y[i * 7 + l] * acc[l * 3 + j];
+                sn += y[i * 7 + l] * acc[21 + l * 3 + j];
+            }
+            out[49 + i * 3 + j] = sp;
+            out[70 + i * 3 + j] = sn;
+        }
+    }
+    for (int i = 0; i < 105; ++i)
+        if (!isfinite(out[i])) return 2;
+    return 0;
+}
+
+/* Batched adaptive-mode discretization; same layouts as orc_discretize_rk4; n_nodes [N*(K-1)] may be NULL. */
+int orc_discretize_rk45(const double *x, const double *u, const double *tf, const orc_params *p, int N, int K,
+                        double rtol, double atol, double max_step, double *out, int *status, int *n_nodes,
+                        int nthreads)
+{
+    long total = (long)N * (K - 1);
+    int bad = 0;
+    if (K < 2 || N < 1) return 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : bad)
+    for (long i = 0; i < total; ++i) {
+        int s = (int)(i / (K - 1)), k = (int)(i % (K - 1));
+        double xk[7], u0[3], u1[3];
+        for (int c = 0; c < 7; ++c) xk[c] = x[((long)s * 7 + c) * K + k];
+        for (int c = 0; c < 3; ++c) {
+            u0[c] = u[((long)s * 3 + c) * K + k];
+            u1[c] = u[((long)s * 3 + c) * K + k + 1];
+        }
+        /* tau = np.linspace(0, 1, K): start + i*step, last point exactly 1 (linearize_discretize.py:356) */
+        double step = 1.0 / (K - 1);
+        double t0 = k * step, t1 = (k + 1 == K - 1) ? 1.0 : (k + 1) * step;
+        int nn = 0;
+        int st = interval_rk45(xk, u0, u1, tf[s], t0, t1, rtol, atol, max_step, p, p->include_J2, out + i * 105, &nn);
+        if (status) status[i] = st;
+        if (n_nodes) n_nodes[i] = nn;
+        bad += (st != 0);
+    }
+    return bad;
+}
+
 /* controller laws, control.py:20-29,47-53,66-84,104-143 */
 static void ctrl_eval(int kind, const double *cp, const double *tab, int Ku, double end_tau, const double *x,
                       double tau, double *u)

@@ -53,6 +53,42 @@ def test_j2_and_node_count_match_reference_fixtures(M, gold_disc, const):
         assert rel_err(_sel(o, ks), g[f"d3_n21_uni_{n}"]) < TOL_REF, n
 
 
+@pytest.mark.parametrize("sc", ["d0", "d1", "d3", "d4"])
+def test_default_mode_matches_reference_default_fixtures(M, gold_disc, const, sc):
+    """Discretizer as shipped (use_uniform_steps=False): the device replays scipy's RK45 step controller, so the
+    matrices match the unmodified reference's default output (<= 1e-8; observed ~1e-10, the symplectic-inverse
+    defect of the RK45 solution)"""
+    g = gold_disc
+    d = M.Discretizer(const)
+    assert d.use_uniform_steps is False
+    out = d.discretize(M.Simulator.satellite_dynamics, g[sc + "_x"], g[sc + "_u"], float(g[sc + "_tf"]))
+    for n, o in zip(NAMES, out):
+        assert rel_err(o, g[f"{sc}_def_{n}"]) < TOL_REF, (sc, n)
+    if sc == "d3":
+        dj = M.Discretizer(const, include_J2=True)
+        out = dj.discretize(M.Simulator.satellite_dynamics, g["d3_x"], g["d3_u"], 2.0)
+        for n, o in zip(NAMES, out):
+            assert rel_err(_sel(o, g["d3_j2_ks"]), g[f"d3_j2_def_{n}"]) < TOL_REF, n
+
+
+def test_default_mode_batch_matches_c_oracle_and_its_node_counts(M, const):
+    from oracle import c_oracle as C
+    _, x, u = synth_batch(48, 60, 1.5, const)
+    tfv = 1.5 * (1 + 0.1 * np.arange(48) / 48)
+    ref = C.discretize_batch_adaptive(x, u, tfv, const)
+    res = M.discretize_batch(x, u, tfv, const, adaptive=dict(rtol=1e-3, atol=1e-6, max_step=1e-2))
+    assert res.status.max() == 0 and ref[5].max() == 0
+    assert np.array_equal(res.n_nodes, ref[6])                  # the same steps were accepted
+    for n, o, r in zip(NAMES, res.stacked(), ref[:5]):
+        assert rel_err(o, r) < 1e-8, n
+    # tighter tolerances -> more nodes, and convergence towards the uniform-node answer
+    fine = M.discretize_batch(x, u, tfv, const, adaptive=dict(rtol=1e-9, atol=1e-12, max_step=2e-4))
+    uni = M.discretize_batch(x, u, tfv, const)
+    assert fine.n_nodes.min() > res.n_nodes.max()
+    for n, o, r in zip(NAMES, fine.stacked(), uni.stacked()):
+        assert rel_err(o, r) < 1e-6, n
+
+
 def test_scipy_zoh_flag_is_the_same_hold(M, gold_disc, const):
     """test_discretizer.py:152-157 (test_custom_ZOH)"""
     g = gold_disc

@@ -75,6 +75,23 @@ def test_c_oracle_j2_and_other_node_count(gold_disc, const):
         assert rel_err(_sel(o[0], ks), g[f"d3_n21_uni_{n}"]) < TOL_UNIFORM
 
 
+@pytest.mark.parametrize("sc", ["d0", "d1", "d3", "d4"])
+def test_c_oracle_rk45_replica_matches_reference_default_mode(gold_disc, const, sc):
+    """the restated scipy RK45 controller reproduces the reference's DEFAULT mode (adaptive quadrature nodes)
+    to rounding: same accepted steps, same matrices"""
+    g = gold_disc
+    out = C.discretize_batch_adaptive(g[sc + "_x"][None], g[sc + "_u"][None], float(g[sc + "_tf"]), const)
+    assert out[5].max() == 0
+    for n, o in zip(NAMES, out[:5]):
+        assert rel_err(o[0], g[f"{sc}_def_{n}"]) < 1e-12, (sc, n)
+    if sc == "d3":
+        assert out[6].min() >= 4 and out[6].max() <= 8          # SURVEY: 4-8 nodes per interval
+        ks = g["d3_j2_ks"]
+        oj = C.discretize_batch_adaptive(g["d3_x"][None], g["d3_u"][None], 2.0, const, include_J2=True)
+        for n, o in zip(NAMES, oj[:5]):
+            assert rel_err(_sel(o[0], ks), g[f"d3_j2_def_{n}"]) < 1e-12, n
+
+
 def test_reference_default_mode_distance_is_its_own_quadrature_error(gold_disc, const):
     """Documented, not gated: default-mode B+- sit ~1e-3 from the uniform-node answer."""
     g = gold_disc
