@@ -198,6 +198,7 @@ int64_t mpc_launch_count(void);
 /* Experiment knob: selects an alternative block-size / register-cap build of the discretization kernel
  * (0 = production).  Results are identical; only occupancy differs.  See DESIGN.md, tuning table. */
 int mpc_set_tuning(int variant);
+int mpc_set_skew(int cycles);
 
 #ifdef __cplusplus
 }

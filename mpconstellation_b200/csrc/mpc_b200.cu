@@ -63,13 +63,14 @@ mpc::PropParams prop_params(const mpc_params *p)
 }
 
 std::atomic<int> g_tuning{0};
+std::atomic<int> g_skew{0};
 
-template <bool J2, int BLOCK, int MAXREG, int NDST>
+template <bool J2, int BLOCK, int MAXREG, int NDST, int SCHED = 0>
 int launch_disc_cfg(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                     int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
                     cudaStream_t st)
 {
-    auto kern = mpc::discretize_kernel<J2, BLOCK, MAXREG, NDST>;
+    auto kern = mpc::discretize_kernel<J2, BLOCK, MAXREG, NDST, SCHED>;
     const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -81,7 +82,7 @@ int launch_disc_cfg(const double *x, const double *u, const double *tf, const mp
     }
     const long long n_int = (long long)n_sats * (K - 1);
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, g_skew.load());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
@@ -102,6 +103,10 @@ int launch_disc_n(const double *x, const double *u, const double *tf, const mpc:
             case 3: return launch_disc_cfg<false, 32, 184, 1>(MPC_ARGS);   // 11 warps / SM
             case 4: return launch_disc_cfg<false, 64, 168, 1>(MPC_ARGS);   // 12 warps / SM
             case 5: return launch_disc_cfg<false, 64, 255, 1>(MPC_ARGS);   //  8 warps / SM, smaller CTAs
+            case 6: return launch_disc_cfg<false, 128, 255, 1, 1>(MPC_ARGS);  // ILP-ordered schedule
+            case 7: return launch_disc_cfg<false, 32, 224, 1, 1>(MPC_ARGS);   // ILP-ordered schedule, 9 warps / SM
+            case 8: return launch_disc_cfg<false, 256, 255, 1, 0>(MPC_ARGS);  // one 8-warp CTA / SM
+            case 9: return launch_disc_cfg<false, 256, 255, 1, 1>(MPC_ARGS);
             default: break;
         }
     }
@@ -324,9 +329,15 @@ int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc
 
 int64_t mpc_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int mpc_set_skew(int cycles)
+{
+    g_skew.store(cycles < 0 ? 0 : cycles);
+    return MPC_SUCCESS;
+}
+
 int mpc_set_tuning(int variant)
 {
-    if (variant < 0 || variant > 5) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);
+    if (variant < 0 || variant > 9) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);
     g_tuning.store(variant);
     return MPC_SUCCESS;
 }
