@@ -289,6 +289,24 @@ def gpu_arm(args):
         disc_ms.append(e1.elapsed_time(e2))
     launches = M.launch_count() - launches0
     clocks = sampler.stop()
+    # the reference's shipped default quadrature mode (adaptive RK45 nodes, replayed on the device): reported
+    # next to the headline, which is the fixed-step RK4 / 101-node mode north_star names
+    adaptive_ms = None
+    if world == 1:
+        nn = torch.empty(n_int, dtype=torch.int32, device=dev)
+        ts = []
+        for _ in range(4):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            M.discretize_batch_device(x, u, tfd, const, out=out, status=std, adaptive=dict(rtol=1e-3, atol=1e-6, max_step=1e-2),
+                                      n_nodes=nn)
+            eb.record()
+            torch.cuda.synchronize(dev)
+            ts.append(ea.elapsed_time(eb))
+        adaptive_ms = float(min(ts[1:]))
+        adaptive_nodes = (int(nn.min()), int(nn.max()))
+        M.discretize_batch_device(x, u, tfd, const, n_sub=n_sub, out=out, status=std)   # restore the headline result
+        torch.cuda.synchronize(dev)
     total_ms = float(np.sum(step_ms))
     if dist is not None:
         t = torch.tensor([total_ms, float(np.sum(disc_ms))], dtype=torch.float64, device=dev)
@@ -366,7 +384,11 @@ def gpu_arm(args):
                    "bytes_received_per_rank_per_step": int((world - 1) * n_int * 105 * 8)} if world > 1 else None,
         "gpu_launches": int(launches),
         "kernel": {"discretize_ms": disc_ms_avg, "propagate_ms": ms_per_step - disc_ms_avg if world == 1 else None,
-                   "discretize_intervals_per_s_per_gpu": n_int / (disc_ms_avg * 1e-3)},
+                   "discretize_intervals_per_s_per_gpu": n_int / (disc_ms_avg * 1e-3),
+                   "default_mode_adaptive_rk45": None if adaptive_ms is None else {
+                       "discretize_ms": adaptive_ms, "intervals_per_s": n_int / (adaptive_ms * 1e-3),
+                       "nodes_per_interval": list(adaptive_nodes),
+                       "note": "use_uniform_steps=False (reference default): quadrature on scipy-RK45 accepted steps"}},
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tflops / peak_tflops, "traffic": None,
                      "peak_source": "DFMA-chain microbenchmark (mpc_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",

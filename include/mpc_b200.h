@@ -76,6 +76,8 @@ typedef struct mpc_controller {
     double thrust[3];      /* CONSTANT: the vector; TANGENTIAL: thrust[0] = magnitude */
     double end_tau;        /* SEQUENCE: tf_u / tf_sim (control.py:101) */
     const double *table;   /* SEQUENCE: device pointer (device API) or host pointer (host API) */
+    const double *end_tau_per_sat; /* SEQUENCE, optional [N]: per-satellite end_tau (overrides end_tau); same
+                                      pointer kind as `table`; NULL = use the scalar */
 } mpc_controller;
 
 /* ---------------------------------------------------------------- library */
@@ -198,7 +200,6 @@ int64_t mpc_launch_count(void);
 /* Experiment knob: selects an alternative block-size / register-cap build of the discretization kernel
  * (0 = production).  Results are identical; only occupancy differs.  See DESIGN.md, tuning table. */
 int mpc_set_tuning(int variant);
-int mpc_set_skew(int cycles);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ class MpcParams(ctypes.Structure):
 class MpcController(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("table_len", ctypes.c_int32), ("table_per_sat", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("thrust", ctypes.c_double * 3), ("end_tau", ctypes.c_double),
-                ("table", ctypes.c_void_p)]
+                ("table", ctypes.c_void_p), ("end_tau_per_sat", ctypes.c_void_p)]
 
 
 class MpcError(RuntimeError):
@@ -103,8 +103,6 @@ def lib():
     L.mpc_propagate_batch_host.argtypes = [vp, _DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP]
     L.mpc_propagate_discretize_host.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, _DP]
     L.mpc_fp64_peak_probe.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
-    L.mpc_set_skew.argtypes = [i]
-    L.mpc_set_skew.restype = i
     L.mpc_set_tuning.argtypes = [i]
     L.mpc_set_tuning.restype = i
     for name in ("mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
@@ -121,7 +119,7 @@ EXPORTED_SYMBOLS = [
     "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_propagate_batch",
     "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
     "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host",
-    "mpc_fp64_peak_probe", "mpc_set_tuning", "mpc_set_skew",
+    "mpc_fp64_peak_probe", "mpc_set_tuning",
 ]
 
 

@@ -130,19 +130,27 @@ def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_su
     return res
 
 
-def _ctrl_struct(spec, n_sats, table_addr=None):
+def _ctrl_struct(spec, n_sats, table_addr=None, end_tau_addr=None):
     c = _lib.MpcController()
     c.kind = spec.kind
     c.thrust[0], c.thrust[1], c.thrust[2] = [float(t) for t in spec.thrust]
-    c.end_tau = float(spec.end_tau)
     keep = None
+    if np.ndim(spec.end_tau) == 0:
+        c.end_tau = float(spec.end_tau)
+    else:
+        et = np.ascontiguousarray(spec.end_tau, dtype=np.float64)
+        if et.shape != (n_sats,):
+            raise ValueError("per-satellite end_tau must have shape [N]")
+        c.end_tau = float(et[0])
+        c.end_tau_per_sat = end_tau_addr if end_tau_addr is not None else et.ctypes.data
+        keep = [et]
     if spec.kind == _lib.CTRL_SEQUENCE:
         tab = spec.table
         if tab.ndim == 3 and tab.shape[0] != n_sats:
             raise ValueError("per-satellite sequence table must be [N,3,Ku]")
         c.table_len = tab.shape[-1]
         c.table_per_sat = int(tab.ndim == 3)
-        keep = tab
+        keep = [keep, tab]
         c.table = table_addr if table_addr is not None else tab.ctypes.data
     return c, keep
 
@@ -276,17 +284,21 @@ def propagate_batch_device(y0, tf, controller, const, include_drag=True, include
         u_out = torch.empty((N, 3, T), dtype=torch.float64, device=y0.device)
     if status is None:
         status = torch.empty(N, dtype=torch.int32, device=y0.device)
-    tab_dev = None
+    tab_dev = et_dev = None
     if spec.kind == _lib.CTRL_SEQUENCE:
         tab_dev = torch.as_tensor(spec.table, dtype=torch.float64).to(y0.device).contiguous()
-    c, _keep = _ctrl_struct(spec, N, table_addr=tab_dev.data_ptr() if tab_dev is not None else None)
+        if np.ndim(spec.end_tau) != 0:
+            et_dev = torch.as_tensor(np.asarray(spec.end_tau, dtype=np.float64)).to(y0.device).contiguous()
+    c, _keep = _ctrl_struct(spec, N, table_addr=tab_dev.data_ptr() if tab_dev is not None else None,
+                            end_tau_addr=et_dev.data_ptr() if et_dev is not None else None)
     p = _lib.make_params(const, include_J2, include_drag)
     stream = torch.cuda.current_stream(y0.device).cuda_stream
     _lib.check(_lib.lib().mpc_propagate_batch(y0.data_ptr(), tf.data_ptr(), ctypes.byref(p), ctypes.byref(c), N,
                                               int(T), int(n_sub), y.data_ptr(), u_out.data_ptr(),
                                               status.data_ptr(), stream))
-    if tab_dev is not None:
-        tab_dev.record_stream(torch.cuda.current_stream(y0.device))
+    for t_ in (tab_dev, et_dev):
+        if t_ is not None:
+            t_.record_stream(torch.cuda.current_stream(y0.device))
     return y, u_out, status
 
 

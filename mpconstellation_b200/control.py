@@ -22,7 +22,7 @@ class ControllerSpec:
     kind: int = _lib.CTRL_ZERO
     thrust: tuple = (0.0, 0.0, 0.0)
     table: np.ndarray = field(default=None, repr=False)   # (3,Ku) or (N,3,Ku)
-    end_tau: float = 1.0
+    end_tau: object = 1.0                                  # scalar, or [N] array (one end_tau per satellite)
 
     def host_u_func(self):
         """u(x, tau) on the host, same arithmetic as the device law (used by extract_uk on the host
@@ -42,7 +42,7 @@ class ControllerSpec:
             def fn(x, tau):
                 if tau > end_tau:
                     return np.zeros(3)
-                t = tau / end_tau
+                t = tau / end_tau       # (host law: scalar end_tau only)
                 Ku = tab.shape[-1]
                 if t == 1:
                     return tab[..., -1]

@@ -133,132 +133,6 @@ __device__ __forceinline__ void sym_mul_add(const Sym3 &g, double px, double py,
     oz = fma(g.zz, pz, fma(g.yz, py, fma(g.xz, px, cz)));
 }
 
-// ---- batched Newton chains: the same arithmetic as fast_rsqrt / fast_rcp, written for N independent
-// arguments so that the instruction stream carries N-way ILP through the 7-deep dependent chains
-// (a dependent DFMA issues every ~8.8 cycles on sm_100a, the pipe accepts one every 2: see DESIGN.md).
-template <int N>
-__device__ __forceinline__ void fast_rsqrt_n(const double (&a)[N], double (&y)[N])
-{
-    double h[N], e[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(a[i]));
-#pragma unroll
-    for (int i = 0; i < N; ++i) h[i] = 0.5 * a[i];
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) e[i] = -h[i] * y[i];
-#pragma unroll
-        for (int i = 0; i < N; ++i) e[i] = fma(e[i], y[i], 0.5);
-#pragma unroll
-        for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
-    }
-}
-
-template <int N>
-__device__ __forceinline__ void fast_rcp_n(const double (&a)[N], double (&y)[N])
-{
-    double e[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(a[i]));
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) e[i] = fma(-a[i], y[i], 1.0);
-#pragma unroll
-        for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
-    }
-}
-
-// gravity() with 1/|r| supplied by the caller (so several stages can share one batched Newton pass)
-template <bool J2>
-__device__ __forceinline__ void gravity_ir(const DiscParams &P, double rx, double ry, double rz, double ir, double &ax,
-                                           double &ay, double &az, Sym3 &g)
-{
-    const double ir2 = ir * ir;
-    const double mu3 = P.mu * ir * ir2;
-    const double nx = rx * ir, ny = ry * ir, nz = rz * ir;
-    const double t3 = 3.0 * mu3;
-    const double tx = t3 * nx, ty = t3 * ny, tz = t3 * nz;
-    g.xx = fma(tx, nx, -mu3);
-    g.yy = fma(ty, ny, -mu3);
-    g.zz = fma(tz, nz, -mu3);
-    g.xy = tx * ny;
-    g.xz = tx * nz;
-    g.yz = ty * nz;
-    ax = -mu3 * rx;
-    ay = -mu3 * ry;
-    az = -mu3 * rz;
-    if (J2) {
-        const double q = nz * nz;
-        const double k5 = P.kj2 * ir2 * ir2 * ir;
-        const double c1 = fma(5.0, q, -1.0);
-        const double c3 = fma(5.0, q, -3.0);
-        const double k5c1 = k5 * c1;
-        ax = fma(k5c1, rx, ax);
-        ay = fma(k5c1, ry, ay);
-        az = fma(k5 * c3, rz, az);
-        const double e = k5 * fma(35.0, q, -5.0);
-        const double f = k5 * fma(-35.0, q, 15.0);
-        const double ex = e * nx, ey = e * ny;
-        g.xx += fma(-ex, nx, k5c1);
-        g.yy += fma(-ey, ny, k5c1);
-        g.xy = fma(-ex, ny, g.xy);
-        g.xz = fma(f * nx, nz, g.xz);
-        g.yz = fma(f * ny, nz, g.yz);
-        g.zz = fma(k5, fma(q, fma(-35.0, q, 30.0), -3.0), g.zz);
-    }
-}
-
-// Two columns of Phi through one RK4 step, statements interleaved (6 independent FMA chains).
-// MASS_A: column A is column 6 (forcing d_j).
-template <bool MASS_A>
-__device__ __forceinline__ void column_step2(double (&ar)[3], double (&av)[3], double (&br)[3], double (&bv)[3],
-                                             const StageLin &s1, const StageLin &s2, const StageLin &s3,
-                                             const StageLin &s4, double hs, double hh, double hh2, double hshh,
-                                             double hs2_6, double hs_6)
-{
-    double ka1[3], ka2[3], ka3[3], ka4[3], kb1[3], kb2[3], kb3[3], kb4[3], qa[3], qb[3], ba[3], bb[3];
-    auto mulA = [&](const StageLin &st, const double (&p)[3], double (&o)[3]) {
-        if (MASS_A) sym_mul_add(st.g, p[0], p[1], p[2], st.dx, st.dy, st.dz, o[0], o[1], o[2]);
-        else sym_mul(st.g, p[0], p[1], p[2], o[0], o[1], o[2]);
-    };
-    mulA(s1, ar, ka1);
-    sym_mul(s1.g, br[0], br[1], br[2], kb1[0], kb1[1], kb1[2]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        qa[i] = fma(hh, av[i], ar[i]);
-        qb[i] = fma(hh, bv[i], br[i]);
-    }
-    mulA(s2, qa, ka2);
-    sym_mul(s2.g, qb[0], qb[1], qb[2], kb2[0], kb2[1], kb2[2]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        qa[i] = fma(hh2, ka1[i], qa[i]);
-        qb[i] = fma(hh2, kb1[i], qb[i]);
-    }
-    mulA(s3, qa, ka3);
-    sym_mul(s3.g, qb[0], qb[1], qb[2], kb3[0], kb3[1], kb3[2]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        ba[i] = fma(hs, av[i], ar[i]);
-        bb[i] = fma(hs, bv[i], br[i]);
-        qa[i] = fma(hshh, ka2[i], ba[i]);
-        qb[i] = fma(hshh, kb2[i], bb[i]);
-    }
-    mulA(s4, qa, ka4);
-    sym_mul(s4.g, qb[0], qb[1], qb[2], kb4[0], kb4[1], kb4[2]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double wa = ka2[i] + ka3[i], wb = kb2[i] + kb3[i];
-        const double sa = ka1[i] + wa, sb = kb1[i] + wb;
-        ar[i] = fma(hs2_6, sa, ba[i]);
-        br[i] = fma(hs2_6, sb, bb[i]);
-        av[i] = fma(hs_6, (sa + wa) + ka4[i], av[i]);
-        bv[i] = fma(hs_6, (sb + wb) + kb4[i], bv[i]);
-    }
-}
-
 // One column of Phi through one RK4 step (Nystrom form of the classical stages).
 // MASSCOL: column 6, whose forcing is d_j = -u/m^2 at each stage (Phi[6][6] == 1).
 template <bool MASSCOL>
@@ -518,27 +392,16 @@ __device__ __forceinline__ int epilogue_store(volatile double *acc, const double
 }
 #undef ACC
 
-template <bool J2, int BLOCK, int MAXREG, int NDST, int SCHED>
+template <bool J2, int BLOCK, int MAXREG, int NDST>
 __global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG)
 discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ tf_arr,
                   DiscParams P, int n_sats, int K, int n_sub, DstTab dst, long long pitch, long long offset,
-                  int32_t *__restrict__ status, int skew)
+                  int32_t *__restrict__ status)
 {
     extern __shared__ double acc_smem[];
     const long long n_int = (long long)n_sats * (K - 1);
     const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (gid >= n_int) return;
-    // Phase skew: the two warps that share an SM sub-partition run the same instruction stream; started
-    // together they reach the low-ILP Newton chains together and the FP64 pipe idles.  Delaying one of them by
-    // about half a loop iteration lets one warp's chains overlap the other's FMA-dense column phase.
-    if (skew > 0) {
-        const bool late = (BLOCK >= 256) ? (((threadIdx.x >> 5) & 4) != 0) : (((blockIdx.x / 148) & 1) != 0);
-        if (late) {
-            const long long t_start = clock64();
-            while (clock64() - t_start < skew) {
-            }
-        }
-    }
     // volatile: keep the accumulators IN shared memory (the compiler would otherwise promote these
     // thread-private slots to registers and spill them to local memory, which is write-through to L2)
     volatile double *acc = acc_smem + threadIdx.x;
@@ -579,205 +442,108 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     double iun = (uu > 4.930380657631324e-32) ? fast_rsqrt(uu) : 0.0;  // |u| <= eps  (:208)
     double un = uu * iun;
 
-    if (SCHED == 0) {
-        for (int n = 0; n <= n_sub; ++n) {
-            // ---- stage 1 == quadrature node n ------------------------------------------------------
-            StageLin s1;
-            double a1x, a1y, a1z;
-            gravity<J2>(P, rx, ry, rz, a1x, a1y, a1z, s1.g);
-            bad |= !(m > 0.0);
-            const double im = fast_rcp(m);
-            const double tx = ux * im, ty = uy * im, tz = uz * im;  // u/m
-            // xi' = -(Dxf x + Duf u) = -[v; G r; mdot]  (the -u/m and +u/m terms cancel, :232-235)
-            double grx, gry, grz;
-            sym_mul(s1.g, rx, ry, rz, grx, gry, grz);
-            a1x += tx;
-            a1y += ty;
-            a1z += tz;
-            s1.dx = -tx * im;
-            s1.dy = -ty * im;
-            s1.dz = -tz * im;
-            const double md1 = -un * P.inv_ve;  // mass flow (simulator.py:160)
-            {
-                const double sfrac = (double)n * inv_n;                     // lambda+   (:61)
-                const double w = (n == 0 || n == n_sub) ? 0.5 : 1.0;        // trapezoid end weights (:77-80)
-                const double ws = w * sfrac;
-                node_accumulate<BLOCK>(acc, pr, pv, P, im, ux, uy, uz, iun, md1, vx, vy, vz, a1x, a1y, a1z, grx, gry, grz, w, ws);
-            }
-            if (n == n_sub) break;
-
-            // ---- stages 2..4 of the state (Nystrom form; mass stages are explicit in tau) -----------
-            const double sm = ((double)n + 0.5) * inv_n, se = (double)(n + 1) * inv_n;
-            const double umx = fma(sm, dux, u0x), umy = fma(sm, duy, u0y), umz = fma(sm, duz, u0z);
-            const double uex = fma(se, dux, u0x), uey = fma(se, duy, u0y), uez = fma(se, duz, u0z);
-            const double uum = fma(umx, umx, fma(umy, umy, umz * umz));
-            const double uue = fma(uex, uex, fma(uey, uey, uez * uez));
-            const double iunm = (uum > 4.930380657631324e-32) ? fast_rsqrt(uum) : 0.0;
-            const double iune = (uue > 4.930380657631324e-32) ? fast_rsqrt(uue) : 0.0;
-            const double mdm = -(uum * iunm) * P.inv_ve;
-            const double mde = -(uue * iune) * P.inv_ve;
-            const double m2 = fma(hh, md1, m);
-            const double m3 = fma(hh, mdm, m);
-            const double m4 = fma(hs, mdm, m);
-            bad |= !(m4 > 0.0);
-
-            StageLin s2, s3, s4;
-            double a2x, a2y, a2z, a3x, a3y, a3z, a4x, a4y, a4z;
-            const double r2x = fma(hh, vx, rx), r2y = fma(hh, vy, ry), r2z = fma(hh, vz, rz);
-            gravity<J2>(P, r2x, r2y, r2z, a2x, a2y, a2z, s2.g);
-            {
-                const double i2 = fast_rcp(m2);
-                const double qx = umx * i2, qy = umy * i2, qz = umz * i2;
-                a2x += qx;
-                a2y += qy;
-                a2z += qz;
-                s2.dx = -qx * i2;
-                s2.dy = -qy * i2;
-                s2.dz = -qz * i2;
-            }
-            const double r3x = fma(hh2, a1x, r2x), r3y = fma(hh2, a1y, r2y), r3z = fma(hh2, a1z, r2z);
-            gravity<J2>(P, r3x, r3y, r3z, a3x, a3y, a3z, s3.g);
-            {
-                const double i3 = fast_rcp(m3);
-                const double qx = umx * i3, qy = umy * i3, qz = umz * i3;
-                a3x += qx;
-                a3y += qy;
-                a3z += qz;
-                s3.dx = -qx * i3;
-                s3.dy = -qy * i3;
-                s3.dz = -qz * i3;
-            }
-            const double bx = fma(hs, vx, rx), by = fma(hs, vy, ry), bz = fma(hs, vz, rz);
-            const double r4x = fma(hshh, a2x, bx), r4y = fma(hshh, a2y, by), r4z = fma(hshh, a2z, bz);
-            gravity<J2>(P, r4x, r4y, r4z, a4x, a4y, a4z, s4.g);
-            {
-                const double i4 = fast_rcp(m4);
-                const double qx = uex * i4, qy = uey * i4, qz = uez * i4;
-                a4x += qx;
-                a4y += qy;
-                a4z += qz;
-                s4.dx = -qx * i4;
-                s4.dy = -qy * i4;
-                s4.dz = -qz * i4;
-            }
-            // ---- state update -------------------------------------------------------------------------
-            {
-                const double wx = a2x + a3x, wy = a2y + a3y, wz = a2z + a3z;
-                const double sx = a1x + wx, sy = a1y + wy, sz = a1z + wz;
-                rx = fma(hs2_6, sx, bx);
-                ry = fma(hs2_6, sy, by);
-                rz = fma(hs2_6, sz, bz);
-                vx = fma(hs_6, (sx + wx) + a4x, vx);
-                vy = fma(hs_6, (sy + wy) + a4y, vy);
-                vz = fma(hs_6, (sz + wz) + a4z, vz);
-                m = fma(hs_6, fma(4.0, mdm, md1) + mde, m);
-            }
-            // ---- variational columns ----------------------------------------------------------------
-            // the mass column first: its forcing terms d1..d4 are dead for the remaining six columns
-            column_step<true>(pr[6], pv[6], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
-    #pragma unroll
-            for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
-            ux = uex;
-            uy = uey;
-            uz = uez;
-            iun = iune;
-            un = uue * iune;
-        }
-    } else {
-        // Same arithmetic, ordered for instruction-level parallelism: the Newton chains of one step are evaluated
-        // in batches (4 rsqrt, 4 rcp, 2 rsqrt), and the Phi columns are stepped two at a time.
-        for (int n = 0; n < n_sub; ++n) {
-            const double sm = ((double)n + 0.5) * inv_n, se = (double)(n + 1) * inv_n;
-            const double umx = fma(sm, dux, u0x), umy = fma(sm, duy, u0y), umz = fma(sm, duz, u0z);
-            const double uex = fma(se, dux, u0x), uey = fma(se, duy, u0y), uez = fma(se, duz, u0z);
-            const double uum = fma(umx, umx, fma(umy, umy, umz * umz));
-            const double uue = fma(uex, uex, fma(uey, uey, uez * uez));
-            const double r2x = fma(hh, vx, rx), r2y = fma(hh, vy, ry), r2z = fma(hh, vz, rz);
-            const double q4[4] = {fma(rx, rx, fma(ry, ry, rz * rz)), fma(r2x, r2x, fma(r2y, r2y, r2z * r2z)),
-                                  fmax(uum, 1e-300), fmax(uue, 1e-300)};
-            double y4[4];
-            fast_rsqrt_n<4>(q4, y4);
-            const double iunm = (uum > 4.930380657631324e-32) ? y4[2] : 0.0;
-            const double iune = (uue > 4.930380657631324e-32) ? y4[3] : 0.0;
-            const double md1 = -un * P.inv_ve;
-            const double mdm = -(uum * iunm) * P.inv_ve;
-            const double mde = -(uue * iune) * P.inv_ve;
-            const double m4[4] = {m, fma(hh, md1, m), fma(hh, mdm, m), fma(hs, mdm, m)};
-            bad |= !(m4[3] > 0.0) | !(m > 0.0);
-            double im4[4];
-            fast_rcp_n<4>(m4, im4);
-            StageLin s1, s2, s3, s4;
-            double a1x, a1y, a1z, a2x, a2y, a2z, a3x, a3y, a3z, a4x, a4y, a4z;
-            gravity_ir<J2>(P, rx, ry, rz, y4[0], a1x, a1y, a1z, s1.g);
-            gravity_ir<J2>(P, r2x, r2y, r2z, y4[1], a2x, a2y, a2z, s2.g);
-            double grx, gry, grz;
-            sym_mul(s1.g, rx, ry, rz, grx, gry, grz);
-            {
-                const double t1x = ux * im4[0], t1y = uy * im4[0], t1z = uz * im4[0];
-                const double t2x = umx * im4[1], t2y = umy * im4[1], t2z = umz * im4[1];
-                a1x += t1x; a1y += t1y; a1z += t1z;
-                a2x += t2x; a2y += t2y; a2z += t2z;
-                s1.dx = -t1x * im4[0]; s1.dy = -t1y * im4[0]; s1.dz = -t1z * im4[0];
-                s2.dx = -t2x * im4[1]; s2.dy = -t2y * im4[1]; s2.dz = -t2z * im4[1];
-            }
-            const double r3x = fma(hh2, a1x, r2x), r3y = fma(hh2, a1y, r2y), r3z = fma(hh2, a1z, r2z);
-            const double bx = fma(hs, vx, rx), by = fma(hs, vy, ry), bz = fma(hs, vz, rz);
-            const double r4x = fma(hshh, a2x, bx), r4y = fma(hshh, a2y, by), r4z = fma(hshh, a2z, bz);
-            const double q2[2] = {fma(r3x, r3x, fma(r3y, r3y, r3z * r3z)), fma(r4x, r4x, fma(r4y, r4y, r4z * r4z))};
-            double y2[2];
-            fast_rsqrt_n<2>(q2, y2);
-            // quadrature node n (stage-1 quantities only): independent work next to the second Newton batch
-            {
-                const double sfrac = (double)n * inv_n;
-                const double w = (n == 0) ? 0.5 : 1.0;
-                node_accumulate<BLOCK>(acc, pr, pv, P, im4[0], ux, uy, uz, iun, md1, vx, vy, vz, a1x, a1y, a1z, grx, gry,
-                                       grz, w, w * sfrac);
-            }
-            gravity_ir<J2>(P, r3x, r3y, r3z, y2[0], a3x, a3y, a3z, s3.g);
-            gravity_ir<J2>(P, r4x, r4y, r4z, y2[1], a4x, a4y, a4z, s4.g);
-            {
-                const double t3x = umx * im4[2], t3y = umy * im4[2], t3z = umz * im4[2];
-                const double t4x = uex * im4[3], t4y = uey * im4[3], t4z = uez * im4[3];
-                a3x += t3x; a3y += t3y; a3z += t3z;
-                a4x += t4x; a4y += t4y; a4z += t4z;
-                s3.dx = -t3x * im4[2]; s3.dy = -t3y * im4[2]; s3.dz = -t3z * im4[2];
-                s4.dx = -t4x * im4[3]; s4.dy = -t4y * im4[3]; s4.dz = -t4z * im4[3];
-            }
-            {
-                const double wx = a2x + a3x, wy = a2y + a3y, wz = a2z + a3z;
-                const double sx = a1x + wx, sy = a1y + wy, sz = a1z + wz;
-                rx = fma(hs2_6, sx, bx);
-                ry = fma(hs2_6, sy, by);
-                rz = fma(hs2_6, sz, bz);
-                vx = fma(hs_6, (sx + wx) + a4x, vx);
-                vy = fma(hs_6, (sy + wy) + a4y, vy);
-                vz = fma(hs_6, (sz + wz) + a4z, vz);
-                m = fma(hs_6, fma(4.0, mdm, md1) + mde, m);
-            }
-            column_step2<true>(pr[6], pv[6], pr[0], pv[0], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
-            column_step2<false>(pr[1], pv[1], pr[2], pv[2], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
-            column_step2<false>(pr[3], pv[3], pr[4], pv[4], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
-            column_step<false>(pr[5], pv[5], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
-            ux = uex;
-            uy = uey;
-            uz = uez;
-            iun = iune;
-            un = uue * iune;
-        }
-        // last quadrature node (tau_{k+1})
+    for (int n = 0; n <= n_sub; ++n) {
+        // ---- stage 1 == quadrature node n ------------------------------------------------------
+        StageLin s1;
+        double a1x, a1y, a1z;
+        gravity<J2>(P, rx, ry, rz, a1x, a1y, a1z, s1.g);
+        bad |= !(m > 0.0);
+        const double im = fast_rcp(m);
+        const double tx = ux * im, ty = uy * im, tz = uz * im;  // u/m
+        // xi' = -(Dxf x + Duf u) = -[v; G r; mdot]  (the -u/m and +u/m terms cancel, :232-235)
+        double grx, gry, grz;
+        sym_mul(s1.g, rx, ry, rz, grx, gry, grz);
+        a1x += tx;
+        a1y += ty;
+        a1z += tz;
+        s1.dx = -tx * im;
+        s1.dy = -ty * im;
+        s1.dz = -tz * im;
+        const double md1 = -un * P.inv_ve;  // mass flow (simulator.py:160)
         {
-            StageLin s1;
-            double a1x, a1y, a1z, grx, gry, grz;
-            gravity<J2>(P, rx, ry, rz, a1x, a1y, a1z, s1.g);
-            bad |= !(m > 0.0);
-            const double im = fast_rcp(m);
-            sym_mul(s1.g, rx, ry, rz, grx, gry, grz);
-            a1x = fma(ux, im, a1x);
-            a1y = fma(uy, im, a1y);
-            a1z = fma(uz, im, a1z);
-            node_accumulate<BLOCK>(acc, pr, pv, P, im, ux, uy, uz, iun, -un * P.inv_ve, vx, vy, vz, a1x, a1y, a1z, grx, gry,
-                                   grz, 0.5, 0.5);
+            const double sfrac = (double)n * inv_n;                     // lambda+   (:61)
+            const double w = (n == 0 || n == n_sub) ? 0.5 : 1.0;        // trapezoid end weights (:77-80)
+            const double ws = w * sfrac;
+            node_accumulate<BLOCK>(acc, pr, pv, P, im, ux, uy, uz, iun, md1, vx, vy, vz, a1x, a1y, a1z, grx, gry, grz, w, ws);
         }
+        if (n == n_sub) break;
+
+        // ---- stages 2..4 of the state (Nystrom form; mass stages are explicit in tau) -----------
+        const double sm = ((double)n + 0.5) * inv_n, se = (double)(n + 1) * inv_n;
+        const double umx = fma(sm, dux, u0x), umy = fma(sm, duy, u0y), umz = fma(sm, duz, u0z);
+        const double uex = fma(se, dux, u0x), uey = fma(se, duy, u0y), uez = fma(se, duz, u0z);
+        const double uum = fma(umx, umx, fma(umy, umy, umz * umz));
+        const double uue = fma(uex, uex, fma(uey, uey, uez * uez));
+        const double iunm = (uum > 4.930380657631324e-32) ? fast_rsqrt(uum) : 0.0;
+        const double iune = (uue > 4.930380657631324e-32) ? fast_rsqrt(uue) : 0.0;
+        const double mdm = -(uum * iunm) * P.inv_ve;
+        const double mde = -(uue * iune) * P.inv_ve;
+        const double m2 = fma(hh, md1, m);
+        const double m3 = fma(hh, mdm, m);
+        const double m4 = fma(hs, mdm, m);
+        bad |= !(m4 > 0.0);
+
+        StageLin s2, s3, s4;
+        double a2x, a2y, a2z, a3x, a3y, a3z, a4x, a4y, a4z;
+        const double r2x = fma(hh, vx, rx), r2y = fma(hh, vy, ry), r2z = fma(hh, vz, rz);
+        gravity<J2>(P, r2x, r2y, r2z, a2x, a2y, a2z, s2.g);
+        {
+            const double i2 = fast_rcp(m2);
+            const double qx = umx * i2, qy = umy * i2, qz = umz * i2;
+            a2x += qx;
+            a2y += qy;
+            a2z += qz;
+            s2.dx = -qx * i2;
+            s2.dy = -qy * i2;
+            s2.dz = -qz * i2;
+        }
+        const double r3x = fma(hh2, a1x, r2x), r3y = fma(hh2, a1y, r2y), r3z = fma(hh2, a1z, r2z);
+        gravity<J2>(P, r3x, r3y, r3z, a3x, a3y, a3z, s3.g);
+        {
+            const double i3 = fast_rcp(m3);
+            const double qx = umx * i3, qy = umy * i3, qz = umz * i3;
+            a3x += qx;
+            a3y += qy;
+            a3z += qz;
+            s3.dx = -qx * i3;
+            s3.dy = -qy * i3;
+            s3.dz = -qz * i3;
+        }
+        const double bx = fma(hs, vx, rx), by = fma(hs, vy, ry), bz = fma(hs, vz, rz);
+        const double r4x = fma(hshh, a2x, bx), r4y = fma(hshh, a2y, by), r4z = fma(hshh, a2z, bz);
+        gravity<J2>(P, r4x, r4y, r4z, a4x, a4y, a4z, s4.g);
+        {
+            const double i4 = fast_rcp(m4);
+            const double qx = uex * i4, qy = uey * i4, qz = uez * i4;
+            a4x += qx;
+            a4y += qy;
+            a4z += qz;
+            s4.dx = -qx * i4;
+            s4.dy = -qy * i4;
+            s4.dz = -qz * i4;
+        }
+        // ---- state update -------------------------------------------------------------------------
+        {
+            const double wx = a2x + a3x, wy = a2y + a3y, wz = a2z + a3z;
+            const double sx = a1x + wx, sy = a1y + wy, sz = a1z + wz;
+            rx = fma(hs2_6, sx, bx);
+            ry = fma(hs2_6, sy, by);
+            rz = fma(hs2_6, sz, bz);
+            vx = fma(hs_6, (sx + wx) + a4x, vx);
+            vy = fma(hs_6, (sy + wy) + a4y, vy);
+            vz = fma(hs_6, (sz + wz) + a4z, vz);
+            m = fma(hs_6, fma(4.0, mdm, md1) + mde, m);
+        }
+        // ---- variational columns ----------------------------------------------------------------
+        // the mass column first: its forcing terms d1..d4 are dead for the remaining six columns
+        column_step<true>(pr[6], pv[6], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
+        ux = uex;
+        uy = uey;
+        uz = uez;
+        iun = iune;
+        un = uue * iune;
     }
 
     // ---- epilogue: left-multiply by Phi_end, scale by the step, store SoA -----------------------

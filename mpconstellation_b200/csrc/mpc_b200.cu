@@ -63,14 +63,13 @@ mpc::PropParams prop_params(const mpc_params *p)
 }
 
 std::atomic<int> g_tuning{0};
-std::atomic<int> g_skew{0};
 
-template <bool J2, int BLOCK, int MAXREG, int NDST, int SCHED = 0>
+template <bool J2, int BLOCK, int MAXREG, int NDST>
 int launch_disc_cfg(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                     int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
                     cudaStream_t st)
 {
-    auto kern = mpc::discretize_kernel<J2, BLOCK, MAXREG, NDST, SCHED>;
+    auto kern = mpc::discretize_kernel<J2, BLOCK, MAXREG, NDST>;
     const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -82,7 +81,7 @@ int launch_disc_cfg(const double *x, const double *u, const double *tf, const mp
     }
     const long long n_int = (long long)n_sats * (K - 1);
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, g_skew.load());
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
@@ -103,10 +102,7 @@ int launch_disc_n(const double *x, const double *u, const double *tf, const mpc:
             case 3: return launch_disc_cfg<false, 32, 184, 1>(MPC_ARGS);   // 11 warps / SM
             case 4: return launch_disc_cfg<false, 64, 168, 1>(MPC_ARGS);   // 12 warps / SM
             case 5: return launch_disc_cfg<false, 64, 255, 1>(MPC_ARGS);   //  8 warps / SM, smaller CTAs
-            case 6: return launch_disc_cfg<false, 128, 255, 1, 1>(MPC_ARGS);  // ILP-ordered schedule
-            case 7: return launch_disc_cfg<false, 32, 224, 1, 1>(MPC_ARGS);   // ILP-ordered schedule, 9 warps / SM
-            case 8: return launch_disc_cfg<false, 256, 255, 1, 0>(MPC_ARGS);  // one 8-warp CTA / SM
-            case 9: return launch_disc_cfg<false, 256, 255, 1, 1>(MPC_ARGS);
+            case 6: return launch_disc_cfg<false, 256, 255, 1>(MPC_ARGS);  // one 8-warp CTA / SM
             default: break;
         }
     }
@@ -206,13 +202,13 @@ int check_ctrl(const mpc_controller *c)
     if (c->kind < MPC_CTRL_ZERO || c->kind > MPC_CTRL_SEQUENCE) return fail(MPC_E_UNSUPPORTED, "unknown controller kind %d", c->kind);
     if (c->kind == MPC_CTRL_SEQUENCE) {
         if (!c->table || c->table_len < 2) return fail(MPC_E_INVALID, "sequence controller needs a table with >= 2 columns");
-        if (!(c->end_tau > 0.0)) return fail(MPC_E_INVALID, "sequence controller needs end_tau > 0");
+        if (!c->end_tau_per_sat && !(c->end_tau > 0.0)) return fail(MPC_E_INVALID, "sequence controller needs end_tau > 0");
     }
     return MPC_SUCCESS;
 }
 
 int prop_device(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *c,
-                const double *table_dev, int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status,
+                const double *table_dev, const double *end_tau_dev, int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status,
                 cudaStream_t st)
 {
     if (!y0 || !tf || !p || !y) return fail(MPC_E_INVALID, "null pointer argument");
@@ -230,6 +226,7 @@ int prop_device(const double *y0, const double *tf, const mpc_params *p, const m
     C.t2 = c->thrust[2];
     C.end_tau = c->end_tau;
     C.table = (c->kind == MPC_CTRL_SEQUENCE) ? table_dev : nullptr;
+    C.end_tau_arr = (c->kind == MPC_CTRL_SEQUENCE) ? end_tau_dev : nullptr;
     const unsigned grid = (unsigned)((n_sats + kPropBlock - 1) / kPropBlock);
     mpc::propagate_kernel<kPropBlock><<<grid, kPropBlock, 0, st>>>(y0, tf, prop_params(p), C, n_sats, T, n_sub, y,
                                                                   u_out, status);
@@ -248,7 +245,8 @@ struct mpc_ctx {
     // grow-only device workspace
     double *d_x = nullptr, *d_u = nullptr, *d_tf = nullptr, *d_out = nullptr, *d_y0 = nullptr, *d_tab = nullptr;
     int32_t *d_status = nullptr, *d_status2 = nullptr, *d_nodes = nullptr;
-    size_t cap_nodes = 0;
+    double *d_endtau = nullptr;
+    size_t cap_nodes = 0, cap_endtau = 0;
     size_t cap_x = 0, cap_u = 0, cap_tf = 0, cap_out = 0, cap_y0 = 0, cap_tab = 0, cap_status = 0, cap_status2 = 0;
 };
 
@@ -329,15 +327,9 @@ int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc
 
 int64_t mpc_launch_count(void) { return (int64_t)g_launches.load(); }
 
-int mpc_set_skew(int cycles)
-{
-    g_skew.store(cycles < 0 ? 0 : cycles);
-    return MPC_SUCCESS;
-}
-
 int mpc_set_tuning(int variant)
 {
-    if (variant < 0 || variant > 9) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);
+    if (variant < 0 || variant > 6) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);
     g_tuning.store(variant);
     return MPC_SUCCESS;
 }
@@ -380,7 +372,8 @@ int mpc_discretize_batch_adaptive(const double *x, const double *u, const double
 int mpc_propagate_batch(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
                         int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status, void *stream)
 {
-    return prop_device(y0, tf, p, ctrl, ctrl ? ctrl->table : nullptr, n_sats, T, n_sub, y, u_out, status,
+    return prop_device(y0, tf, p, ctrl, ctrl ? ctrl->table : nullptr, ctrl ? ctrl->end_tau_per_sat : nullptr, n_sats, T,
+                       n_sub, y, u_out, status,
                        (cudaStream_t)stream);
 }
 
@@ -416,6 +409,7 @@ int mpc_ctx_destroy(mpc_ctx *c)
     cudaFree(c->d_status);
     cudaFree(c->d_status2);
     cudaFree(c->d_nodes);
+    cudaFree(c->d_endtau);
     delete c;
     return MPC_SUCCESS;
 }
@@ -516,6 +510,11 @@ static int upload_table(mpc_ctx *ctx, const mpc_controller *ctrl, int n_sats, cu
     int rc = ensure(ctx->d_tab, ctx->cap_tab, cnt);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_tab, ctrl->table, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (ctrl->end_tau_per_sat) {
+        if ((rc = ensure(ctx->d_endtau, ctx->cap_endtau, (size_t)n_sats))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_endtau, ctrl->end_tau_per_sat, (size_t)n_sats * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+    }
     return MPC_SUCCESS;
 }
 
@@ -538,7 +537,7 @@ int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, c
     CUDA_TRY(cudaMemcpyAsync(ctx->d_y0, y0, (size_t)n_sats * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_tf, tf, (size_t)n_sats * sizeof(double), cudaMemcpyHostToDevice, st));
     if ((rc = upload_table(ctx, ctrl, n_sats, st))) return rc;
-    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p, ctrl, ctx->d_tab, n_sats, T, n_sub, ctx->d_x, ctx->d_u, ctx->d_status2, st)))
+    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p, ctrl, ctx->d_tab, ctrl->end_tau_per_sat ? ctx->d_endtau : nullptr, n_sats, T, n_sub, ctx->d_x, ctx->d_u, ctx->d_status2, st)))
         return rc;
     CUDA_TRY(cudaMemcpyAsync(y_host, ctx->d_x, (size_t)n_sats * 7 * T * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (u_host) CUDA_TRY(cudaMemcpyAsync(u_host, ctx->d_u, (size_t)n_sats * 3 * T * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -578,7 +577,8 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
     if ((rc = upload_table(ctx, ctrl, n_sats, st))) return rc;
     // the whole batch is propagated first (one thread per satellite is latency-bound: chunking it
     // would only serialise the latency), then discretized chunk by chunk while results stream out
-    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p_prop, ctrl, ctx->d_tab, n_sats, K, n_sub_prop, ctx->d_x, ctx->d_u,
+    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p_prop, ctrl, ctx->d_tab, ctrl->end_tau_per_sat ? ctx->d_endtau : nullptr, n_sats, K,
+                          n_sub_prop, ctx->d_x, ctx->d_u,
                           ctx->d_status2, st)))
         return rc;
     const mpc::DiscParams P = disc_params(p_disc);

@@ -27,10 +27,11 @@ struct CtrlParams {
     double t0, t1, t2;  // constant thrust vector, or t0 = tangential magnitude
     double end_tau;
     const double *table;
+    const double *end_tau_arr;  // optional per-satellite end_tau
 };
 
-__device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__restrict__ tab, const double (&y)[7],
-                                          double tau, double &ux, double &uy, double &uz)
+__device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__restrict__ tab, double end_tau,
+                                          const double (&y)[7], double tau, double &ux, double &uy, double &uz)
 {
     ux = uy = uz = 0.0;
     if (C.kind == 1) {  // control.py:47-53
@@ -48,9 +49,9 @@ __device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__r
         uy = ih * fma(hz, nx, -hx * nz);
         uz = ih * fma(hx, ny, -hy * nx);
     } else if (C.kind == 3) {  // control.py:104-143: FOH table on tau/end_tau, zero after end_tau
-        if (tau <= C.end_tau) {
+        if (tau <= end_tau) {
             const int Ku = C.table_len;
-            const double t = tau / C.end_tau;
+            const double t = tau / end_tau;
             if (t == 1.0) {
                 ux = tab[Ku - 1];
                 uy = tab[2 * Ku - 1];
@@ -72,10 +73,10 @@ __device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__r
 
 // f(y,u) without the tf factor (simulator.py:130-160); returns nonzero on non-positive mass
 __device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C, const double *__restrict__ tab,
-                                        const double (&y)[7], double tau, double (&dy)[7])
+                                        double end_tau, const double (&y)[7], double tau, double (&dy)[7])
 {
     double ux, uy, uz;
-    ctrl_eval(C, tab, y, tau, ux, uy, uz);
+    ctrl_eval(C, tab, end_tau, y, tau, ux, uy, uz);
     const double m = y[6];
     const double r2 = fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2]));
     const double ir = fast_rsqrt(r2);
@@ -123,6 +124,7 @@ propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_ar
     const int s = blockIdx.x * BLOCK + threadIdx.x;
     if (s >= n_sats) return;
     const double *tab = C.table ? C.table + (C.table_per_sat ? (long long)s * 3 * C.table_len : 0) : nullptr;
+    const double end_tau = C.end_tau_arr ? C.end_tau_arr[s] : C.end_tau;
     const double tf = tf_arr[s];
     double y[7], k1[7], k2[7], k3[7], k4[7], yt[7];
 #pragma unroll
@@ -150,7 +152,7 @@ propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_ar
         for (int c = 0; c < 7; ++c) yo[(long long)c * T + j] = y[c];
         if (uo) {
             double ux, uy, uz;
-            ctrl_eval(C, tab, y, tau_j, ux, uy, uz);
+            ctrl_eval(C, tab, end_tau, y, tau_j, ux, uy, uz);
             uo[j] = ux;
             uo[T + j] = uy;
             uo[2 * (long long)T + j] = uz;
@@ -162,16 +164,16 @@ propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_ar
             const double t0 = (n == 0) ? tau_j : fma((double)n, h, tau_j);
             const double t1 = (n == n_sub - 1) ? tau_n : fma((double)(n + 1), h, tau_j);
             const double tm = 0.5 * (t0 + t1);
-            bad |= prop_rhs(P, C, tab, y, t0, k1);
+            bad |= prop_rhs(P, C, tab, end_tau, y, t0, k1);
 #pragma unroll
             for (int c = 0; c < 7; ++c) yt[c] = fma(hh, k1[c], y[c]);
-            bad |= prop_rhs(P, C, tab, yt, tm, k2);
+            bad |= prop_rhs(P, C, tab, end_tau, yt, tm, k2);
 #pragma unroll
             for (int c = 0; c < 7; ++c) yt[c] = fma(hh, k2[c], y[c]);
-            bad |= prop_rhs(P, C, tab, yt, tm, k3);
+            bad |= prop_rhs(P, C, tab, end_tau, yt, tm, k3);
 #pragma unroll
             for (int c = 0; c < 7; ++c) yt[c] = fma(hs, k3[c], y[c]);
-            bad |= prop_rhs(P, C, tab, yt, t1, k4);
+            bad |= prop_rhs(P, C, tab, end_tau, yt, t1, k4);
             if (bad) break;
 #pragma unroll
             for (int c = 0; c < 7; ++c) y[c] = fma(hs_6, (k1[c] + k4[c]) + 2.0 * (k2[c] + k3[c]), y[c]);

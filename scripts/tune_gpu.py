@@ -13,10 +13,9 @@ y0 = torch.from_numpy(Y).to(dev); tfd = torch.full((N,), 2.0, dtype=torch.float6
 c = M.ConstantTangentialThrustController(tangential_thrust=0.5)
 y, u, st = M.propagate_batch_device(y0, tfd, c, const, include_drag=False, include_J2=False, T=K)
 ref = None
-variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,3,4,5").split(",")]
-skews = [int(v) for v in os.environ.get("SKEWS", "0").split(",")]
-for v, sk in [(v, sk) for v in variants for sk in skews]:
-    _lib.check(_lib.lib().mpc_set_tuning(v)); _lib.lib().mpc_set_skew(sk)
+variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,3,4,5,6").split(",")]
+for v in variants:
+    _lib.check(_lib.lib().mpc_set_tuning(v))
     ts = []
     for it in range(6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -24,6 +23,6 @@ for v, sk in [(v, sk) for v in variants for sk in skews]:
         ts.append(e0.elapsed_time(e1))
     o = out.cpu().numpy()
     if ref is None: ref = o
-    print(f"variant {v} skew {sk}: best {min(ts[1:]):.3f} ms  median {np.median(ts[1:]):.3f} ms -> {N*(K-1)/min(ts[1:])*1e3:.4e} intervals/s; "
+    print(f"variant {v}: best {min(ts[1:]):.3f} ms  median {np.median(ts[1:]):.3f} ms -> {N*(K-1)/min(ts[1:])*1e3:.4e} intervals/s; "
           f"max|diff vs v0| {np.max(np.abs(o-ref)):.2e} status {int(st2.max())}")
-_lib.lib().mpc_set_tuning(0); _lib.lib().mpc_set_skew(0)
+_lib.lib().mpc_set_tuning(0)

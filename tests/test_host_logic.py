@@ -33,7 +33,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.MpcParams) == 10 * 8 + 2 * 4
-    assert ctypes.sizeof(_lib.MpcController) == 4 * 4 + 3 * 8 + 8 + 8
+    assert ctypes.sizeof(_lib.MpcController) == 4 * 4 + 3 * 8 + 8 + 8 + 8
     assert _lib.MpcController.table.offset == 48
 
 
