@@ -390,7 +390,10 @@ def gpu_arm(args):
                        "nodes_per_interval": list(adaptive_nodes),
                        "note": "use_uniform_steps=False (reference default): quadrature on scipy-RK45 accepted steps"}},
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peak_tflops, "traffic": None,
+                     "frac": achieved_tflops / peak_tflops,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
+                     # command (profiles/r01_d_discretize_final.txt: 66.0 + 628.6 MB); algorithmic = 944 B x 815,104
+                     "traffic": 694.66e6 if (N, K, n_sub) == (4096, 200, 100) else None,
                      "peak_source": "DFMA-chain microbenchmark (mpc_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
                      "peak_nominal": FP64_NOMINAL_TFLOPS, "flop_per_interval": fl,
                      "fp64_pipe_frac": fp64_instr_per_interval(n_sub) * n_int / (disc_ms_avg * 1e-3) / (peak_tflops * 1e12 / 2),

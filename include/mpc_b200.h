@@ -133,6 +133,17 @@ int mpc_discretize_batch_adaptive(const double *x, const double *u, const double
                                   void *stream);
 
 /*
+ * u on its own grid: u is [n_sats][3][u_cols] with u_cols != K.  The reference accepts this (u_FOH takes its grid
+ * from u itself, linearize_discretize.py:308-315; its own test_linearize_many passes a (3,3K) array,
+ * test_discretizer.py:103): the hold is evaluated on u's global grid inside every interval.  adaptive = 0: fixed-step
+ * mode (n_sub used), adaptive = 1: default mode (rtol, atol, max_step, n_nodes used).
+ */
+int mpc_discretize_batch_ugrid(const double *x, const double *u, int u_cols, const double *tf, const mpc_params *p,
+                               int n_sats, int K, int adaptive, int n_sub, double rtol, double atol, double max_step,
+                               double *out, int64_t out_pitch, int64_t out_offset, int32_t *status, int32_t *n_nodes,
+                               void *stream);
+
+/*
  * Replaces Simulator.get_trajectory_ODE (simulator.py:164-189) for a batch of satellites, and
  * Discretizer.extract_uk (linearize_discretize.py:393-411) on the sampled trajectory.
  *
@@ -172,6 +183,12 @@ int mpc_discretize_batch_adaptive_host(mpc_ctx *ctx, const double *x, const doub
                                        const mpc_params *p, int n_sats, int K, double rtol, double atol,
                                        double max_step, double *out_host, int32_t *status_host,
                                        int32_t *n_nodes_host);
+
+/* Host-buffer form of mpc_discretize_batch_ugrid. */
+int mpc_discretize_batch_ugrid_host(mpc_ctx *ctx, const double *x, const double *u, int u_cols, const double *tf,
+                                    const mpc_params *p, int n_sats, int K, int adaptive, int n_sub, double rtol,
+                                    double atol, double max_step, double *out_host, int32_t *status_host,
+                                    int32_t *n_nodes_host);
 
 /* Host-buffer form of mpc_propagate_batch (ctrl->table is a host pointer here). */
 int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p,

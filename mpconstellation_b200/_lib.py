@@ -92,6 +92,8 @@ def lib():
     d = ctypes.c_double
     L.mpc_discretize_batch_adaptive.argtypes = [_DP, _DP, _DP, pp, i, i, d, d, d, _DP, i64, i64, _DP, _DP, vp]
     L.mpc_discretize_batch_adaptive_host.argtypes = [vp, _DP, _DP, _DP, pp, i, i, d, d, d, _DP, _DP, _DP]
+    L.mpc_discretize_batch_ugrid.argtypes = [_DP, _DP, i, _DP, pp, i, i, i, i, d, d, d, _DP, i64, i64, _DP, _DP, vp]
+    L.mpc_discretize_batch_ugrid_host.argtypes = [vp, _DP, _DP, i, _DP, pp, i, i, i, i, d, d, d, _DP, _DP, _DP]
     L.mpc_propagate_batch.argtypes = [_DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP, vp]
     L.mpc_ctx_create.argtypes = [i, ctypes.POINTER(vp)]
     L.mpc_ctx_destroy.argtypes = [vp]
@@ -107,6 +109,7 @@ def lib():
     L.mpc_set_tuning.restype = i
     for name in ("mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
                  "mpc_discretize_batch_adaptive", "mpc_discretize_batch_adaptive_host",
+                 "mpc_discretize_batch_ugrid", "mpc_discretize_batch_ugrid_host",
                  "mpc_ctx_create", "mpc_ctx_destroy", "mpc_discretize_batch_host", "mpc_propagate_batch_host",
                  "mpc_propagate_discretize_host", "mpc_fp64_peak_probe"):
         getattr(L, name).restype = i
@@ -116,9 +119,9 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "mpc_version", "mpc_last_error", "mpc_device_count", "mpc_device_info", "mpc_launch_count",
-    "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_propagate_batch",
+    "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_discretize_batch_ugrid", "mpc_propagate_batch",
     "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
-    "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host",
+    "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_discretize_batch_ugrid_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host",
     "mpc_fp64_peak_probe", "mpc_set_tuning",
 ]
 

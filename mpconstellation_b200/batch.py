@@ -102,7 +102,10 @@ def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_su
     if x.ndim != 3 or x.shape[1] != 7:
         raise ValueError(f"x must be [N,7,K], got {x.shape}")
     N, _, K = x.shape
-    u = _f64(u, (N, 3, K))
+    u = _f64(u)
+    if u.ndim != 3 or u.shape[:2] != (N, 3) or u.shape[2] < 2:
+        raise ValueError(f"u must be [N,3,Ku] with Ku >= 2, got {u.shape}")
+    Ku = u.shape[2]                      # Ku != K: u lives on its own grid (linearize_discretize.py:308-315)
     tfv = _tf_vec(tf, N)
     n_int = N * (K - 1)
     if out is None:
@@ -113,7 +116,14 @@ def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_su
         status = np.zeros(n_int, dtype=np.int32)
     p = _lib.make_params(const, include_J2, include_drag)
     n_nodes = None
-    if adaptive is None:
+    if Ku != K:
+        ad = adaptive or {}
+        n_nodes = np.zeros(n_int, dtype=np.int32) if adaptive is not None else None
+        _lib.check(_lib.lib().mpc_discretize_batch_ugrid_host(
+            ctx, _lib.addr(x), _lib.addr(u), Ku, _lib.addr(tfv), ctypes.byref(p), N, K, int(adaptive is not None),
+            int(n_sub), float(ad.get("rtol", 1e-3)), float(ad.get("atol", 1e-6)), float(ad.get("max_step", 1e-2)),
+            _lib.addr(out), _lib.addr(status), _lib.addr(n_nodes)))
+    elif adaptive is None:
         _lib.check(_lib.lib().mpc_discretize_batch_host(ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv),
                                                         ctypes.byref(p), N, K, int(n_sub), _lib.addr(out),
                                                         _lib.addr(status)))

@@ -37,13 +37,11 @@ struct AdStage {  // one evaluation of the unscaled dynamics and its linearizati
     double ux, uy, uz;
 };
 
-template <bool J2>
-__device__ __forceinline__ int ad_eval(const DiscParams &P, const double (&x)[7], double s, double u0x, double u0y,
-                                       double u0z, double dux, double duy, double duz, AdStage &o)
+template <bool J2, bool GENU>
+__device__ __forceinline__ int ad_eval(const DiscParams &P, const double (&x)[7], double s, double tau,
+                                       const UHold<GENU> &hold, AdStage &o)
 {
-    o.ux = fma(s, dux, u0x);
-    o.uy = fma(s, duy, u0y);
-    o.uz = fma(s, duz, u0z);
+    hold.at(s, tau, o.ux, o.uy, o.uz);
     double ax, ay, az;
     gravity<J2>(P, x[0], x[1], x[2], ax, ay, az, o.g);
     o.im = fast_rcp(x[6]);
@@ -106,10 +104,10 @@ __device__ __forceinline__ void ad_node(volatile double *sm, int base, const Dis
                            st.k[4], st.k[5], grx, gry, grz, w, w * lam);
 }
 
-template <bool J2, int BLOCK, int NDST>
+template <bool J2, int BLOCK, int NDST, bool GENU>
 __global__ void __launch_bounds__(BLOCK)
 discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in,
-                           const double *__restrict__ tf_arr, DiscParams P, int n_sats, int K, double rtol, double atol,
+                           const double *__restrict__ tf_arr, DiscParams P, int n_sats, int K, int Ku, double rtol, double atol,
                            double max_step, DstTab dst, long long pitch, long long offset, int32_t *__restrict__ status,
                            int32_t *__restrict__ n_nodes)
 {
@@ -122,12 +120,11 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
     const int k = (int)(gid - (long long)sat * (K - 1));
     const double tf = tf_arr[sat];
     const double *xs = x_in + ((long long)sat * 7) * K + k;
-    const double *us = u_in + ((long long)sat * 3) * K + k;
     double x[7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) x[c] = xs[(long long)c * K];
-    const double u0x = us[0], u0y = us[K], u0z = us[2 * (long long)K];
-    const double dux = us[1] - u0x, duy = us[K + 1] - u0y, duz = us[2 * (long long)K + 1] - u0z;
+    UHold<GENU> hold;
+    hold.init(u_in, sat, k, K, Ku);
     // tau = np.linspace(0, 1, K) (:356): start + i*step, last point exactly 1
     const double step = 1.0 / (double)(K - 1);
     const double t0 = (double)k * step, t1 = (k + 1 == K - 1) ? 1.0 : (double)(k + 1) * step;
@@ -142,7 +139,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
     double t = t0;
 
     AdStage st0;
-    bad |= ad_eval<J2>(P, x, 0.0, u0x, u0y, u0z, dux, duy, duz, st0);
+    bad |= ad_eval<J2, GENU>(P, x, 0.0, t0, hold, st0);
     // ---- select_initial_step (common.py); f = tf * k, y0 = [I, x] ------------------------------------------
     double h_abs;
     {
@@ -173,7 +170,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
 #pragma unroll
         for (int i = 0; i < 7; ++i) x1[i] = fma(hs0, st0.k[i], x[i]);
         AdStage stA;
-        bad |= ad_eval<J2>(P, x1, h0 * ilen, u0x, u0y, u0z, dux, duy, duz, stA);
+        bad |= ad_eval<J2, GENU>(P, x1, h0 * ilen, t0 + h0, hold, stA);
         double d2sq = 0.0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
@@ -245,7 +242,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                     xs_[i] = fma(dy, hs, x[i]);
                 }
                 AdStage sg;
-                bad |= ad_eval<J2>(P, xs_, (t + cs[s] * h - t0) * ilen, u0x, u0y, u0z, dux, duy, duz, sg);
+                bad |= ad_eval<J2, GENU>(P, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
 #pragma unroll
                 for (int i = 0; i < 7; ++i) kx[s][i] = sg.k[i];
                 ad_store_stage<BLOCK>(sm, s, sg);
@@ -259,7 +256,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                 for (int l = 0; l < 6; ++l) dy = fma(kx[l][i], bw[l], dy);
                 xn[i] = fma(hs, dy, x[i]);
             }
-            bad |= ad_eval<J2>(P, xn, (t + h - t0) * ilen, u0x, u0y, u0z, dux, duy, duz, st6);
+            bad |= ad_eval<J2, GENU>(P, xn, (t + h - t0) * ilen, t + h, hold, st6);
             ad_store_stage<BLOCK>(sm, 6, st6);
             double esum = 0.0;
 #pragma unroll

@@ -168,6 +168,65 @@ __device__ __forceinline__ void column_step(double (&pr)[3], double (&pv)[3], co
     pv[2] = fma(hs_6, (sz + wz) + k4z, pv[2]);
 }
 
+// Input hold u(tau).  GENU = false: u is given on the K nodes of x, so inside one interval the reference's
+// first-order hold (linearize_discretize.py:294-315) is the straight line between u_k and u_{k+1}.
+// GENU = true: u has its own column count Ku (the reference accepts that: u_FOH takes its grid from u itself,
+// :308-315; its own test_linearize_many does it, test_discretizer.py:103) -- the hold is evaluated on u's global
+// grid with the reference's index arithmetic (tau == 1 -> last column, k = floor(tau / dtau)).
+template <bool GENU>
+struct UHold;
+
+template <>
+struct UHold<false> {
+    double u0x, u0y, u0z, dux, duy, duz;
+    __device__ __forceinline__ void init(const double *u, int sat, int k, int K, int)
+    {
+        const double *us = u + ((long long)sat * 3) * K + k;
+        u0x = us[0];
+        u0y = us[K];
+        u0z = us[2 * (long long)K];
+        dux = us[1] - u0x;
+        duy = us[K + 1] - u0y;
+        duz = us[2 * (long long)K + 1] - u0z;
+    }
+    // s: position inside the interval in [0,1];  tau: the same point on the global grid (unused here)
+    __device__ __forceinline__ void at(double s, double, double &ux, double &uy, double &uz) const
+    {
+        ux = fma(s, dux, u0x);
+        uy = fma(s, duy, u0y);
+        uz = fma(s, duz, u0z);
+    }
+};
+
+template <>
+struct UHold<true> {
+    const double *base;
+    int Ku;
+    __device__ __forceinline__ void init(const double *u, int sat, int, int, int Ku_)
+    {
+        Ku = Ku_;
+        base = u + ((long long)sat * 3) * Ku_;
+    }
+    __device__ __forceinline__ void at(double, double tau, double &ux, double &uy, double &uz) const
+    {
+        if (tau == 1.0 || Ku < 2) {
+            ux = base[Ku - 1];
+            uy = base[2 * Ku - 1];
+            uz = base[3 * (long long)Ku - 1];
+            return;
+        }
+        const double km1 = (double)(Ku - 1);
+        const double dtau = 1.0 / km1;
+        int k = (int)floor(tau / dtau);
+        k = min(max(k, 0), Ku - 2);
+        const double lo = (double)k / km1, hi = (double)(k + 1) / km1;
+        const double ln = (hi - tau) / (hi - lo), lp = (tau - lo) / (hi - lo);
+        ux = fma(ln, base[k], lp * base[k + 1]);
+        uy = fma(ln, base[Ku + k], lp * base[Ku + k + 1]);
+        uz = fma(ln, base[2 * (long long)Ku + k], lp * base[2 * (long long)Ku + k + 1]);
+    }
+};
+
 // Shared-memory accumulator slots (per thread), entry e at smem[e * BLOCK + tid]:
 //   0..17  I0[a][j]   sum w   Phi^-1 Duf   rows a = 0..5 (row 6 handled below), j = 0..2
 //  18..35  I1[a][j]   sum w s Phi^-1 Duf
@@ -392,10 +451,10 @@ __device__ __forceinline__ int epilogue_store(volatile double *acc, const double
 }
 #undef ACC
 
-template <bool J2, int BLOCK, int MAXREG, int NDST>
+template <bool J2, int BLOCK, int MAXREG, int NDST, bool GENU>
 __global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG)
 discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ tf_arr,
-                  DiscParams P, int n_sats, int K, int n_sub, DstTab dst, long long pitch, long long offset,
+                  DiscParams P, int n_sats, int K, int Ku, int n_sub, DstTab dst, long long pitch, long long offset,
                   int32_t *__restrict__ status)
 {
     extern __shared__ double acc_smem[];
@@ -411,12 +470,12 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     const int k = (int)(gid - (long long)s * (K - 1));
     const double tf = tf_arr[s];
     const double *xs = x + ((long long)s * 7) * K + k;
-    const double *us = u + ((long long)s * 3) * K + k;
     double rx = xs[0], ry = xs[K], rz = xs[2 * (long long)K];
     double vx = xs[3 * (long long)K], vy = xs[4 * (long long)K], vz = xs[5 * (long long)K];
     double m = xs[6 * (long long)K];
-    const double u0x = us[0], u0y = us[K], u0z = us[2 * (long long)K];
-    const double dux = us[1] - u0x, duy = us[K + 1] - u0y, duz = us[2 * (long long)K + 1] - u0z;
+    UHold<GENU> hold;
+    hold.init(u, s, k, K, Ku);
+    const double tau0 = (double)k / (double)(K - 1), dtau_k = 1.0 / (double)(K - 1);  // interval [tau_k, tau_k+1]
 
     const double inv_n = 1.0 / (double)n_sub;
     const double h = inv_n / (double)(K - 1);  // step in tau
@@ -437,7 +496,8 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
 
     int bad = 0;
     // thrust at the current node and its norm
-    double ux = u0x, uy = u0y, uz = u0z;
+    double ux, uy, uz;
+    hold.at(0.0, tau0, ux, uy, uz);
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
     double iun = (uu > 4.930380657631324e-32) ? fast_rsqrt(uu) : 0.0;  // |u| <= eps  (:208)
     double un = uu * iun;
@@ -470,8 +530,9 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
 
         // ---- stages 2..4 of the state (Nystrom form; mass stages are explicit in tau) -----------
         const double sm = ((double)n + 0.5) * inv_n, se = (double)(n + 1) * inv_n;
-        const double umx = fma(sm, dux, u0x), umy = fma(sm, duy, u0y), umz = fma(sm, duz, u0z);
-        const double uex = fma(se, dux, u0x), uey = fma(se, duy, u0y), uez = fma(se, duz, u0z);
+        double umx, umy, umz, uex, uey, uez;
+        hold.at(sm, fma(sm, dtau_k, tau0), umx, umy, umz);
+        hold.at(se, (n + 1 == n_sub && k + 2 == K) ? 1.0 : fma(se, dtau_k, tau0), uex, uey, uez);
         const double uum = fma(umx, umx, fma(umy, umy, umz * umz));
         const double uue = fma(uex, uex, fma(uey, uey, uez * uez));
         const double iunm = (uum > 4.930380657631324e-32) ? fast_rsqrt(uum) : 0.0;

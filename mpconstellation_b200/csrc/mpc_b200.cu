@@ -63,13 +63,18 @@ mpc::PropParams prop_params(const mpc_params *p)
 }
 
 std::atomic<int> g_tuning{0};
+thread_local int g_ucols = 0;  // columns of u when it lives on its own grid (set by the *_ugrid entry points)
+struct UcolsScope {            // routes the launchers to the general-grid input hold for the duration of one call
+    explicit UcolsScope(int n) { g_ucols = n; }
+    ~UcolsScope() { g_ucols = 0; }
+};
 
-template <bool J2, int BLOCK, int MAXREG, int NDST>
+template <bool J2, int BLOCK, int MAXREG, int NDST, bool GENU = false>
 int launch_disc_cfg(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                     int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
                     cudaStream_t st)
 {
-    auto kern = mpc::discretize_kernel<J2, BLOCK, MAXREG, NDST>;
+    auto kern = mpc::discretize_kernel<J2, BLOCK, MAXREG, NDST, GENU>;
     const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -81,7 +86,7 @@ int launch_disc_cfg(const double *x, const double *u, const double *tf, const mp
     }
     const long long n_int = (long long)n_sats * (K - 1);
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, g_ucols, n_sub, dst, pitch, offset, status);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
@@ -95,6 +100,7 @@ int launch_disc_n(const double *x, const double *u, const double *tf, const mpc:
                   cudaStream_t st)
 {
 #define MPC_ARGS x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, st
+    if (NDST == 1 && g_ucols > 0) return launch_disc_cfg<J2, kDiscBlock, 255, 1, true>(MPC_ARGS);
     if (!J2 && NDST == 1) {
         switch (g_tuning.load(std::memory_order_relaxed)) {
             case 1: return launch_disc_cfg<false, 32, 224, 1>(MPC_ARGS);   //  9 warps / SM
@@ -133,13 +139,27 @@ struct AdaptiveOpts {   // scipy solve_ivp(RK45) controls of the reference's def
     int32_t *n_nodes;
 };
 
+template <bool J2, bool GENU>
+int launch_adaptive_g(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                      const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                      cudaStream_t st);
+
 template <bool J2>
 int launch_adaptive(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                     const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
                     cudaStream_t st)
 {
+    return g_ucols > 0 ? launch_adaptive_g<J2, true>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st)
+                       : launch_adaptive_g<J2, false>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+}
+
+template <bool J2, bool GENU>
+int launch_adaptive_g(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                      const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                      cudaStream_t st)
+{
     constexpr int BLOCK = 32;
-    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1>;
+    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1, GENU>;
     const size_t smem = (size_t)mpc::kAdSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -151,8 +171,8 @@ int launch_adaptive(const double *x, const double *u, const double *tf, const mp
     }
     const long long n_int = (long long)n_sats * (K - 1);
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, o.rtol, o.atol, o.max_step, dst, pitch, offset, status,
-                                    o.n_nodes);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, g_ucols, o.rtol, o.atol, o.max_step, dst, pitch, offset,
+                                    status, o.n_nodes);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
@@ -369,6 +389,19 @@ int mpc_discretize_batch_adaptive(const double *x, const double *u, const double
                          : launch_adaptive<false>(x, u, tf, P, n_sats, K, o, tab, out_pitch, out_offset, status, (cudaStream_t)stream);
 }
 
+int mpc_discretize_batch_ugrid(const double *x, const double *u, int u_cols, const double *tf, const mpc_params *p,
+                               int n_sats, int K, int adaptive, int n_sub, double rtol, double atol, double max_step,
+                               double *out, int64_t out_pitch, int64_t out_offset, int32_t *status, int32_t *n_nodes,
+                               void *stream)
+{
+    if (u_cols < 2) return fail(MPC_E_INVALID, "u needs at least 2 columns (got %d)", u_cols);
+    UcolsScope scope(u_cols);
+    if (adaptive)
+        return mpc_discretize_batch_adaptive(x, u, tf, p, n_sats, K, rtol, atol, max_step, out, out_pitch, out_offset,
+                                             status, n_nodes, stream);
+    return mpc_discretize_batch(x, u, tf, p, n_sats, K, n_sub, out, out_pitch, out_offset, status, stream);
+}
+
 int mpc_propagate_batch(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
                         int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status, void *stream)
 {
@@ -443,7 +476,8 @@ static int disc_host(mpc_ctx *ctx, const double *x, const double *u, const doubl
     if (n_int == 0) return MPC_SUCCESS;
     CUDA_TRY(cudaSetDevice(ctx->device));
     if ((rc = ensure(ctx->d_x, ctx->cap_x, (size_t)n_sats * 7 * K))) return rc;
-    if ((rc = ensure(ctx->d_u, ctx->cap_u, (size_t)n_sats * 3 * K))) return rc;
+    const int Ku = g_ucols > 0 ? g_ucols : K;   // columns of u (its own grid in the *_ugrid entry points)
+    if ((rc = ensure(ctx->d_u, ctx->cap_u, (size_t)n_sats * 3 * Ku))) return rc;
     if ((rc = ensure(ctx->d_tf, ctx->cap_tf, (size_t)n_sats))) return rc;
     if ((rc = ensure(ctx->d_out, ctx->cap_out, (size_t)n_int * MPC_OUT_ROWS))) return rc;
     if ((rc = ensure(ctx->d_status, ctx->cap_status, (size_t)n_int))) return rc;
@@ -455,10 +489,10 @@ static int disc_host(mpc_ctx *ctx, const double *x, const double *u, const doubl
     CUDA_TRY(cudaMemcpyAsync(ctx->d_tf, tf, (size_t)n_sats * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
     for (int c = 0; c < n_chunks; ++c) {
         const int s0 = c * cs, ns = std::min(cs, n_sats - s0);
-        const double *dx = ctx->d_x + (size_t)s0 * 7 * K, *du = ctx->d_u + (size_t)s0 * 3 * K;
+        const double *dx = ctx->d_x + (size_t)s0 * 7 * K, *du = ctx->d_u + (size_t)s0 * 3 * Ku;
         CUDA_TRY(cudaMemcpyAsync((void *)dx, x + (size_t)s0 * 7 * K, (size_t)ns * 7 * K * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->s_compute));
-        CUDA_TRY(cudaMemcpyAsync((void *)du, u + (size_t)s0 * 3 * K, (size_t)ns * 3 * K * sizeof(double),
+        CUDA_TRY(cudaMemcpyAsync((void *)du, u + (size_t)s0 * 3 * Ku, (size_t)ns * 3 * Ku * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->s_compute));
         mpc::DstTab tab{};
         tab.p[0] = ctx->d_out;
@@ -501,6 +535,18 @@ int mpc_discretize_batch_adaptive_host(mpc_ctx *ctx, const double *x, const doub
 {
     const AdaptiveOpts o{rtol, atol, max_step, nullptr};
     return disc_host(ctx, x, u, tf, p, n_sats, K, 1, &o, out_host, status_host, n_nodes_host);
+}
+
+int mpc_discretize_batch_ugrid_host(mpc_ctx *ctx, const double *x, const double *u, int u_cols, const double *tf,
+                                    const mpc_params *p, int n_sats, int K, int adaptive, int n_sub, double rtol,
+                                    double atol, double max_step, double *out_host, int32_t *status_host,
+                                    int32_t *n_nodes_host)
+{
+    if (u_cols < 2) return fail(MPC_E_INVALID, "u needs at least 2 columns (got %d)", u_cols);
+    UcolsScope scope(u_cols);
+    const AdaptiveOpts o{rtol, atol, max_step, nullptr};
+    return disc_host(ctx, x, u, tf, p, n_sats, K, adaptive ? 1 : n_sub, adaptive ? &o : nullptr, out_host, status_host,
+                     adaptive ? n_nodes_host : nullptr);
 }
 
 static int upload_table(mpc_ctx *ctx, const mpc_controller *ctrl, int n_sats, cudaStream_t st)

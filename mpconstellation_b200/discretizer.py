@@ -72,9 +72,7 @@ class Discretizer:
         K = x.shape[2]
         if K < 2:
             raise ValueError("need at least K = 2 temporal nodes")
-        if u.shape[-1] != K:
-            raise ValueError(f"u has {u.shape[-1]} columns but x has {K}: the device first-order hold needs u on "
-                             "the same K nodes as x")
+        # u may have its own column count: the reference's hold takes its grid from u (linearize_discretize.py:308-315)
         # use_uniform_steps=False (the reference default): quadrature on the steps scipy's RK45 controller accepts
         # (replayed on the device, scipy's default rtol/atol as the reference passes none);
         # use_uniform_steps=True: fixed-step RK4 on the uniform integrator_steps grid.
