@@ -248,8 +248,28 @@ int prop_device(const double *y0, const double *tf, const mpc_params *p, const m
     C.table = (c->kind == MPC_CTRL_SEQUENCE) ? table_dev : nullptr;
     C.end_tau_arr = (c->kind == MPC_CTRL_SEQUENCE) ? end_tau_dev : nullptr;
     const unsigned grid = (unsigned)((n_sats + kPropBlock - 1) / kPropBlock);
-    mpc::propagate_kernel<kPropBlock><<<grid, kPropBlock, 0, st>>>(y0, tf, prop_params(p), C, n_sats, T, n_sub, y,
-                                                                  u_out, status);
+    const mpc::PropParams PP = prop_params(p);
+    // one straight-line kernel per (controller law, drag, J2)
+#define MPC_PROP(KIND, DRAG, J2) \
+    mpc::propagate_kernel<kPropBlock, KIND, DRAG, J2><<<grid, kPropBlock, 0, st>>>(y0, tf, PP, C, n_sats, T, n_sub, y, u_out, status)
+#define MPC_PROP_K(KIND)                                   \
+    do {                                                   \
+        if (p->include_drag) {                             \
+            if (p->include_j2) MPC_PROP(KIND, true, true); \
+            else MPC_PROP(KIND, true, false);              \
+        } else {                                           \
+            if (p->include_j2) MPC_PROP(KIND, false, true); \
+            else MPC_PROP(KIND, false, false);             \
+        }                                                  \
+    } while (0)
+    switch (c->kind) {
+        case MPC_CTRL_ZERO: MPC_PROP_K(0); break;
+        case MPC_CTRL_CONSTANT: MPC_PROP_K(1); break;
+        case MPC_CTRL_TANGENTIAL: MPC_PROP_K(2); break;
+        default: MPC_PROP_K(3); break;
+    }
+#undef MPC_PROP_K
+#undef MPC_PROP
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;

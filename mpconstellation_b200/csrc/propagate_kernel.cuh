@@ -30,25 +30,26 @@ struct CtrlParams {
     const double *end_tau_arr;  // optional per-satellite end_tau
 };
 
+// Controller law, compile-time kind (straight-line code per law); `ir` = 1/|r| of y, already needed by gravity.
+template <int KIND>
 __device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__restrict__ tab, double end_tau,
-                                          const double (&y)[7], double tau, double &ux, double &uy, double &uz)
+                                          const double (&y)[7], double ir, double tau, double &ux, double &uy,
+                                          double &uz)
 {
     ux = uy = uz = 0.0;
-    if (C.kind == 1) {  // control.py:47-53
+    if (KIND == 1) {  // control.py:47-53
         ux = C.t0;
         uy = C.t1;
         uz = C.t2;
-    } else if (C.kind == 2) {  // control.py:66-84: thrust along t_hat = h_hat x r_hat
-        const double ir = fast_rsqrt(fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2])));
-        const double nx = y[0] * ir, ny = y[1] * ir, nz = y[2] * ir;
+    } else if (KIND == 2) {  // control.py:66-84: thrust along t_hat = h_hat x r_hat
         const double hx = fma(y[1], y[5], -y[2] * y[4]);
         const double hy = fma(y[2], y[3], -y[0] * y[5]);
         const double hz = fma(y[0], y[4], -y[1] * y[3]);
-        const double ih = C.t0 * fast_rsqrt(fma(hx, hx, fma(hy, hy, hz * hz)));
-        ux = ih * fma(hy, nz, -hz * ny);
-        uy = ih * fma(hz, nx, -hx * nz);
-        uz = ih * fma(hx, ny, -hy * nx);
-    } else if (C.kind == 3) {  // control.py:104-143: FOH table on tau/end_tau, zero after end_tau
+        const double sc = C.t0 * ir * fast_rsqrt(fma(hx, hx, fma(hy, hy, hz * hz)));   // mag / (|h| |r|)
+        ux = sc * fma(hy, y[2], -hz * y[1]);
+        uy = sc * fma(hz, y[0], -hx * y[2]);
+        uz = sc * fma(hx, y[1], -hy * y[0]);
+    } else if (KIND == 3) {  // control.py:104-143: FOH table on tau/end_tau, zero after end_tau
         if (tau <= end_tau) {
             const int Ku = C.table_len;
             const double t = tau / end_tau;
@@ -72,21 +73,22 @@ __device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__r
 }
 
 // f(y,u) without the tf factor (simulator.py:130-160); returns nonzero on non-positive mass
+template <int KIND, bool DRAG, bool J2>
 __device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C, const double *__restrict__ tab,
                                         double end_tau, const double (&y)[7], double tau, double (&dy)[7])
 {
-    double ux, uy, uz;
-    ctrl_eval(C, tab, end_tau, y, tau, ux, uy, uz);
     const double m = y[6];
     const double r2 = fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2]));
     const double ir = fast_rsqrt(r2);
+    double ux, uy, uz;
+    ctrl_eval<KIND>(C, tab, end_tau, y, ir, tau, ux, uy, uz);
     const double ir2 = ir * ir;
     const double mu3 = P.mu * ir * ir2;
     const double im = fast_rcp(m);
     double ax = fma(-mu3, y[0], ux * im);
     double ay = fma(-mu3, y[1], uy * im);
     double az = fma(-mu3, y[2], uz * im);
-    if (P.include_drag) {
+    if (DRAG) {
         const double v2 = fma(y[3], y[3], fma(y[4], y[4], y[5] * y[5]));
         const double vn = (v2 > 0.0) ? v2 * fast_rsqrt(v2) : 0.0;
         const double c = -P.drag_k * im * vn;
@@ -94,7 +96,7 @@ __device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C
         ay = fma(c, y[4], ay);
         az = fma(c, y[5], az);
     }
-    if (P.include_j2) {
+    if (J2) {
         const double nz = y[2] * ir;
         const double q5 = 5.0 * nz * nz;
         const double k5 = P.kj2 * ir2 * ir2 * ir;
@@ -103,8 +105,13 @@ __device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C
         ay = fma(c1, y[1], ay);
         az = fma(k5 * (q5 - 3.0), y[2], az);
     }
-    const double uu = fma(ux, ux, fma(uy, uy, uz * uz));
-    const double un = (uu > 0.0) ? uu * fast_rsqrt(uu) : 0.0;
+    double un;
+    if (KIND == 0) un = 0.0;
+    else if (KIND == 2) un = fabs(C.t0);          // |t_hat| = 1: the tangential law has constant magnitude
+    else {
+        const double uu = fma(ux, ux, fma(uy, uy, uz * uz));
+        un = (uu > 0.0) ? uu * fast_rsqrt(uu) : 0.0;
+    }
     dy[0] = y[3];
     dy[1] = y[4];
     dy[2] = y[5];
@@ -115,7 +122,7 @@ __device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C
     return !(m > 0.0);
 }
 
-template <int BLOCK>
+template <int BLOCK, int KIND, bool DRAG, bool J2>
 __global__ void __launch_bounds__(BLOCK)
 propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_arr, PropParams P, CtrlParams C,
                  int n_sats, int T, int n_sub, double *__restrict__ y_out, double *__restrict__ u_out,
@@ -152,7 +159,8 @@ propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_ar
         for (int c = 0; c < 7; ++c) yo[(long long)c * T + j] = y[c];
         if (uo) {
             double ux, uy, uz;
-            ctrl_eval(C, tab, end_tau, y, tau_j, ux, uy, uz);
+            const double irs = fast_rsqrt(fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2])));
+            ctrl_eval<KIND>(C, tab, end_tau, y, irs, tau_j, ux, uy, uz);
             uo[j] = ux;
             uo[T + j] = uy;
             uo[2 * (long long)T + j] = uz;
@@ -164,16 +172,16 @@ propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_ar
             const double t0 = (n == 0) ? tau_j : fma((double)n, h, tau_j);
             const double t1 = (n == n_sub - 1) ? tau_n : fma((double)(n + 1), h, tau_j);
             const double tm = 0.5 * (t0 + t1);
-            bad |= prop_rhs(P, C, tab, end_tau, y, t0, k1);
+            bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, y, t0, k1);
 #pragma unroll
             for (int c = 0; c < 7; ++c) yt[c] = fma(hh, k1[c], y[c]);
-            bad |= prop_rhs(P, C, tab, end_tau, yt, tm, k2);
+            bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, yt, tm, k2);
 #pragma unroll
             for (int c = 0; c < 7; ++c) yt[c] = fma(hh, k2[c], y[c]);
-            bad |= prop_rhs(P, C, tab, end_tau, yt, tm, k3);
+            bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, yt, tm, k3);
 #pragma unroll
             for (int c = 0; c < 7; ++c) yt[c] = fma(hs, k3[c], y[c]);
-            bad |= prop_rhs(P, C, tab, end_tau, yt, t1, k4);
+            bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, yt, t1, k4);
             if (bad) break;
 #pragma unroll
             for (int c = 0; c < 7; ++c) y[c] = fma(hs_6, (k1[c] + k4[c]) + 2.0 * (k2[c] + k3[c]), y[c]);
