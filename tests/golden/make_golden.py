@@ -174,7 +174,20 @@ def main():
              p6_t=np.stack([sim.sim_time[s1.id], sim.sim_time[s2.id]]),
              p6_final_dim=np.stack([s1.get_state_vector(), s2.get_state_vector()]))
     np.savez(os.path.join(HERE, "propagate.npz"), **p)
-    for f in ("discretize.npz", "propagate.npz"):
+    # ------------------------------------------------------------------ constraint terms (optimizer.py:80-170)
+    import optimizer as ref_optimizer
+    gd = np.load(os.path.join(HERE, "discretize.npz"))
+    zero_u = np.zeros((3, gd["d4_x"].shape[1]))
+    cases = {"c0": (gd["d3_x"], gd["d3_u"]), "c1": (gd["d2_x"], gd["d2_u"]), "c2": (gd["d4_x"], zero_u)}
+    ct = {"MU": const.MU}
+    for tag, (xb, ub) in cases.items():
+        opt = ref_optimizer.Optimizer([xb], [ub], [np.zeros_like(xb)], 1.0, None, None, scale, verbose=False)
+        out = opt.get_constraint_terms()
+        ct[tag + "_x"], ct[tag + "_u"] = xb, ub
+        for key, val in out.items():
+            ct[f"{tag}_{key}"] = np.asarray(val[0])
+    np.savez(os.path.join(HERE, "constraint_terms.npz"), **ct)
+    for f in ("discretize.npz", "propagate.npz", "constraint_terms.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 
