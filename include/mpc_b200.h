@@ -173,6 +173,8 @@ void mpc_host_free(void *p);
  * Host-buffer form of mpc_discretize_batch: copies x/u/tf to the device, runs the kernel and
  * copies the SoA result back, pipelined in satellite chunks over two streams.
  * out_host is [105][n_sats*(K-1)] (pitch = n_sats*(K-1)); status_host [n_sats*(K-1)] or NULL.
+ * Rows 42..48 (the last row of A_k, structurally 0 0 0 0 0 0 1 because the last row of the Jacobian is zero,
+ * linearize_discretize.py:177-179) are not moved over PCIe: the library writes them into out_host itself.
  */
 int mpc_discretize_batch_host(mpc_ctx *ctx, const double *x, const double *u, const double *tf,
                               const mpc_params *p, int n_sats, int K, int n_sub, double *out_host,
@@ -205,6 +207,39 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
                                   const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
                                   int n_sub_prop, int n_sub_disc, double *y_host, double *u_host,
                                   double *out_host, int32_t *status_host);
+
+/* ---------------------------------------------------------------- constraint terms (next step of the path) */
+
+/*
+ * Replaces Optimizer.get_constraint_terms (optimizer.py:80-170) for a batch of satellites: the step that follows
+ * the discretization inside Optimizer.solve_OPT (optimizer.py:243-262).
+ *
+ *   x  [n_sats][7][K], u [n_sats][3][u_cols]   the reference trajectories / inputs (x_bar, u_bar)
+ *   mu                                         const.MU
+ *   rbar_hat [n_sats][3][K-1]                  r_bar/|r_bar| on nodes 0..K-2            optimizer.py:128-129
+ *   ubar_hat [n_sats][3][u_cols]               as the reference computes it (filled only where |u| <= eps,
+ *                                              i.e. 0/0 = NaN for zero thrust, 0 elsewhere) optimizer.py:132-139
+ *   final_terms [n_sats][MPC_FINAL_TERMS]      terminal-node terms, offsets MPC_FT_*    optimizer.py:108-168
+ */
+#define MPC_FINAL_TERMS 32
+#define MPC_FT_RF_HAT 0         /* 3 */
+#define MPC_FT_VC 3             /* 1 */
+#define MPC_FT_DRVC 4           /* 3 */
+#define MPC_FT_DRVC_RBAR 7      /* 1 */
+#define MPC_FT_VT 8             /* 1 */
+#define MPC_FT_DRVT_DVVT 9      /* 6 */
+#define MPC_FT_DRVT_DVVT_BAR 15 /* 1 */
+#define MPC_FT_VR 16            /* 1 */
+#define MPC_FT_DRVR_DVVR 17     /* 6 */
+#define MPC_FT_DRVR_DVVR_BAR 23 /* 1 */
+#define MPC_FT_VN 24            /* 1 */
+#define MPC_FT_DRVN_DVVN 25     /* 6 */
+#define MPC_FT_DRVN_DVVN_BAR 31 /* 1 */
+int mpc_constraint_terms(const double *x, const double *u, int n_sats, int K, int u_cols, double mu, double *rbar_hat,
+                         double *ubar_hat, double *final_terms, void *stream);
+/* Host-buffer form. */
+int mpc_constraint_terms_host(mpc_ctx *ctx, const double *x, const double *u, int n_sats, int K, int u_cols, double mu,
+                              double *rbar_hat, double *ubar_hat, double *final_terms);
 
 /* ---------------------------------------------------------------- measurement helpers */
 

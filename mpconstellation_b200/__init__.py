@@ -5,6 +5,7 @@ from . import _lib
 from ._lib import pinned_empty
 from .batch import (DiscretizedBatch, discretize_batch, discretize_batch_device, fp64_peak_tflops, launch_count,
                     propagate_batch, propagate_batch_device, propagate_discretize)
+from .constraints import constraint_terms_batch, constraint_terms_device, get_constraint_terms
 from .control import (ConstantTangentialThrustController, ConstantThrustController, Controller, ControllerSpec,
                       SequenceController, spec_from)
 from .discretizer import Discretizer
@@ -14,4 +15,4 @@ from .simulator import Simulator
 __all__ = ["Discretizer", "Simulator", "Satellite", "SatelliteScale", "Constants", "Controller",
            "ConstantThrustController", "ConstantTangentialThrustController", "SequenceController", "ControllerSpec",
            "spec_from", "discretize_batch", "discretize_batch_device", "propagate_batch", "propagate_batch_device",
-           "propagate_discretize", "DiscretizedBatch", "pinned_empty", "fp64_peak_tflops", "launch_count"]
+           "propagate_discretize", "constraint_terms_batch", "constraint_terms_device", "get_constraint_terms", "DiscretizedBatch", "pinned_empty", "fp64_peak_tflops", "launch_count"]

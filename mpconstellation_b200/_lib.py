@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libmpc_b200.so")
 SOURCES = ["mpc_b200.cu"]
-HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "propagate_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
+HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "propagate_kernel.cuh", "constraint_terms_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -23,6 +23,11 @@ MPC_OUT_ROWS = 105
 ROW_A, ROW_BP, ROW_BN, ROW_SIGMA, ROW_XI = 0, 49, 70, 91, 98
 CTRL_ZERO, CTRL_CONSTANT, CTRL_TANGENTIAL, CTRL_SEQUENCE = 0, 1, 2, 3
 ST_OK, ST_MASS, ST_NONFINITE, ST_STEP = 0, 1, 2, 3
+FINAL_TERMS = 32
+# key -> (offset, length) inside the per-satellite terminal block (include/mpc_b200.h MPC_FT_*); length 0 = scalar
+FINAL_TERM_LAYOUT = {"rf_hat": (0, 3), "Vc": (3, 0), "DrVc": (4, 3), "DrVc_rbar": (7, 0), "Vt": (8, 0),
+                     "DrVt_DvVt": (9, 6), "DrVt_DvVt_bar": (15, 0), "Vr": (16, 0), "DrVr_DvVr": (17, 6),
+                     "DrVr_DvVr_bar": (23, 0), "Vn": (24, 0), "DrVn_DvVn": (25, 6), "DrVn_DvVn_bar": (31, 0)}
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4
 
 
@@ -104,6 +109,8 @@ def lib():
     L.mpc_discretize_batch_host.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, _DP, _DP]
     L.mpc_propagate_batch_host.argtypes = [vp, _DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP]
     L.mpc_propagate_discretize_host.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, _DP]
+    L.mpc_constraint_terms.argtypes = [_DP, _DP, i, i, i, d, _DP, _DP, _DP, vp]
+    L.mpc_constraint_terms_host.argtypes = [vp, _DP, _DP, i, i, i, d, _DP, _DP, _DP]
     L.mpc_fp64_peak_probe.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.mpc_set_tuning.argtypes = [i]
     L.mpc_set_tuning.restype = i
@@ -111,7 +118,8 @@ def lib():
                  "mpc_discretize_batch_adaptive", "mpc_discretize_batch_adaptive_host",
                  "mpc_discretize_batch_ugrid", "mpc_discretize_batch_ugrid_host",
                  "mpc_ctx_create", "mpc_ctx_destroy", "mpc_discretize_batch_host", "mpc_propagate_batch_host",
-                 "mpc_propagate_discretize_host", "mpc_fp64_peak_probe"):
+                 "mpc_propagate_discretize_host", "mpc_fp64_peak_probe", "mpc_constraint_terms",
+                 "mpc_constraint_terms_host"):
         getattr(L, name).restype = i
     _lib = L
     return L
@@ -122,6 +130,7 @@ EXPORTED_SYMBOLS = [
     "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_discretize_batch_ugrid", "mpc_propagate_batch",
     "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
     "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_discretize_batch_ugrid_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host",
+    "mpc_constraint_terms", "mpc_constraint_terms_host",
     "mpc_fp64_peak_probe", "mpc_set_tuning",
 ]
 

@@ -1,0 +1,77 @@
+"""Optimizer.get_constraint_terms (optimizer.py:80-170) for a batch of satellites, on the GPU.
+
+This is the step that follows the discretization inside Optimizer.solve_OPT (optimizer.py:243-262): unit vectors
+of the reference positions / thrusts and the linearised circular-orbit terminal conditions.  The reference's
+formulas are mirrored literally, including its inverted `ubar_hat` mask (optimizer.py:137-138) and the operator
+precedence of `Dv_h_hat` (optimizer.py:121) -- they define what the optimizer is handed.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .batch import _ctx, _f64
+
+KEYS = ['rbar_hat', 'ubar_hat', 'rf_hat', 'Vc', 'DrVc', 'DrVc_rbar', 'Vt', 'DrVt_DvVt', 'DrVt_DvVt_bar',
+        'Vr', 'DrVr_DvVr', 'DrVr_DvVr_bar', 'Vn', 'DrVn_DvVn', 'DrVn_DvVn_bar']    # optimizer.py:101-104
+
+
+def _split_final(fin):
+    """[N,32] terminal block -> {key: [N] or [N,len]} views (layout: include/mpc_b200.h MPC_FT_*)."""
+    out = {}
+    for key, (off, ln) in _lib.FINAL_TERM_LAYOUT.items():
+        out[key] = fin[:, off] if ln == 0 else fin[:, off:off + ln]
+    return out
+
+
+def constraint_terms_batch(x, u, const, device=0):
+    """x [N,7,K], u [N,3,Ku] (host arrays) -> dict of stacked arrays: rbar_hat [N,3,K-1], ubar_hat [N,3,Ku],
+    rf_hat [N,3], Vc [N], DrVc [N,3], ... with the reference's keys."""
+    ctx = _ctx(device)
+    x = _f64(x)
+    u = _f64(u)
+    if x.ndim != 3 or x.shape[1] != 7 or x.shape[2] < 2:
+        raise ValueError(f"x must be [N,7,K] with K >= 2, got {x.shape}")
+    N, _, K = x.shape
+    if u.ndim != 3 or u.shape[:2] != (N, 3) or u.shape[2] < 1:
+        raise ValueError(f"u must be [N,3,Ku], got {u.shape}")
+    Ku = u.shape[2]
+    rbar = np.empty((N, 3, K - 1))
+    ubar = np.empty((N, 3, Ku))
+    fin = np.empty((N, _lib.FINAL_TERMS))
+    _lib.check(_lib.lib().mpc_constraint_terms_host(ctx, _lib.addr(x), _lib.addr(u), N, K, Ku, float(const.MU),
+                                                    _lib.addr(rbar), _lib.addr(ubar), _lib.addr(fin)))
+    out = {"rbar_hat": rbar, "ubar_hat": ubar}
+    out.update(_split_final(fin))
+    return out
+
+
+def constraint_terms_device(x, u, const, rbar_hat=None, ubar_hat=None, final_terms=None):
+    """Device form: x [N,7,K], u [N,3,Ku] float64 CUDA tensors; enqueued on torch's current stream.
+    Returns (rbar_hat [N,3,K-1], ubar_hat [N,3,Ku], final_terms [N,32])."""
+    import torch
+    N, _, K = x.shape
+    Ku = u.shape[2]
+    assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and u.is_contiguous() and u.shape[:2] == (N, 3)
+    if rbar_hat is None:
+        rbar_hat = torch.empty((N, 3, K - 1), dtype=torch.float64, device=x.device)
+    if ubar_hat is None:
+        ubar_hat = torch.empty((N, 3, Ku), dtype=torch.float64, device=x.device)
+    if final_terms is None:
+        final_terms = torch.empty((N, _lib.FINAL_TERMS), dtype=torch.float64, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.lib().mpc_constraint_terms(x.data_ptr(), u.data_ptr(), N, K, Ku, float(const.MU),
+                                               rbar_hat.data_ptr(), ubar_hat.data_ptr(), final_terms.data_ptr(),
+                                               stream))
+    return rbar_hat, ubar_hat, final_terms
+
+
+def get_constraint_terms(x_bar, u_bar, const, device=0):
+    """Drop-in for Optimizer.get_constraint_terms: x_bar / u_bar are the optimizer's N-element lists of (7,K) /
+    (3,K) arrays; returns the same dict of N-element lists (optimizer.py:84-100)."""
+    if len(x_bar) == 0:
+        return {k: [] for k in KEYS}
+    stacked = constraint_terms_batch(np.stack([np.asarray(a, dtype=np.float64) for a in x_bar]),
+                                     np.stack([np.asarray(a, dtype=np.float64) for a in u_bar]), const, device=device)
+    n = len(x_bar)
+    return {k: [stacked[k][i] if stacked[k].ndim > 1 else float(stacked[k][i]) for i in range(n)] for k in KEYS}

@@ -16,6 +16,7 @@
 #include "discretize_kernel.cuh"
 #include "discretize_adaptive_kernel.cuh"
 #include "propagate_kernel.cuh"
+#include "constraint_terms_kernel.cuh"
 
 namespace {
 
@@ -280,12 +281,15 @@ int prop_device(const double *y0, const double *tf, const mpc_params *p, const m
 // ------------------------------------------------------------------------------------------------
 struct mpc_ctx {
     int device = 0;
+    int sm_count = 148;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     std::vector<cudaEvent_t> ev;  // one per chunk slot
     // grow-only device workspace
     double *d_x = nullptr, *d_u = nullptr, *d_tf = nullptr, *d_out = nullptr, *d_y0 = nullptr, *d_tab = nullptr;
     int32_t *d_status = nullptr, *d_status2 = nullptr, *d_nodes = nullptr;
     double *d_endtau = nullptr;
+    int32_t *h_stage = nullptr;  // pinned staging for the int32 status / node-count words (caller buffers may be pageable)
+    size_t cap_stage = 0;
     size_t cap_nodes = 0, cap_endtau = 0;
     size_t cap_x = 0, cap_u = 0, cap_tf = 0, cap_out = 0, cap_y0 = 0, cap_tab = 0, cap_status = 0, cap_status2 = 0;
 };
@@ -305,6 +309,20 @@ int ensure(T *&ptr, size_t &cap, size_t count)
     return MPC_SUCCESS;
 }
 
+int ensure_stage(mpc_ctx *ctx, size_t count)
+{
+    if (count <= ctx->cap_stage) return MPC_SUCCESS;
+    if (ctx->h_stage) CUDA_TRY(cudaFreeHost(ctx->h_stage));
+    ctx->h_stage = nullptr;
+    ctx->cap_stage = 0;
+    if (cudaHostAlloc((void **)&ctx->h_stage, count * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MPC_E_NOMEM, "cudaHostAlloc of %zu bytes failed", count * sizeof(int32_t));
+    }
+    ctx->cap_stage = count;
+    return MPC_SUCCESS;
+}
+
 int ensure_events(mpc_ctx *ctx, size_t n)
 {
     while (ctx->ev.size() < n) {
@@ -315,22 +333,38 @@ int ensure_events(mpc_ctx *ctx, size_t n)
     return MPC_SUCCESS;
 }
 
-// satellites per chunk of the host pipeline: about 8 chunks, never smaller than ~64k intervals
-int chunk_sats(int n_sats, int K)
+// Satellites per chunk of the host pipeline: one wave of the discretization kernel (9 one-warp CTAs per SM in
+// the small-batch configuration launch_disc_n picks for a chunk of this size), so that no chunk ends in a
+// partially filled wave, the first D2H starts after ~0.3 ms and the copy engine then never idles.
+int chunk_sats(const mpc_ctx *ctx, int n_sats, int K)
 {
     const long long per_sat = std::max(1, K - 1);
-    long long by_count = (n_sats + 7) / 8;
-    long long by_size = (65536 + per_sat - 1) / per_sat;
-    long long c = std::max(by_count, by_size);
-    return (int)std::min<long long>(std::max<long long>(c, 1), std::max(n_sats, 1));
+    const long long wave = (long long)ctx->sm_count * 9 * 32;
+    return (int)std::min<long long>(std::max<long long>(wave / per_sat, 1), std::max(n_sats, 1));
 }
 
-// D2H of the columns [c0, c0+nc) of the SoA result (105 rows), host pitch = n_int
+// Rows 42..48 of the SoA result are the last row of A_k = Phi(tau_{k+1}).  The last row of the Jacobian A is
+// zero (linearize_discretize.py:177-179), so that row of Phi never leaves its initial value e7^T: the kernels
+// store the constants 0,0,0,0,0,0,1 there.  The host pipeline does not move 7/105 of the result over PCIe for
+// that: it copies rows [0,42) and [49,105) and writes the seven constant rows into the host buffer itself
+// while the DMA engine is busy.
+constexpr int kConstRow0 = MPC_ROW_A + 42, kConstRow1 = MPC_ROW_A + 49;
+
+// D2H of the columns [c0, c0+nc) of the SoA result (all rows but the constant ones), host pitch = n_int
 int copy_out_chunk(double *out_host, const double *d_out, long long n_int, long long c0, long long nc, cudaStream_t st)
 {
-    CUDA_TRY(cudaMemcpy2DAsync(out_host + c0, (size_t)n_int * sizeof(double), d_out + c0, (size_t)n_int * sizeof(double),
-                               (size_t)nc * sizeof(double), MPC_OUT_ROWS, cudaMemcpyDeviceToHost, st));
+    const size_t pitch = (size_t)n_int * sizeof(double), width = (size_t)nc * sizeof(double);
+    CUDA_TRY(cudaMemcpy2DAsync(out_host + c0, pitch, d_out + c0, pitch, width, kConstRow0, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpy2DAsync(out_host + (size_t)kConstRow1 * n_int + c0, pitch, d_out + (size_t)kConstRow1 * n_int + c0,
+                               pitch, width, MPC_OUT_ROWS - kConstRow1, cudaMemcpyDeviceToHost, st));
     return MPC_SUCCESS;
+}
+
+void fill_const_rows(double *out_host, long long n_int)
+{
+    memset(out_host + (size_t)kConstRow0 * n_int, 0, (size_t)6 * n_int * sizeof(double));
+    double *one = out_host + (size_t)(kConstRow1 - 1) * n_int;
+    for (long long i = 0; i < n_int; ++i) one[i] = 1.0;
 }
 
 }  // namespace
@@ -439,6 +473,7 @@ int mpc_ctx_create(int device, mpc_ctx **out)
     CUDA_TRY(cudaSetDevice(device));
     mpc_ctx *c = new mpc_ctx();
     c->device = device;
+    CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     *out = c;
@@ -463,6 +498,7 @@ int mpc_ctx_destroy(mpc_ctx *c)
     cudaFree(c->d_status2);
     cudaFree(c->d_nodes);
     cudaFree(c->d_endtau);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     delete c;
     return MPC_SUCCESS;
 }
@@ -502,7 +538,7 @@ static int disc_host(mpc_ctx *ctx, const double *x, const double *u, const doubl
     if ((rc = ensure(ctx->d_out, ctx->cap_out, (size_t)n_int * MPC_OUT_ROWS))) return rc;
     if ((rc = ensure(ctx->d_status, ctx->cap_status, (size_t)n_int))) return rc;
     if (ad && n_nodes_host && (rc = ensure(ctx->d_nodes, ctx->cap_nodes, (size_t)n_int))) return rc;
-    const int cs = chunk_sats(n_sats, K);
+    const int cs = chunk_sats(ctx, n_sats, K);
     const int n_chunks = (n_sats + cs - 1) / cs;
     if ((rc = ensure_events(ctx, (size_t)n_chunks))) return rc;
     const mpc::DiscParams P = disc_params(p);
@@ -531,14 +567,19 @@ static int disc_host(mpc_ctx *ctx, const double *x, const double *u, const doubl
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev[c], 0));
         if ((rc = copy_out_chunk(out_host, ctx->d_out, n_int, off, (long long)ns * (K - 1), ctx->s_copy))) return rc;
     }
+    // The host writes the structural constants while the GPU / DMA engine work.  The int32 words go through
+    // pinned staging: a copy into a pageable caller buffer would block this thread until the whole pipeline drains.
+    fill_const_rows(out_host, n_int);
+    const bool want_nodes = ad && n_nodes_host;
+    if ((rc = ensure_stage(ctx, (size_t)n_int * 2))) return rc;
     if (status_host)
-        CUDA_TRY(cudaMemcpyAsync(status_host, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 ctx->s_copy));
-    if (ad && n_nodes_host)
-        CUDA_TRY(cudaMemcpyAsync(n_nodes_host, ctx->d_nodes, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 ctx->s_copy));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+    if (want_nodes)
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage + n_int, ctx->d_nodes, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_compute));
+    if (status_host) memcpy(status_host, ctx->h_stage, (size_t)n_int * sizeof(int32_t));
+    if (want_nodes) memcpy(n_nodes_host, ctx->h_stage + n_int, (size_t)n_int * sizeof(int32_t));
     return MPC_SUCCESS;
 }
 
@@ -634,7 +675,7 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
     if ((rc = ensure(ctx->d_out, ctx->cap_out, (size_t)n_int * MPC_OUT_ROWS))) return rc;
     if ((rc = ensure(ctx->d_status, ctx->cap_status, (size_t)n_int))) return rc;
     if ((rc = ensure(ctx->d_status2, ctx->cap_status2, (size_t)n_sats))) return rc;
-    const int cs = chunk_sats(n_sats, K);
+    const int cs = chunk_sats(ctx, n_sats, K);
     const int n_chunks = (n_sats + cs - 1) / cs;
     if ((rc = ensure_events(ctx, (size_t)n_chunks))) return rc;
     cudaStream_t st = ctx->s_compute;
@@ -647,6 +688,12 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
                           n_sub_prop, ctx->d_x, ctx->d_u,
                           ctx->d_status2, st)))
         return rc;
+    // the reference trajectory and inputs go back to the host while the first chunks are being discretized
+    if ((rc = ensure_events(ctx, (size_t)n_chunks + 1))) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev[n_chunks], st));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev[n_chunks], 0));
+    if (y_host) CUDA_TRY(cudaMemcpyAsync(y_host, ctx->d_x, (size_t)n_sats * 7 * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
+    if (u_host) CUDA_TRY(cudaMemcpyAsync(u_host, ctx->d_u, (size_t)n_sats * 3 * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
     const mpc::DiscParams P = disc_params(p_disc);
     for (int c = 0; c < n_chunks; ++c) {
         const int s0 = c * cs, ns = std::min(cs, n_sats - s0);
@@ -661,24 +708,76 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ctx->ev[c], st));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev[c], 0));
-        if (c == 0) {
-            if (y_host) CUDA_TRY(cudaMemcpyAsync(y_host, ctx->d_x, (size_t)n_sats * 7 * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
-            if (u_host) CUDA_TRY(cudaMemcpyAsync(u_host, ctx->d_u, (size_t)n_sats * 3 * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
-        }
         if ((rc = copy_out_chunk(out_host, ctx->d_out, n_int, off, (long long)ns * (K - 1), ctx->s_copy))) return rc;
     }
-    if (status_host)
-        CUDA_TRY(cudaMemcpyAsync(status_host, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+    fill_const_rows(out_host, n_int);   // host writes the structural constants while the GPU / DMA engine work
+    if (status_host) {   // int32 words through pinned staging (see disc_host)
+        if ((rc = ensure_stage(ctx, (size_t)n_int + n_sats))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage + n_int, ctx->d_status2, (size_t)n_sats * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+    }
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
     CUDA_TRY(cudaStreamSynchronize(st));
-    // a satellite whose propagation failed poisons its intervals: surface it in the interval status
     if (status_host) {
-        std::vector<int32_t> ps((size_t)n_sats);
-        CUDA_TRY(cudaMemcpy(ps.data(), ctx->d_status2, (size_t)n_sats * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        memcpy(status_host, ctx->h_stage, (size_t)n_int * sizeof(int32_t));
+        // a satellite whose propagation failed poisons its intervals: surface it in the interval status
+        const int32_t *ps = ctx->h_stage + n_int;
         for (int s = 0; s < n_sats; ++s)
-            if (ps[(size_t)s])
-                for (int k = 0; k < K - 1; ++k) status_host[(size_t)s * (K - 1) + k] = ps[(size_t)s];
+            if (ps[s])
+                for (int k = 0; k < K - 1; ++k) status_host[(size_t)s * (K - 1) + k] = ps[s];
     }
+    return MPC_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------- constraint terms
+static int cterms_check(const void *x, const void *u, int n_sats, int K, int Ku, const void *rbar, const void *ubar,
+                        const void *fin)
+{
+    if (!x || !u || !rbar || !ubar || !fin) return fail(MPC_E_INVALID, "null pointer argument");
+    if (n_sats < 0 || K < 2 || Ku < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, K >= 2, Ku >= 1 (got %d, %d, %d)", n_sats, K, Ku);
+    return MPC_SUCCESS;
+}
+
+static int cterms_launch(const double *x, const double *u, int n_sats, int K, int Ku, double mu, double *rbar,
+                         double *ubar, double *fin, cudaStream_t st)
+{
+    const long long n = (long long)n_sats * std::max(K, Ku);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    mpc::constraint_terms_kernel<<<grid, 256, 0, st>>>(x, u, n_sats, K, Ku, mu, 2.220446049250313e-16, rbar, ubar, fin);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
+int mpc_constraint_terms(const double *x, const double *u, int n_sats, int K, int u_cols, double mu, double *rbar_hat,
+                         double *ubar_hat, double *final_terms, void *stream)
+{
+    int rc = cterms_check(x, u, n_sats, K, u_cols, rbar_hat, ubar_hat, final_terms);
+    if (rc || n_sats == 0) return rc;
+    return cterms_launch(x, u, n_sats, K, u_cols, mu, rbar_hat, ubar_hat, final_terms, (cudaStream_t)stream);
+}
+
+int mpc_constraint_terms_host(mpc_ctx *ctx, const double *x, const double *u, int n_sats, int K, int u_cols, double mu,
+                              double *rbar_hat, double *ubar_hat, double *final_terms)
+{
+    if (!ctx) return fail(MPC_E_INVALID, "null ctx");
+    int rc = cterms_check(x, u, n_sats, K, u_cols, rbar_hat, ubar_hat, final_terms);
+    if (rc || n_sats == 0) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t nx = (size_t)n_sats * 7 * K, nu = (size_t)n_sats * 3 * u_cols, nr = (size_t)n_sats * 3 * (K - 1),
+                 nf = (size_t)n_sats * MPC_FINAL_TERMS;
+    if ((rc = ensure(ctx->d_x, ctx->cap_x, nx))) return rc;
+    if ((rc = ensure(ctx->d_u, ctx->cap_u, nu))) return rc;
+    if ((rc = ensure(ctx->d_out, ctx->cap_out, nr + nu + nf))) return rc;
+    cudaStream_t st = ctx->s_compute;
+    double *d_r = ctx->d_out, *d_ub = d_r + nr, *d_f = d_ub + nu;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_x, x, nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_u, u, nu * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = cterms_launch(ctx->d_x, ctx->d_u, n_sats, K, u_cols, mu, d_r, d_ub, d_f, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(rbar_hat, d_r, nr * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ubar_hat, d_ub, nu * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(final_terms, d_f, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return MPC_SUCCESS;
 }
 

@@ -298,6 +298,55 @@ def extract_uk(x, tau, u_func):
     return np.column_stack([u_func(x[:, i], tau[i]) for i in range(x.shape[1])])
 
 
+
+# ------------------------------------------------------------------ constraint terms (optimizer.py:80-170)
+
+def _skew(x):                                              # optimizer.py:41-45
+    return np.array([[0, -x[2], x[1]], [x[2], 0, -x[0]], [-x[1], x[0], 0]])
+
+
+def constraint_terms(x_bar, u_bar, MU):
+    """Optimizer.get_constraint_terms for ONE satellite (optimizer.py:106-169), restated statement by
+    statement -- including the precedence of `Dv_h_hat` (:121) and the inverted `ubar_hat` mask (:137-138).
+    x_bar (7,K), u_bar (3,Ku) -> dict with the reference's keys."""
+    I = np.eye(3)
+    r, v = x_bar[0:3, -1], x_bar[3:6, -1]
+    nr = np.linalg.norm(r)
+    rv = np.concatenate([r, v])
+    h = np.cross(r, v)
+    nh = np.linalg.norm(h)
+    r_hat, h_hat = r / nr, h / nh
+    t_hat = np.cross(h_hat, r_hat)
+    Dr_h = ((nh**-1 * I) - (nh**-3 * np.outer(h, h))) @ (-_skew(v))
+    Dv_h = (nh**-1 * I) - (nh**-3 * np.outer(h, h)) @ (_skew(r))
+    Dr_r = (nr**-1 * I) - (nr**-3 * np.outer(r, r))
+    Dr_t = (-_skew(r_hat) @ Dr_h) + (_skew(h_hat) @ Dr_r)
+    Dv_t = -_skew(r_hat) @ Dv_h
+    out = {}
+    rb = x_bar[0:3, :-1]
+    out["rbar_hat"] = rb / np.linalg.norm(rb, axis=0)
+    un = np.linalg.norm(u_bar, axis=0)
+    uh = np.zeros(u_bar.shape)
+    idx = un <= np.finfo(float).eps
+    with np.errstate(invalid="ignore", divide="ignore"):
+        uh[:, idx] = u_bar[:, idx] / un[idx]
+    out["ubar_hat"] = uh
+    out["rf_hat"] = r_hat
+    out["Vc"] = np.sqrt(MU / nr)
+    DrVc = (-1 / 2) * (MU**0.5) * (nr**(-5 / 2)) * r
+    out["DrVc"], out["DrVc_rbar"] = DrVc, np.dot(DrVc, r)
+    out["Vt"] = np.dot(v, t_hat)
+    g = np.concatenate([np.dot(v, Dr_t), t_hat + np.dot(v, Dv_t)])
+    out["DrVt_DvVt"], out["DrVt_DvVt_bar"] = g, np.dot(g, rv)
+    out["Vr"] = np.dot(v, r_hat)
+    g = np.concatenate([np.dot(v, Dr_r), r_hat])
+    out["DrVr_DvVr"], out["DrVr_DvVr_bar"] = g, np.dot(g, rv)
+    out["Vn"] = np.dot(v, h_hat)
+    g = np.concatenate([np.dot(v, Dr_h), h_hat + np.dot(v, Dv_h)])
+    out["DrVn_DvVn"], out["DrVn_DvVn_bar"] = g, np.dot(g, rv)
+    return out
+
+
 def rollout(A_k, B_kp, B_kn, Sigma_k, xi_k, x0, u, tf):
     """Discrete model rolled forward -- the implicit check the reference's tests make.
     ref: test_discretizer.py:110-113, optimizer.py:327-339."""

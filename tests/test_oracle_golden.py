@@ -1,8 +1,10 @@
 """CPU: pins oracle/ against fixtures produced by the unmodified reference (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import NAMES, rel_err
+from conftest import GOLDEN, NAMES, rel_err
 from oracle import c_oracle as C
 from oracle import mpc_oracle as O
 
@@ -187,3 +189,22 @@ def test_c_oracle_mass_failure_flag(const):
     y0 = np.array([[1.0, 0, 0, 0, 6.28, 0, 1e-3]])
     y, _, st = C.propagate_batch(y0, 5.0, const, C.CTRL_CONSTANT, (5.0, 0, 0), T=50, n_sub=20)
     assert st[0] == 1
+
+
+CT_KEYS = ['rbar_hat', 'ubar_hat', 'rf_hat', 'Vc', 'DrVc', 'DrVc_rbar', 'Vt', 'DrVt_DvVt', 'DrVt_DvVt_bar',
+           'Vr', 'DrVr_DvVr', 'DrVr_DvVr_bar', 'Vn', 'DrVn_DvVn', 'DrVn_DvVn_bar']
+
+
+@pytest.mark.parametrize("tag", ["c0", "c1", "c2"])
+def test_py_oracle_constraint_terms_vs_reference(tag):
+    """oracle.constraint_terms == Optimizer.get_constraint_terms of the unmodified reference (optimizer.py:80-170),
+    fixtures from tests/golden/make_golden.py; c2 has zero thrust (the reference's NaN ubar_hat)."""
+    g = np.load(os.path.join(GOLDEN, "constraint_terms.npz"))
+    out = O.constraint_terms(g[tag + "_x"], g[tag + "_u"], float(g["MU"]))
+    assert sorted(out) == sorted(CT_KEYS)
+    for k in CT_KEYS:
+        np.testing.assert_array_equal(np.asarray(out[k]), g[f"{tag}_{k}"], err_msg=k)
+    if tag == "c2":
+        assert np.isnan(out["ubar_hat"]).all()
+    else:
+        assert (out["ubar_hat"] == 0).all()
