@@ -4,6 +4,8 @@ All satellites of a run are propagated in ONE batched kernel launch instead of t
 loop over solve_ivp calls (simulator.py:41-45,58-62); signatures, return structures, segment
 bookkeeping and the mass-error behaviour follow the reference.
 """
+import os
+from datetime import datetime
 from types import SimpleNamespace
 
 import numpy as np
@@ -80,6 +82,21 @@ class Simulator:
         """ref: simulator.py:164-189.  Returns an object with .y (7,T) and .t (T,) like solve_ivp's."""
         y, u, t = self._propagate([sat], tf, spec_from(u_func))
         return SimpleNamespace(y=y[0], t=t, u=u[0], success=True, status=0, message="fixed-step RK4 on sm_100a")
+
+    def save_to_csv(self, suffix="", redimensionalize=True, directory="."):
+        """ref: simulator.py:192-201 -- one `trajectory_<date>_<sat.id><suffix>.csv` per satellite, rows = samples,
+        7 comma-separated columns (np.savetxt default '%.18e'), read by the reference's visualizer.m.
+        `directory` is an addition (the reference writes into the working directory); returns the paths."""
+        date = datetime.today().strftime('%Y-%m-%d-%H-%M-%S')
+        paths = []
+        for sat in self.sats:
+            data = self.sim_data[sat.id]
+            if redimensionalize:
+                data = self.scale.redim_state(data)
+            path = os.path.join(directory, f"trajectory_{date}_{sat.id}{suffix}.csv")
+            np.savetxt(path, np.asarray(data).T, delimiter=",")
+            paths.append(path)
+        return paths
 
     # -- reference statics kept as host callables ------------------------------------------------------
     @staticmethod

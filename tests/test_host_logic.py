@@ -163,3 +163,22 @@ def test_host_dynamics_matches_oracle(gold_prop, const):
     assert np.allclose(a, b, rtol=1e-14, atol=1e-18)
     with pytest.raises(Exception, match="INVALID SATELLITE MASS"):
         M.Simulator.satellite_dynamics(0.0, np.array([1, 0, 0, 0, 1, 0, -1.0]), uf, 1.0, const)
+
+
+def test_save_to_csv_wire_format(tmp_path, gold_prop):
+    """simulator.py:192-201: trajectory_<date>_<id><suffix>.csv, one row per sample, 7 columns, redimensionalized;
+    the file np.loadtxt / MATLAB csvread (visualizer.m) read back is the trajectory to the last bit"""
+    sat = M.Satellite(np.array([7e6, 0, 0]), np.array([0, 7.5e3, 0]), 1000.0)
+    scale = M.SatelliteScale(sat=sat)
+    sim = M.Simulator(sats=[sat], scale=scale)
+    traj = np.asarray(gold_prop["p1_y"], dtype=float)          # a (7,T) trajectory from the unmodified reference
+    sim.sim_data = {sat.id: traj}
+    for redim in (True, False):
+        (path,) = sim.save_to_csv(suffix="_t", redimensionalize=redim, directory=str(tmp_path))
+        name = os.path.basename(path)
+        assert re.fullmatch(r"trajectory_\d{4}-\d\d-\d\d-\d\d-\d\d-\d\d_%s_t\.csv" % sat.id, name)
+        lines = open(path).read().splitlines()
+        assert len(lines) == traj.shape[1] and all(len(ln.split(",")) == 7 for ln in lines)
+        back = np.loadtxt(path, delimiter=",")
+        want = scale.redim_state(traj).T if redim else traj.T
+        assert np.array_equal(back, want)
