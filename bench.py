@@ -233,7 +233,7 @@ def gpu_arm(args):
         gather_mode = args.gather
         if gather_mode == "fused":
             try:
-                fused = D.FusedGather(N * world, K, device=dev, mode=args.fused_mode)
+                fused = D.FusedGather(N * world, K, device=dev, mode=args.fused_mode, chunk_waves=args.chunk_waves)
             except Exception as exc:            # no peer mapping on this box: fall back to the NCCL baseline
                 if rank == 0:
                     print(f"[bench] symmetric memory unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
@@ -421,7 +421,8 @@ def main():
     ap.add_argument("--tf", type=float, default=2.0)
     ap.add_argument("--n-sub", dest="n_sub", type=int, default=100, help="RK4 steps per interval (integrator_steps-1)")
     ap.add_argument("--chunks", type=int, default=8, help="compute/all-gather overlap chunks (N>1, --gather nccl)")
-    ap.add_argument("--fused-mode", dest="fused_mode", default="unicast", choices=["unicast", "multicast"])
+    ap.add_argument("--fused-mode", dest="fused_mode", default="unicast", choices=["unicast", "multicast", "push"])
+    ap.add_argument("--chunk-waves", dest="chunk_waves", type=int, default=1, help="--fused-mode push: kernel waves per pushed chunk")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: all-gather by peer stores from inside the kernel (fused) or chunked NCCL all-gather")
     ap.add_argument("--ref-sats", dest="ref_sats", type=int, default=2, help="satellites per step of the reference arm")

@@ -208,6 +208,21 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
                                   int n_sub_prop, int n_sub_disc, double *y_host, double *u_host,
                                   double *out_host, int32_t *status_host);
 
+/*
+ * All-gather of the discretized matrices by the COPY ENGINES, overlapped with the kernel: the batch is discretized
+ * in chunks of `chunk_waves` full waves of the kernel into dst[0] (local); as soon as a chunk is done its columns
+ * are pushed to dst[1..n_dst-1] (peer-mapped buffers of the other ranks, same layout) by cudaMemcpy2DAsync on one
+ * stream per peer -- NVLink carries chunk c while the SMs compute chunk c+1, no SM time and no store-queue stalls
+ * are spent on the exchange.  When the call returns, everything is enqueued and `stream` waits for the pushes.
+ * Rows 42..48 (structural constants, see mpc_discretize_batch_host) are NOT pushed: every destination buffer must
+ * have been initialised once with mpc_fill_const_rows.  x, u, tf, dst[] device pointers; ctx owns the push streams.
+ */
+int mpc_discretize_batch_push(mpc_ctx *ctx, const double *x, const double *u, const double *tf, const mpc_params *p,
+                              int n_sats, int K, int n_sub, double *const *dst, int n_dst, int64_t out_pitch,
+                              int64_t out_offset, int32_t *status, int chunk_waves, void *stream);
+/* Writes the structural constants (rows 42..47 = 0, row 48 = 1) into all out_pitch columns of a SoA buffer. */
+int mpc_fill_const_rows(double *out, int64_t out_pitch, void *stream);
+
 /* ---------------------------------------------------------------- constraint terms (next step of the path) */
 
 /*
@@ -252,6 +267,14 @@ int64_t mpc_launch_count(void);
 /* Experiment knob: selects an alternative block-size / register-cap build of the discretization kernel
  * (0 = production).  Results are identical; only occupancy differs.  See DESIGN.md, tuning table. */
 int mpc_set_tuning(int variant);
+
+/* Options of the fused (in-kernel store) all-gather, applied by mpc_discretize_batch / _multi:
+ *   skip_const 1: rows 42..48 (structural constants) are stored to dst[0] only, 2: to no destination -- the other
+ *                 buffers must have been initialised with mpc_fill_const_rows (6.7 % less NVLink traffic);
+ *   stagger_phases > 1: the CTAs of the first wave start with a delay of (blockIdx % phases)/phases of one interval's
+ *                 run time, which spreads the store phases of the CTAs over time (NVLink egress stays busy instead
+ *                 of alternating between bursts and silence).  Results are unchanged.  0, 0 = off (default). */
+int mpc_set_gather_tuning(int skip_const, int stagger_phases);
 
 #ifdef __cplusplus
 }

@@ -109,9 +109,13 @@ def lib():
     L.mpc_discretize_batch_host.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, _DP, _DP]
     L.mpc_propagate_batch_host.argtypes = [vp, _DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP]
     L.mpc_propagate_discretize_host.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, _DP]
+    L.mpc_discretize_batch_push.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, ctypes.POINTER(ctypes.c_void_p), i, i64, i64, _DP, i, vp]
+    L.mpc_fill_const_rows.argtypes = [_DP, i64, vp]
     L.mpc_constraint_terms.argtypes = [_DP, _DP, i, i, i, d, _DP, _DP, _DP, vp]
     L.mpc_constraint_terms_host.argtypes = [vp, _DP, _DP, i, i, i, d, _DP, _DP, _DP]
     L.mpc_fp64_peak_probe.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    L.mpc_set_gather_tuning.argtypes = [i, i]
+    L.mpc_set_gather_tuning.restype = i
     L.mpc_set_tuning.argtypes = [i]
     L.mpc_set_tuning.restype = i
     for name in ("mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
@@ -119,7 +123,7 @@ def lib():
                  "mpc_discretize_batch_ugrid", "mpc_discretize_batch_ugrid_host",
                  "mpc_ctx_create", "mpc_ctx_destroy", "mpc_discretize_batch_host", "mpc_propagate_batch_host",
                  "mpc_propagate_discretize_host", "mpc_fp64_peak_probe", "mpc_constraint_terms",
-                 "mpc_constraint_terms_host"):
+                 "mpc_constraint_terms_host", "mpc_discretize_batch_push", "mpc_fill_const_rows"):
         getattr(L, name).restype = i
     _lib = L
     return L
@@ -130,8 +134,8 @@ EXPORTED_SYMBOLS = [
     "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_discretize_batch_ugrid", "mpc_propagate_batch",
     "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
     "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_discretize_batch_ugrid_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host",
-    "mpc_constraint_terms", "mpc_constraint_terms_host",
-    "mpc_fp64_peak_probe", "mpc_set_tuning",
+    "mpc_constraint_terms", "mpc_constraint_terms_host", "mpc_discretize_batch_push", "mpc_fill_const_rows",
+    "mpc_fp64_peak_probe", "mpc_set_tuning", "mpc_set_gather_tuning",
 ]
 
 

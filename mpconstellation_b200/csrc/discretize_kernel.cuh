@@ -238,6 +238,11 @@ constexpr int kMaxDst = 8;
 
 struct DstTab {  // destination buffers of the (optionally multi-destination) SoA store
     double *p[kMaxDst];
+    // fused all-gather options (all zero for a plain launch):
+    int skip_const;            // 1: rows 42..48 (structural constants) go to p[0] only; 2: to no destination
+    int stagger_phases;        // > 1: CTAs of the first wave start with a delay of (blockIdx % phases)/phases of one
+    int first_wave_ctas;       //      interval's run time, so that the store phases of the CTAs sharing the NVLink
+    long long stagger_cycles;  //      egress do not coincide; stagger_cycles = run time of one interval in SM clocks
 };
 
 // Quadrature-node accumulation shared by the fixed-step and the adaptive kernel:
@@ -405,8 +410,13 @@ __device__ __forceinline__ int epilogue_store(volatile double *acc, const double
             store(a * 7 + c, pr[c][a]);
             store((a + 3) * 7 + c, pv[c][a]);
         }
+    if (dst.skip_const == 0) {
 #pragma unroll
-    for (int c = 0; c < 7; ++c) store(42 + c, (c == 6) ? 1.0 : 0.0);
+        for (int c = 0; c < 7; ++c) store(42 + c, (c == 6) ? 1.0 : 0.0);
+    } else if (dst.skip_const == 1) {   // remote buffers were initialised once with the constants
+#pragma unroll
+        for (int c = 0; c < 7; ++c) dsts[0][(long long)(42 + c) * pitch + col] = (c == 6) ? 1.0 : 0.0;
+    }
     // Bp = sB*I1, Bn = sB*(I0 - I1), Sigma = sS*IS, xi = sB*IX
     // result row a: sum_c Phi[a][c] I[c][.],  Phi[a][c] = pr[c][a] (a<3) / pv[c][a-3] (a<6); row 6 = I[6][.]
 #pragma unroll
@@ -461,6 +471,11 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     const long long n_int = (long long)n_sats * (K - 1);
     const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (gid >= n_int) return;
+    if (dst.stagger_phases > 1 && (int)blockIdx.x < dst.first_wave_ctas) {
+        const long long wait = dst.stagger_cycles * (long long)(blockIdx.x % dst.stagger_phases) / dst.stagger_phases;
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) __nanosleep(2000);
+    }
     // volatile: keep the accumulators IN shared memory (the compiler would otherwise promote these
     // thread-private slots to registers and spill them to local memory, which is write-through to L2)
     volatile double *acc = acc_smem + threadIdx.x;

@@ -64,6 +64,7 @@ mpc::PropParams prop_params(const mpc_params *p)
 }
 
 std::atomic<int> g_tuning{0};
+std::atomic<int> g_gather_skip_const{0}, g_gather_stagger{0};   // mpc_set_gather_tuning
 thread_local int g_ucols = 0;  // columns of u when it lives on its own grid (set by the *_ugrid entry points)
 struct UcolsScope {            // routes the launchers to the general-grid input hold for the duration of one call
     explicit UcolsScope(int n) { g_ucols = n; }
@@ -208,8 +209,17 @@ int disc_device(const double *x, const double *u, const double *tf, const mpc_pa
     const long long n_int = (long long)n_sats * (K - 1);
     if (pitch < offset + n_int || offset < 0) return fail(MPC_E_INVALID, "out_pitch/out_offset do not hold the batch");
     if (n_int == 0) return MPC_SUCCESS;
-    mpc::DstTab tab;
+    mpc::DstTab tab{};
     for (int d = 0; d < mpc::kMaxDst; ++d) tab.p[d] = (d < n_dst) ? dst[d] : nullptr;
+    tab.skip_const = g_gather_skip_const.load(std::memory_order_relaxed);
+    tab.stagger_phases = g_gather_stagger.load(std::memory_order_relaxed);
+    if (tab.stagger_phases > 1) {
+        int dev = 0, sms = 148;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        tab.first_wave_ctas = sms * 2;                           // 2 CTAs of 128 threads per SM (launch_disc_n)
+        tab.stagger_cycles = (long long)n_sub * 4940LL;          // ~2470 clocks per RK4 step and warp, 2 warps per scheduler
+    }
     for (int d = 0; d < n_dst; ++d)
         if (!tab.p[d]) return fail(MPC_E_INVALID, "null destination %d", d);
     const mpc::DiscParams P = disc_params(p);
@@ -288,6 +298,9 @@ struct mpc_ctx {
     double *d_x = nullptr, *d_u = nullptr, *d_tf = nullptr, *d_out = nullptr, *d_y0 = nullptr, *d_tab = nullptr;
     int32_t *d_status = nullptr, *d_status2 = nullptr, *d_nodes = nullptr;
     double *d_endtau = nullptr;
+    cudaStream_t s_aux[3] = {};              // compute streams the chunk kernels of the push gather rotate over
+    cudaStream_t s_push[MPC_MAX_DST] = {};   // one stream per peer for the copy-engine gather (mpc_discretize_batch_push)
+    std::vector<cudaEvent_t> ev_push;       // [chunk] kernel-done events + [MPC_MAX_DST] stream-join events
     int32_t *h_stage = nullptr;  // pinned staging for the int32 status / node-count words (caller buffers may be pageable)
     size_t cap_stage = 0;
     size_t cap_nodes = 0, cap_endtau = 0;
@@ -401,6 +414,15 @@ int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc
 
 int64_t mpc_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int mpc_set_gather_tuning(int skip_const, int stagger_phases)
+{
+    if (skip_const < 0 || skip_const > 2 || stagger_phases < 0 || stagger_phases > 64)
+        return fail(MPC_E_INVALID, "bad gather tuning (%d, %d)", skip_const, stagger_phases);
+    g_gather_skip_const.store(skip_const);
+    g_gather_stagger.store(stagger_phases);
+    return MPC_SUCCESS;
+}
+
 int mpc_set_tuning(int variant)
 {
     if (variant < 0 || variant > 6) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);
@@ -488,6 +510,11 @@ int mpc_ctx_destroy(mpc_ctx *c)
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    for (cudaStream_t ps : c->s_push)
+        if (ps) cudaStreamDestroy(ps);
+    for (cudaStream_t ps : c->s_aux)
+        if (ps) cudaStreamDestroy(ps);
+    for (cudaEvent_t e : c->ev_push) cudaEventDestroy(e);
     cudaFree(c->d_x);
     cudaFree(c->d_u);
     cudaFree(c->d_tf);
@@ -725,6 +752,89 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
         for (int s = 0; s < n_sats; ++s)
             if (ps[s])
                 for (int k = 0; k < K - 1; ++k) status_host[(size_t)s * (K - 1) + k] = ps[s];
+    }
+    return MPC_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------- copy-engine gather
+int mpc_fill_const_rows(double *out, int64_t out_pitch, void *stream)
+{
+    if (!out || out_pitch < 0) return fail(MPC_E_INVALID, "bad argument");
+    if (out_pitch == 0) return MPC_SUCCESS;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(out + (size_t)kConstRow0 * out_pitch, 0, (size_t)6 * out_pitch * sizeof(double), st));
+    const unsigned grid = (unsigned)std::min<long long>((out_pitch + 255) / 256, 148LL * 8);
+    mpc::fill_kernel<<<grid, 256, 0, st>>>(out + (size_t)(kConstRow1 - 1) * out_pitch, (long long)out_pitch, 1.0);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
+int mpc_discretize_batch_push(mpc_ctx *ctx, const double *x, const double *u, const double *tf, const mpc_params *p,
+                              int n_sats, int K, int n_sub, double *const *dst, int n_dst, int64_t out_pitch,
+                              int64_t out_offset, int32_t *status, int chunk_waves, void *stream)
+{
+    if (!ctx) return fail(MPC_E_INVALID, "null ctx");
+    int rc = check_disc_args(x, u, tf, p, n_sats, K, n_sub);
+    if (rc) return rc;
+    if (!dst || n_dst < 1 || n_dst > MPC_MAX_DST) return fail(MPC_E_INVALID, "bad destination list");
+    for (int d = 0; d < n_dst; ++d)
+        if (!dst[d]) return fail(MPC_E_INVALID, "null destination %d", d);
+    const long long n_int = (long long)n_sats * (K - 1);
+    if (out_pitch < out_offset + n_int || out_offset < 0) return fail(MPC_E_INVALID, "out_pitch/out_offset do not hold the batch");
+    if (n_int == 0) return MPC_SUCCESS;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int d = 1; d < n_dst; ++d)
+        if (!ctx->s_push[d]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_push[d], cudaStreamNonBlocking));
+    const int cs = (int)std::min<long long>((long long)chunk_sats(ctx, n_sats, K) * std::max(chunk_waves, 1), n_sats);
+    const int n_chunks = (n_sats + cs - 1) / cs;
+    for (cudaStream_t &a : ctx->s_aux)
+        if (!a) CUDA_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    while (ctx->ev_push.size() < (size_t)n_chunks + MPC_MAX_DST + 4) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_push.push_back(e);
+    }
+    const mpc::DiscParams P = disc_params(p);
+    mpc::DstTab tab{};
+    tab.p[0] = dst[0];
+    const size_t pitch_b = (size_t)out_pitch * sizeof(double);
+    // The chunk kernels are independent: they rotate over three compute streams forked from the caller's stream,
+    // so the CTAs of chunk c+1 fill the SMs while the last CTAs of chunk c drain (no bubble between chunks).
+    const size_t ev_fork = (size_t)n_chunks + MPC_MAX_DST;
+    CUDA_TRY(cudaEventRecord(ctx->ev_push[ev_fork], st));
+    for (cudaStream_t a : ctx->s_aux) CUDA_TRY(cudaStreamWaitEvent(a, ctx->ev_push[ev_fork], 0));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s0 = c * cs, ns = std::min(cs, n_sats - s0);
+        const long long off = out_offset + (long long)s0 * (K - 1), nc = (long long)ns * (K - 1);
+        const double *dx = x + (size_t)s0 * 7 * K, *du = u + (size_t)s0 * 3 * K;
+        int32_t *stc = status ? status + (size_t)s0 * (K - 1) : nullptr;
+        cudaStream_t sk = ctx->s_aux[c % 3];
+        rc = p->include_j2 ? launch_disc_n<true, 1>(dx, du, tf + s0, P, ns, K, n_sub, tab, out_pitch, off, stc, sk)
+                           : launch_disc_n<false, 1>(dx, du, tf + s0, P, ns, K, n_sub, tab, out_pitch, off, stc, sk);
+        if (rc) return rc;
+        if (n_dst == 1) continue;
+        CUDA_TRY(cudaEventRecord(ctx->ev_push[c], sk));
+        // peers in rotated order per chunk so that the copy engines do not all target the same GPU at once
+        for (int i = 1; i < n_dst; ++i) {
+            const int d = 1 + (i - 1 + c) % (n_dst - 1);
+            cudaStream_t ps = ctx->s_push[d];
+            CUDA_TRY(cudaStreamWaitEvent(ps, ctx->ev_push[c], 0));
+            CUDA_TRY(cudaMemcpy2DAsync(dst[d] + off, pitch_b, dst[0] + off, pitch_b, (size_t)nc * sizeof(double), kConstRow0,
+                                       cudaMemcpyDeviceToDevice, ps));
+            CUDA_TRY(cudaMemcpy2DAsync(dst[d] + (size_t)kConstRow1 * out_pitch + off, pitch_b,
+                                       dst[0] + (size_t)kConstRow1 * out_pitch + off, pitch_b, (size_t)nc * sizeof(double),
+                                       MPC_OUT_ROWS - kConstRow1, cudaMemcpyDeviceToDevice, ps));
+        }
+    }
+    for (int d = 1; d < n_dst; ++d) {   // the caller's stream continues only when every push has landed
+        CUDA_TRY(cudaEventRecord(ctx->ev_push[(size_t)n_chunks + d], ctx->s_push[d]));
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_push[(size_t)n_chunks + d], 0));
+    }
+    for (int a = 0; a < 3; ++a) {       // ... and every chunk kernel has finished
+        CUDA_TRY(cudaEventRecord(ctx->ev_push[ev_fork + 1 + a], ctx->s_aux[a]));
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_push[ev_fork + 1 + a], 0));
     }
     return MPC_SUCCESS;
 }

@@ -212,4 +212,9 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters,
     out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+__global__ void fill_kernel(double *__restrict__ p, long long n, double v)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
 }  // namespace mpc

@@ -80,10 +80,16 @@ def _dst_count(world):
 class FusedGather:
     """All-gather of the discretized matrices by peer stores from inside the discretization kernel."""
 
-    def __init__(self, n_sats_total, K, group=None, device=None, mode="unicast"):
+    def __init__(self, n_sats_total, K, group=None, device=None, mode="unicast", chunk_waves=1, skip_const=True,
+                 stagger=None):
         """mode "unicast": one peer-mapped store per destination rank (works on any P2P-capable box);
         mode "multicast": one store to the NVSwitch multicast address of the symmetric buffer, replicated by the
-        switch to every rank (NVLS) -- 1/world of the SM store instructions and of the egress traffic."""
+        switch to every rank (NVLS) -- 1/world of the SM store instructions and of the egress traffic;
+        mode "push": the kernel stores locally, chunk by chunk, and the copy engines push every finished chunk to
+        the peers' buffers over NVLink while the next chunk is computed (`mpc_discretize_batch_push`): no SM time
+        and no store-queue stalls go into the exchange, and the structurally constant rows are not sent.
+        skip_const: rows 42..48 (the last row of A_k, constants 0..0 1) are written once into every buffer here and
+        never sent again (6.7 % less NVLink traffic).  stagger: see mpc_set_gather_tuning."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -106,6 +112,18 @@ class FusedGather:
         self.mc_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
         if mode == "multicast" and not self.mc_ptr:
             raise RuntimeError("this box / torch build exposes no multicast (NVLS) mapping for symmetric memory")
+        self.chunk_waves = int(chunk_waves)
+        self.skip_const = bool(skip_const) or mode == "push"
+        # measured on 8xB200 (profiles/r01_e_multi_gpu.txt): 4 phases help once the step is NVLink-ingress bound
+        self.stagger = int(stagger) if stagger is not None else (4 if self.world >= 8 and mode == "unicast" else 0)
+        if self.skip_const:
+            # rows 42..48 of every buffer are constants that are never sent: written once, here, by the owner
+            _lib.check(_lib.lib().mpc_fill_const_rows(self.buf.data_ptr(), self.pitch,
+                                                      torch.cuda.current_stream(self.device).cuda_stream))
+            torch.cuda.synchronize(self.device)
+            self.handle.barrier()
+        if mode == "push":
+            self.peers = [ptrs[self.rank]] + [ptrs[r] for r in order[1:]]
         self.s0, self.s1 = shard_range(n_sats_total, self.rank, self.world)
         self.status = torch.zeros(max(1, (self.s1 - self.s0) * (K - 1)), dtype=torch.int32, device=self.device)
 
@@ -115,6 +133,21 @@ class FusedGather:
         rank's `self.buf` holds all N satellites."""
         from . import batch
         assert x.shape[0] == self.s1 - self.s0 and x.shape[2] == self.K
+        tuned = self.mode != "push" and (self.skip_const or self.stagger > 1)
+        if tuned:
+            _lib.check(_lib.lib().mpc_set_gather_tuning((2 if self.mode == "multicast" else 1) if self.skip_const else 0,
+                                                        self.stagger))
+        try:
+            self._launch(x, u, tf, const, include_J2, n_sub)
+        finally:
+            if tuned:
+                _lib.check(_lib.lib().mpc_set_gather_tuning(0, 0))
+        if barrier:
+            self.handle.barrier()
+        return self.buf
+
+    def _launch(self, x, u, tf, const, include_J2, n_sub):
+        from . import batch
         if x.shape[0] > 0 and self.mode == "multicast":
             import ctypes
             import torch
@@ -123,13 +156,20 @@ class FusedGather:
             _lib.check(_lib.lib().mpc_discretize_batch(x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p),
                                                        x.shape[0], self.K, int(n_sub), self.mc_ptr, self.pitch,
                                                        self.s0 * (self.K - 1), self.status.data_ptr(), stream))
+        elif x.shape[0] > 0 and self.mode == "push":
+            import ctypes
+            import torch
+            p = _lib.make_params(const, include_J2, False)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            arr = (ctypes.c_void_p * len(self.peers))(*self.peers)
+            _lib.check(_lib.lib().mpc_discretize_batch_push(
+                batch._ctx(self.device.index or 0), x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p), x.shape[0],
+                self.K, int(n_sub), arr, len(self.peers), self.pitch, self.s0 * (self.K - 1), self.status.data_ptr(),
+                self.chunk_waves, stream))
         elif x.shape[0] > 0:
             batch.discretize_batch_device(x, u, tf, const, include_J2=include_J2, n_sub=n_sub, out=self.buf,
                                           out_pitch=self.pitch, out_offset=self.s0 * (self.K - 1),
                                           status=self.status, extra_dst=self.dst[1:])
-        if barrier:
-            self.handle.barrier()
-        return self.buf
 
     def view(self):
         return GatheredView(self.buf, self.n_sats, self.K, self.world, layout="global")

@@ -36,9 +36,21 @@ full, _ = M.discretize_batch_device(y_all, u_all, tfd_all, const)
 torch.cuda.synchronize()
 t_local = timed(lambda: M.discretize_batch_device(x, u, tfd, const))
 
-fg = D.FusedGather(N * world, K, device=dev)
+fg = D.FusedGather(N * world, K, device=dev, skip_const=False)
 fg.buf.zero_(); torch.cuda.synchronize(); dist.barrier()
 t_fused = timed(lambda: fg.discretize(x, u, tfd, const))
+variants = {}
+ok_var = 1
+for mode in ("unicast", "multicast"):
+    for stag in (0, 4, 8, 16):
+        try:
+            fv = D.FusedGather(N * world, K, device=dev, mode=mode, skip_const=True, stagger=stag)
+        except Exception:
+            continue
+        fv.buf[:42].zero_(); fv.buf[49:].zero_(); torch.cuda.synchronize(); dist.barrier()
+        variants[f"{mode}+skip_const+stagger{stag}"] = timed(lambda: fv.discretize(x, u, tfd, const))
+        ok_var &= int(torch.equal(fv.buf, full))
+        del fv
 ok_fused = torch.equal(fg.buf, full)
 v = fg.view()
 A = v.sat(N * world - 1)[0]
@@ -46,12 +58,19 @@ ok_view = np.array_equal(A, full[:49, -(K - 1):].T.reshape(K - 1, 7, 7).cpu().nu
 
 t_mc, ok_mc = float("nan"), 1
 try:
-    fm = D.FusedGather(N * world, K, device=dev, mode="multicast")
+    fm = D.FusedGather(N * world, K, device=dev, mode="multicast", skip_const=False)
     fm.buf.zero_(); torch.cuda.synchronize(); dist.barrier()
     t_mc = timed(lambda: fm.discretize(x, u, tfd, const))
     ok_mc = int(torch.equal(fm.buf, full))
 except Exception as exc:
     if rank == 0: print("multicast unavailable:", exc)
+t_push, ok_push = {}, 1
+for cw in (1, 2):
+    fp = D.FusedGather(N * world, K, device=dev, mode="push", chunk_waves=cw)
+    fp.buf[:42].zero_(); fp.buf[49:].zero_(); torch.cuda.synchronize(); dist.barrier()
+    t_push[cw] = timed(lambda: fp.discretize(x, u, tfd, const))
+    ok_push &= int(torch.equal(fp.buf, full))
+    del fp
 loc = torch.empty((105, n_int), dtype=torch.float64, device=dev)
 def nccl_step():
     def produce(c0, c1):
@@ -67,10 +86,13 @@ def nccl_plain():
     nccl_plain.res = torch.empty((world * 105, n_int), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(nccl_plain.res, loc)
 t_plain = timed(nccl_plain)
-res = torch.tensor([int(ok_fused), int(ok_view), int(ok_nccl), int(ok_mc)], device=dev); dist.all_reduce(res, op=dist.ReduceOp.MIN)
+res = torch.tensor([int(ok_fused), int(ok_view), int(ok_nccl), int(ok_mc), int(ok_push), int(ok_var)], device=dev); dist.all_reduce(res, op=dist.ReduceOp.MIN)
 if rank == 0:
     gb = (world - 1) * n_int * 840 / 1e9
     print(f"world {world}  N/rank {N}  K {K}: local-only {t_local:.3f} ms | fused peer-store gather {t_fused:.3f} ms | fused multicast-store gather {t_mc:.3f} ms | "
+          f"copy-engine push (1 / 2 waves per chunk) {t_push[1]:.3f} / {t_push[2]:.3f} ms | "
           f"NCCL chunked-overlap {t_nccl:.3f} ms | kernel then NCCL all-gather {t_plain:.3f} ms | "
-          f"{gb:.2f} GB received per rank | verified fused/view/nccl/multicast = {res.tolist()}")
+          f"{gb:.2f} GB received per rank | verified fused/view/nccl/multicast/push/variants = {res.tolist()}")
+    for k_, v_ in variants.items():
+        print(f"   {k_}: {v_:.3f} ms")
 dist.destroy_process_group()

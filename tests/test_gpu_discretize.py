@@ -242,3 +242,43 @@ def test_full_size_config3_properties(M, const):
     ref = C.discretize_batch(np.ascontiguousarray(x[sats]), np.ascontiguousarray(u[sats]), 2.0, const)
     for n, o, r in zip(NAMES, (A[sats], Bp[sats], Bn[sats], S[sats], X[sats]), ref[:5]):
         assert rel_err(o, r) < TOL_ORACLE, n
+
+
+def test_copy_engine_push_gather_on_one_gpu(M, const):
+    """mpc_discretize_batch_push with local buffers standing in for the peers: several chunks (the batch spans
+    three waves of the kernel), column offset inside a wider gathered buffer, constant rows pre-filled by
+    mpc_fill_const_rows and never pushed; every destination ends up bit-identical to a plain launch"""
+    import ctypes
+    import torch
+    from mpconstellation_b200 import _lib, batch
+    dev = torch.device("cuda:0")
+    sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    K = 40
+    N = (3 * sm * 9 * 32) // (K - 1) - 5                 # just under three one-wave chunks
+    y0, _, _ = synth_batch(N, 2, 1.0, const)
+    tfv = torch.full((N,), 1.0, dtype=torch.float64, device=dev)
+    x, u, _ = M.propagate_batch_device(torch.from_numpy(y0).to(dev), tfv, M.ConstantTangentialThrustController(tangential_thrust=0.5),
+                                       const, include_drag=False, include_J2=False, T=K)
+    ref, st = M.discretize_batch_device(x, u, tfv, const, n_sub=20)
+    n, pad = N * (K - 1), 77
+    bufs = [torch.full((105, n + 2 * pad), float("nan"), dtype=torch.float64, device=dev) for _ in range(3)]
+    L = _lib.lib()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for b in bufs:
+        _lib.check(L.mpc_fill_const_rows(b.data_ptr(), b.shape[1], stream))
+    status = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    p = _lib.make_params(const, False, False)
+    arr = (ctypes.c_void_p * 3)(*[b.data_ptr() for b in bufs])
+    for waves in (1, 2):
+        _lib.check(L.mpc_discretize_batch_push(batch._ctx(0), x.data_ptr(), u.data_ptr(), tfv.data_ptr(), ctypes.byref(p),
+                                               N, K, 20, arr, 3, n + 2 * pad, pad, status.data_ptr(), waves, stream))
+        torch.cuda.synchronize()
+        assert int(status.max()) == 0 and int(status.min()) == 0
+        for b in bufs:
+            assert torch.equal(b[:, pad:pad + n], ref)
+            for edge in (b[:42, :pad], b[49:, :pad], b[:42, pad + n:], b[49:, pad + n:]):
+                assert bool(torch.isnan(edge).all())      # nothing written outside the batch's columns
+            assert bool((b[42:48] == 0).all()) and bool((b[48] == 1).all())
+        for b in bufs[1:]:
+            b[:42].fill_(float("nan"))
+            b[49:].fill_(float("nan"))
