@@ -350,7 +350,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
 
     double pr[7][3], pv[7][3];
     ad_load_phi<BLOCK>(sm, cur, pr, pv);
-    const int nonfinite = epilogue_store<BLOCK, NDST>(sm, pr, pv, tf, 1.0, dst, pitch, offset + gid);
+    const int nonfinite = epilogue_store<BLOCK, NDST>(sm, pr, pv, tf, 1.0, tf, dst, pitch, offset + gid);
     if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : (fail ? 3 : 0));
     if (n_nodes) n_nodes[gid] = nodes;
 }

@@ -133,39 +133,41 @@ __device__ __forceinline__ void sym_mul_add(const Sym3 &g, double px, double py,
     oz = fma(g.zz, pz, fma(g.yz, py, fma(g.xz, px, cz)));
 }
 
-// One column of Phi through one RK4 step (Nystrom form of the classical stages).
+// One column of Phi through one RK4 step (Nystrom form of the classical stages), in the STEP-NORMALISED
+// variables of discretize_kernel: velocities scaled by the step hs, G and d scaled by hs^2, so the step is 1 and
+// every Runge-Kutta coefficient is a literal (an immediate / constant-bank operand instead of a third register
+// operand: a DFMA with three distinct register sources issues every 3 cycles on sm_100a, with two every 2).
 // MASSCOL: column 6, whose forcing is d_j = -u/m^2 at each stage (Phi[6][6] == 1).
 template <bool MASSCOL>
 __device__ __forceinline__ void column_step(double (&pr)[3], double (&pv)[3], const StageLin &s1,
-                                            const StageLin &s2, const StageLin &s3, const StageLin &s4,
-                                            double hs, double hh, double hh2, double hshh, double hs2_6,
-                                            double hs_6)
+                                            const StageLin &s2, const StageLin &s3, const StageLin &s4)
 {
+    constexpr double c6 = 1.0 / 6.0;
     double k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
     if (MASSCOL) sym_mul_add(s1.g, pr[0], pr[1], pr[2], s1.dx, s1.dy, s1.dz, k1x, k1y, k1z);
     else sym_mul(s1.g, pr[0], pr[1], pr[2], k1x, k1y, k1z);
-    // stage 2 position: p + h/2 p_v
-    const double q2x = fma(hh, pv[0], pr[0]), q2y = fma(hh, pv[1], pr[1]), q2z = fma(hh, pv[2], pr[2]);
+    // stage 2 position: p + 1/2 p_v
+    const double q2x = fma(0.5, pv[0], pr[0]), q2y = fma(0.5, pv[1], pr[1]), q2z = fma(0.5, pv[2], pr[2]);
     if (MASSCOL) sym_mul_add(s2.g, q2x, q2y, q2z, s2.dx, s2.dy, s2.dz, k2x, k2y, k2z);
     else sym_mul(s2.g, q2x, q2y, q2z, k2x, k2y, k2z);
-    // stage 3 position: p + h/2 (p_v + h/2 k1) = q2 + h^2/4 k1
-    const double q3x = fma(hh2, k1x, q2x), q3y = fma(hh2, k1y, q2y), q3z = fma(hh2, k1z, q2z);
+    // stage 3 position: p + 1/2 (p_v + 1/2 k1) = q2 + 1/4 k1
+    const double q3x = fma(0.25, k1x, q2x), q3y = fma(0.25, k1y, q2y), q3z = fma(0.25, k1z, q2z);
     if (MASSCOL) sym_mul_add(s3.g, q3x, q3y, q3z, s3.dx, s3.dy, s3.dz, k3x, k3y, k3z);
     else sym_mul(s3.g, q3x, q3y, q3z, k3x, k3y, k3z);
-    // stage 4 position: p + h (p_v + h/2 k2)
-    const double bx = fma(hs, pv[0], pr[0]), by = fma(hs, pv[1], pr[1]), bz = fma(hs, pv[2], pr[2]);
-    const double q4x = fma(hshh, k2x, bx), q4y = fma(hshh, k2y, by), q4z = fma(hshh, k2z, bz);
+    // stage 4 position: p + (p_v + 1/2 k2)
+    const double bx = pv[0] + pr[0], by = pv[1] + pr[1], bz = pv[2] + pr[2];
+    const double q4x = fma(0.5, k2x, bx), q4y = fma(0.5, k2y, by), q4z = fma(0.5, k2z, bz);
     if (MASSCOL) sym_mul_add(s4.g, q4x, q4y, q4z, s4.dx, s4.dy, s4.dz, k4x, k4y, k4z);
     else sym_mul(s4.g, q4x, q4y, q4z, k4x, k4y, k4z);
-    // p_r+ = p_r + h p_v + h^2/6 (k1+k2+k3);  p_v+ = p_v + h/6 (k1 + 2k2 + 2k3 + k4)
+    // p_r+ = p_r + p_v + 1/6 (k1+k2+k3);  p_v+ = p_v + 1/6 (k1 + 2k2 + 2k3 + k4)
     const double wx = k2x + k3x, wy = k2y + k3y, wz = k2z + k3z;
     const double sx = k1x + wx, sy = k1y + wy, sz = k1z + wz;
-    pr[0] = fma(hs2_6, sx, bx);
-    pr[1] = fma(hs2_6, sy, by);
-    pr[2] = fma(hs2_6, sz, bz);
-    pv[0] = fma(hs_6, (sx + wx) + k4x, pv[0]);
-    pv[1] = fma(hs_6, (sy + wy) + k4y, pv[1]);
-    pv[2] = fma(hs_6, (sz + wz) + k4z, pv[2]);
+    pr[0] = fma(c6, sx, bx);
+    pr[1] = fma(c6, sy, by);
+    pr[2] = fma(c6, sz, bz);
+    pv[0] = fma(c6, (sx + wx) + k4x, pv[0]);
+    pv[1] = fma(c6, (sy + wy) + k4y, pv[1]);
+    pv[2] = fma(c6, (sz + wz) + k4z, pv[2]);
 }
 
 // Input hold u(tau).  GENU = false: u is given on the K nodes of x, so inside one interval the reference's
@@ -189,6 +191,11 @@ struct UHold<false> {
         duy = us[K + 1] - u0y;
         duz = us[2 * (long long)K + 1] - u0z;
     }
+    __device__ __forceinline__ void scale(double f)   // hold f*u(tau) from now on
+    {
+        u0x *= f; u0y *= f; u0z *= f;
+        dux *= f; duy *= f; duz *= f;
+    }
     // s: position inside the interval in [0,1];  tau: the same point on the global grid (unused here)
     __device__ __forceinline__ void at(double s, double, double &ux, double &uy, double &uz) const
     {
@@ -202,17 +209,20 @@ template <>
 struct UHold<true> {
     const double *base;
     int Ku;
+    double f;
     __device__ __forceinline__ void init(const double *u, int sat, int, int, int Ku_)
     {
         Ku = Ku_;
+        f = 1.0;
         base = u + ((long long)sat * 3) * Ku_;
     }
+    __device__ __forceinline__ void scale(double f_) { f = f_; }
     __device__ __forceinline__ void at(double, double tau, double &ux, double &uy, double &uz) const
     {
         if (tau == 1.0 || Ku < 2) {
-            ux = base[Ku - 1];
-            uy = base[2 * Ku - 1];
-            uz = base[3 * (long long)Ku - 1];
+            ux = f * base[Ku - 1];
+            uy = f * base[2 * Ku - 1];
+            uz = f * base[3 * (long long)Ku - 1];
             return;
         }
         const double km1 = (double)(Ku - 1);
@@ -221,9 +231,9 @@ struct UHold<true> {
         k = min(max(k, 0), Ku - 2);
         const double lo = (double)k / km1, hi = (double)(k + 1) / km1;
         const double ln = (hi - tau) / (hi - lo), lp = (tau - lo) / (hi - lo);
-        ux = fma(ln, base[k], lp * base[k + 1]);
-        uy = fma(ln, base[Ku + k], lp * base[Ku + k + 1]);
-        uz = fma(ln, base[2 * (long long)Ku + k], lp * base[2 * (long long)Ku + k + 1]);
+        ux = f * fma(ln, base[k], lp * base[k + 1]);
+        uy = f * fma(ln, base[Ku + k], lp * base[Ku + k + 1]);
+        uz = f * fma(ln, base[2 * (long long)Ku + k], lp * base[2 * (long long)Ku + k + 1]);
     }
 };
 
@@ -387,11 +397,16 @@ __device__ __forceinline__ void node_accumulate(volatile double *acc, const doub
 }
 
 // Epilogue shared by both kernels: A_k = Phi_end; [B_kp B_kn Sigma_k xi_k] = Phi_end * integrals, with the
-// integrals scaled by sB (B and xi carry tf, :182,214) / sS (Sigma does not, :252); SoA store to NDST buffers.
+// integrals scaled by sB (B carries tf, :182,214) / sS (Sigma does not, :252) / sX (xi; = sB unless the caller's
+// accumulated xi vectors carry a factor of their own); SoA store to NDST buffers.
 // linearize_discretize.py:43-44,77-80.  Returns nonzero when a stored value is not finite.
+// cs / vs undo a similarity scaling of the velocity block: the caller's Phi is D Phi D^-1 and its integrals are
+// D * (integrals) with D = diag(I3, cs I3, 1), vs = 1/cs (discretize_kernel: cs = step; adaptive kernel: cs = vs = 1,
+// and the multiplications by 1.0 leave every bit unchanged).
 template <int BLOCK, int NDST>
 __device__ __forceinline__ int epilogue_store(volatile double *acc, const double (&pr)[7][3], const double (&pv)[7][3],
-                                              double sB, double sS, const DstTab &dst, long long pitch, long long col)
+                                              double sB, double sS, double sX, const DstTab &dst, long long pitch,
+                                              long long col, double cs = 1.0, double vs = 1.0)
 {
     double *dsts[NDST];
 #pragma unroll
@@ -407,8 +422,9 @@ __device__ __forceinline__ int epilogue_store(volatile double *acc, const double
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
-            store(a * 7 + c, pr[c][a]);
-            store((a + 3) * 7 + c, pv[c][a]);
+            const bool vcol = (c >= 3 && c < 6);
+            store(a * 7 + c, vcol ? pr[c][a] * cs : pr[c][a]);
+            store((a + 3) * 7 + c, vcol ? pv[c][a] : pv[c][a] * vs);
         }
     if (dst.skip_const == 0) {
 #pragma unroll
@@ -436,8 +452,8 @@ __device__ __forceinline__ int epilogue_store(volatile double *acc, const double
             I[6] = sS * ACC(54);
         } else {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) I[c] = sB * ACC(42 + c);
-            I[6] = sB * ACC(55);
+            for (int c = 0; c < 6; ++c) I[c] = sX * ACC(42 + c);
+            I[6] = sX * ACC(55);
         }
 #pragma unroll
         for (int a = 0; a < 7; ++a) {
@@ -450,6 +466,7 @@ __device__ __forceinline__ int epilogue_store(volatile double *acc, const double
                 v = pv[0][a - 3] * I[0];
 #pragma unroll
                 for (int c = 1; c < 7; ++c) v = fma(pv[c][a - 3], I[c], v);
+                v *= vs;
             } else {
                 v = I[6];
             }
@@ -495,7 +512,24 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     const double inv_n = 1.0 / (double)n_sub;
     const double h = inv_n / (double)(K - 1);  // step in tau
     const double hs = tf * h;                  // step of the unscaled system
-    const double hh = 0.5 * hs, hh2 = hh * hh, hshh = hs * hh, hs2_6 = hs * hs * (1.0 / 6.0), hs_6 = hs * (1.0 / 6.0);
+    // ---- step-normalised variables ------------------------------------------------------------------
+    // With D = diag(I3, hs I3, 1) the kernel carries D x (velocity times the step) and D Phi D^-1, and integrates in
+    // units of the step: r' = v~, v~' = hs^2 a, m' = hs mdot.  hs^2 is folded into MU, kJ2 and the held input
+    // (u~ = hs^2 u), hs into 1/(G0 ISP), so it costs nothing per step, and every Runge-Kutta coefficient becomes a
+    // literal.  D Phi D^-1 is symplectic too (D^T J D = hs J), so the inverse formula is unchanged.  The
+    // quadrature accumulates Phi~^-1 (D g) -- for Sigma and xi' with the common factor 1/hs taken out -- and the
+    // epilogue undoes D.  Same arithmetic as before up to rounding.
+    const double hs2 = hs * hs;
+    DiscParams Ph;
+    Ph.mu = P.mu * hs2;
+    Ph.kj2 = P.kj2 * hs2;
+    Ph.inv_ve = P.inv_ve / hs;                 // mdot~ = hs mdot = -|u~| / (hs G0 ISP)
+    hold.scale(hs2);
+    const double eps2 = 4.930380657631324e-32 * (hs2 * hs2);   // |u| <= eps  <=>  |u~|^2 <= eps^2 hs^4   (:208)
+    vx *= hs;
+    vy *= hs;
+    vz *= hs;
+    constexpr double c6 = 1.0 / 6.0;
 
     // Phi columns: pr[c] = rows 0..2 of column c, pv[c] = rows 3..5.  Phi(tau_k) = I   (:34)
     double pr[7][3], pv[7][3];
@@ -514,17 +548,17 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     double ux, uy, uz;
     hold.at(0.0, tau0, ux, uy, uz);
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
-    double iun = (uu > 4.930380657631324e-32) ? fast_rsqrt(uu) : 0.0;  // |u| <= eps  (:208)
+    double iun = (uu > eps2) ? fast_rsqrt(uu) : 0.0;
     double un = uu * iun;
 
     for (int n = 0; n <= n_sub; ++n) {
         // ---- stage 1 == quadrature node n ------------------------------------------------------
         StageLin s1;
         double a1x, a1y, a1z;
-        gravity<J2>(P, rx, ry, rz, a1x, a1y, a1z, s1.g);
+        gravity<J2>(Ph, rx, ry, rz, a1x, a1y, a1z, s1.g);
         bad |= !(m > 0.0);
         const double im = fast_rcp(m);
-        const double tx = ux * im, ty = uy * im, tz = uz * im;  // u/m
+        const double tx = ux * im, ty = uy * im, tz = uz * im;  // u~/m
         // xi' = -(Dxf x + Duf u) = -[v; G r; mdot]  (the -u/m and +u/m terms cancel, :232-235)
         double grx, gry, grz;
         sym_mul(s1.g, rx, ry, rz, grx, gry, grz);
@@ -534,12 +568,13 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
         s1.dx = -tx * im;
         s1.dy = -ty * im;
         s1.dz = -tz * im;
-        const double md1 = -un * P.inv_ve;  // mass flow (simulator.py:160)
+        const double md1 = -un * Ph.inv_ve;  // hs * mass flow (simulator.py:160)
         {
             const double sfrac = (double)n * inv_n;                     // lambda+   (:61)
             const double w = (n == 0 || n == n_sub) ? 0.5 : 1.0;        // trapezoid end weights (:77-80)
             const double ws = w * sfrac;
-            node_accumulate<BLOCK>(acc, pr, pv, P, im, ux, uy, uz, iun, md1, vx, vy, vz, a1x, a1y, a1z, grx, gry, grz, w, ws);
+            // D Duf = [0; hs I/m; b^T];  hs D Sigma = [v~; a~; mdot~];  hs D xi' = -[v~; G~ r; mdot~_B]
+            node_accumulate<BLOCK>(acc, pr, pv, P, im * hs, ux, uy, uz, iun, md1, vx, vy, vz, a1x, a1y, a1z, grx, gry, grz, w, ws);
         }
         if (n == n_sub) break;
 
@@ -550,19 +585,19 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
         hold.at(se, (n + 1 == n_sub && k + 2 == K) ? 1.0 : fma(se, dtau_k, tau0), uex, uey, uez);
         const double uum = fma(umx, umx, fma(umy, umy, umz * umz));
         const double uue = fma(uex, uex, fma(uey, uey, uez * uez));
-        const double iunm = (uum > 4.930380657631324e-32) ? fast_rsqrt(uum) : 0.0;
-        const double iune = (uue > 4.930380657631324e-32) ? fast_rsqrt(uue) : 0.0;
-        const double mdm = -(uum * iunm) * P.inv_ve;
-        const double mde = -(uue * iune) * P.inv_ve;
-        const double m2 = fma(hh, md1, m);
-        const double m3 = fma(hh, mdm, m);
-        const double m4 = fma(hs, mdm, m);
+        const double iunm = (uum > eps2) ? fast_rsqrt(uum) : 0.0;
+        const double iune = (uue > eps2) ? fast_rsqrt(uue) : 0.0;
+        const double mdm = -(uum * iunm) * Ph.inv_ve;
+        const double mde = -(uue * iune) * Ph.inv_ve;
+        const double m2 = fma(0.5, md1, m);
+        const double m3 = fma(0.5, mdm, m);
+        const double m4 = m + mdm;
         bad |= !(m4 > 0.0);
 
         StageLin s2, s3, s4;
         double a2x, a2y, a2z, a3x, a3y, a3z, a4x, a4y, a4z;
-        const double r2x = fma(hh, vx, rx), r2y = fma(hh, vy, ry), r2z = fma(hh, vz, rz);
-        gravity<J2>(P, r2x, r2y, r2z, a2x, a2y, a2z, s2.g);
+        const double r2x = fma(0.5, vx, rx), r2y = fma(0.5, vy, ry), r2z = fma(0.5, vz, rz);
+        gravity<J2>(Ph, r2x, r2y, r2z, a2x, a2y, a2z, s2.g);
         {
             const double i2 = fast_rcp(m2);
             const double qx = umx * i2, qy = umy * i2, qz = umz * i2;
@@ -573,8 +608,8 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             s2.dy = -qy * i2;
             s2.dz = -qz * i2;
         }
-        const double r3x = fma(hh2, a1x, r2x), r3y = fma(hh2, a1y, r2y), r3z = fma(hh2, a1z, r2z);
-        gravity<J2>(P, r3x, r3y, r3z, a3x, a3y, a3z, s3.g);
+        const double r3x = fma(0.25, a1x, r2x), r3y = fma(0.25, a1y, r2y), r3z = fma(0.25, a1z, r2z);
+        gravity<J2>(Ph, r3x, r3y, r3z, a3x, a3y, a3z, s3.g);
         {
             const double i3 = fast_rcp(m3);
             const double qx = umx * i3, qy = umy * i3, qz = umz * i3;
@@ -585,9 +620,9 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             s3.dy = -qy * i3;
             s3.dz = -qz * i3;
         }
-        const double bx = fma(hs, vx, rx), by = fma(hs, vy, ry), bz = fma(hs, vz, rz);
-        const double r4x = fma(hshh, a2x, bx), r4y = fma(hshh, a2y, by), r4z = fma(hshh, a2z, bz);
-        gravity<J2>(P, r4x, r4y, r4z, a4x, a4y, a4z, s4.g);
+        const double bx = vx + rx, by = vy + ry, bz = vz + rz;
+        const double r4x = fma(0.5, a2x, bx), r4y = fma(0.5, a2y, by), r4z = fma(0.5, a2z, bz);
+        gravity<J2>(Ph, r4x, r4y, r4z, a4x, a4y, a4z, s4.g);
         {
             const double i4 = fast_rcp(m4);
             const double qx = uex * i4, qy = uey * i4, qz = uez * i4;
@@ -602,19 +637,19 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
         {
             const double wx = a2x + a3x, wy = a2y + a3y, wz = a2z + a3z;
             const double sx = a1x + wx, sy = a1y + wy, sz = a1z + wz;
-            rx = fma(hs2_6, sx, bx);
-            ry = fma(hs2_6, sy, by);
-            rz = fma(hs2_6, sz, bz);
-            vx = fma(hs_6, (sx + wx) + a4x, vx);
-            vy = fma(hs_6, (sy + wy) + a4y, vy);
-            vz = fma(hs_6, (sz + wz) + a4z, vz);
-            m = fma(hs_6, fma(4.0, mdm, md1) + mde, m);
+            rx = fma(c6, sx, bx);
+            ry = fma(c6, sy, by);
+            rz = fma(c6, sz, bz);
+            vx = fma(c6, (sx + wx) + a4x, vx);
+            vy = fma(c6, (sy + wy) + a4y, vy);
+            vz = fma(c6, (sz + wz) + a4z, vz);
+            m = fma(c6, fma(4.0, mdm, md1) + mde, m);
         }
         // ---- variational columns ----------------------------------------------------------------
         // the mass column first: its forcing terms d1..d4 are dead for the remaining six columns
-        column_step<true>(pr[6], pv[6], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
+        column_step<true>(pr[6], pv[6], s1, s2, s3, s4);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3, s4, hs, hh, hh2, hshh, hs2_6, hs_6);
+        for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3, s4);
         ux = uex;
         uy = uey;
         uz = uez;
@@ -622,8 +657,10 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
         un = uue * iune;
     }
 
-    // ---- epilogue: left-multiply by Phi_end, scale by the step, store SoA -----------------------
-    const int nonfinite = epilogue_store<BLOCK, NDST>(acc, pr, pv, hs, h, dst, pitch, offset + gid);
+    // ---- epilogue: left-multiply by Phi_end, undo D, scale by the step, store SoA -----------------
+    // B and xi carry tf (scale tf h = hs), Sigma does not (h); the accumulated Sigma and xi vectors carry the factor hs
+    const double ihs = 1.0 / hs;
+    const int nonfinite = epilogue_store<BLOCK, NDST>(acc, pr, pv, hs, h * ihs, 1.0, dst, pitch, offset + gid, hs, ihs);
     if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : 0);
 #undef ACC
 }
