@@ -32,19 +32,20 @@ FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SM x 64 DFMA/clk 
 
 
 def flops_per_interval(n_sub, include_j2=False):
-    """ALGORITHMIC FP64 work of one interval: the arithmetic of the algorithm DESIGN.md section 5 states
-    (42 live Phi entries, symmetric G, Nystrom-form RK4, symplectic inverse, 56 accumulators), FMA = 2 flop,
-    mul/add = 1, MUFU seeds not counted.  One thread does one interval with no recomputation, so this equals
-    the executed DFMA/DMUL/DADD count: per RK4 step + quadrature node 582 FMA + 221 mul + 98 add (J2: 630 /
-    281 / 119), plus ~800 flop for the last node and the Phi_end * [integrals] epilogue.  Cross-checked
-    against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/r01_c: 149.1 kflop)."""
-    per_step = (2 * 630 + 281 + 119) if include_j2 else (2 * 582 + 221 + 98)
-    return n_sub * per_step + 800
+    """ALGORITHMIC FP64 work of one interval: the arithmetic of the algorithm DESIGN.md section 4 states
+    (42 live Phi entries, symmetric G, Nystrom-form RK4 in step-normalised variables, symplectic inverse, 56
+    accumulators), FMA = 2 flop, mul/add = 1, MUFU seeds not counted.  One thread does one interval with no
+    recomputation, so this equals the executed DFMA/DMUL/DADD count: per RK4 step + quadrature node 548 FMA + 228 mul
+    + 128 add (J2: 599 / 288 / 147), plus the last node and the Phi_end * [integrals] epilogue (1249 flop; J2 1310).
+    Counted from the SASS of the shipped kernel (scripts/sass_reuse.py) and cross-checked against ncu
+    smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/)."""
+    per_step = (2 * 599 + 288 + 147) if include_j2 else (2 * 548 + 228 + 128)
+    return n_sub * per_step + (1310 if include_j2 else 1249)
 
 
 def fp64_instr_per_interval(n_sub, include_j2=False):
     """FP64-pipe instructions (DFMA+DMUL+DADD) per interval: the pipe-occupancy view of the same work."""
-    return n_sub * ((630 + 281 + 119) if include_j2 else (582 + 221 + 98)) + 500
+    return n_sub * ((599 + 288 + 147) if include_j2 else (548 + 228 + 128)) + (785 if include_j2 else 742)
 
 
 def bytes_per_interval():

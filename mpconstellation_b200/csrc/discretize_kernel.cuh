@@ -69,10 +69,22 @@ __device__ __forceinline__ double fast_rsqrt(double a)
     return y;
 }
 
-// acceleration (without the thrust/mass part) and its gradient at position r
+// 1/sqrt(uu) if uu > thr, else 0 (the reference's |u| <= eps guard, linearize_discretize.py:208), without a branch:
+// the Newton sequence always runs (on a harmless argument when the guard trips) and a select picks the result, so
+// a warp with mixed thrust / no-thrust intervals does not diverge and no BSSY/BSYNC pair sits in the step loop.
+__device__ __forceinline__ double inv_norm_guarded(double uu, double thr)
+{
+    const bool on = uu > thr;
+    const double r = fast_rsqrt(on ? uu : 1.0);
+    return on ? r : 0.0;
+}
+
+// acceleration (without the thrust/mass part) and its gradient at position r.
+// G r comes for free from Euler's theorem on homogeneous functions: a_g is homogeneous of degree -2 in r and a_J2 of
+// degree -4, so (d a_g/d r) r = -2 a_g and (d a_J2/d r) r = -4 a_J2  =>  G r = -2 a - 2 a_J2  (a = a_g + a_J2).
 template <bool J2>
 __device__ __forceinline__ void gravity(const DiscParams &P, double rx, double ry, double rz, double &ax,
-                                        double &ay, double &az, Sym3 &g)
+                                        double &ay, double &az, Sym3 &g, double *gr = nullptr)
 {
     const double r2 = fma(rx, rx, fma(ry, ry, rz * rz));
     const double ir = fast_rsqrt(r2);
@@ -92,6 +104,11 @@ __device__ __forceinline__ void gravity(const DiscParams &P, double rx, double r
     ax = -mu3 * rx;
     ay = -mu3 * ry;
     az = -mu3 * rz;
+    if (gr) {
+        gr[0] = -2.0 * ax;
+        gr[1] = -2.0 * ay;
+        gr[2] = -2.0 * az;
+    }
     if (J2) {
         // a_J2 = kJ2/|r|^5 diag(5q-1, 5q-1, 5q-3) r,  q = (z/|r|)^2      (simulator.py:156-157)
         // its gradient (the symmetric Hessian of the J2 potential; equals the reference's
@@ -102,9 +119,15 @@ __device__ __forceinline__ void gravity(const DiscParams &P, double rx, double r
         const double c1 = fma(5.0, q, -1.0);
         const double c3 = fma(5.0, q, -3.0);
         const double k5c1 = k5 * c1;
-        ax = fma(k5c1, rx, ax);
-        ay = fma(k5c1, ry, ay);
-        az = fma(k5 * c3, rz, az);
+        const double jx = k5c1 * rx, jy = k5c1 * ry, jz = (k5 * c3) * rz;
+        ax += jx;
+        ay += jy;
+        az += jz;
+        if (gr) {
+            gr[0] = fma(-4.0, jx, gr[0]);
+            gr[1] = fma(-4.0, jy, gr[1]);
+            gr[2] = fma(-4.0, jz, gr[2]);
+        }
         const double e = k5 * fma(35.0, q, -5.0);   // k5 (35q - 5)
         const double f = k5 * fma(-35.0, q, 15.0);  // k5 (15 - 35q)
         const double ex = e * nx, ey = e * ny;
@@ -548,20 +571,19 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     double ux, uy, uz;
     hold.at(0.0, tau0, ux, uy, uz);
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
-    double iun = (uu > eps2) ? fast_rsqrt(uu) : 0.0;
+    double iun = inv_norm_guarded(uu, eps2);
     double un = uu * iun;
 
     for (int n = 0; n <= n_sub; ++n) {
         // ---- stage 1 == quadrature node n ------------------------------------------------------
         StageLin s1;
         double a1x, a1y, a1z;
-        gravity<J2>(Ph, rx, ry, rz, a1x, a1y, a1z, s1.g);
+        double gr[3];   // G r of xi' = -(Dxf x + Duf u) = -[v; G r; mdot]  (the -u/m and +u/m terms cancel, :232-235)
+        gravity<J2>(Ph, rx, ry, rz, a1x, a1y, a1z, s1.g, gr);
         bad |= !(m > 0.0);
         const double im = fast_rcp(m);
         const double tx = ux * im, ty = uy * im, tz = uz * im;  // u~/m
-        // xi' = -(Dxf x + Duf u) = -[v; G r; mdot]  (the -u/m and +u/m terms cancel, :232-235)
-        double grx, gry, grz;
-        sym_mul(s1.g, rx, ry, rz, grx, gry, grz);
+        const double grx = gr[0], gry = gr[1], grz = gr[2];
         a1x += tx;
         a1y += ty;
         a1z += tz;
@@ -585,8 +607,8 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
         hold.at(se, (n + 1 == n_sub && k + 2 == K) ? 1.0 : fma(se, dtau_k, tau0), uex, uey, uez);
         const double uum = fma(umx, umx, fma(umy, umy, umz * umz));
         const double uue = fma(uex, uex, fma(uey, uey, uez * uez));
-        const double iunm = (uum > eps2) ? fast_rsqrt(uum) : 0.0;
-        const double iune = (uue > eps2) ? fast_rsqrt(uue) : 0.0;
+        const double iunm = inv_norm_guarded(uum, eps2);
+        const double iune = inv_norm_guarded(uue, eps2);
         const double mdm = -(uum * iunm) * Ph.inv_ve;
         const double mde = -(uue * iune) * Ph.inv_ve;
         const double m2 = fma(0.5, md1, m);
