@@ -207,6 +207,11 @@ def gpu_arm(args):
     _lib.require_gpu()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    try:
+        local_phys = int(vis.split(",")[local]) if vis else local      # NVML index of this rank's GPU
+    except (ValueError, IndexError):
+        local_phys = local
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -323,6 +328,9 @@ def gpu_arm(args):
     disc_ms_avg = disc_total / args.steps
 
     # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside the timed region) --
+    # every rank keeps its host thread and its pinned buffers on the NUMA node of its own GPU (first touch)
+    cpus0 = os.sched_getaffinity(0)
+    cpus = M.bind_host_to_gpu(local_phys)
     y0_h = M.pinned_empty((N, 7))
     y0_h[:] = Y
     out_h = M.pinned_empty((105, n_int))
@@ -338,6 +346,7 @@ def gpu_arm(args):
         if i >= 2:
             e2e_t.append(dt)
     e2e_s = float(np.mean(e2e_t))
+    os.sched_setaffinity(0, cpus0)          # the CPU baseline below uses every host core again
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -380,6 +389,7 @@ def gpu_arm(args):
                 "h2d_bytes_per_step": int(y0_h.nbytes + N * 8),
                 "d2h_bytes_per_step": int(out_h.nbytes + y_h.nbytes + u_h.nbytes + n_int * 4),
                 "api": "mpconstellation_b200.propagate_discretize (C-ABI mpc_propagate_discretize_host), pinned host buffers",
+                "host_cpus_rank0": len(cpus),
                 "matches_device_path": same},
         "gather": {"mode": gather_mode + (":" + args.fused_mode if fused is not None else ""), "verified": gathered_ok,
                    "bytes_received_per_rank_per_step": int((world - 1) * n_int * 105 * 8)} if world > 1 else None,

@@ -256,6 +256,18 @@ int mpc_constraint_terms(const double *x, const double *u, int n_sats, int K, in
 int mpc_constraint_terms_host(mpc_ctx *ctx, const double *x, const double *u, int n_sats, int K, int u_cols, double mu,
                               double *rbar_hat, double *ubar_hat, double *final_terms);
 
+/*
+ * Sparse (CSR) assembly of the dynamics constraint optimizer.py:327-339 from a SoA discretization result on the
+ * device:  J z = rhs,  one row per (s, i, k) in pyomo's generation order, row = (s*7 + i)*(K-1) + k, exactly
+ * MPC_JAC_NNZ_PER_ROW = 16 non-zeros per row in ascending column order (indptr[r] = 16 r), variables numbered
+ *   x[s,i,k] -> (s*7+i)*K + k | u[s,j,k] -> 7NK + (s*3+j)*K + k | nu[s,i,k] -> 10NK + (s*7+i)*K + k | tf -> 17NK.
+ * values [rows*16], indices [rows*16] (int64; may be NULL when only the values change between SCP iterations),
+ * rhs [rows] = xi_k.  soa / pitch / offset as written by mpc_discretize_batch.  Device pointers, caller's stream.
+ */
+#define MPC_JAC_NNZ_PER_ROW 16
+int mpc_dynamics_jacobian(const double *soa, int64_t pitch, int64_t offset, int n_sats, int K, double *values,
+                          int64_t *indices, double *rhs, void *stream);
+
 /* ---------------------------------------------------------------- measurement helpers */
 
 /* FP64 FMA-chain microbenchmark: measured DFMA peak of `device` in TFLOP/s (2 flop per FMA). */

@@ -75,3 +75,69 @@ def get_constraint_terms(x_bar, u_bar, const, device=0):
                                      np.stack([np.asarray(a, dtype=np.float64) for a in u_bar]), const, device=device)
     n = len(x_bar)
     return {k: [stacked[k][i] if stacked[k].ndim > 1 else float(stacked[k][i]) for i in range(n)] for k in KEYS}
+
+
+# ------------------------------------------------------------------ sparse dynamics constraint (optimizer.py:327-339)
+
+NNZ_PER_ROW = 16
+
+
+class DynamicsJacobian:
+    """CSR form  J z = rhs  of the reference's dynamics constraint (dynamics_const_rule, optimizer.py:327-339) for N
+    satellites: rows in pyomo's generation order (s, i, k), row = (s*7+i)*(K-1)+k; 16 non-zeros per row; variables
+    z = [x (N,7,K) | u (N,3,K) | nu (N,7,K) | tf] flattened C-order (include/mpc_b200.h, mpc_dynamics_jacobian)."""
+
+    def __init__(self, values, indices, rhs, n_sats, K):
+        self.values, self.indices, self.rhs, self.n_sats, self.K = values, indices, rhs, n_sats, K
+        self.rows = n_sats * 7 * (K - 1)
+        self.cols = 17 * n_sats * K + 1
+
+    @property
+    def indptr(self):
+        return np.arange(self.rows + 1, dtype=np.int64) * NNZ_PER_ROW
+
+    def pack(self, x, u, nu, tf):
+        """decision vector z from x [N,7,K], u [N,3,K], nu [N,7,K] (last column unused by the constraint), tf scalar"""
+        return np.concatenate([np.ravel(x), np.ravel(u), np.ravel(nu), [float(tf)]])
+
+    def residual(self, z):
+        """J z - rhs, reshaped [N,7,K-1]: zero where the reference's constraint holds"""
+        v = np.asarray(self.values).reshape(self.rows, NNZ_PER_ROW)
+        c = np.asarray(self.indices).reshape(self.rows, NNZ_PER_ROW)
+        return ((v * np.asarray(z)[c]).sum(axis=1) - np.asarray(self.rhs)).reshape(self.n_sats, 7, self.K - 1)
+
+    def to_scipy(self):
+        from scipy.sparse import csr_matrix
+        return csr_matrix((np.asarray(self.values), np.asarray(self.indices), self.indptr), shape=(self.rows, self.cols))
+
+
+def dynamics_jacobian_device(soa, n_sats, K, pitch=None, offset=0, values=None, indices=None, rhs=None,
+                             with_indices=True):
+    """Device form: soa is the [105, pitch] float64 CUDA tensor a discretization wrote (columns offset.. hold the
+    batch).  Returns (values [rows*16] f64, indices [rows*16] i64 or None, rhs [rows] f64) CUDA tensors; enqueued on
+    torch's current stream.  Between SCP iterations only the values change: pass with_indices=False."""
+    import torch
+    rows = n_sats * 7 * (K - 1)
+    pitch = soa.shape[1] if pitch is None else int(pitch)
+    assert soa.is_cuda and soa.dtype == torch.float64 and soa.is_contiguous()
+    if values is None:
+        values = torch.empty(rows * NNZ_PER_ROW, dtype=torch.float64, device=soa.device)
+    if indices is None and with_indices:
+        indices = torch.empty(rows * NNZ_PER_ROW, dtype=torch.int64, device=soa.device)
+    if rhs is None:
+        rhs = torch.empty(rows, dtype=torch.float64, device=soa.device)
+    stream = torch.cuda.current_stream(soa.device).cuda_stream
+    _lib.check(_lib.lib().mpc_dynamics_jacobian(soa.data_ptr(), pitch, int(offset), int(n_sats), int(K),
+                                                values.data_ptr(), indices.data_ptr() if indices is not None else None,
+                                                rhs.data_ptr(), stream))
+    return values, indices, rhs
+
+
+def dynamics_jacobian(matrices):
+    """Host form: `matrices` is a DiscretizedBatch (e.g. Linearization.matrices); the assembly runs on the GPU.
+    Returns a DynamicsJacobian with numpy arrays."""
+    import torch
+    _lib.require_gpu()
+    soa = torch.from_numpy(np.ascontiguousarray(matrices.soa)).cuda()
+    v, c, r = dynamics_jacobian_device(soa, matrices.n_sats, matrices.K)
+    return DynamicsJacobian(v.cpu().numpy(), c.cpu().numpy(), r.cpu().numpy(), matrices.n_sats, matrices.K)

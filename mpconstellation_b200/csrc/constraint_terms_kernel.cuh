@@ -202,4 +202,56 @@ constraint_terms_kernel(const double *__restrict__ x, const double *__restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse assembly of the dynamics constraint (optimizer.py:327-339) from the SoA discretization result.
+//
+//   x[s,i,k+1] - ( sum_j A_k[s][k,i,j] x[s,j,k] + sum_j B_kn[s][k,i,j] u[s,j,k] + sum_j B_kp[s][k,i,j] u[s,j,k+1]
+//                  + Sigma_k[s][i,k] tf + xi_k[s][i,k] + nu[s,i,k] ) == 0
+//
+// is one row of   J z = rhs   with rhs = xi_k[s][i,k].  Rows follow the order pyomo generates them in
+// (Constraint(sIDX, xIDX, kIDX), k = K-1 skipped):  row = (s*7 + i)*(K-1) + k.  Variables are numbered
+//   x[s,i,k]  -> (s*7 + i)*K + k                    u[s,j,k] -> 7NK + (s*3 + j)*K + k
+//   nu[s,i,k] -> 10NK + (s*7 + i)*K + k             tf       -> 17NK           (one shared final time, optimizer.py:281)
+// Every row has exactly 16 structural non-zeros, stored in ascending column order:
+//   [ -A[i,0..6] with +1 at x[s,i,k+1] merged in order ] ... see the column list in the kernel.
+// CSR: indptr[r] = 16 r (implicit), indices [rows*16], values [rows*16], rhs [rows].
+// One thread per row; consecutive threads = consecutive k, so the SoA reads are coalesced.
+constexpr int kJacNnzPerRow = 16;
+
+__global__ void __launch_bounds__(256)
+dynamics_jacobian_kernel(const double *__restrict__ soa, long long pitch, long long offset, int n_sats, int K,
+                         double *__restrict__ values, int64_t *__restrict__ indices, double *__restrict__ rhs)
+{
+    const long long rows = (long long)n_sats * 7 * (K - 1);
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int k = (int)(r % (K - 1));
+    const long long si = r / (K - 1);
+    const int i = (int)(si % 7);
+    const long long s = si / 7;
+    const long long col = offset + s * (K - 1) + k;   // column of this interval in the SoA result
+    const long long NK = (long long)n_sats * K;
+    const long long x0 = s * 7 * K, u0 = 7 * NK + s * 3 * K, nu0 = 10 * NK + (s * 7 + i) * (long long)K, tfc = 17 * NK;
+    double *vo = values + r * kJacNnzPerRow;
+    int64_t *co = indices ? indices + r * kJacNnzPerRow : nullptr;
+    auto put = [&](int pos, double val, long long column) {
+        vo[pos] = val;
+        if (co) co[pos] = column;
+    };
+    // ascending column order: x[s,0..i,k] | x[s,i,k+1] | x[s,i+1..6,k] | u[s,j,k], u[s,j,k+1] per j | nu | tf
+#pragma unroll
+    for (int j = 0; j < 7; ++j)                                                          // -A_k[k,i,j] * x[s,j,k]
+        put(j + (j > i ? 1 : 0), -soa[(long long)(i * 7 + j) * pitch + col], x0 + (long long)j * K + k);
+    put(i + 1, 1.0, x0 + (long long)i * K + k + 1);                                      // +x[s,i,k+1]
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        put(8 + 2 * j, -soa[(long long)(70 + i * 3 + j) * pitch + col], u0 + (long long)j * K + k);       // -B_kn u[s,j,k]
+        put(9 + 2 * j, -soa[(long long)(49 + i * 3 + j) * pitch + col], u0 + (long long)j * K + k + 1);   // -B_kp u[s,j,k+1]
+    }
+    put(14, -1.0, nu0 + k);                                                               // -nu[s,i,k]
+    put(15, -soa[(long long)(91 + i) * pitch + col], tfc);                                // -Sigma_k[i,k] * tf
+    rhs[r] = soa[(long long)(98 + i) * pitch + col];                     // xi_k[i,k]
+}
+
 }  // namespace mpc

@@ -891,6 +891,21 @@ int mpc_constraint_terms_host(mpc_ctx *ctx, const double *x, const double *u, in
     return MPC_SUCCESS;
 }
 
+int mpc_dynamics_jacobian(const double *soa, int64_t pitch, int64_t offset, int n_sats, int K, double *values,
+                          int64_t *indices, double *rhs, void *stream)
+{
+    if (!soa || !values || !rhs) return fail(MPC_E_INVALID, "null pointer argument");
+    if (n_sats < 0 || K < 2) return fail(MPC_E_INVALID, "need n_sats >= 0, K >= 2");
+    const long long rows = (long long)n_sats * 7 * (K - 1);
+    if (pitch < offset + (long long)n_sats * (K - 1) || offset < 0) return fail(MPC_E_INVALID, "pitch/offset do not hold the batch");
+    if (rows == 0) return MPC_SUCCESS;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    mpc::dynamics_jacobian_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(soa, pitch, offset, n_sats, K, values, indices, rhs);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
 int mpc_fp64_peak_probe(int device, int repeats, double *tflops, double *ms)
 {
     if (!tflops) return fail(MPC_E_INVALID, "null output");

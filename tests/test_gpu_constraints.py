@@ -80,3 +80,33 @@ def test_constraint_terms_edges(M, const):
     assert out["rbar_hat"].shape == (1, 3, 1) and out["DrVn_DvVn"].shape == (1, 6)
     with pytest.raises(ValueError):
         constraint_terms_batch(x[:, :6], u, const)
+
+
+def test_sparse_dynamics_jacobian_reproduces_the_pyomo_rule(M, const):
+    """mpc_dynamics_jacobian: J z - rhs equals the residual of dynamics_const_rule (optimizer.py:327-339) evaluated
+    with the rule's own indexing, for random decision vectors; structure: 16 nnz per row, ascending columns"""
+    from mpconstellation_b200.constraints import dynamics_jacobian
+    from mpconstellation_b200.scp import Linearization
+    y0, x, u = synth_batch(5, 9, 0.7, const)
+    mats = M.discretize_batch(x, u, 0.7, const, n_sub=10)
+    lin = Linearization(x, u, np.full(5, 0.7), mats)
+    jac = dynamics_jacobian(mats)
+    N, K = 5, 9
+    assert jac.rows == N * 7 * (K - 1) and jac.cols == 17 * N * K + 1
+    idx = jac.indices.reshape(jac.rows, 16)
+    assert np.all(np.diff(idx, axis=1) > 0) and idx.min() >= 0 and idx.max() == jac.cols - 1
+    rng = np.random.default_rng(3)
+    xz, uz, nuz, tfz = rng.standard_normal((N, 7, K)), rng.standard_normal((N, 3, K)), rng.standard_normal((N, 7, K)), 0.9
+    res = jac.residual(jac.pack(xz, uz, nuz, tfz))
+    for s in range(N):
+        want = lin.dynamics_residual(s, xz[s], uz[s], tfz, nu=nuz[s])
+        assert np.max(np.abs(res[s] - want)) < 1e-12 * max(1.0, np.max(np.abs(want)))
+    # scipy view of the same CSR
+    J = jac.to_scipy()
+    assert J.shape == (jac.rows, jac.cols) and J.nnz == 16 * jac.rows
+    assert np.allclose(J @ jac.pack(xz, uz, nuz, tfz) - jac.rhs, res.ravel(), rtol=0, atol=1e-12)
+    # on the reference point with nu = the FOH defect the constraint holds
+    nu0 = np.zeros((N, 7, K))
+    for s in range(N):
+        nu0[s, :, :K - 1] = lin.dynamics_residual(s, x[s], u[s], 0.7)
+    assert np.max(np.abs(jac.residual(jac.pack(x, u, nu0, 0.7)))) < 1e-13
