@@ -15,7 +15,7 @@ CTRL_ZERO, CTRL_CONSTANT, CTRL_TANGENTIAL, CTRL_SEQUENCE = 0, 1, 2, 3
 
 
 class OrcParams(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_double) for n in ("MU", "R_E", "J2", "G0", "ISP", "S", "R0", "RHO", "C_D", "RHO_ATM")] + \
+    _fields_ = [(n, ctypes.c_double) for n in ("MU", "R_E", "J2", "G0", "ISP", "S", "R0", "RHO", "C_D", "RHO_ATM", "CD_A", "RHO_A")] + \
                [("include_J2", ctypes.c_int), ("include_drag", ctypes.c_int)]
 
 
@@ -54,16 +54,18 @@ def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
 
 
-def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.983e-13):
+def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.983e-13, drag=None):
+    """drag = (CD, rho_n): the discretizer's drag branch (linearize_discretize.py:160-169) with constant density"""
+    cd_a, rho_a = (0.0, 0.0) if drag is None else (float(drag[0]), float(drag[1]))
     return OrcParams(const.MU, const.R_E, const.J2, const.G0, const.ISP, const.S, const.R0, const.RHO,
-                     c_d, rho_atm, int(include_J2), int(include_drag))
+                     c_d, rho_atm, cd_a, rho_a, int(include_J2), int(include_drag or drag is not None))
 
 
 def max_threads():
     return lib().orc_max_threads()
 
 
-def discretize_batch(x, u, tf, const, include_J2=False, n_sub=100, nthreads=0):
+def discretize_batch(x, u, tf, const, include_J2=False, n_sub=100, nthreads=0, drag=None):
     """x [N,7,K], u [N,3,K], tf scalar or [N] -> (A[N,K-1,7,7], B_kp[N,K-1,7,3], B_kn, Sigma[N,7,K-1], xi[N,7,K-1], status)."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
@@ -71,7 +73,7 @@ def discretize_batch(x, u, tf, const, include_J2=False, n_sub=100, nthreads=0):
     tf = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
     out = np.zeros((N, K - 1, 105))
     status = np.zeros(N * (K - 1), dtype=np.int32)
-    p = make_params(const, include_J2)
+    p = make_params(const, include_J2, drag=drag)
     lib().orc_discretize_rk4(_dp(x), _dp(u), _dp(tf), ctypes.byref(p), N, K, n_sub, _dp(out),
                              status.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), nthreads)
     A = out[:, :, 0:49].reshape(N, K - 1, 7, 7)
@@ -82,7 +84,8 @@ def discretize_batch(x, u, tf, const, include_J2=False, n_sub=100, nthreads=0):
     return A, Bp, Bn, S, X, status.reshape(N, K - 1)
 
 
-def discretize_batch_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6, max_step=1e-2, nthreads=0):
+def discretize_batch_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6, max_step=1e-2, nthreads=0,
+                              drag=None):
     """The reference's default mode (quadrature on the accepted RK45 steps).  Returns the same tuple as
     discretize_batch plus the node count per interval."""
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -92,7 +95,7 @@ def discretize_batch_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol
     out = np.zeros((N, K - 1, 105))
     status = np.zeros(N * (K - 1), dtype=np.int32)
     nodes = np.zeros(N * (K - 1), dtype=np.int32)
-    p = make_params(const, include_J2)
+    p = make_params(const, include_J2, drag=drag)
     ip = ctypes.POINTER(ctypes.c_int)
     lib().orc_discretize_rk45(_dp(x), _dp(u), _dp(tf), ctypes.byref(p), N, K, rtol, atol, max_step, _dp(out),
                               status.ctypes.data_as(ip), nodes.ctypes.data_as(ip), nthreads)

@@ -34,6 +34,8 @@
 typedef struct {
     double MU, R_E, J2, G0, ISP, S, R0, RHO; /* satellite_scale.py:42-44 */
     double C_D, RHO_ATM;                     /* constants.py:7, simulator.py:112 */
+    double CD_A, RHO_A;                      /* const.CD and rho_func(r) of the discretizer's drag branch
+                                                (linearize_discretize.py:162-168; constant density, drho = 0) */
     int include_J2, include_drag;
 } orc_params;
 
@@ -69,7 +71,20 @@ static int dyn(const double *y, const double *u, const orc_params *p, int drag, 
     return 0;
 }
 
-/* Dxf (7x7 row-major), linearize_discretize.py:134-179 without the (unusable) drag branch */
+/* Dxf (7x7 row-major), linearize_discretize.py:134-179; drag != 0 adds the branch :160-169 with a constant
+ * density (drho_func = 0, so Dr_aD vanishes) */
+static void dxf_drag(const double *x, const orc_params *p, double *D)
+{
+    const double *v = x + 3;
+    double m = x[6], vn = norm3(v);
+    double kv = -p->RHO_A * p->CD_A * p->S / (2.0 * m);        /* :166 */
+    double km = p->RHO_A * p->CD_A * p->S / (2.0 * m * m);     /* :168 */
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) D[(3 + i) * 7 + 3 + j] = kv * ((i == j ? vn : 0.0) + v[i] * v[j] / vn);
+        D[(3 + i) * 7 + 6] += km * vn * v[i];
+    }
+}
+
 static void dxf(const double *x, const double *u, const orc_params *p, int j2, double *D)
 {
     memset(D, 0, 49 * sizeof(double));
@@ -113,7 +128,8 @@ static int aug_rhs(const double *y, const double *u, double tf, const orc_params
 {
     double D[49], f[7];
     dxf(y + 49, u, p, j2, D);
-    if (dyn(y + 49, u, p, 0, j2, f)) return 1;
+    if (p->include_drag) dxf_drag(y + 49, p, D);
+    if (dyn(y + 49, u, p, p->include_drag, j2, f)) return 1;
     for (int i = 0; i < 7; ++i)
         for (int j = 0; j < 7; ++j) {
             double s = 0.0;
@@ -180,8 +196,9 @@ static int interval(const double *xk, const double *u0, const double *u1, double
         if (inv7(y, Pinv)) return 3;
         duf(xs, un, p, Bm);
         for (int i = 0; i < 21; ++i) Bm[i] *= tf;
-        if (dyn(xs, un, p, 0, j2, sig)) return 1;
+        if (dyn(xs, un, p, p->include_drag, j2, sig)) return 1;
         dxf(xs, un, p, j2, Dx);
+        if (p->include_drag) dxf_drag(xs, p, Dx);
         for (int i = 0; i < 7; ++i) {
             double s = 0.0;
             for (int l = 0; l < 7; ++l) s += tf * Dx[i * 7 + l] * xs[l];
@@ -331,8 +348,9 @@ static int node_integrands(const aug_ctx *c, double t, const double *y, double *
     if (inv7(y, Pinv)) return 3;
     duf(xs, un, c->p, Bm);
     for (int i = 0; i < 21; ++i) Bm[i] *= c->tf;
-    if (dyn(xs, un, c->p, 0, c->j2, sig)) return 1;
+    if (dyn(xs, un, c->p, c->p->include_drag, c->j2, sig)) return 1;
     dxf(xs, un, c->p, c->j2, Dx);
+    if (c->p->include_drag) dxf_drag(xs, c->p, Dx);
     for (int i = 0; i < 7; ++i) {
         double s = 0.0;
         for (int l = 0; l < 7; ++l) s += c->tf * Dx[i * 7 + l] * xs[l];

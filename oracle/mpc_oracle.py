@@ -114,10 +114,10 @@ def dynamics(y, u, tf, const, include_drag=True, include_J2=True):
     return tf * dy
 
 
-def jac_x(x, u, tf, const, include_J2=False):
-    """A = tf * d f / d x (7x7).  ref: linearize_discretize.py:119-183 (drag branch is
-    unusable in the reference -- Constants has no CD and rho_func is None -- so it is
-    not restated; callers must not ask for it)."""
+def jac_x(x, u, tf, const, include_J2=False, drag=None):
+    """A = tf * d f / d x (7x7).  ref: linearize_discretize.py:119-183.  The drag branch (:160-169) is unreachable
+    with the reference's defaults (Constants has no CD, rho_func is None); it runs once the caller supplies them:
+    drag = (CD, rho, drho) with rho = rho_func(r), drho = drho_func(r) already evaluated."""
     r = x[0:3].reshape(3, 1)
     rx, ry, rz = x[0], x[1], x[2]
     rn = np.linalg.norm(r)
@@ -138,6 +138,13 @@ def jac_x(x, u, tf, const, include_J2=False):
     A[0:3, 3:6] = np.eye(3)
     A[3:6, 0:3] = grav + j2
     A[3:6, 6:7] = -T / m ** 2                                                          # :175
+    if drag is not None:
+        CD, rho, drho = drag
+        v = x[3:6].reshape(3, 1)
+        vn = np.linalg.norm(v)
+        A[3:6, 0:3] += ((-CD * const.S / (2 * m)) * vn * v) @ (drho * r.T / rn)        # :165
+        A[3:6, 3:6] = ((-rho * CD * const.S) / (2 * m)) * (vn * np.eye(3) + (1 / vn) * (v @ v.T))   # :166-167
+        A[3:6, 6:7] += ((rho * CD * const.S) / (2 * m ** 2)) * vn * v                  # :168
     return tf * A
 
 
@@ -168,8 +175,12 @@ def foh(tau, u_nodes):
 # --------------------------------------------------------------------------- discretization
 
 def interval_matrices(k, x, u, tf, const, include_J2=False, use_uniform_steps=False,
-                      integrator_steps=101, ivp_max_step=1e-2, ivp_solver="RK45"):
-    """One interval: (A_k, B_kp, B_kn, Sigma_k, xi_k).  ref: linearize_discretize.py:8-82."""
+                      integrator_steps=101, ivp_max_step=1e-2, ivp_solver="RK45", drag=None):
+    """One interval: (A_k, B_kp, B_kn, Sigma_k, xi_k).  ref: linearize_discretize.py:8-82.
+    drag = (CD, rho_n) enables include_drag with a constant density: the dynamics then carry the simulator's drag
+    (global C_D, 500 km density, simulator.py:150-153) and A the terms of linearize_discretize.py:160-169."""
+    dr = None if drag is None else (drag[0], drag[1], 0.0)
+    has_drag = drag is not None
     K = x.shape[1]
     tau = np.linspace(0, 1, K)
     t0, t1 = tau[k], tau[k + 1]
@@ -180,8 +191,8 @@ def interval_matrices(k, x, u, tf, const, include_J2=False, use_uniform_steps=Fa
         ut = foh(t, u)
         Phi = y[0:49].reshape(7, 7)
         xs = y[49:56]
-        dPhi = jac_x(xs, ut, tf, const, include_J2) @ Phi
-        dx = dynamics(xs, ut, tf, const, include_drag=False, include_J2=include_J2)
+        dPhi = jac_x(xs, ut, tf, const, include_J2, dr) @ Phi
+        dx = dynamics(xs, ut, tf, const, include_drag=has_drag, include_J2=include_J2)
         return np.concatenate([dPhi.ravel(), dx])
 
     y0 = np.concatenate([np.eye(7).ravel(), x[:, k]])
@@ -200,8 +211,8 @@ def interval_matrices(k, x, u, tf, const, include_J2=False, use_uniform_steps=Fa
         ut = foh(t, u)
         xi = xs_all[:, i]
         Bs[i] = jac_u(xi, ut, tf, const)                                               # :65
-        Ss[:, i] = dynamics(xi, ut, 1, const, include_drag=False, include_J2=include_J2)  # :66, :252-253
-        Xs[:, i] = -(jac_x(xi, ut, tf, const, include_J2) @ xi + Bs[i] @ ut)           # :67, :232-235
+        Ss[:, i] = dynamics(xi, ut, 1, const, include_drag=has_drag, include_J2=include_J2)  # :66, :252-253
+        Xs[:, i] = -(jac_x(xi, ut, tf, const, include_J2, dr) @ xi + Bs[i] @ ut)       # :67, :232-235
     Pinv = np.linalg.inv(Phi_all)                                                      # :69
     Bn_int = Pinv @ (Bs * lam_n[:, None, None])
     Bp_int = Pinv @ (Bs * lam_p[:, None, None])

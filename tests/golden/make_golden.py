@@ -46,6 +46,59 @@ def disc(const, x, u, tf, uniform, J2=False, steps=101, ks=None):
             np.column_stack([r[3] for r in res]), np.column_stack([r[4] for r in res]))
 
 
+def disc_drag(const, x, u, tf, uniform, rho_n, J2=False, ks=None):
+    """Discretizer with the drag branch enabled (linearize_discretize.py:160-169).  The shipped reference cannot
+    reach it with its defaults (rho_func=None, Constants has no CD) but runs it once the caller supplies what the
+    branch reads: const.CD, rho_func, drho_func.  Constant density, as Simulator.get_atmo_density (simulator.py:112)."""
+    d = R.Discretizer(const, rho_func=lambda r: rho_n, drho_func=lambda r: 0.0, include_drag=True, include_J2=J2)
+    d.use_uniform_steps = uniform
+    K = x.shape[1]
+    d._Discretizer__tau = np.linspace(0, 1, K)
+    d._Discretizer__u = u
+    opts = dict(use_uniform_steps=uniform, integrator_steps=d.integrator_steps, ivp_max_step=d.ivp_max_step,
+                ivp_solver=d.ivp_solver)
+    funcs = dict(dPhi_gen=d.dPhi_gen, f=F, u_func=d.u_func, B_func=d.B_func, Sigma_func=d.Sigma_func, xi_func=d.xi_func)
+    res = [R.get_matrices(opts, funcs, tf, d._Discretizer__tau, x, k) for k in ks]
+    return (np.stack([r[0] for r in res]), np.stack([r[1] for r in res]), np.stack([r[2] for r in res]),
+            np.column_stack([r[3] for r in res]), np.column_stack([r[4] for r in res]))
+
+
+def drag_fixtures():
+    """tests/golden/discretize_drag.npz: tangential-thrust trajectory flown WITH drag, discretized with drag.
+    g0: the physical parameters (S as scaled by SatelliteScale, C_D 2.5, 500 km density);
+    g1: S x 1e4 (drag ~4e-4 of gravity, so that every drag term is well above the parity tolerance) + J2, and an
+        A-side density 1.7x the one the dynamics use (the two are independent inputs of the reference)."""
+    import constants as ref_constants
+    import simulator as ref_simulator
+    sat = R.Satellite(R_INIT, V_INIT, M_INIT)
+    scale = R.SatelliteScale(sat=sat)
+    c = R.ConstantTangentialThrustController([sat], 0.5)
+    g = {}
+    for tag, s_mult, rho_mult, J2 in (("g0", 1.0, 1.0, False), ("g1", 1e4, 1.7, True)):
+        const = scale.get_normalized_constants()
+        const.S = const.S * s_mult
+        const.CD = ref_constants.C_D
+        rho_n = ref_simulator.Simulator.get_atmo_density(np.array([1.0, 0.0, 0.0]), const.R0) / const.RHO * rho_mult
+        sim = R.Simulator(sats=[R.Satellite(R_INIT, V_INIT, M_INIT)], controller=c, scale=scale, base_res=40,
+                          include_drag=True, include_J2=J2)
+        # the simulator asks its scale for the constants on every call: hand it the modified bag
+        scale_mod = type("ScaleWithS", (), {"get_normalized_constants": lambda self: const,
+                                            "normalize_state": scale.normalize_state,
+                                            "redim_state": scale.redim_state})()
+        sim.scale = scale_mod
+        sim.run(tf=1)
+        sid = sim.sats[0].id
+        x, t = sim.sim_data[sid], sim.sim_time[sid]
+        u = R.Discretizer.extract_uk(x, t, c)
+        ks = list(range(0, x.shape[1] - 1, 3))
+        g.update({f"{tag}_x": x, f"{tag}_u": u, f"{tag}_tf": 1.0, f"{tag}_ks": np.array(ks),
+                  f"{tag}_const": const_vec(const), f"{tag}_cd": const.CD, f"{tag}_rho_n": rho_n, f"{tag}_j2": int(J2)})
+        g.update(pack(f"{tag}_uni", disc_drag(const, x, u, 1.0, True, rho_n, J2=J2, ks=ks)))
+        g.update(pack(f"{tag}_def", disc_drag(const, x, u, 1.0, False, rho_n, J2=J2, ks=ks)))
+    np.savez(os.path.join(HERE, "discretize_drag.npz"), **g)
+    print("discretize_drag.npz", os.path.getsize(os.path.join(HERE, "discretize_drag.npz")) // 1024, "KiB")
+
+
 def pack(prefix, out):
     names = ["A_k", "B_kp", "B_kn", "Sigma_k", "xi_k"]
     return {f"{prefix}_{n}": o for n, o in zip(names, out)}
@@ -191,5 +244,7 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "drag":
+    drag_fixtures()
+elif __name__ == "__main__":
     main()

@@ -208,3 +208,38 @@ def test_py_oracle_constraint_terms_vs_reference(tag):
         assert np.isnan(out["ubar_hat"]).all()
     else:
         assert (out["ubar_hat"] == 0).all()
+
+
+@pytest.mark.parametrize("tag", ["g0", "g1"])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_py_oracle_drag_branch_vs_reference(tag, uniform):
+    """Discretizer(include_drag=True) of the unmodified reference with const.CD / rho_func / drho_func supplied
+    (linearize_discretize.py:160-169; fixtures: make_golden.py drag).  g1 has S x 1e4 + J2: drag is 3e-4 of the answer."""
+    g = np.load(os.path.join(GOLDEN, "discretize_drag.npz"))
+    c = O.OracleConstants(*g[tag + "_const"])
+    mode = "uni" if uniform else "def"
+    for n, k in enumerate(g[tag + "_ks"][:4]):
+        out = O.interval_matrices(int(k), g[tag + "_x"], g[tag + "_u"], 1.0, c, include_J2=bool(g[tag + "_j2"]),
+                                  use_uniform_steps=uniform, drag=(float(g[tag + "_cd"]), float(g[tag + "_rho_n"])))
+        ref = [g[f"{tag}_{mode}_{nm}"] for nm in NAMES]
+        got_ref = (ref[0][n], ref[1][n], ref[2][n], ref[3][:, n], ref[4][:, n])
+        for nm, a, b in zip(NAMES, out, got_ref):
+            assert rel_err(a, b) < 1e-13, (nm, k)
+
+
+@pytest.mark.parametrize("tag", ["g0", "g1"])
+def test_c_oracle_drag_branch_vs_reference(tag):
+    """plain-C restatement with the drag branch: RK4/101-node mode vs the reference's uniform mode (1e-8), RK45 replica
+    vs the reference's default mode (1e-10)"""
+    g = np.load(os.path.join(GOLDEN, "discretize_drag.npz"))
+    c = O.OracleConstants(*g[tag + "_const"])
+    drag = (float(g[tag + "_cd"]), float(g[tag + "_rho_n"]))
+    ks = g[tag + "_ks"]
+    j2 = bool(g[tag + "_j2"])
+    out = C.discretize_batch(g[tag + "_x"][None], g[tag + "_u"][None], 1.0, c, include_J2=j2, drag=drag)
+    assert out[5].max() == 0
+    for nm, o, r in zip(NAMES, [_sel(a[0], ks) for a in out[:5]], [g[f"{tag}_uni_{n}"] for n in NAMES]):
+        assert rel_err(o, r) < TOL_UNIFORM, nm
+    out = C.discretize_batch_adaptive(g[tag + "_x"][None], g[tag + "_u"][None], 1.0, c, include_J2=j2, drag=drag)
+    for nm, o, r in zip(NAMES, [_sel(a[0], ks) for a in out[:5]], [g[f"{tag}_def_{n}"] for n in NAMES]):
+        assert rel_err(o, r) < 1e-10, nm
