@@ -57,9 +57,12 @@ extern "C" {
 typedef struct mpc_params {
     double mu, r_e, j2, g0, isp;
     double s_area, r0, rho;
-    double c_d, rho_atm;
+    double c_d, rho_atm;  /* drag of the DYNAMICS: module-level C_D and density        simulator.py:150-153 */
+    double disc_cd;       /* drag of the LINEARISATION: const.CD ...                  linearize_discretize.py:165-168 */
+    double disc_rho;      /* ... and rho_func(r) (constant density, drho_func = 0); 0, 0 = not supplied */
     int32_t include_j2;   /* Discretizer(include_J2=...) / Simulator(include_J2=...) */
-    int32_t include_drag; /* Simulator(include_drag=...); the discretizer rejects it like the reference */
+    int32_t include_drag; /* Simulator(include_drag=...); Discretizer(include_drag=...): needs disc_cd / disc_rho --
+                             without them the reference raises (rho_func is None, Constants has no CD) and so do we */
 } mpc_params;
 
 /* Controller laws the propagator can evaluate on the device (control.py). */

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libmpc_b200.so")
 SOURCES = ["mpc_b200.cu"]
-HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "propagate_kernel.cuh", "constraint_terms_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
+HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "propagate_kernel.cuh", "constraint_terms_kernel.cuh", "discretize_drag_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -33,7 +33,7 @@ E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4
 
 class MpcParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double) for n in
-                ("mu", "r_e", "j2", "g0", "isp", "s_area", "r0", "rho", "c_d", "rho_atm")] + \
+                ("mu", "r_e", "j2", "g0", "isp", "s_area", "r0", "rho", "c_d", "rho_atm", "disc_cd", "disc_rho")] + \
                [("include_j2", ctypes.c_int32), ("include_drag", ctypes.c_int32)]
 
 
@@ -151,11 +151,13 @@ def require_gpu():
         raise RuntimeError("mpconstellation_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
 
 
-def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.983e-13):
-    """Pack a reference-style Constants bag (constants.py:11-20) into the C struct."""
+def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.983e-13, disc_drag=None):
+    """Pack a reference-style Constants bag (constants.py:11-20) into the C struct.  disc_drag = (CD, rho): what the
+    discretizer's drag branch reads (const.CD, rho_func(r); linearize_discretize.py:162-168)."""
     g = lambda n, d=0.0: float(getattr(const, n, d))
+    cd_a, rho_a = (0.0, 0.0) if disc_drag is None else (float(disc_drag[0]), float(disc_drag[1]))
     return MpcParams(g("MU"), g("R_E"), g("J2"), g("G0"), g("ISP"), g("S"), g("R0", 1.0), g("RHO", 1.0),
-                     float(c_d), float(rho_atm), int(bool(include_J2)), int(bool(include_drag)))
+                     float(c_d), float(rho_atm), cd_a, rho_a, int(bool(include_J2)), int(bool(include_drag)))
 
 
 def pinned_empty(shape, dtype=np.float64):

@@ -87,7 +87,7 @@ def raise_on_status(status):
 
 
 def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_sub=100, out=None, status=None,
-                     device=0, check=True, adaptive=None):
+                     device=0, check=True, adaptive=None, disc_drag=None):
     """Discretize every interval of every satellite in one launch sequence (host arrays).
 
     x [N,7,K], u [N,3,K], tf scalar or [N]; `out` may be a preallocated (ideally pinned) [105, N*(K-1)]
@@ -96,6 +96,9 @@ def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_su
     adaptive=None: fixed-step RK4 with n_sub steps, trapezoid on the n_sub+1 step nodes (the reference's
     use_uniform_steps=True node set).  adaptive=dict(rtol=1e-3, atol=1e-6, max_step=1e-2): the reference's
     default mode, quadrature on the steps scipy's RK45 controller accepts; the result carries `.n_nodes`.
+
+    include_drag=True needs disc_drag=(CD, rho): const.CD and the (constant) value of rho_func the reference's drag
+    branch reads (linearize_discretize.py:162-168); without them the call is rejected like the reference's.
     """
     ctx = _ctx(device)
     x = _f64(x)
@@ -114,7 +117,7 @@ def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_su
         raise ValueError("out must be C-contiguous float64 [105, N*(K-1)]")
     if status is None:
         status = np.zeros(n_int, dtype=np.int32)
-    p = _lib.make_params(const, include_J2, include_drag)
+    p = _lib.make_params(const, include_J2, include_drag, disc_drag=disc_drag)
     n_nodes = None
     if Ku != K:
         ad = adaptive or {}

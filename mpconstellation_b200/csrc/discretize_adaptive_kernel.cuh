@@ -14,12 +14,18 @@
 // 7 stage matrices G_s shared by all columns, symplectic Phi^-1 at the nodes, non-uniform trapezoid panels
 // (np.trapz with x = sol.t, :77-80).  Per-thread storage in shared memory, [slot][thread]:
 //   0..55 accumulators | 56..97 Phi (buffer 0) | 98..139 Phi (buffer 1) | 140..202 G_s, d_s of the 7 stages
+//
+// DRAG = true: the drag branch of the linearisation (linearize_discretize.py:160-169, constant density; see
+// discretize_drag_kernel.cuh): the velocity block V of the Jacobian joins G and d in the stage storage (15 instead
+// of 9 slots per stage), the columns get V p_v, and the nodes use the general 6x6 solve instead of the symplectic
+// inverse.
 #pragma once
 #include "discretize_kernel.cuh"
+#include "discretize_drag_kernel.cuh"
 
 namespace mpc {
 
-constexpr int kAdSlots = 203;
+constexpr int kAdSlots = 203, kAdSlotsDrag = 245;
 constexpr int kAdPhi0 = 56, kAdPhi1 = 98, kAdGs = 140;
 
 __device__ __constant__ double kDpA[6][5] = {{0, 0, 0, 0, 0},
@@ -29,19 +35,14 @@ __device__ __constant__ double kDpA[6][5] = {{0, 0, 0, 0, 0},
                                              {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
                                              {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
 
-struct AdStage {  // one evaluation of the unscaled dynamics and its linearization
-    double k[7];  // f / tf = [v; a; mdot]
-    Sym3 g;
-    double d[3];
-    double im, iun, un;
-    double ux, uy, uz;
-};
+typedef DragEval AdStage;  // one evaluation of the unscaled dynamics and its linearization (v, gr, dragv: DRAG only)
 
-template <bool J2, bool GENU>
-__device__ __forceinline__ int ad_eval(const DiscParams &P, const double (&x)[7], double s, double tau,
-                                       const UHold<GENU> &hold, AdStage &o)
+template <bool J2, bool GENU, bool DRAG>
+__device__ __forceinline__ int ad_eval(const DiscParams &P, double kf, double ka, const double (&x)[7], double s,
+                                       double tau, const UHold<GENU> &hold, AdStage &o)
 {
     hold.at(s, tau, o.ux, o.uy, o.uz);
+    if (DRAG) return drag_eval<J2>(P, kf, ka, x, o.ux, o.uy, o.uz, o);
     double ax, ay, az;
     gravity<J2>(P, x[0], x[1], x[2], ax, ay, az, o.g);
     o.im = fast_rcp(x[6]);
@@ -64,10 +65,18 @@ __device__ __forceinline__ int ad_eval(const DiscParams &P, const double (&x)[7]
 
 #define SM(e) sm[(e) * BLOCK]
 
-template <int BLOCK>
+template <int BLOCK, bool DRAG>
 __device__ __forceinline__ void ad_store_stage(volatile double *sm, int s, const AdStage &st)
 {
-    const int b = kAdGs + s * 9;
+    const int b = kAdGs + s * (DRAG ? 15 : 9);
+    if (DRAG) {
+        SM(b + 9) = st.v.xx;
+        SM(b + 10) = st.v.xy;
+        SM(b + 11) = st.v.xz;
+        SM(b + 12) = st.v.yy;
+        SM(b + 13) = st.v.yz;
+        SM(b + 14) = st.v.zz;
+    }
     SM(b + 0) = st.g.xx;
     SM(b + 1) = st.g.xy;
     SM(b + 2) = st.g.xz;
@@ -92,25 +101,30 @@ __device__ __forceinline__ void ad_load_phi(volatile double *sm, int base, doubl
 }
 
 // node terms at (Phi in buffer `base`, state x, stage st): acc += w * integrands, lambda+ = lam
-template <int BLOCK>
+template <int BLOCK, bool DRAG>
 __device__ __forceinline__ void ad_node(volatile double *sm, int base, const DiscParams &P, const double (&x)[7],
                                         const AdStage &st, double w, double lam)
 {
     double pr[7][3], pv[7][3];
     ad_load_phi<BLOCK>(sm, base, pr, pv);
+    if (DRAG) {
+        node_accumulate_general<BLOCK>(sm, pr, pv, P, st, x, w, w * lam);
+        return;
+    }
     double grx, gry, grz;
     sym_mul(st.g, x[0], x[1], x[2], grx, gry, grz);
     node_accumulate<BLOCK>(sm, pr, pv, P, st.im, st.ux, st.uy, st.uz, st.iun, st.k[6], x[3], x[4], x[5], st.k[3],
                            st.k[4], st.k[5], grx, gry, grz, w, w * lam);
 }
 
-template <bool J2, int BLOCK, int NDST, bool GENU>
+template <bool J2, int BLOCK, int NDST, bool GENU, bool DRAG = false>
 __global__ void __launch_bounds__(BLOCK)
 discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in,
                            const double *__restrict__ tf_arr, DiscParams P, int n_sats, int K, int Ku, double rtol, double atol,
                            double max_step, DstTab dst, long long pitch, long long offset, int32_t *__restrict__ status,
-                           int32_t *__restrict__ n_nodes)
+                           int32_t *__restrict__ n_nodes, double kf = 0.0, double ka = 0.0)
 {
+    constexpr int kStage = DRAG ? 15 : 9;
     extern __shared__ double acc_smem[];
     const long long n_int = (long long)n_sats * (K - 1);
     const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
@@ -131,7 +145,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
     const double ilen = 1.0 / (t1 - t0);
 
 #pragma unroll 1
-    for (int e = 0; e < kAdSlots; ++e) SM(e) = 0.0;
+    for (int e = 0; e < (DRAG ? kAdSlotsDrag : kAdSlots); ++e) SM(e) = 0.0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) SM(kAdPhi0 + c * 6 + c) = 1.0;  // Phi(tau_k) = I   (:34)
     int cur = kAdPhi0, nxt = kAdPhi1;
@@ -139,7 +153,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
     double t = t0;
 
     AdStage st0;
-    bad |= ad_eval<J2, GENU>(P, x, 0.0, t0, hold, st0);
+    bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x, 0.0, t0, hold, st0);
     // ---- select_initial_step (common.py); f = tf * k, y0 = [I, x] ------------------------------------------
     double h_abs;
     {
@@ -156,6 +170,17 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
         // f0 of Phi = tf * A(x0) * I: column c of A.  rows 0..2 = e_{c-3} (c = 3..5), rows 3..5 = G[:,c] (c<3) / d (c=6)
         // nonzero entries: Phi_r' = I (scale s0: y0 entry is 0), Phi_v' = G (diag on s0... all y0 zeros) and d
         const double g[9] = {st0.g.xx, st0.g.xy, st0.g.xz, st0.g.xy, st0.g.yy, st0.g.yz, st0.g.xz, st0.g.yz, st0.g.zz};
+        // (DRAG) the velocity block V of A: its diagonal sits on the diagonal of Phi (y0 = 1, scale s1)
+        double v0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, vA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (DRAG) {
+            const double t_[9] = {st0.v.xx, st0.v.xy, st0.v.xz, st0.v.xy, st0.v.yy, st0.v.yz, st0.v.xz, st0.v.yz, st0.v.zz};
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                v0[i] = t_[i];
+                const double sc = (i % 4 == 0) ? s1 : s0;
+                d1sq += (tf * t_[i] / sc) * (tf * t_[i] / sc);
+            }
+        }
         d1sq += 3.0 * (tf / s0) * (tf / s0);
 #pragma unroll
         for (int i = 0; i < 9; ++i) d1sq += (tf * g[i] / s0) * (tf * g[i] / s0);
@@ -170,7 +195,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
 #pragma unroll
         for (int i = 0; i < 7; ++i) x1[i] = fma(hs0, st0.k[i], x[i]);
         AdStage stA;
-        bad |= ad_eval<J2, GENU>(P, x1, h0 * ilen, t0 + h0, hold, stA);
+        bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x1, h0 * ilen, t0 + h0, hold, stA);
         double d2sq = 0.0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
@@ -181,13 +206,18 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
         // Phi1 = I + hs0 * A0 (columns): p_r = e_c(r) + hs0 * e_{c-3}, p_v = e_{c-3}(v) + hs0 * (G0[:,c] | d0)
         // f1 = A1 Phi1: rows r: Phi1_v ; rows v: G1 Phi1_r + d1 * Phi1[6][c]
         const double g1[9] = {stA.g.xx, stA.g.xy, stA.g.xz, stA.g.xy, stA.g.yy, stA.g.yz, stA.g.xz, stA.g.yz, stA.g.zz};
+        if (DRAG) {
+            const double t_[9] = {stA.v.xx, stA.v.xy, stA.v.xz, stA.v.xy, stA.v.yy, stA.v.yz, stA.v.xz, stA.v.yz, stA.v.zz};
+#pragma unroll
+            for (int i = 0; i < 9; ++i) vA[i] = t_[i];
+        }
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
             double p1r[3], p1v[3], f0r[3], f0v[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 f0r[a] = (c == a + 3) ? 1.0 : 0.0;
-                f0v[a] = (c < 3) ? g[a * 3 + c] : ((c == 6) ? st0.d[a] : 0.0);
+                f0v[a] = (c < 3) ? g[a * 3 + c] : ((c == 6) ? st0.d[a] : v0[a * 3 + (c - 3)]);
                 p1r[a] = ((c == a) ? 1.0 : 0.0) + hs0 * f0r[a];
                 p1v[a] = ((c == a + 3) ? 1.0 : 0.0) + hs0 * f0v[a];
             }
@@ -195,6 +225,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
             for (int a = 0; a < 3; ++a) {
                 const double f1r = p1v[a];
                 double f1v = g1[a * 3 + 0] * p1r[0] + g1[a * 3 + 1] * p1r[1] + g1[a * 3 + 2] * p1r[2];
+                if (DRAG) f1v += vA[a * 3 + 0] * p1v[0] + vA[a * 3 + 1] * p1v[1] + vA[a * 3 + 2] * p1v[2];
                 if (c == 6) f1v += stA.d[a];
                 const double scr = (c == a) ? s1 : s0, scv = (c == a + 3) ? s1 : s0;
                 const double e1 = tf * (f1r - f0r[a]) / scr, e2 = tf * (f1v - f0v[a]) / scv;
@@ -229,7 +260,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
             double kx[7][7];
 #pragma unroll
             for (int i = 0; i < 7; ++i) kx[0][i] = st0.k[i];
-            ad_store_stage<BLOCK>(sm, 0, st0);
+            ad_store_stage<BLOCK, DRAG>(sm, 0, st0);
             const double cs[6] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
 #pragma unroll
             for (int s = 1; s < 6; ++s) {
@@ -242,10 +273,10 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                     xs_[i] = fma(dy, hs, x[i]);
                 }
                 AdStage sg;
-                bad |= ad_eval<J2, GENU>(P, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
+                bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
 #pragma unroll
                 for (int i = 0; i < 7; ++i) kx[s][i] = sg.k[i];
-                ad_store_stage<BLOCK>(sm, s, sg);
+                ad_store_stage<BLOCK, DRAG>(sm, s, sg);
             }
             const double bw[6] = {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
             const double ew[7] = {-71.0 / 57600, 0.0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
@@ -256,8 +287,8 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                 for (int l = 0; l < 6; ++l) dy = fma(kx[l][i], bw[l], dy);
                 xn[i] = fma(hs, dy, x[i]);
             }
-            bad |= ad_eval<J2, GENU>(P, xn, (t + h - t0) * ilen, t + h, hold, st6);
-            ad_store_stage<BLOCK>(sm, 6, st6);
+            bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xn, (t + h - t0) * ilen, t + h, hold, st6);
+            ad_store_stage<BLOCK, DRAG>(sm, 6, st6);
             double esum = 0.0;
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
@@ -300,9 +331,15 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
 #pragma unroll
                         for (int i = 0; i < 6; ++i) SM(nxt + c * 6 + i) = q[i];
                     }
-                    const int b = kAdGs + s * 9;
+                    const int b = kAdGs + s * kStage;
                     const double gxx = SM(b), gxy = SM(b + 1), gxz = SM(b + 2), gyy = SM(b + 3), gyz = SM(b + 4), gzz = SM(b + 5);
-                    const double dx = SM(b + 6) * dflag, dy_ = SM(b + 7) * dflag, dz = SM(b + 8) * dflag;
+                    double dx = SM(b + 6) * dflag, dy_ = SM(b + 7) * dflag, dz = SM(b + 8) * dflag;
+                    if (DRAG) {   // + V q_v
+                        const double vxx = SM(b + 9), vxy = SM(b + 10), vxz = SM(b + 11), vyy = SM(b + 12), vyz = SM(b + 13), vzz = SM(b + 14);
+                        dx = fma(vxz, q[5], fma(vxy, q[4], fma(vxx, q[3], dx)));
+                        dy_ = fma(vyz, q[5], fma(vyy, q[4], fma(vxy, q[3], dy_)));
+                        dz = fma(vzz, q[5], fma(vyz, q[4], fma(vxz, q[3], dz)));
+                    }
                     kr[s][0] = q[3];
                     kr[s][1] = q[4];
                     kr[s][2] = q[5];
@@ -336,8 +373,8 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
         if (fail) break;
         // ---- accepted: trapezoid panel [t, t_new] (np.trapz, x = sol.t) ------------------------------------------
         const double w = 0.5 * (t_new - t);
-        ad_node<BLOCK>(sm, cur, P, x, st0, w, (t - t0) * ilen);
-        ad_node<BLOCK>(sm, nxt, P, xn, st6, w, (t_new - t0) * ilen);
+        ad_node<BLOCK, DRAG>(sm, cur, P, x, st0, w, (t - t0) * ilen);
+        ad_node<BLOCK, DRAG>(sm, nxt, P, xn, st6, w, (t_new - t0) * ilen);
         const int tmp = cur;
         cur = nxt;
         nxt = tmp;

@@ -1,0 +1,279 @@
+// discretize_drag_kernel.cuh -- fixed-step discretization WITH the drag branch of the linearisation.
+//
+// Discretizer(include_drag=True) (linearize_discretize.py:160-169) is unreachable with the reference's defaults
+// (rho_func = None, Constants has no CD) but runs once the caller supplies const.CD, rho_func and drho_func.  This
+// kernel covers that case for a CONSTANT density (what Simulator.get_atmo_density returns, simulator.py:112; then
+// drho = 0 and Dr_aD vanishes):
+//     f   = [v; a_g (+a_J2) + u/m - (kf/m) |v| v; mdot]                 kf = 1/2 C_D S rho_atm/RHO   (simulator.py:152)
+//     Dxf = [[0 I 0],[G, V, d],[0 0 0]],   V = -(ka/m)(|v| I + v v^T/|v|),  d = -u/m^2 + (ka/m^2)|v| v,
+//                                                                       ka = 1/2 const.CD S rho_func  (:166-168)
+// The two structural shortcuts of discretize_kernel do not survive drag: the columns of Phi are no longer
+// second-order systems in position only (V multiplies the velocity part) and Phi6 is no longer symplectic.  So this
+// kernel is the plain formulation: classical RK4 on the first-order system in unscaled variables (step hs = tf h),
+// and at every node a 6x6 Gauss-Jordan solve  Phi6 Z = [Duf_v | c | Sigma6 | xi'6]  (no pivoting: Phi6 over one
+// interval is a small perturbation of [[I, tI],[tG, I]], pivots ~ 1).  One thread per interval; Phi and the state in
+// registers (the compiler may spill: this is the rarely used mode, built for correctness); accumulators and the four
+// stage linearisations in shared memory, [slot][thread].
+#pragma once
+#include "discretize_kernel.cuh"
+
+namespace mpc {
+
+constexpr int kDragStageSlots = 15;                      // G (6) V (6) d (3)
+constexpr int kDragSlots = kAccSlots + 4 * kDragStageSlots;
+
+struct DragEval {
+    double k[7];   // f / tf
+    Sym3 g, v;
+    double d[3];
+    double im, iun, un, gr[3], dragv[3];   // dragv = (ka/m) |v| v
+    double ux, uy, uz;
+};
+
+template <bool J2>
+__device__ __forceinline__ int drag_eval(const DiscParams &P, double kf, double ka, const double (&x)[7], double ux,
+                                         double uy, double uz, DragEval &o)
+{
+    double ax, ay, az;
+    gravity<J2>(P, x[0], x[1], x[2], ax, ay, az, o.g, o.gr);
+    o.ux = ux;
+    o.uy = uy;
+    o.uz = uz;
+    o.im = fast_rcp(x[6]);
+    const double tx = ux * o.im, ty = uy * o.im, tz = uz * o.im;
+    const double uu = fma(ux, ux, fma(uy, uy, uz * uz));
+    o.iun = inv_norm_guarded(uu, 4.930380657631324e-32);
+    o.un = uu * o.iun;
+    const double vv = fma(x[3], x[3], fma(x[4], x[4], x[5] * x[5]));
+    const double ivn = fast_rsqrt(vv), vn = vv * ivn;          // 1/|v|, |v|
+    const double cf = -kf * o.im * vn;                         // a_D = cf v
+    o.k[0] = x[3];
+    o.k[1] = x[4];
+    o.k[2] = x[5];
+    o.k[3] = fma(cf, x[3], ax + tx);
+    o.k[4] = fma(cf, x[4], ay + ty);
+    o.k[5] = fma(cf, x[5], az + tz);
+    o.k[6] = -o.un * P.inv_ve;
+    const double ca = ka * o.im;                               // ka/m
+    const double cvn = -ca * vn, civ = -ca * ivn;
+    o.v.xx = fma(civ * x[3], x[3], cvn);
+    o.v.yy = fma(civ * x[4], x[4], cvn);
+    o.v.zz = fma(civ * x[5], x[5], cvn);
+    o.v.xy = civ * x[3] * x[4];
+    o.v.xz = civ * x[3] * x[5];
+    o.v.yz = civ * x[4] * x[5];
+    const double cm = ca * vn;                                 // (ka/m) |v|
+    o.dragv[0] = cm * x[3];
+    o.dragv[1] = cm * x[4];
+    o.dragv[2] = cm * x[5];
+    o.d[0] = fma(o.dragv[0], o.im, -tx * o.im);
+    o.d[1] = fma(o.dragv[1], o.im, -ty * o.im);
+    o.d[2] = fma(o.dragv[2], o.im, -tz * o.im);
+    return !(x[6] > 0.0);
+}
+
+#define ACC(e) acc[(e) * BLOCK]
+
+template <int BLOCK>
+__device__ __forceinline__ void drag_store_stage(volatile double *acc, int s, const DragEval &e)
+{
+    const int b = kAccSlots + s * kDragStageSlots;
+    ACC(b + 0) = e.g.xx; ACC(b + 1) = e.g.xy; ACC(b + 2) = e.g.xz; ACC(b + 3) = e.g.yy; ACC(b + 4) = e.g.yz; ACC(b + 5) = e.g.zz;
+    ACC(b + 6) = e.v.xx; ACC(b + 7) = e.v.xy; ACC(b + 8) = e.v.xz; ACC(b + 9) = e.v.yy; ACC(b + 10) = e.v.yz; ACC(b + 11) = e.v.zz;
+    ACC(b + 12) = e.d[0]; ACC(b + 13) = e.d[1]; ACC(b + 14) = e.d[2];
+}
+
+// derivative of one column y = (pr, pv) under stage s: (pv, G pr + V pv + d * mflag)
+template <int BLOCK>
+__device__ __forceinline__ void drag_col_rhs(volatile double *acc, int s, const double (&y)[6], double mflag, double (&k)[6])
+{
+    const int b = kAccSlots + s * kDragStageSlots;
+    const Sym3 g = {ACC(b + 0), ACC(b + 1), ACC(b + 2), ACC(b + 3), ACC(b + 4), ACC(b + 5)};
+    const Sym3 v = {ACC(b + 6), ACC(b + 7), ACC(b + 8), ACC(b + 9), ACC(b + 10), ACC(b + 11)};
+    k[0] = y[3];
+    k[1] = y[4];
+    k[2] = y[5];
+    double gx, gy, gz;
+    sym_mul_add(g, y[0], y[1], y[2], ACC(b + 12) * mflag, ACC(b + 13) * mflag, ACC(b + 14) * mflag, gx, gy, gz);
+    sym_mul_add(v, y[3], y[4], y[5], gx, gy, gz, k[3], k[4], k[5]);
+}
+
+// General-inverse quadrature node (unscaled variables): acc += w * Phi^-1 [Duf, Sigma, xi'], acc1 += ws * Phi^-1 Duf.
+// Same slot layout as node_accumulate.  linearize_discretize.py:63-75.
+template <int BLOCK>
+__device__ __forceinline__ void node_accumulate_general(volatile double *acc, const double (&pr)[7][3], const double (&pv)[7][3],
+                                                     const DiscParams &P, const DragEval &e, const double (&x)[7],
+                                                     double w, double ws)
+{
+    double M[6][6], R[6][6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            M[a][c] = pr[c][a];
+            M[a + 3][c] = pv[c][a];
+        }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) R[a][j] = (a == j + 3) ? e.im : 0.0;   // Duf rows 3..5 = I/m             (:201)
+        R[a][3] = (a < 3) ? pr[6][a] : pv[6][a - 3];                        // c = Phi[0:6, 6]
+        R[a][4] = e.k[a];                                                   // Sigma = f(tf=1)                (:252-253)
+    }
+    // xi' = -(Dxf x + Duf u): the -u/m and +u/m terms cancel;  V v + d_D m = -(ka/m)|v| v
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        R[a][5] = -x[3 + a];
+        R[a + 3][5] = e.dragv[a] - e.gr[a];
+    }
+    // Gauss-Jordan without pivoting
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const double ip = 1.0 / M[p][p];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            M[p][c] *= ip;
+            R[p][c] *= ip;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            if (r == p) continue;
+            const double f = M[r][p];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                M[r][c] = fma(-f, M[p][c], M[r][c]);
+                R[r][c] = fma(-f, R[p][c], R[r][c]);
+            }
+        }
+    }
+    const double bs = -P.inv_ve * e.iun;
+    const double b[3] = {bs * e.ux, bs * e.uy, bs * e.uz};      // last row of Duf (0 under the eps guard, :208)
+    const double md = e.k[6];
+    const double mdb = (e.iun != 0.0) ? md : 0.0;               // last row of Duf u
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const double ea = -R[a][3];                             // Phi^-1[0:6, 6] = -Phi6^-1 c
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double q = fma(ea, b[j], R[a][j]);
+            ACC(a * 3 + j) = fma(w, q, ACC(a * 3 + j));
+            ACC(18 + a * 3 + j) = fma(ws, q, ACC(18 + a * 3 + j));
+        }
+        ACC(36 + a) = fma(w, fma(ea, md, R[a][4]), ACC(36 + a));
+        ACC(42 + a) = fma(w, fma(ea, -mdb, R[a][5]), ACC(42 + a));
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        ACC(48 + j) = fma(w, b[j], ACC(48 + j));
+        ACC(51 + j) = fma(ws, b[j], ACC(51 + j));
+    }
+    ACC(54) = fma(w, md, ACC(54));
+    ACC(55) = fma(-w, mdb, ACC(55));
+}
+
+template <bool J2, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+discretize_drag_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in, const double *__restrict__ tf_arr,
+                       DiscParams P, double kf, double ka, int n_sats, int K, int n_sub, DstTab dst, long long pitch,
+                       long long offset, int32_t *__restrict__ status)
+{
+    extern __shared__ double acc_smem[];
+    const long long n_int = (long long)n_sats * (K - 1);
+    const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (gid >= n_int) return;
+    volatile double *acc = acc_smem + threadIdx.x;
+    const int s = (int)(gid / (K - 1));
+    const int k = (int)(gid - (long long)s * (K - 1));
+    const double tf = tf_arr[s];
+    const double *xs = x_in + ((long long)s * 7) * K + k;
+    double x[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) x[c] = xs[(long long)c * K];
+    UHold<false> hold;
+    hold.init(u_in, s, k, K, K);
+    const double inv_n = 1.0 / (double)n_sub;
+    const double h = inv_n / (double)(K - 1);
+    const double hs = tf * h, hh = 0.5 * hs, h6 = hs * (1.0 / 6.0);
+
+    double pr[7][3], pv[7][3];
+#pragma unroll
+    for (int c = 0; c < 7; ++c)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            pr[c][a] = (c == a) ? 1.0 : 0.0;
+            pv[c][a] = (c == a + 3) ? 1.0 : 0.0;
+        }
+#pragma unroll 1
+    for (int e = 0; e < kDragSlots; ++e) ACC(e) = 0.0;
+
+    int bad = 0;
+    for (int n = 0; n <= n_sub; ++n) {
+        double ux, uy, uz;
+        hold.at((double)n * inv_n, 0.0, ux, uy, uz);
+        DragEval e1;
+        bad |= drag_eval<J2>(P, kf, ka, x, ux, uy, uz, e1);
+        {
+            const double w = (n == 0 || n == n_sub) ? 0.5 : 1.0;
+            node_accumulate_general<BLOCK>(acc, pr, pv, P, e1, x, w, w * ((double)n * inv_n));
+        }
+        if (n == n_sub) break;
+        drag_store_stage<BLOCK>(acc, 0, e1);
+        // ---- state: classical RK4 on the first-order system ------------------------------------------------
+        double xt[7], ksum[7];
+        double umx, umy, umz, uex, uey, uez;
+        hold.at(((double)n + 0.5) * inv_n, 0.0, umx, umy, umz);
+        hold.at((double)(n + 1) * inv_n, 0.0, uex, uey, uez);
+        DragEval es;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            ksum[i] = e1.k[i];
+            xt[i] = fma(hh, e1.k[i], x[i]);
+        }
+        bad |= drag_eval<J2>(P, kf, ka, xt, umx, umy, umz, es);
+        drag_store_stage<BLOCK>(acc, 1, es);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            ksum[i] = fma(2.0, es.k[i], ksum[i]);
+            xt[i] = fma(hh, es.k[i], x[i]);
+        }
+        bad |= drag_eval<J2>(P, kf, ka, xt, umx, umy, umz, es);
+        drag_store_stage<BLOCK>(acc, 2, es);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            ksum[i] = fma(2.0, es.k[i], ksum[i]);
+            xt[i] = fma(hs, es.k[i], x[i]);
+        }
+        bad |= drag_eval<J2>(P, kf, ka, xt, uex, uey, uez, es);
+        drag_store_stage<BLOCK>(acc, 3, es);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = fma(h6, ksum[i] + es.k[i], x[i]);
+        // ---- columns of Phi ----------------------------------------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const double mflag = (c == 6) ? 1.0 : 0.0;
+            double y[6] = {pr[c][0], pr[c][1], pr[c][2], pv[c][0], pv[c][1], pv[c][2]};
+            double k1[6], k2[6], k3[6], k4[6], yt[6];
+            drag_col_rhs<BLOCK>(acc, 0, y, mflag, k1);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) yt[i] = fma(hh, k1[i], y[i]);
+            drag_col_rhs<BLOCK>(acc, 1, yt, mflag, k2);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) yt[i] = fma(hh, k2[i], y[i]);
+            drag_col_rhs<BLOCK>(acc, 2, yt, mflag, k3);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) yt[i] = fma(hs, k3[i], y[i]);
+            drag_col_rhs<BLOCK>(acc, 3, yt, mflag, k4);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                pr[c][i] = fma(h6, (k1[i] + k4[i]) + 2.0 * (k2[i] + k3[i]), y[i]);
+                pv[c][i] = fma(h6, (k1[3 + i] + k4[3 + i]) + 2.0 * (k2[3 + i] + k3[3 + i]), y[3 + i]);
+            }
+        }
+    }
+    // B and xi carry tf (tf h = hs), Sigma does not (h)                               (:77-80, :182, :214, :252)
+    const int nonfinite = epilogue_store<BLOCK, 1>(acc, pr, pv, hs, h, hs, dst, pitch, offset + gid);
+    if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : 0);
+}
+#undef ACC
+
+}  // namespace mpc

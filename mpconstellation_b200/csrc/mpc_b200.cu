@@ -17,6 +17,7 @@
 #include "discretize_adaptive_kernel.cuh"
 #include "propagate_kernel.cuh"
 #include "constraint_terms_kernel.cuh"
+#include "discretize_drag_kernel.cuh"
 
 namespace {
 
@@ -139,6 +140,8 @@ int launch_disc(const double *x, const double *u, const double *tf, const mpc::D
 struct AdaptiveOpts {   // scipy solve_ivp(RK45) controls of the reference's default quadrature mode
     double rtol, atol, max_step;
     int32_t *n_nodes;
+    int drag = 0;           // drag branch of the linearisation (set from mpc_params by with_drag)
+    double kf = 0.0, ka = 0.0;
 };
 
 template <bool J2, bool GENU>
@@ -155,14 +158,14 @@ int launch_adaptive(const double *x, const double *u, const double *tf, const mp
                        : launch_adaptive_g<J2, false>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
 }
 
-template <bool J2, bool GENU>
-int launch_adaptive_g(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+template <bool J2, bool GENU, bool DRAG>
+int launch_adaptive_k(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                       const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
                       cudaStream_t st)
 {
     constexpr int BLOCK = 32;
-    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1, GENU>;
-    const size_t smem = (size_t)mpc::kAdSlots * BLOCK * sizeof(double);
+    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1, GENU, DRAG>;
+    const size_t smem = (size_t)(DRAG ? mpc::kAdSlotsDrag : mpc::kAdSlots) * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -174,10 +177,29 @@ int launch_adaptive_g(const double *x, const double *u, const double *tf, const 
     const long long n_int = (long long)n_sats * (K - 1);
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
     kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, g_ucols, o.rtol, o.atol, o.max_step, dst, pitch, offset,
-                                    status, o.n_nodes);
+                                    status, o.n_nodes, o.kf, o.ka);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
+}
+
+template <bool J2, bool GENU>
+int launch_adaptive_g(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                      const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                      cudaStream_t st)
+{
+    if (o.drag) {
+        if (GENU) return fail(MPC_E_UNSUPPORTED, "include_drag with u on its own grid is not supported");
+        return launch_adaptive_k<J2, false, true>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+    }
+    return launch_adaptive_k<J2, GENU, false>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+}
+
+void with_drag(AdaptiveOpts &o, const mpc_params *p)
+{
+    o.drag = p->include_drag;
+    o.kf = p->include_drag ? 0.5 * p->c_d * p->s_area * (p->rho_atm / p->rho) : 0.0;
+    o.ka = p->include_drag ? 0.5 * p->disc_cd * p->s_area * p->disc_rho : 0.0;
 }
 
 int check_adaptive(double rtol, double atol, double max_step)
@@ -192,11 +214,53 @@ int check_disc_args(const void *x, const void *u, const void *tf, const mpc_para
     if (!x || !u || !tf || !p) return fail(MPC_E_INVALID, "null pointer argument");
     if (n_sats < 0 || K < 2 || n_sub < 1)
         return fail(MPC_E_INVALID, "need n_sats >= 0, K >= 2, n_sub >= 1 (got %d, %d, %d)", n_sats, K, n_sub);
-    if (p->include_drag)
-        // the reference's drag linearisation needs const.CD and a rho_func it never provides
-        // (linearize_discretize.py:162-169): it raises; so do we
-        return fail(MPC_E_UNSUPPORTED, "include_drag is not supported by the discretizer (the reference raises too)");
+    if (p->include_drag && !(p->disc_cd > 0.0 && p->disc_rho >= 0.0))
+        // the reference's drag linearisation needs const.CD and a rho_func (linearize_discretize.py:162-169); with
+        // its defaults (no CD attribute, rho_func = None) it raises; so do we when they are not supplied
+        return fail(MPC_E_UNSUPPORTED, "include_drag needs disc_cd / disc_rho (const.CD, rho_func): the reference raises without them too");
     return MPC_SUCCESS;
+}
+
+// drag branch of the linearisation: coefficients of the dynamics (kf) and of the Jacobian (ka)
+double drag_kf(const mpc_params *p) { return 0.5 * p->c_d * p->s_area * (p->rho_atm / p->rho); }
+double drag_ka(const mpc_params *p) { return 0.5 * p->disc_cd * p->s_area * p->disc_rho; }
+
+template <bool J2>
+int launch_disc_drag(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, double kf, double ka,
+                     int n_sats, int K, int n_sub, const mpc::DstTab &dst, long long pitch, long long offset,
+                     int32_t *status, cudaStream_t st)
+{
+    constexpr int BLOCK = 64;
+    auto kern = mpc::discretize_drag_kernel<J2, BLOCK>;
+    const size_t smem = (size_t)mpc::kDragSlots * BLOCK * sizeof(double);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured_dev = dev;
+    }
+    const long long n_int = (long long)n_sats * (K - 1);
+    const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, kf, ka, n_sats, K, n_sub, dst, pitch, offset, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
+// one chunk of a fixed-step discretization on stream st: plain or drag kernel
+int launch_fixed(const double *x, const double *u, const double *tf, const mpc_params *p, const mpc::DiscParams &P,
+                 int n_sats, int K, int n_sub, const mpc::DstTab &tab, long long pitch, long long offset, int32_t *status,
+                 cudaStream_t st)
+{
+    if (p->include_drag) {
+        if (g_ucols > 0) return fail(MPC_E_UNSUPPORTED, "include_drag with u on its own grid is not supported");
+        return p->include_j2 ? launch_disc_drag<true>(x, u, tf, P, drag_kf(p), drag_ka(p), n_sats, K, n_sub, tab, pitch, offset, status, st)
+                             : launch_disc_drag<false>(x, u, tf, P, drag_kf(p), drag_ka(p), n_sats, K, n_sub, tab, pitch, offset, status, st);
+    }
+    return p->include_j2 ? launch_disc_n<true, 1>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, st)
+                         : launch_disc_n<false, 1>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, st);
 }
 
 int disc_device(const double *x, const double *u, const double *tf, const mpc_params *p, int n_sats, int K,
@@ -223,6 +287,10 @@ int disc_device(const double *x, const double *u, const double *tf, const mpc_pa
     for (int d = 0; d < n_dst; ++d)
         if (!tab.p[d]) return fail(MPC_E_INVALID, "null destination %d", d);
     const mpc::DiscParams P = disc_params(p);
+    if (p->include_drag) {
+        if (n_dst != 1) return fail(MPC_E_UNSUPPORTED, "include_drag with several destinations is not supported");
+        return launch_fixed(x, u, tf, p, P, n_sats, K, n_sub, tab, pitch, offset, status, st);
+    }
     return p->include_j2 ? launch_disc<true>(x, u, tf, P, n_sats, K, n_sub, tab, n_dst, pitch, offset, status, st)
                          : launch_disc<false>(x, u, tf, P, n_sats, K, n_sub, tab, n_dst, pitch, offset, status, st);
 }
@@ -459,7 +527,8 @@ int mpc_discretize_batch_adaptive(const double *x, const double *u, const double
     if (n_int == 0) return MPC_SUCCESS;
     mpc::DstTab tab{};
     tab.p[0] = out;
-    const AdaptiveOpts o{rtol, atol, max_step, n_nodes};
+    AdaptiveOpts o{rtol, atol, max_step, n_nodes};
+    with_drag(o, p);
     const mpc::DiscParams P = disc_params(p);
     return p->include_j2 ? launch_adaptive<true>(x, u, tf, P, n_sats, K, o, tab, out_pitch, out_offset, status, (cudaStream_t)stream)
                          : launch_adaptive<false>(x, u, tf, P, n_sats, K, o, tab, out_pitch, out_offset, status, (cudaStream_t)stream);
@@ -582,12 +651,12 @@ static int disc_host(mpc_ctx *ctx, const double *x, const double *u, const doubl
         const long long off = (long long)s0 * (K - 1);
         if (ad) {
             AdaptiveOpts o = *ad;
+            with_drag(o, p);
             o.n_nodes = n_nodes_host ? ctx->d_nodes + off : nullptr;
             rc = p->include_j2 ? launch_adaptive<true>(dx, du, ctx->d_tf + s0, P, ns, K, o, tab, n_int, off, ctx->d_status + off, ctx->s_compute)
                                : launch_adaptive<false>(dx, du, ctx->d_tf + s0, P, ns, K, o, tab, n_int, off, ctx->d_status + off, ctx->s_compute);
         } else {
-            rc = p->include_j2 ? launch_disc_n<true, 1>(dx, du, ctx->d_tf + s0, P, ns, K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute)
-                               : launch_disc_n<false, 1>(dx, du, ctx->d_tf + s0, P, ns, K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute);
+            rc = launch_fixed(dx, du, ctx->d_tf + s0, p, P, ns, K, n_sub, tab, n_int, off, ctx->d_status + off, ctx->s_compute);
         }
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ctx->ev[c], ctx->s_compute));
@@ -689,7 +758,8 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
     if (!ctx || !y0 || !tf || !p_prop || !p_disc || !out_host) return fail(MPC_E_INVALID, "null pointer argument");
     const int K = T;
     if (n_sats < 0 || K < 2 || n_sub_prop < 1 || n_sub_disc < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 2, n_sub >= 1");
-    if (p_disc->include_drag) return fail(MPC_E_UNSUPPORTED, "include_drag is not supported by the discretizer (the reference raises too)");
+    if (p_disc->include_drag && !(p_disc->disc_cd > 0.0 && p_disc->disc_rho >= 0.0))
+        return fail(MPC_E_UNSUPPORTED, "include_drag needs disc_cd / disc_rho (const.CD, rho_func): the reference raises without them too");
     int rc = check_ctrl(ctrl);
     if (rc) return rc;
     if (n_sats == 0) return MPC_SUCCESS;
@@ -727,11 +797,8 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
         mpc::DstTab tab{};
         tab.p[0] = ctx->d_out;
         const long long off = (long long)s0 * (K - 1);
-        rc = p_disc->include_j2
-                 ? launch_disc_n<true, 1>(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, P, ns,
-                                          K, n_sub_disc, tab, n_int, off, ctx->d_status + off, st)
-                 : launch_disc_n<false, 1>(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, P,
-                                           ns, K, n_sub_disc, tab, n_int, off, ctx->d_status + off, st);
+        rc = launch_fixed(ctx->d_x + (size_t)s0 * 7 * K, ctx->d_u + (size_t)s0 * 3 * K, ctx->d_tf + s0, p_disc, P, ns, K,
+                          n_sub_disc, tab, n_int, off, ctx->d_status + off, st);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ctx->ev[c], st));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev[c], 0));
@@ -777,6 +844,7 @@ int mpc_discretize_batch_push(mpc_ctx *ctx, const double *x, const double *u, co
     if (!ctx) return fail(MPC_E_INVALID, "null ctx");
     int rc = check_disc_args(x, u, tf, p, n_sats, K, n_sub);
     if (rc) return rc;
+    if (p->include_drag) return fail(MPC_E_UNSUPPORTED, "include_drag is not supported by the push gather");
     if (!dst || n_dst < 1 || n_dst > MPC_MAX_DST) return fail(MPC_E_INVALID, "bad destination list");
     for (int d = 0; d < n_dst; ++d)
         if (!dst[d]) return fail(MPC_E_INVALID, "null destination %d", d);

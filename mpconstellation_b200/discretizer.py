@@ -45,12 +45,30 @@ class Discretizer:
                 raise TypeError("'NoneType' object is not callable")
             if not hasattr(self.const, "CD"):
                 raise AttributeError("'Constants' object has no attribute 'CD'")
-            raise NotImplementedError("drag linearization is not available in the GPU discretizer")
+            if self.drho_func is None:
+                raise TypeError("'NoneType' object is not callable")
         if self.ivp_solver != 'RK45':
             raise NotImplementedError(f"ivp_solver={self.ivp_solver!r}: the device integrator is fixed-step RK4 "
                                       "on the reference's node grid (stated against RK45)")
         if self.use_uniform_steps and int(self.integrator_steps) < 2:
             raise ValueError("integrator_steps must be >= 2")
+
+    def _disc_drag(self, x):
+        """(CD, rho) for the device, or None.  The drag branch (linearize_discretize.py:160-169) calls rho_func(r) and
+        drho_func(r) at every state; the kernels implement a CONSTANT density (what Simulator.get_atmo_density
+        returns, simulator.py:112), so both callables are sampled on the reference trajectory and anything else is
+        rejected loudly -- there is no CPU fallback."""
+        if not self.include_drag:
+            return None
+        pos = np.moveaxis(x[:, 0:3, :], 1, 2).reshape(-1, 3)
+        if pos.shape[0] > 64:
+            pos = pos[np.linspace(0, pos.shape[0] - 1, 64).astype(int)]
+        rho = np.array([float(self.rho_func(r)) for r in pos])
+        drho = np.array([float(np.max(np.abs(self.drho_func(r)))) for r in pos])
+        if rho.size and (np.ptp(rho) != 0.0 or np.any(drho != 0.0)):
+            raise NotImplementedError("the GPU discretizer linearizes drag for a constant density only "
+                                      "(rho_func constant, drho_func zero along the trajectory)")
+        return float(self.const.CD), float(rho[0]) if rho.size else 0.0
 
     # -- the reference entry point -------------------------------------------------------------------
     def discretize(self, f, x, u, tf):
@@ -78,7 +96,8 @@ class Discretizer:
         # use_uniform_steps=True: fixed-step RK4 on the uniform integrator_steps grid.
         adaptive = None if self.use_uniform_steps else dict(rtol=self.ivp_rtol, atol=self.ivp_atol,
                                                             max_step=float(self.ivp_max_step))
-        return batch.discretize_batch(x, u, tf, self.const, include_J2=self.include_J2, include_drag=False,
+        return batch.discretize_batch(x, u, tf, self.const, include_J2=self.include_J2,
+                                      include_drag=bool(self.include_drag), disc_drag=self._disc_drag(x),
                                       n_sub=max(1, int(self.integrator_steps) - 1), out=out, device=self.device,
                                       check=check, adaptive=adaptive)
 

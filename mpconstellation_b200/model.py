@@ -20,9 +20,9 @@ RHO_ATMO = 9.983e-13        # kg / m^3, the constant the reference's density mod
 
 
 class Constants:
-    """Bag of (normalized) constants handed to the dynamics."""
-
-    __slots__ = ("MU", "R_E", "J2", "G0", "ISP", "S", "R0", "RHO")
+    """Bag of (normalized) constants handed to the dynamics (constants.py:11-20).  A plain class like the reference's:
+    callers may add attributes -- Discretizer(include_drag=True) reads `const.CD` (linearize_discretize.py:165-168),
+    which the reference's own Constants never sets."""
 
     def __init__(self, MU, R_E, J2, G0, ISP, S, R0, RHO):
         self.MU, self.R_E, self.J2, self.G0 = MU, R_E, J2, G0

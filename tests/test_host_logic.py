@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.MpcParams) == 10 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.MpcParams) == 12 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.MpcController) == 4 * 4 + 3 * 8 + 8 + 8 + 8
     assert _lib.MpcController.table.offset == 48
 
@@ -120,6 +120,15 @@ def test_discretizer_option_errors_mirror_reference():
     d = M.Discretizer(const, include_drag=True)
     with pytest.raises(TypeError):                       # reference: 'NoneType' object is not callable
         d.discretize(f, x, u, 1.0)
+    d = M.Discretizer(const, rho_func=lambda r: 1.0, drho_func=lambda r: 0.0, include_drag=True)
+    with pytest.raises(AttributeError):                  # reference: 'Constants' object has no attribute 'CD'
+        d.discretize(f, x, u, 1.0)
+    const_cd = M.SatelliteScale().get_normalized_constants()
+    const_cd.CD = 2.5
+    d = M.Discretizer(const_cd, rho_func=lambda r: float(np.linalg.norm(r)), drho_func=lambda r: 0.0, include_drag=True)
+    xv = np.ones((7, 3)) * np.array([1.0, 2.0, 3.0])
+    with pytest.raises(NotImplementedError, match="constant density"):      # a density profile cannot run on the device
+        d.discretize(f, xv, u, 1.0)
     d = M.Discretizer(const)
     with pytest.raises(NotImplementedError):
         d.discretize(lambda *a, **k: None, x, u, 1.0)
