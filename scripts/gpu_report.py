@@ -16,6 +16,24 @@ for sc in ("d0", "d1", "d2", "d3", "d4"):
         d = M.Discretizer(const); d.use_uniform_steps = uni
         out = d.discretize(M.Simulator.satellite_dynamics, g[sc + "_x"], g[sc + "_u"], float(g[sc + "_tf"]))
         print(f"  {sc} K={g[sc+'_x'].shape[1]:3d} use_uniform_steps={uni!s:5}: " + "  ".join(f"{n} {norm_rel_err(o, g[f'{sc}_{mode}_{n}']):.1e}" for n, o in zip(NAMES, out)))
+gd = np.load(os.path.join(ROOT, "tests/golden/discretize_drag.npz"))
+for tag in ("g0", "g1"):
+    cv = OracleConstants(*gd[tag + "_const"])
+    bag = type("Const", (), {k: getattr(cv, k) for k in ("MU", "R_E", "J2", "G0", "ISP", "S", "R0", "RHO")})()
+    bag.CD = float(gd[tag + "_cd"]); rho_n = float(gd[tag + "_rho_n"]); ks = gd[tag + "_ks"]
+    for mode, uni in (("uni", True), ("def", False)):
+        d = M.Discretizer(bag, rho_func=lambda r: rho_n, drho_func=lambda r: 0.0, include_drag=True, include_J2=bool(gd[tag + "_j2"]))
+        d.use_uniform_steps = uni
+        out = d.discretize(M.Simulator.satellite_dynamics, gd[tag + "_x"], gd[tag + "_u"], 1.0)
+        sel = [o[ks] if o.ndim == 3 else o[:, ks] for o in out]
+        print(f"  {tag} include_drag=True (S x{1 if tag == 'g0' else 10000}) use_uniform_steps={uni!s:5}: " + "  ".join(f"{n} {norm_rel_err(o, gd[f'{tag}_{mode}_{n}']):.1e}" for n, o in zip(NAMES, sel)))
+gc = np.load(os.path.join(ROOT, "tests/golden/constraint_terms.npz"))
+for tag in ("c0", "c1"):
+    cm = type("Const", (), {"MU": float(gc["MU"])})()
+    ct = M.get_constraint_terms([gc[tag + "_x"]], [gc[tag + "_u"]], cm)
+    worst = max(float(np.max(np.abs(np.asarray(ct[k][0]) - gc[f"{tag}_{k}"])) / max(1.0, float(np.max(np.abs(gc[f"{tag}_{k}"])))))
+                for k in ct if k != "ubar_hat")
+    print(f"  {tag} get_constraint_terms: max scaled error over all terms {worst:.1e}")
 dev = torch.device("cuda:0")
 ctrl = M.ConstantTangentialThrustController(tangential_thrust=0.5)
 print("== kernel times (device-resident, CUDA events, best of 5)")
@@ -36,5 +54,19 @@ for name, N, K, tf in (("config 1", 1, 50, 0.5), ("config 2", 64, 100, 1.0), ("c
     nn = torch.zeros(N * (K - 1), dtype=torch.int32, device=dev)
     ta = best(lambda: M.discretize_batch_device(y, u, tfd, c2, adaptive=dict(), n_nodes=nn))
     n_int = N * (K - 1)
+    if N == 4096:
+        import ctypes
+        from mpconstellation_b200 import _lib
+        o2 = torch.empty((105, n_int), dtype=torch.float64, device=dev); st2 = torch.empty(n_int, dtype=torch.int32, device=dev)
+        pd = _lib.make_params(c2, False, True, disc_drag=(2.5, 27123.37))
+        sm_ = torch.cuda.current_stream(dev).cuda_stream
+        tdg = best(lambda: _lib.check(_lib.lib().mpc_discretize_batch(y.data_ptr(), u.data_ptr(), tfd.data_ptr(), ctypes.byref(pd), N, K, 100, o2.data_ptr(), n_int, 0, st2.data_ptr(), sm_)))
+        tda = best(lambda: _lib.check(_lib.lib().mpc_discretize_batch_adaptive(y.data_ptr(), u.data_ptr(), tfd.data_ptr(), ctypes.byref(pd), N, K, 1e-3, 1e-6, 1e-2, o2.data_ptr(), n_int, 0, st2.data_ptr(), None, sm_)))
+        from mpconstellation_b200.constraints import constraint_terms_device, dynamics_jacobian_device
+        tct = best(lambda: constraint_terms_device(y, u, c2))
+        full, _ = M.discretize_batch_device(y, u, tfd, c2)
+        tjac = best(lambda: dynamics_jacobian_device(full, N, K))
+        print(f"  {name}: with the drag branch of the linearisation: uniform-101 {tdg:.3f} ms, default/adaptive {tda:.3f} ms | "
+              f"constraint terms {tct:.3f} ms | sparse dynamics Jacobian ({N*7*(K-1)*16*8/1e6:.0f} MB of values) {tjac:.3f} ms")
     print(f"  {name}: {N} sats x K={K} ({n_int} intervals): propagate {tp:.3f} ms (drag+J2 {tpd:.3f}) | discretize uniform-101 {tu:.3f} ms "
           f"({n_int/tu*1e3:.3e}/s), J2 {tj:.3f} ms | default/adaptive {ta:.3f} ms ({n_int/ta*1e3:.3e}/s, nodes {int(nn.min())}-{int(nn.max())})")
