@@ -392,7 +392,9 @@ def gpu_arm(args):
                 "host_cpus_rank0": len(cpus),
                 "matches_device_path": same},
         "gather": {"mode": gather_mode + (":" + args.fused_mode if fused is not None else ""), "verified": gathered_ok,
-                   "bytes_received_per_rank_per_step": int((world - 1) * n_int * 105 * 8)} if world > 1 else None,
+                   "bytes_received_per_rank_per_step": int((world - 1) * n_int * 8 * (98 if fused is not None and fused.skip_const else 105)),
+                   "note": "rows 42..48 of the SoA result (last row of A_k, constants) are written once by the owner and never sent"
+                           if fused is not None and fused.skip_const else None} if world > 1 else None,
         "gpu_launches": int(launches),
         "kernel": {"discretize_ms": disc_ms_avg, "propagate_ms": ms_per_step - disc_ms_avg if world == 1 else None,
                    "discretize_intervals_per_s_per_gpu": n_int / (disc_ms_avg * 1e-3),
