@@ -191,3 +191,53 @@ def test_save_to_csv_wire_format(tmp_path, gold_prop):
         back = np.loadtxt(path, delimiter=",")
         want = scale.redim_state(traj).T if redim else traj.T
         assert np.array_equal(back, want)
+
+
+def test_final_term_layout_matches_header_and_reference_keys():
+    """_lib.FINAL_TERM_LAYOUT <-> MPC_FT_* in include/mpc_b200.h <-> the keys of Optimizer.get_constraint_terms"""
+    from mpconstellation_b200 import constraints
+    text = open(os.path.join(ROOT, "include", "mpc_b200.h")).read()
+    defs = dict(re.findall(r"#define MPC_FT_([A-Z_]+) (\d+)", text))
+    want = {"rf_hat": "RF_HAT", "Vc": "VC", "DrVc": "DRVC", "DrVc_rbar": "DRVC_RBAR", "Vt": "VT", "DrVt_DvVt": "DRVT_DVVT",
+            "DrVt_DvVt_bar": "DRVT_DVVT_BAR", "Vr": "VR", "DrVr_DvVr": "DRVR_DVVR", "DrVr_DvVr_bar": "DRVR_DVVR_BAR",
+            "Vn": "VN", "DrVn_DvVn": "DRVN_DVVN", "DrVn_DvVn_bar": "DRVN_DVVN_BAR"}
+    assert set(want) == set(_lib.FINAL_TERM_LAYOUT) and set(want) | {"rbar_hat", "ubar_hat"} == set(constraints.KEYS)
+    for key, (off, ln) in _lib.FINAL_TERM_LAYOUT.items():
+        assert int(defs[want[key]]) == off
+    spans = sorted((off, max(ln, 1)) for off, ln in _lib.FINAL_TERM_LAYOUT.values())
+    assert spans[0][0] == 0 and all(a + n == b for (a, n), (b, _) in zip(spans, spans[1:]))
+    assert spans[-1][0] + spans[-1][1] == _lib.FINAL_TERMS == int(re.search(r"#define MPC_FINAL_TERMS (\d+)", text).group(1))
+
+
+def test_dynamics_jacobian_container_against_a_dense_restatement():
+    """DynamicsJacobian (host container of mpc_dynamics_jacobian's CSR): pack / residual / to_scipy on synthetic
+    values laid out exactly as the kernel documents them (include/mpc_b200.h), against the pyomo rule written densely"""
+    from mpconstellation_b200.constraints import DynamicsJacobian
+    N, K = 2, 4
+    rng = np.random.default_rng(1)
+    A, Bn, Bp = rng.standard_normal((N, K - 1, 7, 7)), rng.standard_normal((N, K - 1, 7, 3)), rng.standard_normal((N, K - 1, 7, 3))
+    Sg, Xi = rng.standard_normal((N, 7, K - 1)), rng.standard_normal((N, 7, K - 1))
+    rows = N * 7 * (K - 1)
+    vals, idx, rhs = np.zeros((rows, 16)), np.zeros((rows, 16), dtype=np.int64), np.zeros(rows)
+    NK = N * K
+    for s in range(N):
+        for i in range(7):
+            for k in range(K - 1):
+                r = (s * 7 + i) * (K - 1) + k
+                ent = [((s * 7 + j) * K + k, -A[s, k, i, j]) for j in range(7)] + [((s * 7 + i) * K + k + 1, 1.0)]
+                ent += [(7 * NK + (s * 3 + j) * K + k, -Bn[s, k, i, j]) for j in range(3)]
+                ent += [(7 * NK + (s * 3 + j) * K + k + 1, -Bp[s, k, i, j]) for j in range(3)]
+                ent += [(10 * NK + (s * 7 + i) * K + k, -1.0), (17 * NK, -Sg[s, i, k])]
+                ent.sort()
+                idx[r], vals[r], rhs[r] = [e[0] for e in ent], [e[1] for e in ent], Xi[s, i, k]
+    jac = DynamicsJacobian(vals.ravel(), idx.ravel(), rhs, N, K)
+    x, u, nu, tf = rng.standard_normal((N, 7, K)), rng.standard_normal((N, 3, K)), rng.standard_normal((N, 7, K)), 1.3
+    res = jac.residual(jac.pack(x, u, nu, tf))
+    for s in range(N):
+        for k in range(K - 1):
+            want = x[s, :, k + 1] - (A[s, k] @ x[s, :, k] + Bn[s, k] @ u[s, :, k] + Bp[s, k] @ u[s, :, k + 1]
+                                     + Sg[s, :, k] * tf + Xi[s, :, k] + nu[s, :, k])
+            assert np.allclose(res[s, :, k], want, rtol=0, atol=1e-12)
+    J = jac.to_scipy()
+    assert J.shape == (rows, 17 * NK + 1) and np.allclose(J @ jac.pack(x, u, nu, tf) - rhs, res.ravel(), atol=1e-12)
+    assert np.array_equal(jac.indptr, np.arange(rows + 1) * 16)
