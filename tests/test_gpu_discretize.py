@@ -282,3 +282,34 @@ def test_copy_engine_push_gather_on_one_gpu(M, const):
         for b in bufs[1:]:
             b[:42].fill_(float("nan"))
             b[49:].fill_(float("nan"))
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_zero_and_mixed_thrust_and_single_step(M, const, adaptive):
+    """|u| <= eps guard (linearize_discretize.py:208): coasting satellites, satellites whose thrust switches off inside
+    the horizon (thrust / no-thrust intervals side by side in one warp), and n_sub = 1; against the C oracle"""
+    from oracle import c_oracle as C
+    _, x, u = synth_batch(9, 21, 0.6, const)
+    u[0] = 0.0                                   # coasting
+    u[3, :, 10:] = 0.0                           # thrust ends at node 10: interval 9 has u_k != 0, u_k+1 == 0
+    u[5, :, ::2] = 0.0                           # every other node
+    u[7] = 1e-18                                 # below eps but not zero
+    if adaptive:
+        ref = C.discretize_batch_adaptive(x, u, 0.6, const)
+        res = M.discretize_batch(x, u, 0.6, const, adaptive=dict())
+        assert np.array_equal(res.n_nodes, ref[6])
+    else:
+        ref = C.discretize_batch(x, u, 0.6, const, n_sub=25)
+        res = M.discretize_batch(x, u, 0.6, const, n_sub=25)
+        # n_sub = 1 (two quadrature nodes): on a short horizon, where one RK4 step is accurate and the symplectic
+        # inverse of the numerical Phi equals its dense inverse to rounding (DESIGN.md, "very coarse steps")
+        r1 = C.discretize_batch(x, u, 0.004, const, n_sub=1)
+        g1 = M.discretize_batch(x, u, 0.004, const, n_sub=1)
+        for n, o, r in zip(NAMES, g1.stacked(), r1[:5]):
+            assert rel_err(o, r) < TOL_ORACLE, ("n_sub=1", n)
+    assert res.status.max() == 0 and ref[5].max() == 0
+    for n, o, r in zip(NAMES, res.stacked(), ref[:5]):
+        assert rel_err(o, r) < TOL_ORACLE, n
+    Bp, Bn = res.stacked()[1], res.stacked()[2]
+    assert not np.any(Bp[0, :, 6, :]) and not np.any(Bn[0, :, 6, :])      # coasting: no mass-flow sensitivity (row 6 of B)
+    assert not np.any(Bp[7, :, 6, :])                                     # |u| <= eps: the guard zeroes that row
