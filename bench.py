@@ -336,12 +336,13 @@ def gpu_arm(args):
     out_h = M.pinned_empty((105, n_int))
     y_h = M.pinned_empty((N, 7, K))
     u_h = M.pinned_empty((N, 3, K))
+    st_h = M.pinned_empty(n_int, np.int32)
     e2e_t = []
     for i in range(2 + max(3, args.steps // 2)):
         barrier()
         t0 = time.perf_counter()
         res, _, _ = M.propagate_discretize(y0_h, tf, ctrl, const, T=K, n_sub_prop=n_prop, n_sub_disc=n_sub, out=out_h,
-                                           y_out=y_h, u_out=u_h, device=local)
+                                           y_out=y_h, u_out=u_h, status=st_h, device=local)
         dt = time.perf_counter() - t0
         if i >= 2:
             e2e_t.append(dt)

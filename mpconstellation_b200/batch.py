@@ -209,7 +209,8 @@ def propagate_batch(y0, tf, controller, const, include_drag=True, include_J2=Tru
 
 
 def propagate_discretize(y0, tf, controller, const, T, prop_drag=False, prop_J2=False, disc_J2=False,
-                         n_sub_prop=None, n_sub_disc=100, out=None, y_out=None, u_out=None, device=0, check=True):
+                         n_sub_prop=None, n_sub_disc=100, out=None, y_out=None, u_out=None, device=0, check=True,
+                         status=None):
     """One SCP linearization pass on the device: propagate -> extract_uk -> discretize, the reference
     trajectory staying in HBM between the kernels (control.py:180-188 pattern).  K = T.
     Returns (DiscretizedBatch, y [N,7,T], u [N,3,T])."""
@@ -226,7 +227,10 @@ def propagate_discretize(y0, tf, controller, const, T, prop_drag=False, prop_J2=
         out = _lib.pinned_empty((_lib.MPC_OUT_ROWS, n_int))
     y = y_out if y_out is not None else _lib.pinned_empty((N, 7, T))
     uo = u_out if u_out is not None else _lib.pinned_empty((N, 3, T))
-    status = np.zeros(n_int, dtype=np.int32)
+    if status is None:
+        status = np.zeros(n_int, dtype=np.int32)
+    elif status.shape != (n_int,) or status.dtype != np.int32 or not status.flags["C_CONTIGUOUS"]:
+        raise ValueError("status must be C-contiguous int32 [N*(T-1)] (pinned: pinned_empty(n, np.int32))")
     pp = _lib.make_params(const, prop_J2, prop_drag)
     pd = _lib.make_params(const, disc_J2, False)
     c, _keep = _ctrl_struct(spec, N)

@@ -404,6 +404,18 @@ int ensure_stage(mpc_ctx *ctx, size_t count)
     return MPC_SUCCESS;
 }
 
+// true when p is page-locked host memory (mpc_host_alloc / cudaHostAlloc / cudaHostRegister): an async copy into it
+// does not block the enqueuing thread, so no staging is needed
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int ensure_events(mpc_ctx *ctx, size_t n)
 {
     while (ctx->ev.size() < n) {
@@ -668,14 +680,16 @@ static int disc_host(mpc_ctx *ctx, const double *x, const double *u, const doubl
     fill_const_rows(out_host, n_int);
     const bool want_nodes = ad && n_nodes_host;
     if ((rc = ensure_stage(ctx, (size_t)n_int * 2))) return rc;
-    if (status_host)
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
-    if (want_nodes)
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage + n_int, ctx->d_nodes, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+    int32_t *st_dst = status_host ? (is_pinned(status_host) ? status_host : ctx->h_stage) : nullptr;
+    int32_t *nn_dst = want_nodes ? (is_pinned(n_nodes_host) ? n_nodes_host : ctx->h_stage + n_int) : nullptr;
+    if (st_dst)
+        CUDA_TRY(cudaMemcpyAsync(st_dst, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+    if (nn_dst)
+        CUDA_TRY(cudaMemcpyAsync(nn_dst, ctx->d_nodes, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_compute));
-    if (status_host) memcpy(status_host, ctx->h_stage, (size_t)n_int * sizeof(int32_t));
-    if (want_nodes) memcpy(n_nodes_host, ctx->h_stage + n_int, (size_t)n_int * sizeof(int32_t));
+    if (st_dst && st_dst != status_host) memcpy(status_host, st_dst, (size_t)n_int * sizeof(int32_t));
+    if (nn_dst && nn_dst != n_nodes_host) memcpy(n_nodes_host, nn_dst, (size_t)n_int * sizeof(int32_t));
     return MPC_SUCCESS;
 }
 
@@ -807,13 +821,14 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
     fill_const_rows(out_host, n_int);   // host writes the structural constants while the GPU / DMA engine work
     if (status_host) {   // int32 words through pinned staging (see disc_host)
         if ((rc = ensure_stage(ctx, (size_t)n_int + n_sats))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage, ctx->d_status, (size_t)n_int * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+        CUDA_TRY(cudaMemcpyAsync(is_pinned(status_host) ? status_host : ctx->h_stage, ctx->d_status, (size_t)n_int * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, ctx->s_copy));
         CUDA_TRY(cudaMemcpyAsync(ctx->h_stage + n_int, ctx->d_status2, (size_t)n_sats * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (status_host) {
-        memcpy(status_host, ctx->h_stage, (size_t)n_int * sizeof(int32_t));
+        if (!is_pinned(status_host)) memcpy(status_host, ctx->h_stage, (size_t)n_int * sizeof(int32_t));
         // a satellite whose propagation failed poisons its intervals: surface it in the interval status
         const int32_t *ps = ctx->h_stage + n_int;
         for (int s = 0; s < n_sats; ++s)
