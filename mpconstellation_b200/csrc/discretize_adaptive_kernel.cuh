@@ -44,7 +44,8 @@ __device__ __forceinline__ int ad_eval(const DiscParams &P, double kf, double ka
     hold.at(s, tau, o.ux, o.uy, o.uz);
     if (DRAG) return drag_eval<J2>(P, kf, ka, x, o.ux, o.uy, o.uz, o);
     double ax, ay, az;
-    gravity<J2>(P, x[0], x[1], x[2], ax, ay, az, o.g);
+    gravity<J2>(P, x[0], x[1], x[2], ax, ay, az, o.g, o.gr);
+    o.dragv[0] = o.dragv[1] = o.dragv[2] = 0.0;
     o.im = fast_rcp(x[6]);
     const double tx = o.ux * o.im, ty = o.uy * o.im, tz = o.uz * o.im;
     const double uu = fma(o.ux, o.ux, fma(o.uy, o.uy, o.uz * o.uz));
@@ -107,14 +108,11 @@ __device__ __forceinline__ void ad_node(volatile double *sm, int base, const Dis
 {
     double pr[7][3], pv[7][3];
     ad_load_phi<BLOCK>(sm, base, pr, pv);
-    if (DRAG) {
-        node_accumulate_general<BLOCK>(sm, pr, pv, P, st, x, w, w * lam);
-        return;
-    }
-    double grx, gry, grz;
-    sym_mul(st.g, x[0], x[1], x[2], grx, gry, grz);
-    node_accumulate<BLOCK>(sm, pr, pv, P, st.im, st.ux, st.uy, st.uz, st.iun, st.k[6], x[3], x[4], x[5], st.k[3],
-                           st.k[4], st.k[5], grx, gry, grz, w, w * lam);
+    // The reference inverts the NUMERICAL Phi (np.linalg.inv, :69).  Under RK45 at rtol 1e-3 that matrix is symplectic
+    // only to the integrator's error (1e-11 on 0.01-orbit intervals, 2e-8 on 0.06-orbit ones), so the symplectic
+    // inverse of the fixed-step kernel would differ from the reference by that much here: the default mode solves the
+    // 6x6 system instead (Gauss-Jordan, pivots ~ 1) and matches the dense inverse to rounding on any interval length.
+    node_accumulate_general<BLOCK>(sm, pr, pv, P, st, x, w, w * lam);
 }
 
 template <bool J2, int BLOCK, int NDST, bool GENU, bool DRAG = false>
