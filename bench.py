@@ -215,6 +215,9 @@ def gpu_arm(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it (NCCL_DEBUG=INFO etc. is respected)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     N, K, tf, n_sub = args.sats, args.nodes, args.tf, args.n_sub
     n_int = N * (K - 1)
