@@ -401,6 +401,9 @@ def gpu_arm(args):
                            if fused is not None and fused.skip_const else None} if world > 1 else None,
         "gpu_launches": int(launches),
         "kernel": {"discretize_ms": disc_ms_avg, "propagate_ms": ms_per_step - disc_ms_avg if world == 1 else None,
+                   # propagation is sequential in tau (latency-bound), reported as satellite-steps/s
+                   "propagate_sat_steps_per_s": (N * (K - 1) * n_prop / ((ms_per_step - disc_ms_avg) * 1e-3)) if world == 1 else None,
+                   "propagate_rk4_steps_per_satellite": (K - 1) * n_prop,
                    "discretize_intervals_per_s_per_gpu": n_int / (disc_ms_avg * 1e-3),
                    "default_mode_adaptive_rk45": None if adaptive_ms is None else {
                        "discretize_ms": adaptive_ms, "intervals_per_s": n_int / (adaptive_ms * 1e-3),
