@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--tf", type=float, default=2.0)
     ap.add_argument("--n-sub", dest="n_sub", type=int, default=100, help="RK4 steps per interval (integrator_steps-1)")
     ap.add_argument("--chunks", type=int, default=8, help="compute/all-gather overlap chunks (N>1, --gather nccl)")
-    ap.add_argument("--fused-mode", dest="fused_mode", default="unicast", choices=["unicast", "multicast", "push"])
+    ap.add_argument("--fused-mode", dest="fused_mode", default="unicast", choices=["unicast", "multicast", "push", "pushk"])
     ap.add_argument("--chunk-waves", dest="chunk_waves", type=int, default=1, help="--fused-mode push: kernel waves per pushed chunk")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: all-gather by peer stores from inside the kernel (fused) or chunked NCCL all-gather")

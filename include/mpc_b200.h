@@ -219,10 +219,12 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
  * are spent on the exchange.  When the call returns, everything is enqueued and `stream` waits for the pushes.
  * Rows 42..48 (structural constants, see mpc_discretize_batch_host) are NOT pushed: every destination buffer must
  * have been initialised once with mpc_fill_const_rows.  x, u, tf, dst[] device pointers; ctx owns the push streams.
+ * use_copy_kernel = 1: the pushes are done by a small copy kernel on a highest-priority stream instead of the copy
+ * engines (one launch per chunk writing to all peers).
  */
 int mpc_discretize_batch_push(mpc_ctx *ctx, const double *x, const double *u, const double *tf, const mpc_params *p,
                               int n_sats, int K, int n_sub, double *const *dst, int n_dst, int64_t out_pitch,
-                              int64_t out_offset, int32_t *status, int chunk_waves, void *stream);
+                              int64_t out_offset, int32_t *status, int chunk_waves, int use_copy_kernel, void *stream);
 /* Writes the structural constants (rows 42..47 = 0, row 48 = 1) into all out_pitch columns of a SoA buffer. */
 int mpc_fill_const_rows(double *out, int64_t out_pitch, void *stream);
 

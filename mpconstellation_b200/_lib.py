@@ -109,7 +109,7 @@ def lib():
     L.mpc_discretize_batch_host.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, _DP, _DP]
     L.mpc_propagate_batch_host.argtypes = [vp, _DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP]
     L.mpc_propagate_discretize_host.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, _DP]
-    L.mpc_discretize_batch_push.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, ctypes.POINTER(ctypes.c_void_p), i, i64, i64, _DP, i, vp]
+    L.mpc_discretize_batch_push.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, ctypes.POINTER(ctypes.c_void_p), i, i64, i64, _DP, i, i, vp]
     L.mpc_fill_const_rows.argtypes = [_DP, i64, vp]
     L.mpc_dynamics_jacobian.argtypes = [_DP, i64, i64, i, i, _DP, _DP, _DP, vp]
     L.mpc_constraint_terms.argtypes = [_DP, _DP, i, i, i, d, _DP, _DP, _DP, vp]

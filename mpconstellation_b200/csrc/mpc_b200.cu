@@ -366,6 +366,7 @@ struct mpc_ctx {
     double *d_x = nullptr, *d_u = nullptr, *d_tf = nullptr, *d_out = nullptr, *d_y0 = nullptr, *d_tab = nullptr;
     int32_t *d_status = nullptr, *d_status2 = nullptr, *d_nodes = nullptr;
     double *d_endtau = nullptr;
+    cudaStream_t s_pushk = nullptr;          // high-priority stream of the copy kernels (push gather, SM-driven variant)
     cudaStream_t s_aux[3] = {};              // compute streams the chunk kernels of the push gather rotate over
     cudaStream_t s_push[MPC_MAX_DST] = {};   // one stream per peer for the copy-engine gather (mpc_discretize_batch_push)
     std::vector<cudaEvent_t> ev_push;       // [chunk] kernel-done events + [MPC_MAX_DST] stream-join events
@@ -595,6 +596,7 @@ int mpc_ctx_destroy(mpc_ctx *c)
         if (ps) cudaStreamDestroy(ps);
     for (cudaStream_t ps : c->s_aux)
         if (ps) cudaStreamDestroy(ps);
+    if (c->s_pushk) cudaStreamDestroy(c->s_pushk);
     for (cudaEvent_t e : c->ev_push) cudaEventDestroy(e);
     cudaFree(c->d_x);
     cudaFree(c->d_u);
@@ -854,7 +856,7 @@ int mpc_fill_const_rows(double *out, int64_t out_pitch, void *stream)
 
 int mpc_discretize_batch_push(mpc_ctx *ctx, const double *x, const double *u, const double *tf, const mpc_params *p,
                               int n_sats, int K, int n_sub, double *const *dst, int n_dst, int64_t out_pitch,
-                              int64_t out_offset, int32_t *status, int chunk_waves, void *stream)
+                              int64_t out_offset, int32_t *status, int chunk_waves, int use_copy_kernel, void *stream)
 {
     if (!ctx) return fail(MPC_E_INVALID, "null ctx");
     int rc = check_disc_args(x, u, tf, p, n_sats, K, n_sub);
@@ -870,6 +872,14 @@ int mpc_discretize_batch_push(mpc_ctx *ctx, const double *x, const double *u, co
     cudaStream_t st = (cudaStream_t)stream;
     for (int d = 1; d < n_dst; ++d)
         if (!ctx->s_push[d]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_push[d], cudaStreamNonBlocking));
+    if (use_copy_kernel && !ctx->s_pushk) {
+        // the copy kernels must get SM slots ahead of the compute CTAs still queued: highest stream priority
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&ctx->s_pushk, cudaStreamNonBlocking, hi));
+    }
+    mpc::PeerTab peers{};
+    for (int d = 1; d < n_dst; ++d) peers.p[d - 1] = dst[d];
     const int cs = (int)std::min<long long>((long long)chunk_sats(ctx, n_sats, K) * std::max(chunk_waves, 1), n_sats);
     const int n_chunks = (n_sats + cs - 1) / cs;
     for (cudaStream_t &a : ctx->s_aux)
@@ -899,6 +909,13 @@ int mpc_discretize_batch_push(mpc_ctx *ctx, const double *x, const double *u, co
         if (rc) return rc;
         if (n_dst == 1) continue;
         CUDA_TRY(cudaEventRecord(ctx->ev_push[c], sk));
+        if (use_copy_kernel) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->s_pushk, ctx->ev_push[c], 0));
+            mpc::push_chunk_kernel<<<(unsigned)ctx->sm_count, 256, 0, ctx->s_pushk>>>(dst[0], peers, n_dst - 1, out_pitch, off, nc);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CUDA_TRY(cudaGetLastError());
+            continue;
+        }
         // peers in rotated order per chunk so that the copy engines do not all target the same GPU at once
         for (int i = 1; i < n_dst; ++i) {
             const int d = 1 + (i - 1 + c) % (n_dst - 1);
@@ -912,8 +929,10 @@ int mpc_discretize_batch_push(mpc_ctx *ctx, const double *x, const double *u, co
         }
     }
     for (int d = 1; d < n_dst; ++d) {   // the caller's stream continues only when every push has landed
-        CUDA_TRY(cudaEventRecord(ctx->ev_push[(size_t)n_chunks + d], ctx->s_push[d]));
+        cudaStream_t ps = use_copy_kernel ? ctx->s_pushk : ctx->s_push[d];
+        CUDA_TRY(cudaEventRecord(ctx->ev_push[(size_t)n_chunks + d], ps));
         CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_push[(size_t)n_chunks + d], 0));
+        if (use_copy_kernel) break;
     }
     for (int a = 0; a < 3; ++a) {       // ... and every chunk kernel has finished
         CUDA_TRY(cudaEventRecord(ctx->ev_push[ev_fork + 1 + a], ctx->s_aux[a]));

@@ -217,4 +217,25 @@ __global__ void fill_kernel(double *__restrict__ p, long long n, double v)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// Push the columns [off, off+nc) of a SoA result (all rows but the structurally constant 42..48) from the local buffer
+// to n_peers peer-mapped buffers of the same layout: the SM-driven alternative to the copy engines for the all-gather
+// (a store to a peer sustains the full NVLink rate from a handful of CTAs; scripts/micro/nvl_store.cu).
+struct PeerTab {
+    double *p[8];
+};
+
+__global__ void __launch_bounds__(256)
+push_chunk_kernel(const double *__restrict__ src, PeerTab peers, int n_peers, long long pitch, long long off, long long nc)
+{
+    const long long n_el = 98 * nc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
+        const int r98 = (int)(i / nc);
+        const long long c = i - (long long)r98 * nc;
+        const int row = r98 < 42 ? r98 : r98 + 7;
+        const long long a = (long long)row * pitch + off + c;
+        const double v = src[a];
+        for (int d = 0; d < n_peers; ++d) peers.p[d][a] = v;
+    }
+}
+
 }  // namespace mpc

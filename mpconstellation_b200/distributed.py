@@ -87,7 +87,8 @@ class FusedGather:
         switch to every rank (NVLS) -- 1/world of the SM store instructions and of the egress traffic;
         mode "push": the kernel stores locally, chunk by chunk, and the copy engines push every finished chunk to
         the peers' buffers over NVLink while the next chunk is computed (`mpc_discretize_batch_push`): no SM time
-        and no store-queue stalls go into the exchange, and the structurally constant rows are not sent.
+        and no store-queue stalls go into the exchange, and the structurally constant rows are not sent;
+        mode "pushk": the same pipeline with a small highest-priority copy kernel per chunk instead of the copy engines.
         skip_const: rows 42..48 (the last row of A_k, constants 0..0 1) are written once into every buffer here and
         never sent again (6.7 % less NVLink traffic).  stagger: see mpc_set_gather_tuning."""
         import torch
@@ -113,7 +114,7 @@ class FusedGather:
         if mode == "multicast" and not self.mc_ptr:
             raise RuntimeError("this box / torch build exposes no multicast (NVLS) mapping for symmetric memory")
         self.chunk_waves = int(chunk_waves)
-        self.skip_const = bool(skip_const) or mode == "push"
+        self.skip_const = bool(skip_const) or mode in ("push", "pushk")
         # measured on 8xB200 (profiles/r01_e_multi_gpu.txt): 4 phases help once the step is NVLink-ingress bound
         self.stagger = int(stagger) if stagger is not None else (4 if self.world >= 8 and mode == "unicast" else 0)
         if self.skip_const:
@@ -122,7 +123,7 @@ class FusedGather:
                                                       torch.cuda.current_stream(self.device).cuda_stream))
             torch.cuda.synchronize(self.device)
             self.handle.barrier()
-        if mode == "push":
+        if mode in ("push", "pushk"):
             self.peers = [ptrs[self.rank]] + [ptrs[r] for r in order[1:]]
         self.s0, self.s1 = shard_range(n_sats_total, self.rank, self.world)
         self.status = torch.zeros(max(1, (self.s1 - self.s0) * (K - 1)), dtype=torch.int32, device=self.device)
@@ -133,7 +134,7 @@ class FusedGather:
         rank's `self.buf` holds all N satellites."""
         from . import batch
         assert x.shape[0] == self.s1 - self.s0 and x.shape[2] == self.K
-        tuned = self.mode != "push" and (self.skip_const or self.stagger > 1)
+        tuned = self.mode not in ("push", "pushk") and (self.skip_const or self.stagger > 1)
         if tuned:
             _lib.check(_lib.lib().mpc_set_gather_tuning((2 if self.mode == "multicast" else 1) if self.skip_const else 0,
                                                         self.stagger))
@@ -156,7 +157,7 @@ class FusedGather:
             _lib.check(_lib.lib().mpc_discretize_batch(x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p),
                                                        x.shape[0], self.K, int(n_sub), self.mc_ptr, self.pitch,
                                                        self.s0 * (self.K - 1), self.status.data_ptr(), stream))
-        elif x.shape[0] > 0 and self.mode == "push":
+        elif x.shape[0] > 0 and self.mode in ("push", "pushk"):
             import ctypes
             import torch
             p = _lib.make_params(const, include_J2, False)
@@ -165,7 +166,7 @@ class FusedGather:
             _lib.check(_lib.lib().mpc_discretize_batch_push(
                 batch._ctx(self.device.index or 0), x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p), x.shape[0],
                 self.K, int(n_sub), arr, len(self.peers), self.pitch, self.s0 * (self.K - 1), self.status.data_ptr(),
-                self.chunk_waves, stream))
+                self.chunk_waves, int(self.mode == "pushk"), stream))
         elif x.shape[0] > 0:
             batch.discretize_batch_device(x, u, tf, const, include_J2=include_J2, n_sub=n_sub, out=self.buf,
                                           out_pitch=self.pitch, out_offset=self.s0 * (self.K - 1),

@@ -65,8 +65,9 @@ try:
 except Exception as exc:
     if rank == 0: print("multicast unavailable:", exc)
 t_push, ok_push = {}, 1
-for cw in (1, 2):
-    fp = D.FusedGather(N * world, K, device=dev, mode="push", chunk_waves=cw)
+for cw in (1, 2, "k1", "k2"):
+    fp = D.FusedGather(N * world, K, device=dev, mode="pushk" if isinstance(cw, str) else "push",
+                       chunk_waves=int(str(cw).lstrip("k")))
     fp.buf[:42].zero_(); fp.buf[49:].zero_(); torch.cuda.synchronize(); dist.barrier()
     t_push[cw] = timed(lambda: fp.discretize(x, u, tfd, const))
     ok_push &= int(torch.equal(fp.buf, full))
@@ -90,7 +91,7 @@ res = torch.tensor([int(ok_fused), int(ok_view), int(ok_nccl), int(ok_mc), int(o
 if rank == 0:
     gb = (world - 1) * n_int * 840 / 1e9
     print(f"world {world}  N/rank {N}  K {K}: local-only {t_local:.3f} ms | fused peer-store gather {t_fused:.3f} ms | fused multicast-store gather {t_mc:.3f} ms | "
-          f"copy-engine push (1 / 2 waves per chunk) {t_push[1]:.3f} / {t_push[2]:.3f} ms | "
+          f"copy-engine push (1 / 2 waves per chunk) {t_push[1]:.3f} / {t_push[2]:.3f} ms | copy-kernel push (1 / 2 waves) {t_push['k1']:.3f} / {t_push['k2']:.3f} ms | "
           f"NCCL chunked-overlap {t_nccl:.3f} ms | kernel then NCCL all-gather {t_plain:.3f} ms | "
           f"{gb:.2f} GB received per rank | verified fused/view/nccl/multicast/push/variants = {res.tolist()}")
     for k_, v_ in variants.items():

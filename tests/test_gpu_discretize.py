@@ -269,9 +269,10 @@ def test_copy_engine_push_gather_on_one_gpu(M, const):
     status = torch.full((n,), -1, dtype=torch.int32, device=dev)
     p = _lib.make_params(const, False, False)
     arr = (ctypes.c_void_p * 3)(*[b.data_ptr() for b in bufs])
-    for waves in (1, 2):
+    for waves, copy_kernel in ((1, 0), (2, 0), (1, 1)):
         _lib.check(L.mpc_discretize_batch_push(batch._ctx(0), x.data_ptr(), u.data_ptr(), tfv.data_ptr(), ctypes.byref(p),
-                                               N, K, 20, arr, 3, n + 2 * pad, pad, status.data_ptr(), waves, stream))
+                                               N, K, 20, arr, 3, n + 2 * pad, pad, status.data_ptr(), waves, copy_kernel,
+                                               stream))
         torch.cuda.synchronize()
         assert int(status.max()) == 0 and int(status.min()) == 0
         for b in bufs:
