@@ -6,7 +6,17 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import mpconstellation_b200 as M
 from bench import make_constellation
-from oracle.mpc_oracle import OracleConstants, norm_rel_err
+from types import SimpleNamespace
+
+
+def OracleConstants(MU, R_E, J2, G0, ISP, S, R0, RHO):      # the fixtures' constant vector as a Constants-like bag
+    return SimpleNamespace(MU=MU, R_E=R_E, J2=J2, G0=G0, ISP=ISP, S=S, R0=R0, RHO=RHO)
+
+
+def norm_rel_err(a, b):                                      # the parity metric of the tests: max|a-b| / max|b|
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
+
+
 g = np.load(os.path.join(ROOT, "tests/golden/discretize.npz")); const = OracleConstants(*g["const"])
 NAMES = ["A_k", "B_kp", "B_kn", "Sigma_k", "xi_k"]
 print("== parity vs the unmodified reference (tests/golden), norm-relative max|d|/max|ref| per matrix")
