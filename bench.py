@@ -4,7 +4,7 @@
 Workload (BASELINE.json configs[2], the largest single-GPU configuration): 4096 satellites x K=200
 nodes (815,104 intervals), tangential thrust 0.5, tf=2.  One STEP = one SCP linearization pass over the
 batch: propagate every satellite (reference trajectory + extract_uk) then discretize every interval
-(integrator_steps=101: 100 RK4 steps + 101-node trapezoid per interval).
+(integrator_steps=101: 100 fixed fourth-order Runge-Kutta(-Nystrom) steps + 101-node trapezoid per interval).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [...]                          # the reference algorithm on the host cores
@@ -33,19 +33,19 @@ FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SM x 64 DFMA/clk 
 
 def flops_per_interval(n_sub, include_j2=False):
     """ALGORITHMIC FP64 work of one interval: the arithmetic of the algorithm DESIGN.md section 4 states
-    (42 live Phi entries, symmetric G, Nystrom-form RK4 in step-normalised variables, symplectic inverse, 56
-    accumulators), FMA = 2 flop, mul/add = 1, MUFU seeds not counted.  One thread does one interval with no
-    recomputation, so this equals the executed DFMA/DMUL/DADD count: per RK4 step + quadrature node 548 FMA + 228 mul
-    + 128 add (J2: 599 / 288 / 147), plus the last node and the Phi_end * [integrals] epilogue (1249 flop; J2 1310).
-    Counted from the SASS of the shipped kernel (scripts/sass_reuse.py) and cross-checked against ncu
-    smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/)."""
-    per_step = (2 * 599 + 288 + 147) if include_j2 else (2 * 548 + 228 + 128)
+    (42 live Phi entries, symmetric G, Nystrom's 3-stage fourth-order Runge-Kutta method in step-normalised variables,
+    symplectic inverse, 56 accumulators), FMA = 2 flop, mul/add = 1, MUFU seeds not counted.  One thread does one
+    interval with no recomputation, so this equals the executed DFMA/DMUL/DADD count: per step + quadrature node
+    532 FMA + 182 mul + 55 add (J2: 571 / 230 / 69), plus the last node and the Phi_end * [integrals] epilogue
+    (1249 flop; J2 1310).  Counted from the SASS of the shipped kernel (scripts/sass_reuse.py) and cross-checked
+    against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/)."""
+    per_step = (2 * 571 + 230 + 69) if include_j2 else (2 * 532 + 182 + 55)
     return n_sub * per_step + (1310 if include_j2 else 1249)
 
 
 def fp64_instr_per_interval(n_sub, include_j2=False):
     """FP64-pipe instructions (DFMA+DMUL+DADD) per interval: the pipe-occupancy view of the same work."""
-    return n_sub * ((599 + 288 + 147) if include_j2 else (548 + 228 + 128)) + (785 if include_j2 else 742)
+    return n_sub * ((571 + 230 + 69) if include_j2 else (532 + 182 + 55)) + (785 if include_j2 else 742)
 
 
 def bytes_per_interval():
@@ -198,7 +198,7 @@ def workload_config(args):
     return {"workload": f"{args.sats} satellites x K={args.nodes} nodes ({args.sats * (args.nodes - 1)} intervals) per GPU: "
                         "propagate (tangential thrust 0.5, no drag/J2) + discretize, BASELINE configs[2]",
             "sats_per_gpu": args.sats, "K": args.nodes, "tf": args.tf, "integrator_steps": args.n_sub + 1,
-            "integrator": "fixed-step RK4, trapezoid on the RK4 nodes", "l2": "flushed between timed steps (256 MiB write)",
+            "integrator": "fixed-step fourth-order Runge-Kutta-Nystrom (3 stages), trapezoid on the step nodes", "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": f"satellites sharded over {args.gpus} GPU(s)" + (f", all-gather of the SoA matrices inside the step ({args.gather})" if args.gpus > 1 else "")}
 
 

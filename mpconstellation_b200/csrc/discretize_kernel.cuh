@@ -156,41 +156,38 @@ __device__ __forceinline__ void sym_mul_add(const Sym3 &g, double px, double py,
     oz = fma(g.zz, pz, fma(g.yz, py, fma(g.xz, px, cz)));
 }
 
-// One column of Phi through one RK4 step (Nystrom form of the classical stages), in the STEP-NORMALISED
-// variables of discretize_kernel: velocities scaled by the step hs, G and d scaled by hs^2, so the step is 1 and
-// every Runge-Kutta coefficient is a literal (an immediate / constant-bank operand instead of a third register
+// One column of Phi through one step of Nystrom's 3-stage fourth-order method for p'' = G(t) p (+ d):
+//     k1 = G1 p,  k2 = G2 (p + 1/2 p' + 1/8 k1),  k3 = G3 (p + p' + 1/2 k2),
+//     p+ = p + p' + 1/6 (k1 + 2 k2),   p'+ = p' + 1/6 (k1 + 4 k2 + k3)
+// in the STEP-NORMALISED variables of discretize_kernel: velocities scaled by the step hs, G and d scaled by hs^2, so
+// the step is 1 and every coefficient is a literal (an immediate / constant-bank operand instead of a third register
 // operand: a DFMA with three distinct register sources issues every 3 cycles on sm_100a, with two every 2).
-// MASSCOL: column 6, whose forcing is d_j = -u/m^2 at each stage (Phi[6][6] == 1).
+// G1..G3 are the stage matrices of the SAME scheme applied to the state, so Phi is the exact derivative of the
+// numerical flow.  MASSCOL: column 6, whose forcing is d_j = -u/m^2 at each stage (Phi[6][6] == 1).
 template <bool MASSCOL>
 __device__ __forceinline__ void column_step(double (&pr)[3], double (&pv)[3], const StageLin &s1,
-                                            const StageLin &s2, const StageLin &s3, const StageLin &s4)
+                                            const StageLin &s2, const StageLin &s3)
 {
     constexpr double c6 = 1.0 / 6.0;
-    double k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
+    double k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
     if (MASSCOL) sym_mul_add(s1.g, pr[0], pr[1], pr[2], s1.dx, s1.dy, s1.dz, k1x, k1y, k1z);
     else sym_mul(s1.g, pr[0], pr[1], pr[2], k1x, k1y, k1z);
-    // stage 2 position: p + 1/2 p_v
-    const double q2x = fma(0.5, pv[0], pr[0]), q2y = fma(0.5, pv[1], pr[1]), q2z = fma(0.5, pv[2], pr[2]);
+    // stage 2 position: p + 1/2 p_v + 1/8 k1
+    const double q2x = fma(0.125, k1x, fma(0.5, pv[0], pr[0])), q2y = fma(0.125, k1y, fma(0.5, pv[1], pr[1])),
+                 q2z = fma(0.125, k1z, fma(0.5, pv[2], pr[2]));
     if (MASSCOL) sym_mul_add(s2.g, q2x, q2y, q2z, s2.dx, s2.dy, s2.dz, k2x, k2y, k2z);
     else sym_mul(s2.g, q2x, q2y, q2z, k2x, k2y, k2z);
-    // stage 3 position: p + 1/2 (p_v + 1/2 k1) = q2 + 1/4 k1
-    const double q3x = fma(0.25, k1x, q2x), q3y = fma(0.25, k1y, q2y), q3z = fma(0.25, k1z, q2z);
+    // stage 3 position: p + p_v + 1/2 k2
+    const double bx = pv[0] + pr[0], by = pv[1] + pr[1], bz = pv[2] + pr[2];
+    const double q3x = fma(0.5, k2x, bx), q3y = fma(0.5, k2y, by), q3z = fma(0.5, k2z, bz);
     if (MASSCOL) sym_mul_add(s3.g, q3x, q3y, q3z, s3.dx, s3.dy, s3.dz, k3x, k3y, k3z);
     else sym_mul(s3.g, q3x, q3y, q3z, k3x, k3y, k3z);
-    // stage 4 position: p + (p_v + 1/2 k2)
-    const double bx = pv[0] + pr[0], by = pv[1] + pr[1], bz = pv[2] + pr[2];
-    const double q4x = fma(0.5, k2x, bx), q4y = fma(0.5, k2y, by), q4z = fma(0.5, k2z, bz);
-    if (MASSCOL) sym_mul_add(s4.g, q4x, q4y, q4z, s4.dx, s4.dy, s4.dz, k4x, k4y, k4z);
-    else sym_mul(s4.g, q4x, q4y, q4z, k4x, k4y, k4z);
-    // p_r+ = p_r + p_v + 1/6 (k1+k2+k3);  p_v+ = p_v + 1/6 (k1 + 2k2 + 2k3 + k4)
-    const double wx = k2x + k3x, wy = k2y + k3y, wz = k2z + k3z;
-    const double sx = k1x + wx, sy = k1y + wy, sz = k1z + wz;
-    pr[0] = fma(c6, sx, bx);
-    pr[1] = fma(c6, sy, by);
-    pr[2] = fma(c6, sz, bz);
-    pv[0] = fma(c6, (sx + wx) + k4x, pv[0]);
-    pv[1] = fma(c6, (sy + wy) + k4y, pv[1]);
-    pv[2] = fma(c6, (sz + wz) + k4z, pv[2]);
+    pr[0] = fma(c6, fma(2.0, k2x, k1x), bx);
+    pr[1] = fma(c6, fma(2.0, k2y, k1y), by);
+    pr[2] = fma(c6, fma(2.0, k2z, k1z), bz);
+    pv[0] = fma(c6, fma(4.0, k2x, k1x) + k3x, pv[0]);
+    pv[1] = fma(c6, fma(4.0, k2y, k1y) + k3y, pv[1]);
+    pv[2] = fma(c6, fma(4.0, k2z, k1z) + k3z, pv[2]);
 }
 
 // Input hold u(tau).  GENU = false: u is given on the K nodes of x, so inside one interval the reference's
@@ -600,7 +597,9 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
         }
         if (n == n_sub) break;
 
-        // ---- stages 2..4 of the state (Nystrom form; mass stages are explicit in tau) -----------
+        // ---- stages 2, 3 of the state: Nystrom's 3-stage fourth-order method for r'' = a(tau, r) ----------------
+        // (the mass is a quadrature of mdot(tau): m at the half step from the quadratic through the three mdot
+        //  values, m at the end by Simpson -- which is also the mass update)
         const double sm = ((double)n + 0.5) * inv_n, se = (double)(n + 1) * inv_n;
         double umx, umy, umz, uex, uey, uez;
         hold.at(sm, fma(sm, dtau_k, tau0), umx, umy, umz);
@@ -611,14 +610,14 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
         const double iune = inv_norm_guarded(uue, eps2);
         const double mdm = -(uum * iunm) * Ph.inv_ve;
         const double mde = -(uue * iune) * Ph.inv_ve;
-        const double m2 = fma(0.5, md1, m);
-        const double m3 = fma(0.5, mdm, m);
-        const double m4 = m + mdm;
-        bad |= !(m4 > 0.0);
+        const double m2 = fma(1.0 / 24.0, fma(8.0, mdm, 5.0 * md1) - mde, m);
+        const double m3 = fma(c6, fma(4.0, mdm, md1) + mde, m);
+        bad |= !(m3 > 0.0);
 
-        StageLin s2, s3, s4;
-        double a2x, a2y, a2z, a3x, a3y, a3z, a4x, a4y, a4z;
-        const double r2x = fma(0.5, vx, rx), r2y = fma(0.5, vy, ry), r2z = fma(0.5, vz, rz);
+        StageLin s2, s3;
+        double a2x, a2y, a2z, a3x, a3y, a3z;
+        const double r2x = fma(0.125, a1x, fma(0.5, vx, rx)), r2y = fma(0.125, a1y, fma(0.5, vy, ry)),
+                     r2z = fma(0.125, a1z, fma(0.5, vz, rz));
         gravity<J2>(Ph, r2x, r2y, r2z, a2x, a2y, a2z, s2.g);
         {
             const double i2 = fast_rcp(m2);
@@ -630,11 +629,12 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             s2.dy = -qy * i2;
             s2.dz = -qz * i2;
         }
-        const double r3x = fma(0.25, a1x, r2x), r3y = fma(0.25, a1y, r2y), r3z = fma(0.25, a1z, r2z);
+        const double bx = vx + rx, by = vy + ry, bz = vz + rz;
+        const double r3x = fma(0.5, a2x, bx), r3y = fma(0.5, a2y, by), r3z = fma(0.5, a2z, bz);
         gravity<J2>(Ph, r3x, r3y, r3z, a3x, a3y, a3z, s3.g);
         {
             const double i3 = fast_rcp(m3);
-            const double qx = umx * i3, qy = umy * i3, qz = umz * i3;
+            const double qx = uex * i3, qy = uey * i3, qz = uez * i3;
             a3x += qx;
             a3y += qy;
             a3z += qz;
@@ -642,36 +642,19 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
             s3.dy = -qy * i3;
             s3.dz = -qz * i3;
         }
-        const double bx = vx + rx, by = vy + ry, bz = vz + rz;
-        const double r4x = fma(0.5, a2x, bx), r4y = fma(0.5, a2y, by), r4z = fma(0.5, a2z, bz);
-        gravity<J2>(Ph, r4x, r4y, r4z, a4x, a4y, a4z, s4.g);
-        {
-            const double i4 = fast_rcp(m4);
-            const double qx = uex * i4, qy = uey * i4, qz = uez * i4;
-            a4x += qx;
-            a4y += qy;
-            a4z += qz;
-            s4.dx = -qx * i4;
-            s4.dy = -qy * i4;
-            s4.dz = -qz * i4;
-        }
         // ---- state update -------------------------------------------------------------------------
-        {
-            const double wx = a2x + a3x, wy = a2y + a3y, wz = a2z + a3z;
-            const double sx = a1x + wx, sy = a1y + wy, sz = a1z + wz;
-            rx = fma(c6, sx, bx);
-            ry = fma(c6, sy, by);
-            rz = fma(c6, sz, bz);
-            vx = fma(c6, (sx + wx) + a4x, vx);
-            vy = fma(c6, (sy + wy) + a4y, vy);
-            vz = fma(c6, (sz + wz) + a4z, vz);
-            m = fma(c6, fma(4.0, mdm, md1) + mde, m);
-        }
+        rx = fma(c6, fma(2.0, a2x, a1x), bx);
+        ry = fma(c6, fma(2.0, a2y, a1y), by);
+        rz = fma(c6, fma(2.0, a2z, a1z), bz);
+        vx = fma(c6, fma(4.0, a2x, a1x) + a3x, vx);
+        vy = fma(c6, fma(4.0, a2y, a1y) + a3y, vy);
+        vz = fma(c6, fma(4.0, a2z, a1z) + a3z, vz);
+        m = m3;
         // ---- variational columns ----------------------------------------------------------------
-        // the mass column first: its forcing terms d1..d4 are dead for the remaining six columns
-        column_step<true>(pr[6], pv[6], s1, s2, s3, s4);
+        // the mass column first: its forcing terms d1..d3 are dead for the remaining six columns
+        column_step<true>(pr[6], pv[6], s1, s2, s3);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3, s4);
+        for (int c = 0; c < 6; ++c) column_step<false>(pr[c], pv[c], s1, s2, s3);
         ux = uex;
         uy = uey;
         uz = uez;

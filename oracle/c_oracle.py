@@ -61,6 +61,12 @@ def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.
                      c_d, rho_atm, cd_a, rho_a, int(include_J2), int(include_drag or drag is not None))
 
 
+def set_scheme(name):
+    """Integration scheme of the fixed-step mode: "rkn4" (default; Nystrom's 3-stage 4th-order method, what the CUDA
+    kernel runs) or "rk4" (classical RK4 on the first-order 56-vector)."""
+    lib().orc_set_scheme({"rk4": 0, "rkn4": 1}[name])
+
+
 def max_threads():
     return lib().orc_max_threads()
 

@@ -173,6 +173,65 @@ static int inv7(const double *M, double *Inv)
     return 0;
 }
 
+/* Integration scheme of the fixed-step mode.  1 (default): Nystrom's 3-stage fourth-order Runge-Kutta method for
+ * y'' = f(t, y) -- what the CUDA kernel runs: positions / velocities of the state and of every Phi column are a
+ * second-order system (no drag in the discretizer), the mass is a quadrature of mdot(tau).  0: the classical RK4 on
+ * the first-order 56-vector (also used whenever drag is on: the acceleration then depends on the velocity). */
+static int g_scheme = 1;
+void orc_set_scheme(int scheme) { g_scheme = scheme; }
+
+/* accelerations of the second-order part at the stage vector ys (only its positions, mass and Phi row 6 matter) */
+static int accel(const double *ys, const double *u, const orc_params *p, int j2, double *ax, double *aP)
+{
+    double f[7], D[49];
+    if (dyn(ys + 49, u, p, 0, j2, f)) return 1;
+    dxf(ys + 49, u, p, j2, D);
+    for (int i = 0; i < 3; ++i) {
+        ax[i] = f[3 + i];
+        for (int j = 0; j < 7; ++j) {
+            double s = 0.0;
+            for (int l = 0; l < 7; ++l) s += D[(3 + i) * 7 + l] * ys[l * 7 + j];
+            aP[i * 7 + j] = s;
+        }
+    }
+    return 0;
+}
+
+/* one RKN4 step of size hs (unscaled time) from y; inputs at the start / middle / end of the step */
+static int rkn4_step(double *y, const double *u1, const double *um, const double *ue, double hs, const orc_params *p, int j2)
+{
+    double a1[3], a2[3], a3[3], P1[21], P2[21], P3[21], ys[56];
+    const double ve = p->G0 * p->ISP;
+    const double md1 = -norm3(u1) / ve, mdm = -norm3(um) / ve, mde = -norm3(ue) / ve;
+    const double m = y[55];
+    const double m2 = m + hs * (5.0 * md1 + 8.0 * mdm - mde) / 24.0;   /* integral of the quadratic through the 3 values */
+    const double m3 = m + hs * (md1 + 4.0 * mdm + mde) / 6.0;          /* Simpson */
+    if (accel(y, u1, p, j2, a1, P1)) return 1;
+    memcpy(ys, y, sizeof ys);
+    for (int i = 0; i < 3; ++i) {
+        ys[49 + i] = y[49 + i] + 0.5 * hs * y[52 + i] + hs * hs / 8.0 * a1[i];
+        for (int j = 0; j < 7; ++j) ys[i * 7 + j] = y[i * 7 + j] + 0.5 * hs * y[(3 + i) * 7 + j] + hs * hs / 8.0 * P1[i * 7 + j];
+    }
+    ys[55] = m2;
+    if (accel(ys, um, p, j2, a2, P2)) return 1;
+    for (int i = 0; i < 3; ++i) {
+        ys[49 + i] = y[49 + i] + hs * y[52 + i] + hs * hs / 2.0 * a2[i];
+        for (int j = 0; j < 7; ++j) ys[i * 7 + j] = y[i * 7 + j] + hs * y[(3 + i) * 7 + j] + hs * hs / 2.0 * P2[i * 7 + j];
+    }
+    ys[55] = m3;
+    if (accel(ys, ue, p, j2, a3, P3)) return 1;
+    for (int i = 0; i < 3; ++i) {
+        y[49 + i] += hs * y[52 + i] + hs * hs / 6.0 * (a1[i] + 2.0 * a2[i]);
+        y[52 + i] += hs / 6.0 * (a1[i] + 4.0 * a2[i] + a3[i]);
+        for (int j = 0; j < 7; ++j) {
+            y[i * 7 + j] += hs * y[(3 + i) * 7 + j] + hs * hs / 6.0 * (P1[i * 7 + j] + 2.0 * P2[i * 7 + j]);
+            y[(3 + i) * 7 + j] += hs / 6.0 * (P1[i * 7 + j] + 4.0 * P2[i * 7 + j] + P3[i * 7 + j]);
+        }
+    }
+    y[55] = m3;
+    return !(m3 > 0.0);
+}
+
 /* One interval; out = A(49) B_kp(21) B_kn(21) Sigma(7) xi(7); linearize_discretize.py:8-82.
  * u0/u1 are the FOH end points of this interval (u is linear inside one interval, :305-315). */
 static int interval(const double *xk, const double *u0, const double *u1, double tf, double dtau, int n_sub,
@@ -228,6 +287,10 @@ static int interval(const double *xk, const double *u0, const double *u1, double
         for (int i = 0; i < 3; ++i) {
             um[i] = (1.0 - lm) * u0[i] + lm * u1[i];
             ue[i] = (1.0 - le) * u0[i] + le * u1[i];
+        }
+        if (g_scheme == 1 && !p->include_drag) {
+            if (rkn4_step(y, un, um, ue, tf * h, p, j2)) return 1;
+            continue;
         }
         if (aug_rhs(y, un, tf, p, j2, k1)) return 1;
         for (int i = 0; i < 56; ++i) yt[i] = y[i] + 0.5 * h * k1[i];
