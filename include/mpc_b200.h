@@ -99,7 +99,7 @@ int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc
  *   x   [n_sats][7][K]   reference trajectories (scaled states)            discretize() arg `x`
  *   u   [n_sats][3][K]   reference inputs on the same K nodes              discretize() arg `u`
  *   tf  [n_sats]         reference final time per satellite                discretize() arg `tf`
- *   n_sub                RK4 steps per interval = integrator_steps - 1     Discretizer.integrator_steps
+ *   n_sub                fixed fourth-order Runge-Kutta(-Nystrom) steps per interval = integrator_steps - 1
  *   out                  SoA, out[row * out_pitch + out_offset + s*(K-1) + k], row in [0,105)
  *   status [n_sats*(K-1)] MPC_ST_* per interval (may be NULL)
  *

@@ -12,9 +12,10 @@
 //   * A = [[0 I 0],[G 0 d],[0 0 0]] with G symmetric (gravity gradient, + J2 gradient) and
 //     d = -u/m^2 (linearize_discretize.py:146-179): the last row of Phi stays e7^T, each of the
 //     7 columns of Phi is an independent second-order system  p_r'' = G(tau) p_r (+ d)
-//   * classical RK4 on a second-order system can be written in Nystrom form (same stages, same
-//     result up to rounding, fewer operations); the 4 stage matrices G1..G4 come from the state
-//     trajectory alone, so they are computed once per step and shared by the 7 columns
+//   * a second-order system whose force does not depend on the velocity can be integrated with Nystrom's 3-stage
+//     fourth-order Runge-Kutta method (three force evaluations per step instead of the classical scheme's four,
+//     same order); the 3 stage matrices G1..G3 come from the state trajectory alone, so they are computed once
+//     per step and shared by the 7 columns
 //   * the 6x6 block of Phi is symplectic (G symmetric, no drag in the discretizer), so
 //     Phi6^-1 = [[Pvv^T, -Prv^T],[-Pvr^T, Prr^T]]  and  Phi^-1 = [[Phi6^-1, -Phi6^-1 c],[0 1]]:
 //     the per-node inverse (:69) costs no factorisation

@@ -48,7 +48,7 @@ class Discretizer:
             if self.drho_func is None:
                 raise TypeError("'NoneType' object is not callable")
         if self.ivp_solver != 'RK45':
-            raise NotImplementedError(f"ivp_solver={self.ivp_solver!r}: the device integrator is fixed-step RK4 "
+            raise NotImplementedError(f"ivp_solver={self.ivp_solver!r}: the device integrator is a fixed-step 4th-order Runge-Kutta method "
                                       "on the reference's node grid (stated against RK45)")
         if self.use_uniform_steps and int(self.integrator_steps) < 2:
             raise ValueError("integrator_steps must be >= 2")
@@ -93,7 +93,7 @@ class Discretizer:
         # u may have its own column count: the reference's hold takes its grid from u (linearize_discretize.py:308-315)
         # use_uniform_steps=False (the reference default): quadrature on the steps scipy's RK45 controller accepts
         # (replayed on the device, scipy's default rtol/atol as the reference passes none);
-        # use_uniform_steps=True: fixed-step RK4 on the uniform integrator_steps grid.
+        # use_uniform_steps=True: fixed-step fourth-order Runge-Kutta(-Nystrom) on the uniform integrator_steps grid.
         adaptive = None if self.use_uniform_steps else dict(rtol=self.ivp_rtol, atol=self.ivp_atol,
                                                             max_step=float(self.ivp_max_step))
         return batch.discretize_batch(x, u, tf, self.const, include_J2=self.include_J2,
