@@ -499,25 +499,15 @@ __device__ __forceinline__ int epilogue_store(volatile double *acc, const double
 }
 #undef ACC
 
-template <bool J2, int BLOCK, int MAXREG, int NDST, bool GENU>
-__global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG)
-discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ tf_arr,
-                  DiscParams P, int n_sats, int K, int Ku, int n_sub, DstTab dst, long long pitch, long long offset,
-                  int32_t *__restrict__ status)
-{
-    extern __shared__ double acc_smem[];
-    const long long n_int = (long long)n_sats * (K - 1);
-    const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
-    if (gid >= n_int) return;
-    if (dst.stagger_phases > 1 && (int)blockIdx.x < dst.first_wave_ctas) {
-        const long long wait = dst.stagger_cycles * (long long)(blockIdx.x % dst.stagger_phases) / dst.stagger_phases;
-        const long long t0 = clock64();
-        while (clock64() - t0 < wait) __nanosleep(2000);
-    }
-    // volatile: keep the accumulators IN shared memory (the compiler would otherwise promote these
-    // thread-private slots to registers and spill them to local memory, which is write-through to L2)
-    volatile double *acc = acc_smem + threadIdx.x;
+// One interval, one integrator step per quadrature node: the whole per-thread computation (the kernel below is a thin
+// wrapper; discretize_pair_kernel falls back to it for intervals whose steps are too long for its midpoint interpolation).
 #define ACC(e) acc[(e) * BLOCK]
+template <bool J2, int BLOCK, int NDST, bool GENU>
+__device__ __forceinline__ void discretize_thread(const double *__restrict__ x, const double *__restrict__ u,
+                                                  const double *__restrict__ tf_arr, const DiscParams &P, int K, int Ku,
+                                                  int n_sub, const DstTab &dst, long long pitch, long long offset,
+                                                  int32_t *__restrict__ status, long long gid, volatile double *acc)
+{
 
     const int s = (int)(gid / (K - 1));
     const int k = (int)(gid - (long long)s * (K - 1));
@@ -668,7 +658,28 @@ discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, co
     const double ihs = 1.0 / hs;
     const int nonfinite = epilogue_store<BLOCK, NDST>(acc, pr, pv, hs, h * ihs, 1.0, dst, pitch, offset + gid, hs, ihs);
     if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : 0);
+}
 #undef ACC
+
+template <bool J2, int BLOCK, int MAXREG, int NDST, bool GENU>
+__global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG)
+discretize_kernel(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ tf_arr,
+                  DiscParams P, int n_sats, int K, int Ku, int n_sub, DstTab dst, long long pitch, long long offset,
+                  int32_t *__restrict__ status)
+{
+    extern __shared__ double acc_smem[];
+    const long long n_int = (long long)n_sats * (K - 1);
+    const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (gid >= n_int) return;
+    if (dst.stagger_phases > 1 && (int)blockIdx.x < dst.first_wave_ctas) {
+        const long long wait = dst.stagger_cycles * (long long)(blockIdx.x % dst.stagger_phases) / dst.stagger_phases;
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) __nanosleep(2000);
+    }
+    // volatile: keep the accumulators IN shared memory (the compiler would otherwise promote these
+    // thread-private slots to registers and spill them to local memory, which is write-through to L2)
+    discretize_thread<J2, BLOCK, NDST, GENU>(x, u, tf_arr, P, K, Ku, n_sub, dst, pitch, offset, status, gid,
+                                             acc_smem + threadIdx.x);
 }
 
 }  // namespace mpc

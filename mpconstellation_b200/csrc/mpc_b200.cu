@@ -18,6 +18,7 @@
 #include "propagate_kernel.cuh"
 #include "constraint_terms_kernel.cuh"
 #include "discretize_drag_kernel.cuh"
+#include "discretize_pair_kernel.cuh"
 
 namespace {
 
@@ -95,6 +96,32 @@ int launch_disc_cfg(const double *x, const double *u, const double *tf, const mp
     return MPC_SUCCESS;
 }
 
+// discretize_pair_kernel: integrator steps spanning two quadrature nodes (needs an even number of panels)
+template <bool J2, int BLOCK, int MAXREG, int NDST>
+int launch_pair_cfg(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                    int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                    cudaStream_t st)
+{
+    auto kern = mpc::discretize_pair_kernel<J2, BLOCK, MAXREG, NDST>;
+    const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured_dev = dev;
+    }
+    const long long n_int = (long long)n_sats * (K - 1);
+    const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
+std::atomic<int> g_pair{1};   // mpc_set_tuning(7) switches the two-node steps off (one step per node everywhere)
+
 // The production configuration plus the experimental ones mpc_set_tuning() selects (single destination,
 // no J2 only: they exist to measure occupancy / register-cap trade-offs).
 template <bool J2, int NDST>
@@ -117,9 +144,11 @@ int launch_disc_n(const double *x, const double *u, const double *tf, const mpc:
     }
     // Small batches (BASELINE configs 1-2: 49 ... 6,336 intervals) cannot fill 148 SMs with 128-thread CTAs:
     // one-warp CTAs spread them over as many SMs as possible (same code, 224-register build, 9 CTAs/SM).
+    // two quadrature nodes per integrator step where that is accurate (decided per thread inside the kernel)
+    const bool pair = (g_ucols == 0) && g_pair.load(std::memory_order_relaxed);
     if (NDST == 1 && (long long)n_sats * (K - 1) < 148LL * 9 * 32 * 2)
-        return launch_disc_cfg<J2, 32, 224, 1>(MPC_ARGS);
-    return launch_disc_cfg<J2, kDiscBlock, 255, NDST>(MPC_ARGS);
+        return pair ? launch_pair_cfg<J2, 32, 255, 1>(MPC_ARGS) : launch_disc_cfg<J2, 32, 224, 1>(MPC_ARGS);
+    return pair ? launch_pair_cfg<J2, kDiscBlock, 255, NDST>(MPC_ARGS) : launch_disc_cfg<J2, kDiscBlock, 255, NDST>(MPC_ARGS);
 #undef MPC_ARGS
 }
 
@@ -506,6 +535,10 @@ int mpc_set_gather_tuning(int skip_const, int stagger_phases)
 
 int mpc_set_tuning(int variant)
 {
+    if (variant == 7 || variant == 8) {   // 7: one integrator step per node everywhere; 8: two-node steps back on
+        g_pair.store(variant == 8);
+        return MPC_SUCCESS;
+    }
     if (variant < 0 || variant > 6) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);
     g_tuning.store(variant);
     return MPC_SUCCESS;

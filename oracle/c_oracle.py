@@ -62,9 +62,10 @@ def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.
 
 
 def set_scheme(name):
-    """Integration scheme of the fixed-step mode: "rkn4" (default; Nystrom's 3-stage 4th-order method, what the CUDA
-    kernel runs) or "rk4" (classical RK4 on the first-order 56-vector)."""
-    lib().orc_set_scheme({"rk4": 0, "rkn4": 1}[name])
+    """Integration scheme of the fixed-step mode: "rkn4x2" (default; what the CUDA kernels run: Nystrom's 3-stage
+    4th-order method, steps spanning two quadrature nodes with a Hermite midpoint where the step is short enough),
+    "rkn4" (one Nystrom step per node) or "rk4" (classical RK4 on the first-order 56-vector)."""
+    lib().orc_set_scheme({"rk4": 0, "rkn4": 1, "rkn4x2": 2}[name])
 
 
 def max_threads():

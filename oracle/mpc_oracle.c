@@ -173,11 +173,12 @@ static int inv7(const double *M, double *Inv)
     return 0;
 }
 
-/* Integration scheme of the fixed-step mode.  1 (default): Nystrom's 3-stage fourth-order Runge-Kutta method for
+/* Integration scheme of the fixed-step mode.  2 (default): scheme 1 with steps spanning two quadrature nodes where that
+ * is accurate (see interval()).  1: Nystrom's 3-stage fourth-order Runge-Kutta method for
  * y'' = f(t, y) -- what the CUDA kernel runs: positions / velocities of the state and of every Phi column are a
  * second-order system (no drag in the discretizer), the mass is a quadrature of mdot(tau).  0: the classical RK4 on
  * the first-order 56-vector (also used whenever drag is on: the acceleration then depends on the velocity). */
-static int g_scheme = 1;
+static int g_scheme = 2;
 void orc_set_scheme(int scheme) { g_scheme = scheme; }
 
 /* accelerations of the second-order part at the stage vector ys (only its positions, mass and Phi row 6 matter) */
@@ -237,7 +238,7 @@ static int rkn4_step(double *y, const double *u1, const double *um, const double
 static int interval(const double *xk, const double *u0, const double *u1, double tf, double dtau, int n_sub,
                     const orc_params *p, int j2, double *out)
 {
-    double y[56], k1[56], k2[56], k3[56], k4[56], yt[56];
+    double y[56], k1[56], k2[56], k3[56], k4[56], yt[56], ypend[56];
     memset(y, 0, sizeof y);
     for (int i = 0; i < 7; ++i) {
         y[i * 7 + i] = 1.0;
@@ -245,6 +246,14 @@ static int interval(const double *xk, const double *u0, const double *u1, double
     }
     double accBp[21] = {0}, accBn[21] = {0}, accS[7] = {0}, accX[7] = {0};
     double h = dtau / n_sub;
+    /* scheme 2 (default, what the CUDA kernels do): integrator steps spanning two nodes with a Hermite midpoint, where
+     * the step is short against the local orbital rate (omega H <= 3.2e-3 rad) and the number of panels is even;
+     * one step per node otherwise */
+    int use_pair = 0;
+    if (g_scheme == 2 && !p->include_drag && n_sub % 2 == 0) {
+        double rn = norm3(xk), H = 2.0 * tf * h;
+        use_pair = (p->MU * H * H / (rn * rn * rn) <= 1.0e-5);
+    }
     for (int n = 0; n <= n_sub; ++n) {
         double lam_p = (double)n / n_sub, lam_n = 1.0 - lam_p;
         double un[3];
@@ -288,7 +297,38 @@ static int interval(const double *xk, const double *u0, const double *u1, double
             um[i] = (1.0 - lm) * u0[i] + lm * u1[i];
             ue[i] = (1.0 - le) * u0[i] + le * u1[i];
         }
-        if (g_scheme == 1 && !p->include_drag) {
+        if (use_pair) {
+            /* RKN4 steps spanning TWO quadrature nodes; the odd node from the cubic Hermite interpolant of the step
+             * (positions and velocities at both ends), the mass there from the quadratic through the three mdot values */
+            if (n % 2 == 1) {   /* odd node done: move on to the end of the pending step */
+                memcpy(y, ypend, sizeof y);
+                continue;
+            }
+            double u2m[3], u2e[3];
+            double l1 = (n + 1.0) / n_sub, l2 = (n + 2.0) / n_sub;
+            for (int i = 0; i < 3; ++i) {
+                u2m[i] = (1.0 - l1) * u0[i] + l1 * u1[i];
+                u2e[i] = (1.0 - l2) * u0[i] + l2 * u1[i];
+            }
+            const double H = 2.0 * tf * h, ve = p->G0 * p->ISP;
+            const double md1 = -norm3(un) / ve, mdm = -norm3(u2m) / ve, mde = -norm3(u2e) / ve;
+            memcpy(ypend, y, sizeof y);
+            if (rkn4_step(ypend, un, u2m, u2e, H, p, j2)) return 1;
+            double ymid[56];
+            memcpy(ymid, y, sizeof y);
+            for (int i = 0; i < 3; ++i) {
+                for (int j = -1; j < 7; ++j) {   /* j = -1: the state, j >= 0: column j of Phi */
+                    int ip = (j < 0) ? 49 + i : i * 7 + j, iv = (j < 0) ? 52 + i : (3 + i) * 7 + j;
+                    double p0 = y[ip], p1 = ypend[ip], v0 = y[iv], v1 = ypend[iv];
+                    ymid[ip] = 0.5 * (p0 + p1) + H / 8.0 * (v0 - v1);
+                    ymid[iv] = 1.5 * (p1 - p0) / H - 0.25 * (v0 + v1);
+                }
+            }
+            ymid[55] = y[55] + H * (5.0 * md1 + 8.0 * mdm - mde) / 24.0;
+            memcpy(y, ymid, sizeof y);
+            continue;
+        }
+        if (g_scheme >= 1 && !p->include_drag) {
             if (rkn4_step(y, un, um, ue, tf * h, p, j2)) return 1;
             continue;
         }

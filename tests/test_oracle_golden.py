@@ -243,3 +243,25 @@ def test_c_oracle_drag_branch_vs_reference(tag):
     out = C.discretize_batch_adaptive(g[tag + "_x"][None], g[tag + "_u"][None], 1.0, c, include_J2=j2, drag=drag)
     for nm, o, r in zip(NAMES, [_sel(a[0], ks) for a in out[:5]], [g[f"{tag}_def_{n}"] for n in NAMES]):
         assert rel_err(o, r) < 1e-10, nm
+
+
+def test_c_oracle_integration_schemes_agree(gold_disc, const):
+    """The three fixed-step schemes of the oracle on the reference's tangential scenario (K=200, tf=2): classical RK4
+    on the 56-vector, Nystrom's 3-stage method per node, and the default (two-node steps + Hermite midpoint) differ by
+    rounding / 1e-13, far below the reference's own 1e-10; all are 4th order (halving the step divides the error by ~16)."""
+    x, u = gold_disc["d3_x"][None], gold_disc["d3_u"][None]
+    res = {}
+    try:
+        for sch in ("rk4", "rkn4", "rkn4x2"):
+            C.set_scheme(sch)
+            res[sch] = C.discretize_batch(x, u, 2.0, const)
+        for a, b in (("rkn4", "rk4"), ("rkn4x2", "rkn4")):
+            for nm, p, q in zip(NAMES, res[a][:5], res[b][:5]):
+                assert rel_err(p, q) < 1e-12, (a, b, nm)
+        xs, us = x[:, :, :20], u[:, :, :20]             # 19 intervals of 0.42 orbit: coarse on purpose
+        C.set_scheme("rkn4")
+        fine = C.discretize_batch(xs, us, 8.0, const, n_sub=400)[0]
+        e8, e16 = (rel_err(C.discretize_batch(xs, us, 8.0, const, n_sub=n)[0], fine) for n in (8, 16))
+        assert 10.0 < e8 / e16 < 24.0
+    finally:
+        C.set_scheme("rkn4x2")
