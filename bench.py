@@ -32,20 +32,26 @@ FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SM x 64 DFMA/clk 
 
 
 def flops_per_interval(n_sub, include_j2=False):
-    """ALGORITHMIC FP64 work of one interval: the arithmetic of the algorithm DESIGN.md section 4 states
-    (42 live Phi entries, symmetric G, Nystrom's 3-stage fourth-order Runge-Kutta method in step-normalised variables,
-    symplectic inverse, 56 accumulators), FMA = 2 flop, mul/add = 1, MUFU seeds not counted.  One thread does one
-    interval with no recomputation, so this equals the executed DFMA/DMUL/DADD count: per step + quadrature node
-    532 FMA + 182 mul + 55 add (J2: 571 / 230 / 69), plus the last node and the Phi_end * [integrals] epilogue
-    (1249 flop; J2 1310).  Counted from the SASS of the shipped kernel (scripts/sass_reuse.py) and cross-checked
-    against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/)."""
-    per_step = (2 * 571 + 230 + 69) if include_j2 else (2 * 532 + 182 + 55)
-    return n_sub * per_step + (1310 if include_j2 else 1249)
+    """ALGORITHMIC FP64 work of one interval: the arithmetic of the algorithm DESIGN.md section 4 states (42 live Phi
+    entries, symmetric G, Nystrom's 3-stage fourth-order Runge-Kutta method in step-normalised variables with steps that
+    span two quadrature nodes and a cubic-Hermite midpoint, symplectic inverse, 56 accumulators), FMA = 2 flop,
+    mul/add = 1, MUFU seeds not counted.  One thread does one interval with no recomputation, so this equals the
+    executed DFMA/DMUL/DADD count: per integrator step (= two quadrature nodes) 754 FMA + 242 mul + 99 add (J2: 798 /
+    298 / 116), plus the last node and the Phi_end * [integrals] epilogue (1249 flop; J2 1310).  An odd n_sub runs one
+    step per node (532 / 182 / 55; J2 571 / 230 / 69).  Counted from the SASS of the shipped kernel
+    (scripts/sass_reuse.py) and cross-checked against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on."""
+    tail = 1310 if include_j2 else 1249
+    if n_sub % 2 == 0:
+        return (n_sub // 2) * ((2 * 798 + 298 + 116) if include_j2 else (2 * 754 + 242 + 99)) + tail
+    return n_sub * ((2 * 571 + 230 + 69) if include_j2 else (2 * 532 + 182 + 55)) + tail
 
 
 def fp64_instr_per_interval(n_sub, include_j2=False):
     """FP64-pipe instructions (DFMA+DMUL+DADD) per interval: the pipe-occupancy view of the same work."""
-    return n_sub * ((571 + 230 + 69) if include_j2 else (532 + 182 + 55)) + (785 if include_j2 else 742)
+    tail = 785 if include_j2 else 742
+    if n_sub % 2 == 0:
+        return (n_sub // 2) * ((798 + 298 + 116) if include_j2 else (754 + 242 + 99)) + tail
+    return n_sub * ((571 + 230 + 69) if include_j2 else (532 + 182 + 55)) + tail
 
 
 def bytes_per_interval():
@@ -198,7 +204,7 @@ def workload_config(args):
     return {"workload": f"{args.sats} satellites x K={args.nodes} nodes ({args.sats * (args.nodes - 1)} intervals) per GPU: "
                         "propagate (tangential thrust 0.5, no drag/J2) + discretize, BASELINE configs[2]",
             "sats_per_gpu": args.sats, "K": args.nodes, "tf": args.tf, "integrator_steps": args.n_sub + 1,
-            "integrator": "fixed-step fourth-order Runge-Kutta-Nystrom (3 stages), trapezoid on the step nodes", "l2": "flushed between timed steps (256 MiB write)",
+            "integrator": "fixed-step fourth-order Runge-Kutta-Nystrom (3 stages), one step per two quadrature nodes with a cubic-Hermite midpoint, trapezoid on all integrator_steps nodes", "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": f"satellites sharded over {args.gpus} GPU(s)" + (f", all-gather of the SoA matrices inside the step ({args.gather})" if args.gpus > 1 else "")}
 
 
@@ -432,7 +438,7 @@ def gpu_arm(args):
                                     "frac": (2084 * n_sub + 1386) * n_int / (disc_ms_avg * 1e-3) / 1e12 / peak_tflops},
                      "fp64_pipe_frac": fp64_instr_per_interval(n_sub) * n_int / (disc_ms_avg * 1e-3) / (peak_tflops * 1e12 / 2),
                      "fp64_pipe_note": "FP64 instructions issued / (measured DFMA issue rate): DMUL/DADD occupy a DFMA slot but count 1 flop",
-                     "kernel": "mpc::discretize_kernel",
+                     "kernel": "mpc::discretize_pair_kernel",
                      "hbm": {"achieved": bytes_per_interval() * n_int / (disc_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "peak_source": hbm_src, "bytes_per_interval": bytes_per_interval()}},
         "clocks": clocks,

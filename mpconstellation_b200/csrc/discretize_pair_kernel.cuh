@@ -68,18 +68,31 @@ struct NodeVec {
 // Contribution of ONE column of Phi (values pr, pv at the node) to the quadrature accumulators: column 3+a gives row a
 // of every Phi^-1 product (TOP), column a gives row 3+a (see node_accumulate for the algebra; s = +1 / -1).
 #define ACC(e) acc[(e) * BLOCK]
+// Split in two so that the caller can issue the eight shared-memory loads BEFORE it steps the column: their latency
+// then hides behind the column's arithmetic instead of stalling the accumulation (the accesses are volatile, they stay
+// where the source puts them).
+struct ColAcc {
+    double A0[3], A1[3], AS, AX;
+};
+
 template <int BLOCK, bool TOP>
-__device__ __forceinline__ void node_accumulate_column(volatile double *acc, int a, const double (&pr)[3], const double (&pv)[3],
-                                                       const NodeVec &n)
+__device__ __forceinline__ void column_acc_load(volatile double *acc, int a, ColAcc &c)
 {
     const int i0 = (TOP ? 0 : 9) + a * 3, i1 = (TOP ? 18 : 27) + a * 3, is = (TOP ? 36 : 39) + a, ix = (TOP ? 42 : 45) + a;
-    double A0[3], A1[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        A0[j] = ACC(i0 + j);
-        A1[j] = ACC(i1 + j);
+        c.A0[j] = ACC(i0 + j);
+        c.A1[j] = ACC(i1 + j);
     }
-    double AS = ACC(is), AX = ACC(ix);
+    c.AS = ACC(is);
+    c.AX = ACC(ix);
+}
+
+template <int BLOCK, bool TOP>
+__device__ __forceinline__ void node_accumulate_column(volatile double *acc, int a, const double (&pr)[3], const double (&pv)[3],
+                                                       const NodeVec &n, const ColAcc &c)
+{
+    const int i0 = (TOP ? 0 : 9) + a * 3, i1 = (TOP ? 18 : 27) + a * 3, is = (TOP ? 36 : 39) + a, ix = (TOP ? 42 : 45) + a;
     // e = s (pr.cv - pv.cr),  dv = pv.v,  pa = pr.a,  pg = pr.(G r)
     double e = pr[0] * n.cv[0], dv = pv[0] * n.vv[0], pa = pr[0] * n.aa[0], pg = pr[0] * n.gg[0];
 #pragma unroll
@@ -99,11 +112,11 @@ __device__ __forceinline__ void node_accumulate_column(volatile double *acc, int
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const double q = fma(n.b[j], e, sim * pr[j]);               // b_j e - s im pr_j
-        ACC(i0 + j) = fma(n.w, q, A0[j]);
-        ACC(i1 + j) = fma(n.ws, q, A1[j]);
+        ACC(i0 + j) = fma(n.w, q, c.A0[j]);
+        ACC(i1 + j) = fma(n.ws, q, c.A1[j]);
     }
-    ACC(is) = fma(n.w, S, AS);
-    ACC(ix) = fma(n.w, X, AX);
+    ACC(is) = fma(n.w, S, c.AS);
+    ACC(ix) = fma(n.w, X, c.AX);
 }
 
 template <bool J2, int BLOCK, int MAXREG, int NDST>
@@ -249,6 +262,14 @@ discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ 
             s3.dy = -qy * i3;
             s3.dz = -qz * i3;
         }
+        // row-6 accumulators of the middle node: loaded here, used after the state update (latency hidden)
+        double r6a[3], r6b[3];
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+            r6a[jj] = ACC(48 + jj);
+            r6b[jj] = ACC(51 + jj);
+        }
+        const double r6s = ACC(54), r6x = ACC(55);
         // ---- state: end of the step and Hermite midpoint ----------------------------------------------------------
         NodeVec nv;
         {
@@ -287,20 +308,23 @@ discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ 
             // row 6 of the middle node: Phi^-1 row 6 = e7^T
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj) {
-                ACC(48 + jj) = ACC(48 + jj) + nv.b[jj];
-                ACC(51 + jj) = fma(nv.ws, nv.b[jj], ACC(51 + jj));
+                ACC(48 + jj) = r6a[jj] + nv.b[jj];
+                ACC(51 + jj) = fma(nv.ws, nv.b[jj], r6b[jj]);
             }
-            ACC(54) = ACC(54) + nv.md;
-            ACC(55) = ACC(55) - nv.mdb;
+            ACC(54) = r6s + nv.md;
+            ACC(55) = r6x - nv.mdb;
         }
         // ---- variational columns: step, and the middle node's terms column by column -------------------------------
         column_step_mid<true>(pr[6], pv[6], s1, s2, s3, nv.cr, nv.cv);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             double mr[3], mv[3];
+            ColAcc ca;
+            if (c < 3) column_acc_load<BLOCK, false>(acc, c, ca);
+            else column_acc_load<BLOCK, true>(acc, c - 3, ca);
             column_step_mid<false>(pr[c], pv[c], s1, s2, s3, mr, mv);
-            if (c < 3) node_accumulate_column<BLOCK, false>(acc, c, mr, mv, nv);
-            else node_accumulate_column<BLOCK, true>(acc, c - 3, mr, mv, nv);
+            if (c < 3) node_accumulate_column<BLOCK, false>(acc, c, mr, mv, nv, ca);
+            else node_accumulate_column<BLOCK, true>(acc, c - 3, mr, mv, nv, ca);
         }
         ux = uex;
         uy = uey;
