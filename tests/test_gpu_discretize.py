@@ -300,6 +300,14 @@ def test_zero_and_mixed_thrust_and_single_step(M, const, adaptive):
         res = M.discretize_batch(x, u, 0.6, const, adaptive=dict())
         assert np.array_equal(res.n_nodes, ref[6])
     else:
+        # n_sub = 200: short steps, even panel count -> the two-node-step path of the kernel (and of the oracle)
+        r2 = C.discretize_batch(x, u, 0.6, const, n_sub=200)
+        g2 = M.discretize_batch(x, u, 0.6, const, n_sub=200)
+        assert g2.status.max() == 0 and r2[5].max() == 0
+        for n, o, r in zip(NAMES, g2.stacked(), r2[:5]):
+            assert rel_err(o, r) < TOL_ORACLE, ("n_sub=200", n)
+        assert not np.any(g2.stacked()[1][0, :, 6, :]) and not np.any(g2.stacked()[1][7, :, 6, :])
+        # n_sub = 25: odd -> one step per node
         ref = C.discretize_batch(x, u, 0.6, const, n_sub=25)
         res = M.discretize_batch(x, u, 0.6, const, n_sub=25)
         # n_sub = 1 (two quadrature nodes): on a short horizon, where one RK4 step is accurate and the symplectic
@@ -314,3 +322,25 @@ def test_zero_and_mixed_thrust_and_single_step(M, const, adaptive):
     Bp, Bn = res.stacked()[1], res.stacked()[2]
     assert not np.any(Bp[0, :, 6, :]) and not np.any(Bn[0, :, 6, :])      # coasting: no mass-flow sensitivity (row 6 of B)
     assert not np.any(Bp[7, :, 6, :])                                     # |u| <= eps: the guard zeroes that row
+
+
+def test_two_node_steps_and_one_step_per_node_agree(M, const):
+    """mpc_set_tuning(7) switches the two-node steps (Hermite midpoint) off: on the reference's kind of grid the two
+    integrators agree to ~1e-12, and a batch mixing short and long intervals (per-satellite tf: some threads take the
+    two-node path, some fall back) matches the oracle, which makes the same per-interval choice"""
+    from oracle import c_oracle as C
+    from mpconstellation_b200 import _lib
+    _, x, u = synth_batch(40, 60, 0.6, const)
+    a = M.discretize_batch(x, u, 0.6, const, n_sub=100).soa.copy()
+    try:
+        _lib.check(_lib.lib().mpc_set_tuning(7))
+        b = M.discretize_batch(x, u, 0.6, const, n_sub=100).soa.copy()
+    finally:
+        _lib.check(_lib.lib().mpc_set_tuning(8))
+    assert not np.array_equal(a, b) and rel_err(a, b) < 1e-11
+    tfv = np.where(np.arange(40) % 2 == 0, 0.3, 3.0)           # 0.005- and 0.05-orbit intervals side by side
+    ref = C.discretize_batch(x, u, tfv, const, n_sub=100)
+    res = M.discretize_batch(x, u, tfv, const, n_sub=100)
+    assert res.status.max() == 0
+    for n, o, r in zip(NAMES, res.stacked(), ref[:5]):
+        assert rel_err(o, r) < TOL_ORACLE, n
