@@ -99,7 +99,11 @@ int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc
  *   x   [n_sats][7][K]   reference trajectories (scaled states)            discretize() arg `x`
  *   u   [n_sats][3][K]   reference inputs on the same K nodes              discretize() arg `u`
  *   tf  [n_sats]         reference final time per satellite                discretize() arg `tf`
- *   n_sub                fixed fourth-order Runge-Kutta(-Nystrom) steps per interval = integrator_steps - 1
+ *   n_sub                trapezoid panels per interval = integrator_steps - 1 (quadrature nodes = n_sub + 1).  The
+ *                        integrator (fixed-step fourth-order Runge-Kutta-Nystrom) takes one step per panel, or one
+ *                        step per TWO panels with the node in between read off the step's cubic Hermite interpolant
+ *                        where that is accurate to ~1e-12 (even n_sub, step short against the orbital rate; decided
+ *                        per interval on the device; mpc_set_tuning(7) forces one step per panel everywhere)
  *   out                  SoA, out[row * out_pitch + out_offset + s*(K-1) + k], row in [0,105)
  *   status [n_sats*(K-1)] MPC_ST_* per interval (may be NULL)
  *
@@ -281,8 +285,9 @@ int mpc_fp64_peak_probe(int device, int repeats, double *tflops, double *ms);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches evidence). */
 int64_t mpc_launch_count(void);
 
-/* Experiment knob: selects an alternative block-size / register-cap build of the discretization kernel
- * (0 = production).  Results are identical; only occupancy differs.  See DESIGN.md, tuning table. */
+/* Experiment knob: 1..6 select an alternative block-size / register-cap build of the one-step-per-node discretization
+ * kernel (0 = production; results identical, only occupancy differs; DESIGN.md, tuning table).  7 / 8 switch the
+ * two-node integrator steps of the production kernel off / on (results differ by ~1e-12). */
 int mpc_set_tuning(int variant);
 
 /* Options of the fused (in-kernel store) all-gather, applied by mpc_discretize_batch / _multi:

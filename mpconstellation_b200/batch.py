@@ -93,7 +93,7 @@ def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_su
     x [N,7,K], u [N,3,K], tf scalar or [N]; `out` may be a preallocated (ideally pinned) [105, N*(K-1)]
     array.  Returns a DiscretizedBatch.  ref: linearize_discretize.py:334-390 / :8-82.
 
-    adaptive=None: fixed-step fourth-order Runge-Kutta(-Nystrom) with n_sub steps, trapezoid on the n_sub+1 step nodes (the reference's
+    adaptive=None: fixed-step fourth-order Runge-Kutta-Nystrom, trapezoid on n_sub+1 nodes (the reference's
     use_uniform_steps=True node set).  adaptive=dict(rtol=1e-3, atol=1e-6, max_step=1e-2): the reference's
     default mode, quadrature on the steps scipy's RK45 controller accepts; the result carries `.n_nodes`.
 
