@@ -80,7 +80,7 @@ def make_constellation(n_sats, seed=20240531):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index=0, period=0.02):
+    def __init__(self, index=0, period=0.004):
         super().__init__(daemon=True)
         self.period, self.samples, self.reasons, self.max_mhz = period, [], set(), None
         self._halt = threading.Event()
