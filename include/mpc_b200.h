@@ -216,6 +216,32 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
                                   double *out_host, int32_t *status_host);
 
 /*
+ * The same SCP inner step on DEVICE buffers, enqueued on `stream`, with the propagation overlapped with the
+ * discretization (control.py:180-188: run_nonlinear -> extract_uk -> Discretizer.discretize, for every satellite).
+ * The propagation is sequential in tau and latency-bound; interval k only needs the samples k and k+1.  The intervals
+ * are cut into `n_windows` windows along k (0 = default, 16); the propagation kernel publishes a progress word per
+ * window and the discretization of window b is gated on it by a stream memory operation (cuStreamWaitValue32) on an
+ * internal stream -- no kernel spins.  Results (x [N][7][T], u [N][3][T], the SoA matrices, both status arrays) are
+ * bit-identical to mpc_propagate_batch followed by mpc_discretize_batch.  Batches too small for windows to fill the
+ * machine, and the drag branch, run the two kernels back to back on `stream`.  ctrl->table / end_tau_per_sat are
+ * device pointers (as in mpc_propagate_batch).  One call per ctx may be in flight at a time; `stream` continues only
+ * when everything has finished.
+ */
+int mpc_propagate_discretize(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                             const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T, int n_sub_prop,
+                             int n_sub_disc, double *x, double *u, double *out, int64_t out_pitch, int64_t out_offset,
+                             int32_t *status_prop, int32_t *status_disc, int n_windows, void *stream);
+
+/* mpc_propagate_discretize with the multi-destination store of mpc_discretize_batch_multi (fused all-gather: dst[0] is
+ * the local buffer, dst[1..] peer-mapped buffers of the same layout; n_dst = 1, 2, 4 or 8; honours
+ * mpc_set_gather_tuning, the staggered start applying to the first window only). */
+int mpc_propagate_discretize_multi(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                   const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                   int n_sub_prop, int n_sub_disc, double *x, double *u, double *const *dst, int n_dst,
+                                   int64_t out_pitch, int64_t out_offset, int32_t *status_prop, int32_t *status_disc,
+                                   int n_windows, void *stream);
+
+/*
  * All-gather of the discretized matrices by the COPY ENGINES, overlapped with the kernel: the batch is discretized
  * in chunks of `chunk_waves` full waves of the kernel into dst[0] (local); as soon as a chunk is done its columns
  * are pushed to dst[1..n_dst-1] (peer-mapped buffers of the other ranks, same layout) by cudaMemcpy2DAsync on one

@@ -319,6 +319,62 @@ def propagate_batch_device(y0, tf, controller, const, include_drag=True, include
     return y, u_out, status
 
 
+def propagate_discretize_device(y0, tf, controller, const, T, prop_drag=False, prop_J2=False, disc_J2=False,
+                                n_sub_prop=None, n_sub_disc=100, y=None, u_out=None, out=None, out_pitch=None,
+                                out_offset=0, status_prop=None, status_disc=None, n_windows=0, extra_dst=None,
+                                out_ptr=None):
+    """Device form of propagate_discretize: one SCP linearization pass (control.py:180-188) on CUDA tensors, enqueued on
+    torch's current stream, with the propagation overlapped with the discretization (mpc_propagate_discretize: the
+    intervals are discretized window by window along k as the propagation publishes its progress).  Bit-identical to
+    propagate_batch_device followed by discretize_batch_device.  y0 [N,7], tf [N] float64 CUDA tensors; K = T.
+    `extra_dst`: further [105, pitch] buffers (tensors or raw peer-mapped addresses) every result is also stored to
+    (total 1, 2, 4 or 8: the fused all-gather); `out_ptr`: raw address used instead of out.data_ptr() (a multicast
+    mapping of `out`).  Returns (out [105, pitch], y [N,7,T], u [N,3,T], status_prop [N], status_disc [N*(T-1)])."""
+    torch = _torch()
+    N = y0.shape[0]
+    T = int(T)
+    dev = y0.device
+    assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous() and y0.shape == (N, 7) and tf.shape == (N,)
+    n_int = N * (T - 1)
+    spec = spec_from(controller)
+    if n_sub_prop is None:
+        n_sub_prop = default_n_sub(T)
+    if y is None:
+        y = torch.empty((N, 7, T), dtype=torch.float64, device=dev)
+    if u_out is None:
+        u_out = torch.empty((N, 3, T), dtype=torch.float64, device=dev)
+    if out is None:
+        out = torch.empty((_lib.MPC_OUT_ROWS, n_int), dtype=torch.float64, device=dev)
+    pitch = out.shape[1] if out_pitch is None else int(out_pitch)
+    if status_prop is None:
+        status_prop = torch.empty(N, dtype=torch.int32, device=dev)
+    if status_disc is None:
+        status_disc = torch.empty(n_int, dtype=torch.int32, device=dev)
+    assert y.shape == (N, 7, T) and u_out.shape == (N, 3, T) and y.is_contiguous() and u_out.is_contiguous()
+    tab_dev = et_dev = None
+    if spec.kind == _lib.CTRL_SEQUENCE:
+        tab_dev = torch.as_tensor(spec.table, dtype=torch.float64).to(dev).contiguous()
+        if np.ndim(spec.end_tau) != 0:
+            et_dev = torch.as_tensor(np.asarray(spec.end_tau, dtype=np.float64)).to(dev).contiguous()
+    c, _keep = _ctrl_struct(spec, N, table_addr=tab_dev.data_ptr() if tab_dev is not None else None,
+                            end_tau_addr=et_dev.data_ptr() if et_dev is not None else None)
+    pp = _lib.make_params(const, prop_J2, prop_drag)
+    pd = _lib.make_params(const, disc_J2, False)
+    cur = torch.cuda.current_stream(dev)
+    ptrs = [int(out_ptr) if out_ptr is not None else out.data_ptr()]
+    ptrs += [int(d_ if isinstance(d_, int) else d_.data_ptr()) for d_ in (extra_dst or [])]
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    _lib.check(_lib.lib().mpc_propagate_discretize_multi(
+        _ctx(dev.index if dev.index is not None else torch.cuda.current_device()), y0.data_ptr(), tf.data_ptr(),
+        ctypes.byref(pp), ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop), int(n_sub_disc), y.data_ptr(),
+        u_out.data_ptr(), arr, len(ptrs), pitch, int(out_offset), status_prop.data_ptr(), status_disc.data_ptr(),
+        int(n_windows), cur.cuda_stream))
+    for t_ in (tab_dev, et_dev):
+        if t_ is not None:
+            t_.record_stream(cur)
+    return out, y, u_out, status_prop, status_disc
+
+
 def fp64_peak_tflops(device=0, repeats=5):
     _lib.require_gpu()
     tf_, ms = ctypes.c_double(), ctypes.c_double()

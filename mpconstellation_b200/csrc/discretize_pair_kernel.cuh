@@ -123,12 +123,14 @@ template <bool J2, int BLOCK, int MAXREG, int NDST>
 __global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG)
 discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ tf_arr,
                        DiscParams P, int n_sats, int K, int n_sub, DstTab dst, long long pitch, long long offset,
-                       int32_t *__restrict__ status)
+                       int32_t *__restrict__ status, int k0, int kc)
 {
+    // The launch covers the intervals k in [k0, k0 + kc) of every satellite (the whole batch: k0 = 0, kc = K - 1).  A
+    // window of k is what the overlapped propagate -> discretize pass launches as soon as the propagation has produced
+    // the samples up to k0 + kc (mpc_propagate_discretize).  gid is the interval's global index s (K-1) + k either way.
     extern __shared__ double acc_smem[];
-    const long long n_int = (long long)n_sats * (K - 1);
-    const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
-    if (gid >= n_int) return;
+    const long long tid = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (tid >= (long long)n_sats * kc) return;
     if (dst.stagger_phases > 1 && (int)blockIdx.x < dst.first_wave_ctas) {
         const long long wait = dst.stagger_cycles * (long long)(blockIdx.x % dst.stagger_phases) / dst.stagger_phases;
         const long long t0 = clock64();
@@ -136,8 +138,9 @@ discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ 
     }
     volatile double *acc = acc_smem + threadIdx.x;
 
-    const int s = (int)(gid / (K - 1));
-    const int k = (int)(gid - (long long)s * (K - 1));
+    const int s = (int)(tid / kc);
+    const int k = k0 + (int)(tid - (long long)s * kc);
+    const long long gid = (long long)s * (K - 1) + k;
     const double tf = tf_arr[s];
     const double *xs = x + ((long long)s * 7) * K + k;
     double rx = xs[0], ry = xs[K], rz = xs[2 * (long long)K];

@@ -2,6 +2,7 @@
 // point either launches CUDA work or returns an error.
 #include "../../include/mpc_b200.h"
 
+#include <cuda.h>   // types of the stream memory operations only; the entry point is fetched at run time
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -43,6 +44,7 @@ int fail(int code, const char *fmt, ...)
 
 constexpr int kDiscBlock = 128;
 constexpr int kPropBlock = 32;
+constexpr int kPropBlockOverlap = 128;
 
 mpc::DiscParams disc_params(const mpc_params *p)
 {
@@ -100,8 +102,9 @@ int launch_disc_cfg(const double *x, const double *u, const double *tf, const mp
 template <bool J2, int BLOCK, int MAXREG, int NDST>
 int launch_pair_cfg(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                     int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
-                    cudaStream_t st)
+                    cudaStream_t st, int k0 = 0, int kc = -1)
 {
+    if (kc < 0) kc = K - 1;   // the whole batch
     auto kern = mpc::discretize_pair_kernel<J2, BLOCK, MAXREG, NDST>;
     const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
@@ -112,9 +115,9 @@ int launch_pair_cfg(const double *x, const double *u, const double *tf, const mp
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured_dev = dev;
     }
-    const long long n_int = (long long)n_sats * (K - 1);
+    const long long n_int = (long long)n_sats * kc;
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, k0, kc);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
@@ -335,9 +338,11 @@ int check_ctrl(const mpc_controller *c)
     return MPC_SUCCESS;
 }
 
+// progress / seg_len: see propagate_kernel (the overlapped pass); then the CTAs are 4 warps instead of 1, so that the
+// propagation occupies 32 SMs instead of 128 while the discretization runs beside it
 int prop_device(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *c,
                 const double *table_dev, const double *end_tau_dev, int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status,
-                cudaStream_t st)
+                cudaStream_t st, unsigned int *progress = nullptr, int seg_len = 0)
 {
     if (!y0 || !tf || !p || !y) return fail(MPC_E_INVALID, "null pointer argument");
     if (n_sats < 0 || T < 0 || n_sub < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 0, n_sub >= 1");
@@ -356,10 +361,18 @@ int prop_device(const double *y0, const double *tf, const mpc_params *p, const m
     C.table = (c->kind == MPC_CTRL_SEQUENCE) ? table_dev : nullptr;
     C.end_tau_arr = (c->kind == MPC_CTRL_SEQUENCE) ? end_tau_dev : nullptr;
     const unsigned grid = (unsigned)((n_sats + kPropBlock - 1) / kPropBlock);
+    const unsigned grid_ov = (unsigned)((n_sats + kPropBlockOverlap - 1) / kPropBlockOverlap);
     const mpc::PropParams PP = prop_params(p);
     // one straight-line kernel per (controller law, drag, J2)
-#define MPC_PROP(KIND, DRAG, J2) \
-    mpc::propagate_kernel<kPropBlock, KIND, DRAG, J2><<<grid, kPropBlock, 0, st>>>(y0, tf, PP, C, n_sats, T, n_sub, y, u_out, status)
+#define MPC_PROP(KIND, DRAG, J2)                                                                                          \
+    do {                                                                                                                  \
+        if (progress)                                                                                                     \
+            mpc::propagate_kernel<kPropBlockOverlap, KIND, DRAG, J2><<<grid_ov, kPropBlockOverlap, 0, st>>>(              \
+                y0, tf, PP, C, n_sats, T, n_sub, y, u_out, status, progress, seg_len);                                    \
+        else                                                                                                              \
+            mpc::propagate_kernel<kPropBlock, KIND, DRAG, J2><<<grid, kPropBlock, 0, st>>>(y0, tf, PP, C, n_sats, T,      \
+                                                                                           n_sub, y, u_out, status);     \
+    } while (0)
 #define MPC_PROP_K(KIND)                                   \
     do {                                                   \
         if (p->include_drag) {                             \
@@ -399,6 +412,10 @@ struct mpc_ctx {
     cudaStream_t s_aux[3] = {};              // compute streams the chunk kernels of the push gather rotate over
     cudaStream_t s_push[MPC_MAX_DST] = {};   // one stream per peer for the copy-engine gather (mpc_discretize_batch_push)
     std::vector<cudaEvent_t> ev_push;       // [chunk] kernel-done events + [MPC_MAX_DST] stream-join events
+    // overlapped propagate -> discretize pass (mpc_propagate_discretize)
+    cudaStream_t s_prop = nullptr, s_win[2] = {};   // propagation (highest priority) / discretization windows
+    cudaEvent_t ev_ov[4] = {};                      // fork + three joins
+    unsigned int *d_progress = nullptr;             // [kMaxWindows] warps of the propagation past each window's last sample
     int32_t *h_stage = nullptr;  // pinned staging for the int32 status / node-count words (caller buffers may be pageable)
     size_t cap_stage = 0;
     size_t cap_nodes = 0, cap_endtau = 0;
@@ -630,6 +647,12 @@ int mpc_ctx_destroy(mpc_ctx *c)
     for (cudaStream_t ps : c->s_aux)
         if (ps) cudaStreamDestroy(ps);
     if (c->s_pushk) cudaStreamDestroy(c->s_pushk);
+    if (c->s_prop) cudaStreamDestroy(c->s_prop);
+    for (cudaStream_t w : c->s_win)
+        if (w) cudaStreamDestroy(w);
+    for (cudaEvent_t e : c->ev_ov)
+        if (e) cudaEventDestroy(e);
+    cudaFree(c->d_progress);
     for (cudaEvent_t e : c->ev_push) cudaEventDestroy(e);
     cudaFree(c->d_x);
     cudaFree(c->d_u);
@@ -872,6 +895,166 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
     }
     return MPC_SUCCESS;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------- overlapped propagate -> discretize
+// One SCP linearization pass on device buffers (control.py:180-188: propagate -> extract_uk -> discretize) with the
+// propagation HIDDEN behind the discretization.  The propagation is sequential in tau and latency-bound (a handful of
+// warps, ~0.56 ms whatever the batch), the discretization fills the machine for milliseconds and interval k only needs
+// the samples k and k+1.  So the intervals are cut into n_windows windows along k; the propagation kernel publishes a
+// per-window progress word, and window b's discretization kernel is gated on it by a stream memory operation
+// (cuStreamWaitValue32) -- the dependency is resolved by the stream front end, no CTA ever spins on a flag, nothing can
+// deadlock.  Windows alternate over two streams so that the tail of one overlaps the head of the next.  Same kernels,
+// same arithmetic: the result is bit-identical to mpc_propagate_batch followed by mpc_discretize_batch.
+namespace {
+
+constexpr int kMaxWindows = 64;
+
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+StreamWaitValue32Fn stream_wait_value32()
+{
+    static StreamWaitValue32Fn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return (StreamWaitValue32Fn)f;
+    }();
+    return fn;
+}
+
+int ensure_overlap(mpc_ctx *ctx)
+{
+    if (ctx->s_prop) return MPC_SUCCESS;
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (cudaStream_t &w : ctx->s_win) CUDA_TRY(cudaStreamCreateWithFlags(&w, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : ctx->ev_ov) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc((void **)&ctx->d_progress, kMaxWindows * sizeof(unsigned int)));
+    CUDA_TRY(cudaStreamCreateWithPriority(&ctx->s_prop, cudaStreamNonBlocking, hi));
+    return MPC_SUCCESS;
+}
+
+}  // namespace
+
+namespace {
+
+template <bool J2>
+int launch_window(int n_dst, const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                  int n_sub, const mpc::DstTab &tab, long long pitch, long long offset, int32_t *status, cudaStream_t st,
+                  int k0, int kc)
+{
+    switch (n_dst) {
+        case 1: return launch_pair_cfg<J2, kDiscBlock, 255, 1>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, st, k0, kc);
+        case 2: return launch_pair_cfg<J2, kDiscBlock, 255, 2>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, st, k0, kc);
+        case 4: return launch_pair_cfg<J2, kDiscBlock, 255, 4>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, st, k0, kc);
+        case 8: return launch_pair_cfg<J2, kDiscBlock, 255, 8>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, st, k0, kc);
+        default: return fail(MPC_E_INVALID, "n_dst must be 1, 2, 4 or 8 (got %d)", n_dst);
+    }
+}
+
+int prop_disc_overlapped(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                         const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T, int n_sub_prop,
+                         int n_sub_disc, double *x, double *u, double *const *dst, int n_dst, int64_t out_pitch,
+                         int64_t out_offset, int32_t *status_prop, int32_t *status_disc, int n_windows, cudaStream_t st)
+{
+    if (!ctx || !y0 || !tf || !p_prop || !p_disc || !x || !u || !dst)
+        return fail(MPC_E_INVALID, "null pointer argument");
+    const int K = T;
+    int rc = check_disc_args(x, u, tf, p_disc, n_sats, K, n_sub_disc);
+    if (rc) return rc;
+    if (n_sub_prop < 1) return fail(MPC_E_INVALID, "need n_sub_prop >= 1");
+    if ((rc = check_ctrl(ctrl))) return rc;
+    if (n_dst != 1 && n_dst != 2 && n_dst != 4 && n_dst != 8) return fail(MPC_E_INVALID, "n_dst must be 1, 2, 4 or 8 (got %d)", n_dst);
+    for (int d = 0; d < n_dst; ++d)
+        if (!dst[d]) return fail(MPC_E_INVALID, "null destination %d", d);
+    const long long n_int = (long long)n_sats * (K - 1);
+    if (out_pitch < out_offset + n_int || out_offset < 0) return fail(MPC_E_INVALID, "out_pitch/out_offset do not hold the batch");
+    if (n_windows < 0 || n_windows > kMaxWindows) return fail(MPC_E_INVALID, "n_windows must be in [0, %d]", kMaxWindows);
+    if (n_sats == 0) return MPC_SUCCESS;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // Windows only pay when each of them still fills the machine (one wave = 2 CTAs of 128 threads per SM) and when the
+    // two-node-step kernel runs (the windowed launch exists for it); otherwise the two kernels run back to back.
+    const long long wave = (long long)ctx->sm_count * 2 * kDiscBlock;
+    int nw = n_windows ? n_windows : 16;
+    nw = (int)std::min<long long>(nw, std::min<long long>(n_int / wave, K - 1));
+    const bool windowed = nw >= 2 && !p_disc->include_drag && g_pair.load(std::memory_order_relaxed) &&
+                          g_tuning.load(std::memory_order_relaxed) == 0 && stream_wait_value32() != nullptr;
+    const double *tab_dev = ctrl->table, *et_dev = ctrl->end_tau_per_sat;
+    if (!windowed) {
+        if ((rc = prop_device(y0, tf, p_prop, ctrl, tab_dev, et_dev, n_sats, K, n_sub_prop, x, u, status_prop, st))) return rc;
+        return disc_device(x, u, tf, p_disc, n_sats, K, n_sub_disc, dst, n_dst, out_pitch, out_offset, status_disc, st);
+    }
+    if ((rc = ensure_overlap(ctx))) return rc;
+    const int seg = (K - 1 + nw - 1) / nw;         // intervals per window
+    nw = (K - 1 + seg - 1) / seg;
+    const unsigned int n_warps = (unsigned int)((n_sats + 31) / 32);
+    CUDA_TRY(cudaMemsetAsync(ctx->d_progress, 0, kMaxWindows * sizeof(unsigned int), st));
+    CUDA_TRY(cudaEventRecord(ctx->ev_ov[0], st));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_prop, ctx->ev_ov[0], 0));
+    for (cudaStream_t w : ctx->s_win) CUDA_TRY(cudaStreamWaitEvent(w, ctx->ev_ov[0], 0));
+    if ((rc = prop_device(y0, tf, p_prop, ctrl, tab_dev, et_dev, n_sats, K, n_sub_prop, x, u, status_prop, ctx->s_prop,
+                          ctx->d_progress, seg)))
+        return rc;
+    const mpc::DiscParams P = disc_params(p_disc);
+    mpc::DstTab tab{};
+    for (int d = 0; d < mpc::kMaxDst; ++d) tab.p[d] = (d < n_dst) ? dst[d] : nullptr;
+    tab.skip_const = g_gather_skip_const.load(std::memory_order_relaxed);
+    const int stagger = g_gather_stagger.load(std::memory_order_relaxed);
+    for (int b = 0; b < nw; ++b) {
+        cudaStream_t sw = ctx->s_win[b & 1];
+        const int k0 = b * seg, kc = std::min(seg, K - 1 - k0);
+        // the staggered start of the fused all-gather (mpc_set_gather_tuning) belongs to the very first wave only
+        tab.stagger_phases = (b == 0) ? stagger : 0;
+        if (tab.stagger_phases > 1) {
+            tab.first_wave_ctas = ctx->sm_count * 2;
+            tab.stagger_cycles = (long long)n_sub_disc * 4940LL;
+        }
+        const CUresult cr = stream_wait_value32()((CUstream)sw, (CUdeviceptr)(uintptr_t)(ctx->d_progress + b), n_warps,
+                                                  CU_STREAM_WAIT_VALUE_GEQ);
+        if (cr != CUDA_SUCCESS) return fail(MPC_E_CUDA, "cuStreamWaitValue32 failed (CUresult %d)", (int)cr);
+        rc = p_disc->include_j2
+                 ? launch_window<true>(n_dst, x, u, tf, P, n_sats, K, n_sub_disc, tab, out_pitch, out_offset, status_disc, sw, k0, kc)
+                 : launch_window<false>(n_dst, x, u, tf, P, n_sats, K, n_sub_disc, tab, out_pitch, out_offset, status_disc, sw, k0, kc);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_ov[1], ctx->s_prop));
+    CUDA_TRY(cudaEventRecord(ctx->ev_ov[2], ctx->s_win[0]));
+    CUDA_TRY(cudaEventRecord(ctx->ev_ov[3], ctx->s_win[1]));
+    for (int e = 1; e < 4; ++e) CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_ov[e], 0));
+    return MPC_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" int mpc_propagate_discretize(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                        const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                        int n_sub_prop, int n_sub_disc, double *x, double *u, double *out,
+                                        int64_t out_pitch, int64_t out_offset, int32_t *status_prop,
+                                        int32_t *status_disc, int n_windows, void *stream)
+{
+    if (!out) return fail(MPC_E_INVALID, "null pointer argument");
+    double *dst[1] = {out};
+    return prop_disc_overlapped(ctx, y0, tf, p_prop, p_disc, ctrl, n_sats, T, n_sub_prop, n_sub_disc, x, u, dst, 1,
+                                out_pitch, out_offset, status_prop, status_disc, n_windows, (cudaStream_t)stream);
+}
+
+extern "C" int mpc_propagate_discretize_multi(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                              const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                              int n_sub_prop, int n_sub_disc, double *x, double *u, double *const *dst,
+                                              int n_dst, int64_t out_pitch, int64_t out_offset, int32_t *status_prop,
+                                              int32_t *status_disc, int n_windows, void *stream)
+{
+    return prop_disc_overlapped(ctx, y0, tf, p_prop, p_disc, ctrl, n_sats, T, n_sub_prop, n_sub_disc, x, u, dst, n_dst,
+                                out_pitch, out_offset, status_prop, status_disc, n_windows, (cudaStream_t)stream);
+}
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------- copy-engine gather
 int mpc_fill_const_rows(double *out, int64_t out_pitch, void *stream)

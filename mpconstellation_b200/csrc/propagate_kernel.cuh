@@ -126,8 +126,12 @@ template <int BLOCK, int KIND, bool DRAG, bool J2>
 __global__ void __launch_bounds__(BLOCK)
 propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_arr, PropParams P, CtrlParams C,
                  int n_sats, int T, int n_sub, double *__restrict__ y_out, double *__restrict__ u_out,
-                 int32_t *__restrict__ status)
+                 int32_t *__restrict__ status, unsigned int *progress = nullptr, int seg_len = 0)
 {
+    // progress != nullptr: the kernel publishes how far it has come.  Window b of the discretization covers the intervals
+    // [b seg_len, min((b+1) seg_len, T-1)) and needs the samples up to e_b = min((b+1) seg_len, T-1): once every lane of a
+    // warp has stored sample e_b, the warp adds 1 to progress[b] (stores fenced first).  A stream memory operation on the
+    // discretization's stream waits for progress[b] == number of warps (mpc_propagate_discretize): no kernel ever spins.
     const int s = blockIdx.x * BLOCK + threadIdx.x;
     if (s >= n_sats) return;
     const double *tab = C.table ? C.table + (C.table_per_sat ? (long long)s * 3 * C.table_len : 0) : nullptr;
@@ -153,18 +157,24 @@ propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_ar
                 uo[T + j] = qnan;
                 uo[2 * (long long)T + j] = qnan;
             }
-            continue;
-        }
+        } else {
 #pragma unroll
-        for (int c = 0; c < 7; ++c) yo[(long long)c * T + j] = y[c];
-        if (uo) {
-            double ux, uy, uz;
-            const double irs = fast_rsqrt(fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2])));
-            ctrl_eval<KIND>(C, tab, end_tau, y, irs, tau_j, ux, uy, uz);
-            uo[j] = ux;
-            uo[T + j] = uy;
-            uo[2 * (long long)T + j] = uz;
+            for (int c = 0; c < 7; ++c) yo[(long long)c * T + j] = y[c];
+            if (uo) {
+                double ux, uy, uz;
+                const double irs = fast_rsqrt(fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2])));
+                ctrl_eval<KIND>(C, tab, end_tau, y, irs, tau_j, ux, uy, uz);
+                uo[j] = ux;
+                uo[T + j] = uy;
+                uo[2 * (long long)T + j] = uz;
+            }
         }
+        if (progress && j > 0 && (j == T - 1 || j % seg_len == 0)) {   // j is the last sample some window needs
+            __threadfence();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) atomicAdd(progress + ((j == T - 1) ? (T - 2) / seg_len : j / seg_len - 1), 1u);
+        }
+        if (bad) continue;
         if (j == T - 1) break;
         const double tau_n = (double)(j + 1) / Tm1;
         for (int n = 0; n < n_sub; ++n) {

@@ -147,6 +147,38 @@ class FusedGather:
             self.handle.barrier()
         return self.buf
 
+    def propagate_discretize(self, y0, tf, controller, const, include_J2=False, n_sub_prop=None, n_sub=100, y=None,
+                             u_out=None, status_prop=None, barrier=True, n_windows=0):
+        """One SCP linearization pass of this rank's shard with the all-gather fused in AND the propagation hidden
+        behind the discretization (`mpc_propagate_discretize_multi`): y0 [n_local,7], tf [n_local] CUDA float64.
+        Modes "unicast" and "multicast"; the push modes keep the two-kernel sequence.  Returns (buf, y, u, status_prop);
+        results are bit-identical to propagate_batch_device + discretize()."""
+        from . import batch
+        assert y0.shape[0] == self.s1 - self.s0
+        if self.mode in ("push", "pushk") or y0.shape[0] == 0:
+            y, u_out, status_prop = batch.propagate_batch_device(y0, tf, controller, const, include_drag=False,
+                                                                 include_J2=include_J2, T=self.K, n_sub=n_sub_prop,
+                                                                 y=y, u_out=u_out, status=status_prop)
+            self.discretize(y, u_out, tf, const, include_J2=include_J2, n_sub=n_sub, barrier=barrier)
+            return self.buf, y, u_out, status_prop
+        tuned = self.skip_const or self.stagger > 1
+        if tuned:
+            _lib.check(_lib.lib().mpc_set_gather_tuning((2 if self.mode == "multicast" else 1) if self.skip_const else 0,
+                                                        self.stagger))
+        try:
+            mc = self.mode == "multicast"
+            _, y, u_out, status_prop, _ = batch.propagate_discretize_device(
+                y0, tf, controller, const, self.K, prop_J2=include_J2, disc_J2=include_J2, n_sub_prop=n_sub_prop,
+                n_sub_disc=n_sub, y=y, u_out=u_out, out=self.buf, out_pitch=self.pitch,
+                out_offset=self.s0 * (self.K - 1), status_prop=status_prop, status_disc=self.status,
+                n_windows=n_windows, extra_dst=None if mc else self.dst[1:], out_ptr=self.mc_ptr if mc else None)
+        finally:
+            if tuned:
+                _lib.check(_lib.lib().mpc_set_gather_tuning(0, 0))
+        if barrier:
+            self.handle.barrier()
+        return self.buf, y, u_out, status_prop
+
     def _launch(self, x, u, tf, const, include_J2, n_sub):
         from . import batch
         if x.shape[0] > 0 and self.mode == "multicast":

@@ -170,3 +170,44 @@ def test_device_tensor_api(M, const):
                                         c, const, include_drag=False, include_J2=False, T=50)
     torch.cuda.synchronize()
     assert np.array_equal(y.cpu().numpy(), yh) and np.array_equal(u.cpu().numpy(), uh) and int(st.max()) == 0
+
+
+@pytest.mark.parametrize("case", ["windows_default", "windows_ragged_j2", "sequence_mass_failure", "small_batch", "odd_panels"])
+def test_overlapped_propagate_discretize_is_bit_identical(M, const, case):
+    """mpc_propagate_discretize (propagation hidden behind the discretization, windows along k gated by stream memory
+    operations) against the two kernels run back to back: same arithmetic, so every output must be bit-identical."""
+    import torch
+    dev = torch.device("cuda:0")
+    N, T, tf, n_sub, nw, j2 = {"windows_default": (2048, 120, 1.5, 20, 0, False),
+                               "windows_ragged_j2": (1500, 131, 2.0, 10, 7, True),
+                               "sequence_mass_failure": (1280, 100, 1.0, 10, 4, False),
+                               "small_batch": (5, 17, 0.5, 10, 0, False),
+                               "odd_panels": (1300, 90, 1.0, 9, 3, False)}[case]
+    y0, _, _ = synth_batch(N, 2, 1.0, const)
+    rng = np.random.default_rng(11)
+    tfv = tf * (1 + 0.05 * rng.random(N))
+    c = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    if case == "sequence_mass_failure":
+        c = M.SequenceController(u=0.3 * rng.standard_normal((N, 3, 9)), tf_u=1.0, tf_sim=1.0)
+        y0 = y0.copy()
+        y0[[3, 700, N - 1], 6] = 1e-4          # these satellites run out of mass: NaN trajectories, status set
+    y0d, tfd = torch.from_numpy(y0).to(dev), torch.from_numpy(tfv).to(dev)
+    n_prop = 5
+    y_a, u_a, sp_a = M.propagate_batch_device(y0d, tfd, c, const, include_drag=False, include_J2=j2, T=T, n_sub=n_prop)
+    out_a, sd_a = M.discretize_batch_device(y_a, u_a, tfd, const, include_J2=j2, n_sub=n_sub)
+    pitch = N * (T - 1) + 13
+    out_b = torch.full((105, pitch), float("nan"), dtype=torch.float64, device=dev)
+    for rep in range(2):                       # twice: the progress words must be re-armed by every call
+        _, y_b, u_b, sp_b, sd_b = M.propagate_discretize_device(y0d, tfd, c, const, T, prop_J2=j2, disc_J2=j2,
+                                                                n_sub_prop=n_prop, n_sub_disc=n_sub, out=out_b,
+                                                                out_offset=6, n_windows=nw)
+        torch.cuda.synchronize()
+        eq = lambda a, b: bool(torch.equal(a.view(torch.int64), b.view(torch.int64)))   # NaN-aware bit comparison
+        assert eq(y_a, y_b) and eq(u_a, u_b) and torch.equal(sp_a, sp_b) and torch.equal(sd_a, sd_b)
+        assert eq(out_a, out_b[:, 6:6 + N * (T - 1)])
+        assert bool(torch.isnan(out_b[:, :6]).all()) and bool(torch.isnan(out_b[:, 6 + N * (T - 1):]).all())
+        out_b[:, 6:6 + N * (T - 1)] = float("nan")
+    if case == "sequence_mass_failure":
+        assert sorted(torch.nonzero(sp_b).flatten().tolist()) == [3, 700, N - 1] and int(sd_b.max()) > 0
+    else:
+        assert int(sp_b.max()) == 0 and int(sd_b.max()) == 0
