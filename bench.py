@@ -268,7 +268,8 @@ def gpu_arm(args):
     # One linearization pass.  Default: the propagation is hidden behind the discretization (the intervals are
     # discretized window by window along k as the propagation publishes its progress, mpc_propagate_discretize);
     # --no-overlap runs the two kernels back to back (what the ncu launch list under profiles/ serialises anyway).
-    overlap = not args.no_overlap and (world == 1 or (fused is not None and args.fused_mode in ("unicast", "multicast")))
+    overlap = not args.no_overlap and (world == 1 or (fused is not None and fused.overlap_ok and
+                                                      args.fused_mode in ("unicast", "multicast")))
 
     def step():
         if overlap and world == 1:

@@ -125,6 +125,7 @@ class FusedGather:
             self.handle.barrier()
         if mode in ("push", "pushk"):
             self.peers = [ptrs[self.rank]] + [ptrs[r] for r in order[1:]]
+        self.overlap_ok = self.world <= 2      # see propagate_discretize
         self.s0, self.s1 = shard_range(n_sats_total, self.rank, self.world)
         self.status = torch.zeros(max(1, (self.s1 - self.s0) * (K - 1)), dtype=torch.int32, device=self.device)
 
@@ -151,11 +152,14 @@ class FusedGather:
                              u_out=None, status_prop=None, barrier=True, n_windows=0):
         """One SCP linearization pass of this rank's shard with the all-gather fused in AND the propagation hidden
         behind the discretization (`mpc_propagate_discretize_multi`): y0 [n_local,7], tf [n_local] CUDA float64.
-        Modes "unicast" and "multicast"; the push modes keep the two-kernel sequence.  Returns (buf, y, u, status_prop);
-        results are bit-identical to propagate_batch_device + discretize()."""
+        Modes "unicast" and "multicast" at world <= 2; the push modes and larger worlds keep the two-kernel sequence:
+        a window stores runs of ~13 columns per row and satellite, fine for HBM and for one peer, but with 7 peers the
+        step is NVLink-ingress bound and the fragmented peer stores cost more than the hidden propagation buys
+        (8 x B200: 7.77 ms back to back, 13.8 ms windowed; 2 x B200: 3.95 -> 3.70 ms; profiles/r01_n_overlap.txt).
+        Returns (buf, y, u, status_prop); results are bit-identical to propagate_batch_device + discretize()."""
         from . import batch
         assert y0.shape[0] == self.s1 - self.s0
-        if self.mode in ("push", "pushk") or y0.shape[0] == 0:
+        if self.mode in ("push", "pushk") or y0.shape[0] == 0 or not self.overlap_ok:
             y, u_out, status_prop = batch.propagate_batch_device(y0, tf, controller, const, include_drag=False,
                                                                  include_J2=include_J2, T=self.K, n_sub=n_sub_prop,
                                                                  y=y, u_out=u_out, status=status_prop)

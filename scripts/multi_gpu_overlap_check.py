@@ -49,6 +49,8 @@ for mode in os.environ.get("MODES", "unicast,multicast").split(","):
             print(f"{mode} unavailable: {exc}")
         continue
 
+    fg.overlap_ok = True          # measure the windowed pass at any world size (the library enables it for world <= 2)
+
     def b2b():
         M.propagate_batch_device(y0, tfd, ctrl, const, include_drag=False, include_J2=False, T=K, y=x, u_out=u)
         fg.discretize(x, u, tfd, const)
