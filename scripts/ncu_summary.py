@@ -37,12 +37,16 @@ with open(out, "w") as f:
             f.write(f"   {v:7.3f}  {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}\n")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     lines = src.splitlines()
-    start = next((i for i, l in enumerate(lines) if l.startswith('"Address"')), None)
-    if start is not None:
-        rd = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+    starts = [i for i, l in enumerate(lines) if l.startswith('"Address"')] + [len(lines)]
+    prev, n = None, -1
+    for a, b in zip(starts[:-1], starts[1:]):       # source tables of the captured launches (ncu may print each twice)
+        if lines[a:b] == prev:
+            continue
+        prev, n = lines[a:b], n + 1
+        rd = [r for r in csv.DictReader(io.StringIO("\n".join(lines[a:b]))) if (r.get("# Samples") or "0").isdigit()]
         tot = sum(int(r["# Samples"] or 0) for r in rd)
-        f.write(f"-- top SASS instructions by stall samples (total samples {tot})\n")
-        top = sorted(rd, key=lambda r: -int(r["# Samples"] or 0))[:25]
+        f.write(f"-- launch {n}: top SASS instructions by stall samples (total samples {tot})\n")
+        top = sorted(rd, key=lambda r: -int(r["# Samples"] or 0))[:25 if n == 0 else 8]
         for r in top:
             reasons = sorted(((int(r[k] or 0), k) for k in r if k.startswith("stall_") and "Not Issued" not in k), reverse=True)[:2]
             f.write(f"   {int(r['# Samples']):6d}  {r['Source'][:70]:70s} {reasons}\n")
@@ -54,7 +58,7 @@ with open(out, "w") as f:
                 op = r["Source"].split()[1]
             op = op.split(".")[0]
             agg[op] = agg.get(op, 0) + int(r["# Samples"] or 0)
-        f.write("-- stall samples by opcode\n")
+        f.write(f"-- launch {n}: stall samples by opcode\n")
         for op, v in sorted(agg.items(), key=lambda kv: -kv[1])[:10]:
             f.write(f"   {100.0 * v / max(tot, 1):5.1f}%  {op}\n")
 print(open(out).read())
