@@ -427,7 +427,8 @@ def gpu_arm(args):
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     fl = flops_per_interval(n_sub)
     achieved_tflops = fl * n_int / (disc_ms_avg * 1e-3) / 1e12
-    cpu = cpu_port_baseline(N, K, tf, n_sub) if not args.no_cpu_baseline else None
+    # the CPU baseline is a rank-0, N=1 measurement (under torchrun OMP_NUM_THREADS=1 would make it a one-core number)
+    cpu = cpu_port_baseline(N, K, tf, n_sub) if (world == 1 and not args.no_cpu_baseline) else None
     line = {
         "metric": "discretized intervals/sec", "value": value, "unit": "intervals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
