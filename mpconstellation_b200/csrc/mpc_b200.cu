@@ -1001,6 +1001,7 @@ int prop_disc_overlapped(mpc_ctx *ctx, const double *y0, const double *tf, const
     if ((rc = prop_device(y0, tf, p_prop, ctrl, tab_dev, et_dev, n_sats, K, n_sub_prop, x, u, status_prop, ctx->s_prop,
                           ctx->d_progress, seg)))
         return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev_ov[1], ctx->s_prop));   // propagation done: join of the caller's stream (and the gate of last resort)
     const mpc::DiscParams P = disc_params(p_disc);
     mpc::DstTab tab{};
     for (int d = 0; d < mpc::kMaxDst; ++d) tab.p[d] = (d < n_dst) ? dst[d] : nullptr;
@@ -1015,15 +1016,16 @@ int prop_disc_overlapped(mpc_ctx *ctx, const double *y0, const double *tf, const
             tab.first_wave_ctas = ctx->sm_count * 2;
             tab.stagger_cycles = (long long)n_sub_disc * 4940LL;
         }
-        const CUresult cr = stream_wait_value32()((CUstream)sw, (CUdeviceptr)(uintptr_t)(ctx->d_progress + b), n_warps,
-                                                  CU_STREAM_WAIT_VALUE_GEQ);
-        if (cr != CUDA_SUCCESS) return fail(MPC_E_CUDA, "cuStreamWaitValue32 failed (CUresult %d)", (int)cr);
+        // gate: progress[b] == number of warps.  Should the driver refuse the memory operation, the window waits for the
+        // whole propagation instead (an ordinary event): coarser, still correct, nothing is left half enqueued.
+        if (stream_wait_value32()((CUstream)sw, (CUdeviceptr)(uintptr_t)(ctx->d_progress + b), n_warps,
+                                  CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            CUDA_TRY(cudaStreamWaitEvent(sw, ctx->ev_ov[1], 0));
         rc = p_disc->include_j2
                  ? launch_window<true>(n_dst, x, u, tf, P, n_sats, K, n_sub_disc, tab, out_pitch, out_offset, status_disc, sw, k0, kc)
                  : launch_window<false>(n_dst, x, u, tf, P, n_sats, K, n_sub_disc, tab, out_pitch, out_offset, status_disc, sw, k0, kc);
         if (rc) return rc;
     }
-    CUDA_TRY(cudaEventRecord(ctx->ev_ov[1], ctx->s_prop));
     CUDA_TRY(cudaEventRecord(ctx->ev_ov[2], ctx->s_win[0]));
     CUDA_TRY(cudaEventRecord(ctx->ev_ov[3], ctx->s_win[1]));
     for (int e = 1; e < 4; ++e) CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_ov[e], 0));
