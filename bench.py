@@ -3,8 +3,10 @@
 
 Workload (BASELINE.json configs[2], the largest single-GPU configuration): 4096 satellites x K=200
 nodes (815,104 intervals), tangential thrust 0.5, tf=2.  One STEP = one SCP linearization pass over the
-batch: propagate every satellite (reference trajectory + extract_uk) then discretize every interval
+batch: propagate every satellite (reference trajectory + extract_uk) and discretize every interval
 (integrator_steps=101: 100 fixed fourth-order Runge-Kutta(-Nystrom) steps + 101-node trapezoid per interval).
+The propagation runs beside the discretization (windows of k gated on its progress, mpc_propagate_discretize;
+bit-identical to the two kernels back to back, which --no-overlap times instead).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [...]                          # the reference algorithm on the host cores
