@@ -99,6 +99,47 @@ def drag_fixtures():
     print("discretize_drag.npz", os.path.getsize(os.path.join(HERE, "discretize_drag.npz")) // 1024, "KiB")
 
 
+def bench_fixtures():
+    """tests/golden/bench_workload.npz: satellites of the BENCHMARK's own synthetic constellation (bench.make_constellation,
+    SURVEY 8d: Hubble state rotated about z by 2 pi i / N, speed scaled by 1 + 0.1 U[0,1), N = 4096) flown and
+    discretized by the unmodified reference exactly as bench.py's step does it (tangential thrust 0.5, tf = 2,
+    base_res = 100 -> K = 200, no drag / J2; use_uniform_steps=True, integrator_steps=101, and the default mode),
+    so that the numbers the benchmark produces at full size are pinned to the reference itself, not only to the oracle."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    HUBBLE = np.concatenate([R_INIT, V_INIT, [M_INIT]])
+    N, tf = 4096, 2.0
+    sat0 = R.Satellite(R_INIT, V_INIT, M_INIT)
+    scale = R.SatelliteScale(sat=sat0)                    # one scale from satellite 0 (test_simulator.py:49)
+    const = scale.get_normalized_constants()
+    # bench.make_constellation, restated with the reference's own scale object
+    y = scale.normalize_state(HUBBLE)
+    rng = np.random.default_rng(20240531)
+    ang = 2 * np.pi * np.arange(N) / N
+    ca, sa = np.cos(ang), np.sin(ang)
+    f = 1 + 0.1 * rng.random(N)
+    Y = np.tile(y, (N, 1))
+    Y[:, 0], Y[:, 1] = ca * y[0] - sa * y[1], sa * y[0] + ca * y[1]
+    Y[:, 3], Y[:, 4] = (ca * y[3] - sa * y[4]) * f, (sa * y[3] + ca * y[4]) * f
+    Y[:, 5] = y[5] * f
+    idx = np.array([0, 1365, 2730, 4095])
+    ks = np.array([0, 23, 57, 101, 150, 198])
+    g = {"const": const_vec(const), "idx": idx, "ks": ks, "y0": Y[idx], "tf": tf, "n_sats": N}
+    c = R.ConstantTangentialThrustController(tangential_thrust=0.5)
+    for j, i in enumerate(idx):
+        yd = scale.redim_state(Y[i])
+        s = R.Satellite(yd[0:3], yd[3:6], float(yd[6]))
+        sim = R.Simulator(sats=[s], controller=c, scale=scale, base_res=100, include_drag=False, include_J2=False)
+        sim.run(tf=tf)
+        x, t = sim.sim_data[s.id], sim.sim_time[s.id]
+        u = R.Discretizer.extract_uk(x, t, c)
+        g.update({f"s{j}_x": x, f"s{j}_u": u})
+        g.update(pack(f"s{j}_uni", disc(const, x, u, tf, True, ks=list(ks))))
+        g.update(pack(f"s{j}_def", disc(const, x, u, tf, False, ks=list(ks))))
+        print("satellite", i, "done")
+    np.savez(os.path.join(HERE, "bench_workload.npz"), **g)
+    print("bench_workload.npz", os.path.getsize(os.path.join(HERE, "bench_workload.npz")) // 1024, "KiB")
+
+
 def pack(prefix, out):
     names = ["A_k", "B_kp", "B_kn", "Sigma_k", "xi_k"]
     return {f"{prefix}_{n}": o for n, o in zip(names, out)}
@@ -246,5 +287,7 @@ def main():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "drag":
     drag_fixtures()
+elif __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bench":
+    bench_fixtures()
 elif __name__ == "__main__":
     main()

@@ -344,3 +344,41 @@ def test_two_node_steps_and_one_step_per_node_agree(M, const):
     assert res.status.max() == 0
     for n, o, r in zip(NAMES, res.stacked(), ref[:5]):
         assert rel_err(o, r) < TOL_ORACLE, n
+
+
+def test_bench_step_at_full_size_matches_the_unmodified_reference(M):
+    """The benchmark's own step -- 4096 satellites x K=200 through propagate_discretize_device, bench.py's arguments --
+    against the unmodified reference flown on 4 satellites of that constellation (tests/golden/bench_workload.npz,
+    made by tests/golden/make_golden.py bench): own propagation + own discretization vs the reference's RK45 propagation
+    + its uniform-node discretization, end to end."""
+    import os
+    import torch
+    import bench
+    from conftest import GOLDEN
+    gb = np.load(os.path.join(GOLDEN, "bench_workload.npz"))
+    N, K, tf = int(gb["n_sats"]), 200, float(gb["tf"])
+    Y, const_m = bench.make_constellation(N)
+    dev = torch.device("cuda:0")
+    y0, tfd = torch.from_numpy(Y).to(dev), torch.full((N,), tf, dtype=torch.float64, device=dev)
+    ctrl = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    out, x, u, sp, sd = M.propagate_discretize_device(y0, tfd, ctrl, const_m, K, n_sub_prop=M.batch.default_n_sub(K),
+                                                      n_sub_disc=100)
+    nn = torch.empty(N * (K - 1), dtype=torch.int32, device=dev)
+    out_def, sd2 = M.discretize_batch_device(x, u, tfd, const_m, adaptive=dict(rtol=1e-3, atol=1e-6, max_step=1e-2), n_nodes=nn)
+    torch.cuda.synchronize()
+    assert int(sp.max()) == 0 and int(sd.max()) == 0 and int(sd2.max()) == 0
+    ks = gb["ks"]
+    rows = {"A_k": (0, 49, (7, 7)), "B_kp": (49, 21, (7, 3)), "B_kn": (70, 21, (7, 3)), "Sigma_k": (91, 7, None), "xi_k": (98, 7, None)}
+    worst = 0.0
+    for j, s in enumerate(gb["idx"]):
+        assert rel_err(x[s].cpu().numpy(), gb[f"s{j}_x"]) < 1e-6        # north_star tolerance on propagated states
+        assert rel_err(u[s].cpu().numpy(), gb[f"s{j}_u"]) < 1e-6
+        for tag, soa in (("uni", out), ("def", out_def)):
+            blk = soa[:, s * (K - 1):(s + 1) * (K - 1)].cpu().numpy()
+            for n, (r0, nr, shp) in rows.items():
+                got = blk[r0:r0 + nr][:, ks]
+                got = got.T.reshape((len(ks),) + shp) if shp else got
+                e = rel_err(got, gb[f"s{j}_{tag}_{n}"])
+                worst = max(worst, e)
+                assert e < TOL_REF, (int(s), tag, n, e)
+    print(f"bench step vs reference: worst norm-relative error {worst:.2e}")

@@ -265,3 +265,41 @@ def test_c_oracle_integration_schemes_agree(gold_disc, const):
         assert 10.0 < e8 / e16 < 24.0
     finally:
         C.set_scheme("rkn4x2")
+
+
+# ---------------------------------------------------------------- the benchmark's own workload, through the reference
+@pytest.fixture(scope="module")
+def gold_bench():
+    import os
+    from conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "bench_workload.npz"))
+
+
+def test_bench_constellation_is_the_one_the_reference_flew(gold_bench):
+    """bench.make_constellation (product-side SatelliteScale) builds the initial states the fixture's satellites were
+    flown from by the unmodified reference (tests/golden/make_golden.py bench)"""
+    import bench
+    gb = gold_bench
+    Y, cm = bench.make_constellation(int(gb["n_sats"]))
+    assert rel_err(Y[gb["idx"]], gb["y0"]) < 1e-15
+    assert rel_err(np.array([cm.MU, cm.R_E, cm.J2, cm.G0, cm.ISP, cm.S, cm.R0, cm.RHO]), gb["const"]) < 1e-15
+
+
+def test_c_oracle_on_the_bench_workload_vs_reference(gold_bench):
+    """4 satellites of the 4096-satellite benchmark constellation: propagation (<= 1e-6, north_star), uniform-node
+    matrices (<= 1e-8) and default-mode matrices (RK45 replica, <= 1e-10) against the unmodified reference"""
+    gb = gold_bench
+    cb = O.OracleConstants(*gb["const"])
+    ks, tf = gb["ks"], float(gb["tf"])
+    y, u, st = C.propagate_batch(gb["y0"], tf, cb, C.CTRL_TANGENTIAL, (0.5, 0, 0), include_drag=False, include_J2=False,
+                                 T=200, n_sub=6)
+    assert st.max() == 0
+    for j in range(len(gb["idx"])):
+        assert rel_err(y[j], gb[f"s{j}_x"]) < 1e-6 and rel_err(u[j], gb[f"s{j}_u"]) < 1e-6
+        x_ref, u_ref = gb[f"s{j}_x"][None], gb[f"s{j}_u"][None]
+        out = C.discretize_batch(x_ref, u_ref, tf, cb)
+        for n, o in zip(NAMES, out[:5]):
+            assert rel_err(_sel(o[0], ks), gb[f"s{j}_uni_{n}"]) < TOL_UNIFORM, (j, n)
+        out = C.discretize_batch_adaptive(x_ref, u_ref, tf, cb)
+        for n, o in zip(NAMES, out[:5]):
+            assert rel_err(_sel(o[0], ks), gb[f"s{j}_def_{n}"]) < 1e-10, (j, n)
