@@ -930,13 +930,17 @@ StreamWaitValue32Fn stream_wait_value32()
 
 int ensure_overlap(mpc_ctx *ctx)
 {
-    if (ctx->s_prop) return MPC_SUCCESS;
-    int lo = 0, hi = 0;
-    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    for (cudaStream_t &w : ctx->s_win) CUDA_TRY(cudaStreamCreateWithFlags(&w, cudaStreamNonBlocking));
-    for (cudaEvent_t &e : ctx->ev_ov) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CUDA_TRY(cudaMalloc((void **)&ctx->d_progress, kMaxWindows * sizeof(unsigned int)));
-    CUDA_TRY(cudaStreamCreateWithPriority(&ctx->s_prop, cudaStreamNonBlocking, hi));
+    // every resource on its own, so that a failure half way leaves nothing to leak or to create twice
+    for (cudaStream_t &w : ctx->s_win)
+        if (!w) CUDA_TRY(cudaStreamCreateWithFlags(&w, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : ctx->ev_ov)
+        if (!e) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!ctx->d_progress) CUDA_TRY(cudaMalloc((void **)&ctx->d_progress, kMaxWindows * sizeof(unsigned int)));
+    if (!ctx->s_prop) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&ctx->s_prop, cudaStreamNonBlocking, hi));
+    }
     return MPC_SUCCESS;
 }
 
