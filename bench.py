@@ -466,9 +466,10 @@ def gpu_arm(args):
                      # -- at N > 1 -- the exchange included)
                      "in_step": {"achieved": fl * n_int / (ms_per_step * 1e-3) / 1e12,
                                  "frac": fl * n_int / (ms_per_step * 1e-3) / 1e12 / peak_tflops},
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-                     # command (profiles/r01_d_discretize_final.txt: 66.0 + 628.6 MB); algorithmic = 944 B x 815,104
-                     "traffic": 694.66e6 if (N, K, n_sub) == (4096, 200, 100) else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one full-batch launch, ncu --set full capture of
+                     # this command (profiles/r01_n_discretize_pair_windows.txt, third kernel: 65.80 + 628.39 MB);
+                     # algorithmic = 944 B x 815,104 = 769.5 MB (the 13 input doubles are shared by neighbours in L2)
+                     "traffic": 694.19e6 if (N, K, n_sub) == (4096, 200, 100) else None,
                      "peak_source": "DFMA-chain microbenchmark (mpc_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
                      "peak_nominal": FP64_NOMINAL_TFLOPS, "flop_per_interval": fl,
                      # SURVEY.md 8(d) counts the reference formulation (plain RK4 on 42+7 unknowns, dense Phi^-1
