@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE ONLY -- the CUDA kernel sources (mpconstellation_b200/csrc/*.cuh) compiled for the HOST with g++.
+
+Purpose: `pytest -m "not gpu"` runs in a container without a GPU; this lets it exercise the arithmetic, the thread ->
+(satellite, interval) indexing, the windowed launches and the status logic of the very source that nvcc compiles for
+sm_100a, against the oracles and the reference fixtures.  The sources are copied into tests/hostk/_build/ with exactly
+two lines replaced (the inline-PTX MUFU seeds of fast_rcp / fast_rsqrt -> a float-precision host seed; the Newton
+refinement that follows is the kernel's own), CUDA keywords are defined away by include/hostk_shim.h, and the threads
+of a launch run one after the other (every kernel is one independent thread per work unit).
+
+This is a checker, like oracle/: nothing in mpconstellation_b200/ may import it, it is never what is measured or
+shipped, and it says nothing about performance.
+"""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "mpconstellation_b200", "csrc")
+BUILD = os.path.join(HERE, "_build")
+SO = os.path.join(BUILD, "libmpc_hostk.so")
+SOURCES = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_pair_kernel.cuh",
+           "discretize_drag_kernel.cuh", "propagate_kernel.cuh"]
+_SEEDS = [(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rcp_seed(a);"),
+          (r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rsqrt_seed(a);")]
+
+
+def build(force=False):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "hostk_main.cpp"),
+                                                       os.path.join(HERE, "include", "hostk_shim.h"), __file__]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
+        return SO
+    os.makedirs(BUILD, exist_ok=True)
+    n_sub = 0
+    for s in SOURCES:
+        text = open(os.path.join(CSRC, s)).read()
+        for pat, rep in _SEEDS:
+            text, n = re.subn(pat, rep, text)
+            n_sub += n
+        assert "asm(" not in text, f"{s}: inline PTX the host build does not know"
+        open(os.path.join(BUILD, s), "w").write(text)
+    assert n_sub == 2, "expected exactly the two MUFU seeds to be replaced"
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-mfma", "-ffp-contract=fast", "-fno-math-errno", "-w",
+           "-I", os.path.join(HERE, "include"), "-I", BUILD, "-o", SO, os.path.join(HERE, "hostk_main.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _const8(const):
+    return np.array([const.MU, const.R_E, const.J2, const.G0, const.ISP, const.S, const.R0, const.RHO], dtype=np.float64)
+
+
+def discretize(x, u, tf, const, include_J2=False, n_sub=100, pair=True, k0=0, kc=-1, out=None, pitch=None, offset=0,
+               status=None):
+    """The fixed-step kernels (discretize_pair_kernel / discretize_kernel) on host arrays x [N,7,K], u [N,3,K] -> SoA
+    [105, pitch] + status, with the launch window (k0, kc) of the overlapped pass."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    N, _, K = x.shape
+    tfv = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    n_int = N * (K - 1)
+    pitch = n_int if pitch is None else int(pitch)
+    if out is None:
+        out = np.full((105, pitch), np.nan)
+    if status is None:
+        status = np.full(n_int, -1, dtype=np.int32)
+    c8 = _const8(const)
+    lib().hostk_discretize(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, int(n_sub), int(pair), int(k0), int(kc),
+                           _p(out), ctypes.c_longlong(pitch), ctypes.c_longlong(offset), _p(status))
+    return out, status
+
+
+def discretize_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6, max_step=1e-2):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    N, _, K = x.shape
+    tfv = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    n_int = N * (K - 1)
+    out = np.full((105, n_int), np.nan)
+    status = np.full(n_int, -1, dtype=np.int32)
+    nodes = np.zeros(n_int, dtype=np.int32)
+    c8 = _const8(const)
+    lib().hostk_discretize_adaptive(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, ctypes.c_double(rtol),
+                                    ctypes.c_double(atol), ctypes.c_double(max_step), _p(out), ctypes.c_longlong(n_int),
+                                    ctypes.c_longlong(0), _p(status), _p(nodes))
+    return out, status, nodes
+
+
+def propagate(y0, tf, const, kind=0, thrust=(0.0, 0.0, 0.0), table=None, end_tau=1.0, include_drag=False, include_J2=False,
+              T=100, n_sub=1, c_d=2.5, rho_atm=9.983e-13, seg_len=0):
+    """propagate_kernel on host arrays y0 [N,7] -> y [N,7,T], u [N,3,T], status [N], progress words (seg_len > 0)."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    N = y0.shape[0]
+    tfv = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    y = np.full((N, 7, T), np.nan)
+    uo = np.full((N, 3, T), np.nan)
+    status = np.full(N, -1, dtype=np.int32)
+    progress = np.zeros(64, dtype=np.uint32) if seg_len > 0 else None
+    th = np.ascontiguousarray(np.asarray(thrust, dtype=np.float64))
+    tab = None if table is None else np.ascontiguousarray(table, dtype=np.float64)
+    c8 = _const8(const)
+    lib().hostk_propagate(_p(y0), _p(tfv), _p(c8), int(include_J2), int(include_drag), ctypes.c_double(c_d),
+                          ctypes.c_double(rho_atm), int(kind), _p(th), _p(tab), 0 if tab is None else tab.shape[-1],
+                          ctypes.c_double(end_tau), N, int(T), int(n_sub), _p(y), _p(uo), _p(status), _p(progress),
+                          int(seg_len))
+    return y, uo, status, progress
+
+
+def stacked(soa, N, K):
+    """SoA [105, N*(K-1)] -> (A, B_kp, B_kn, Sigma, xi) in the reference's shapes with a leading satellite axis."""
+    n = K - 1
+    v = soa.reshape(105, N, n)
+    A = v[0:49].transpose(1, 2, 0).reshape(N, n, 7, 7)
+    Bp = v[49:70].transpose(1, 2, 0).reshape(N, n, 7, 3)
+    Bn = v[70:91].transpose(1, 2, 0).reshape(N, n, 7, 3)
+    return A, Bp, Bn, v[91:98].transpose(1, 0, 2), v[98:105].transpose(1, 0, 2)

@@ -1,0 +1,121 @@
+// TEST INFRASTRUCTURE ONLY -- see include/hostk_shim.h.  Wraps the host-compiled kernel sources (copied into _build/ by
+// tests/hostk/__init__.py with the two inline-PTX seeds replaced) in extern "C" entry points that run the "threads" of a
+// launch one after the other.
+#include "hostk_shim.h"
+
+#include <vector>
+
+#include "discretize_kernel.cuh"
+#include "discretize_adaptive_kernel.cuh"
+#include "discretize_pair_kernel.cuh"
+#include "propagate_kernel.cuh"
+
+namespace mpc {
+double acc_smem[256 * 64];   // the kernels' `extern __shared__ double acc_smem[]` (<= 245 slots x BLOCK 32)
+}
+
+namespace {
+constexpr int kBlock = 32;
+
+template <typename F>
+void run_grid(long long n_threads, F &&body)
+{
+    const long long grid = (n_threads + kBlock - 1) / kBlock;
+    for (long long b = 0; b < grid; ++b)
+        for (int t = 0; t < kBlock; ++t) {
+            blockIdx.x = (unsigned)b;
+            threadIdx.x = (unsigned)t;
+            body();
+        }
+}
+
+mpc::DiscParams disc_params(const double *c, int)
+{
+    mpc::DiscParams P;
+    P.mu = c[0];
+    P.kj2 = 1.5 * c[2] * c[0] * c[1] * c[1];
+    P.inv_ve = 1.0 / (c[3] * c[4]);
+    return P;
+}
+}  // namespace
+
+// const8 = [MU, R_E, J2, G0, ISP, S, R0, RHO] (the order of mpc_params / OracleConstants)
+extern "C" int hostk_discretize(const double *x, const double *u, const double *tf, const double *const8, int include_j2,
+                                int n_sats, int K, int n_sub, int pair, int k0, int kc, double *out, long long pitch,
+                                long long offset, int32_t *status)
+{
+    const mpc::DiscParams P = disc_params(const8, include_j2);
+    mpc::DstTab dst{};
+    dst.p[0] = out;
+    if (kc < 0) kc = K - 1;
+    if (pair) {
+        run_grid((long long)n_sats * kc, [&] {
+            if (include_j2) mpc::discretize_pair_kernel<true, kBlock, 255, 1>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, k0, kc);
+            else mpc::discretize_pair_kernel<false, kBlock, 255, 1>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, k0, kc);
+        });
+    } else {
+        run_grid((long long)n_sats * (K - 1), [&] {
+            if (include_j2) mpc::discretize_kernel<true, kBlock, 255, 1, false>(x, u, tf, P, n_sats, K, K, n_sub, dst, pitch, offset, status);
+            else mpc::discretize_kernel<false, kBlock, 255, 1, false>(x, u, tf, P, n_sats, K, K, n_sub, dst, pitch, offset, status);
+        });
+    }
+    return 0;
+}
+
+extern "C" int hostk_discretize_adaptive(const double *x, const double *u, const double *tf, const double *const8,
+                                         int include_j2, int n_sats, int K, double rtol, double atol, double max_step,
+                                         double *out, long long pitch, long long offset, int32_t *status, int32_t *n_nodes)
+{
+    const mpc::DiscParams P = disc_params(const8, include_j2);
+    mpc::DstTab dst{};
+    dst.p[0] = out;
+    run_grid((long long)n_sats * (K - 1), [&] {
+        if (include_j2)
+            mpc::discretize_adaptive_kernel<true, kBlock, 1, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
+        else
+            mpc::discretize_adaptive_kernel<false, kBlock, 1, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
+    });
+    return 0;
+}
+
+// controller: kind 0 zero / 1 constant (t0,t1,t2) / 2 tangential (t0) / 3 sequence table [3][table_len] (shared) with end_tau
+extern "C" int hostk_propagate(const double *y0, const double *tf, const double *const8, int include_j2, int include_drag,
+                               double c_d, double rho_atm, int kind, const double *thrust, const double *table,
+                               int table_len, double end_tau, int n_sats, int T, int n_sub, double *y, double *u_out,
+                               int32_t *status, unsigned *progress, int seg_len)
+{
+    mpc::PropParams PP;
+    PP.mu = const8[0];
+    PP.kj2 = 1.5 * const8[2] * const8[0] * const8[1] * const8[1];
+    PP.inv_ve = 1.0 / (const8[3] * const8[4]);
+    PP.drag_k = include_drag ? 0.5 * c_d * const8[5] * (rho_atm / const8[7]) : 0.0;
+    PP.include_j2 = include_j2;
+    PP.include_drag = include_drag;
+    mpc::CtrlParams C{};
+    C.kind = kind;
+    C.table_len = table_len;
+    C.t0 = thrust[0];
+    C.t1 = thrust[1];
+    C.t2 = thrust[2];
+    C.end_tau = end_tau;
+    C.table = kind == 3 ? table : nullptr;
+#define HK_PROP(KIND, DRAG, J2) \
+    run_grid(n_sats, [&] { mpc::propagate_kernel<kBlock, KIND, DRAG, J2>(y0, tf, PP, C, n_sats, T, n_sub, y, u_out, status, progress, seg_len); })
+#define HK_PROP_K(KIND)                                        \
+    do {                                                       \
+        if (include_drag) {                                    \
+            if (include_j2) HK_PROP(KIND, true, true);         \
+            else HK_PROP(KIND, true, false);                   \
+        } else {                                               \
+            if (include_j2) HK_PROP(KIND, false, true);        \
+            else HK_PROP(KIND, false, false);                  \
+        }                                                      \
+    } while (0)
+    switch (kind) {
+        case 0: HK_PROP_K(0); break;
+        case 1: HK_PROP_K(1); break;
+        case 2: HK_PROP_K(2); break;
+        default: HK_PROP_K(3); break;
+    }
+    return 0;
+}

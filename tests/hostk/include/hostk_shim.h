@@ -1,0 +1,48 @@
+// TEST INFRASTRUCTURE ONLY (tests/hostk) -- compiles the CUDA kernel sources of mpconstellation_b200/csrc for the HOST so
+// that `pytest -m "not gpu"` can check the arithmetic, the indexing and the status logic of the very code that runs on
+// the B200 against the oracles without a GPU.  Every kernel here is one independent thread per work unit with private
+// shared-memory slots ([slot][thread]), so running the threads one after the other is a faithful emulation.
+// Nothing under mpconstellation_b200/ may include, load or call this: the product has no CPU path
+// (tests/test_host_logic.py::test_product_package_never_imports_the_oracle also scans for it).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define __device__
+#define __global__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __maxnreg__(...)
+#define __shared__
+#define __constant__
+#define CUDART_INF (__builtin_inf())
+
+struct hostk_dim3 {
+    unsigned x, y, z;
+};
+static thread_local hostk_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline long long clock64() { return 0; }
+static inline void __nanosleep(unsigned) {}
+static inline void __threadfence() {}
+static inline void __syncwarp() {}
+static inline unsigned atomicAdd(unsigned *p, unsigned v)
+{
+    const unsigned o = *p;
+    *p = o + v;
+    return o;
+}
+static inline double __longlong_as_double(long long v)
+{
+    double d;
+    memcpy(&d, &v, sizeof d);
+    return d;
+}
+// Stand-ins for the MUFU seeds (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64: ~20 good bits): the exact value rounded to
+// float.  The kernels refine the seed with two Newton steps, so results agree with the device to rounding.
+static inline double hostk_rcp_seed(double a) { return (double)(float)(1.0 / a); }
+static inline double hostk_rsqrt_seed(double a) { return (double)(float)(1.0 / sqrt(a)); }

@@ -51,6 +51,7 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("mpc_oracle-free", ""), f"{f} mentions the oracle"
+                assert "hostk" not in text, f"{f} mentions the host build of the kernel sources (tests/hostk, test-only)"
 
 
 def test_scale_and_constants_mirror_reference(gold_disc):

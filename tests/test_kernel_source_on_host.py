@@ -1,0 +1,169 @@
+"""The CUDA kernel SOURCES compiled for the host (tests/hostk, test infrastructure) against the reference fixtures and
+the oracles: arithmetic, thread -> (satellite, interval) indexing, windowed launches, status words and progress words of
+the code nvcc compiles for sm_100a, checked in the GPU-less container.  The GPU parity tests proper are tests/test_gpu_*.py;
+this file makes sure a kernel edit cannot silently change the mathematics between two GPU runs."""
+import os
+
+import numpy as np
+import pytest
+
+import hostk
+from conftest import GOLDEN, NAMES, rel_err, synth_batch
+from oracle import c_oracle as C
+from oracle import mpc_oracle as O
+
+TOL_REF = 1e-8        # vs the unmodified reference (same tolerance as the GPU tests)
+TOL_ORACLE = 1e-10    # vs the plain-C oracle on the same inputs
+
+
+def _sel(o, ks):
+    return o[ks] if o.ndim == 3 else o[:, ks]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    hostk.build()
+
+
+@pytest.mark.parametrize("pair", [True, False])
+@pytest.mark.parametrize("sc", ["d0", "d1", "d2", "d3", "d4"])
+def test_fixed_step_kernels_match_reference_fixtures(gold_disc, const, sc, pair):
+    """discretize_pair_kernel (two-node steps) and discretize_kernel (one step per node), test_discretizer.py:30-150"""
+    g = gold_disc
+    x, u, tf = g[sc + "_x"][None], g[sc + "_u"][None], float(g[sc + "_tf"])
+    soa, st = hostk.discretize(x, u, tf, const, pair=pair)
+    assert st.max() == 0 and st.min() == 0 and np.all(np.isfinite(soa))
+    for n, o in zip(NAMES, hostk.stacked(soa, 1, x.shape[2])):
+        assert rel_err(o[0], g[f"{sc}_uni_{n}"]) < TOL_REF, (sc, n)
+
+
+def test_j2_and_node_count_match_reference_fixtures(gold_disc, const):
+    g = gold_disc
+    ks = g["d3_j2_ks"]
+    soa, st = hostk.discretize(g["d3_x"][None], g["d3_u"][None], 2.0, const, include_J2=True)
+    for n, o in zip(NAMES, hostk.stacked(soa, 1, 200)):
+        assert rel_err(_sel(o[0], ks), g[f"d3_j2_uni_{n}"]) < TOL_REF, n
+    soa, st = hostk.discretize(g["d3_x"][None], g["d3_u"][None], 2.0, const, n_sub=20)
+    for n, o in zip(NAMES, hostk.stacked(soa, 1, 200)):
+        assert rel_err(_sel(o[0], ks), g[f"d3_n21_uni_{n}"]) < TOL_REF, n
+
+
+@pytest.mark.parametrize("sc", ["d0", "d1", "d3", "d4"])
+def test_adaptive_kernel_matches_reference_default_mode(gold_disc, const, sc):
+    """discretize_adaptive_kernel replays scipy's RK45 controller: the reference's DEFAULT mode, same node counts"""
+    g = gold_disc
+    x, u, tf = g[sc + "_x"][None], g[sc + "_u"][None], float(g[sc + "_tf"])
+    soa, st, nodes = hostk.discretize_adaptive(x, u, tf, const)
+    assert st.max() == 0
+    for n, o in zip(NAMES, hostk.stacked(soa, 1, x.shape[2])):
+        assert rel_err(o[0], g[f"{sc}_def_{n}"]) < TOL_ORACLE, (sc, n)
+    ref = C.discretize_batch_adaptive(x, u, tf, const)
+    assert np.array_equal(nodes, ref[6].reshape(-1))
+    if sc == "d3":
+        ks = g["d3_j2_ks"]
+        soa, st, _ = hostk.discretize_adaptive(x, u, tf, const, include_J2=True)
+        for n, o in zip(NAMES, hostk.stacked(soa, 1, 200)):
+            assert rel_err(_sel(o[0], ks), g[f"d3_j2_def_{n}"]) < TOL_ORACLE, n
+
+
+@pytest.mark.parametrize("n_sats,K,tf,j2,n_sub", [(16, 60, 1.0, False, 100), (7, 33, 0.7, True, 100), (3, 50, 2.0, True, 16),
+                                                  (40, 3, 0.02, False, 7), (3, 2, 0.05, True, 100)])
+def test_batch_matches_c_oracle(const, n_sats, K, tf, j2, n_sub):
+    """ragged shapes, J2, per-satellite tf, odd panel counts (per-thread fall back to one step per node)"""
+    _, x, u = synth_batch(n_sats, K, tf, const)
+    tfv = tf * (1 + 0.01 * np.arange(n_sats))
+    soa, st = hostk.discretize(x, u, tfv, const, include_J2=j2, n_sub=n_sub)
+    ref = C.discretize_batch(x, u, tfv, const, include_J2=j2, n_sub=n_sub)
+    assert st.max() == 0 and ref[5].max() == 0
+    for n, o, r in zip(NAMES, hostk.stacked(soa, n_sats, K), ref[:5]):
+        assert rel_err(o, r) < TOL_ORACLE, n
+    A = hostk.stacked(soa, n_sats, K)[0]
+    assert np.all(A[..., 6, 6] == 1.0) and not np.any(A[..., 6, :6])          # structural constants of Phi's last row
+
+
+def test_windowed_launches_assemble_the_full_launch_bit_for_bit(const):
+    """the (k0, kc) launch window of the overlapped pass (mpc_propagate_discretize): ragged windows, pitch / offset, and
+    nothing written outside the batch"""
+    N, K = 9, 41
+    _, x, u = synth_batch(N, K, 0.8, const)
+    full, st_full = hostk.discretize(x, u, 0.8, const)
+    n_int = N * (K - 1)
+    out = np.full((105, n_int + 11), np.nan)
+    st = np.full(n_int, -1, dtype=np.int32)
+    for k0, kc in ((0, 7), (7, 13), (20, 1), (21, 19)):
+        hostk.discretize(x, u, 0.8, const, k0=k0, kc=kc, out=out, pitch=n_int + 11, offset=4, status=st)
+    assert np.array_equal(out[:, 4:4 + n_int], full) and np.array_equal(st, st_full)
+    assert np.isnan(out[:, :4]).all() and np.isnan(out[:, 4 + n_int:]).all()
+
+
+@pytest.mark.parametrize("case", ["p0", "p1", "p2", "p4"])
+def test_propagate_kernel_vs_reference_and_c_oracle(gold_prop, const, case):
+    gp = gold_prop
+    y0 = O.normalize_state(gp["x0_dim"], O.scale_factors(gp["x0_dim"]))
+    kw = {"p0": dict(kind=0, T=500, include_drag=True, include_J2=True),
+          "p1": dict(kind=2, thrust=(0.5, 0, 0), T=200),
+          "p2": dict(kind=1, thrust=tuple(gp["p2_thrust"]), T=300, include_drag=True, include_J2=True),
+          "p4": dict(kind=2, thrust=(0.1, 0, 0), T=200, include_drag=True, include_J2=True)}[case]
+    T, tf = kw["T"], float(gp[case + "_tf"])
+    n_sub = int(np.ceil(1000 / (T - 1)))
+    y, u, st, _ = hostk.propagate(y0[None], tf, const, n_sub=n_sub, **kw)
+    assert st[0] == 0
+    assert rel_err(y[0], gp[case + "_y"]) < 1e-6          # north_star tolerance on propagated states
+    ckind = {0: C.CTRL_ZERO, 1: C.CTRL_CONSTANT, 2: C.CTRL_TANGENTIAL}[kw["kind"]]
+    yr, ur, sr = C.propagate_batch(y0[None], tf, const, ckind, kw.get("thrust", (0, 0, 0)), T=T, n_sub=n_sub,
+                                   include_drag=kw.get("include_drag", False), include_J2=kw.get("include_J2", False))
+    assert rel_err(y, yr) < 1e-11 and (kw["kind"] == 0 or rel_err(u, ur) < 1e-10)
+
+
+def test_propagate_progress_words_sequence_controller_and_mass_failure(const):
+    """what the overlapped pass relies on: every warp adds 1 to every window's word, also when some of its satellites
+    have run out of mass (NaN-filled trajectories, status 1) and when the batch does not fill its last warp"""
+    N, T, seg = 70, 50, 6
+    y0, _, _ = synth_batch(N, 2, 1.0, const)
+    y0 = y0.copy()
+    y0[[2, 40], 6] = 1e-4
+    rng = np.random.default_rng(5)
+    tab = 0.3 * rng.standard_normal((3, 9))
+    y, u, st, prog = hostk.propagate(y0, 1.0, const, kind=3, table=tab, end_tau=1.0, T=T, n_sub=4, seg_len=seg)
+    n_win = (T - 1 + seg - 1) // seg
+    assert list(prog[:n_win]) == [3] * n_win and not prog[n_win:].any()          # ceil(70 / 32) warps
+    assert sorted(np.nonzero(st)[0]) == [2, 40] and np.isnan(y[2]).any() and np.isfinite(np.delete(y, [2, 40], 0)).all()
+    yr, ur, sr = C.propagate_batch(y0, 1.0, const, C.CTRL_SEQUENCE, table=tab, end_tau=1.0, include_drag=False,
+                                   include_J2=False, T=T, n_sub=4)
+    ok = np.delete(np.arange(N), [2, 40])
+    assert np.array_equal(sr, st) and rel_err(y[ok], yr[ok]) < 1e-11 and rel_err(u[ok], ur[ok]) < 1e-10
+
+
+def test_bench_workload_chain_vs_reference():
+    """propagate_kernel -> discretize_pair_kernel / discretize_adaptive_kernel on 4 satellites of the benchmark's
+    constellation against the unmodified reference's own propagation + discretization (bench_workload.npz)"""
+    gb = np.load(os.path.join(GOLDEN, "bench_workload.npz"))
+    cb = O.OracleConstants(*gb["const"])
+    ks, tf = gb["ks"], float(gb["tf"])
+    y, u, st, _ = hostk.propagate(gb["y0"], tf, cb, kind=2, thrust=(0.5, 0, 0), T=200, n_sub=6)
+    assert st.max() == 0
+    soa, sd = hostk.discretize(y, u, tf, cb)
+    soa_d, sd2, _ = hostk.discretize_adaptive(y, u, tf, cb)
+    assert sd.max() == 0 and sd2.max() == 0
+    for j in range(len(gb["idx"])):
+        assert rel_err(y[j], gb[f"s{j}_x"]) < 1e-6 and rel_err(u[j], gb[f"s{j}_u"]) < 1e-6
+        for tag, s in (("uni", soa), ("def", soa_d)):
+            for n, o in zip(NAMES, hostk.stacked(s, 4, 200)):
+                assert rel_err(_sel(o[j], ks), gb[f"s{j}_{tag}_{n}"]) < TOL_REF, (j, tag, n)
+
+
+def test_zero_thrust_and_mass_failure_status(const):
+    """coasting intervals (the |u| <= eps guard, linearize_discretize.py:208) and a non-positive mass"""
+    N, K = 4, 9
+    _, x, u = synth_batch(N, K, 0.4, const)
+    u = u.copy()
+    u[1] = 0.0
+    u[2, :, 4:] = 0.0
+    x = x.copy()
+    x[3, 6, 5] = -1.0
+    soa, st = hostk.discretize(x, u, 0.4, const)
+    ref = C.discretize_batch(x, u, 0.4, const)
+    st2 = st.reshape(N, K - 1)
+    assert st2[:3].max() == 0 and st2[3, 5] == 1 and np.array_equal(st2 != 0, ref[5] != 0)
+    for n, o, r in zip(NAMES, hostk.stacked(soa, N, K), ref[:5]):
+        assert rel_err(o[:3], r[:3]) < TOL_ORACLE, n
