@@ -22,7 +22,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "mpconstellation_b20
 BUILD = os.path.join(HERE, "_build")
 SO = os.path.join(BUILD, "libmpc_hostk.so")
 SOURCES = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_pair_kernel.cuh",
-           "discretize_drag_kernel.cuh", "propagate_kernel.cuh"]
+           "discretize_drag_kernel.cuh", "propagate_kernel.cuh", "constraint_terms_kernel.cuh"]
 _SEEDS = [(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rcp_seed(a);"),
           (r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rsqrt_seed(a);")]
 
@@ -122,6 +122,51 @@ def propagate(y0, tf, const, kind=0, thrust=(0.0, 0.0, 0.0), table=None, end_tau
                           ctypes.c_double(end_tau), N, int(T), int(n_sub), _p(y), _p(uo), _p(status), _p(progress),
                           int(seg_len))
     return y, uo, status, progress
+
+
+def discretize_drag(x, u, tf, const, drag, include_J2=False, n_sub=100, adaptive=None, c_d=2.5, rho_atm=9.983e-13):
+    """The drag kernels (discretize_drag_kernel / the DRAG variant of the adaptive kernel); drag = (const.CD, rho_func
+    value), as mpconstellation_b200.discretize_batch(disc_drag=...)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    N, _, K = x.shape
+    tfv = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    n_int = N * (K - 1)
+    out = np.full((105, n_int), np.nan)
+    status = np.full(n_int, -1, dtype=np.int32)
+    nodes = np.zeros(n_int, dtype=np.int32)
+    c8 = _const8(const)
+    kf = 0.5 * c_d * const.S * (rho_atm / const.RHO)
+    ka = 0.5 * drag[0] * const.S * drag[1]
+    ad = adaptive if adaptive is not None else {}
+    D = ctypes.c_double
+    lib().hostk_discretize_drag(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), D(kf), D(ka), N, K, int(n_sub),
+                                int(adaptive is not None), D(ad.get("rtol", 1e-3)), D(ad.get("atol", 1e-6)),
+                                D(ad.get("max_step", 1e-2)), _p(out), ctypes.c_longlong(n_int), _p(status), _p(nodes))
+    return out, status, nodes
+
+
+def constraint_terms(x, u, mu):
+    """constraint_terms_kernel on host arrays x [N,7,K], u [N,3,Ku] -> rbar_hat [N,3,K-1], ubar_hat [N,3,Ku], fin [N,32]"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    N, _, K = x.shape
+    Ku = u.shape[2]
+    rbar, ubar, fin = np.full((N, 3, K - 1), np.nan), np.full((N, 3, Ku), np.nan), np.full((N, 32), np.nan)
+    lib().hostk_constraint_terms(_p(x), _p(u), N, K, Ku, ctypes.c_double(mu), _p(rbar), _p(ubar), _p(fin))
+    return rbar, ubar, fin
+
+
+def dynamics_jacobian(soa, n_sats, K):
+    """dynamics_jacobian_kernel: CSR values [rows,16], indices [rows,16], rhs [rows] of the dynamics constraint"""
+    soa = np.ascontiguousarray(soa, dtype=np.float64)
+    rows = n_sats * 7 * (K - 1)
+    values = np.full((rows, 16), np.nan)
+    indices = np.full((rows, 16), -1, dtype=np.int64)
+    rhs = np.full(rows, np.nan)
+    lib().hostk_dynamics_jacobian(_p(soa), ctypes.c_longlong(soa.shape[1]), ctypes.c_longlong(0), n_sats, K, _p(values),
+                                  _p(indices), _p(rhs))
+    return values, indices, rhs
 
 
 def stacked(soa, N, K):

@@ -9,6 +9,8 @@
 #include "discretize_adaptive_kernel.cuh"
 #include "discretize_pair_kernel.cuh"
 #include "propagate_kernel.cuh"
+#include "discretize_drag_kernel.cuh"
+#include "constraint_terms_kernel.cuh"
 
 namespace mpc {
 double acc_smem[256 * 64];   // the kernels' `extern __shared__ double acc_smem[]` (<= 245 slots x BLOCK 32)
@@ -24,6 +26,7 @@ void run_grid(long long n_threads, F &&body)
     for (long long b = 0; b < grid; ++b)
         for (int t = 0; t < kBlock; ++t) {
             blockIdx.x = (unsigned)b;
+            blockDim.x = kBlock;
             threadIdx.x = (unsigned)t;
             body();
         }
@@ -117,5 +120,44 @@ extern "C" int hostk_propagate(const double *y0, const double *tf, const double 
         case 2: HK_PROP_K(2); break;
         default: HK_PROP_K(3); break;
     }
+    return 0;
+}
+
+// drag branch of the linearisation: kf = 0.5 C_D S (rho_atm / RHO) (dynamics), ka = 0.5 const.CD S rho_func (Jacobian)
+extern "C" int hostk_discretize_drag(const double *x, const double *u, const double *tf, const double *const8,
+                                     int include_j2, double kf, double ka, int n_sats, int K, int n_sub, int adaptive,
+                                     double rtol, double atol, double max_step, double *out, long long pitch,
+                                     int32_t *status, int32_t *n_nodes)
+{
+    const mpc::DiscParams P = disc_params(const8, include_j2);
+    mpc::DstTab dst{};
+    dst.p[0] = out;
+    run_grid((long long)n_sats * (K - 1), [&] {
+        if (adaptive) {
+            if (include_j2)
+                mpc::discretize_adaptive_kernel<true, kBlock, 1, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, ka);
+            else
+                mpc::discretize_adaptive_kernel<false, kBlock, 1, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, ka);
+        } else {
+            if (include_j2) mpc::discretize_drag_kernel<true, kBlock>(x, u, tf, P, kf, ka, n_sats, K, n_sub, dst, pitch, 0, status);
+            else mpc::discretize_drag_kernel<false, kBlock>(x, u, tf, P, kf, ka, n_sats, K, n_sub, dst, pitch, 0, status);
+        }
+    });
+    return 0;
+}
+
+extern "C" int hostk_constraint_terms(const double *x, const double *u, int n_sats, int K, int Ku, double mu,
+                                      double *rbar_hat, double *ubar_hat, double *fin)
+{
+    run_grid((long long)n_sats * (K > Ku ? K : Ku),
+             [&] { mpc::constraint_terms_kernel(x, u, n_sats, K, Ku, mu, 2.220446049250313e-16, rbar_hat, ubar_hat, fin); });
+    return 0;
+}
+
+extern "C" int hostk_dynamics_jacobian(const double *soa, long long pitch, long long offset, int n_sats, int K,
+                                       double *values, int64_t *indices, double *rhs)
+{
+    run_grid((long long)n_sats * 7 * (K - 1),
+             [&] { mpc::dynamics_jacobian_kernel(soa, pitch, offset, n_sats, K, values, indices, rhs); });
     return 0;
 }

@@ -167,3 +167,86 @@ def test_zero_thrust_and_mass_failure_status(const):
     assert st2[:3].max() == 0 and st2[3, 5] == 1 and np.array_equal(st2 != 0, ref[5] != 0)
     for n, o, r in zip(NAMES, hostk.stacked(soa, N, K), ref[:5]):
         assert rel_err(o[:3], r[:3]) < TOL_ORACLE, n
+
+
+# ------------------------------------------------------------------------------------------- drag branch (K1c)
+def _oracle_const(vec):
+    return O.OracleConstants(*vec)
+
+
+@pytest.mark.parametrize("tag", ["g0", "g1"])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_drag_kernels_match_reference_fixtures(tag, uniform):
+    """discretize_drag_kernel / the DRAG variant of the adaptive kernel vs the reference's drag branch
+    (linearize_discretize.py:160-169) run with const.CD, rho_func, drho_func supplied (tests/golden/make_golden.py drag)"""
+    g = np.load(os.path.join(GOLDEN, "discretize_drag.npz"))
+    cst = _oracle_const(g[tag + "_const"])
+    drag = (float(g[tag + "_cd"]), float(g[tag + "_rho_n"]))
+    x, u, tf, ks = g[tag + "_x"][None], g[tag + "_u"][None], float(g[tag + "_tf"]), g[tag + "_ks"]
+    soa, st, _ = hostk.discretize_drag(x, u, tf, cst, drag, include_J2=bool(g[tag + "_j2"]),
+                                       adaptive=None if uniform else {})
+    assert st.max() == 0
+    mode = "uni" if uniform else "def"
+    for n, o in zip(NAMES, hostk.stacked(soa, 1, x.shape[2])):
+        assert rel_err(_sel(o[0], ks), g[f"{tag}_{mode}_{n}"]) < TOL_REF, (tag, mode, n)
+
+
+@pytest.mark.parametrize("j2", [False, True])
+def test_drag_batch_matches_c_oracle(const, j2):
+    import copy
+    cst = copy.copy(const)
+    cst.S = const.S * 3e3
+    _, x, u = synth_batch(11, 13, 0.4, cst)
+    tf = np.linspace(0.3, 0.5, 11)
+    drag = (2.2, 4.0e4)
+    ref = C.discretize_batch(x, u, tf, cst, include_J2=j2, n_sub=40, drag=drag)
+    soa, st, _ = hostk.discretize_drag(x, u, tf, cst, drag, include_J2=j2, n_sub=40)
+    assert st.max() == 0 and ref[5].max() == 0
+    for n, o, r in zip(NAMES, hostk.stacked(soa, 11, 13), ref[:5]):
+        assert rel_err(o, r) < TOL_ORACLE, n
+    ref = C.discretize_batch_adaptive(x, u, tf, cst, include_J2=j2, drag=drag)
+    soa, st, nodes = hostk.discretize_drag(x, u, tf, cst, drag, include_J2=j2, adaptive={})
+    assert st.max() == 0 and np.array_equal(nodes, ref[6].reshape(-1))
+    for n, o, r in zip(NAMES, hostk.stacked(soa, 11, 13), ref[:5]):
+        assert rel_err(o, r) < TOL_ORACLE, n
+
+
+# ------------------------------------------------------------------- constraint terms and the sparse dynamics Jacobian
+CT_KEYS = {"rf_hat": (0, 3), "Vc": (3, 0), "DrVc": (4, 3), "DrVc_rbar": (7, 0), "Vt": (8, 0), "DrVt_DvVt": (9, 6),
+           "DrVt_DvVt_bar": (15, 0), "Vr": (16, 0), "DrVr_DvVr": (17, 6), "DrVr_DvVr_bar": (23, 0), "Vn": (24, 0),
+           "DrVn_DvVn": (25, 6), "DrVn_DvVn_bar": (31, 0)}
+
+
+@pytest.mark.parametrize("tag", ["c0", "c1", "c2"])
+def test_constraint_terms_kernel_vs_reference_fixtures(tag):
+    """constraint_terms_kernel vs Optimizer.get_constraint_terms of the unmodified reference (optimizer.py:80-170):
+    unit vectors bit for bit (NaN positions of the inverted ubar_hat mask included), terminal terms to 5e-13"""
+    g = np.load(os.path.join(GOLDEN, "constraint_terms.npz"))
+    rbar, ubar, fin = hostk.constraint_terms(g[tag + "_x"][None], g[tag + "_u"][None], float(g["MU"]))
+    np.testing.assert_array_equal(rbar[0], g[f"{tag}_rbar_hat"])
+    np.testing.assert_array_equal(ubar[0], g[f"{tag}_ubar_hat"])
+    for key, (off, ln) in CT_KEYS.items():
+        got = fin[0, off:off + ln] if ln else fin[0, off]
+        ref = np.asarray(g[f"{tag}_{key}"])
+        assert np.max(np.abs(got - ref)) <= 5e-13 * max(np.max(np.abs(ref)), 1.0), key
+
+
+def test_dynamics_jacobian_kernel_reproduces_the_pyomo_rule(const):
+    """dynamics_jacobian_kernel: J z - rhs equals the residual of dynamics_const_rule (optimizer.py:327-339) written
+    out with the rule's own indexing on the matrices the discretization kernel produced"""
+    N, K = 3, 7
+    _, x, u = synth_batch(N, K, 0.7, const)
+    soa, st = hostk.discretize(x, u, 0.7, const, n_sub=10)
+    A, Bp, Bn, S, X = hostk.stacked(soa, N, K)
+    values, indices, rhs = hostk.dynamics_jacobian(soa, N, K)
+    assert np.all(np.diff(indices, axis=1) > 0) and indices.min() >= 0 and indices.max() == 17 * N * K
+    rng = np.random.default_rng(3)
+    xz, uz, nuz, tfz = rng.standard_normal((N, 7, K)), rng.standard_normal((N, 3, K)), rng.standard_normal((N, 7, K)), 0.9
+    z = np.concatenate([xz.ravel(), uz.ravel(), nuz.ravel(), [tfz]])
+    res = ((values * z[indices]).sum(axis=1) - rhs).reshape(N, 7, K - 1)
+    for s in range(N):
+        for k in range(K - 1):
+            for i in range(7):
+                want = xz[s, i, k + 1] - (A[s, k, i] @ xz[s, :, k] + Bn[s, k, i] @ uz[s, :, k] + Bp[s, k, i] @ uz[s, :, k + 1]
+                                          + S[s, i, k] * tfz + X[s, i, k] + nuz[s, i, k])
+                assert abs(res[s, i, k] - want) < 1e-12 * max(1.0, abs(want)), (s, i, k)
