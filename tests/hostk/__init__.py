@@ -27,7 +27,16 @@ _SEEDS = [(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y
           (r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rsqrt_seed(a);")]
 
 
-def build(force=False):
+def build(force=False, sanitize=False):
+    """g++ build of the kernel sources.  sanitize=True: a second library with AddressSanitizer + UBSan instrumentation
+    (tests/hostk/sanitize_driver.py runs it in a subprocess with the ASan runtime preloaded)."""
+    if sanitize:
+        return _build(os.path.join(BUILD, "libmpc_hostk_asan.so"), force,
+                      ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"])
+    return _build(SO, force, ["-O2"])
+
+
+def _build(SO, force, opt):
     srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "hostk_main.cpp"),
                                                        os.path.join(HERE, "include", "hostk_shim.h"), __file__]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
@@ -42,7 +51,7 @@ def build(force=False):
         assert "asm(" not in text, f"{s}: inline PTX the host build does not know"
         open(os.path.join(BUILD, s), "w").write(text)
     assert n_sub == 2, "expected exactly the two MUFU seeds to be replaced"
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-mfma", "-ffp-contract=fast", "-fno-math-errno", "-w",
+    cmd = ["g++"] + opt + ["-std=c++17", "-shared", "-fPIC", "-mfma", "-ffp-contract=fast", "-fno-math-errno", "-w",
            "-I", os.path.join(HERE, "include"), "-I", BUILD, "-o", SO, os.path.join(HERE, "hostk_main.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -56,7 +65,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        _lib = ctypes.CDLL(build())
+        _lib = ctypes.CDLL(build(sanitize=bool(os.environ.get("HOSTK_SANITIZE"))))
     return _lib
 
 

@@ -250,3 +250,36 @@ def test_dynamics_jacobian_kernel_reproduces_the_pyomo_rule(const):
                 want = xz[s, i, k + 1] - (A[s, k, i] @ xz[s, :, k] + Bn[s, k, i] @ uz[s, :, k] + Bp[s, k, i] @ uz[s, :, k + 1]
                                           + S[s, i, k] * tfz + X[s, i, k] + nuz[s, i, k])
                 assert abs(res[s, i, k] - want) < 1e-12 * max(1.0, abs(want)), (s, i, k)
+
+
+# ----------------------------------------------------------------------------- memory safety of the kernels' indexing
+def _run_sanitized(code_or_path, is_path):
+    import subprocess
+    import sys
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("no AddressSanitizer runtime next to this gcc")
+    hostk.build(sanitize=True)
+    env = dict(os.environ, HOSTK_SANITIZE="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1",
+               PYTHONPATH=os.pathsep.join([os.path.dirname(os.path.abspath(__file__)), os.path.dirname(GOLDEN.rstrip("/")) + "/.."]))
+    cmd = [sys.executable, code_or_path] if is_path else [sys.executable, "-c", code_or_path]
+    return subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+
+
+def test_kernel_sources_under_address_sanitizer():
+    """compute-sanitizer is closed on the GPU pool; the kernels' indexing is memchecked here instead: every kernel source
+    on ragged shapes, launch windows, progress words, exactly sized heap buffers, under ASan + UBSan
+    (tests/hostk/sanitize_driver.py).  A positive control makes sure the detector is live."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = _run_sanitized(os.path.join(root, "tests", "hostk", "sanitize_driver.py"), True)
+    assert res.returncode == 0 and "launches clean" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "AddressSanitizer" not in res.stderr and "runtime error" not in res.stderr
+    control = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.join(root, 'tests')!r}); sys.path.insert(0, {root!r})\n"
+        "import hostk\nfrom conftest import synth_batch\nfrom oracle.mpc_oracle import OracleConstants\n"
+        f"const = OracleConstants(*np.load({os.path.join(GOLDEN, 'discretize.npz')!r})['const'])\n"
+        "y0, x, u = synth_batch(3, 5, 0.3, const)\n"
+        "hostk.discretize(x, u, 0.3, const, out=np.full((105, 11), np.nan), pitch=12)   # one column short\n")
+    res = _run_sanitized(control, False)
+    assert res.returncode != 0 and "heap-buffer-overflow" in res.stderr
