@@ -313,7 +313,10 @@ int64_t mpc_launch_count(void);
 
 /* Experiment knob: 1..6 select an alternative block-size / register-cap build of the one-step-per-node discretization
  * kernel (0 = production; results identical, only occupancy differs; DESIGN.md, tuning table).  7 / 8 switch the
- * two-node integrator steps of the production kernel off / on (results differ by ~1e-12). */
+ * two-node integrator steps of the production kernel off / on (results differ by ~1e-12).  9 / 10 switch the COMPACT
+ * build of the adaptive (default-mode) kernel on / off: dynamics evaluation and node term as real calls instead of
+ * inlined copies (same arithmetic, checked on the host build of the sources; an instruction-fetch experiment that has
+ * not been timed on a GPU yet -- off by default). */
 int mpc_set_tuning(int variant);
 
 /* Options of the fused (in-kernel store) all-gather, applied by mpc_discretize_batch / _multi:

@@ -190,13 +190,15 @@ int launch_adaptive(const double *x, const double *u, const double *tf, const mp
                        : launch_adaptive_g<J2, false>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
 }
 
-template <bool J2, bool GENU, bool DRAG>
+std::atomic<int> g_compact{0};   // mpc_set_tuning(9): COMPACT build of the adaptive kernel (experimental, see the kernel)
+
+template <bool J2, bool GENU, bool DRAG, bool COMPACT = false>
 int launch_adaptive_k(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                       const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
                       cudaStream_t st)
 {
     constexpr int BLOCK = 32;
-    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1, GENU, DRAG>;
+    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1, GENU, DRAG, COMPACT>;
     const size_t smem = (size_t)(DRAG ? mpc::kAdSlotsDrag : mpc::kAdSlots) * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -224,6 +226,8 @@ int launch_adaptive_g(const double *x, const double *u, const double *tf, const 
         if (GENU) return fail(MPC_E_UNSUPPORTED, "include_drag with u on its own grid is not supported");
         return launch_adaptive_k<J2, false, true>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
     }
+    if (!GENU && g_compact.load(std::memory_order_relaxed))
+        return launch_adaptive_k<J2, false, false, true>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
     return launch_adaptive_k<J2, GENU, false>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
 }
 
@@ -554,6 +558,10 @@ int mpc_set_tuning(int variant)
 {
     if (variant == 7 || variant == 8) {   // 7: one integrator step per node everywhere; 8: two-node steps back on
         g_pair.store(variant == 8);
+        return MPC_SUCCESS;
+    }
+    if (variant == 9 || variant == 10) {  // 9: COMPACT build of the adaptive (default-mode) kernel; 10: back to the inlined build
+        g_compact.store(variant == 9);
         return MPC_SUCCESS;
     }
     if (variant < 0 || variant > 6) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);

@@ -97,7 +97,7 @@ def discretize(x, u, tf, const, include_J2=False, n_sub=100, pair=True, k0=0, kc
     return out, status
 
 
-def discretize_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6, max_step=1e-2):
+def discretize_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6, max_step=1e-2, compact=False):
     x = np.ascontiguousarray(x, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
     N, _, K = x.shape
@@ -109,7 +109,7 @@ def discretize_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6,
     c8 = _const8(const)
     lib().hostk_discretize_adaptive(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, ctypes.c_double(rtol),
                                     ctypes.c_double(atol), ctypes.c_double(max_step), _p(out), ctypes.c_longlong(n_int),
-                                    ctypes.c_longlong(0), _p(status), _p(nodes))
+                                    ctypes.c_longlong(0), _p(status), _p(nodes), int(compact))
     return out, status, nodes
 
 

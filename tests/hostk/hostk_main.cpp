@@ -67,11 +67,21 @@ extern "C" int hostk_discretize(const double *x, const double *u, const double *
 
 extern "C" int hostk_discretize_adaptive(const double *x, const double *u, const double *tf, const double *const8,
                                          int include_j2, int n_sats, int K, double rtol, double atol, double max_step,
-                                         double *out, long long pitch, long long offset, int32_t *status, int32_t *n_nodes)
+                                         double *out, long long pitch, long long offset, int32_t *status, int32_t *n_nodes,
+                                         int compact)
 {
     const mpc::DiscParams P = disc_params(const8, include_j2);
     mpc::DstTab dst{};
     dst.p[0] = out;
+    if (compact) {   // the COMPACT build (dynamics evaluation and node term as real calls)
+        run_grid((long long)n_sats * (K - 1), [&] {
+            if (include_j2)
+                mpc::discretize_adaptive_kernel<true, kBlock, 1, false, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
+            else
+                mpc::discretize_adaptive_kernel<false, kBlock, 1, false, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
+        });
+        return 0;
+    }
     run_grid((long long)n_sats * (K - 1), [&] {
         if (include_j2)
             mpc::discretize_adaptive_kernel<true, kBlock, 1, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);

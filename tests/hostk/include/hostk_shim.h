@@ -13,6 +13,7 @@
 #define __global__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __maxnreg__(...)
 #define __shared__

@@ -66,6 +66,17 @@ def test_adaptive_kernel_matches_reference_default_mode(gold_disc, const, sc):
             assert rel_err(_sel(o[0], ks), g[f"d3_j2_def_{n}"]) < TOL_ORACLE, n
 
 
+@pytest.mark.parametrize("j2", [False, True])
+def test_compact_build_of_the_adaptive_kernel_is_the_same_arithmetic(const, j2):
+    """discretize_adaptive_kernel<..., COMPACT = true> (mpc_set_tuning(9): dynamics evaluation and node term as real
+    calls instead of inlined copies, an experiment on instruction fetch) must produce what the inlined build produces"""
+    _, x, u = synth_batch(6, 25, 1.1, const)
+    a = hostk.discretize_adaptive(x, u, 1.1, const, include_J2=j2)
+    b = hostk.discretize_adaptive(x, u, 1.1, const, include_J2=j2, compact=True)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[1].max() == 0
+    assert rel_err(b[0], a[0]) < 1e-14
+
+
 @pytest.mark.parametrize("n_sats,K,tf,j2,n_sub", [(16, 60, 1.0, False, 100), (7, 33, 0.7, True, 100), (3, 50, 2.0, True, 16),
                                                   (40, 3, 0.02, False, 7), (3, 2, 0.05, True, 100)])
 def test_batch_matches_c_oracle(const, n_sats, K, tf, j2, n_sub):
