@@ -294,3 +294,47 @@ def test_kernel_sources_under_address_sanitizer():
         "hostk.discretize(x, u, 0.3, const, out=np.full((105, 11), np.nan), pitch=12)   # one column short\n")
     res = _run_sanitized(control, False)
     assert res.returncode != 0 and "heap-buffer-overflow" in res.stderr
+
+
+# ------------------------------------------------------------------- what the matrices MEAN (independent of the reference's code)
+@pytest.mark.parametrize("j2", [False, True])
+def test_matrices_are_the_derivatives_of_the_nonlinear_flow(const, j2):
+    """x_{k+1} = F(x_k, u_k, u_{k+1}, tf) is the nonlinear flow over one interval under the first-order
+    hold; the discretization must be its linearization: A_k = dF/dx_k, B_kn = dF/du_k, B_kp = dF/du_{k+1},
+    Sigma_k = dF/dtf, and xi_k closes the affine model at the reference point.  F and its central differences come from
+    the plain-C propagation oracle (RK4, FOH table of two columns), the matrices from the kernel source.  Phi is integrated
+    (agreement 1e-9); B-, B+, Sigma, xi are the reference's 101-node TRAPEZOID rule (linearize_discretize.py:77-80), whose
+    O(h^2) error on the quadratic-in-tau position rows of B (lambda * (tau - tau_k): 1.7e-5 of the row) is the
+    reference's own and is mirrored, so those agree with the true derivatives to ~4e-6 of the matrix norm."""
+    N, K, tf = 2, 12, 0.6
+    _, x, u = synth_batch(N, K, tf, const)
+    u = u + 0.05 * np.random.default_rng(2).standard_normal(u.shape)      # a hold that really varies inside the interval
+    soa, st = hostk.discretize(x, u, tf, const, include_J2=j2)
+    A, Bp, Bn, S, X = hostk.stacked(soa, N, K)
+    dtau = 1.0 / (K - 1)
+
+    def flow(xk, uk, uk1, tf_):
+        y, _, s = C.propagate_batch(xk[None], tf_ * dtau, const, C.CTRL_SEQUENCE, table=np.column_stack([uk, uk1]),
+                                    end_tau=1.0, include_drag=False, include_J2=j2, T=2, n_sub=200)
+        assert s[0] == 0
+        return y[0, :, 1]
+
+    def jac(f, z, h):
+        cols = []
+        for j in range(len(z)):
+            e = np.zeros(len(z))
+            e[j] = h
+            cols.append((f(z + e) - f(z - e)) / (2 * h))
+        return np.column_stack(cols)
+
+    for s_, k in ((0, 0), (1, 5), (1, K - 2)):
+        xk, uk, uk1 = x[s_, :, k], u[s_, :, k], u[s_, :, k + 1]
+        x1 = flow(xk, uk, uk1, tf)
+        fdA = jac(lambda z: flow(z, uk, uk1, tf), xk, 1e-6)
+        fdBn = jac(lambda z: flow(xk, z, uk1, tf), uk, 1e-6)
+        fdBp = jac(lambda z: flow(xk, uk, z, tf), uk1, 1e-6)
+        fdS = (flow(xk, uk, uk1, tf + 1e-6) - flow(xk, uk, uk1, tf - 1e-6)) / 2e-6
+        assert rel_err(A[s_, k], fdA) < 2e-8 and rel_err(Bn[s_, k], fdBn) < 2e-5 and rel_err(Bp[s_, k], fdBp) < 2e-5
+        assert rel_err(S[s_, :, k], fdS) < 2e-5
+        affine = A[s_, k] @ xk + Bn[s_, k] @ uk + Bp[s_, k] @ uk1 + S[s_, :, k] * tf + X[s_, :, k]
+        assert rel_err(affine, x1) < 5e-6          # closes up to the same trapezoid error (1e-6 with this rough hold)
