@@ -128,7 +128,7 @@ def propagate(y0, tf, const, kind=0, thrust=(0.0, 0.0, 0.0), table=None, end_tau
     c8 = _const8(const)
     lib().hostk_propagate(_p(y0), _p(tfv), _p(c8), int(include_J2), int(include_drag), ctypes.c_double(c_d),
                           ctypes.c_double(rho_atm), int(kind), _p(th), _p(tab), 0 if tab is None else tab.shape[-1],
-                          ctypes.c_double(end_tau), N, int(T), int(n_sub), _p(y), _p(uo), _p(status), _p(progress),
+                          int(tab is not None and tab.ndim == 3), ctypes.c_double(end_tau), N, int(T), int(n_sub), _p(y), _p(uo), _p(status), _p(progress),
                           int(seg_len))
     return y, uo, status, progress
 

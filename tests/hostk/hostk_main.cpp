@@ -94,8 +94,8 @@ extern "C" int hostk_discretize_adaptive(const double *x, const double *u, const
 // controller: kind 0 zero / 1 constant (t0,t1,t2) / 2 tangential (t0) / 3 sequence table [3][table_len] (shared) with end_tau
 extern "C" int hostk_propagate(const double *y0, const double *tf, const double *const8, int include_j2, int include_drag,
                                double c_d, double rho_atm, int kind, const double *thrust, const double *table,
-                               int table_len, double end_tau, int n_sats, int T, int n_sub, double *y, double *u_out,
-                               int32_t *status, unsigned *progress, int seg_len)
+                               int table_len, int table_per_sat, double end_tau, int n_sats, int T, int n_sub, double *y,
+                               double *u_out, int32_t *status, unsigned *progress, int seg_len)
 {
     mpc::PropParams PP;
     PP.mu = const8[0];
@@ -107,6 +107,7 @@ extern "C" int hostk_propagate(const double *y0, const double *tf, const double 
     mpc::CtrlParams C{};
     C.kind = kind;
     C.table_len = table_len;
+    C.table_per_sat = table_per_sat;
     C.t0 = thrust[0];
     C.t1 = thrust[1];
     C.t2 = thrust[2];

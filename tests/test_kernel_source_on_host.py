@@ -338,3 +338,42 @@ def test_matrices_are_the_derivatives_of_the_nonlinear_flow(const, j2):
         assert rel_err(S[s_, :, k], fdS) < 2e-5
         affine = A[s_, k] @ xk + Bn[s_, k] @ uk + Bp[s_, k] @ uk1 + S[s_, :, k] * tf + X[s_, :, k]
         assert rel_err(affine, x1) < 5e-6          # closes up to the same trapezoid error (1e-6 with this rough hold)
+
+
+# ------------------------------------------------------------------------------------------- seeded differential sweep
+@pytest.mark.parametrize("seed", range(16))
+def test_seeded_sweep_against_c_oracle(const, seed):
+    """the cases of tests/test_gpu_fuzz.py (random shapes, horizons, step counts, drag / J2 flags, controller laws) on the
+    host build of the kernel sources: propagation, fixed-step and adaptive discretization against the plain-C oracle"""
+    from test_gpu_fuzz import _case
+    c = _case(seed)
+    rng, n, K, tf = c["rng"], c["n"], c["K"], c["tf"]
+    y0, _, _ = synth_batch(n, 2, 0.1, const, seed=seed)
+    tfv = tf * (1 + 0.1 * rng.random(n))
+    tab, et, cp = None, 1.0, (0.0, 0.0, 0.0)
+    if c["kind"] == 1:
+        cp = tuple(rng.uniform(-0.5, 0.5, 3))
+    elif c["kind"] == 2:
+        cp = (float(rng.uniform(0.1, 1.0)), 0.0, 0.0)
+    elif c["kind"] == 3:
+        tab = rng.uniform(-0.4, 0.4, (n, 3, int(rng.integers(2, 30))))
+        et = float(rng.uniform(1.0, 2.5))
+    ck = [C.CTRL_ZERO, C.CTRL_CONSTANT, C.CTRL_TANGENTIAL, C.CTRL_SEQUENCE][c["kind"]]
+    T = max(K, 2)
+    n_prop = int(rng.integers(1, 12))
+    y, u, st, _ = hostk.propagate(y0, tfv, const, kind=c["kind"], thrust=cp, table=tab, end_tau=et, include_drag=c["drag"],
+                                  include_J2=c["j2"], T=T, n_sub=n_prop)
+    yr, ur, sr = C.propagate_batch(y0, tfv, const, ck, cp, table=tab, end_tau=et, include_drag=c["drag"],
+                                   include_J2=c["j2"], T=T, n_sub=n_prop)
+    assert st.max() == 0 and sr.max() == 0
+    assert rel_err(y, yr) < 1e-11 and np.max(np.abs(u - ur)) < 1e-11
+    ref = C.discretize_batch(yr, ur, tfv, const, include_J2=c["j2"], n_sub=c["n_sub"])
+    soa, sd = hostk.discretize(yr, ur, tfv, const, include_J2=c["j2"], n_sub=c["n_sub"])
+    assert sd.max() == 0 and ref[5].max() == 0
+    for nm, o, r in zip(NAMES, hostk.stacked(soa, n, T), ref[:5]):
+        assert rel_err(o, r) < 1e-10, (nm, rel_err(o, r))
+    ref = C.discretize_batch_adaptive(yr, ur, tfv, const, include_J2=c["j2"])
+    soa, sd, nodes = hostk.discretize_adaptive(yr, ur, tfv, const, include_J2=c["j2"])
+    assert sd.max() == 0 and np.array_equal(nodes, ref[6].reshape(-1))
+    for nm, o, r in zip(NAMES, hostk.stacked(soa, n, T), ref[:5]):
+        assert rel_err(o, r) < 1e-10, (nm, rel_err(o, r))
