@@ -377,3 +377,34 @@ def test_seeded_sweep_against_c_oracle(const, seed):
     assert sd.max() == 0 and np.array_equal(nodes, ref[6].reshape(-1))
     for nm, o, r in zip(NAMES, hostk.stacked(soa, n, T), ref[:5]):
         assert rel_err(o, r) < 1e-10, (nm, rel_err(o, r))
+
+
+# ------------------------------------------------------------------------------------- poisoned inputs must terminate
+@pytest.mark.timeout(300)
+def test_poisoned_inputs_terminate_and_are_flagged(const):
+    """A kernel that never returns hangs a GPU.  Every kernel source on NaN / Inf / zero-radius / non-positive-mass /
+    huge inputs and absurd tf: the step loops end (the adaptive controller caps its node count, a NaN error accepts the
+    step), and the affected units carry a non-zero status (mass 1, non-finite 2, step-size failure 3)."""
+    _, x, u = synth_batch(4, 6, 0.3, const)
+    idx = np.arange(x.size).reshape(x.shape)
+    poisons = {"nan": (np.where(idx % 17 == 3, np.nan, x), u), "inf": (np.where(idx % 19 == 5, np.inf, x), u),
+               "r0": (x * np.array([0, 0, 0, 1, 1, 1, 1.0])[None, :, None], u),
+               "m-": (x * np.array([1, 1, 1, 1, 1, 1, -1.0])[None, :, None], u),
+               "unan": (x, u * np.nan), "uhuge": (x, u * 1e200)}
+    for tag, (xm, um) in poisons.items():
+        for tf in (0.3, np.nan, np.inf, 1e6):
+            st = [hostk.discretize(xm, um, tf, const)[1], hostk.discretize_adaptive(xm, um, tf, const)[1],
+                  hostk.discretize_drag(xm, um, tf, const, (2.2, 4e4), n_sub=6)[1],
+                  hostk.discretize_drag(xm, um, tf, const, (2.2, 4e4), adaptive={})[1]]
+            nodes = hostk.discretize_adaptive(xm, um, tf, const)[2]
+            assert nodes.max() <= 4097
+            for s in st:
+                assert s.min() >= 0 and s.max() <= 3 and s.max() > 0, (tag, tf)
+                if tag in ("r0", "m-", "unan", "uhuge") or not np.isfinite(tf):
+                    assert s.min() > 0, (tag, tf)          # every unit of the batch is affected
+    y0 = x[:, :, 0]
+    for ym in (y0 * np.nan, y0 * np.array([1, 1, 1, 1, 1, 1, -1.0])):
+        for tf in (0.3, np.nan, 1e9):
+            _, _, st, prog = hostk.propagate(ym, tf, const, kind=2, thrust=(0.5, 0, 0), include_drag=True, include_J2=True,
+                                             T=20, n_sub=3, seg_len=4)
+            assert st.min() == 1 and list(prog[:5]) == [1] * 5          # flagged, and the progress words still complete
