@@ -155,6 +155,25 @@ def discretize_drag(x, u, tf, const, drag, include_J2=False, n_sub=100, adaptive
     return out, status, nodes
 
 
+def discretize_ugrid(x, u, tf, const, include_J2=False, n_sub=100, adaptive=None):
+    """u [N,3,Ku] on its own grid (Ku != K): the GENU builds of discretize_kernel / discretize_adaptive_kernel."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    N, _, K = x.shape
+    tfv = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    n_int = N * (K - 1)
+    out = np.full((105, n_int), np.nan)
+    status = np.full(n_int, -1, dtype=np.int32)
+    nodes = np.zeros(n_int, dtype=np.int32)
+    ad = adaptive if adaptive is not None else {}
+    D = ctypes.c_double
+    c8 = _const8(const)
+    lib().hostk_discretize_ugrid(_p(x), _p(u), int(u.shape[2]), _p(tfv), _p(c8), int(include_J2), N, K,
+                                 int(adaptive is not None), int(n_sub), D(ad.get("rtol", 1e-3)), D(ad.get("atol", 1e-6)),
+                                 D(ad.get("max_step", 1e-2)), _p(out), ctypes.c_longlong(n_int), _p(status), _p(nodes))
+    return out, status, nodes
+
+
 def constraint_terms(x, u, mu):
     """constraint_terms_kernel on host arrays x [N,7,K], u [N,3,Ku] -> rbar_hat [N,3,K-1], ubar_hat [N,3,Ku], fin [N,32]"""
     x = np.ascontiguousarray(x, dtype=np.float64)

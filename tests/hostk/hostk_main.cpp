@@ -172,3 +172,24 @@ extern "C" int hostk_dynamics_jacobian(const double *soa, long long pitch, long 
              [&] { mpc::dynamics_jacobian_kernel(soa, pitch, offset, n_sats, K, values, indices, rhs); });
     return 0;
 }
+
+// u on its own grid (u_cols columns; linearize_discretize.py:308-315): the GENU builds of the one-step-per-node kernel and
+// of the adaptive kernel (what mpc_discretize_batch_ugrid launches)
+extern "C" int hostk_discretize_ugrid(const double *x, const double *u, int u_cols, const double *tf, const double *const8,
+                                      int include_j2, int n_sats, int K, int adaptive, int n_sub, double rtol, double atol,
+                                      double max_step, double *out, long long pitch, int32_t *status, int32_t *n_nodes)
+{
+    const mpc::DiscParams P = disc_params(const8, include_j2);
+    mpc::DstTab dst{};
+    dst.p[0] = out;
+    run_grid((long long)n_sats * (K - 1), [&] {
+        if (adaptive) {
+            if (include_j2) mpc::discretize_adaptive_kernel<true, kBlock, 1, true, false>(x, u, tf, P, n_sats, K, u_cols, rtol, atol, max_step, dst, pitch, 0, status, n_nodes);
+            else mpc::discretize_adaptive_kernel<false, kBlock, 1, true, false>(x, u, tf, P, n_sats, K, u_cols, rtol, atol, max_step, dst, pitch, 0, status, n_nodes);
+        } else {
+            if (include_j2) mpc::discretize_kernel<true, kBlock, 255, 1, true>(x, u, tf, P, n_sats, K, u_cols, n_sub, dst, pitch, 0, status);
+            else mpc::discretize_kernel<false, kBlock, 255, 1, true>(x, u, tf, P, n_sats, K, u_cols, n_sub, dst, pitch, 0, status);
+        }
+    });
+    return 0;
+}

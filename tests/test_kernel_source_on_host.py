@@ -408,3 +408,25 @@ def test_poisoned_inputs_terminate_and_are_flagged(const):
             _, _, st, prog = hostk.propagate(ym, tf, const, kind=2, thrust=(0.5, 0, 0), include_drag=True, include_J2=True,
                                              T=20, n_sub=3, seg_len=4)
             assert st.min() == 1 and list(prog[:5]) == [1] * 5          # flagged, and the progress words still complete
+
+
+def test_u_on_its_own_grid_kernels(gold_disc, const):
+    """the GENU builds (mpc_discretize_batch_ugrid): the reference's own test_linearize_many passes a (3, 3K) u
+    (test_discretizer.py:103); same checks as tests/test_gpu_discretize.py::test_u_on_its_own_grid_like_reference...,
+    plus: with u given on x's own grid the general hold is the plain one"""
+    g = gold_disc
+    ks = [int(k) for k in g["d2q_ks"]]
+    x, uq = g["d2_x"][None], g["d2q_u"][None]
+    soa, st, _ = hostk.discretize_ugrid(x, uq, 1.0, const)
+    assert st.max() == 0
+    for n, o in zip(NAMES, hostk.stacked(soa, 1, x.shape[2])):
+        assert rel_err(_sel(o[0], ks), g[f"d2q_uni_{n}"]) < 1e-3, n          # limited by the reference's own RK45 error
+    soa, st, _ = hostk.discretize_ugrid(x, uq, 1.0, const, adaptive={})
+    ref = [O.interval_matrices(k, g["d2_x"], g["d2q_u"], 1.0, const) for k in ks]
+    for i, (n, o) in enumerate(zip(NAMES, hostk.stacked(soa, 1, x.shape[2]))):
+        want = np.stack([r[i] for r in ref]) if i < 3 else np.column_stack([r[i] for r in ref])
+        assert rel_err(_sel(o[0], ks), want) < TOL_REF, n
+    xs, us = g["d4_x"][None], g["d4_u"][None]
+    a, _ = hostk.discretize(xs, us, 0.5, const, pair=False)
+    b, _, _ = hostk.discretize_ugrid(xs, us, 0.5, const)
+    assert rel_err(b, a) < 1e-12
