@@ -249,7 +249,7 @@ def gpu_arm(args):
     std = torch.empty(n_int, dtype=torch.int32, device=dev)
     out = torch.empty((105, n_int), dtype=torch.float64, device=dev) if world == 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-    n_prop = M.batch.default_n_sub(K)
+    n_prop = M.batch.default_n_sub(K) if args.prop == "rk4" else 0   # 0: the reference's RK45, replayed (default)
     fused = None
     gather_mode = "none"
     if world > 1:
@@ -453,8 +453,9 @@ def gpu_arm(args):
                    "overlap": ("propagation hidden behind the discretization: windows along k gated by stream memory operations "
                                "(mpc_propagate_discretize), bit-identical results") if overlap else "none (kernels back to back)",
                    # propagation is sequential in tau (latency-bound), reported as satellite-steps/s
-                   "propagate_sat_steps_per_s": N * (K - 1) * n_prop / (prop_ms_avg * 1e-3),
-                   "propagate_rk4_steps_per_satellite": (K - 1) * n_prop,
+                   "propagator": "scipy RK45 replayed (max_step 0.001: 1000 steps x 6 stages per satellite), dense-output samples"
+                                 if n_prop == 0 else f"fixed-step RK4, {(K - 1) * n_prop} steps x 4 stages per satellite",
+                   "propagate_sat_steps_per_s": N * (1000 if n_prop == 0 else (K - 1) * n_prop) / (prop_ms_avg * 1e-3),
                    "discretize_intervals_per_s_per_gpu": n_int / (disc_ms_avg * 1e-3),
                    "default_mode_adaptive_rk45": None if adaptive_ms is None else {
                        "discretize_ms": adaptive_ms, "intervals_per_s": n_int / (adaptive_ms * 1e-3),
@@ -512,6 +513,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true",
                     help="run propagate and discretize back to back instead of overlapped")
+    ap.add_argument("--prop", default="rk45", choices=["rk45", "rk4"],
+                    help="propagator: the reference's RK45 replayed step for step (default) or fixed-step RK4")
     ap.add_argument("--windows", type=int, default=0, help="windows along k of the overlapped pass (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -157,14 +157,29 @@ int mpc_discretize_batch_ugrid(const double *x, const double *u, int u_cols, con
  *   y0  [n_sats][7]      normalized initial states (scale.normalize_state(sat.get_state_vector()))
  *   tf  [n_sats]
  *   T                    eval_points = int(base_res * tf)    (simulator.py:38,185)
- *   n_sub                RK4 steps between consecutive samples; the reference's max_step=0.001
- *                        (simulator.py:186) corresponds to n_sub = ceil(1000/(T-1))
+ *   n_sub                0: THE REFERENCE'S INTEGRATOR, replayed step for step -- scipy's RK45 (Dormand-Prince 5(4))
+ *                        with its step-size controller, max_step = 0.001 and default tolerances exactly as
+ *                        simulator.py:185-187 calls solve_ivp, samples read off the 4th-order dense output of the step
+ *                        that covers them (propagate_rk45_kernel; agrees with the reference to ~1e-13, also where the
+ *                        thrust jumps inside a run: control.py:127-141).
+ *                        >= 1: fixed-step classical RK4 with n_sub steps between consecutive samples (the reference's
+ *                        max_step corresponds to n_sub = ceil(1000/(T-1))); agrees with the reference to ~1e-8 on
+ *                        smooth inputs only
  *   y   [n_sats][7][T]   sol.y per satellite; sample times are linspace(0,1,T)
  *   u_out [n_sats][3][T] controller output at every sample (may be NULL)
  *   status [n_sats]      MPC_ST_* (may be NULL)
  */
 int mpc_propagate_batch(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
                         int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status, void *stream);
+
+/*
+ * mpc_propagate_batch(n_sub = 0) with the three numbers solve_ivp would take (simulator.py:185-187 hard-codes
+ * max_step = 0.001 and leaves rtol = 1e-3, atol = 1e-6 at scipy's defaults).  n_steps [n_sats] (may be NULL) receives
+ * the number of steps attempted per satellite (accepted + rejected; scipy's nfev = 2 + 6 n_steps).
+ */
+int mpc_propagate_batch_rk45(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
+                             int n_sats, int T, double rtol, double atol, double max_step, double *y, double *u_out,
+                             int32_t *status, int32_t *n_steps, void *stream);
 
 /* ---------------------------------------------------------------- host API */
 typedef struct mpc_ctx mpc_ctx;
@@ -204,11 +219,18 @@ int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, c
                              const mpc_controller *ctrl, int n_sats, int T, int n_sub, double *y_host,
                              double *u_host, int32_t *status_host);
 
+/* Host-buffer form of mpc_propagate_batch_rk45. */
+int mpc_propagate_batch_rk45_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p,
+                                  const mpc_controller *ctrl, int n_sats, int T, double rtol, double atol,
+                                  double max_step, double *y_host, double *u_host, int32_t *status_host,
+                                  int32_t *n_steps_host);
+
 /*
  * SCP inner step on host buffers, fused on the device (control.py:180-188 pattern): propagate the
  * batch, evaluate the controller on the samples (extract_uk), discretize about the result.  The
  * reference trajectory never leaves HBM between the two kernels.  K = T.
- * Any of y_host / u_host may be NULL when the caller only wants the matrices.
+ * Any of y_host / u_host may be NULL when the caller only wants the matrices.  n_sub_prop as n_sub of
+ * mpc_propagate_batch (0 = the reference's RK45, replayed), here and in the two entry points below.
  */
 int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
                                   const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
@@ -316,7 +338,9 @@ int64_t mpc_launch_count(void);
  * two-node integrator steps of the production kernel off / on (results differ by ~1e-12).  9 / 10 switch the COMPACT
  * build of the adaptive (default-mode) kernel on / off: dynamics evaluation and node term as real calls instead of
  * inlined copies (same arithmetic, checked on the host build of the sources; an instruction-fetch experiment that has
- * not been timed on a GPU yet -- off by default). */
+ * not been timed on a GPU yet -- off by default).  11 / 12: RK45 propagator without / with the speculative first stage
+ * of the next step (same results).  13: satellites per warp of the RK45 propagator chosen automatically, 14..19: forced
+ * to 32, 16, 8, 4, 2, 1 (same results). */
 int mpc_set_tuning(int variant);
 
 /* Options of the fused (in-kernel store) all-gather, applied by mpc_discretize_batch / _multi:

@@ -15,9 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libmpc_b200.so")
 SOURCES = ["mpc_b200.cu"]
-HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "propagate_kernel.cuh", "constraint_terms_kernel.cuh", "discretize_drag_kernel.cuh", "discretize_pair_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
+HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "constraint_terms_kernel.cuh", "discretize_drag_kernel.cuh", "discretize_pair_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-split-compile", "0"]
 
 MPC_OUT_ROWS = 105
 ROW_A, ROW_BP, ROW_BN, ROW_SIGMA, ROW_XI = 0, 49, 70, 91, 98
@@ -100,6 +100,8 @@ def lib():
     L.mpc_discretize_batch_ugrid.argtypes = [_DP, _DP, i, _DP, pp, i, i, i, i, d, d, d, _DP, i64, i64, _DP, _DP, vp]
     L.mpc_discretize_batch_ugrid_host.argtypes = [vp, _DP, _DP, i, _DP, pp, i, i, i, i, d, d, d, _DP, _DP, _DP]
     L.mpc_propagate_batch.argtypes = [_DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP, vp]
+    L.mpc_propagate_batch_rk45.argtypes = [_DP, _DP, pp, pc, i, i, d, d, d, _DP, _DP, _DP, _DP, vp]
+    L.mpc_propagate_batch_rk45_host.argtypes = [vp, _DP, _DP, pp, pc, i, i, d, d, d, _DP, _DP, _DP, _DP]
     L.mpc_ctx_create.argtypes = [i, ctypes.POINTER(vp)]
     L.mpc_ctx_destroy.argtypes = [vp]
     L.mpc_host_alloc.argtypes = [ctypes.c_size_t]
@@ -121,7 +123,7 @@ def lib():
     L.mpc_set_gather_tuning.restype = i
     L.mpc_set_tuning.argtypes = [i]
     L.mpc_set_tuning.restype = i
-    for name in ("mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
+    for name in ("mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host", "mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
                  "mpc_discretize_batch_adaptive", "mpc_discretize_batch_adaptive_host",
                  "mpc_discretize_batch_ugrid", "mpc_discretize_batch_ugrid_host",
                  "mpc_ctx_create", "mpc_ctx_destroy", "mpc_discretize_batch_host", "mpc_propagate_batch_host",
@@ -135,6 +137,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "mpc_version", "mpc_last_error", "mpc_device_count", "mpc_device_info", "mpc_launch_count",
     "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_discretize_batch_ugrid", "mpc_propagate_batch",
+    "mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host",
     "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
     "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_discretize_batch_ugrid_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host", "mpc_propagate_discretize", "mpc_propagate_discretize_multi",
     "mpc_constraint_terms", "mpc_constraint_terms_host", "mpc_discretize_batch_push", "mpc_fill_const_rows",

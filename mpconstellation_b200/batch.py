@@ -15,6 +15,14 @@ from .control import ControllerSpec, spec_from
 
 _ctx_lock = threading.Lock()
 _ctxs = {}
+_call_locks = {}
+
+
+def _lock(device=0):
+    """One lock per device context: an mpc_ctx owns ONE workspace (device buffers, events, pinned staging), and ctypes
+    releases the GIL during a call, so two Python threads must not be inside host-API calls of the same ctx at once."""
+    with _ctx_lock:
+        return _call_locks.setdefault(device, threading.RLock())
 
 
 def _ctx(device=0):
@@ -119,23 +127,24 @@ def discretize_batch(x, u, tf, const, include_J2=False, include_drag=False, n_su
         status = np.zeros(n_int, dtype=np.int32)
     p = _lib.make_params(const, include_J2, include_drag, disc_drag=disc_drag)
     n_nodes = None
-    if Ku != K:
-        ad = adaptive or {}
-        n_nodes = np.zeros(n_int, dtype=np.int32) if adaptive is not None else None
-        _lib.check(_lib.lib().mpc_discretize_batch_ugrid_host(
-            ctx, _lib.addr(x), _lib.addr(u), Ku, _lib.addr(tfv), ctypes.byref(p), N, K, int(adaptive is not None),
-            int(n_sub), float(ad.get("rtol", 1e-3)), float(ad.get("atol", 1e-6)), float(ad.get("max_step", 1e-2)),
-            _lib.addr(out), _lib.addr(status), _lib.addr(n_nodes)))
-    elif adaptive is None:
-        _lib.check(_lib.lib().mpc_discretize_batch_host(ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv),
-                                                        ctypes.byref(p), N, K, int(n_sub), _lib.addr(out),
-                                                        _lib.addr(status)))
-    else:
-        n_nodes = np.zeros(n_int, dtype=np.int32)
-        _lib.check(_lib.lib().mpc_discretize_batch_adaptive_host(
-            ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv), ctypes.byref(p), N, K, float(adaptive.get("rtol", 1e-3)),
-            float(adaptive.get("atol", 1e-6)), float(adaptive.get("max_step", 1e-2)), _lib.addr(out), _lib.addr(status),
-            _lib.addr(n_nodes)))
+    with _lock(device):
+        if Ku != K:
+            ad = adaptive or {}
+            n_nodes = np.zeros(n_int, dtype=np.int32) if adaptive is not None else None
+            _lib.check(_lib.lib().mpc_discretize_batch_ugrid_host(
+                ctx, _lib.addr(x), _lib.addr(u), Ku, _lib.addr(tfv), ctypes.byref(p), N, K, int(adaptive is not None),
+                int(n_sub), float(ad.get("rtol", 1e-3)), float(ad.get("atol", 1e-6)), float(ad.get("max_step", 1e-2)),
+                _lib.addr(out), _lib.addr(status), _lib.addr(n_nodes)))
+        elif adaptive is None:
+            _lib.check(_lib.lib().mpc_discretize_batch_host(ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv),
+                                                            ctypes.byref(p), N, K, int(n_sub), _lib.addr(out),
+                                                            _lib.addr(status)))
+        else:
+            n_nodes = np.zeros(n_int, dtype=np.int32)
+            _lib.check(_lib.lib().mpc_discretize_batch_adaptive_host(
+                ctx, _lib.addr(x), _lib.addr(u), _lib.addr(tfv), ctypes.byref(p), N, K, float(adaptive.get("rtol", 1e-3)),
+                float(adaptive.get("atol", 1e-6)), float(adaptive.get("max_step", 1e-2)), _lib.addr(out), _lib.addr(status),
+                _lib.addr(n_nodes)))
     res = DiscretizedBatch(out, status.reshape(N, K - 1), N, K)
     res.n_nodes = None if n_nodes is None else n_nodes.reshape(N, K - 1)
     if check:
@@ -176,11 +185,16 @@ def default_n_sub(T, max_step=0.001):
 
 
 def propagate_batch(y0, tf, controller, const, include_drag=True, include_J2=True, T=100, n_sub=None,
-                    want_u=True, device=0, check=True, y_out=None, u_out=None):
+                    want_u=True, device=0, check=True, y_out=None, u_out=None, rk45=None, n_steps=None):
     """Propagate N satellites over tau in [0,1] and sample at linspace(0,1,T) (host arrays).
 
     y0 [N,7] normalized states; returns (y [N,7,T], u [N,3,T] or None, t [T], status [N]).
     ref: simulator.py:164-189 (+ extract_uk, linearize_discretize.py:393-411).
+
+    n_sub=None (default): the reference's own integrator, replayed on the device -- scipy's RK45 with its step-size
+    controller exactly as simulator.py:185-187 calls it (max_step=0.001, rtol 1e-3, atol 1e-6, dense-output samples);
+    `rk45=dict(rtol=, atol=, max_step=)` overrides those numbers, `n_steps` (int32 [N]) receives the steps attempted.
+    n_sub >= 1: fixed-step RK4 with n_sub steps between samples (default_n_sub(T) mirrors max_step=0.001).
     """
     ctx = _ctx(device)
     y0 = _f64(y0)
@@ -191,7 +205,9 @@ def propagate_batch(y0, tf, controller, const, include_drag=True, include_J2=Tru
     spec = spec_from(controller)
     tfv = _tf_vec(tf, N)
     if n_sub is None:
-        n_sub = default_n_sub(T)
+        n_sub = 0
+    if n_sub != 0 and rk45 is not None:
+        raise ValueError("rk45 options only apply to the reference integrator (n_sub=None)")
     y = y_out if y_out is not None else _lib.pinned_empty((N, 7, T))
     uo = (u_out if u_out is not None else _lib.pinned_empty((N, 3, T))) if want_u else None
     status = np.zeros(N, dtype=np.int32)
@@ -200,9 +216,20 @@ def propagate_batch(y0, tf, controller, const, include_drag=True, include_J2=Tru
         return y, uo, t, status
     p = _lib.make_params(const, include_J2, include_drag)
     c, _keep = _ctrl_struct(spec, N)
-    _lib.check(_lib.lib().mpc_propagate_batch_host(ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(p),
-                                                   ctypes.byref(c), N, T, int(n_sub), _lib.addr(y),
-                                                   _lib.addr(uo), _lib.addr(status)))
+    if n_sub == 0:
+        o = rk45 or {}
+        if n_steps is not None and (n_steps.shape != (N,) or n_steps.dtype != np.int32):
+            raise ValueError("n_steps must be int32 [N]")
+        with _lock(device):
+            _lib.check(_lib.lib().mpc_propagate_batch_rk45_host(
+                ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(p), ctypes.byref(c), N, T, float(o.get("rtol", 1e-3)),
+                float(o.get("atol", 1e-6)), float(o.get("max_step", 1e-3)), _lib.addr(y), _lib.addr(uo),
+                _lib.addr(status), _lib.addr(n_steps)))
+    else:
+        with _lock(device):
+            _lib.check(_lib.lib().mpc_propagate_batch_host(ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(p),
+                                                           ctypes.byref(c), N, T, int(n_sub), _lib.addr(y),
+                                                           _lib.addr(uo), _lib.addr(status)))
     if check:
         raise_on_status(status)
     return y, uo, t, status
@@ -222,7 +249,7 @@ def propagate_discretize(y0, tf, controller, const, T, prop_drag=False, prop_J2=
     tfv = _tf_vec(tf, N)
     n_int = N * (T - 1)
     if n_sub_prop is None:
-        n_sub_prop = default_n_sub(T)
+        n_sub_prop = 0                    # the reference's RK45, replayed (see propagate_batch)
     if out is None:
         out = _lib.pinned_empty((_lib.MPC_OUT_ROWS, n_int))
     y = y_out if y_out is not None else _lib.pinned_empty((N, 7, T))
@@ -234,10 +261,11 @@ def propagate_discretize(y0, tf, controller, const, T, prop_drag=False, prop_J2=
     pp = _lib.make_params(const, prop_J2, prop_drag)
     pd = _lib.make_params(const, disc_J2, False)
     c, _keep = _ctrl_struct(spec, N)
-    _lib.check(_lib.lib().mpc_propagate_discretize_host(ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(pp),
-                                                        ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop),
-                                                        int(n_sub_disc), _lib.addr(y), _lib.addr(uo), _lib.addr(out),
-                                                        _lib.addr(status)))
+    with _lock(device):
+        _lib.check(_lib.lib().mpc_propagate_discretize_host(ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(pp),
+                                                            ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop),
+                                                            int(n_sub_disc), _lib.addr(y), _lib.addr(uo),
+                                                            _lib.addr(out), _lib.addr(status)))
     res = DiscretizedBatch(out, status.reshape(N, T - 1), N, T)
     if check:
         res.raise_on_error()
@@ -294,7 +322,7 @@ def propagate_batch_device(y0, tf, controller, const, include_drag=True, include
     N = y0.shape[0]
     spec = spec_from(controller)
     if n_sub is None:
-        n_sub = default_n_sub(T)
+        n_sub = 0                         # the reference's RK45, replayed (see propagate_batch)
     if y is None:
         y = torch.empty((N, 7, T), dtype=torch.float64, device=y0.device)
     if u_out is None:
@@ -338,7 +366,7 @@ def propagate_discretize_device(y0, tf, controller, const, T, prop_drag=False, p
     n_int = N * (T - 1)
     spec = spec_from(controller)
     if n_sub_prop is None:
-        n_sub_prop = default_n_sub(T)
+        n_sub_prop = 0                    # the reference's RK45, replayed (see propagate_batch)
     if y is None:
         y = torch.empty((N, 7, T), dtype=torch.float64, device=dev)
     if u_out is None:
@@ -364,11 +392,13 @@ def propagate_discretize_device(y0, tf, controller, const, T, prop_drag=False, p
     ptrs = [int(out_ptr) if out_ptr is not None else out.data_ptr()]
     ptrs += [int(d_ if isinstance(d_, int) else d_.data_ptr()) for d_ in (extra_dst or [])]
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
-    _lib.check(_lib.lib().mpc_propagate_discretize_multi(
-        _ctx(dev.index if dev.index is not None else torch.cuda.current_device()), y0.data_ptr(), tf.data_ptr(),
-        ctypes.byref(pp), ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop), int(n_sub_disc), y.data_ptr(),
-        u_out.data_ptr(), arr, len(ptrs), pitch, int(out_offset), status_prop.data_ptr(), status_disc.data_ptr(),
-        int(n_windows), cur.cuda_stream))
+    dev_i = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _lock(dev_i):   # the ctx owns the internal streams / progress words of the overlapped pass
+        _lib.check(_lib.lib().mpc_propagate_discretize_multi(
+            _ctx(dev_i), y0.data_ptr(), tf.data_ptr(),
+            ctypes.byref(pp), ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop), int(n_sub_disc), y.data_ptr(),
+            u_out.data_ptr(), arr, len(ptrs), pitch, int(out_offset), status_prop.data_ptr(), status_disc.data_ptr(),
+            int(n_windows), cur.cuda_stream))
     for t_ in (tab_dev, et_dev):
         if t_ is not None:
             t_.record_stream(cur)

@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .batch import _ctx, _f64
+from .batch import _ctx, _f64, _lock
 
 KEYS = ['rbar_hat', 'ubar_hat', 'rf_hat', 'Vc', 'DrVc', 'DrVc_rbar', 'Vt', 'DrVt_DvVt', 'DrVt_DvVt_bar',
         'Vr', 'DrVr_DvVr', 'DrVr_DvVr_bar', 'Vn', 'DrVn_DvVn', 'DrVn_DvVn_bar']    # optimizer.py:101-104
@@ -39,8 +39,9 @@ def constraint_terms_batch(x, u, const, device=0):
     rbar = np.empty((N, 3, K - 1))
     ubar = np.empty((N, 3, Ku))
     fin = np.empty((N, _lib.FINAL_TERMS))
-    _lib.check(_lib.lib().mpc_constraint_terms_host(ctx, _lib.addr(x), _lib.addr(u), N, K, Ku, float(const.MU),
-                                                    _lib.addr(rbar), _lib.addr(ubar), _lib.addr(fin)))
+    with _lock(device):
+        _lib.check(_lib.lib().mpc_constraint_terms_host(ctx, _lib.addr(x), _lib.addr(u), N, K, Ku, float(const.MU),
+                                                        _lib.addr(rbar), _lib.addr(ubar), _lib.addr(fin)))
     out = {"rbar_hat": rbar, "ubar_hat": ubar}
     out.update(_split_final(fin))
     return out

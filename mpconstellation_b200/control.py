@@ -115,30 +115,63 @@ _BY_NAME = {
 }
 
 
+def _known_law(obj):
+    """ControllerSpec of a controller OBJECT whose control law is one the device evaluates, else None.  Only exact
+    classes qualify: a subclass may override get_u_func (a feedback law on top of ConstantThrustController, say) and
+    would silently fly its parent's law, so it is refused unless its get_u_func is still the known implementation."""
+    klass = type(obj)
+    if isinstance(obj, Controller):                      # this package's controllers
+        if klass.get_u_func is Controller.get_u_func and klass.device_spec in _OWN_SPECS:
+            return obj.device_spec()
+        return None
+    if klass.__name__ in _BY_NAME:                       # the reference's own classes, by exact name
+        return _BY_NAME[klass.__name__](obj)
+    return None
+
+
+def stateless(controller):
+    """True when controller.update() cannot change the law between satellites (what lets run_segment propagate every
+    satellite in one launch): this package's controllers with the inherited no-op update, or reference controllers
+    whose update is the base class's `pass` (control.py:31-35)."""
+    klass = type(controller)
+    if isinstance(controller, Controller):
+        return klass.update is Controller.update
+    base = [k for k in klass.__mro__ if k.__name__ == "Controller"]
+    return bool(base) and getattr(klass, "update", None) is getattr(base[0], "update", None)
+
+
 def spec_from(obj):
-    """ControllerSpec from: a ControllerSpec, one of this package's controllers, a reference controller
-    object (matched by class name), an OptimalController after update() (its sequence_controller), or a
-    u_func closure produced by any of those.  Anything else cannot run on the device: NotImplementedError."""
+    """ControllerSpec from: a ControllerSpec, one of this package's controllers, a reference controller object (exact
+    class, matched by name), an OptimalController after update() (its sequence_controller), or a u_func closure produced
+    by any of those.  Anything else -- subclasses with their own law included -- cannot run on the device:
+    NotImplementedError (the package never falls back to calling Python per stage)."""
     if isinstance(obj, ControllerSpec):
         return obj
     if hasattr(obj, "mpc_spec"):
         return obj.mpc_spec
-    if hasattr(obj, "device_spec"):
-        return obj.device_spec()
-    if hasattr(obj, "sequence_controller"):       # reference OptimalController (control.py:217,245)
+    if hasattr(obj, "sequence_controller"):              # reference OptimalController after update() (control.py:217,245)
         return spec_from(obj.sequence_controller)
-    for klass in type(obj).__mro__:
-        if klass.__name__ in _BY_NAME and not callable(getattr(obj, "__call__", None)):
-            return _BY_NAME[klass.__name__](obj)
-    if callable(obj):
+    if type(obj).__name__ == "OptimalController":
+        # before the first update() the reference's get_u_func (control.py:244-245) raises exactly this
+        raise AttributeError("'OptimalController' object has no attribute 'sequence_controller'")
+    if not callable(obj) or isinstance(obj, Controller):
+        spec = _known_law(obj)
+        if spec is not None:
+            return spec
+    elif callable(obj):
         qual = getattr(obj, "__qualname__", "")
         cells = [c.cell_contents for c in (getattr(obj, "__closure__", None) or ())]
         for c in cells:                            # reference lambdas close over `self`
-            for klass in type(c).__mro__:
-                if klass.__name__ in _BY_NAME and klass.__name__ != "Controller":
-                    return _BY_NAME[klass.__name__](c)
+            if type(c).__name__ != "Controller":
+                spec = None if isinstance(c, (int, float, str, np.ndarray)) else _known_law(c)
+                if spec is not None:
+                    return spec
         if qual.startswith("Controller.get_u_func"):
             return ControllerSpec()
     raise NotImplementedError(
         f"controller / u_func {obj!r} has no device encoding: the GPU propagator evaluates the reference's "
         "controller laws (zero, constant, tangential, sequence) on the device and cannot call back into Python")
+
+
+_OWN_SPECS = (Controller.device_spec, ConstantThrustController.device_spec,
+              ConstantTangentialThrustController.device_spec, SequenceController.device_spec)

@@ -17,6 +17,7 @@
 #include "discretize_kernel.cuh"
 #include "discretize_adaptive_kernel.cuh"
 #include "propagate_kernel.cuh"
+#include "propagate_rk45_kernel.cuh"
 #include "constraint_terms_kernel.cuh"
 #include "discretize_drag_kernel.cuh"
 #include "discretize_pair_kernel.cuh"
@@ -342,14 +343,68 @@ int check_ctrl(const mpc_controller *c)
     return MPC_SUCCESS;
 }
 
+// How the propagation is integrated.  n_sub >= 1: fixed-step RK4 with n_sub steps between samples.  n_sub == 0: the
+// reference's own integrator (simulator.py:185-187: solve_ivp RK45, max_step = 0.001, scipy's default tolerances, samples
+// off the dense output), replayed step for step by propagate_rk45_kernel; `rk` overrides those three numbers.
+struct PropMode {
+    int n_sub = 0;
+    mpc::Rk45Opts rk{1e-3, 1e-6, 1e-3};
+    int32_t *n_steps = nullptr;   // RK45 only: steps attempted per satellite (accepted + rejected), may be NULL
+    bool rk45() const { return n_sub == 0; }
+};
+
+std::atomic<int> g_rk45_spec{1};   // mpc_set_tuning(11/12): speculative first stage of the next step off / on
+std::atomic<int> g_rk45_lpw{0};    // mpc_set_tuning(13..16): satellites per warp of the RK45 propagator (0 = automatic)
+
+// satellites per warp: a warp's FP64 instructions cost the same issue slots whether 8 or 32 lanes are active, and the
+// propagation is a chain of dependent stages, so a batch is spread over as many SM sub-partitions as there are
+// (4 per SM) before warps are filled up
+int rk45_lanes_per_warp(int n_sats, int sm_count)
+{
+    const int forced = g_rk45_lpw.load(std::memory_order_relaxed);
+    if (forced > 0) return forced;
+    const long long slots = (long long)sm_count * 4;
+    for (int lpw = 1; lpw < 32; lpw *= 2)
+        if ((long long)n_sats <= slots * lpw) return lpw;
+    return 32;
+}
+
+template <int KIND, bool DRAG, bool J2>
+void launch_rk45(bool overlap, bool spec, unsigned n_warps, cudaStream_t st, const double *y0, const double *tf,
+                 const mpc::PropParams &PP, const mpc::CtrlParams &C, const mpc::Rk45Opts &O, int n_sats, int T, int lpw,
+                 double *y, double *u_out, int32_t *status, int32_t *n_steps, unsigned int *progress, int seg_len)
+{
+    // beside the discretization (overlap) the propagation runs as 4-warp CTAs so that it takes CTA slots on few SMs
+    if (overlap) {
+        const unsigned grid = (n_warps + 3) / 4;
+        if (spec)
+            mpc::propagate_rk45_kernel<kPropBlockOverlap, KIND, DRAG, J2, true><<<grid, kPropBlockOverlap, 0, st>>>(
+                y0, tf, PP, C, O, n_sats, T, lpw, y, u_out, status, n_steps, progress, seg_len);
+        else
+            mpc::propagate_rk45_kernel<kPropBlockOverlap, KIND, DRAG, J2, false><<<grid, kPropBlockOverlap, 0, st>>>(
+                y0, tf, PP, C, O, n_sats, T, lpw, y, u_out, status, n_steps, progress, seg_len);
+    } else {
+        if (spec)
+            mpc::propagate_rk45_kernel<kPropBlock, KIND, DRAG, J2, true><<<n_warps, kPropBlock, 0, st>>>(
+                y0, tf, PP, C, O, n_sats, T, lpw, y, u_out, status, n_steps, progress, seg_len);
+        else
+            mpc::propagate_rk45_kernel<kPropBlock, KIND, DRAG, J2, false><<<n_warps, kPropBlock, 0, st>>>(
+                y0, tf, PP, C, O, n_sats, T, lpw, y, u_out, status, n_steps, progress, seg_len);
+    }
+}
+
 // progress / seg_len: see propagate_kernel (the overlapped pass); then the CTAs are 4 warps instead of 1, so that the
-// propagation occupies 32 SMs instead of 128 while the discretization runs beside it
+// propagation occupies 32 SMs instead of 128 while the discretization runs beside it.  *progress_target receives the
+// value progress[b] reaches when window b may start (warps for the RK4 kernel, satellites for the RK45 one).
 int prop_device(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *c,
-                const double *table_dev, const double *end_tau_dev, int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status,
-                cudaStream_t st, unsigned int *progress = nullptr, int seg_len = 0)
+                const double *table_dev, const double *end_tau_dev, int n_sats, int T, const PropMode &mode, double *y, double *u_out, int32_t *status,
+                cudaStream_t st, unsigned int *progress = nullptr, int seg_len = 0, unsigned int *progress_target = nullptr)
 {
     if (!y0 || !tf || !p || !y) return fail(MPC_E_INVALID, "null pointer argument");
-    if (n_sats < 0 || T < 0 || n_sub < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 0, n_sub >= 1");
+    const int n_sub = mode.n_sub;
+    if (n_sats < 0 || T < 0 || n_sub < 0) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 0, n_sub >= 0");
+    if (mode.rk45() && (!(mode.rk.rtol > 0.0) || !(mode.rk.atol > 0.0) || !(mode.rk.max_step > 0.0)))
+        return fail(MPC_E_INVALID, "the RK45 propagator needs rtol, atol, max_step > 0");
     int rc = check_ctrl(c);
     if (rc) return rc;
     if (n_sats == 0 || T == 0) return MPC_SUCCESS;
@@ -367,10 +422,21 @@ int prop_device(const double *y0, const double *tf, const mpc_params *p, const m
     const unsigned grid = (unsigned)((n_sats + kPropBlock - 1) / kPropBlock);
     const unsigned grid_ov = (unsigned)((n_sats + kPropBlockOverlap - 1) / kPropBlockOverlap);
     const mpc::PropParams PP = prop_params(p);
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // beside the discretization full warps keep the propagation on few SMs; on its own it spreads out
+    const int lpw = progress ? 32 : rk45_lanes_per_warp(n_sats, sms);
+    const unsigned n_warps = (unsigned)((n_sats + lpw - 1) / lpw);
+    const bool spec = g_rk45_spec.load(std::memory_order_relaxed) != 0;
+    if (progress_target) *progress_target = mode.rk45() ? (unsigned)n_sats : (unsigned)((n_sats + 31) / 32);
     // one straight-line kernel per (controller law, drag, J2)
 #define MPC_PROP(KIND, DRAG, J2)                                                                                          \
     do {                                                                                                                  \
-        if (progress)                                                                                                     \
+        if (mode.rk45())                                                                                                  \
+            launch_rk45<KIND, DRAG, J2>(progress != nullptr, spec, n_warps, st, y0, tf, PP, C, mode.rk, n_sats, T, lpw, y, \
+                                        u_out, status, mode.n_steps, progress, seg_len);                                  \
+        else if (progress)                                                                                                \
             mpc::propagate_kernel<kPropBlockOverlap, KIND, DRAG, J2><<<grid_ov, kPropBlockOverlap, 0, st>>>(              \
                 y0, tf, PP, C, n_sats, T, n_sub, y, u_out, status, progress, seg_len);                                    \
         else                                                                                                              \
@@ -398,6 +464,13 @@ int prop_device(const double *y0, const double *tf, const mpc_params *p, const m
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
+}
+
+PropMode mode_of(int n_sub)
+{
+    PropMode m;
+    m.n_sub = n_sub;
+    return m;
 }
 
 }  // namespace
@@ -564,6 +637,15 @@ int mpc_set_tuning(int variant)
         g_compact.store(variant == 9);
         return MPC_SUCCESS;
     }
+    if (variant == 11 || variant == 12) {  // RK45 propagator: speculative first stage of the next step off / on
+        g_rk45_spec.store(variant == 12);
+        return MPC_SUCCESS;
+    }
+    if (variant >= 13 && variant <= 19) {  // RK45 propagator: satellites per warp 13 automatic, 14..19 -> 32,16,8,4,2,1
+        static const int lpw[7] = {0, 32, 16, 8, 4, 2, 1};
+        g_rk45_lpw.store(lpw[variant - 13]);
+        return MPC_SUCCESS;
+    }
     if (variant < 0 || variant > 6) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);
     g_tuning.store(variant);
     return MPC_SUCCESS;
@@ -622,8 +704,19 @@ int mpc_propagate_batch(const double *y0, const double *tf, const mpc_params *p,
                         int n_sats, int T, int n_sub, double *y, double *u_out, int32_t *status, void *stream)
 {
     return prop_device(y0, tf, p, ctrl, ctrl ? ctrl->table : nullptr, ctrl ? ctrl->end_tau_per_sat : nullptr, n_sats, T,
-                       n_sub, y, u_out, status,
+                       mode_of(n_sub), y, u_out, status,
                        (cudaStream_t)stream);
+}
+
+int mpc_propagate_batch_rk45(const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
+                             int n_sats, int T, double rtol, double atol, double max_step, double *y, double *u_out,
+                             int32_t *status, int32_t *n_steps, void *stream)
+{
+    PropMode m;
+    m.rk = mpc::Rk45Opts{rtol, atol, max_step};
+    m.n_steps = n_steps;
+    return prop_device(y0, tf, p, ctrl, ctrl ? ctrl->table : nullptr, ctrl ? ctrl->end_tau_per_sat : nullptr, n_sats, T, m,
+                       y, u_out, status, (cudaStream_t)stream);
 }
 
 int mpc_ctx_create(int device, mpc_ctx **out)
@@ -801,12 +894,12 @@ static int upload_table(mpc_ctx *ctx, const mpc_controller *ctrl, int n_sats, cu
     return MPC_SUCCESS;
 }
 
-int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p,
-                             const mpc_controller *ctrl, int n_sats, int T, int n_sub, double *y_host,
-                             double *u_host, int32_t *status_host)
+static int prop_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p, const mpc_controller *ctrl,
+                     int n_sats, int T, PropMode mode, double *y_host, double *u_host, int32_t *status_host,
+                     int32_t *n_steps_host)
 {
     if (!ctx || !y0 || !tf || !p || !y_host) return fail(MPC_E_INVALID, "null pointer argument");
-    if (n_sats < 0 || T < 0 || n_sub < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 0, n_sub >= 1");
+    if (n_sats < 0 || T < 0 || mode.n_sub < 0) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 0, n_sub >= 0");
     int rc = check_ctrl(ctrl);
     if (rc) return rc;
     if (n_sats == 0 || T == 0) return MPC_SUCCESS;
@@ -820,14 +913,37 @@ int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, c
     CUDA_TRY(cudaMemcpyAsync(ctx->d_y0, y0, (size_t)n_sats * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_tf, tf, (size_t)n_sats * sizeof(double), cudaMemcpyHostToDevice, st));
     if ((rc = upload_table(ctx, ctrl, n_sats, st))) return rc;
-    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p, ctrl, ctx->d_tab, ctrl->end_tau_per_sat ? ctx->d_endtau : nullptr, n_sats, T, n_sub, ctx->d_x, ctx->d_u, ctx->d_status2, st)))
+    if (mode.rk45() && n_steps_host) {
+        if ((rc = ensure(ctx->d_nodes, ctx->cap_nodes, (size_t)n_sats))) return rc;
+        mode.n_steps = ctx->d_nodes;
+    }
+    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p, ctrl, ctx->d_tab, ctrl->end_tau_per_sat ? ctx->d_endtau : nullptr, n_sats, T, mode, ctx->d_x, ctx->d_u, ctx->d_status2, st)))
         return rc;
     CUDA_TRY(cudaMemcpyAsync(y_host, ctx->d_x, (size_t)n_sats * 7 * T * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (u_host) CUDA_TRY(cudaMemcpyAsync(u_host, ctx->d_u, (size_t)n_sats * 3 * T * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (status_host)
         CUDA_TRY(cudaMemcpyAsync(status_host, ctx->d_status2, (size_t)n_sats * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (mode.rk45() && n_steps_host)
+        CUDA_TRY(cudaMemcpyAsync(n_steps_host, ctx->d_nodes, (size_t)n_sats * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return MPC_SUCCESS;
+}
+
+int mpc_propagate_batch_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p,
+                             const mpc_controller *ctrl, int n_sats, int T, int n_sub, double *y_host,
+                             double *u_host, int32_t *status_host)
+{
+    return prop_host(ctx, y0, tf, p, ctrl, n_sats, T, mode_of(n_sub), y_host, u_host, status_host, nullptr);
+}
+
+int mpc_propagate_batch_rk45_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p,
+                                  const mpc_controller *ctrl, int n_sats, int T, double rtol, double atol,
+                                  double max_step, double *y_host, double *u_host, int32_t *status_host,
+                                  int32_t *n_steps_host)
+{
+    PropMode m;
+    m.rk = mpc::Rk45Opts{rtol, atol, max_step};
+    return prop_host(ctx, y0, tf, p, ctrl, n_sats, T, m, y_host, u_host, status_host, n_steps_host);
 }
 
 int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
@@ -837,7 +953,7 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
 {
     if (!ctx || !y0 || !tf || !p_prop || !p_disc || !out_host) return fail(MPC_E_INVALID, "null pointer argument");
     const int K = T;
-    if (n_sats < 0 || K < 2 || n_sub_prop < 1 || n_sub_disc < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 2, n_sub >= 1");
+    if (n_sats < 0 || K < 2 || n_sub_prop < 0 || n_sub_disc < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 2, n_sub_prop >= 0, n_sub_disc >= 1");
     if (p_disc->include_drag && !(p_disc->disc_cd > 0.0 && p_disc->disc_rho >= 0.0))
         return fail(MPC_E_UNSUPPORTED, "include_drag needs disc_cd / disc_rho (const.CD, rho_func): the reference raises without them too");
     int rc = check_ctrl(ctrl);
@@ -862,7 +978,7 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
     // the whole batch is propagated first (one thread per satellite is latency-bound: chunking it
     // would only serialise the latency), then discretized chunk by chunk while results stream out
     if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p_prop, ctrl, ctx->d_tab, ctrl->end_tau_per_sat ? ctx->d_endtau : nullptr, n_sats, K,
-                          n_sub_prop, ctx->d_x, ctx->d_u,
+                          mode_of(n_sub_prop), ctx->d_x, ctx->d_u,
                           ctx->d_status2, st)))
         return rc;
     // the reference trajectory and inputs go back to the host while the first chunks are being discretized
@@ -980,7 +1096,7 @@ int prop_disc_overlapped(mpc_ctx *ctx, const double *y0, const double *tf, const
     const int K = T;
     int rc = check_disc_args(x, u, tf, p_disc, n_sats, K, n_sub_disc);
     if (rc) return rc;
-    if (n_sub_prop < 1) return fail(MPC_E_INVALID, "need n_sub_prop >= 1");
+    if (n_sub_prop < 0) return fail(MPC_E_INVALID, "need n_sub_prop >= 0");
     if ((rc = check_ctrl(ctrl))) return rc;
     if (n_dst != 1 && n_dst != 2 && n_dst != 4 && n_dst != 8) return fail(MPC_E_INVALID, "n_dst must be 1, 2, 4 or 8 (got %d)", n_dst);
     for (int d = 0; d < n_dst; ++d)
@@ -999,19 +1115,19 @@ int prop_disc_overlapped(mpc_ctx *ctx, const double *y0, const double *tf, const
                           g_tuning.load(std::memory_order_relaxed) == 0 && stream_wait_value32() != nullptr;
     const double *tab_dev = ctrl->table, *et_dev = ctrl->end_tau_per_sat;
     if (!windowed) {
-        if ((rc = prop_device(y0, tf, p_prop, ctrl, tab_dev, et_dev, n_sats, K, n_sub_prop, x, u, status_prop, st))) return rc;
+        if ((rc = prop_device(y0, tf, p_prop, ctrl, tab_dev, et_dev, n_sats, K, mode_of(n_sub_prop), x, u, status_prop, st))) return rc;
         return disc_device(x, u, tf, p_disc, n_sats, K, n_sub_disc, dst, n_dst, out_pitch, out_offset, status_disc, st);
     }
     if ((rc = ensure_overlap(ctx))) return rc;
     const int seg = (K - 1 + nw - 1) / nw;         // intervals per window
     nw = (K - 1 + seg - 1) / seg;
-    const unsigned int n_warps = (unsigned int)((n_sats + 31) / 32);
+    unsigned int gate = 0;   // value of progress[b] that opens window b
     CUDA_TRY(cudaMemsetAsync(ctx->d_progress, 0, kMaxWindows * sizeof(unsigned int), st));
     CUDA_TRY(cudaEventRecord(ctx->ev_ov[0], st));
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_prop, ctx->ev_ov[0], 0));
     for (cudaStream_t w : ctx->s_win) CUDA_TRY(cudaStreamWaitEvent(w, ctx->ev_ov[0], 0));
-    if ((rc = prop_device(y0, tf, p_prop, ctrl, tab_dev, et_dev, n_sats, K, n_sub_prop, x, u, status_prop, ctx->s_prop,
-                          ctx->d_progress, seg)))
+    if ((rc = prop_device(y0, tf, p_prop, ctrl, tab_dev, et_dev, n_sats, K, mode_of(n_sub_prop), x, u, status_prop, ctx->s_prop,
+                          ctx->d_progress, seg, &gate)))
         return rc;
     CUDA_TRY(cudaEventRecord(ctx->ev_ov[1], ctx->s_prop));   // propagation done: join of the caller's stream (and the gate of last resort)
     const mpc::DiscParams P = disc_params(p_disc);
@@ -1028,9 +1144,9 @@ int prop_disc_overlapped(mpc_ctx *ctx, const double *y0, const double *tf, const
             tab.first_wave_ctas = ctx->sm_count * 2;
             tab.stagger_cycles = (long long)n_sub_disc * 4940LL;
         }
-        // gate: progress[b] == number of warps.  Should the driver refuse the memory operation, the window waits for the
+        // gate: progress[b] == number of warps (RK4 propagator) / satellites (RK45 propagator).  Should the driver refuse the memory operation, the window waits for the
         // whole propagation instead (an ordinary event): coarser, still correct, nothing is left half enqueued.
-        if (stream_wait_value32()((CUstream)sw, (CUdeviceptr)(uintptr_t)(ctx->d_progress + b), n_warps,
+        if (stream_wait_value32()((CUstream)sw, (CUdeviceptr)(uintptr_t)(ctx->d_progress + b), gate,
                                   CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
             CUDA_TRY(cudaStreamWaitEvent(sw, ctx->ev_ov[1], 0));
         rc = p_disc->include_j2

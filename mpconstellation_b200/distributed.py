@@ -129,12 +129,23 @@ class FusedGather:
         self.s0, self.s1 = shard_range(n_sats_total, self.rank, self.world)
         self.status = torch.zeros(max(1, (self.s1 - self.s0) * (K - 1)), dtype=torch.int32, device=self.device)
 
-    def discretize(self, x, u, tf, const, include_J2=False, n_sub=100, barrier=True):
+    def _pre_barrier(self, pre_barrier):
+        """The kernel of this rank stores into EVERY rank's buffer.  The barrier after the kernel only says "all results
+        of this step have landed"; nothing there stops a fast rank from starting the next step and overwriting its column
+        range in a peer's buffer while that peer is still reading the previous result.  So every step opens with a
+        barrier as well, enqueued on the current stream behind whatever the caller enqueued there to consume the
+        previous result: "every rank is done with step n" before any store of step n+1 (a few microseconds).  A caller
+        that synchronises all ranks itself between consuming and the next step may pass pre_barrier=False."""
+        if pre_barrier and self.world > 1:
+            self.handle.barrier(channel=1)
+
+    def discretize(self, x, u, tf, const, include_J2=False, n_sub=100, barrier=True, pre_barrier=True):
         """x [n_local,7,K], u [n_local,3,K], tf [n_local] (this rank's shard_range block, CUDA float64).  Enqueues
         the kernel on the current stream; with barrier=True also the cross-rank barrier after which every
-        rank's `self.buf` holds all N satellites."""
+        rank's `self.buf` holds all N satellites (pre_barrier: see _pre_barrier)."""
         from . import batch
         assert x.shape[0] == self.s1 - self.s0 and x.shape[2] == self.K
+        self._pre_barrier(pre_barrier)
         tuned = self.mode not in ("push", "pushk") and (self.skip_const or self.stagger > 1)
         if tuned:
             _lib.check(_lib.lib().mpc_set_gather_tuning((2 if self.mode == "multicast" else 1) if self.skip_const else 0,
@@ -149,7 +160,7 @@ class FusedGather:
         return self.buf
 
     def propagate_discretize(self, y0, tf, controller, const, include_J2=False, n_sub_prop=None, n_sub=100, y=None,
-                             u_out=None, status_prop=None, barrier=True, n_windows=0):
+                             u_out=None, status_prop=None, barrier=True, n_windows=0, pre_barrier=True):
         """One SCP linearization pass of this rank's shard with the all-gather fused in AND the propagation hidden
         behind the discretization (`mpc_propagate_discretize_multi`): y0 [n_local,7], tf [n_local] CUDA float64.
         Modes "unicast" and "multicast" at world <= 2; the push modes and larger worlds keep the two-kernel sequence:
@@ -163,8 +174,10 @@ class FusedGather:
             y, u_out, status_prop = batch.propagate_batch_device(y0, tf, controller, const, include_drag=False,
                                                                  include_J2=include_J2, T=self.K, n_sub=n_sub_prop,
                                                                  y=y, u_out=u_out, status=status_prop)
-            self.discretize(y, u_out, tf, const, include_J2=include_J2, n_sub=n_sub, barrier=barrier)
+            self.discretize(y, u_out, tf, const, include_J2=include_J2, n_sub=n_sub, barrier=barrier,
+                            pre_barrier=pre_barrier)
             return self.buf, y, u_out, status_prop
+        self._pre_barrier(pre_barrier)
         tuned = self.skip_const or self.stagger > 1
         if tuned:
             _lib.check(_lib.lib().mpc_set_gather_tuning((2 if self.mode == "multicast" else 1) if self.skip_const else 0,

@@ -11,7 +11,7 @@ from types import SimpleNamespace
 import numpy as np
 
 from . import batch
-from .control import Controller, spec_from
+from .control import Controller, spec_from, stateless
 from .model import C_D, RHO_ATMO, R_EARTH, SatelliteScale
 
 
@@ -29,7 +29,10 @@ class Simulator:
         self.include_J2 = include_J2
         self.scale = SatelliteScale() if scale is None else scale
         self.verbose = verbose
-        self.max_time_step = 0.001   # simulator.py:186; sets the RK4 sub-steps between samples
+        self.max_time_step = 0.001   # simulator.py:186: solve_ivp's max_step
+        # "rk45": the reference's integrator (scipy RK45 + step-size controller + dense-output samples, simulator.py:185-187)
+        # replayed step for step on the device; "rk4": fixed-step RK4, ceil(1/(max_time_step (T-1))) steps per sample
+        self.integrator = "rk45"
         self.device = 0
 
     # -- batched core --------------------------------------------------------------------------------
@@ -37,9 +40,14 @@ class Simulator:
         const = self.scale.get_normalized_constants()
         y0 = np.stack([self.scale.normalize_state(s.get_state_vector()) for s in sats]) if sats else np.zeros((0, 7))
         T = int(self.eval_points)
+        if self.integrator == "rk45":
+            mode = dict(n_sub=None, rk45=dict(max_step=self.max_time_step))
+        elif self.integrator == "rk4":
+            mode = dict(n_sub=batch.default_n_sub(T, self.max_time_step))
+        else:
+            raise ValueError(f"unknown integrator {self.integrator!r} (rk45 | rk4)")
         y, u, t, _ = batch.propagate_batch(y0, tf, controller, const, include_drag=self.include_drag,
-                                           include_J2=self.include_J2, T=T,
-                                           n_sub=batch.default_n_sub(T, self.max_time_step), device=self.device)
+                                           include_J2=self.include_J2, T=T, device=self.device, **mode)
         return y, u, t
 
     def run(self, tf=10):
@@ -52,23 +60,35 @@ class Simulator:
         return self.sim_data, self.sim_time
 
     def run_segment(self, tf=1):
-        """ref: simulator.py:50-77.  controller.update() is called once per satellite, as the reference does
-        (:60); all satellites are then propagated together."""
+        """ref: simulator.py:50-77.  The reference goes satellite by satellite: controller.update(), propagate, write the
+        final state back to the satellite.  With a controller whose update() is the base class's no-op that order cannot
+        matter and all satellites are propagated in ONE launch; a controller that re-plans in update() (the reference's
+        OptimalController reads the satellite state and shortens its horizon there, control.py:170-235) is served in the
+        reference's order, one satellite per launch, so that every satellite flies the plan made for it."""
         self.eval_points = int(self.base_res * tf)
-        for _ in self.sats:
+        if stateless(self.controller):
+            for _ in self.sats:
+                self.controller.update()
+            y, u, t = self._propagate(self.sats, tf, self.controller)
+            for i, sat in enumerate(self.sats):
+                self._append_segment(sat, y[i], u[i], t, tf)
+            return
+        for sat in self.sats:
             self.controller.update()
-        y, u, t = self._propagate(self.sats, tf, self.controller)
-        for i, sat in enumerate(self.sats):
-            sat.update_state_vector(self.scale.redim_state(y[i][:, -1]))
-            if sat.id in self.sim_data and sat.id in self.sim_time:
-                time = t + self.sim_time.get(sat.id, [0])[-1] * tf + 0.0000001      # simulator.py:70
-                self.sim_data[sat.id] = np.concatenate([self.sim_data[sat.id], y[i]], axis=1)
-                self.sim_time[sat.id] = np.concatenate([self.sim_time[sat.id], time])
-                self.sim_u[sat.id] = np.concatenate([self.sim_u[sat.id], u[i]], axis=1)
-            else:
-                self.sim_data[sat.id] = np.array(y[i])
-                self.sim_time[sat.id] = t.copy()
-                self.sim_u[sat.id] = np.array(u[i])
+            y, u, t = self._propagate([sat], tf, spec_from(self.controller))
+            self._append_segment(sat, y[0], u[0], t, tf)
+
+    def _append_segment(self, sat, y, u, t, tf):
+        sat.update_state_vector(self.scale.redim_state(y[:, -1]))
+        if sat.id in self.sim_data and sat.id in self.sim_time:
+            time = t + self.sim_time.get(sat.id, [0])[-1] * tf + 0.0000001      # simulator.py:70
+            self.sim_data[sat.id] = np.concatenate([self.sim_data[sat.id], y], axis=1)
+            self.sim_time[sat.id] = np.concatenate([self.sim_time[sat.id], time])
+            self.sim_u[sat.id] = np.concatenate([self.sim_u[sat.id], u], axis=1)
+        else:
+            self.sim_data[sat.id] = np.array(y)
+            self.sim_time[sat.id] = t.copy()
+            self.sim_u[sat.id] = np.array(u)
 
     def run_segments(self, tf=1, num_segments=1):
         """ref: simulator.py:79-94."""
@@ -81,7 +101,7 @@ class Simulator:
     def get_trajectory_ODE(self, sat, tf, u_func):
         """ref: simulator.py:164-189.  Returns an object with .y (7,T) and .t (T,) like solve_ivp's."""
         y, u, t = self._propagate([sat], tf, spec_from(u_func))
-        return SimpleNamespace(y=y[0], t=t, u=u[0], success=True, status=0, message="fixed-step RK4 on sm_100a")
+        return SimpleNamespace(y=y[0], t=t, u=u[0], success=True, status=0, message=f"{self.integrator} on sm_100a")
 
     def save_to_csv(self, suffix="", redimensionalize=True, directory="."):
         """ref: simulator.py:192-201 -- one `trajectory_<date>_<sat.id><suffix>.csv` per satellite, rows = samples,

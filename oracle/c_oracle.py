@@ -46,6 +46,11 @@ def lib():
         _lib.orc_discretize_rk45.argtypes = [dp, dp, dp, ctypes.POINTER(OrcParams), ctypes.c_int, ctypes.c_int,
                                              ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, ip, ip, ctypes.c_int]
         _lib.orc_discretize_rk45.restype = ctypes.c_int
+        _lib.orc_propagate_rk45.argtypes = [dp, dp, ctypes.POINTER(OrcParams), ctypes.c_int, dp, dp, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, dp, ip, ip, ip,
+                                            ctypes.c_int]
+        _lib.orc_propagate_rk45.restype = ctypes.c_int
         _lib.orc_max_threads.restype = ctypes.c_int
     return _lib
 
@@ -134,3 +139,34 @@ def propagate_batch(y0, tf, const, kind=CTRL_ZERO, cparams=(0.0, 0.0, 0.0), tabl
                             float(end_tau), N, T, n_sub, _dp(y), _dp(uo),
                             status.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), nthreads)
     return y, uo, status
+
+
+def propagate_batch_rk45(y0, tf, const, kind=CTRL_ZERO, cparams=(0.0, 0.0, 0.0), table=None, end_tau=1.0,
+                         include_drag=True, include_J2=True, T=100, rtol=1e-3, atol=1e-6, max_step=1e-3, nthreads=0):
+    """The reference's own integrator (simulator.py:185-187: solve_ivp RK45, max_step=0.001, t_eval=linspace(0,1,T)),
+    restated in C: step-size controller + dense output.  y0 [N,7] -> (y[N,7,T], u[N,3,T], status[N], n_steps[N],
+    n_rejected[N]).  end_tau: scalar or [N]."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    N = y0.shape[0]
+    tf = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    cp = np.ascontiguousarray(np.resize(np.asarray(cparams, dtype=np.float64), 3))
+    Ku, per_sat = 0, 0
+    if table is not None:
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        Ku = table.shape[-1]
+        per_sat = int(table.ndim == 3)
+    et_arr = None
+    if np.ndim(end_tau) != 0:
+        et_arr = np.ascontiguousarray(end_tau, dtype=np.float64)
+        end_tau = float(et_arr[0])
+    y = np.zeros((N, 7, T))
+    uo = np.zeros((N, 3, T))
+    status = np.zeros(N, dtype=np.int32)
+    steps = np.zeros(N, dtype=np.int32)
+    rej = np.zeros(N, dtype=np.int32)
+    p = make_params(const, include_J2, include_drag)
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib().orc_propagate_rk45(_dp(y0), _dp(tf), ctypes.byref(p), kind, _dp(cp), _dp(table), Ku, per_sat,
+                             float(end_tau), _dp(et_arr), N, T, rtol, atol, max_step, _dp(y), _dp(uo),
+                             status.ctypes.data_as(ip), steps.ctypes.data_as(ip), rej.ctypes.data_as(ip), nthreads)
+    return y, uo, status, steps, rej

@@ -726,6 +726,172 @@ int orc_propagate_rk4(const double *y0, const double *tf, const orc_params *p, i
     return bad;
 }
 
+/*
+ * Propagation as the reference integrates it (simulator.py:185-187):
+ *     solve_ivp(satellite_dynamics, [0, 1], y0, t_eval=linspace(0, 1, T), max_step=0.001)        (RK45, rtol 1e-3, atol 1e-6)
+ * i.e. scipy's Dormand-Prince 5(4) with its step-size controller (integrate/_ivp/rk.py RungeKutta._step_impl, rk_step;
+ * common.py select_initial_step, norm) and the samples read off the 4th-order dense output of the step that covers them
+ * (rk.py RkDenseOutput._call_impl, RK45.P; ivp.py: t_eval points with t_old < t_eval <= t, searchsorted side='right').
+ * scipy (1.18.1 in this image) is a third-party dependency the reference neither vendors nor pins; this restates its
+ * published algorithm, statement for statement, on the 7-vector.  n_steps / n_rej [N] (may be NULL): accepted / rejected
+ * step counts (nfev = 2 + 6 (n_steps + n_rej)).
+ */
+static const double DP_P[7][4] = {
+    {1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
+    {0.0, 0.0, 0.0, 0.0},
+    {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
+    {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
+    {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
+    {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
+    {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
+
+static double rms7(const double *v)
+{
+    double s = 0.0;
+    for (int i = 0; i < 7; ++i) s += v[i] * v[i];
+    return sqrt(s) / sqrt(7.0);
+}
+
+int orc_propagate_rk45(const double *y0, const double *tf, const orc_params *p, int kind, const double *cp,
+                       const double *ctrl_tab, int Ku, int tab_per_sat, double end_tau, const double *end_tau_arr, int N,
+                       int T, double rtol, double atol, double max_step, double *y_out, double *u_out, int *status,
+                       int *n_steps, int *n_rej, int nthreads)
+{
+    int bad = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int s = 0; s < N; ++s) {
+        const double *tab = ctrl_tab ? ctrl_tab + (tab_per_sat ? (long)s * 3 * Ku : 0) : 0;
+        const double et = end_tau_arr ? end_tau_arr[s] : end_tau;
+        const double tfs = tf[s], t_bound = 1.0;
+        double y[7], f[7], K[7][7], ynew[7], fnew[7], tmp[7], sc[7], us[3];
+        int st = 0, steps = 0, rej = 0;
+        for (int c = 0; c < 7; ++c) y[c] = y0[s * 7 + c];
+        double t = 0.0;
+        /* np.linspace(0, 1, T): arange(T) * step, last point exactly 1 */
+        const double lstep = (T > 1) ? 1.0 / (double)(T - 1) : 0.0;
+#define TEVAL(j) (((j) == T - 1 && T > 1) ? 1.0 : (double)(j) * lstep)
+        int ti = 0;
+        st |= prop_rhs(y, t, tfs, p, kind, cp, tab, Ku, et, f);
+        double h_abs = 0.0;
+        if (!st) { /* select_initial_step */
+            double interval_length = fabs(t_bound - t);
+            for (int i = 0; i < 7; ++i) sc[i] = atol + fabs(y[i]) * rtol;
+            for (int i = 0; i < 7; ++i) tmp[i] = y[i] / sc[i];
+            double d0 = rms7(tmp);
+            for (int i = 0; i < 7; ++i) tmp[i] = f[i] / sc[i];
+            double d1 = rms7(tmp);
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            if (h0 > interval_length) h0 = interval_length;
+            for (int i = 0; i < 7; ++i) ynew[i] = y[i] + h0 * f[i];
+            st |= prop_rhs(ynew, t + h0, tfs, p, kind, cp, tab, Ku, et, fnew);
+            for (int i = 0; i < 7; ++i) tmp[i] = (fnew[i] - f[i]) / sc[i];
+            double d2 = rms7(tmp) / h0;
+            double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+            h_abs = fmin(fmin(100 * h0, h1), fmin(interval_length, max_step));
+        }
+        while (!st && t < t_bound) {
+            double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
+            if (h_abs > max_step) h_abs = max_step;
+            else if (h_abs < min_step) h_abs = min_step;
+            int accepted = 0, rejected = 0;
+            double t_new = t, h = 0.0;
+            while (!accepted && !st) {
+                if (h_abs < min_step) {
+                    st = 4;
+                    break;
+                }
+                h = h_abs;
+                t_new = t + h;
+                if (t_new - t_bound > 0) t_new = t_bound;
+                h = t_new - t;
+                h_abs = fabs(h);
+                memcpy(K[0], f, sizeof f);
+                for (int q = 1; q < 6 && !st; ++q) {
+                    for (int i = 0; i < 7; ++i) {
+                        double dy = 0.0;
+                        for (int l = 0; l < q; ++l) dy += K[l][i] * DP_A[q][l];
+                        tmp[i] = y[i] + dy * h;
+                    }
+                    st |= prop_rhs(tmp, t + DP_C[q] * h, tfs, p, kind, cp, tab, Ku, et, K[q]);
+                }
+                if (st) break;
+                for (int i = 0; i < 7; ++i) {
+                    double d = 0.0;
+                    for (int l = 0; l < 6; ++l) d += K[l][i] * DP_B[l];
+                    ynew[i] = y[i] + h * d;
+                }
+                st |= prop_rhs(ynew, t + h, tfs, p, kind, cp, tab, Ku, et, fnew);
+                if (st) break;
+                memcpy(K[6], fnew, sizeof fnew);
+                for (int i = 0; i < 7; ++i) {
+                    double e = 0.0;
+                    for (int l = 0; l < 7; ++l) e += K[l][i] * DP_E[l];
+                    tmp[i] = e * h / (atol + fmax(fabs(y[i]), fabs(ynew[i])) * rtol);
+                }
+                double err = rms7(tmp);
+                if (err < 1.0) {
+                    double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+                    if (rejected && factor > 1.0) factor = 1.0;
+                    h_abs *= factor;
+                    accepted = 1;
+                } else {
+                    h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+                    rejected = 1;
+                    ++rej;
+                }
+            }
+            if (st) break;
+            ++steps;
+            /* samples with t_eval <= t_new, off the dense output of this step */
+            if (ti < T && TEVAL(ti) <= t_new) {
+                double Q[7][4];
+                for (int i = 0; i < 7; ++i)
+                    for (int m = 0; m < 4; ++m) {
+                        double q = 0.0;
+                        for (int l = 0; l < 7; ++l) q += K[l][i] * DP_P[l][m];
+                        Q[i][m] = q;
+                    }
+                while (ti < T && TEVAL(ti) <= t_new) {
+                    double te = TEVAL(ti), xx = (te - t) / h, pw[4], ys[7];
+                    pw[0] = xx;
+                    for (int m = 1; m < 4; ++m) pw[m] = pw[m - 1] * xx;
+                    for (int i = 0; i < 7; ++i) {
+                        double q = 0.0;
+                        for (int m = 0; m < 4; ++m) q += Q[i][m] * pw[m];
+                        ys[i] = h * q + y[i];
+                        y_out[((long)s * 7 + i) * T + ti] = ys[i];
+                    }
+                    if (u_out) { /* extract_uk, linearize_discretize.py:393-411 */
+                        ctrl_eval(kind, cp, tab, Ku, et, ys, te, us);
+                        for (int c = 0; c < 3; ++c) u_out[((long)s * 3 + c) * T + ti] = us[c];
+                    }
+                    ++ti;
+                }
+            }
+            memcpy(y, ynew, sizeof y);
+            memcpy(f, fnew, sizeof f);
+            t = t_new;
+            if (steps > 50000000) st = 4;
+        }
+#undef TEVAL
+        if (st) { /* the reference raises: nothing is returned for this satellite */
+            for (int j = ti; j < T; ++j) {
+                for (int i = 0; i < 7; ++i) y_out[((long)s * 7 + i) * T + j] = NAN;
+                if (u_out)
+                    for (int c = 0; c < 3; ++c) u_out[((long)s * 3 + c) * T + j] = NAN;
+            }
+        }
+        if (status) status[s] = st;
+        if (n_steps) n_steps[s] = steps;
+        if (n_rej) n_rej[s] = rej;
+        bad += (st != 0);
+    }
+    return bad;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -22,7 +22,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "mpconstellation_b20
 BUILD = os.path.join(HERE, "_build")
 SO = os.path.join(BUILD, "libmpc_hostk.so")
 SOURCES = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_pair_kernel.cuh",
-           "discretize_drag_kernel.cuh", "propagate_kernel.cuh", "constraint_terms_kernel.cuh"]
+           "discretize_drag_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "constraint_terms_kernel.cuh"]
 _SEEDS = [(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rcp_seed(a);"),
           (r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rsqrt_seed(a);")]
 
@@ -131,6 +131,34 @@ def propagate(y0, tf, const, kind=0, thrust=(0.0, 0.0, 0.0), table=None, end_tau
                           int(tab is not None and tab.ndim == 3), ctypes.c_double(end_tau), N, int(T), int(n_sub), _p(y), _p(uo), _p(status), _p(progress),
                           int(seg_len))
     return y, uo, status, progress
+
+
+def propagate_rk45(y0, tf, const, kind=0, thrust=(0.0, 0.0, 0.0), table=None, end_tau=1.0, include_drag=False,
+                   include_J2=False, T=100, rtol=1e-3, atol=1e-6, max_step=1e-3, spec=True, lpw=32, c_d=2.5,
+                   rho_atm=9.983e-13, seg_len=0):
+    """propagate_rk45_kernel (the reference's solve_ivp call, replayed) on host arrays y0 [N,7] -> y [N,7,T], u [N,3,T],
+    status [N], n_steps [N] (attempted steps), progress words (seg_len > 0).  end_tau: scalar or [N]."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    N = y0.shape[0]
+    tfv = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    y = np.full((N, 7, T), np.nan)
+    uo = np.full((N, 3, T), np.nan)
+    status = np.full(N, -1, dtype=np.int32)
+    steps = np.zeros(N, dtype=np.int32)
+    progress = np.zeros(64, dtype=np.uint32) if seg_len > 0 else None
+    th = np.ascontiguousarray(np.asarray(thrust, dtype=np.float64))
+    tab = None if table is None else np.ascontiguousarray(table, dtype=np.float64)
+    et_arr = None
+    if np.ndim(end_tau) != 0:
+        et_arr = np.ascontiguousarray(end_tau, dtype=np.float64)
+        end_tau = float(et_arr[0])
+    c8 = _const8(const)
+    D = ctypes.c_double
+    lib().hostk_propagate_rk45(_p(y0), _p(tfv), _p(c8), int(include_J2), int(include_drag), D(c_d), D(rho_atm), int(kind),
+                               _p(th), _p(tab), 0 if tab is None else tab.shape[-1], int(tab is not None and tab.ndim == 3),
+                               D(end_tau), _p(et_arr), N, int(T), D(rtol), D(atol), D(max_step), int(spec), int(lpw),
+                               _p(y), _p(uo), _p(status), _p(steps), _p(progress), int(seg_len))
+    return y, uo, status, steps, progress
 
 
 def discretize_drag(x, u, tf, const, drag, include_J2=False, n_sub=100, adaptive=None, c_d=2.5, rho_atm=9.983e-13):

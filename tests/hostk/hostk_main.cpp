@@ -9,6 +9,7 @@
 #include "discretize_adaptive_kernel.cuh"
 #include "discretize_pair_kernel.cuh"
 #include "propagate_kernel.cuh"
+#include "propagate_rk45_kernel.cuh"
 #include "discretize_drag_kernel.cuh"
 #include "constraint_terms_kernel.cuh"
 
@@ -130,6 +131,56 @@ extern "C" int hostk_propagate(const double *y0, const double *tf, const double 
         case 1: HK_PROP_K(1); break;
         case 2: HK_PROP_K(2); break;
         default: HK_PROP_K(3); break;
+    }
+    return 0;
+}
+
+// the RK45 replay of the reference's integrator (propagate_rk45_kernel); spec = 1: with the speculative first stage
+extern "C" int hostk_propagate_rk45(const double *y0, const double *tf, const double *const8, int include_j2, int include_drag,
+                                    double c_d, double rho_atm, int kind, const double *thrust, const double *table,
+                                    int table_len, int table_per_sat, double end_tau, const double *end_tau_arr, int n_sats,
+                                    int T, double rtol, double atol, double max_step, int spec, int lpw, double *y,
+                                    double *u_out, int32_t *status, int32_t *n_steps, unsigned *progress, int seg_len)
+{
+    mpc::PropParams PP;
+    PP.mu = const8[0];
+    PP.kj2 = 1.5 * const8[2] * const8[0] * const8[1] * const8[1];
+    PP.inv_ve = 1.0 / (const8[3] * const8[4]);
+    PP.drag_k = include_drag ? 0.5 * c_d * const8[5] * (rho_atm / const8[7]) : 0.0;
+    PP.include_j2 = include_j2;
+    PP.include_drag = include_drag;
+    mpc::CtrlParams C{};
+    C.kind = kind;
+    C.table_len = table_len;
+    C.table_per_sat = table_per_sat;
+    C.t0 = thrust[0];
+    C.t1 = thrust[1];
+    C.t2 = thrust[2];
+    C.end_tau = end_tau;
+    C.table = kind == 3 ? table : nullptr;
+    C.end_tau_arr = kind == 3 ? end_tau_arr : nullptr;
+    const mpc::Rk45Opts O{rtol, atol, max_step};
+    const long long n_threads = (long long)((n_sats + lpw - 1) / lpw) * 32;   // one warp per lpw satellites
+#define HK_R45(KIND, DRAG, J2)                                                                                               \
+    run_grid(n_threads, [&] {                                                                                                \
+        if (spec) mpc::propagate_rk45_kernel<kBlock, KIND, DRAG, J2, true>(y0, tf, PP, C, O, n_sats, T, lpw, y, u_out, status, n_steps, progress, seg_len); \
+        else mpc::propagate_rk45_kernel<kBlock, KIND, DRAG, J2, false>(y0, tf, PP, C, O, n_sats, T, lpw, y, u_out, status, n_steps, progress, seg_len);    \
+    })
+#define HK_R45_K(KIND)                                        \
+    do {                                                      \
+        if (include_drag) {                                   \
+            if (include_j2) HK_R45(KIND, true, true);         \
+            else HK_R45(KIND, true, false);                   \
+        } else {                                              \
+            if (include_j2) HK_R45(KIND, false, true);        \
+            else HK_R45(KIND, false, false);                  \
+        }                                                     \
+    } while (0)
+    switch (kind) {
+        case 0: HK_R45_K(0); break;
+        case 1: HK_R45_K(1); break;
+        case 2: HK_R45_K(2); break;
+        default: HK_R45_K(3); break;
     }
     return 0;
 }

@@ -37,6 +37,16 @@ static inline unsigned atomicAdd(unsigned *p, unsigned v)
     *p = o + v;
     return o;
 }
+static inline unsigned __activemask() { return 1u << (threadIdx.x & 31); }   // the threads run one after the other
+static inline unsigned __match_any_sync(unsigned m, int) { return m; }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline long long __double_as_longlong(double d)
+{
+    long long v;
+    memcpy(&v, &d, sizeof v);
+    return v;
+}
 static inline double __longlong_as_double(long long v)
 {
     double d;

@@ -113,6 +113,70 @@ def test_reference_style_controller_objects_are_recognised():
     assert spec_from(OptimalLike()).end_tau == 2.0
 
 
+def test_controllers_with_their_own_law_are_refused_not_flown_as_their_parent():
+    """a subclass may override get_u_func: flying its parent's law would be silently wrong"""
+    class PD(M.ConstantThrustController):
+        def get_u_func(self, sat_id=None):
+            return lambda x, tau: -0.1 * np.asarray(x[3:6])
+
+    with pytest.raises(NotImplementedError):
+        spec_from(PD())
+    with pytest.raises(NotImplementedError):
+        spec_from(PD().get_u_func())
+
+    class Tuned(M.ConstantThrustController):              # same law, only the constructor differs: still fine
+        def __init__(self):
+            super().__init__(thrust=np.array([0.0, 0.2, 0.0]))
+
+    assert spec_from(Tuned()).thrust == (0.0, 0.2, 0.0)
+
+    class ConstantThrustController:                      # reference-style base ...
+        thrust = np.array([0., 0., 0.1])
+
+    class Feedback(ConstantThrustController):            # ... and a subclass of it: another name, another law
+        pass
+
+    with pytest.raises(NotImplementedError):
+        spec_from(Feedback())
+
+    class OptimalController:                             # the reference's raises AttributeError before update()
+        pass
+
+    with pytest.raises(AttributeError):
+        spec_from(OptimalController())
+
+
+def test_run_segment_serves_replanning_controllers_in_the_reference_order(monkeypatch):
+    """simulator.py:58-64: update(), propagate, write back -- per satellite.  A controller that re-plans in update()
+    must see that order (one launch per satellite); a stateless one is propagated in a single batched launch."""
+    calls = []
+
+    def fake_propagate(self, sats, tf, controller):
+        calls.append((len(sats), spec_from(controller).thrust))
+        T = int(self.eval_points)
+        y = np.zeros((len(sats), 7, T))
+        y[:, 6] = 1.0
+        return y, np.zeros((len(sats), 3, T)), np.linspace(0, 1, T)
+
+    monkeypatch.setattr(M.Simulator, "_propagate", fake_propagate)
+
+    class Replanning(M.ConstantThrustController):
+        n = 0
+
+        def update(self):
+            self.n += 1
+            self.thrust = np.array([0.1 * self.n, 0.0, 0.0])
+
+    sats = [M.Satellite() for _ in range(3)]
+    sim = M.Simulator(sats=sats, controller=Replanning(), base_res=10)
+    sim.run_segment(tf=1)
+    assert [c[0] for c in calls] == [1, 1, 1] and np.allclose([c[1][0] for c in calls], [0.1, 0.2, 0.3])
+    calls.clear()
+    sim = M.Simulator(sats=sats, controller=M.ConstantThrustController(thrust=np.array([0.3, 0, 0])), base_res=10)
+    sim.run_segments(tf=2, num_segments=2)
+    assert [c[0] for c in calls] == [3, 3] and sim.sim_data[sats[0].id].shape == (7, 20)
+
+
 def test_discretizer_option_errors_mirror_reference():
     const = M.SatelliteScale().get_normalized_constants()
     f = M.Simulator.satellite_dynamics

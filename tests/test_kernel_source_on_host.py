@@ -145,14 +145,95 @@ def test_propagate_progress_words_sequence_controller_and_mass_failure(const):
     assert np.array_equal(sr, st) and rel_err(y[ok], yr[ok]) < 1e-11 and rel_err(u[ok], ur[ok]) < 1e-10
 
 
+# ---- propagate_rk45_kernel: the reference's solve_ivp call replayed (simulator.py:185-187) -------------------------------
+_RK45 = {"p0": dict(kind=0, T=500, include_drag=True, include_J2=True), "p1": dict(kind=2, thrust=(0.5, 0, 0), T=200),
+         "p2": dict(kind=1, T=300, include_drag=True, include_J2=True),
+         "p4": dict(kind=2, thrust=(0.1, 0, 0), T=200, include_drag=True, include_J2=True),
+         "p5": dict(kind=3, end_tau=0.75, T=120)}
+TOL_RK45 = 2e-12     # the same algorithm step for step: rounding only (observed <= 4e-13 over 5 orbits)
+
+
+@pytest.mark.parametrize("spec", [True, False])
+@pytest.mark.parametrize("case", sorted(_RK45))
+def test_rk45_propagate_kernel_reproduces_reference_trajectories(gold_prop, const, case, spec):
+    """every propagation fixture of the unmodified reference, the thrust cut-off inside the run (p5) included, to
+    rounding; 1000 steps like scipy (nfev 6002); the speculative-first-stage build is the same arithmetic"""
+    gp = gold_prop
+    y0 = O.normalize_state(gp["x0_dim"], O.scale_factors(gp["x0_dim"]))
+    kw = dict(_RK45[case])
+    if case == "p2":
+        kw["thrust"] = tuple(gp["p2_thrust"])
+    if case == "p5":
+        kw["table"] = gp["p5_u_tab"]
+    y, u, st, steps, _ = hostk.propagate_rk45(y0[None], float(gp[case + "_tf"]), const, spec=spec, **kw)
+    assert st[0] == 0 and steps[0] == 1000
+    assert rel_err(y[0], gp[case + "_y"]) < TOL_RK45
+    if case in ("p1", "p5"):
+        assert rel_err(u[0], gp[case + "_u"]) < TOL_RK45
+
+
+def test_rk45_propagate_kernel_three_sats_lanes_per_warp_and_progress(gold_prop):
+    gp = gold_prop
+    c3 = O.OracleConstants(*gp["p3_const"])
+    sf = O.scale_factors(gp["p3_y0_dim"][0])
+    y0 = np.stack([O.normalize_state(y, sf) for y in gp["p3_y0_dim"]])
+    ref = None
+    for lpw in (32, 2, 1):
+        y, u, st, steps, prog = hostk.propagate_rk45(y0, 5.0, c3, include_drag=True, include_J2=True, T=500, lpw=lpw, seg_len=37)
+        assert st.max() == 0 and rel_err(y, gp["p3_y"]) < TOL_RK45
+        n_win = (499 + 36) // 37
+        assert list(prog[:n_win]) == [3] * n_win and not prog[n_win:].any()     # one count per satellite and window
+        ref = y if ref is None else ref
+        assert np.array_equal(y, ref)                                            # the mapping does not touch the arithmetic
+
+
+def test_rk45_propagate_kernel_step_control_and_failures(const):
+    """step-size control engaged (max_step large: rejections at the thrust cut-off) against the C restatement of
+    scipy: same step counts, same trajectory; per-satellite tables and end_tau; a satellite that runs out of mass is
+    flagged, NaN-filled from the sample it failed at, and still releases every window; a NaN state ends with the
+    step-size underflow scipy would report."""
+    N, T = 9, 64
+    y0, _, _ = synth_batch(N, 2, 1.0, const)
+    rng = np.random.default_rng(11)
+    tab = 0.5 * rng.standard_normal((N, 3, 5))
+    et = 0.2 + 0.8 * rng.random(N)
+    for ms in (1.0, 0.05, 1e-3):
+        yr, ur, sr, steps, rej = C.propagate_batch_rk45(y0, 1.7, const, C.CTRL_SEQUENCE, table=tab, end_tau=et,
+                                                         include_drag=False, include_J2=True, T=T, max_step=ms)
+        for spec in (True, False):
+            y, u, st, n, _ = hostk.propagate_rk45(y0, 1.7, const, kind=3, table=tab, end_tau=et, include_J2=True, T=T,
+                                                  max_step=ms, spec=spec)
+            assert st.max() == 0 and np.array_equal(n, steps + rej)
+            # (free step-size control amplifies rounding: err is a cancelling sum, h follows err^-1/5, and the O(h) error at
+            # the cut-off follows h -- scipy itself and its C restatement differ by 1e-10 there)
+            tol = 1e-9 if ms == 1.0 else TOL_RK45
+            assert rel_err(y, yr) < tol and rel_err(u, ur) < max(tol, 1e-11)
+        assert ms < 1.0 or rej.sum() > 0
+    yb = y0.copy()
+    yb[4, 6] = 2e-3                       # runs out of mass part way
+    yb[7, 1] = np.nan                     # poisoned state
+    big = np.tile(np.array([[3.0], [0.0], [0.0]]), (1, 4))
+    y, u, st, n, prog = hostk.propagate_rk45(yb, 1.0, const, kind=3, table=big, end_tau=1.0, T=T, seg_len=9)
+    assert st[4] == 1 and st[7] == 3 and np.delete(st, [4, 7]).max() == 0
+    assert np.isfinite(y[4, :, 0]).all() and np.isnan(y[4, :, -1]).all() and np.isnan(y[7]).all()
+    assert np.isfinite(np.delete(y, [4, 7], 0)).all()
+    n_win = (T - 1 + 8) // 9
+    assert list(prog[:n_win]) == [N] * n_win
+    _, _, sr, _, _ = C.propagate_batch_rk45(yb, 1.0, const, C.CTRL_SEQUENCE, table=big, end_tau=1.0, include_drag=False,
+                                            include_J2=False, T=T)
+    assert np.array_equal(sr != 0, st != 0)
+
+
 def test_bench_workload_chain_vs_reference():
     """propagate_kernel -> discretize_pair_kernel / discretize_adaptive_kernel on 4 satellites of the benchmark's
     constellation against the unmodified reference's own propagation + discretization (bench_workload.npz)"""
     gb = np.load(os.path.join(GOLDEN, "bench_workload.npz"))
     cb = O.OracleConstants(*gb["const"])
     ks, tf = gb["ks"], float(gb["tf"])
-    y, u, st, _ = hostk.propagate(gb["y0"], tf, cb, kind=2, thrust=(0.5, 0, 0), T=200, n_sub=6)
+    y, u, st, _, _ = hostk.propagate_rk45(gb["y0"], tf, cb, kind=2, thrust=(0.5, 0, 0), T=200)
     assert st.max() == 0
+    for j in range(len(gb["idx"])):       # the replayed integrator: the reference's own trajectory to rounding
+        assert rel_err(y[j], gb[f"s{j}_x"]) < TOL_RK45 and rel_err(u[j], gb[f"s{j}_u"]) < TOL_RK45
     soa, sd = hostk.discretize(y, u, tf, cb)
     soa_d, sd2, _ = hostk.discretize_adaptive(y, u, tf, cb)
     assert sd.max() == 0 and sd2.max() == 0

@@ -185,6 +185,57 @@ def test_c_oracle_sequence_controller(gold_prop, const):
     assert rel_err(y[0], gp["p5_y"]) < 5e-3 and rel_err(u[0], gp["p5_u"]) < 1e-12
 
 
+# ---- the reference's own integrator restated (orc_propagate_rk45: scipy RK45 + controller + dense output) ----------
+_RK45_CASES = {"p0": dict(kind=C.CTRL_ZERO, T=500),
+               "p1": dict(kind=C.CTRL_TANGENTIAL, cparams=(0.5, 0, 0), T=200, include_drag=False, include_J2=False),
+               "p2": dict(kind=C.CTRL_CONSTANT, T=300), "p4": dict(kind=C.CTRL_TANGENTIAL, cparams=(0.1, 0, 0), T=200),
+               "p5": dict(kind=C.CTRL_SEQUENCE, T=120, end_tau=0.75, include_drag=False, include_J2=False)}
+
+
+@pytest.mark.parametrize("case", sorted(_RK45_CASES))
+def test_c_oracle_rk45_propagation_reproduces_the_reference(gold_prop, const, case):
+    """simulator.py:185-187 restated in C against trajectories of the unmodified reference: rounding-level agreement,
+    INCLUDING the thrust cut-off inside the run (p5: SequenceController with end_tau = 0.75, control.py:127-141), and
+    scipy's step count (nfev 6002 = 2 + 6 * 1000 steps, none rejected)."""
+    gp = gold_prop
+    y0, _ = _y0(gp)
+    kw = dict(_RK45_CASES[case])
+    if case == "p2":
+        kw["cparams"] = gp["p2_thrust"]
+    if case == "p5":
+        kw["table"] = gp["p5_u_tab"]
+    y, u, st, steps, rej = C.propagate_batch_rk45(y0[None], float(gp[case + "_tf"]), const, **kw)
+    assert st[0] == 0 and steps[0] == 1000 and rej[0] == 0
+    assert rel_err(y[0], gp[case + "_y"]) < 1e-12
+    if case in ("p1", "p5"):
+        assert rel_err(u[0], gp[case + "_u"]) < 1e-12
+
+
+def test_c_oracle_rk45_three_sats_and_segments(gold_prop):
+    gp = gold_prop
+    c3 = O.OracleConstants(*gp["p3_const"])
+    sf = O.scale_factors(gp["p3_y0_dim"][0])
+    y0 = np.stack([O.normalize_state(y, sf) for y in gp["p3_y0_dim"]])
+    y, _, st, steps, _ = C.propagate_batch_rk45(y0, 5.0, c3, C.CTRL_ZERO, T=500)
+    assert st.max() == 0 and rel_err(y, gp["p3_y"]) < 1e-12
+
+
+def test_c_oracle_rk45_step_control_engages(const):
+    """With the reference's max_step = 0.001 the controller never binds (1000 steps, no rejection).  With a larger
+    max_step it does: steps are rejected at the thrust cut-off and retried exactly as scipy does it (checked against
+    scipy itself through the numpy restatement of the reference, which takes max_step as an argument)."""
+    y0 = np.array([1.0, 0, 0, 0, 6.28, 0.3, 1.0])
+    tab = np.array([[0.5] * 4, [0.15] * 4, [0.0, 3.0, 0.0, 0.0]])
+    n_rej = 0
+    for tf, ms in ((0.5, 1.0), (2.0, 1.0), (2.0, 0.05)):
+        yr, _ = O.propagate(y0, tf, O.ctrl_sequence(tab, 0.37 * tf, tf), const, False, False, 64, max_step=ms)
+        y, u, st, steps, rej = C.propagate_batch_rk45(y0[None], tf, const, C.CTRL_SEQUENCE, table=tab, end_tau=0.37,
+                                                       include_drag=False, include_J2=False, T=64, max_step=ms)
+        assert st[0] == 0 and rel_err(y[0], yr) < 1e-12
+        n_rej += rej[0]
+    assert n_rej >= 4
+
+
 def test_c_oracle_mass_failure_flag(const):
     y0 = np.array([[1.0, 0, 0, 0, 6.28, 0, 1e-3]])
     y, _, st = C.propagate_batch(y0, 5.0, const, C.CTRL_CONSTANT, (5.0, 0, 0), T=50, n_sub=20)
