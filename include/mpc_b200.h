@@ -335,10 +335,8 @@ int64_t mpc_launch_count(void);
 
 /* Experiment knob: 1..6 select an alternative block-size / register-cap build of the one-step-per-node discretization
  * kernel (0 = production; results identical, only occupancy differs; DESIGN.md, tuning table).  7 / 8 switch the
- * two-node integrator steps of the production kernel off / on (results differ by ~1e-12).  9 / 10 switch the COMPACT
- * build of the adaptive (default-mode) kernel on / off: dynamics evaluation and node term as real calls instead of
- * inlined copies (same arithmetic, checked on the host build of the sources; an instruction-fetch experiment that has
- * not been timed on a GPU yet -- off by default).  11 / 12: RK45 propagator without / with the speculative first stage
+ * two-node integrator steps of the production kernel off / on (results differ by ~1e-12).  9 / 10 switch to the
+ * round-1 build of the default-mode (adaptive) kernel and back (same results to rounding; A/B measurements).  11 / 12: RK45 propagator without / with the speculative first stage
  * of the next step (same results).  13: satellites per warp of the RK45 propagator chosen automatically, 14..19: forced
  * to 32, 16, 8, 4, 2, 1 (same results). */
 int mpc_set_tuning(int variant);

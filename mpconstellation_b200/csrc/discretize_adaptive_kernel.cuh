@@ -115,41 +115,7 @@ __device__ __forceinline__ void ad_node(volatile double *sm, int base, const Dis
     node_accumulate_general<BLOCK>(sm, pr, pv, P, st, x, w, w * lam);
 }
 
-// COMPACT build of the kernel (template flag, off by default): the dynamics evaluation (8 call sites) and the node
-// term (2 call sites, each with a fully unrolled 6x6 solve) become real calls instead of inlined copies.  Same
-// arithmetic; the hot region shrinks from ~2600 to ~1400 instructions (scripts/sass_code_size.py), which is what the
-// instruction-fetch stalls of the one-warp-per-scheduler configuration are about (profiles/r01_g).
-template <bool J2, bool GENU, bool DRAG>
-__device__ __noinline__ int ad_eval_outlined(const DiscParams &P, double kf, double ka, const double (&x)[7], double s,
-                                             double tau, const UHold<GENU> &hold, AdStage &o)
-{
-    return ad_eval<J2, GENU, DRAG>(P, kf, ka, x, s, tau, hold, o);
-}
-
-template <int BLOCK, bool DRAG>
-__device__ __noinline__ void ad_node_outlined(volatile double *sm, int base, const DiscParams &P, const double (&x)[7],
-                                              const AdStage &st, double w, double lam)
-{
-    ad_node<BLOCK, DRAG>(sm, base, P, x, st, w, lam);
-}
-
-template <bool COMPACT, bool J2, bool GENU, bool DRAG>
-__device__ __forceinline__ int ad_eval_sel(const DiscParams &P, double kf, double ka, const double (&x)[7], double s,
-                                           double tau, const UHold<GENU> &hold, AdStage &o)
-{
-    if constexpr (COMPACT) return ad_eval_outlined<J2, GENU, DRAG>(P, kf, ka, x, s, tau, hold, o);
-    else return ad_eval<J2, GENU, DRAG>(P, kf, ka, x, s, tau, hold, o);
-}
-
-template <bool COMPACT, int BLOCK, bool DRAG>
-__device__ __forceinline__ void ad_node_sel(volatile double *sm, int base, const DiscParams &P, const double (&x)[7],
-                                            const AdStage &st, double w, double lam)
-{
-    if constexpr (COMPACT) ad_node_outlined<BLOCK, DRAG>(sm, base, P, x, st, w, lam);
-    else ad_node<BLOCK, DRAG>(sm, base, P, x, st, w, lam);
-}
-
-template <bool J2, int BLOCK, int NDST, bool GENU, bool DRAG = false, bool COMPACT = false>
+template <bool J2, int BLOCK, int NDST, bool GENU, bool DRAG = false>
 __global__ void __launch_bounds__(BLOCK)
 discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in,
                            const double *__restrict__ tf_arr, DiscParams P, int n_sats, int K, int Ku, double rtol, double atol,
@@ -185,7 +151,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
     double t = t0;
 
     AdStage st0;
-    bad |= ad_eval_sel<COMPACT, J2, GENU, DRAG>(P, kf, ka, x, 0.0, t0, hold, st0);
+    bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x, 0.0, t0, hold, st0);
     // ---- select_initial_step (common.py); f = tf * k, y0 = [I, x] ------------------------------------------
     double h_abs;
     {
@@ -227,7 +193,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
 #pragma unroll
         for (int i = 0; i < 7; ++i) x1[i] = fma(hs0, st0.k[i], x[i]);
         AdStage stA;
-        bad |= ad_eval_sel<COMPACT, J2, GENU, DRAG>(P, kf, ka, x1, h0 * ilen, t0 + h0, hold, stA);
+        bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x1, h0 * ilen, t0 + h0, hold, stA);
         double d2sq = 0.0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
@@ -305,7 +271,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                     xs_[i] = fma(dy, hs, x[i]);
                 }
                 AdStage sg;
-                bad |= ad_eval_sel<COMPACT, J2, GENU, DRAG>(P, kf, ka, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
+                bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
 #pragma unroll
                 for (int i = 0; i < 7; ++i) kx[s][i] = sg.k[i];
                 ad_store_stage<BLOCK, DRAG>(sm, s, sg);
@@ -319,7 +285,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                 for (int l = 0; l < 6; ++l) dy = fma(kx[l][i], bw[l], dy);
                 xn[i] = fma(hs, dy, x[i]);
             }
-            bad |= ad_eval_sel<COMPACT, J2, GENU, DRAG>(P, kf, ka, xn, (t + h - t0) * ilen, t + h, hold, st6);
+            bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xn, (t + h - t0) * ilen, t + h, hold, st6);
             ad_store_stage<BLOCK, DRAG>(sm, 6, st6);
             double esum = 0.0;
 #pragma unroll
@@ -405,8 +371,8 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
         if (fail) break;
         // ---- accepted: trapezoid panel [t, t_new] (np.trapz, x = sol.t) ------------------------------------------
         const double w = 0.5 * (t_new - t);
-        ad_node_sel<COMPACT, BLOCK, DRAG>(sm, cur, P, x, st0, w, (t - t0) * ilen);
-        ad_node_sel<COMPACT, BLOCK, DRAG>(sm, nxt, P, xn, st6, w, (t_new - t0) * ilen);
+        ad_node<BLOCK, DRAG>(sm, cur, P, x, st0, w, (t - t0) * ilen);
+        ad_node<BLOCK, DRAG>(sm, nxt, P, xn, st6, w, (t_new - t0) * ilen);
         const int tmp = cur;
         cur = nxt;
         nxt = tmp;

@@ -1,0 +1,368 @@
+// discretize_default_kernel.cuh -- the reference's DEFAULT quadrature mode, second build (round 2).
+//
+// Same mathematics as discretize_adaptive_kernel (see its header: scipy's RK45 controller replayed per interval,
+// non-uniform trapezoid rule on the accepted steps, linearize_discretize.py:29-30,49-50,77-80,109), restructured for
+// what limited that kernel (profiles/r01_g: one warp per scheduler because of 52 KiB of shared memory per warp, and a
+// 41 KB hot loop that does not fit the 32 KB instruction cache):
+//
+//   * Phi does not live in shared memory.  The two copies a step needs (the accepted Phi and the candidate of the step
+//     being tried -- a rejected step must not destroy the former) ping-pong between two row blocks of the OUTPUT buffer
+//     itself: rows 0..41 (where A_k ends up anyway) and rows 49..90 (B_kp / B_kn, written only by the epilogue).  The
+//     layout is the SoA one, [row][interval]: every access of a warp is one coalesced 256-byte line, it stays in L2
+//     for the life of the warp, and each entry is read / written once per step.  Shared memory per thread drops from
+//     203 to 119 slots (56 accumulators + 7 stage linearisations of 9), i.e. 7 instead of 4 warps per SM.
+//   * every quadrature node is evaluated ONCE, with its full trapezoid weight (t_{j+1} - t_{j-1})/2, when the step that
+//     leaves it has been accepted (the old build evaluated both ends of every panel: 2 (n-1) instead of n node terms,
+//     each with a 6x6 solve), and the step loop is arranged so that the node term has a single call site;
+//   * the stage states of the 7-vector are formed from running sums with literal tableau coefficients.
+// Results agree with the first build to rounding (the panel sums are associated differently) and with the unmodified
+// reference's default-mode fixtures to <= 1e-10; node counts are identical.
+#pragma once
+#include "discretize_adaptive_kernel.cuh"
+
+namespace mpc {
+
+constexpr int kDfAcc = 56;                        // accumulators (layout of kAccSlots)
+constexpr int kDfSlots = kDfAcc + 7 * 9;          // + G_s (6), d_s (3) of the 7 stages
+constexpr int kDfSlotsDrag = kDfAcc + 7 * 15;     // + V_s (6): drag branch of the linearisation
+constexpr int kDfPhiA = 0, kDfPhiB = 49;          // the two Phi row blocks inside the output buffer
+
+#define SM(e) sm[(e) * BLOCK]
+
+template <int BLOCK, bool DRAG>
+__device__ __forceinline__ void df_store_stage(volatile double *sm, int s, const AdStage &st)
+{
+    const int b = kDfAcc + s * (DRAG ? 15 : 9);
+    SM(b + 0) = st.g.xx;
+    SM(b + 1) = st.g.xy;
+    SM(b + 2) = st.g.xz;
+    SM(b + 3) = st.g.yy;
+    SM(b + 4) = st.g.yz;
+    SM(b + 5) = st.g.zz;
+    SM(b + 6) = st.d[0];
+    SM(b + 7) = st.d[1];
+    SM(b + 8) = st.d[2];
+    if (DRAG) {
+        SM(b + 9) = st.v.xx;
+        SM(b + 10) = st.v.xy;
+        SM(b + 11) = st.v.xz;
+        SM(b + 12) = st.v.yy;
+        SM(b + 13) = st.v.yz;
+        SM(b + 14) = st.v.zz;
+    }
+}
+
+template <bool J2, int BLOCK, bool GENU, bool DRAG>
+__global__ void __launch_bounds__(BLOCK)
+discretize_default_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in,
+                          const double *__restrict__ tf_arr, DiscParams P, int n_sats, int K, int Ku, double rtol, double atol,
+                          double max_step, DstTab dst, long long pitch, long long offset, int32_t *__restrict__ status,
+                          int32_t *__restrict__ n_nodes, double kf = 0.0, double ka = 0.0)
+{
+    constexpr int kStage = DRAG ? 15 : 9;
+    extern __shared__ double acc_smem[];
+    const long long n_int = (long long)n_sats * (K - 1);
+    const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (gid >= n_int) return;
+    volatile double *sm = acc_smem + threadIdx.x;
+    const int sat = (int)(gid / (K - 1));
+    const int k = (int)(gid - (long long)sat * (K - 1));
+    const double tf = tf_arr[sat];
+    const double *xs = x_in + ((long long)sat * 7) * K + k;
+    double x[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) x[c] = xs[(long long)c * K];
+    UHold<GENU> hold;
+    hold.init(u_in, sat, k, K, Ku);
+    // tau = np.linspace(0, 1, K) (:356): start + i*step, last point exactly 1
+    const double step = 1.0 / (double)(K - 1);
+    const double t0 = (double)k * step, t1 = (k + 1 == K - 1) ? 1.0 : (double)(k + 1) * step;
+    const double ilen = 1.0 / (t1 - t0);
+    // this thread's column of the output buffer: Phi scratch blocks at rows kDfPhiA.. and kDfPhiB..
+    double *const col = dst.p[0] + offset + gid;
+    double *cur = col + (long long)kDfPhiA * pitch, *nxt = col + (long long)kDfPhiB * pitch;
+
+#pragma unroll 1
+    for (int e = 0; e < kDfAcc; ++e) SM(e) = 0.0;
+    int bad = 0, fail = 0, nodes = 1;
+    bool first = true;            // Phi(tau_k) = I (:34): not read from memory
+    double t = t0;
+
+    AdStage st0;
+    bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x, 0.0, t0, hold, st0);
+    // ---- select_initial_step (common.py); f = tf * k, y0 = [I, x] ----------------------------------------------
+    double h_abs;
+    {
+        const double interval_length = fabs(t1 - t0);
+        const double s1 = atol + rtol, s0 = atol;
+        double d0sq = 7.0 / (s1 * s1), d1sq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const double sc = atol + fabs(x[i]) * rtol;
+            d0sq += (x[i] / sc) * (x[i] / sc);
+            d1sq += (tf * st0.k[i] / sc) * (tf * st0.k[i] / sc);
+        }
+        const double g[9] = {st0.g.xx, st0.g.xy, st0.g.xz, st0.g.xy, st0.g.yy, st0.g.yz, st0.g.xz, st0.g.yz, st0.g.zz};
+        double v0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, vA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (DRAG) {
+            const double t_[9] = {st0.v.xx, st0.v.xy, st0.v.xz, st0.v.xy, st0.v.yy, st0.v.yz, st0.v.xz, st0.v.yz, st0.v.zz};
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                v0[i] = t_[i];
+                const double sc = (i % 4 == 0) ? s1 : s0;
+                d1sq += (tf * t_[i] / sc) * (tf * t_[i] / sc);
+            }
+        }
+        d1sq += 3.0 * (tf / s0) * (tf / s0);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) d1sq += (tf * g[i] / s0) * (tf * g[i] / s0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) d1sq += (tf * st0.d[i] / s0) * (tf * st0.d[i] / s0);
+        const double d0 = sqrt(d0sq / 56.0), d1 = sqrt(d1sq / 56.0);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, interval_length);
+        const double hs0 = h0 * tf;
+        double x1[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x1[i] = fma(hs0, st0.k[i], x[i]);
+        AdStage stA;
+        bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x1, h0 * ilen, t0 + h0, hold, stA);
+        double d2sq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const double sc = atol + fabs(x[i]) * rtol;
+            const double df = tf * (stA.k[i] - st0.k[i]) / sc;
+            d2sq += df * df;
+        }
+        const double g1[9] = {stA.g.xx, stA.g.xy, stA.g.xz, stA.g.xy, stA.g.yy, stA.g.yz, stA.g.xz, stA.g.yz, stA.g.zz};
+        if (DRAG) {
+            const double t_[9] = {stA.v.xx, stA.v.xy, stA.v.xz, stA.v.xy, stA.v.yy, stA.v.yz, stA.v.xz, stA.v.yz, stA.v.zz};
+#pragma unroll
+            for (int i = 0; i < 9; ++i) vA[i] = t_[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            double p1r[3], p1v[3], f0r[3], f0v[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                f0r[a] = (c == a + 3) ? 1.0 : 0.0;
+                f0v[a] = (c < 3) ? g[a * 3 + c] : ((c == 6) ? st0.d[a] : v0[a * 3 + (c - 3)]);
+                p1r[a] = ((c == a) ? 1.0 : 0.0) + hs0 * f0r[a];
+                p1v[a] = ((c == a + 3) ? 1.0 : 0.0) + hs0 * f0v[a];
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double f1r = p1v[a];
+                double f1v = g1[a * 3 + 0] * p1r[0] + g1[a * 3 + 1] * p1r[1] + g1[a * 3 + 2] * p1r[2];
+                if (DRAG) f1v += vA[a * 3 + 0] * p1v[0] + vA[a * 3 + 1] * p1v[1] + vA[a * 3 + 2] * p1v[2];
+                if (c == 6) f1v += stA.d[a];
+                const double scr = (c == a) ? s1 : s0, scv = (c == a + 3) ? s1 : s0;
+                const double e1 = tf * (f1r - f0r[a]) / scr, e2 = tf * (f1v - f0v[a]) / scv;
+                d2sq += e1 * e1 + e2 * e2;
+            }
+        }
+        const double d2 = sqrt(d2sq / 56.0) / h0;
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+        h_abs = fmin(fmin(100.0 * h0, h1), fmin(interval_length, max_step));
+    }
+
+    // ---- solve_ivp main loop.  One trip per quadrature node: try steps from node j until one is accepted (none when
+    // t has reached the end), then add node j with its full trapezoid weight, then move on. ---------------------------
+    double half_prev = 0.0;       // (t_j - t_{j-1}) / 2
+#pragma unroll 1
+    for (;;) {
+        const bool last = !(t < t1);
+        double half_next = 0.0, t_new = t;
+        double xn[7];
+        AdStage st6;
+        if (!last) {
+            const double min_step = 10.0 * fabs(nextafter(t, CUDART_INF) - t);
+            if (h_abs > max_step) h_abs = max_step;
+            else if (h_abs < min_step) h_abs = min_step;
+            bool accepted = false, rejected = false;
+            while (!accepted) {
+                if (h_abs < min_step) {
+                    fail = 1;
+                    break;
+                }
+                t_new = t + h_abs;
+                if (t_new - t1 > 0.0) t_new = t1;
+                const double h = t_new - t;
+                h_abs = fabs(h);
+                const double hs = h * tf;
+                // -- state stages (registers): running sums y_s = x + hs sum_l a_sl k_l, literal coefficients ----------
+                double kx[6][7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) kx[0][i] = st0.k[i];
+                df_store_stage<BLOCK, DRAG>(sm, 0, st0);
+                const double cs[6] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
+#pragma unroll
+                for (int s = 1; s < 6; ++s) {
+                    double xs_[7];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) {
+                        double dy = 0.0;
+#pragma unroll
+                        for (int l = 0; l < s; ++l) dy = fma(kx[l][i], kDpA[s][l], dy);
+                        xs_[i] = fma(dy, hs, x[i]);
+                    }
+                    AdStage sg;
+                    bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) kx[s][i] = sg.k[i];
+                    df_store_stage<BLOCK, DRAG>(sm, s, sg);
+                }
+                const double bw[6] = {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+                const double ew[7] = {-71.0 / 57600, 0.0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    double dy = 0.0;
+#pragma unroll
+                    for (int l = 0; l < 6; ++l) dy = fma(kx[l][i], bw[l], dy);
+                    xn[i] = fma(hs, dy, x[i]);
+                }
+                bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xn, (t + h - t0) * ilen, t + h, hold, st6);
+                df_store_stage<BLOCK, DRAG>(sm, 6, st6);
+                double esum = 0.0;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    double e = st6.k[i] * ew[6];
+#pragma unroll
+                    for (int l = 0; l < 6; ++l) e = fma(kx[l][i], ew[l], e);
+                    const double q = e * hs * fast_rcp(atol + fmax(fabs(x[i]), fabs(xn[i])) * rtol);
+                    esum = fma(q, q, esum);
+                }
+                // -- Phi columns: global (L2) -> registers -> global, stage matrices from shared memory ----------------
+#pragma unroll 1
+                for (int c = 0; c < 7; ++c) {
+                    double p[6], kr[7][3], kv[7][3];
+                    if (first) {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) p[i] = (i == c) ? 1.0 : 0.0;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) p[i] = cur[(long long)(c * 6 + i) * pitch];
+                    }
+                    const double dflag = (c == 6) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) {
+                        double q[6];
+                        if (s == 0) {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) q[i] = p[i];
+                        } else if (s < 6) {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) {
+                                double dy = 0.0;
+#pragma unroll
+                                for (int l = 0; l < s; ++l) dy = fma((i < 3) ? kr[l][i] : kv[l][i - 3], kDpA[s][l], dy);
+                                q[i] = fma(dy, hs, p[i]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) {
+                                double dy = 0.0;
+#pragma unroll
+                                for (int l = 0; l < 6; ++l) dy = fma((i < 3) ? kr[l][i] : kv[l][i - 3], bw[l], dy);
+                                q[i] = fma(hs, dy, p[i]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) nxt[(long long)(c * 6 + i) * pitch] = q[i];
+                        }
+                        const int b = kDfAcc + s * kStage;
+                        const double gxx = SM(b), gxy = SM(b + 1), gxz = SM(b + 2), gyy = SM(b + 3), gyz = SM(b + 4), gzz = SM(b + 5);
+                        double dx = SM(b + 6) * dflag, dy_ = SM(b + 7) * dflag, dz = SM(b + 8) * dflag;
+                        if (DRAG) {   // + V q_v
+                            const double vxx = SM(b + 9), vxy = SM(b + 10), vxz = SM(b + 11), vyy = SM(b + 12), vyz = SM(b + 13), vzz = SM(b + 14);
+                            dx = fma(vxz, q[5], fma(vxy, q[4], fma(vxx, q[3], dx)));
+                            dy_ = fma(vyz, q[5], fma(vyy, q[4], fma(vxy, q[3], dy_)));
+                            dz = fma(vzz, q[5], fma(vyz, q[4], fma(vxz, q[3], dz)));
+                        }
+                        kr[s][0] = q[3];
+                        kr[s][1] = q[4];
+                        kr[s][2] = q[5];
+                        kv[s][0] = fma(gxz, q[2], fma(gxy, q[1], fma(gxx, q[0], dx)));
+                        kv[s][1] = fma(gyz, q[2], fma(gyy, q[1], fma(gxy, q[0], dy_)));
+                        kv[s][2] = fma(gzz, q[2], fma(gyz, q[1], fma(gxz, q[0], dz)));
+                        if (s == 6) {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) {
+                                double e = 0.0;
+#pragma unroll
+                                for (int l = 0; l < 7; ++l) e = fma((i < 3) ? kr[l][i] : kv[l][i - 3], ew[l], e);
+                                const double qq = e * hs * fast_rcp(atol + fmax(fabs(p[i]), fabs(q[i])) * rtol);
+                                esum = fma(qq, qq, esum);
+                            }
+                        }
+                    }
+                }
+                const double err = sqrt(esum * (1.0 / 56.0));
+                if (!(err >= 1.0)) {   // also accepts a NaN error so that a poisoned unit terminates (status flags it)
+                    double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+                    if (rejected) factor = fmin(1.0, factor);
+                    if (!(factor == factor)) factor = 1.0;
+                    h_abs *= factor;
+                    accepted = true;
+                } else {
+                    h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+                    rejected = true;
+                }
+            }
+            half_next = 0.5 * (t_new - t);
+        }
+        // ---- node j: w_j = (t_j - t_{j-1})/2 + (t_{j+1} - t_j)/2, np.trapz with x = sol.t (:77-80) ---------------------
+        // (after a step-size underflow nothing is accumulated any more: the unit is flagged)
+        if (!fail) {
+            double pr[7][3], pv[7][3];
+            if (first) {
+#pragma unroll
+                for (int c = 0; c < 7; ++c)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        pr[c][a] = (c == a) ? 1.0 : 0.0;
+                        pv[c][a] = (c == a + 3) ? 1.0 : 0.0;
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 7; ++c)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        pr[c][a] = cur[(long long)(c * 6 + a) * pitch];
+                        pv[c][a] = cur[(long long)(c * 6 + 3 + a) * pitch];
+                    }
+            }
+            const double w = half_prev + half_next;
+            // The reference inverts the NUMERICAL Phi (np.linalg.inv, :69): general 6x6 solve, see discretize_adaptive_kernel
+            node_accumulate_general<BLOCK>(sm, pr, pv, P, st0, x, w, w * ((t - t0) * ilen));
+        }
+        if (last || fail) break;
+        double *const tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+        first = false;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = xn[i];
+        st0 = st6;
+        half_prev = half_next;
+        t = t_new;
+        if (++nodes > 4096) {
+            fail = 1;
+            break;
+        }
+    }
+
+    double pr[7][3], pv[7][3];
+#pragma unroll
+    for (int c = 0; c < 7; ++c)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            pr[c][a] = first ? ((c == a) ? 1.0 : 0.0) : cur[(long long)(c * 6 + a) * pitch];
+            pv[c][a] = first ? ((c == a + 3) ? 1.0 : 0.0) : cur[(long long)(c * 6 + 3 + a) * pitch];
+        }
+    const int nonfinite = epilogue_store<BLOCK, 1>(sm, pr, pv, tf, 1.0, tf, dst, pitch, offset + gid);
+    if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : (fail ? 3 : 0));
+    if (n_nodes) n_nodes[gid] = nodes;
+}
+#undef SM
+
+}  // namespace mpc

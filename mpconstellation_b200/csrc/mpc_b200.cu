@@ -16,6 +16,7 @@
 
 #include "discretize_kernel.cuh"
 #include "discretize_adaptive_kernel.cuh"
+#include "discretize_default_kernel.cuh"
 #include "propagate_kernel.cuh"
 #include "propagate_rk45_kernel.cuh"
 #include "constraint_terms_kernel.cuh"
@@ -191,17 +192,11 @@ int launch_adaptive(const double *x, const double *u, const double *tf, const mp
                        : launch_adaptive_g<J2, false>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
 }
 
-std::atomic<int> g_compact{0};   // mpc_set_tuning(9): COMPACT build of the adaptive kernel (experimental, see the kernel)
+std::atomic<int> g_default_v1{0};   // mpc_set_tuning(9): the round-1 build of the default-mode kernel (A/B measurements)
 
-template <bool J2, bool GENU, bool DRAG, bool COMPACT = false>
-int launch_adaptive_k(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
-                      const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
-                      cudaStream_t st)
+template <typename Kern>
+int configure_smem(Kern kern, size_t smem, int &configured_dev)
 {
-    constexpr int BLOCK = 32;
-    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1, GENU, DRAG, COMPACT>;
-    const size_t smem = (size_t)(DRAG ? mpc::kAdSlotsDrag : mpc::kAdSlots) * BLOCK * sizeof(double);
-    static thread_local int configured_dev = -1;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (configured_dev != dev) {
@@ -209,6 +204,44 @@ int launch_adaptive_k(const double *x, const double *u, const double *tf, const 
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured_dev = dev;
     }
+    return MPC_SUCCESS;
+}
+
+// round-1 build: Phi and its candidate in shared memory (52 KiB per warp), both ends of every panel evaluated
+template <bool J2, bool GENU, bool DRAG>
+int launch_adaptive_v1(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                       const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                       cudaStream_t st)
+{
+    constexpr int BLOCK = 32;
+    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1, GENU, DRAG>;
+    const size_t smem = (size_t)(DRAG ? mpc::kAdSlotsDrag : mpc::kAdSlots) * BLOCK * sizeof(double);
+    static thread_local int configured_dev = -1;
+    int rc = configure_smem(kern, smem, configured_dev);
+    if (rc) return rc;
+    const long long n_int = (long long)n_sats * (K - 1);
+    const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, g_ucols, o.rtol, o.atol, o.max_step, dst, pitch, offset,
+                                    status, o.n_nodes, o.kf, o.ka);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
+
+// shipped build (discretize_default_kernel): Phi ping-pongs through the output buffer, 30 KiB of shared memory per warp
+template <bool J2, bool GENU, bool DRAG>
+int launch_adaptive_k(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                      const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                      cudaStream_t st)
+{
+    if (g_default_v1.load(std::memory_order_relaxed))
+        return launch_adaptive_v1<J2, GENU, DRAG>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+    constexpr int BLOCK = 32;
+    auto kern = mpc::discretize_default_kernel<J2, BLOCK, GENU, DRAG>;
+    const size_t smem = (size_t)(DRAG ? mpc::kDfSlotsDrag : mpc::kDfSlots) * BLOCK * sizeof(double);
+    static thread_local int configured_dev = -1;
+    int rc = configure_smem(kern, smem, configured_dev);
+    if (rc) return rc;
     const long long n_int = (long long)n_sats * (K - 1);
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
     kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, g_ucols, o.rtol, o.atol, o.max_step, dst, pitch, offset,
@@ -227,8 +260,6 @@ int launch_adaptive_g(const double *x, const double *u, const double *tf, const 
         if (GENU) return fail(MPC_E_UNSUPPORTED, "include_drag with u on its own grid is not supported");
         return launch_adaptive_k<J2, false, true>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
     }
-    if (!GENU && g_compact.load(std::memory_order_relaxed))
-        return launch_adaptive_k<J2, false, false, true>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
     return launch_adaptive_k<J2, GENU, false>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
 }
 
@@ -633,8 +664,8 @@ int mpc_set_tuning(int variant)
         g_pair.store(variant == 8);
         return MPC_SUCCESS;
     }
-    if (variant == 9 || variant == 10) {  // 9: COMPACT build of the adaptive (default-mode) kernel; 10: back to the inlined build
-        g_compact.store(variant == 9);
+    if (variant == 9 || variant == 10) {  // 9: round-1 build of the default-mode kernel; 10: back to the shipped one
+        g_default_v1.store(variant == 9);
         return MPC_SUCCESS;
     }
     if (variant == 11 || variant == 12) {  // RK45 propagator: speculative first stage of the next step off / on

@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "mpconstellation_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 SO = os.path.join(BUILD, "libmpc_hostk.so")
-SOURCES = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_pair_kernel.cuh",
+SOURCES = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_default_kernel.cuh", "discretize_pair_kernel.cuh",
            "discretize_drag_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "constraint_terms_kernel.cuh"]
 _SEEDS = [(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rcp_seed(a);"),
           (r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rsqrt_seed(a);")]
@@ -97,7 +97,8 @@ def discretize(x, u, tf, const, include_J2=False, n_sub=100, pair=True, k0=0, kc
     return out, status
 
 
-def discretize_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6, max_step=1e-2, compact=False):
+def discretize_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6, max_step=1e-2, v1=False):
+    """the default-mode kernel (discretize_default_kernel); v1=True: the round-1 build (discretize_adaptive_kernel)"""
     x = np.ascontiguousarray(x, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
     N, _, K = x.shape
@@ -109,7 +110,7 @@ def discretize_adaptive(x, u, tf, const, include_J2=False, rtol=1e-3, atol=1e-6,
     c8 = _const8(const)
     lib().hostk_discretize_adaptive(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, ctypes.c_double(rtol),
                                     ctypes.c_double(atol), ctypes.c_double(max_step), _p(out), ctypes.c_longlong(n_int),
-                                    ctypes.c_longlong(0), _p(status), _p(nodes), int(compact))
+                                    ctypes.c_longlong(0), _p(status), _p(nodes), int(v1))
     return out, status, nodes
 
 

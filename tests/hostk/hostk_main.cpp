@@ -7,6 +7,7 @@
 
 #include "discretize_kernel.cuh"
 #include "discretize_adaptive_kernel.cuh"
+#include "discretize_default_kernel.cuh"
 #include "discretize_pair_kernel.cuh"
 #include "propagate_kernel.cuh"
 #include "propagate_rk45_kernel.cuh"
@@ -74,20 +75,20 @@ extern "C" int hostk_discretize_adaptive(const double *x, const double *u, const
     const mpc::DiscParams P = disc_params(const8, include_j2);
     mpc::DstTab dst{};
     dst.p[0] = out;
-    if (compact) {   // the COMPACT build (dynamics evaluation and node term as real calls)
+    if (compact) {   // (parameter name kept) 1: the round-1 build, Phi in shared memory, both ends of every panel evaluated
         run_grid((long long)n_sats * (K - 1), [&] {
             if (include_j2)
-                mpc::discretize_adaptive_kernel<true, kBlock, 1, false, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
+                mpc::discretize_adaptive_kernel<true, kBlock, 1, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
             else
-                mpc::discretize_adaptive_kernel<false, kBlock, 1, false, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
+                mpc::discretize_adaptive_kernel<false, kBlock, 1, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
         });
         return 0;
     }
-    run_grid((long long)n_sats * (K - 1), [&] {
+    run_grid((long long)n_sats * (K - 1), [&] {   // the shipped build
         if (include_j2)
-            mpc::discretize_adaptive_kernel<true, kBlock, 1, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
+            mpc::discretize_default_kernel<true, kBlock, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
         else
-            mpc::discretize_adaptive_kernel<false, kBlock, 1, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
+            mpc::discretize_default_kernel<false, kBlock, false, false>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset, status, n_nodes);
     });
     return 0;
 }
@@ -197,9 +198,9 @@ extern "C" int hostk_discretize_drag(const double *x, const double *u, const dou
     run_grid((long long)n_sats * (K - 1), [&] {
         if (adaptive) {
             if (include_j2)
-                mpc::discretize_adaptive_kernel<true, kBlock, 1, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, ka);
+                mpc::discretize_default_kernel<true, kBlock, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, ka);
             else
-                mpc::discretize_adaptive_kernel<false, kBlock, 1, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, ka);
+                mpc::discretize_default_kernel<false, kBlock, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, ka);
         } else {
             if (include_j2) mpc::discretize_drag_kernel<true, kBlock>(x, u, tf, P, kf, ka, n_sats, K, n_sub, dst, pitch, 0, status);
             else mpc::discretize_drag_kernel<false, kBlock>(x, u, tf, P, kf, ka, n_sats, K, n_sub, dst, pitch, 0, status);
@@ -235,8 +236,8 @@ extern "C" int hostk_discretize_ugrid(const double *x, const double *u, int u_co
     dst.p[0] = out;
     run_grid((long long)n_sats * (K - 1), [&] {
         if (adaptive) {
-            if (include_j2) mpc::discretize_adaptive_kernel<true, kBlock, 1, true, false>(x, u, tf, P, n_sats, K, u_cols, rtol, atol, max_step, dst, pitch, 0, status, n_nodes);
-            else mpc::discretize_adaptive_kernel<false, kBlock, 1, true, false>(x, u, tf, P, n_sats, K, u_cols, rtol, atol, max_step, dst, pitch, 0, status, n_nodes);
+            if (include_j2) mpc::discretize_default_kernel<true, kBlock, true, false>(x, u, tf, P, n_sats, K, u_cols, rtol, atol, max_step, dst, pitch, 0, status, n_nodes);
+            else mpc::discretize_default_kernel<false, kBlock, true, false>(x, u, tf, P, n_sats, K, u_cols, rtol, atol, max_step, dst, pitch, 0, status, n_nodes);
         } else {
             if (include_j2) mpc::discretize_kernel<true, kBlock, 255, 1, true>(x, u, tf, P, n_sats, K, u_cols, n_sub, dst, pitch, 0, status);
             else mpc::discretize_kernel<false, kBlock, 255, 1, true>(x, u, tf, P, n_sats, K, u_cols, n_sub, dst, pitch, 0, status);
