@@ -14,7 +14,11 @@
 //   * every quadrature node is evaluated ONCE, with its full trapezoid weight (t_{j+1} - t_{j-1})/2, when the step that
 //     leaves it has been accepted (the old build evaluated both ends of every panel: 2 (n-1) instead of n node terms,
 //     each with a 6x6 solve), and the step loop is arranged so that the node term has a single call site;
-//   * the stage states of the 7-vector are formed from running sums with literal tableau coefficients.
+//   * launched as ONE 7-warp CTA per SM: the hot loop (36 KB of SASS) is larger than the SM's instruction cache, and
+//     one-warp CTAs walk it out of phase, each paying its own instruction misses (measured: 3.75 warps stalled on
+//     instruction fetch per issue, the GPC-level instruction cache 98 % busy, 2.64 ms).  The warps of one CTA start
+//     together and take the same 4-5 steps, stay within a few cache lines of each other and share every fetched line
+//     (instruction-cache hit rate 68 % -> 93 %, 1.97 ms; profiles/r02_b, r02_c).
 // Results agree with the first build to rounding (the panel sums are associated differently) and with the unmodified
 // reference's default-mode fixtures to <= 1e-10; node counts are identical.
 #pragma once
@@ -85,8 +89,10 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
 #pragma unroll 1
     for (int e = 0; e < kDfAcc; ++e) SM(e) = 0.0;
     int bad = 0, fail = 0, nodes = 1;
-    bool first = true;            // Phi(tau_k) = I (:34): not read from memory
     double t = t0;
+    // Phi(tau_k) = I (:34)
+#pragma unroll
+    for (int e = 0; e < 42; ++e) cur[(long long)e * pitch] = (e % 7 == 0 && e < 36) ? 1.0 : 0.0;
 
     AdStage st0;
     bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x, 0.0, t0, hold, st0);
@@ -190,7 +196,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                 const double h = t_new - t;
                 h_abs = fabs(h);
                 const double hs = h * tf;
-                // -- state stages (registers): running sums y_s = x + hs sum_l a_sl k_l, literal coefficients ----------
+                // -- state stages (registers) ------------------------------------------------------------------------
                 double kx[6][7];
 #pragma unroll
                 for (int i = 0; i < 7; ++i) kx[0][i] = st0.k[i];
@@ -233,15 +239,18 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                     esum = fma(q, q, esum);
                 }
                 // -- Phi columns: global (L2) -> registers -> global, stage matrices from shared memory ----------------
+                // (the next column is requested from L2 while this one is stepped)
+                double pn[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) pn[i] = cur[(long long)i * pitch];
 #pragma unroll 1
                 for (int c = 0; c < 7; ++c) {
                     double p[6], kr[7][3], kv[7][3];
-                    if (first) {
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) p[i] = (i == c) ? 1.0 : 0.0;
-                    } else {
+                    for (int i = 0; i < 6; ++i) p[i] = pn[i];
+                    if (c < 6) {
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) p[i] = cur[(long long)(c * 6 + i) * pitch];
+                        for (int i = 0; i < 6; ++i) pn[i] = cur[(long long)((c + 1) * 6 + i) * pitch];
                     }
                     const double dflag = (c == 6) ? 1.0 : 0.0;
 #pragma unroll
@@ -314,23 +323,13 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
         // (after a step-size underflow nothing is accumulated any more: the unit is flagged)
         if (!fail) {
             double pr[7][3], pv[7][3];
-            if (first) {
 #pragma unroll
-                for (int c = 0; c < 7; ++c)
+            for (int c = 0; c < 7; ++c)
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        pr[c][a] = (c == a) ? 1.0 : 0.0;
-                        pv[c][a] = (c == a + 3) ? 1.0 : 0.0;
-                    }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 7; ++c)
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        pr[c][a] = cur[(long long)(c * 6 + a) * pitch];
-                        pv[c][a] = cur[(long long)(c * 6 + 3 + a) * pitch];
-                    }
-            }
+                for (int a = 0; a < 3; ++a) {
+                    pr[c][a] = cur[(long long)(c * 6 + a) * pitch];
+                    pv[c][a] = cur[(long long)(c * 6 + 3 + a) * pitch];
+                }
             const double w = half_prev + half_next;
             // The reference inverts the NUMERICAL Phi (np.linalg.inv, :69): general 6x6 solve, see discretize_adaptive_kernel
             node_accumulate_general<BLOCK>(sm, pr, pv, P, st0, x, w, w * ((t - t0) * ilen));
@@ -339,7 +338,6 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
         double *const tmp = cur;
         cur = nxt;
         nxt = tmp;
-        first = false;
 #pragma unroll
         for (int i = 0; i < 7; ++i) x[i] = xn[i];
         st0 = st6;
@@ -356,8 +354,8 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
     for (int c = 0; c < 7; ++c)
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            pr[c][a] = first ? ((c == a) ? 1.0 : 0.0) : cur[(long long)(c * 6 + a) * pitch];
-            pv[c][a] = first ? ((c == a + 3) ? 1.0 : 0.0) : cur[(long long)(c * 6 + 3 + a) * pitch];
+            pr[c][a] = cur[(long long)(c * 6 + a) * pitch];
+            pv[c][a] = cur[(long long)(c * 6 + 3 + a) * pitch];
         }
     const int nonfinite = epilogue_store<BLOCK, 1>(sm, pr, pv, tf, 1.0, tf, dst, pitch, offset + gid);
     if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : (fail ? 3 : 0));

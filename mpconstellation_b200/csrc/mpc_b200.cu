@@ -229,14 +229,13 @@ int launch_adaptive_v1(const double *x, const double *u, const double *tf, const
 }
 
 // shipped build (discretize_default_kernel): Phi ping-pongs through the output buffer, 30 KiB of shared memory per warp
-template <bool J2, bool GENU, bool DRAG>
-int launch_adaptive_k(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
-                      const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
-                      cudaStream_t st)
+std::atomic<int> g_default_block{224};   // mpc_set_tuning(20/21/22): 32 / 128 / 224 threads per CTA
+
+template <bool J2, bool GENU, bool DRAG, int BLOCK>
+int launch_default_b(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                     const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                     cudaStream_t st)
 {
-    if (g_default_v1.load(std::memory_order_relaxed))
-        return launch_adaptive_v1<J2, GENU, DRAG>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
-    constexpr int BLOCK = 32;
     auto kern = mpc::discretize_default_kernel<J2, BLOCK, GENU, DRAG>;
     const size_t smem = (size_t)(DRAG ? mpc::kDfSlotsDrag : mpc::kDfSlots) * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
@@ -249,6 +248,29 @@ int launch_adaptive_k(const double *x, const double *u, const double *tf, const 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
+}
+
+template <bool J2, bool GENU, bool DRAG>
+int launch_adaptive_k(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                      const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
+                      cudaStream_t st)
+{
+    if (g_default_v1.load(std::memory_order_relaxed))
+        return launch_adaptive_v1<J2, GENU, DRAG>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+    // The hot loop of this kernel (39 KB of SASS) is larger than the SM's instruction cache.  One-warp CTAs start at
+    // different times and walk it out of phase, each paying its own instruction misses (profiles/r02_b: 3.75 warps
+    // stalled on instruction fetch per issue).  The warps of ONE large CTA start together and take the same 4-5 steps:
+    // they stay within a few cache lines of each other and share every fetched line.  7 warps = 213 KiB of shared memory
+    // fill an SM; small batches keep one-warp CTAs so that they still spread over all SMs.  (The drag variant needs 41 KiB
+    // per warp: 5 warps.)
+    const long long n_int = (long long)n_sats * (K - 1);
+    int block = g_default_block.load(std::memory_order_relaxed);
+    if (n_int < 148LL * 224) block = 32;
+    if (!DRAG && !GENU) {
+        if (block == 224) return launch_default_b<J2, GENU, DRAG, 224>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+        if (block == 128) return launch_default_b<J2, GENU, DRAG, 128>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+    }
+    return launch_default_b<J2, GENU, DRAG, 32>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
 }
 
 template <bool J2, bool GENU>
@@ -675,6 +697,11 @@ int mpc_set_tuning(int variant)
     if (variant >= 13 && variant <= 19) {  // RK45 propagator: satellites per warp 13 automatic, 14..19 -> 32,16,8,4,2,1
         static const int lpw[7] = {0, 32, 16, 8, 4, 2, 1};
         g_rk45_lpw.store(lpw[variant - 13]);
+        return MPC_SUCCESS;
+    }
+    if (variant >= 20 && variant <= 22) {  // default-mode kernel: threads per CTA 32 / 128 / 224
+        static const int blk[3] = {32, 128, 224};
+        g_default_block.store(blk[variant - 20]);
         return MPC_SUCCESS;
     }
     if (variant < 0 || variant > 6) return fail(MPC_E_INVALID, "unknown tuning variant %d", variant);

@@ -30,8 +30,10 @@ if "--once" in sys.argv:
     torch.cuda.synchronize()
     sys.exit(0)
 res = {}
-for name, variant in (("round-1 build", 9), ("shipped build", 10)):
-    _lib.check(_lib.lib().mpc_set_tuning(variant))
+for name, variant in (("round-1 build", (9, 20)), ("shipped, 32-thread CTAs", (10, 20)), ("shipped, 128-thread CTAs", (10, 21)),
+                      ("shipped build", (10, 22))):
+    for v in variant:
+        _lib.check(_lib.lib().mpc_set_tuning(v))
     out = torch.full((105, n_int), float("nan"), dtype=torch.float64, device=dev)
     st = torch.empty(n_int, dtype=torch.int32, device=dev)
     nn = torch.empty(n_int, dtype=torch.int32, device=dev)
@@ -50,6 +52,8 @@ for name, variant in (("round-1 build", 9), ("shipped build", 10)):
     print(f"{name}: mean {np.mean(ts):.3f} ms  min {np.min(ts):.3f} ms  status max {int(st.max())}  nodes {int(nn.min())}-{int(nn.max())}"
           f" (mean {float(nn.double().mean()):.3f})  {n_int / np.mean(ts) / 1e3:.3e} intervals/s")
 _lib.check(_lib.lib().mpc_set_tuning(10))
+_lib.check(_lib.lib().mpc_set_tuning(22))
+assert torch.equal(res["shipped, 32-thread CTAs"][0], res["shipped build"][0]), "CTA size must not change a bit"
 a, b = res["round-1 build"], res["shipped build"]
 for r0, r1, nm in ((0, 49, "A_k"), (49, 70, "B_kp"), (70, 91, "B_kn"), (91, 98, "Sigma_k"), (98, 105, "xi_k")):
     den = float(a[0][r0:r1].abs().max())
