@@ -10,11 +10,12 @@
 //     itself: rows 0..41 (where A_k ends up anyway) and rows 49..90 (B_kp / B_kn, written only by the epilogue).  The
 //     layout is the SoA one, [row][interval]: every access of a warp is one coalesced 256-byte line, it stays in L2
 //     for the life of the warp, and each entry is read / written once per step.  Shared memory per thread drops from
-//     203 to 119 slots (56 accumulators + 7 stage linearisations of 9), i.e. 7 instead of 4 warps per SM.
+//     203 to 111 slots (48 accumulators + 7 stage linearisations of 9; the 8 accumulators of row 6, plain sums that
+//     need no Phi, are kept in rows 91..98 of the output buffer as well), i.e. 8 instead of 4 warps per SM.
 //   * every quadrature node is evaluated ONCE, with its full trapezoid weight (t_{j+1} - t_{j-1})/2, when the step that
 //     leaves it has been accepted (the old build evaluated both ends of every panel: 2 (n-1) instead of n node terms,
 //     each with a 6x6 solve), and the step loop is arranged so that the node term has a single call site;
-//   * launched as ONE 7-warp CTA per SM: the hot loop (36 KB of SASS) is larger than the SM's instruction cache, and
+//   * launched as ONE 8-warp CTA per SM: the hot loop (36 KB of SASS) is larger than the SM's instruction cache, and
 //     one-warp CTAs walk it out of phase, each paying its own instruction misses (measured: 3.75 warps stalled on
 //     instruction fetch per issue, the GPC-level instruction cache 98 % busy, 2.64 ms).  The warps of one CTA start
 //     together and take the same 4-5 steps, stay within a few cache lines of each other and share every fetched line
@@ -26,10 +27,12 @@
 
 namespace mpc {
 
-constexpr int kDfAcc = 56;                        // accumulators (layout of kAccSlots)
-constexpr int kDfSlots = kDfAcc + 7 * 9;          // + G_s (6), d_s (3) of the 7 stages
+constexpr int kDfAcc = 48;                        // accumulators in shared memory: slots 0..47 of the kAccSlots layout; the 8
+                                                  // of row 6 (slots 48..55) live in the output buffer (rows kDfRow6..)
+constexpr int kDfSlots = kDfAcc + 7 * 9;          // + G_s (6), d_s (3) of the 7 stages: 111 slots, 8 warps per SM
 constexpr int kDfSlotsDrag = kDfAcc + 7 * 15;     // + V_s (6): drag branch of the linearisation
 constexpr int kDfPhiA = 0, kDfPhiB = 49;          // the two Phi row blocks inside the output buffer
+constexpr int kDfRow6 = 91;                       // rows 91..98: the row-6 accumulators until the epilogue
 
 #define SM(e) sm[(e) * BLOCK]
 
@@ -88,6 +91,9 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
 
 #pragma unroll 1
     for (int e = 0; e < kDfAcc; ++e) SM(e) = 0.0;
+    double *const row6 = col + (long long)kDfRow6 * pitch;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) row6[(long long)q * pitch] = 0.0;
     int bad = 0, fail = 0, nodes = 1;
     double t = t0;
     // Phi(tau_k) = I (:34)
@@ -332,7 +338,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                 }
             const double w = half_prev + half_next;
             // The reference inverts the NUMERICAL Phi (np.linalg.inv, :69): general 6x6 solve, see discretize_adaptive_kernel
-            node_accumulate_general<BLOCK>(sm, pr, pv, P, st0, x, w, w * ((t - t0) * ilen));
+            node_accumulate_general<BLOCK>(sm, pr, pv, P, st0, x, w, w * ((t - t0) * ilen), row6, pitch);
         }
         if (last || fail) break;
         double *const tmp = cur;
@@ -357,6 +363,8 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
             pr[c][a] = cur[(long long)(c * 6 + a) * pitch];
             pv[c][a] = cur[(long long)(c * 6 + 3 + a) * pitch];
         }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) SM(48 + q) = row6[(long long)q * pitch];   // (the stage slots are dead by now)
     const int nonfinite = epilogue_store<BLOCK, 1>(sm, pr, pv, tf, 1.0, tf, dst, pitch, offset + gid);
     if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : (fail ? 3 : 0));
     if (n_nodes) n_nodes[gid] = nodes;

@@ -100,10 +100,12 @@ __device__ __forceinline__ void drag_col_rhs(volatile double *acc, int s, const 
 
 // General-inverse quadrature node (unscaled variables): acc += w * Phi^-1 [Duf, Sigma, xi'], acc1 += ws * Phi^-1 Duf.
 // Same slot layout as node_accumulate.  linearize_discretize.py:63-75.
+// row6 != nullptr: the 8 accumulators of row 6 (slots 48..55) live at row6[0], row6[stride], ... (global memory) instead
+// of the shared-memory slots.
 template <int BLOCK>
 __device__ __forceinline__ void node_accumulate_general(volatile double *acc, const double (&pr)[7][3], const double (&pv)[7][3],
                                                      const DiscParams &P, const DragEval &e, const double (&x)[7],
-                                                     double w, double ws)
+                                                     double w, double ws, double *row6 = nullptr, long long stride = 0)
 {
     double M[6][6], R[6][6];
 #pragma unroll
@@ -145,6 +147,16 @@ __device__ __forceinline__ void node_accumulate_general(volatile double *acc, co
             for (int c = 0; c < 6; ++c) R[r][c] = fma(-f, R[p][c], R[r][c]);
         }
     }
+    // (requested after the solve -- 16 registers fewer while it runs -- and used last: the shared-memory updates cover
+    // most of the L2 latency)
+    double m6[8];
+    if (row6) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m6[q] = row6[(long long)q * stride];
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m6[q] = ACC(48 + q);
+    }
     const double bs = -P.inv_ve * e.iun;
     const double b[3] = {bs * e.ux, bs * e.uy, bs * e.uz};      // last row of Duf (0 under the eps guard, :208)
     const double md = e.k[6];
@@ -163,11 +175,18 @@ __device__ __forceinline__ void node_accumulate_general(volatile double *acc, co
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        ACC(48 + j) = fma(w, b[j], ACC(48 + j));
-        ACC(51 + j) = fma(ws, b[j], ACC(51 + j));
+        m6[j] = fma(w, b[j], m6[j]);
+        m6[3 + j] = fma(ws, b[j], m6[3 + j]);
     }
-    ACC(54) = fma(w, md, ACC(54));
-    ACC(55) = fma(-w, mdb, ACC(55));
+    m6[6] = fma(w, md, m6[6]);
+    m6[7] = fma(-w, mdb, m6[7]);
+    if (row6) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) row6[(long long)q * stride] = m6[q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ACC(48 + q) = m6[q];
+    }
 }
 
 template <bool J2, int BLOCK>

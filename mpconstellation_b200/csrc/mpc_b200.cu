@@ -229,7 +229,7 @@ int launch_adaptive_v1(const double *x, const double *u, const double *tf, const
 }
 
 // shipped build (discretize_default_kernel): Phi ping-pongs through the output buffer, 30 KiB of shared memory per warp
-std::atomic<int> g_default_block{224};   // mpc_set_tuning(20/21/22): 32 / 128 / 224 threads per CTA
+std::atomic<int> g_default_block{256};   // mpc_set_tuning(20/21/22): 32 / 128 / 256 threads per CTA
 
 template <bool J2, bool GENU, bool DRAG, int BLOCK>
 int launch_default_b(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
@@ -265,9 +265,9 @@ int launch_adaptive_k(const double *x, const double *u, const double *tf, const 
     // per warp: 5 warps.)
     const long long n_int = (long long)n_sats * (K - 1);
     int block = g_default_block.load(std::memory_order_relaxed);
-    if (n_int < 148LL * 224) block = 32;
+    if (n_int < 148LL * 256) block = 32;
     if (!DRAG && !GENU) {
-        if (block == 224) return launch_default_b<J2, GENU, DRAG, 224>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+        if (block == 256) return launch_default_b<J2, GENU, DRAG, 256>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
         if (block == 128) return launch_default_b<J2, GENU, DRAG, 128>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
     }
     return launch_default_b<J2, GENU, DRAG, 32>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
@@ -699,8 +699,8 @@ int mpc_set_tuning(int variant)
         g_rk45_lpw.store(lpw[variant - 13]);
         return MPC_SUCCESS;
     }
-    if (variant >= 20 && variant <= 22) {  // default-mode kernel: threads per CTA 32 / 128 / 224
-        static const int blk[3] = {32, 128, 224};
+    if (variant >= 20 && variant <= 22) {  // default-mode kernel: threads per CTA 32 / 128 / 256
+        static const int blk[3] = {32, 128, 256};
         g_default_block.store(blk[variant - 20]);
         return MPC_SUCCESS;
     }
