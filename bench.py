@@ -12,7 +12,10 @@ bit-identical to the two kernels back to back, which --no-overlap times instead)
     python bench.py --impl reference [...]                          # the reference algorithm on the host cores
 
 Under torchrun (N>1) every rank processes its own 4096-satellite shard (weak scaling) and the discretized
-matrices are all-gathered over NCCL/NVLink inside the timed step, as north_star asks.
+matrices are all-gathered over NVLink inside the timed step, as north_star asks (fused into the kernel: peer stores;
+--gather nccl for the NCCL baseline).  `--total-sats 5025` is BASELINE configs[3]: ONE 1 M-interval sweep sharded over
+the ranks (strong scaling).  At N=1 the line also carries `configs`: BASELINE configs 1, 2 and 5 timed on the GPU, the
+plain-C port and (config 5) the reference path on the same shapes.
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, >= 3 warm-up steps, L2 flushed
 between timed steps (256 MiB write), max over ranks, clocks sampled during the timed region.
@@ -54,6 +57,16 @@ def fp64_instr_per_interval(n_sub, include_j2=False):
     if n_sub % 2 == 0:
         return (n_sub // 2) * ((798 + 298 + 116) if include_j2 else (754 + 242 + 99)) + tail
     return n_sub * ((571 + 230 + 69) if include_j2 else (532 + 182 + 55)) + tail
+
+
+def kernel_counters():
+    """Per-launch hardware counters of the shipped kernels, measured with ncu on this workload and committed under
+    profiles/ (each entry names the summary it was read from): dram traffic, executed flop of the default-mode kernel.
+    bench.py never hard-codes them; a kernel change means a new capture and a new entry."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
+    except Exception:
+        return {}
 
 
 def bytes_per_interval():
@@ -151,30 +164,62 @@ def cpu_port_baseline(n_sats, K, tf, n_sub, budget_s=12.0):
 
 
 def reference_arm(args):
-    """--impl reference: the reference ALGORITHM (scipy RK45 + per-node numpy, one process pool over intervals
-    per discretize call, satellites looped serially -- linearize_discretize.py:334-390, optimizer.py:243-249,
-    simulator.py:41-45) restated in oracle/mpc_oracle.py, on all host cores, on a bounded sample per step.
-    The reference itself is pure Python and cannot travel to the GPU box; the restatement makes the same
-    library calls and is pinned to it bit-for-bit by tests/test_oracle_golden.py."""
+    """--impl reference: the UNMODIFIED reference on the box's host cores.  Its hot-path modules are compiled to Python
+    bytecode under oracle/_ref/ by build() where /root/reference is mounted (oracle/refshim.py; no source is copied),
+    and run here through the reference's own public API, per satellite as its callers do (simulator.py:41-45,
+    control.py:180-188, optimizer.py:243-249): Simulator.run (scipy RK45, max_step 0.001) -> Discretizer.extract_uk ->
+    Discretizer.discretize (one mp.Pool over the intervals per call).  A bounded sample of the workload per step.
+    Falls back to the numpy restatement (oracle/mpc_oracle.py, kind "port") only when the bytecode is absent."""
     import warnings
     warnings.filterwarnings("ignore")
-    from oracle import mpc_oracle as O
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import refshim
     n_sats, K, tf = args.sats, args.nodes, args.tf
-    sf = O.scale_factors(HUBBLE)
-    const = O.normalized_constants(sf)
-    Y, _ = make_constellation(n_sats)
     cores = os.cpu_count() or 1
     S = args.ref_sats
-    ctrl = O.ctrl_tangential(0.5)
+    Yn, _ = make_constellation(n_sats)
+    root, kind = refshim.reference_location()
+    if root is not None:
+        import contextlib
+        import io
+        R = refshim.load_reference()
+        hub = R.Satellite(HUBBLE[0:3].copy(), HUBBLE[3:6].copy(), float(HUBBLE[6]))
+        scale = R.SatelliteScale(sat=hub)
+        const = scale.get_normalized_constants()
+        ctrl = R.ConstantTangentialThrustController(tangential_thrust=0.5)
+        F = R.Simulator.satellite_dynamics
+
+        def one_pass(s, uniform):
+            yd = scale.redim_state(Yn[s])
+            sat = R.Satellite(yd[0:3], yd[3:6], float(yd[6]))
+            sim = R.Simulator(sats=[sat], controller=ctrl, scale=scale, base_res=int(round(K / tf)), include_drag=False,
+                              include_J2=False)
+            sim.run(tf=tf)
+            x, t = sim.sim_data[sat.id], sim.sim_time[sat.id]
+            d = R.Discretizer(const)
+            d.use_uniform_steps = uniform
+            d.integrator_steps = args.n_sub + 1
+            with contextlib.redirect_stdout(io.StringIO()):
+                return d.discretize(F, x, R.Discretizer.extract_uk(x, t, ctrl), tf)
+        impl_kind = "reference"
+        what = f"the unmodified reference ({kind} under {os.path.relpath(root, ROOT) if root.startswith(ROOT) else root})"
+    else:
+        from oracle import mpc_oracle as O
+        const = O.normalized_constants(O.scale_factors(HUBBLE))
+        ctrl = O.ctrl_tangential(0.5)
+
+        def one_pass(s, uniform):
+            x, t = O.propagate(Yn[s], tf, ctrl, const, False, False, K)
+            return O.discretize(x, O.extract_uk(x, t, ctrl), tf, const, use_uniform_steps=uniform,
+                                integrator_steps=args.n_sub + 1, processes=cores)
+        impl_kind = "port"
+        what = "oracle/mpc_oracle.py (numpy/scipy restatement; oracle/_ref bytecode not built)"
 
     def step():
         for s in range(S):
-            x, t = O.propagate(Y[s], tf, ctrl, const, False, False, K)
-            u = O.extract_uk(x, t, ctrl)
-            O.discretize(x, u, tf, const, use_uniform_steps=True, integrator_steps=args.n_sub + 1, processes=cores)
+            one_pass(s, True)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -184,18 +229,23 @@ def reference_arm(args):
     val = S * (K - 1) / dt
     # the reference's shipped default (use_uniform_steps=False: quadrature on the 4-8 accepted RK45 steps), once, for the record
     t1 = time.perf_counter()
-    for s in range(S):
-        x, t = O.propagate(Y[s], tf, ctrl, const, False, False, K)
-        O.discretize(x, O.extract_uk(x, t, ctrl), tf, const, use_uniform_steps=False, processes=cores)
-    default_mode = S * (K - 1) / (time.perf_counter() - t1)
-    sample = (f"{S} of {n_sats} satellites x {K-1} intervals per step (propagate + discretize, use_uniform_steps=True, "
-              f"integrator_steps={args.n_sub + 1}), mp.Pool({cores}) per discretize call as the reference does")
+    for s in range(min(S, 4)):
+        one_pass(s, False)
+    default_mode = min(S, 4) * (K - 1) / (time.perf_counter() - t1)
+    sample = (f"{S} of {n_sats} satellites x {K-1} intervals per step; per satellite Simulator.run + extract_uk + "
+              f"Discretizer.discretize (use_uniform_steps=True, integrator_steps={args.n_sub + 1}), mp.Pool({cores}) per "
+              f"discretize call as the reference does; {what}")
+    cfg = workload_config(args)
+    cfg["integrator"] = ("scipy solve_ivp RK45 (rtol 1e-3, atol 1e-6): propagation with max_step 0.001 and dense-output samples; "
+                         f"discretization per interval, Phi and x read off the dense output at {args.n_sub + 1} uniform nodes "
+                         "(use_uniform_steps=True), np.linalg.inv per node, trapezoid rule")
+    cfg["parallelism"] = f"mp.Pool({cores}) over the intervals of one satellite; satellites serial"
     print(json.dumps({
         "impl": "reference", "metric": "discretized intervals/sec", "value": val, "unit": "intervals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": val, "unit": "intervals/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "intervals/s", "cores": cores, "kind": impl_kind, "sample": sample},
         "e2e": {"value": val, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "default_mode_intervals_per_s": default_mode,
         "gpu_launches": 0,
@@ -203,11 +253,129 @@ def reference_arm(args):
 
 
 def workload_config(args):
-    return {"workload": f"{args.sats} satellites x K={args.nodes} nodes ({args.sats * (args.nodes - 1)} intervals) per GPU: "
-                        "propagate (tangential thrust 0.5, no drag/J2) + discretize, BASELINE configs[2]",
+    if getattr(args, "total_sats", 0):
+        wl = (f"{args.total_sats} satellites x K={args.nodes} nodes ({args.total_sats * (args.nodes - 1)} intervals) IN TOTAL, sharded "
+              f"over {args.gpus} GPU(s): propagate (tangential thrust 0.5, no drag/J2) + discretize, BASELINE configs[3]")
+    else:
+        wl = (f"{args.sats} satellites x K={args.nodes} nodes ({args.sats * (args.nodes - 1)} intervals) per GPU: "
+              "propagate (tangential thrust 0.5, no drag/J2) + discretize, BASELINE configs[2]")
+    return {"workload": wl,
             "sats_per_gpu": args.sats, "K": args.nodes, "tf": args.tf, "integrator_steps": args.n_sub + 1,
             "integrator": "fixed-step fourth-order Runge-Kutta-Nystrom (3 stages), one step per two quadrature nodes with a cubic-Hermite midpoint, trapezoid on all integrator_steps nodes", "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": f"satellites sharded over {args.gpus} GPU(s)" + (f", all-gather of the SoA matrices inside the step ({args.gather})" if args.gpus > 1 else "")}
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs 1, 2, 5
+
+def small_configs_record(M, dev, const, with_cpu=True):
+    """BASELINE configs[0], [1], [4] on the same GPU (rank 0, N=1): kernel times on device buffers (CUDA events, mean of 5
+    after 2 warm-ups, the reference's integrator replayed for the propagation), and for config 5 the per-SCP-pass and
+    per-MPC-step wall time through the host API (BatchedSCP: control.py:170-235 for all satellites at once), next to the
+    plain-C port on the same shapes and -- config 5 -- the reference path itself on a 2-satellite sample."""
+    import torch
+    from mpconstellation_b200.scp import BatchedSCP
+    ctrl = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    ad = dict(rtol=1e-3, atol=1e-6, max_step=1e-2)
+
+    def ev_ms(fn, n=5):
+        ts = []
+        for i in range(n + 2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    def wall_ms(fn, n=3):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t0) / n * 1e3
+
+    rec = {}
+    shapes = (("config1", 1, 50, 0.5, "single satellite, K=50 (test_discretizer.py default scenario)"),
+              ("config2", 64, 100, 1.0, "64 satellites x K=100, one SCP linearization pass"),
+              ("config5", 256, 60, 2.0, "256-satellite closed loop: base_res 30, horizon 2 -> K=60, 2 SCP passes per segment"))
+    for name, Ns, Ks, tfs, what in shapes:
+        Ys, _ = make_constellation(Ns)
+        y0 = torch.from_numpy(Ys).to(dev)
+        tfd = torch.full((Ns,), tfs, dtype=torch.float64, device=dev)
+        x, u, _ = M.propagate_batch_device(y0, tfd, ctrl, const, include_drag=False, include_J2=False, T=Ks)
+        r = {"what": what, "satellites": Ns, "K": Ks, "intervals": Ns * (Ks - 1),
+             "propagate_ms": ev_ms(lambda: M.propagate_batch_device(y0, tfd, ctrl, const, include_drag=False, include_J2=False, T=Ks)),
+             "discretize_uniform_ms": ev_ms(lambda: M.discretize_batch_device(x, u, tfd, const, n_sub=100)),
+             "discretize_default_ms": ev_ms(lambda: M.discretize_batch_device(x, u, tfd, const, adaptive=ad)),
+             "pass_uniform_ms": ev_ms(lambda: M.propagate_discretize_device(y0, tfd, ctrl, const, Ks, n_sub_disc=100))}
+        if with_cpu:
+            from oracle import c_oracle as C
+            from oracle.mpc_oracle import OracleConstants
+            oc = OracleConstants(const.MU, const.R_E, const.J2, const.G0, const.ISP, const.S, const.R0, const.RHO)
+            t0 = time.perf_counter()
+            xr, ur, _, _, _ = C.propagate_batch_rk45(Ys, tfs, oc, C.CTRL_TANGENTIAL, (0.5, 0, 0), include_drag=False,
+                                                     include_J2=False, T=Ks)
+            t1 = time.perf_counter()
+            C.discretize_batch(xr, ur, tfs, oc)
+            t2 = time.perf_counter()
+            C.discretize_batch_adaptive(xr, ur, tfs, oc)
+            t3 = time.perf_counter()
+            r["cpu_port_ms"] = {"propagate": (t1 - t0) * 1e3, "discretize_uniform": (t2 - t1) * 1e3,
+                                "discretize_default": (t3 - t2) * 1e3, "cores": C.max_threads()}
+        rec[name] = r
+    # config 5 through the host API, as the closed loop runs it: linearize = propagate + extract_uk + discretize (default
+    # quadrature mode, control.py:187) for all 256 satellites; one MPC step = plan (2 passes) + flight (drag + J2)
+    Ys, _ = make_constellation(256)
+    scp = BatchedSCP(const, base_res=30, tf_horizon=2.0, tf_interval=1.0, n_iterations=2)
+    c5 = rec["config5"]
+    c5["scp_pass_host_ms"] = wall_ms(lambda: scp.linearize(Ys, 2.0, ctrl))
+    scp_u = BatchedSCP(const, base_res=30, tf_horizon=2.0, tf_interval=1.0, n_iterations=2, use_uniform_steps=True)
+    c5["scp_pass_host_uniform_ms"] = wall_ms(lambda: scp_u.linearize(Ys, 2.0, ctrl))
+
+    def mpc_step():
+        s_ = BatchedSCP(const, base_res=30, tf_horizon=2.0, tf_interval=1.0, n_iterations=2)
+        s_.run_segments(Ys, n_segments=1)
+    c5["mpc_step_host_ms"] = wall_ms(mpc_step)
+    c5["mpc_step_note"] = ("one segment of BatchedSCP.run_segments: 2 x (propagate + extract_uk + default-mode discretize) + the "
+                           "flight of the interval with drag + J2, host arrays in and out; the pyomo/ipopt subproblem is not "
+                           "part of this path and is stood in for by hold_reference_solver (no solve time on either side)")
+    if with_cpu:
+        # the reference path on the same shape (control.py:180-188,227 per satellite, serial over satellites), 2-satellite sample
+        try:
+            import contextlib
+            import io
+            import warnings
+            warnings.filterwarnings("ignore")
+            from oracle import refshim
+            R = refshim.load_reference()
+            hub = R.Satellite(HUBBLE[0:3].copy(), HUBBLE[3:6].copy(), float(HUBBLE[6]))
+            scale = R.SatelliteScale(sat=hub)
+            rconst = scale.get_normalized_constants()
+            rc = R.ConstantTangentialThrustController(tangential_thrust=0.5)
+            t0 = time.perf_counter()
+            for s in range(2):
+                yd = scale.redim_state(Ys[s])
+                for _ in range(2):                                   # SCPn_iterations (control.py:166)
+                    sat = R.Satellite(yd[0:3], yd[3:6], float(yd[6]))
+                    sim = R.Simulator(sats=[sat], controller=rc, scale=scale, base_res=30, include_drag=False, include_J2=False)
+                    sim.run(tf=2.0)
+                    xx, tt = sim.sim_data[sat.id], sim.sim_time[sat.id]
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        R.Discretizer(rconst).discretize(R.Simulator.satellite_dynamics, xx, R.Discretizer.extract_uk(xx, tt, rc), 2.0)
+                sat = R.Satellite(yd[0:3], yd[3:6], float(yd[6]))
+                R.Simulator(sats=[sat], controller=rc, scale=scale, base_res=100).run(tf=1.0)   # the flight, drag + J2
+            per_sat = (time.perf_counter() - t0) / 2
+            c5["reference_path"] = {"ms_per_satellite_per_mpc_step": per_sat * 1e3, "ms_per_mpc_step_256_satellites": per_sat * 256e3,
+                                    "sample": "2 satellites, unmodified reference (oracle/_ref bytecode), serial over satellites as "
+                                              "Simulator.run_segment / OptimalController.update are, mp.Pool per discretize call; "
+                                              "subproblem solve excluded on both sides", "cores": os.cpu_count()}
+            c5["mpc_step_vs_reference_path"] = per_sat * 256e3 / c5["mpc_step_host_ms"]
+        except Exception as exc:        # bytecode not built on this box
+            c5["reference_path"] = {"unavailable": str(exc)}
+    return rec
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -234,10 +402,16 @@ def gpu_arm(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
-    N, K, tf, n_sub = args.sats, args.nodes, args.tf, args.n_sub
+    from mpconstellation_b200 import distributed as D
+    K, tf, n_sub = args.nodes, args.tf, args.n_sub
+    # weak scaling: args.sats satellites per rank; strong scaling (--total-sats): one batch sharded over the ranks
+    N_total = args.total_sats if args.total_sats else args.sats * world
+    s0, s1 = D.shard_range(N_total, rank, world)
+    N = s1 - s0
     n_int = N * (K - 1)
-    Y, const = make_constellation(N * world)
-    Y = Y[rank * N:(rank + 1) * N]
+    n_int_total = N_total * (K - 1)
+    Y, const = make_constellation(N_total)
+    Y = np.ascontiguousarray(Y[s0:s1])
     ctrl = M.ConstantTangentialThrustController(tangential_thrust=0.5)
 
     # ---- device-resident step --------------------------------------------------------------------
@@ -253,11 +427,13 @@ def gpu_arm(args):
     fused = None
     gather_mode = "none"
     if world > 1:
-        from mpconstellation_b200 import distributed as D
         gather_mode = args.gather
+        if gather_mode == "nccl" and N_total % world:
+            raise SystemExit("--gather nccl needs equal shards (total satellites divisible by the number of ranks)")
         if gather_mode == "fused":
             try:
-                fused = D.FusedGather(N * world, K, device=dev, mode=args.fused_mode, chunk_waves=args.chunk_waves)
+                fused = D.FusedGather(N_total, K, device=dev, mode=args.fused_mode, chunk_waves=args.chunk_waves,
+                                      layout=args.layout)
             except Exception as exc:            # no peer mapping on this box: fall back to the NCCL baseline
                 if rank == 0:
                     print(f"[bench] symmetric memory unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
@@ -272,6 +448,8 @@ def gpu_arm(args):
     # --no-overlap runs the two kernels back to back (what the ncu launch list under profiles/ serialises anyway).
     overlap = not args.no_overlap and (world == 1 or (fused is not None and fused.overlap_ok and
                                                       args.fused_mode in ("unicast", "multicast")))
+    if N == 0:
+        raise SystemExit("a rank without satellites: use fewer GPUs for this --total-sats")
 
     def step():
         if overlap and world == 1:
@@ -372,7 +550,7 @@ def gpu_arm(args):
         disc_total, prop_total = float(np.sum(disc_ms)), float(np.sum(prop_ms))
     prop_ms_avg = prop_total / args.steps
     ms_per_step = total_ms / args.steps
-    value = world * n_int / (ms_per_step * 1e-3)
+    value = n_int_total / (ms_per_step * 1e-3)
     disc_ms_avg = disc_total / args.steps
 
     # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside the timed region) --
@@ -404,15 +582,20 @@ def gpu_arm(args):
     if world == 1:
         dev_cols = out[:, :K - 1]
     elif fused is not None:
-        dev_cols = fused.buf[:, rank * n_int:rank * n_int + K - 1]
+        # the K-1 intervals of this rank's first satellite, wherever the gathered layout puts them
+        dev_cols = (fused.buf[:, s0:s0 + (K - 1) * N_total:N_total] if fused.layout == "kmajor"
+                    else fused.buf[:, s0 * (K - 1):(s0 + 1) * (K - 1)])
     else:
         dev_cols = local_out[:, :K - 1]
     same = bool(np.array_equal(out_h[:, :K - 1], dev_cols.cpu().numpy()))
     gathered_ok = None
     if fused is not None:
         # every rank must hold every other rank's block: compare a column of each peer block with its owner
-        probe = torch.stack([fused.buf[:, r * n_int + 7] for r in range(world)])
-        mine = fused.buf[:, rank * n_int + 7].clone()
+        # (interval k = 7 of the first satellite of every rank)
+        first = [D.shard_range(N_total, r, world)[0] for r in range(world)]
+        colof = (lambda sg: 7 * N_total + sg) if fused.layout == "kmajor" else (lambda sg: sg * (K - 1) + 7)
+        probe = torch.stack([fused.buf[:, colof(first[r])] for r in range(world)])
+        mine = fused.buf[:, colof(s0)].clone()
         allm = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allm, mine)
         gathered_ok = bool(all(torch.equal(probe[r], allm[r]) for r in range(world)))
@@ -429,20 +612,26 @@ def gpu_arm(args):
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     fl = flops_per_interval(n_sub)
     achieved_tflops = fl * n_int / (disc_ms_avg * 1e-3) / 1e12
+    counters = kernel_counters()
+    is_cfg3 = (N, K, n_sub, world) == (4096, 200, 100, 1)
+    pair_ctr = counters.get("discretize_pair_kernel", {}) if is_cfg3 else {}
+    dflt_ctr = counters.get("discretize_default_kernel", {}) if is_cfg3 else {}
     # the CPU baseline is a rank-0, N=1 measurement (under torchrun OMP_NUM_THREADS=1 would make it a one-core number)
     cpu = cpu_port_baseline(N, K, tf, n_sub) if (world == 1 and not args.no_cpu_baseline) else None
     line = {
         "metric": "discretized intervals/sec", "value": value, "unit": "intervals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-        "e2e": {"value": world * n_int / e2e_s, "unit": "intervals/s", "ms_per_step": e2e_s * 1e3,
+        "scaling": "strong" if args.total_sats else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": n_int_total / e2e_s, "unit": "intervals/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(y0_h.nbytes + N * 8),
                 "d2h_bytes_per_step": int(out_h.nbytes + y_h.nbytes + u_h.nbytes + n_int * 4),
                 "api": "mpconstellation_b200.propagate_discretize (C-ABI mpc_propagate_discretize_host), pinned host buffers",
                 "host_cpus_rank0": len(cpus),
                 "matches_device_path": same},
         "gather": {"mode": gather_mode + (":" + args.fused_mode if fused is not None else ""), "verified": gathered_ok,
-                   "bytes_received_per_rank_per_step": int((world - 1) * n_int * 8 * (98 if fused is not None and fused.skip_const else 105)),
+                   "layout": fused.layout if fused is not None else "rank blocks",
+                   "bytes_received_per_rank_per_step": int((n_int_total - n_int) * 8 * (98 if fused is not None and fused.skip_const else 105)),
                    "note": "rows 42..48 of the SoA result (last row of A_k, constants) are written once by the owner and never sent"
                            if fused is not None and fused.skip_const else None} if world > 1 else None,
         "gpu_launches": int(launches),
@@ -470,7 +659,8 @@ def gpu_arm(args):
                      # dram__bytes_read.sum + dram__bytes_write.sum of one full-batch launch, ncu --set full capture of
                      # this command (profiles/r01_n_discretize_pair_windows.txt, third kernel: 65.80 + 628.39 MB);
                      # algorithmic = 944 B x 815,104 = 769.5 MB (the 13 input doubles are shared by neighbours in L2)
-                     "traffic": 694.19e6 if (N, K, n_sub) == (4096, 200, 100) else None,
+                     # committed in profiles/kernel_counters.json together with the name of the summary it was read from
+                     "traffic": pair_ctr.get("dram_bytes"), "traffic_source": pair_ctr.get("source"),
                      "peak_source": "DFMA-chain microbenchmark (mpc_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
                      "peak_nominal": FP64_NOMINAL_TFLOPS, "flop_per_interval": fl,
                      # SURVEY.md 8(d) counts the reference formulation (plain RK4 on 42+7 unknowns, dense Phi^-1
@@ -487,8 +677,25 @@ def gpu_arm(args):
                              "unit": "GB/s", "peak_source": hbm_src, "bytes_per_interval": bytes_per_interval()}},
         "clocks": clocks,
     }
+    if adaptive_ms is not None:
+        # the reference's DEFAULT quadrature mode (what control.py:187 runs): its own roofline block.  The executed flop
+        # count depends on the data (3-4 accepted RK45 steps per interval here) and is the ncu count of this workload
+        fpi, ipi = dflt_ctr.get("flop_per_interval"), dflt_ctr.get("fp64_instr_per_interval")
+        line["roofline_default_mode"] = {
+            "kernel": "mpc::discretize_default_kernel", "bound": "fp64", "discretize_ms": adaptive_ms,
+            "intervals_per_s": n_int / (adaptive_ms * 1e-3), "nodes_per_interval": list(adaptive_nodes),
+            "flop_per_interval": fpi, "flop_source": dflt_ctr.get("source"),
+            "achieved": None if fpi is None else fpi * n_int / (adaptive_ms * 1e-3) / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": None if fpi is None else fpi * n_int / (adaptive_ms * 1e-3) / 1e12 / peak_tflops,
+            "fp64_pipe_frac": None if ipi is None else ipi * n_int / (adaptive_ms * 1e-3) / (peak_tflops * 1e12 / 2),
+            "traffic": dflt_ctr.get("dram_bytes"),
+            "note": "use_uniform_steps=False: scipy's RK45 controller replayed per interval, trapezoid on the accepted steps"}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+        line["vs_cpu_port"] = {"device": value / cpu["value"], "e2e": line["e2e"]["value"] / cpu["value"],
+                               "note": "this line's value and e2e over cpu_baseline.value (oracle/mpc_oracle.c, OpenMP, all host cores)"}
+    if world == 1 and not args.no_configs:
+        line["configs"] = small_configs_record(M, dev, const, not args.no_cpu_baseline)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -509,7 +716,11 @@ def main():
     ap.add_argument("--chunk-waves", dest="chunk_waves", type=int, default=1, help="--fused-mode push: kernel waves per pushed chunk")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: all-gather by peer stores from inside the kernel (fused) or chunked NCCL all-gather")
-    ap.add_argument("--ref-sats", dest="ref_sats", type=int, default=2, help="satellites per step of the reference arm")
+    ap.add_argument("--ref-sats", dest="ref_sats", type=int, default=8, help="satellites per step of the reference arm")
+    ap.add_argument("--total-sats", dest="total_sats", type=int, default=0,
+                    help="strong scaling: this many satellites in total, sharded over the ranks (5025 = BASELINE configs[3])")
+    ap.add_argument("--no-configs", dest="no_configs", action="store_true", help="skip the configs 1/2/5 record (N=1)")
+    ap.add_argument("--layout", default=None, choices=["satmajor", "kmajor"], help="gathered layout of the fused all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true",
                     help="run propagate and discretize back to back instead of overlapped")

@@ -264,6 +264,37 @@ int mpc_propagate_discretize_multi(mpc_ctx *ctx, const double *y0, const double 
                                    int n_windows, void *stream);
 
 /*
+ * The fused all-gather with its options passed per call (the two entry points above read the process-wide knobs of
+ * mpc_set_gather_tuning), and with a choice of the gathered layout.  Every destination buffer is [105][n_sats_total (K-1)]:
+ *   MPC_LAYOUT_SAT_MAJOR  column = (sat_offset + s) (K-1) + k      (what mpc_discretize_batch writes; per-satellite blocks)
+ *   MPC_LAYOUT_K_MAJOR    column = k n_sats_total + sat_offset + s  (interval k of ALL satellites adjacent)
+ * n_sats_total: satellites of all ranks, sat_offset: first satellite of this rank (s = 0..n_sats-1 are this call's).
+ * In the k-major layout a window of k of the overlapped pass stores whole runs of n_sats consecutive columns per row --
+ * full 256-byte lines per warp, also to the peers -- where the satellite-major layout gives 13-column fragments; that is
+ * what lets the propagation hide behind the discretization at 4 and 8 GPUs as well.  The consumer indexes elements
+ * (optimizer.py:327-339), so the layout is a stride, not a copy (GatheredView in the Python package).
+ * skip_const / stagger_phases: as mpc_set_gather_tuning.  Fixed-step (two-node-step) kernel only.
+ */
+#define MPC_LAYOUT_SAT_MAJOR 0
+#define MPC_LAYOUT_K_MAJOR 1
+typedef struct mpc_gather_opts {
+    int32_t layout;         /* MPC_LAYOUT_* */
+    int32_t skip_const;     /* 0, 1, 2: see mpc_set_gather_tuning */
+    int32_t stagger_phases; /* 0 = off */
+    int32_t reserved;
+    int64_t n_sats_total;
+    int64_t sat_offset;
+} mpc_gather_opts;
+int mpc_discretize_batch_gather(const double *x, const double *u, const double *tf, const mpc_params *p, int n_sats,
+                                int K, int n_sub, double *const *dst, int n_dst, const mpc_gather_opts *g,
+                                int32_t *status, void *stream);
+int mpc_propagate_discretize_gather(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                    const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                    int n_sub_prop, int n_sub_disc, double *x, double *u, double *const *dst, int n_dst,
+                                    const mpc_gather_opts *g, int32_t *status_prop, int32_t *status_disc, int n_windows,
+                                    void *stream);
+
+/*
  * All-gather of the discretized matrices by the COPY ENGINES, overlapped with the kernel: the batch is discretized
  * in chunks of `chunk_waves` full waves of the kernel into dst[0] (local); as soon as a chunk is done its columns
  * are pushed to dst[1..n_dst-1] (peer-mapped buffers of the other ranks, same layout) by cudaMemcpy2DAsync on one

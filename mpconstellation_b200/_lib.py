@@ -43,6 +43,14 @@ class MpcController(ctypes.Structure):
                 ("table", ctypes.c_void_p), ("end_tau_per_sat", ctypes.c_void_p)]
 
 
+class MpcGatherOpts(ctypes.Structure):
+    _fields_ = [("layout", ctypes.c_int32), ("skip_const", ctypes.c_int32), ("stagger_phases", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("n_sats_total", ctypes.c_int64), ("sat_offset", ctypes.c_int64)]
+
+
+LAYOUT_SAT_MAJOR, LAYOUT_K_MAJOR = 0, 1
+
+
 class MpcError(RuntimeError):
     def __init__(self, code, text):
         super().__init__(f"libmpc_b200 error {code}: {text}")
@@ -113,6 +121,9 @@ def lib():
     L.mpc_propagate_discretize_host.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, _DP]
     L.mpc_propagate_discretize.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, i64, i64, _DP, _DP, i, vp]
     L.mpc_propagate_discretize_multi.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, ctypes.POINTER(ctypes.c_void_p), i, i64, i64, _DP, _DP, i, vp]
+    pg = ctypes.POINTER(MpcGatherOpts)
+    L.mpc_discretize_batch_gather.argtypes = [_DP, _DP, _DP, pp, i, i, i, ctypes.POINTER(ctypes.c_void_p), i, pg, _DP, vp]
+    L.mpc_propagate_discretize_gather.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, ctypes.POINTER(ctypes.c_void_p), i, pg, _DP, _DP, i, vp]
     L.mpc_discretize_batch_push.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, ctypes.POINTER(ctypes.c_void_p), i, i64, i64, _DP, i, i, vp]
     L.mpc_fill_const_rows.argtypes = [_DP, i64, vp]
     L.mpc_dynamics_jacobian.argtypes = [_DP, i64, i64, i, i, _DP, _DP, _DP, vp]
@@ -123,7 +134,7 @@ def lib():
     L.mpc_set_gather_tuning.restype = i
     L.mpc_set_tuning.argtypes = [i]
     L.mpc_set_tuning.restype = i
-    for name in ("mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host", "mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
+    for name in ("mpc_discretize_batch_gather", "mpc_propagate_discretize_gather", "mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host", "mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
                  "mpc_discretize_batch_adaptive", "mpc_discretize_batch_adaptive_host",
                  "mpc_discretize_batch_ugrid", "mpc_discretize_batch_ugrid_host",
                  "mpc_ctx_create", "mpc_ctx_destroy", "mpc_discretize_batch_host", "mpc_propagate_batch_host",
@@ -137,7 +148,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "mpc_version", "mpc_last_error", "mpc_device_count", "mpc_device_info", "mpc_launch_count",
     "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_discretize_batch_ugrid", "mpc_propagate_batch",
-    "mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host",
+    "mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host", "mpc_discretize_batch_gather", "mpc_propagate_discretize_gather",
     "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
     "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_discretize_batch_ugrid_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host", "mpc_propagate_discretize", "mpc_propagate_discretize_multi",
     "mpc_constraint_terms", "mpc_constraint_terms_host", "mpc_discretize_batch_push", "mpc_fill_const_rows",

@@ -350,14 +350,16 @@ def propagate_batch_device(y0, tf, controller, const, include_drag=True, include
 def propagate_discretize_device(y0, tf, controller, const, T, prop_drag=False, prop_J2=False, disc_J2=False,
                                 n_sub_prop=None, n_sub_disc=100, y=None, u_out=None, out=None, out_pitch=None,
                                 out_offset=0, status_prop=None, status_disc=None, n_windows=0, extra_dst=None,
-                                out_ptr=None):
+                                out_ptr=None, gather=None):
     """Device form of propagate_discretize: one SCP linearization pass (control.py:180-188) on CUDA tensors, enqueued on
     torch's current stream, with the propagation overlapped with the discretization (mpc_propagate_discretize: the
     intervals are discretized window by window along k as the propagation publishes its progress).  Bit-identical to
     propagate_batch_device followed by discretize_batch_device.  y0 [N,7], tf [N] float64 CUDA tensors; K = T.
     `extra_dst`: further [105, pitch] buffers (tensors or raw peer-mapped addresses) every result is also stored to
     (total 1, 2, 4 or 8: the fused all-gather); `out_ptr`: raw address used instead of out.data_ptr() (a multicast
-    mapping of `out`).  Returns (out [105, pitch], y [N,7,T], u [N,3,T], status_prop [N], status_disc [N*(T-1)])."""
+    mapping of `out`); `gather`: an _lib.MpcGatherOpts -- layout (satellite- or k-major), n_sats_total, sat_offset and the
+    gather options for this call (then out_pitch / out_offset are implied).
+    Returns (out [105, pitch], y [N,7,T], u [N,3,T], status_prop [N], status_disc [N*(T-1)])."""
     torch = _torch()
     N = y0.shape[0]
     T = int(T)
@@ -394,11 +396,18 @@ def propagate_discretize_device(y0, tf, controller, const, T, prop_drag=False, p
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
     dev_i = dev.index if dev.index is not None else torch.cuda.current_device()
     with _lock(dev_i):   # the ctx owns the internal streams / progress words of the overlapped pass
-        _lib.check(_lib.lib().mpc_propagate_discretize_multi(
-            _ctx(dev_i), y0.data_ptr(), tf.data_ptr(),
-            ctypes.byref(pp), ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop), int(n_sub_disc), y.data_ptr(),
-            u_out.data_ptr(), arr, len(ptrs), pitch, int(out_offset), status_prop.data_ptr(), status_disc.data_ptr(),
-            int(n_windows), cur.cuda_stream))
+        if gather is not None:      # fused all-gather with per-call options / layout (mpc_propagate_discretize_gather)
+            _lib.check(_lib.lib().mpc_propagate_discretize_gather(
+                _ctx(dev_i), y0.data_ptr(), tf.data_ptr(),
+                ctypes.byref(pp), ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop), int(n_sub_disc), y.data_ptr(),
+                u_out.data_ptr(), arr, len(ptrs), ctypes.byref(gather), status_prop.data_ptr(), status_disc.data_ptr(),
+                int(n_windows), cur.cuda_stream))
+        else:
+            _lib.check(_lib.lib().mpc_propagate_discretize_multi(
+                _ctx(dev_i), y0.data_ptr(), tf.data_ptr(),
+                ctypes.byref(pp), ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop), int(n_sub_disc), y.data_ptr(),
+                u_out.data_ptr(), arr, len(ptrs), pitch, int(out_offset), status_prop.data_ptr(), status_disc.data_ptr(),
+                int(n_windows), cur.cuda_stream))
     for t_ in (tab_dev, et_dev):
         if t_ is not None:
             t_.record_stream(cur)

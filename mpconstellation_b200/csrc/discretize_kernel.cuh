@@ -274,7 +274,18 @@ struct DstTab {  // destination buffers of the (optionally multi-destination) So
     int stagger_phases;        // > 1: CTAs of the first wave start with a delay of (blockIdx % phases)/phases of one
     int first_wave_ctas;       //      interval's run time, so that the store phases of the CTAs sharing the NVLink
     long long stagger_cycles;  //      egress do not coincide; stagger_cycles = run time of one interval in SM clocks
+    // k-major gathered layout (0 = the default, satellite-major: column = offset + s (K-1) + k).  km_ntot > 0: column =
+    // k * km_ntot + km_soff + s, with km_ntot the satellites of ALL ranks and km_soff the first satellite of this one:
+    // the intervals k of all satellites are adjacent, so a window of k (the overlapped pass) writes whole rows of
+    // consecutive columns -- whole 256-byte lines per warp, also to the peers -- instead of 13-column fragments.
+    long long km_ntot, km_soff;
 };
+
+// column of interval (s, k) in the SoA output
+__device__ __forceinline__ long long out_col(const DstTab &d, long long offset, int s, int k, int K)
+{
+    return d.km_ntot ? (long long)k * d.km_ntot + d.km_soff + s : offset + (long long)s * (K - 1) + k;
+}
 
 // Quadrature-node accumulation shared by the fixed-step and the adaptive kernel:
 //   acc += w * Phi^-1 [Duf, Sigma, xi']   and   acc1 += w*lambda+ * Phi^-1 Duf      (ws = w * lambda+)
@@ -656,7 +667,7 @@ __device__ __forceinline__ void discretize_thread(const double *__restrict__ x, 
     // ---- epilogue: left-multiply by Phi_end, undo D, scale by the step, store SoA -----------------
     // B and xi carry tf (scale tf h = hs), Sigma does not (h); the accumulated Sigma and xi vectors carry the factor hs
     const double ihs = 1.0 / hs;
-    const int nonfinite = epilogue_store<BLOCK, NDST>(acc, pr, pv, hs, h * ihs, 1.0, dst, pitch, offset + gid, hs, ihs);
+    const int nonfinite = epilogue_store<BLOCK, NDST>(acc, pr, pv, hs, h * ihs, 1.0, dst, pitch, out_col(dst, offset, s, k, K), hs, ihs);
     if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : 0);
 }
 #undef ACC

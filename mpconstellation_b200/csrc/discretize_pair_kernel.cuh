@@ -138,8 +138,17 @@ discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ 
     }
     volatile double *acc = acc_smem + threadIdx.x;
 
-    const int s = (int)(tid / kc);
-    const int k = k0 + (int)(tid - (long long)s * kc);
+    // thread -> (satellite, interval): consecutive threads walk the direction in which the output columns are adjacent
+    // (k for the satellite-major layout, the satellite for the k-major one), so that every store of a warp is one line
+    int s, k;
+    if (dst.km_ntot) {
+        const int kk = (int)(tid / n_sats);
+        s = (int)(tid - (long long)kk * n_sats);
+        k = k0 + kk;
+    } else {
+        s = (int)(tid / kc);
+        k = k0 + (int)(tid - (long long)s * kc);
+    }
     const long long gid = (long long)s * (K - 1) + k;
     const double tf = tf_arr[s];
     const double *xs = x + ((long long)s * 7) * K + k;
@@ -339,7 +348,7 @@ discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ 
     // B and xi carry tf (tf h = hn per panel), Sigma does not (h); the accumulated Sigma / xi vectors carry the factor H,
     // the accumulated Duf vectors do not; cs / vs undo D = diag(I, H I, 1)
     const double iH = 1.0 / H;
-    const int nonfinite = epilogue_store<BLOCK, NDST>(acc, pr, pv, hn, h * iH, hn * iH, dst, pitch, offset + gid, H, iH);
+    const int nonfinite = epilogue_store<BLOCK, NDST>(acc, pr, pv, hn, h * iH, hn * iH, dst, pitch, out_col(dst, offset, s, k, K), H, iH);
     if (status) status[gid] = bad ? 1 : (nonfinite ? 2 : 0);
 }
 #undef ACC

@@ -71,6 +71,18 @@ mpc::PropParams prop_params(const mpc_params *p)
 
 std::atomic<int> g_tuning{0};
 std::atomic<int> g_gather_skip_const{0}, g_gather_stagger{0};   // mpc_set_gather_tuning
+// Options of one mpc_*_gather call (layout, what to send, how to start), visible to the launchers for its duration --
+// per call and per thread, unlike the process-wide knobs of mpc_set_gather_tuning (kept for the older entry points).
+struct GatherCall {
+    bool active = false;
+    int skip_const = 0, stagger = 0;
+    long long km_ntot = 0, km_soff = 0;
+};
+thread_local GatherCall g_gather;
+struct GatherScope {
+    explicit GatherScope(const GatherCall &g) { g_gather = g; }
+    ~GatherScope() { g_gather = GatherCall(); }
+};
 thread_local int g_ucols = 0;  // columns of u when it lives on its own grid (set by the *_ugrid entry points)
 struct UcolsScope {            // routes the launchers to the general-grid input hold for the duration of one call
     explicit UcolsScope(int n) { g_ucols = n; }
@@ -365,8 +377,12 @@ int disc_device(const double *x, const double *u, const double *tf, const mpc_pa
     if (n_int == 0) return MPC_SUCCESS;
     mpc::DstTab tab{};
     for (int d = 0; d < mpc::kMaxDst; ++d) tab.p[d] = (d < n_dst) ? dst[d] : nullptr;
-    tab.skip_const = g_gather_skip_const.load(std::memory_order_relaxed);
-    tab.stagger_phases = g_gather_stagger.load(std::memory_order_relaxed);
+    tab.skip_const = g_gather.active ? g_gather.skip_const : g_gather_skip_const.load(std::memory_order_relaxed);
+    tab.stagger_phases = g_gather.active ? g_gather.stagger : g_gather_stagger.load(std::memory_order_relaxed);
+    tab.km_ntot = g_gather.km_ntot;
+    tab.km_soff = g_gather.km_soff;
+    if (tab.km_ntot && (p->include_drag || g_ucols > 0 || !g_pair.load(std::memory_order_relaxed)))
+        return fail(MPC_E_UNSUPPORTED, "the k-major layout is implemented by the two-node-step kernel only");
     if (tab.stagger_phases > 1) {
         int dev = 0, sms = 148;
         CUDA_TRY(cudaGetDevice(&dev));
@@ -1191,8 +1207,10 @@ int prop_disc_overlapped(mpc_ctx *ctx, const double *y0, const double *tf, const
     const mpc::DiscParams P = disc_params(p_disc);
     mpc::DstTab tab{};
     for (int d = 0; d < mpc::kMaxDst; ++d) tab.p[d] = (d < n_dst) ? dst[d] : nullptr;
-    tab.skip_const = g_gather_skip_const.load(std::memory_order_relaxed);
-    const int stagger = g_gather_stagger.load(std::memory_order_relaxed);
+    tab.skip_const = g_gather.active ? g_gather.skip_const : g_gather_skip_const.load(std::memory_order_relaxed);
+    const int stagger = g_gather.active ? g_gather.stagger : g_gather_stagger.load(std::memory_order_relaxed);
+    tab.km_ntot = g_gather.km_ntot;
+    tab.km_soff = g_gather.km_soff;
     for (int b = 0; b < nw; ++b) {
         cudaStream_t sw = ctx->s_win[b & 1];
         const int k0 = b * seg, kc = std::min(seg, K - 1 - k0);
@@ -1240,6 +1258,57 @@ extern "C" int mpc_propagate_discretize_multi(mpc_ctx *ctx, const double *y0, co
 {
     return prop_disc_overlapped(ctx, y0, tf, p_prop, p_disc, ctrl, n_sats, T, n_sub_prop, n_sub_disc, x, u, dst, n_dst,
                                 out_pitch, out_offset, status_prop, status_disc, n_windows, (cudaStream_t)stream);
+}
+
+namespace {
+
+int gather_call(const mpc_gather_opts *g, int n_sats, int K, GatherCall &gc, int64_t &pitch, int64_t &offset)
+{
+    if (!g) return fail(MPC_E_INVALID, "null gather options");
+    if (g->layout != MPC_LAYOUT_SAT_MAJOR && g->layout != MPC_LAYOUT_K_MAJOR) return fail(MPC_E_INVALID, "unknown layout %d", g->layout);
+    if (g->skip_const < 0 || g->skip_const > 2 || g->stagger_phases < 0 || g->stagger_phases > 64)
+        return fail(MPC_E_INVALID, "bad gather options (%d, %d)", g->skip_const, g->stagger_phases);
+    if (g->sat_offset < 0 || g->n_sats_total < g->sat_offset + n_sats)
+        return fail(MPC_E_INVALID, "n_sats_total / sat_offset do not hold this rank's satellites");
+    gc.active = true;
+    gc.skip_const = g->skip_const;
+    gc.stagger = g->stagger_phases;
+    gc.km_ntot = (g->layout == MPC_LAYOUT_K_MAJOR) ? g->n_sats_total : 0;
+    gc.km_soff = (g->layout == MPC_LAYOUT_K_MAJOR) ? g->sat_offset : 0;
+    pitch = g->n_sats_total * (int64_t)(K - 1);
+    offset = g->sat_offset * (int64_t)(K - 1);
+    return MPC_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" int mpc_discretize_batch_gather(const double *x, const double *u, const double *tf, const mpc_params *p,
+                                           int n_sats, int K, int n_sub, double *const *dst, int n_dst,
+                                           const mpc_gather_opts *g, int32_t *status, void *stream)
+{
+    if (K < 2) return fail(MPC_E_INVALID, "need K >= 2");
+    GatherCall gc;
+    int64_t pitch = 0, offset = 0;
+    int rc = gather_call(g, n_sats, K, gc, pitch, offset);
+    if (rc) return rc;
+    GatherScope scope(gc);
+    return disc_device(x, u, tf, p, n_sats, K, n_sub, dst, n_dst, pitch, offset, status, (cudaStream_t)stream);
+}
+
+extern "C" int mpc_propagate_discretize_gather(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                               const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                               int n_sub_prop, int n_sub_disc, double *x, double *u, double *const *dst,
+                                               int n_dst, const mpc_gather_opts *g, int32_t *status_prop,
+                                               int32_t *status_disc, int n_windows, void *stream)
+{
+    if (T < 2) return fail(MPC_E_INVALID, "need T >= 2");
+    GatherCall gc;
+    int64_t pitch = 0, offset = 0;
+    int rc = gather_call(g, n_sats, T, gc, pitch, offset);
+    if (rc) return rc;
+    GatherScope scope(gc);
+    return prop_disc_overlapped(ctx, y0, tf, p_prop, p_disc, ctrl, n_sats, T, n_sub_prop, n_sub_disc, x, u, dst, n_dst, pitch,
+                                offset, status_prop, status_disc, n_windows, (cudaStream_t)stream);
 }
 
 extern "C" {

@@ -43,8 +43,9 @@ def _np(a):
 class GatheredView:
     """Per-satellite access to a gathered SoA buffer.
 
-    layout "global":  buf[105, n_sats*(K-1)]            (FusedGather)
-    layout "rank":    buf[world, 105, per*(K-1)]        (NCCL all-gather of equal rank blocks)
+    layout "global":  buf[105, n_sats*(K-1)], column = s (K-1) + k     (FusedGather, satellite-major)
+    layout "kmajor":  buf[105, n_sats*(K-1)], column = k n_sats + s     (FusedGather, k-major: a strided view per satellite)
+    layout "rank":    buf[world, 105, per*(K-1)]                        (NCCL all-gather of equal rank blocks)
     """
 
     def __init__(self, buf, n_sats, K, world, layout="global"):
@@ -57,6 +58,8 @@ class GatheredView:
         n = self.K - 1
         if self.layout == "global":
             return _np(self.buf[:, s * n:(s + 1) * n])
+        if self.layout == "kmajor":
+            return _np(self.buf[:, s:s + n * self.n_sats:self.n_sats])
         r, ls = s // self.per, s % self.per
         return _np(self.buf[r][:, ls * n:(ls + 1) * n])
 
@@ -81,7 +84,7 @@ class FusedGather:
     """All-gather of the discretized matrices by peer stores from inside the discretization kernel."""
 
     def __init__(self, n_sats_total, K, group=None, device=None, mode="unicast", chunk_waves=1, skip_const=True,
-                 stagger=None):
+                 stagger=None, layout=None):
         """mode "unicast": one peer-mapped store per destination rank (works on any P2P-capable box);
         mode "multicast": one store to the NVSwitch multicast address of the symmetric buffer, replicated by the
         switch to every rank (NVLS) -- 1/world of the SM store instructions and of the egress traffic;
@@ -90,7 +93,10 @@ class FusedGather:
         and no store-queue stalls go into the exchange, and the structurally constant rows are not sent;
         mode "pushk": the same pipeline with a small highest-priority copy kernel per chunk instead of the copy engines.
         skip_const: rows 42..48 (the last row of A_k, constants 0..0 1) are written once into every buffer here and
-        never sent again (6.7 % less NVLink traffic).  stagger: see mpc_set_gather_tuning."""
+        never sent again (6.7 % less NVLink traffic).  stagger: see mpc_set_gather_tuning.
+        layout: "satmajor" (column = s (K-1) + k, per-satellite blocks) or "kmajor" (column = k N + s): in the k-major
+        layout a k-window of the overlapped pass stores whole runs of consecutive columns, so the propagation can hide
+        behind the discretization at any world size (satellite-major: world <= 2 only).  Default: kmajor for world > 2."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -125,7 +131,12 @@ class FusedGather:
             self.handle.barrier()
         if mode in ("push", "pushk"):
             self.peers = [ptrs[self.rank]] + [ptrs[r] for r in order[1:]]
-        self.overlap_ok = self.world <= 2      # see propagate_discretize
+        self.layout = layout if layout is not None else ("kmajor" if self.world > 2 else "satmajor")
+        if self.layout not in ("satmajor", "kmajor"):
+            raise ValueError(f"unknown layout {self.layout!r}")
+        if self.layout == "kmajor" and mode in ("push", "pushk"):
+            raise ValueError("the push modes copy per-satellite column blocks: satellite-major layout only")
+        self.overlap_ok = self.world <= 2 or self.layout == "kmajor"     # see propagate_discretize
         self.s0, self.s1 = shard_range(n_sats_total, self.rank, self.world)
         self.status = torch.zeros(max(1, (self.s1 - self.s0) * (K - 1)), dtype=torch.int32, device=self.device)
 
@@ -146,15 +157,7 @@ class FusedGather:
         from . import batch
         assert x.shape[0] == self.s1 - self.s0 and x.shape[2] == self.K
         self._pre_barrier(pre_barrier)
-        tuned = self.mode not in ("push", "pushk") and (self.skip_const or self.stagger > 1)
-        if tuned:
-            _lib.check(_lib.lib().mpc_set_gather_tuning((2 if self.mode == "multicast" else 1) if self.skip_const else 0,
-                                                        self.stagger))
-        try:
-            self._launch(x, u, tf, const, include_J2, n_sub)
-        finally:
-            if tuned:
-                _lib.check(_lib.lib().mpc_set_gather_tuning(0, 0))
+        self._launch(x, u, tf, const, include_J2, n_sub)
         if barrier:
             self.handle.barrier()
         return self.buf
@@ -162,11 +165,13 @@ class FusedGather:
     def propagate_discretize(self, y0, tf, controller, const, include_J2=False, n_sub_prop=None, n_sub=100, y=None,
                              u_out=None, status_prop=None, barrier=True, n_windows=0, pre_barrier=True):
         """One SCP linearization pass of this rank's shard with the all-gather fused in AND the propagation hidden
-        behind the discretization (`mpc_propagate_discretize_multi`): y0 [n_local,7], tf [n_local] CUDA float64.
-        Modes "unicast" and "multicast" at world <= 2; the push modes and larger worlds keep the two-kernel sequence:
-        a window stores runs of ~13 columns per row and satellite, fine for HBM and for one peer, but with 7 peers the
-        step is NVLink-ingress bound and the fragmented peer stores cost more than the hidden propagation buys
-        (8 x B200: 7.77 ms back to back, 13.8 ms windowed; 2 x B200: 3.95 -> 3.70 ms; profiles/r01_n_overlap.txt).
+        behind the discretization (`mpc_propagate_discretize_gather`): y0 [n_local,7], tf [n_local] CUDA float64.
+        Modes "unicast" and "multicast".  In the satellite-major layout a k-window stores runs of ~13 columns per row and
+        satellite -- fine for HBM and for one peer, but with 7 peers the step is NVLink-ingress bound and the fragmented
+        peer stores cost more than the hidden propagation buys (8 x B200: 7.77 ms back to back, 13.8 ms windowed;
+        profiles/r01_n_overlap.txt) -- so there the overlapped pass is used at world <= 2 only.  In the k-major layout
+        (default for world > 2) a window stores whole runs of consecutive columns and the overlapped pass is used at any
+        world size.  The push modes keep the two-kernel sequence.
         Returns (buf, y, u, status_prop); results are bit-identical to propagate_batch_device + discretize()."""
         from . import batch
         assert y0.shape[0] == self.s1 - self.s0
@@ -178,34 +183,35 @@ class FusedGather:
                             pre_barrier=pre_barrier)
             return self.buf, y, u_out, status_prop
         self._pre_barrier(pre_barrier)
-        tuned = self.skip_const or self.stagger > 1
-        if tuned:
-            _lib.check(_lib.lib().mpc_set_gather_tuning((2 if self.mode == "multicast" else 1) if self.skip_const else 0,
-                                                        self.stagger))
-        try:
-            mc = self.mode == "multicast"
-            _, y, u_out, status_prop, _ = batch.propagate_discretize_device(
-                y0, tf, controller, const, self.K, prop_J2=include_J2, disc_J2=include_J2, n_sub_prop=n_sub_prop,
-                n_sub_disc=n_sub, y=y, u_out=u_out, out=self.buf, out_pitch=self.pitch,
-                out_offset=self.s0 * (self.K - 1), status_prop=status_prop, status_disc=self.status,
-                n_windows=n_windows, extra_dst=None if mc else self.dst[1:], out_ptr=self.mc_ptr if mc else None)
-        finally:
-            if tuned:
-                _lib.check(_lib.lib().mpc_set_gather_tuning(0, 0))
+        mc = self.mode == "multicast"
+        _, y, u_out, status_prop, _ = batch.propagate_discretize_device(
+            y0, tf, controller, const, self.K, prop_J2=include_J2, disc_J2=include_J2, n_sub_prop=n_sub_prop,
+            n_sub_disc=n_sub, y=y, u_out=u_out, out=self.buf, status_prop=status_prop, status_disc=self.status,
+            n_windows=n_windows, extra_dst=None if mc else self.dst[1:], out_ptr=self.mc_ptr if mc else None,
+            gather=self._opts())
         if barrier:
             self.handle.barrier()
         return self.buf, y, u_out, status_prop
 
+    def _opts(self):
+        """Options of one fused-gather launch (passed per call: nothing process-wide is touched)."""
+        return _lib.MpcGatherOpts(_lib.LAYOUT_K_MAJOR if self.layout == "kmajor" else _lib.LAYOUT_SAT_MAJOR,
+                                  (2 if self.mode == "multicast" else 1) if self.skip_const else 0,
+                                  self.stagger if self.stagger > 1 else 0, 0, self.n_sats, self.s0)
+
     def _launch(self, x, u, tf, const, include_J2, n_sub):
         from . import batch
-        if x.shape[0] > 0 and self.mode == "multicast":
+        if x.shape[0] > 0 and self.mode in ("unicast", "multicast"):
             import ctypes
             import torch
             p = _lib.make_params(const, include_J2, False)
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(_lib.lib().mpc_discretize_batch(x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p),
-                                                       x.shape[0], self.K, int(n_sub), self.mc_ptr, self.pitch,
-                                                       self.s0 * (self.K - 1), self.status.data_ptr(), stream))
+            ptrs = [self.mc_ptr] if self.mode == "multicast" else self.dst
+            arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+            g = self._opts()
+            _lib.check(_lib.lib().mpc_discretize_batch_gather(x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p),
+                                                              x.shape[0], self.K, int(n_sub), arr, len(ptrs),
+                                                              ctypes.byref(g), self.status.data_ptr(), stream))
         elif x.shape[0] > 0 and self.mode in ("push", "pushk"):
             import ctypes
             import torch
@@ -216,13 +222,9 @@ class FusedGather:
                 batch._ctx(self.device.index or 0), x.data_ptr(), u.data_ptr(), tf.data_ptr(), ctypes.byref(p), x.shape[0],
                 self.K, int(n_sub), arr, len(self.peers), self.pitch, self.s0 * (self.K - 1), self.status.data_ptr(),
                 self.chunk_waves, int(self.mode == "pushk"), stream))
-        elif x.shape[0] > 0:
-            batch.discretize_batch_device(x, u, tf, const, include_J2=include_J2, n_sub=n_sub, out=self.buf,
-                                          out_pitch=self.pitch, out_offset=self.s0 * (self.K - 1),
-                                          status=self.status, extra_dst=self.dst[1:])
 
     def view(self):
-        return GatheredView(self.buf, self.n_sats, self.K, self.world, layout="global")
+        return GatheredView(self.buf, self.n_sats, self.K, self.world, layout="kmajor" if self.layout == "kmajor" else "global")
 
 
 def nccl_gather_chunks(local, n_chunks, group=None, side_stream=None, produce=None, chunk_cols=None):

@@ -1,9 +1,12 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *unmodified* reference.
 
-Only usable in the build container, where /root/reference is mounted.  Nothing
-on the GPU box may import this module (the reference does not travel); it is
-used solely by tests/golden/make_golden.py to generate the committed fixtures
-that pin oracle/mpc_oracle.py and oracle/mpc_oracle.c.
+Two places the reference can be loaded from:
+  * /root/reference (the build container): used by tests/golden/make_golden.py to generate the committed fixtures
+    that pin oracle/mpc_oracle.py and oracle/mpc_oracle.c;
+  * oracle/_ref/ (git-ignored build output, travels to the GPU box like the built .so files): the reference's six
+    hot-path modules COMPILED to Python bytecode by `compile_reference()` (called from __graft_entry__.build() where
+    /root/reference is mounted) -- no reference source is copied into this repository.  bench.py --impl reference
+    times exactly that code: the unmodified reference on the box's host cores.
 
 The reference's control.py pulls in optimizer.py (pyomo) and sim_plotter.py
 (matplotlib); neither is installed and neither touches the hot path, so they
@@ -15,6 +18,34 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("MPC_REFERENCE_ROOT", "/root/reference")
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+HOT_PATH_MODULES = ("simulator", "control", "linearize_discretize", "satellite", "satellite_scale", "constants")
+
+
+def compile_reference(src_root=None, out_root=None):
+    """py_compile the reference's hot-path modules from where they lie into oracle/_ref/<module>.pyc (sourceless
+    bytecode, importable on the GPU box where /root/reference does not exist).  Returns the list of files written,
+    [] when the reference tree is not present."""
+    import py_compile
+    src_root = src_root or REFERENCE_ROOT
+    out_root = out_root or COMPILED_ROOT
+    if not os.path.isdir(src_root):
+        return []
+    os.makedirs(out_root, exist_ok=True)
+    done = []
+    for m in HOT_PATH_MODULES:
+        done.append(py_compile.compile(os.path.join(src_root, m + ".py"), cfile=os.path.join(out_root, m + ".pyc"),
+                                       doraise=True))
+    return done
+
+
+def reference_location():
+    """(path, kind): where the reference can be imported from here, kind 'source' | 'bytecode' | None."""
+    if os.path.isdir(REFERENCE_ROOT):
+        return REFERENCE_ROOT, "source"
+    if all(os.path.exists(os.path.join(COMPILED_ROOT, m + ".pyc")) for m in HOT_PATH_MODULES):
+        return COMPILED_ROOT, "bytecode"
+    return None, None
 
 
 class _Anything:
@@ -36,8 +67,9 @@ def _stub(name, **attrs):
 
 def load_reference():
     """Returns a namespace with the reference's hot-path classes."""
-    if not os.path.isdir(REFERENCE_ROOT):
-        raise RuntimeError(f"reference tree not present at {REFERENCE_ROOT}")
+    root, kind = reference_location()
+    if root is None:
+        raise RuntimeError(f"reference neither at {REFERENCE_ROOT} nor compiled under {COMPILED_ROOT}")
     if "matplotlib" not in sys.modules:
         plt = _stub("matplotlib.pyplot", subplots=_Anything(), show=_Anything(), Circle=_Anything(),
                     axes=_Anything(), title=_Anything(), gca=_Anything(), legend=_Anything())
@@ -49,8 +81,14 @@ def load_reference():
         _stub("pyomo.core.base")
         _stub("pyomo.core.base.expression", ScalarExpression=object)
         _stub("pyomo.environ")
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if kind == "bytecode":
+        # control.py imports optimizer (pyomo) and sim_plotter (matplotlib): not on the hot path, not compiled
+        if "optimizer" not in sys.modules:
+            _stub("optimizer", Optimizer=_Anything())
+        if "sim_plotter" not in sys.modules:
+            _stub("sim_plotter", plot_orbit_3D=_Anything(), __all__=["plot_orbit_3D"])
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import simulator as ref_simulator  # noqa: F401  (must precede control)
     import control as ref_control
     import linearize_discretize as ref_ld

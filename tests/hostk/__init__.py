@@ -78,7 +78,7 @@ def _const8(const):
 
 
 def discretize(x, u, tf, const, include_J2=False, n_sub=100, pair=True, k0=0, kc=-1, out=None, pitch=None, offset=0,
-               status=None):
+               status=None, km_ntot=0, km_soff=0):
     """The fixed-step kernels (discretize_pair_kernel / discretize_kernel) on host arrays x [N,7,K], u [N,3,K] -> SoA
     [105, pitch] + status, with the launch window (k0, kc) of the overlapped pass."""
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -93,7 +93,8 @@ def discretize(x, u, tf, const, include_J2=False, n_sub=100, pair=True, k0=0, kc
         status = np.full(n_int, -1, dtype=np.int32)
     c8 = _const8(const)
     lib().hostk_discretize(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, int(n_sub), int(pair), int(k0), int(kc),
-                           _p(out), ctypes.c_longlong(pitch), ctypes.c_longlong(offset), _p(status))
+                           _p(out), ctypes.c_longlong(pitch), ctypes.c_longlong(offset), _p(status),
+                           ctypes.c_longlong(km_ntot), ctypes.c_longlong(km_soff))
     return out, status
 
 

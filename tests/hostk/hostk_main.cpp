@@ -47,11 +47,13 @@ mpc::DiscParams disc_params(const double *c, int)
 // const8 = [MU, R_E, J2, G0, ISP, S, R0, RHO] (the order of mpc_params / OracleConstants)
 extern "C" int hostk_discretize(const double *x, const double *u, const double *tf, const double *const8, int include_j2,
                                 int n_sats, int K, int n_sub, int pair, int k0, int kc, double *out, long long pitch,
-                                long long offset, int32_t *status)
+                                long long offset, int32_t *status, long long km_ntot, long long km_soff)
 {
     const mpc::DiscParams P = disc_params(const8, include_j2);
     mpc::DstTab dst{};
     dst.p[0] = out;
+    dst.km_ntot = km_ntot;     // > 0: k-major layout, column = k km_ntot + km_soff + s
+    dst.km_soff = km_soff;
     if (kc < 0) kc = K - 1;
     if (pair) {
         run_grid((long long)n_sats * kc, [&] {

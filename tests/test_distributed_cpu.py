@@ -39,6 +39,16 @@ def test_gathered_view_layouts_agree():
             assert np.array_equal(a, b)
     A = vg.sat(3)[0]
     assert A.shape == (n, 7, 7) and A[1, 2, 5] == glob[2 * 7 + 5, 3 * n + 1]
+    # k-major: column = k n_sats + s; per-satellite access is a strided view of the same buffer (no copy)
+    kmaj = np.zeros_like(glob)
+    for s in range(n_sats):
+        for k in range(n):
+            kmaj[:, k * n_sats + s] = glob[:, s * n + k]
+    vk = D.GatheredView(kmaj, n_sats, K, world, "kmajor")
+    for s in range(n_sats):
+        for a, b in zip(vg.sat(s), vk.sat(s)):
+            assert np.array_equal(a, b)
+    assert np.shares_memory(vk.sat(2)[0], kmaj) and np.shares_memory(vk.sat(2)[3], kmaj)
     with pytest.raises(IndexError):
         vg.sat(5)
 

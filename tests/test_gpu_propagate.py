@@ -276,3 +276,58 @@ def test_overlapped_propagate_discretize_is_bit_identical(M, const, case, n_prop
         assert sorted(torch.nonzero(sp_b).flatten().tolist()) == [3, 700, N - 1] and int(sd_b.max()) > 0
     else:
         assert int(sp_b.max()) == 0 and int(sd_b.max()) == 0
+
+
+@pytest.mark.parametrize("layout", ["kmajor", "satmajor"])
+def test_fused_gather_entry_points_and_layouts_on_one_gpu(M, const, layout):
+    """mpc_propagate_discretize_gather / mpc_discretize_batch_gather (options per call, k-major or satellite-major gathered
+    layout) with two LOCAL buffers standing in for the ranks of an NVLink box: this rank's block lands in both, at its
+    place inside a larger gathered buffer, bit-identical to the plain two-kernel sequence (k-major: permuted), margins
+    untouched, for the overlapped windowed pass and for the plain launch."""
+    import ctypes
+    import torch
+    from mpconstellation_b200 import _lib
+    dev = torch.device("cuda:0")
+    N, T, tf, n_sub, ntot, soff = 1500, 131, 2.0, 10, 2200, 300
+    n = T - 1
+    y0, _, _ = synth_batch(N, 2, 1.0, const)
+    rng = np.random.default_rng(5)
+    tfv = tf * (1 + 0.05 * rng.random(N))
+    c = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    y0d, tfd = torch.from_numpy(y0).to(dev), torch.from_numpy(tfv).to(dev)
+    y_a, u_a, sp_a = M.propagate_batch_device(y0d, tfd, c, const, include_drag=False, include_J2=True, T=T)
+    out_a, sd_a = M.discretize_batch_device(y_a, u_a, tfd, const, include_J2=True, n_sub=n_sub)
+    ref = out_a.view(105, N, n)
+    want = torch.full((105, ntot * n), float("nan"), dtype=torch.float64, device=dev)
+    if layout == "kmajor":
+        want.view(105, n, ntot)[:, :, soff:soff + N] = ref.permute(0, 2, 1)
+    else:
+        want.view(105, ntot, n)[:, soff:soff + N, :] = ref
+    eq = lambda a, b: bool(torch.equal(a.view(torch.int64), b.view(torch.int64)))   # NaN-aware bit comparison
+    g = _lib.MpcGatherOpts(_lib.LAYOUT_K_MAJOR if layout == "kmajor" else _lib.LAYOUT_SAT_MAJOR, 0, 0, 0, ntot, soff)
+    bufs = [torch.full((105, ntot * n), float("nan"), dtype=torch.float64, device=dev) for _ in range(2)]
+    for rep in range(2):
+        _, y_b, u_b, sp_b, sd_b = M.propagate_discretize_device(y0d, tfd, c, const, T, prop_J2=True, disc_J2=True,
+                                                                n_sub_disc=n_sub, out=bufs[0], extra_dst=[bufs[1]],
+                                                                n_windows=7, gather=g)
+        torch.cuda.synchronize()
+        assert eq(y_a, y_b) and eq(u_a, u_b) and torch.equal(sd_a, sd_b) and int(sp_b.max()) == 0
+        for b in bufs:
+            assert eq(b, want)
+            b.fill_(float("nan"))
+    # the plain (not overlapped) launch through mpc_discretize_batch_gather
+    st = torch.empty(N * n, dtype=torch.int32, device=dev)
+    p = _lib.make_params(const, True, False)
+    arr = (ctypes.c_void_p * 2)(bufs[0].data_ptr(), bufs[1].data_ptr())
+    _lib.check(_lib.lib().mpc_discretize_batch_gather(y_a.data_ptr(), u_a.data_ptr(), tfd.data_ptr(), ctypes.byref(p), N, T, n_sub,
+                                                      arr, 2, ctypes.byref(g), st.data_ptr(),
+                                                      torch.cuda.current_stream(dev).cuda_stream))
+    torch.cuda.synchronize()
+    assert eq(bufs[0], want) and eq(bufs[1], want) and torch.equal(st, sd_a)
+    # bad options are refused
+    bad = _lib.MpcGatherOpts(7, 0, 0, 0, ntot, soff)
+    assert _lib.lib().mpc_discretize_batch_gather(y_a.data_ptr(), u_a.data_ptr(), tfd.data_ptr(), ctypes.byref(p), N, T, n_sub,
+                                                  arr, 2, ctypes.byref(bad), st.data_ptr(), None) == _lib.E_INVALID
+    small = _lib.MpcGatherOpts(0, 0, 0, 0, N - 1, 0)
+    assert _lib.lib().mpc_discretize_batch_gather(y_a.data_ptr(), u_a.data_ptr(), tfd.data_ptr(), ctypes.byref(p), N, T, n_sub,
+                                                  arr, 2, ctypes.byref(small), st.data_ptr(), None) == _lib.E_INVALID

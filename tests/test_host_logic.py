@@ -35,6 +35,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.MpcParams) == 12 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.MpcController) == 4 * 4 + 3 * 8 + 8 + 8 + 8
     assert _lib.MpcController.table.offset == 48
+    assert ctypes.sizeof(_lib.MpcGatherOpts) == 4 * 4 + 2 * 8 and _lib.MpcGatherOpts.n_sats_total.offset == 16
 
 
 def test_no_cpu_fallback_without_device():

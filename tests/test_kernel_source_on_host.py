@@ -110,6 +110,37 @@ def test_windowed_launches_assemble_the_full_launch_bit_for_bit(const):
     assert np.isnan(out[:, :4]).all() and np.isnan(out[:, 4 + n_int:]).all()
 
 
+def test_k_major_layout_is_a_permutation_of_the_satellite_major_one(const):
+    """DstTab.km_ntot / km_soff: column = k n_tot + s_off + s.  Same arithmetic per interval, so the k-major result is the
+    satellite-major one permuted, bit for bit -- full launch, ragged k-windows, both kernels, a rank's block inside a
+    larger gathered buffer (margins untouched)."""
+    N, K, ntot, soff = 6, 9, 11, 3
+    _, x, u = synth_batch(N, K, 0.8, const)
+    n = K - 1
+    full, st_full = hostk.discretize(x, u, 0.8, const)
+    want = np.full((105, ntot * n), np.nan)
+    for s_ in range(N):
+        for k in range(n):
+            want[:, k * ntot + soff + s_] = full[:, s_ * n + k]
+    for pair in (True, False):
+        out = np.full((105, ntot * n), np.nan)
+        st = np.full(N * n, -1, dtype=np.int32)
+        windows = ((0, 3), (3, 4), (7, 1)) if pair else ((0, -1),)
+        for k0, kc in windows:
+            hostk.discretize(x, u, 0.8, const, pair=pair, k0=k0, kc=kc, out=out, pitch=ntot * n, status=st,
+                             km_ntot=ntot, km_soff=soff)
+        ok = ~np.isnan(want)
+        if pair:
+            assert np.array_equal(out[ok], want[ok]) and np.isnan(out[~ok]).all() and np.array_equal(st, st_full)
+        else:       # the one-step-per-node kernel integrates differently (~1e-13): same layout, own arithmetic
+            ref1, st1 = hostk.discretize(x, u, 0.8, const, pair=False)
+            want1 = np.full((105, ntot * n), np.nan)
+            for s_ in range(N):
+                for k in range(n):
+                    want1[:, k * ntot + soff + s_] = ref1[:, s_ * n + k]
+            assert np.array_equal(out[ok], want1[ok]) and np.isnan(out[~ok]).all() and np.array_equal(st, st1)
+
+
 @pytest.mark.parametrize("case", ["p0", "p1", "p2", "p4"])
 def test_propagate_kernel_vs_reference_and_c_oracle(gold_prop, const, case):
     gp = gold_prop
