@@ -369,7 +369,9 @@ int64_t mpc_launch_count(void);
  * two-node integrator steps of the production kernel off / on (results differ by ~1e-12).  9 / 10 switch to the
  * round-1 build of the default-mode (adaptive) kernel and back (same results to rounding; A/B measurements).  11 / 12: RK45 propagator without / with the speculative first stage
  * of the next step (same results).  13: satellites per warp of the RK45 propagator chosen automatically, 14..19: forced
- * to 32, 16, 8, 4, 2, 1 (same results). */
+ * to 32, 16, 8, 4, 2, 1 (same results).  20 / 21 / 22: CTA size of the default-mode kernel 32 / 128 / 256 threads (same
+ * results).  23 / 24: the thread-group kernel for small batches (8 lanes per interval) off / on (results equal to
+ * rounding). */
 int mpc_set_tuning(int variant);
 
 /* Options of the fused (in-kernel store) all-gather, applied by mpc_discretize_batch / _multi:

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libmpc_b200.so")
 SOURCES = ["mpc_b200.cu"]
-HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_default_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "constraint_terms_kernel.cuh", "discretize_drag_kernel.cuh", "discretize_pair_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
+HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_default_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "discretize_group_kernel.cuh", "constraint_terms_kernel.cuh", "discretize_drag_kernel.cuh", "discretize_pair_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-split-compile", "0"]
 
@@ -176,18 +176,50 @@ def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.
                      float(c_d), float(rho_atm), cd_a, rho_a, int(bool(include_J2)), int(bool(include_drag)))
 
 
+# Page-locked buffers are expensive to create (cudaHostAlloc: ~0.1-1 ms plus ~0.2 ms per MiB) and the host API hands out
+# three of them per call (trajectory, inputs, matrices).  Buffers whose numpy array has been garbage-collected go back
+# to a small size-bucketed pool instead of being freed, so a loop of calls (the SCP iterations: control.py:183-227)
+# pays for them once.
+_POOL = {}                 # bucket size in bytes -> [addresses]
+_POOL_BYTES = 0
+_POOL_CAP = 2 << 30        # at most 2 GiB parked
+
+
+def _bucket(nbytes):
+    b = 4096
+    while b < nbytes:
+        b <<= 1
+    return b
+
+
+def _release(ptr, bucket):
+    global _POOL_BYTES
+    if _POOL_BYTES + bucket <= _POOL_CAP:
+        _POOL.setdefault(bucket, []).append(ptr)
+        _POOL_BYTES += bucket
+    else:
+        lib().mpc_host_free(ptr)
+
+
 def pinned_empty(shape, dtype=np.float64):
-    """numpy array over page-locked host memory (cudaHostAlloc through the C-ABI)."""
+    """numpy array over page-locked host memory (cudaHostAlloc through the C-ABI), pooled (see above)."""
+    global _POOL_BYTES
     dtype = np.dtype(dtype)
     shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
     nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    bucket = _bucket(max(nbytes, 1))
     L = lib()
-    ptr = L.mpc_host_alloc(max(nbytes, 1))
-    if not ptr:
-        raise MemoryError(L.mpc_last_error().decode())
-    buf = (ctypes.c_char * max(nbytes, 1)).from_address(ptr)
+    free = _POOL.get(bucket)
+    if free:
+        ptr = free.pop()
+        _POOL_BYTES -= bucket
+    else:
+        ptr = L.mpc_host_alloc(bucket)
+        if not ptr:
+            raise MemoryError(L.mpc_last_error().decode())
+    buf = (ctypes.c_char * bucket).from_address(ptr)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
-    weakref.finalize(buf, L.mpc_host_free, ptr)
+    weakref.finalize(buf, _release, ptr, bucket)
     return arr
 
 

@@ -22,6 +22,7 @@
 #include "constraint_terms_kernel.cuh"
 #include "discretize_drag_kernel.cuh"
 #include "discretize_pair_kernel.cuh"
+#include "discretize_group_kernel.cuh"
 
 namespace {
 
@@ -138,6 +139,23 @@ int launch_pair_cfg(const double *x, const double *u, const double *tf, const mp
 }
 
 std::atomic<int> g_pair{1};   // mpc_set_tuning(7) switches the two-node steps off (one step per node everywhere)
+std::atomic<int> g_group{1};  // mpc_set_tuning(23 / 24): the 8-lanes-per-interval kernel for small batches off / on
+// Below this many intervals the thread-group mapping wins (measured on a B200, profiles/r02_*): the one-thread kernel
+// needs 0.113 ms whatever the batch, the group kernel about a third of that until its 8x as many warps queue up.
+constexpr long long kGroupMaxIntervals = 8192;
+
+template <bool J2>
+int launch_group(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
+                 int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status, cudaStream_t st)
+{
+    constexpr int BLOCK = 32;                       // 4 intervals per CTA: spreads a small batch over every SM
+    const long long n_int = (long long)n_sats * (K - 1);
+    const unsigned grid = (unsigned)((n_int * 8 + BLOCK - 1) / BLOCK);
+    mpc::discretize_group_kernel<J2, BLOCK><<<grid, BLOCK, 0, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return MPC_SUCCESS;
+}
 
 // The production configuration plus the experimental ones mpc_set_tuning() selects (single destination,
 // no J2 only: they exist to measure occupancy / register-cap trade-offs).
@@ -163,7 +181,16 @@ int launch_disc_n(const double *x, const double *u, const double *tf, const mpc:
     // one-warp CTAs spread them over as many SMs as possible (same code, 224-register build, 9 CTAs/SM).
     // two quadrature nodes per integrator step where that is accurate (decided per thread inside the kernel)
     const bool pair = (g_ucols == 0) && g_pair.load(std::memory_order_relaxed);
-    if (NDST == 1 && (long long)n_sats * (K - 1) < 148LL * 9 * 32 * 2)
+    const long long n_int = (long long)n_sats * (K - 1);
+    // north_star's "warp or thread-group per interval" for batches below one wave: 8 lanes per interval
+    const int grp = g_group.load(std::memory_order_relaxed);   // 2: at any batch size (measurements)
+    if (NDST == 1 && pair && dst.km_ntot == 0 && grp && (n_int <= kGroupMaxIntervals || grp == 2))
+        return launch_group<J2>(MPC_ARGS);
+    // more warps than SMs but at most one 4-warp CTA per SM: one warp per scheduler on every SM (one-warp CTAs of such a
+    // batch land several to a scheduler: 0.27 instead of 0.115 ms on 15,104 intervals)
+    if (NDST == 1 && pair && n_int > 148LL * 32 && n_int <= 148LL * 128)
+        return launch_pair_cfg<J2, kDiscBlock, 255, 1>(MPC_ARGS);
+    if (NDST == 1 && n_int < 148LL * 9 * 32 * 2)
         return pair ? launch_pair_cfg<J2, 32, 255, 1>(MPC_ARGS) : launch_disc_cfg<J2, 32, 224, 1>(MPC_ARGS);
     return pair ? launch_pair_cfg<J2, kDiscBlock, 255, NDST>(MPC_ARGS) : launch_disc_cfg<J2, kDiscBlock, 255, NDST>(MPC_ARGS);
 #undef MPC_ARGS
@@ -713,6 +740,10 @@ int mpc_set_tuning(int variant)
     if (variant >= 13 && variant <= 19) {  // RK45 propagator: satellites per warp 13 automatic, 14..19 -> 32,16,8,4,2,1
         static const int lpw[7] = {0, 32, 16, 8, 4, 2, 1};
         g_rk45_lpw.store(lpw[variant - 13]);
+        return MPC_SUCCESS;
+    }
+    if (variant >= 23 && variant <= 25) {  // small batches: 8-lanes-per-interval kernel off / on / at any size
+        g_group.store(variant - 23);
         return MPC_SUCCESS;
     }
     if (variant >= 20 && variant <= 22) {  // default-mode kernel: threads per CTA 32 / 128 / 256

@@ -23,7 +23,7 @@ HOT_PATH_MODULES = ("simulator", "control", "linearize_discretize", "satellite",
 
 
 def compile_reference(src_root=None, out_root=None):
-    """py_compile the reference's hot-path modules from where they lie into oracle/_ref/<module>.pyc (sourceless
+    """py_compile the reference's hot-path modules from where they lie into oracle/_ref/<module>.bc (sourceless
     bytecode, importable on the GPU box where /root/reference does not exist).  Returns the list of files written,
     [] when the reference tree is not present."""
     import py_compile
@@ -34,16 +34,32 @@ def compile_reference(src_root=None, out_root=None):
     os.makedirs(out_root, exist_ok=True)
     done = []
     for m in HOT_PATH_MODULES:
-        done.append(py_compile.compile(os.path.join(src_root, m + ".py"), cfile=os.path.join(out_root, m + ".pyc"),
+        # (".bc": `*.pyc` files are dropped by the snapshot that ships the tree to the GPU box)
+        done.append(py_compile.compile(os.path.join(src_root, m + ".py"), cfile=os.path.join(out_root, m + ".bc"),
                                        doraise=True))
     return done
+
+
+class _BytecodeFinder:
+    """Meta-path finder: imports the reference's hot-path modules from oracle/_ref/<module>.bc (sourceless bytecode)."""
+
+    @staticmethod
+    def find_spec(name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if name not in HOT_PATH_MODULES:
+            return None
+        f = os.path.join(COMPILED_ROOT, name + ".bc")
+        if not os.path.exists(f):
+            return None
+        return importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, f), origin=f)
 
 
 def reference_location():
     """(path, kind): where the reference can be imported from here, kind 'source' | 'bytecode' | None."""
     if os.path.isdir(REFERENCE_ROOT):
         return REFERENCE_ROOT, "source"
-    if all(os.path.exists(os.path.join(COMPILED_ROOT, m + ".pyc")) for m in HOT_PATH_MODULES):
+    if all(os.path.exists(os.path.join(COMPILED_ROOT, m + ".bc")) for m in HOT_PATH_MODULES):
         return COMPILED_ROOT, "bytecode"
     return None, None
 
@@ -87,7 +103,9 @@ def load_reference():
             _stub("optimizer", Optimizer=_Anything())
         if "sim_plotter" not in sys.modules:
             _stub("sim_plotter", plot_orbit_3D=_Anything(), __all__=["plot_orbit_3D"])
-    if root not in sys.path:
+        if not any(f is _BytecodeFinder for f in sys.meta_path):
+            sys.meta_path.insert(0, _BytecodeFinder)
+    elif root not in sys.path:
         sys.path.insert(0, root)
     import simulator as ref_simulator  # noqa: F401  (must precede control)
     import control as ref_control

@@ -22,6 +22,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "mpconstellation_b20
 BUILD = os.path.join(HERE, "_build")
 SO = os.path.join(BUILD, "libmpc_hostk.so")
 SOURCES = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_default_kernel.cuh", "discretize_pair_kernel.cuh",
+           "discretize_group_kernel.cuh",
            "discretize_drag_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "constraint_terms_kernel.cuh"]
 _SEEDS = [(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rcp_seed(a);"),
           (r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;" : "=d"\(y\) : "d"\(a\)\);', "y = hostk_rsqrt_seed(a);")]
@@ -51,7 +52,7 @@ def _build(SO, force, opt):
         assert "asm(" not in text, f"{s}: inline PTX the host build does not know"
         open(os.path.join(BUILD, s), "w").write(text)
     assert n_sub == 2, "expected exactly the two MUFU seeds to be replaced"
-    cmd = ["g++"] + opt + ["-std=c++17", "-shared", "-fPIC", "-mfma", "-ffp-contract=fast", "-fno-math-errno", "-w",
+    cmd = ["g++"] + opt + ["-std=c++17", "-pthread", "-shared", "-fPIC", "-mfma", "-ffp-contract=fast", "-fno-math-errno", "-w",
            "-I", os.path.join(HERE, "include"), "-I", BUILD, "-o", SO, os.path.join(HERE, "hostk_main.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -95,6 +96,21 @@ def discretize(x, u, tf, const, include_J2=False, n_sub=100, pair=True, k0=0, kc
     lib().hostk_discretize(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, int(n_sub), int(pair), int(k0), int(kc),
                            _p(out), ctypes.c_longlong(pitch), ctypes.c_longlong(offset), _p(status),
                            ctypes.c_longlong(km_ntot), ctypes.c_longlong(km_soff))
+    return out, status
+
+
+def discretize_group(x, u, tf, const, include_J2=False, n_sub=100, extra_groups=0):
+    """discretize_group_kernel (8 lanes per interval, the small-batch mapping) on host arrays -> SoA [105, N*(K-1)], status"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    N, _, K = x.shape
+    tfv = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
+    n_int = N * (K - 1)
+    out = np.full((105, n_int), np.nan)
+    status = np.full(n_int, -1, dtype=np.int32)
+    c8 = _const8(const)
+    lib().hostk_discretize_group(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, int(n_sub), _p(out),
+                                 ctypes.c_longlong(n_int), ctypes.c_longlong(0), _p(status), int(extra_groups))
     return out, status
 
 

@@ -3,12 +3,14 @@
 // launch one after the other.
 #include "hostk_shim.h"
 
+#include <thread>
 #include <vector>
 
 #include "discretize_kernel.cuh"
 #include "discretize_adaptive_kernel.cuh"
 #include "discretize_default_kernel.cuh"
 #include "discretize_pair_kernel.cuh"
+#include "discretize_group_kernel.cuh"
 #include "propagate_kernel.cuh"
 #include "propagate_rk45_kernel.cuh"
 #include "discretize_drag_kernel.cuh"
@@ -65,6 +67,33 @@ extern "C" int hostk_discretize(const double *x, const double *u, const double *
             if (include_j2) mpc::discretize_kernel<true, kBlock, 255, 1, false>(x, u, tf, P, n_sats, K, K, n_sub, dst, pitch, offset, status);
             else mpc::discretize_kernel<false, kBlock, 255, 1, false>(x, u, tf, P, n_sats, K, K, n_sub, dst, pitch, offset, status);
         });
+    }
+    return 0;
+}
+
+// the thread-group kernel (8 lanes per interval): the lanes of one group run as 8 host threads (see hostk_shim.h), group
+// after group; threadIdx / blockIdx are what the 32-thread CTAs of the real launch would give them
+extern "C" int hostk_discretize_group(const double *x, const double *u, const double *tf, const double *const8, int include_j2,
+                                      int n_sats, int K, int n_sub, double *out, long long pitch, long long offset,
+                                      int32_t *status, int extra_groups)
+{
+    const mpc::DiscParams P = disc_params(const8, include_j2);
+    mpc::DstTab dst{};
+    dst.p[0] = out;
+    const long long n_groups = (long long)n_sats * (K - 1) + extra_groups;   // extra: the idle groups of a last partial warp
+    for (long long g = 0; g < n_groups; ++g) {
+        hostk_group_ctx ctx;
+        std::vector<std::thread> lanes;
+        for (int l = 0; l < 8; ++l)
+            lanes.emplace_back([&, l] {
+                hostk_grp = &ctx;
+                blockDim.x = kBlock;
+                blockIdx.x = (unsigned)(g / 4);
+                threadIdx.x = (unsigned)((g % 4) * 8 + l);
+                if (include_j2) mpc::discretize_group_kernel<true, kBlock>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+                else mpc::discretize_group_kernel<false, kBlock>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+            });
+        for (auto &t : lanes) t.join();
     }
     return 0;
 }

@@ -9,6 +9,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
+
 #define __device__
 #define __global__
 #define __host__
@@ -53,6 +56,45 @@ static inline double __longlong_as_double(long long v)
     memcpy(&d, &v, sizeof d);
     return d;
 }
+// Shuffles of the thread-group kernel (8 lanes per interval): the 8 lanes of ONE group run as 8 host threads that meet at
+// every shuffle (all lanes of a group take the same path), exchanging values through a slot per lane.
+struct hostk_group_ctx {
+    std::mutex m;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned long long gen = 0, slot[8] = {};
+    void barrier()
+    {
+        std::unique_lock<std::mutex> l(m);
+        const unsigned long long g = gen;
+        if (++waiting == 8) {
+            waiting = 0;
+            ++gen;
+            cv.notify_all();
+        } else {
+            cv.wait(l, [&] { return gen != g; });
+        }
+    }
+};
+static thread_local hostk_group_ctx *hostk_grp = nullptr;
+template <typename T>
+static inline T hostk_exchange(T v, int src)
+{
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof v);
+    hostk_grp->slot[threadIdx.x & 7] = bits;
+    hostk_grp->barrier();
+    const unsigned long long r = hostk_grp->slot[src & 7];
+    hostk_grp->barrier();
+    T out;
+    memcpy(&out, &r, sizeof out);
+    return out;
+}
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return hostk_exchange(v, src); }
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int d, int = 32) { return hostk_exchange(v, (int)(threadIdx.x & 7) ^ d); }
+
 // round-to-nearest intrinsics of the constraint-terms kernel (written without contraction on the device: keep the
 // host compiler from fusing them as well)
 __attribute__((noinline)) static double __dmul_rn(double a, double b) { return a * b; }

@@ -382,3 +382,35 @@ def test_bench_step_at_full_size_matches_the_unmodified_reference(M):
                 worst = max(worst, e)
                 assert e < TOL_REF, (int(s), tag, n, e)
     print(f"bench step vs reference: worst norm-relative error {worst:.2e}")
+
+
+@pytest.mark.parametrize("n_sats,K,tf,j2,n_sub", [(1, 50, 0.5, False, 100), (64, 100, 1.0, False, 100), (5, 17, 2.0, True, 10),
+                                                   (3, 9, 3.0, True, 7), (40, 100, 1.0, True, 100)])
+def test_small_batches_use_the_thread_group_kernel_and_agree_with_the_one_thread_kernels(M, const, n_sats, K, tf, j2, n_sub):
+    """BASELINE configs 1-2 and every per-satellite Discretizer.discretize call run the 8-lanes-per-interval kernel
+    (mpc_set_tuning(23) switches it off): A_k bit-identical, everything else to the rounding of its cross-lane sums;
+    also against the C oracle."""
+    import torch
+    from oracle import c_oracle as C
+    dev = torch.device("cuda:0")
+    _, x, u = synth_batch(n_sats, K, tf, const)
+    xd, ud = torch.from_numpy(x).to(dev), torch.from_numpy(u).to(dev)
+    tfd = torch.full((n_sats,), tf, dtype=torch.float64, device=dev)
+    L = M._lib.lib()
+    before = M.launch_count()
+    a, sa = M.discretize_batch_device(xd, ud, tfd, const, include_J2=j2, n_sub=n_sub)
+    try:
+        assert L.mpc_set_tuning(23) == 0
+        b, sb = M.discretize_batch_device(xd, ud, tfd, const, include_J2=j2, n_sub=n_sub)
+    finally:
+        L.mpc_set_tuning(24)
+    torch.cuda.synchronize()
+    assert M.launch_count() - before == 2 and int(sa.max()) == 0 and torch.equal(sa, sb)
+    assert torch.equal(a[0:49], b[0:49])
+    a, b = a.cpu().numpy(), b.cpu().numpy()
+    for r0, r1 in ((49, 70), (70, 91), (91, 98), (98, 105)):
+        assert rel_err(a[r0:r1], b[r0:r1]) < 1e-12
+    ref = C.discretize_batch(x, u, tf, const, include_J2=j2, n_sub=n_sub)
+    got = M.DiscretizedBatch(a, sa.cpu().numpy().reshape(n_sats, K - 1), n_sats, K).stacked()
+    for n, g, r in zip(NAMES, got, ref[:5]):
+        assert rel_err(g, r) < 1e-10, n

@@ -110,6 +110,29 @@ def test_windowed_launches_assemble_the_full_launch_bit_for_bit(const):
     assert np.isnan(out[:, :4]).all() and np.isnan(out[:, 4 + n_int:]).all()
 
 
+@pytest.mark.parametrize("N,K,tf,j2,n_sub", [(3, 6, 0.3, False, 100), (2, 5, 0.5, True, 16), (2, 4, 2.0, False, 7),
+                                             (1, 3, 3.0, True, 10), (1, 2, 0.1, False, 100)])
+def test_thread_group_kernel_matches_the_one_thread_kernels(const, N, K, tf, j2, n_sub):
+    """discretize_group_kernel (8 lanes per interval, the small-batch mapping north_star names; the lanes of a group run
+    as 8 host threads meeting at every shuffle): same scheme per interval as the one-thread kernels -- two-node steps,
+    odd panel counts and over-long steps (one step per node), J2 -- so A_k is bit-identical and the rest agrees to the
+    rounding of the epilogue's cross-lane sums; the idle groups of a last partial warp store nothing; a non-positive
+    mass is flagged on the interval it occurs in."""
+    _, x, u = synth_batch(N, K, tf, const)
+    a, sa = hostk.discretize_group(x, u, tf, const, include_J2=j2, n_sub=n_sub, extra_groups=3)
+    b, sb = hostk.discretize(x, u, tf, const, include_J2=j2, n_sub=n_sub)
+    assert sa.max() == 0 and np.array_equal(sa, sb)
+    assert np.array_equal(a[0:49], b[0:49])
+    for r0, r1 in ((49, 70), (70, 91), (91, 98), (98, 105)):
+        assert rel_err(a[r0:r1], b[r0:r1]) < 1e-13
+    if K > 3:
+        x = x.copy()
+        x[0, 6, 1] = -1.0
+        a, sa = hostk.discretize_group(x, u, tf, const, include_J2=j2, n_sub=n_sub)
+        b, sb = hostk.discretize(x, u, tf, const, include_J2=j2, n_sub=n_sub)
+        assert np.array_equal(sa != 0, sb != 0) and sa[1] == 1
+
+
 def test_k_major_layout_is_a_permutation_of_the_satellite_major_one(const):
     """DstTab.km_ntot / km_soff: column = k n_tot + s_off + s.  Same arithmetic per interval, so the k-major result is the
     satellite-major one permuted, bit for bit -- full launch, ragged k-windows, both kernels, a rank's block inside a
