@@ -140,9 +140,10 @@ int launch_pair_cfg(const double *x, const double *u, const double *tf, const mp
 
 std::atomic<int> g_pair{1};   // mpc_set_tuning(7) switches the two-node steps off (one step per node everywhere)
 std::atomic<int> g_group{1};  // mpc_set_tuning(23 / 24): the 8-lanes-per-interval kernel for small batches off / on
-// Below this many intervals the thread-group mapping wins (measured on a B200, profiles/r02_*): the one-thread kernel
-// needs 0.113 ms whatever the batch, the group kernel about a third of that until its 8x as many warps queue up.
-constexpr long long kGroupMaxIntervals = 8192;
+// Below this many intervals the thread-group mapping wins (measured on a B200, profiles/r02_f_small_batches.txt): the
+// one-thread kernel needs 0.118 ms whatever the batch, the group kernel 0.064 ms up to ~1000 intervals, 0.086 ms at
+// 2376 and the same 0.12 ms at 6336, where its 8x as many warps queue up on the schedulers.
+constexpr long long kGroupMaxIntervals = 4096;
 
 template <bool J2>
 int launch_group(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,

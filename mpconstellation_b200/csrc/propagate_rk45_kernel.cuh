@@ -60,6 +60,14 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
     const double end_tau = C.end_tau_arr ? C.end_tau_arr[s] : C.end_tau;
     const double tf = tf_arr[s];
     const double rtol = O.rtol, atol = O.atol, max_step = O.max_step;
+    // Zero, constant and tangential thrust burn mass at a constant rate: every stage derivative of the mass is the same
+    // number cm, the stage masses are m + h c_s cm (sum_l a_sl = c_s), its error estimate is zero (sum E = 0) and its dense
+    // output is the straight line -- none of the 7-term sums is formed for that component (NC = 6).
+    constexpr bool CM = (KIND != 3);
+    constexpr int NC = CM ? 6 : 7;
+    // err^2 <= sum (e_i h)^2 / (7 atol^2) because every scale is >= atol: when even that bound is below 0.09^10 the
+    // controller's decision (accept, factor 10) is known without forming the 7 scales and their reciprocals
+    const double tiny_thr = 3.486784401e-11 * 7.0 * atol * atol;
     double y[7], K[7][7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) y[c] = y0[(long long)s * 7 + c];
@@ -125,7 +133,8 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 double ys[7];
                 const double a10 = hs * (1.0 / 5);
 #pragma unroll
-                for (int i = 0; i < 7; ++i) ys[i] = fma(K[0][i], a10, y[i]);
+                for (int i = 0; i < NC; ++i) ys[i] = fma(K[0][i], a10, y[i]);
+                if (CM) ys[6] = fma(K[0][6], hs * (1.0 / 5), y[6]);
                 bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (1.0 / 5) * h, K[1]);
             }
             have_k1 = false;
@@ -133,14 +142,16 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 double ys[7];
                 const double a0 = hs * (3.0 / 40), a1 = hs * (9.0 / 40);
 #pragma unroll
-                for (int i = 0; i < 7; ++i) ys[i] = fma(K[1][i], a1, fma(K[0][i], a0, y[i]));
+                for (int i = 0; i < NC; ++i) ys[i] = fma(K[1][i], a1, fma(K[0][i], a0, y[i]));
+                if (CM) ys[6] = fma(K[0][6], hs * (3.0 / 10), y[6]);
                 bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (3.0 / 10) * h, K[2]);
             }
             {
                 double ys[7];
                 const double a0 = hs * (44.0 / 45), a1 = hs * (-56.0 / 15), a2 = hs * (32.0 / 9);
 #pragma unroll
-                for (int i = 0; i < 7; ++i) ys[i] = fma(K[2][i], a2, fma(K[1][i], a1, fma(K[0][i], a0, y[i])));
+                for (int i = 0; i < NC; ++i) ys[i] = fma(K[2][i], a2, fma(K[1][i], a1, fma(K[0][i], a0, y[i])));
+                if (CM) ys[6] = fma(K[0][6], hs * (4.0 / 5), y[6]);
                 bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (4.0 / 5) * h, K[3]);
             }
             {
@@ -148,8 +159,9 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 const double a0 = hs * (19372.0 / 6561), a1 = hs * (-25360.0 / 2187), a2 = hs * (64448.0 / 6561),
                              a3 = hs * (-212.0 / 729);
 #pragma unroll
-                for (int i = 0; i < 7; ++i)
+                for (int i = 0; i < NC; ++i)
                     ys[i] = fma(K[3][i], a3, fma(K[2][i], a2, fma(K[1][i], a1, fma(K[0][i], a0, y[i]))));
+                if (CM) ys[6] = fma(K[0][6], hs * (8.0 / 9), y[6]);
                 bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (8.0 / 9) * h, K[4]);
             }
             {
@@ -157,16 +169,18 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 const double a0 = hs * (9017.0 / 3168), a1 = hs * (-355.0 / 33), a2 = hs * (46732.0 / 5247),
                              a3 = hs * (49.0 / 176), a4 = hs * (-5103.0 / 18656);
 #pragma unroll
-                for (int i = 0; i < 7; ++i)
+                for (int i = 0; i < NC; ++i)
                     ys[i] = fma(K[4][i], a4, fma(K[3][i], a3, fma(K[2][i], a2, fma(K[1][i], a1, fma(K[0][i], a0, y[i])))));
+                if (CM) ys[6] = fma(K[0][6], hs, y[6]);
                 bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + h, K[5]);
             }
             {
                 const double b0 = hs * (35.0 / 384), b2 = hs * (500.0 / 1113), b3 = hs * (125.0 / 192),
                              b4 = hs * (-2187.0 / 6784), b5 = hs * (11.0 / 84);
 #pragma unroll
-                for (int i = 0; i < 7; ++i)
+                for (int i = 0; i < NC; ++i)
                     yn[i] = fma(K[5][i], b5, fma(K[4][i], b4, fma(K[3][i], b3, fma(K[2][i], b2, fma(K[0][i], b0, y[i])))));
+                if (CM) yn[6] = fma(K[0][6], hs, y[6]);
                 bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, yn, t + h, K[6]);
             }
             double k1n[7];
@@ -180,23 +194,33 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 h_pred = tp - t_new;
                 const double a10 = (h_pred * tf) * (1.0 / 5);
 #pragma unroll
-                for (int i = 0; i < 7; ++i) ys[i] = fma(K[6][i], a10, yn[i]);
+                for (int i = 0; i < NC; ++i) ys[i] = fma(K[6][i], a10, yn[i]);
+                if (CM) ys[6] = fma(K[0][6], a10, yn[6]);
                 bad_n = prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t_new + (1.0 / 5) * h_pred, k1n);
             }
             // -- error norm (rk.py _estimate_error_norm) ---------------------------------------------------------------
-            double esum = 0.0;
+            double eh[NC], esum0 = 0.0;
 #pragma unroll
-            for (int i = 0; i < 7; ++i) {
+            for (int i = 0; i < NC; ++i) {
                 double e = K[6][i] * (1.0 / 40);
                 e = fma(K[5][i], -22.0 / 525, e);
                 e = fma(K[4][i], 17253.0 / 339200, e);
                 e = fma(K[3][i], -71.0 / 1920, e);
                 e = fma(K[2][i], 71.0 / 16695, e);
                 e = fma(K[0][i], -71.0 / 57600, e);
-                const double q = e * hs * fast_rcp(atol + fmax(fabs(y[i]), fabs(yn[i])) * rtol);
-                esum = fma(q, q, esum);
+                eh[i] = e * hs;
+                esum0 = fma(eh[i], eh[i], esum0);
             }
-            const double err2 = esum * (1.0 / 7.0);   // error_norm^2 (the decisions below need no square root)
+            double err2 = 0.0;                         // error_norm^2 (the decisions below need no square root)
+            if (!(esum0 <= tiny_thr)) {                // (also taken by a NaN)
+                double esum = 0.0;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const double q = eh[i] * fast_rcp(atol + fmax(fabs(y[i]), fabs(yn[i])) * rtol);
+                    esum = fma(q, q, esum);
+                }
+                err2 = esum * (1.0 / 7.0);
+            }
             if (bad) break;
             if (err2 < 1.0) {
                 // min(10, 0.9 err^-0.2) = 10  <=>  err <= 0.09^5: the common case needs no pow
@@ -230,7 +254,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
             double Q[7][4];
             const double hs = h * tf;
 #pragma unroll
-            for (int i = 0; i < 7; ++i) {
+            for (int i = 0; i < NC; ++i) {
                 Q[i][0] = K[0][i];
                 Q[i][1] = K[0][i] * (-8048581381.0 / 2820520608.0);
                 Q[i][2] = K[0][i] * (8663915743.0 / 2820520608.0);
@@ -238,7 +262,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
             }
             // rows 2..6 of P; in SPEC mode K[1] already belongs to the next step (P's row 1 is zero: not needed)
 #define MPC_QROW(l, p1, p2, p3)                     \
-    _Pragma("unroll") for (int i = 0; i < 7; ++i)  \
+    _Pragma("unroll") for (int i = 0; i < NC; ++i) \
     {                                               \
         Q[i][1] = fma(K[l][i], p1, Q[i][1]);        \
         Q[i][2] = fma(K[l][i], p2, Q[i][2]);        \
@@ -255,10 +279,14 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 const double x2 = xx * xx, x3 = x2 * xx, x4 = x3 * xx;
                 double ys[7];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) {
+                for (int i = 0; i < NC; ++i) {
                     const double q = fma(Q[i][3], x4, fma(Q[i][2], x3, fma(Q[i][1], x2, Q[i][0] * xx)));
                     ys[i] = fma(hs, q, y[i]);
                     yo[(long long)i * T + ti] = ys[i];
+                }
+                if (CM) {
+                    ys[6] = fma(hs * xx, K[0][6], y[6]);
+                    yo[(long long)6 * T + ti] = ys[6];
                 }
                 if (uo) {   // Discretizer.extract_uk (linearize_discretize.py:393-411) on the sample
                     double ux, uy, uz;

@@ -220,8 +220,11 @@ def test_device_api_pitch_offset_and_multi_destination(M, const):
     outs = [torch.zeros((105, n), dtype=torch.float64, device=dev) for _ in range(4)]
     M.discretize_batch_device(xs, us, tfv, const, out=outs[0], extra_dst=outs[1:])
     torch.cuda.synchronize()
-    for o in outs:
-        assert np.array_equal(o.cpu().numpy(), ref)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])                       # every destination gets the same bits
+    # (the 4-destination launch runs the one-thread kernel, `ref` -- a 66-interval single-destination batch -- the
+    # thread-group kernel: equal up to the rounding of the latter's cross-lane sums)
+    assert rel_err(outs[0].cpu().numpy(), ref) < 1e-13
 
 
 def test_full_size_config3_properties(M, const):
@@ -384,7 +387,7 @@ def test_bench_step_at_full_size_matches_the_unmodified_reference(M):
     print(f"bench step vs reference: worst norm-relative error {worst:.2e}")
 
 
-@pytest.mark.parametrize("n_sats,K,tf,j2,n_sub", [(1, 50, 0.5, False, 100), (64, 100, 1.0, False, 100), (5, 17, 2.0, True, 10),
+@pytest.mark.parametrize("n_sats,K,tf,j2,n_sub", [(1, 50, 0.5, False, 100), (41, 100, 1.0, False, 100), (5, 17, 2.0, True, 10),
                                                    (3, 9, 3.0, True, 7), (40, 100, 1.0, True, 100)])
 def test_small_batches_use_the_thread_group_kernel_and_agree_with_the_one_thread_kernels(M, const, n_sats, K, tf, j2, n_sub):
     """BASELINE configs 1-2 and every per-satellite Discretizer.discretize call run the 8-lanes-per-interval kernel
