@@ -64,6 +64,19 @@ __device__ __forceinline__ int ad_eval(const DiscParams &P, double kf, double ka
     return !(x[6] > 0.0);
 }
 
+// End nodes of an interval: the node term takes the input the REFERENCE looks up there (ref_node_input: its global-grid
+// lookup may land in the neighbouring interval; decisive only for the |u| <= eps guard of B_func when u is exactly 0 at
+// the node).  Only what the node term reads is replaced: u, 1/|u| (guarded), |u|.
+template <bool GENU>
+__device__ __forceinline__ void ad_end_node_input(AdStage &o, const double *__restrict__ u_in, int sat, int K, int node)
+{
+    if (GENU) return;            // u on its own grid is looked up on that grid at every node already
+    ref_node_input(u_in + (long long)sat * 3 * K, K, node, 1.0, o.ux, o.uy, o.uz);
+    const double uu = fma(o.ux, o.ux, fma(o.uy, o.uy, o.uz * o.uz));
+    o.iun = (uu > 4.930380657631324e-32) ? fast_rsqrt(uu) : 0.0;
+    o.un = uu * o.iun;
+}
+
 #define SM(e) sm[(e) * BLOCK]
 
 template <int BLOCK, bool DRAG>
@@ -371,6 +384,8 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
         if (fail) break;
         // ---- accepted: trapezoid panel [t, t_new] (np.trapz, x = sol.t) ------------------------------------------
         const double w = 0.5 * (t_new - t);
+        if (t == t0) ad_end_node_input<GENU>(st0, u_in, sat, K, k);
+        if (t_new == t1) ad_end_node_input<GENU>(st6, u_in, sat, K, k + 1);
         ad_node<BLOCK, DRAG>(sm, cur, P, x, st0, w, (t - t0) * ilen);
         ad_node<BLOCK, DRAG>(sm, nxt, P, xn, st6, w, (t_new - t0) * ilen);
         const int tmp = cur;

@@ -336,6 +336,8 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                     pr[c][a] = cur[(long long)(c * 6 + a) * pitch];
                     pv[c][a] = cur[(long long)(c * 6 + 3 + a) * pitch];
                 }
+            if (t == t0) ad_end_node_input<GENU>(st0, u_in, sat, K, k);
+            if (last) ad_end_node_input<GENU>(st0, u_in, sat, K, k + 1);
             const double w = half_prev + half_next;
             // The reference inverts the NUMERICAL Phi (np.linalg.inv, :69): general 6x6 solve, see discretize_adaptive_kernel
             node_accumulate_general<BLOCK>(sm, pr, pv, P, st0, x, w, w * ((t - t0) * ilen), row6, pitch);

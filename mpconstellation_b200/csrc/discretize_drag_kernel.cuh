@@ -227,7 +227,8 @@ discretize_drag_kernel(const double *__restrict__ x_in, const double *__restrict
     int bad = 0;
     for (int n = 0; n <= n_sub; ++n) {
         double ux, uy, uz;
-        hold.at((double)n * inv_n, 0.0, ux, uy, uz);
+        if (n == 0 || n == n_sub) ref_node_input(u_in + (long long)s * 3 * K, K, k + (n == n_sub), 1.0, ux, uy, uz);   // end nodes
+        else hold.at((double)n * inv_n, 0.0, ux, uy, uz);
         DragEval e1;
         bad |= drag_eval<J2>(P, kf, ka, x, ux, uy, uz, e1);
         {

@@ -146,13 +146,19 @@ discretize_group_kernel(const double *__restrict__ x, const double *__restrict__
 
     int bad = 0;
     double ux, uy, uz;
-    hold.at(0.0, 0.0, ux, uy, uz);
+    ref_node_input(u + (long long)s * 3 * K, K, k, H2, ux, uy, uz);               // end node: as the reference looks it up
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
     double iun = inv_norm_guarded(uu, eps2);
     double un = uu * iun;
     double jn = 0.0;                                   // node index of the step's first node, as a double
 
     for (int j = 0; j <= n_steps; ++j) {
+        if (j == n_steps) {                                                         // the other end node
+            ref_node_input(u + (long long)s * 3 * K, K, k + 1, H2, ux, uy, uz);
+            uu = fma(ux, ux, fma(uy, uy, uz * uz));
+            iun = inv_norm_guarded(uu, eps2);
+            un = uu * iun;
+        }
         // ---- stage 1 == quadrature node at the start of the step ---------------------------------------------------
         StageLin s1;
         double a1x, a1y, a1z;

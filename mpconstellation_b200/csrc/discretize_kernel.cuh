@@ -191,6 +191,46 @@ __device__ __forceinline__ void column_step(double (&pr)[3], double (&pv)[3], co
     pv[2] = fma(c6, fma(4.0, k2z, k1z) + k3z, pv[2]);
 }
 
+// Python's float floor division v // w for v >= 0, w > 0 (CPython float_divmod): NOT floor(v / w) -- 0.5 // 0.1 is 4.
+__device__ __forceinline__ double py_floordiv(double v, double w)
+{
+    const double mod = fmod(v, w);
+    const double div = (v - mod) / w;
+    if (div == 0.0) return 0.0;
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+}
+
+// The input the REFERENCE sees at node i of tau = np.linspace(0, 1, Ku): Discretizer.u_FOH (linearize_discretize.py:
+// 294-315) looks the node up on the global grid, k = int(tau // dtau), and interpolates there.  Rounding decides whether
+// tau_i lands in the interval left or right of it (tau_6 = 0.6000000000000001 of an 11-node grid lands in [6, 7], tau_5 =
+// 0.5 in [4, 5]), so the value is u_i only up to ~1e-16 (u_{i+-1} - u_i).  That is immaterial everywhere except in the
+// |u| <= eps guard of B_func (:208): where u_i is exactly 0 next to a thrusting node the reference gets |u| ~ 1e-15 > eps
+// and a unit thrust direction (taken from the NEIGHBOUR) in the mass row of B, where a straight hold gets 0.  The kernels
+// therefore take the inputs of the two END nodes of every interval from here (interior nodes are always looked up in
+// their own interval).  us: u of this satellite, [3][Ku]; f: the kernel's scaling of u.  Called twice per interval.
+__device__ __noinline__ void ref_node_input(const double *__restrict__ us, int Ku, int i, double f, double &ux, double &uy,
+                                            double &uz)
+{
+    if (i >= Ku - 1) {                       // tau == 1: the last column (:305-306)
+        ux = f * us[Ku - 1];
+        uy = f * us[2 * Ku - 1];
+        uz = f * us[3 * (long long)Ku - 1];
+        return;
+    }
+    const double km1 = (double)(Ku - 1);
+    const double dtau = 1.0 / km1;
+    const double tau = (double)i * dtau;     // np.linspace: arange(Ku) * step
+    int kq = (int)py_floordiv(tau, dtau);
+    kq = min(max(kq, 0), Ku - 2);
+    const double tk = (double)kq / km1, tk1 = (double)(kq + 1) / km1;
+    const double ln = (tk1 - tau) / (tk1 - tk), lp = (tau - tk) / (tk1 - tk);
+    ux = f * __dadd_rn(__dmul_rn(ln, us[kq]), __dmul_rn(lp, us[kq + 1]));
+    uy = f * __dadd_rn(__dmul_rn(ln, us[Ku + kq]), __dmul_rn(lp, us[Ku + kq + 1]));
+    uz = f * __dadd_rn(__dmul_rn(ln, us[2 * (long long)Ku + kq]), __dmul_rn(lp, us[2 * (long long)Ku + kq + 1]));
+}
+
 // Input hold u(tau).  GENU = false: u is given on the K nodes of x, so inside one interval the reference's
 // first-order hold (linearize_discretize.py:294-315) is the straight line between u_k and u_{k+1}.
 // GENU = true: u has its own column count Ku (the reference accepts that: u_FOH takes its grid from u itself,
@@ -248,7 +288,7 @@ struct UHold<true> {
         }
         const double km1 = (double)(Ku - 1);
         const double dtau = 1.0 / km1;
-        int k = (int)floor(tau / dtau);
+        int k = (int)py_floordiv(tau, dtau);
         k = min(max(k, 0), Ku - 2);
         const double lo = (double)k / km1, hi = (double)(k + 1) / km1;
         const double ln = (hi - tau) / (hi - lo), lp = (tau - lo) / (hi - lo);
@@ -568,12 +608,19 @@ __device__ __forceinline__ void discretize_thread(const double *__restrict__ x, 
     int bad = 0;
     // thrust at the current node and its norm
     double ux, uy, uz;
-    hold.at(0.0, tau0, ux, uy, uz);
+    if (GENU) hold.at(0.0, tau0, ux, uy, uz);
+    else ref_node_input(u + (long long)s * 3 * K, K, k, hs2, ux, uy, uz);      // end node: as the reference looks it up
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
     double iun = inv_norm_guarded(uu, eps2);
     double un = uu * iun;
 
     for (int n = 0; n <= n_sub; ++n) {
+        if (!GENU && n == n_sub) {                                                  // the other end node
+            ref_node_input(u + (long long)s * 3 * K, K, k + 1, hs2, ux, uy, uz);
+            uu = fma(ux, ux, fma(uy, uy, uz * uz));
+            iun = inv_norm_guarded(uu, eps2);
+            un = uu * iun;
+        }
         // ---- stage 1 == quadrature node n ------------------------------------------------------
         StageLin s1;
         double a1x, a1y, a1z;

@@ -201,12 +201,18 @@ discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ 
 
     int bad = 0;
     double ux, uy, uz;
-    hold.at(0.0, 0.0, ux, uy, uz);
+    ref_node_input(u + (long long)s * 3 * K, K, k, H2, ux, uy, uz);               // end node: as the reference looks it up
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
     double iun = inv_norm_guarded(uu, eps2);
     double un = uu * iun;
 
     for (int j = 0; j <= n_pairs; ++j) {
+        if (j == n_pairs) {                                                         // the other end node
+            ref_node_input(u + (long long)s * 3 * K, K, k + 1, H2, ux, uy, uz);
+            uu = fma(ux, ux, fma(uy, uy, uz * uz));
+            iun = inv_norm_guarded(uu, eps2);
+            un = uu * iun;
+        }
         // ---- stage 1 == even quadrature node 2j -----------------------------------------------------------------
         StageLin s1;
         double a1x, a1y, a1z;

@@ -235,8 +235,36 @@ static int rkn4_step(double *y, const double *u1, const double *um, const double
 
 /* One interval; out = A(49) B_kp(21) B_kn(21) Sigma(7) xi(7); linearize_discretize.py:8-82.
  * u0/u1 are the FOH end points of this interval (u is linear inside one interval, :305-315). */
-static int interval(const double *xk, const double *u0, const double *u1, double tf, double dtau, int n_sub,
-                    const orc_params *p, int j2, double *out)
+/* Python's float floor division for v >= 0, w > 0 (CPython float_divmod); differs from floor(v / w): 0.5 // 0.1 == 4 */
+static double py_floordiv(double v, double w)
+{
+    double mod = fmod(v, w), div = (v - mod) / w;
+    if (div == 0.0) return 0.0;
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+}
+
+/* Discretizer.u_FOH(tau_i, u) for node i of tau = np.linspace(0, 1, K), statement for statement
+ * (linearize_discretize.py:294-315): the lookup k = int(tau // dtau) is on the GLOBAL grid, so a node may be looked up
+ * in the interval next to it -- decisive where u is exactly 0 at the node (|u| <= eps guard of B_func, :208).
+ * us: [3][K] of one satellite. */
+static void ref_node_input(const double *us, int K, int i, double *un)
+{
+    if (i >= K - 1) {
+        for (int c = 0; c < 3; ++c) un[c] = us[c * K + K - 1];
+        return;
+    }
+    double dtau = 1.0 / (K - 1), tau = i * dtau;
+    int k = (int)py_floordiv(tau, dtau);
+    if (k > K - 2) k = K - 2;
+    double tk = (double)k / (K - 1), tk1 = (double)(k + 1) / (K - 1);
+    double ln = (tk1 - tau) / (tk1 - tk), lp = (tau - tk) / (tk1 - tk);
+    for (int c = 0; c < 3; ++c) un[c] = ln * us[c * K + k] + lp * us[c * K + k + 1];
+}
+
+static int interval(const double *xk, const double *u0, const double *u1, const double *e0, const double *e1, double tf,
+                    double dtau, int n_sub, const orc_params *p, int j2, double *out)
 {
     double y[56], k1[56], k2[56], k3[56], k4[56], yt[56], ypend[56];
     memset(y, 0, sizeof y);
@@ -258,6 +286,9 @@ static int interval(const double *xk, const double *u0, const double *u1, double
         double lam_p = (double)n / n_sub, lam_n = 1.0 - lam_p;
         double un[3];
         for (int i = 0; i < 3; ++i) un[i] = lam_n * u0[i] + lam_p * u1[i];
+        /* the two end nodes: the input the reference looks up there (ref_node_input) */
+        if (n == 0) memcpy(un, e0, sizeof un);
+        if (n == n_sub) memcpy(un, e1, sizeof un);
         /* node terms, :63-75 */
         double Pinv[49], Bm[21], Dx[49], sig[7], xi[7];
         const double *xs = y + 49;
@@ -389,7 +420,10 @@ int orc_discretize_rk4(const double *x, const double *u, const double *tf, const
             u0[c] = u[((long)s * 3 + c) * K + k];
             u1[c] = u[((long)s * 3 + c) * K + k + 1];
         }
-        int st = interval(xk, u0, u1, tf[s], dtau, n_sub, p, p->include_J2, out + i * 105);
+        double e0[3], e1[3];
+        ref_node_input(u + (long)s * 3 * K, K, k, e0);
+        ref_node_input(u + (long)s * 3 * K, K, k + 1, e1);
+        int st = interval(xk, u0, u1, e0, e1, tf[s], dtau, n_sub, p, p->include_J2, out + i * 105);
         if (status) status[i] = st;
         bad += (st != 0);
     }
@@ -429,6 +463,7 @@ typedef struct {
     double t0, t1, tf;
     const orc_params *p;
     int j2;
+    const double *e0, *e1; /* inputs at the two end nodes as the reference looks them up (ref_node_input) */
 } aug_ctx;
 
 static int aug_fun(const aug_ctx *c, double t, const double *y, double *dy)
@@ -448,6 +483,8 @@ static int node_integrands(const aug_ctx *c, double t, const double *y, double *
     double un[3], Pinv[49], Bm[21], Dx[49], sig[7], xi[7];
     const double *xs = y + 49;
     for (int i = 0; i < 3; ++i) un[i] = ln * c->u0[i] + lp * c->u1[i];
+    if (t == c->t0) memcpy(un, c->e0, sizeof un);
+    if (t == c->t1) memcpy(un, c->e1, sizeof un);
     if (inv7(y, Pinv)) return 3;
     duf(xs, un, c->p, Bm);
     for (int i = 0; i < 21; ++i) Bm[i] *= c->tf;
@@ -478,11 +515,11 @@ static int node_integrands(const aug_ctx *c, double t, const double *y, double *
     return 0;
 }
 
-static int interval_rk45(const double *xk, const double *u0, const double *u1, double tf, double t0, double t1,
-                         double rtol, double atol, double max_step, const orc_params *p, int j2, double *out,
-                         int *n_nodes)
+static int interval_rk45(const double *xk, const double *u0, const double *u1, const double *e0, const double *e1, double tf,
+                         double t0, double t1, double rtol, double atol, double max_step, const orc_params *p, int j2,
+                         double *out, int *n_nodes)
 {
-    aug_ctx c = {u0, u1, t0, t1, tf, p, j2};
+    aug_ctx c = {u0, u1, t0, t1, tf, p, j2, e0, e1};
     double y[56], f[56], K[7][56], ynew[56], fnew[56], tmp[56], sc[56];
     double acc[56] = {0}, gprev[56], gcur[56];
     memset(y, 0, sizeof y);
@@ -620,7 +657,10 @@ int orc_discretize_rk45(const double *x, const double *u, const double *tf, cons
         double step = 1.0 / (K - 1);
         double t0 = k * step, t1 = (k + 1 == K - 1) ? 1.0 : (k + 1) * step;
         int nn = 0;
-        int st = interval_rk45(xk, u0, u1, tf[s], t0, t1, rtol, atol, max_step, p, p->include_J2, out + i * 105, &nn);
+        double e0[3], e1[3];
+        ref_node_input(u + (long)s * 3 * K, K, k, e0);
+        ref_node_input(u + (long)s * 3 * K, K, k + 1, e1);
+        int st = interval_rk45(xk, u0, u1, e0, e1, tf[s], t0, t1, rtol, atol, max_step, p, p->include_J2, out + i * 105, &nn);
         if (status) status[i] = st;
         if (n_nodes) n_nodes[i] = nn;
         bad += (st != 0);

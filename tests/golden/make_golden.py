@@ -140,6 +140,34 @@ def bench_fixtures():
     print("bench_workload.npz", os.path.getsize(os.path.join(HERE, "bench_workload.npz")) // 1024, "KiB")
 
 
+def coast_fixtures():
+    """tests/golden/discretize_coast.npz: a coast-to-thrust switch with u EXACTLY zero on the coasting nodes (what a
+    bang-off-bang plan looks like).  The reference looks the end nodes of every interval up on the global grid
+    (u_FOH, linearize_discretize.py:308-315): tau_6 = 0.6000000000000001 lands in [6, 7], where it interpolates
+    1e-15 (u_7 - u_6) -- above eps, so B_func's |u| <= eps guard (:208) does not fire and the mass row of B at that node
+    carries the unit direction of u_7 although u_6 = 0.  Pins the kernels' end-node lookup (ref_node_input)."""
+    sat = R.Satellite(R_INIT, V_INIT, M_INIT)
+    scale = R.SatelliteScale(sat=sat)
+    const = scale.get_normalized_constants()
+    g = {"const": const_vec(const)}
+    for tag, K, tf, n_coast in (("c11", 11, 0.6, 7), ("c24", 24, 1.3, 10)):
+        c = R.ConstantTangentialThrustController([sat], 0.5)
+        sim = R.Simulator(sats=[R.Satellite(R_INIT, V_INIT, M_INIT)], controller=c, scale=scale, base_res=int(round(K / tf)) + 1,
+                          include_drag=False, include_J2=False)
+        sim.eval_points = K
+        s0 = sim.sats[0]
+        sol = sim.get_trajectory_ODE(s0, tf, c.get_u_func())
+        x, t = sol.y, sol.t
+        u = R.Discretizer.extract_uk(x, t, c)
+        u[:, :n_coast] = 0.0                       # coast on the first nodes, thrust afterwards
+        u[:, -2:] = 0.0                            # ... and a thrust-to-coast switch at the end
+        g.update({f"{tag}_x": x, f"{tag}_u": u, f"{tag}_tf": tf})
+        g.update(pack(f"{tag}_uni", disc(const, x, u, tf, True)))
+        g.update(pack(f"{tag}_def", disc(const, x, u, tf, False)))
+    np.savez(os.path.join(HERE, "discretize_coast.npz"), **g)
+    print("discretize_coast.npz", os.path.getsize(os.path.join(HERE, "discretize_coast.npz")) // 1024, "KiB")
+
+
 def pack(prefix, out):
     names = ["A_k", "B_kp", "B_kn", "Sigma_k", "xi_k"]
     return {f"{prefix}_{n}": o for n, o in zip(names, out)}
@@ -285,7 +313,9 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 
-if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "drag":
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "coast":
+    coast_fixtures()
+elif __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "drag":
     drag_fixtures()
 elif __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bench":
     bench_fixtures()

@@ -419,3 +419,29 @@ def test_small_batches_use_the_thread_group_kernel_and_agree_with_the_one_thread
     # integrator's own defect -- DESIGN.md, known distances; at the reference's 100 steps per interval they agree to 1e-12)
     for n, g, r in zip(NAMES, got, ref[:5]):
         assert rel_err(g, r) < (1e-10 if n_sub == 100 else 1e-5), n
+
+
+@pytest.mark.parametrize("tag", ["c11", "c24"])
+def test_coast_to_thrust_switch_matches_the_unmodified_reference(M, tag):
+    """u exactly 0 on the coasting nodes: the reference's global-grid lookup of an interval's end nodes decides the
+    |u| <= eps guard of B_func there (linearize_discretize.py:208,308-315); fixture from the unmodified reference, through
+    Discretizer.discretize in both quadrature modes (small batch: thread-group kernel; and the one-thread kernel)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "discretize_coast.npz"))
+    from oracle.mpc_oracle import OracleConstants
+    c = OracleConstants(*g["const"])
+    x, u, tf = g[tag + "_x"], g[tag + "_u"], float(g[tag + "_tf"])
+    d = M.Discretizer(c)
+    L = M._lib.lib()
+    for mode, uniform in (("uni", True), ("def", False)):
+        ref = [g[f"{tag}_{mode}_{n}"] for n in NAMES]
+        d.use_uniform_steps = uniform
+        for variant in (24, 23):
+            try:
+                L.mpc_set_tuning(variant)
+                got = d.discretize(M.Simulator.satellite_dynamics, x, u, tf)
+            finally:
+                L.mpc_set_tuning(24)
+            for n, a, r in zip(NAMES, got, ref):
+                assert rel_err(a, r) < (1e-7 if uniform else 1e-10), (mode, variant, n)
+            assert rel_err(got[1][:, 6], ref[1][:, 6]) < 1e-11 and rel_err(got[2][:, 6], ref[2][:, 6]) < 1e-11

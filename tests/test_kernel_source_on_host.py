@@ -133,6 +133,29 @@ def test_thread_group_kernel_matches_the_one_thread_kernels(const, N, K, tf, j2,
         assert np.array_equal(sa != 0, sb != 0) and sa[1] == 1
 
 
+@pytest.mark.parametrize("tag", ["c11", "c24"])
+def test_kernels_follow_the_reference_lookup_at_a_coast_to_thrust_switch(tag):
+    """every discretization kernel takes the inputs of an interval's two END nodes the way the reference looks them up
+    (ref_node_input; see test_oracles_reproduce_the_reference_on_a_coast_to_thrust_switch): with u exactly 0 on the
+    coasting nodes the mass rows of B_kp / B_kn -- 1-2 % of those rows where a straight hold is used -- match the
+    unmodified reference to rounding."""
+    g = np.load(os.path.join(GOLDEN, "discretize_coast.npz"))
+    c = O.OracleConstants(*g["const"])
+    x, u, tf = g[tag + "_x"], g[tag + "_u"], float(g[tag + "_tf"])
+    K = x.shape[1]
+    runs = {"pair": ("uni", lambda: hostk.discretize(x[None], u[None], tf, c)[0]),
+            "one-step": ("uni", lambda: hostk.discretize(x[None], u[None], tf, c, pair=False)[0]),
+            "group": ("uni", lambda: hostk.discretize_group(x[None], u[None], tf, c)[0]),
+            "default": ("def", lambda: hostk.discretize_adaptive(x[None], u[None], tf, c)[0]),
+            "default-v1": ("def", lambda: hostk.discretize_adaptive(x[None], u[None], tf, c, v1=True)[0])}
+    for name, (mode, run) in runs.items():
+        ref = [g[f"{tag}_{mode}_{n}"] for n in NAMES]
+        got = hostk.stacked(run(), 1, K)
+        for n, a, r in zip(NAMES, got, ref):
+            assert rel_err(a[0], r) < (1e-7 if mode == "uni" else 1e-12), (name, n)
+        assert rel_err(got[1][0][:, 6], ref[1][:, 6]) < 1e-12 and rel_err(got[2][0][:, 6], ref[2][:, 6]) < 1e-12, name
+
+
 def test_k_major_layout_is_a_permutation_of_the_satellite_major_one(const):
     """DstTab.km_ntot / km_soff: column = k n_tot + s_off + s.  Same arithmetic per interval, so the k-major result is the
     satellite-major one permuted, bit for bit -- full launch, ragged k-windows, both kernels, a rank's block inside a

@@ -94,6 +94,28 @@ def test_c_oracle_rk45_replica_matches_reference_default_mode(gold_disc, const, 
             assert rel_err(_sel(o[0], ks), g[f"d3_j2_def_{n}"]) < 1e-12, n
 
 
+@pytest.mark.parametrize("tag", ["c11", "c24"])
+def test_oracles_reproduce_the_reference_on_a_coast_to_thrust_switch(tag):
+    """u exactly 0 on the coasting nodes (a bang-off-bang plan): the reference looks the end nodes of an interval up on the
+    GLOBAL grid (u_FOH, linearize_discretize.py:308-315; tau_6 = 0.6000000000000001 of an 11-node grid lands in [6, 7]) and
+    gets |u| ~ 1e-15 > eps, so the guard of B_func (:208) does not fire and the mass row of B at that node carries the
+    neighbour's thrust direction.  Both restatements follow that lookup (ref_node_input in the C one); fixture from the
+    unmodified reference (make_golden.py coast)."""
+    g = np.load(os.path.join(GOLDEN, "discretize_coast.npz"))
+    c = O.OracleConstants(*g["const"])
+    x, u, tf = g[tag + "_x"], g[tag + "_u"], float(g[tag + "_tf"])
+    for mode, uniform in (("uni", True), ("def", False)):
+        ref = [g[f"{tag}_{mode}_{n}"] for n in NAMES]
+        assert np.max(np.abs(ref[1][:, 6])) > 0 and np.max(np.abs(ref[2][:, 6])) > 0      # the mass rows are in play
+        po = O.discretize(x, u, tf, c, use_uniform_steps=uniform)
+        co = C.discretize_batch(x[None], u[None], tf, c) if uniform else C.discretize_batch_adaptive(x[None], u[None], tf, c)
+        for n, p_, c_, r in zip(NAMES, po, co[:5], ref):
+            assert rel_err(p_, r) < 1e-13, (mode, n)
+            assert rel_err(c_[0], r) < (1e-7 if uniform else 1e-13), (mode, n)           # uniform: the reference's RK45 noise
+        # the rows the lookup decides: the mass rows of B_kp / B_kn
+        assert rel_err(co[1][0][:, 6], ref[1][:, 6]) < 1e-12 and rel_err(co[2][0][:, 6], ref[2][:, 6]) < 1e-12
+
+
 def test_reference_default_mode_distance_is_its_own_quadrature_error(gold_disc, const):
     """Documented, not gated: default-mode B+- sit ~1e-3 from the uniform-node answer."""
     g = gold_disc
