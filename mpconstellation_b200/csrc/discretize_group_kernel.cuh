@@ -145,8 +145,10 @@ discretize_group_kernel(const double *__restrict__ x, const double *__restrict__
     A.AS = A.AX = 0.0;
 
     int bad = 0;
-    double ux, uy, uz;
-    ref_node_input(u + (long long)s * 3 * K, K, k, H2, ux, uy, uz);               // end node: as the reference looks it up
+    double ux, uy, uz, e1x, e1y, e1z;
+    // the two end nodes: as the reference looks them up (ref_node_input)
+    ref_node_input(u + (long long)s * 3 * K, K, k + 1, H2, e1x, e1y, e1z);
+    ref_node_input(u + (long long)s * 3 * K, K, k, H2, ux, uy, uz);
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
     double iun = inv_norm_guarded(uu, eps2);
     double un = uu * iun;
@@ -154,7 +156,9 @@ discretize_group_kernel(const double *__restrict__ x, const double *__restrict__
 
     for (int j = 0; j <= n_steps; ++j) {
         if (j == n_steps) {                                                         // the other end node
-            ref_node_input(u + (long long)s * 3 * K, K, k + 1, H2, ux, uy, uz);
+            ux = e1x;
+            uy = e1y;
+            uz = e1z;
             uu = fma(ux, ux, fma(uy, uy, uz * uz));
             iun = inv_norm_guarded(uu, eps2);
             un = uu * iun;

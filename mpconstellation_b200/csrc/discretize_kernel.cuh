@@ -305,6 +305,8 @@ struct UHold<true> {
 //  42..47  IX[a]      sum w   Phi^-1 xi'
 //  48..50  I0m[j], 51..53 I1m[j], 54 ISm, 55 IXm   (row 6: Phi^-1 row 6 = e7^T)
 constexpr int kAccSlots = 56;
+constexpr int kEndU = kAccSlots;          // 3 more slots: the input of the interval's END node (ref_node_input), parked
+constexpr int kDiscSlots = kAccSlots + 3; //   there from the start of the kernel so that no call sits in the step loop
 constexpr int kMaxDst = 8;
 
 struct DstTab {  // destination buffers of the (optionally multi-destination) SoA store
@@ -609,14 +611,22 @@ __device__ __forceinline__ void discretize_thread(const double *__restrict__ x, 
     // thrust at the current node and its norm
     double ux, uy, uz;
     if (GENU) hold.at(0.0, tau0, ux, uy, uz);
-    else ref_node_input(u + (long long)s * 3 * K, K, k, hs2, ux, uy, uz);      // end node: as the reference looks it up
+    else {       // the two end nodes: as the reference looks them up; the far one waits in shared memory
+        ref_node_input(u + (long long)s * 3 * K, K, k + 1, hs2, ux, uy, uz);
+        ACC(kEndU) = ux;
+        ACC(kEndU + 1) = uy;
+        ACC(kEndU + 2) = uz;
+        ref_node_input(u + (long long)s * 3 * K, K, k, hs2, ux, uy, uz);
+    }
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
     double iun = inv_norm_guarded(uu, eps2);
     double un = uu * iun;
 
     for (int n = 0; n <= n_sub; ++n) {
         if (!GENU && n == n_sub) {                                                  // the other end node
-            ref_node_input(u + (long long)s * 3 * K, K, k + 1, hs2, ux, uy, uz);
+            ux = ACC(kEndU);
+            uy = ACC(kEndU + 1);
+            uz = ACC(kEndU + 2);
             uu = fma(ux, ux, fma(uy, uy, uz * uz));
             iun = inv_norm_guarded(uu, eps2);
             un = uu * iun;

@@ -201,14 +201,21 @@ discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ 
 
     int bad = 0;
     double ux, uy, uz;
-    ref_node_input(u + (long long)s * 3 * K, K, k, H2, ux, uy, uz);               // end node: as the reference looks it up
+    // the two end nodes: as the reference looks them up (ref_node_input); the far one waits in shared memory
+    ref_node_input(u + (long long)s * 3 * K, K, k + 1, H2, ux, uy, uz);
+    ACC(kEndU) = ux;
+    ACC(kEndU + 1) = uy;
+    ACC(kEndU + 2) = uz;
+    ref_node_input(u + (long long)s * 3 * K, K, k, H2, ux, uy, uz);
     double uu = fma(ux, ux, fma(uy, uy, uz * uz));
     double iun = inv_norm_guarded(uu, eps2);
     double un = uu * iun;
 
     for (int j = 0; j <= n_pairs; ++j) {
         if (j == n_pairs) {                                                         // the other end node
-            ref_node_input(u + (long long)s * 3 * K, K, k + 1, H2, ux, uy, uz);
+            ux = ACC(kEndU);
+            uy = ACC(kEndU + 1);
+            uz = ACC(kEndU + 2);
             uu = fma(ux, ux, fma(uy, uy, uz * uz));
             iun = inv_norm_guarded(uu, eps2);
             un = uu * iun;

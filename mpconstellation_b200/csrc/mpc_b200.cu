@@ -96,7 +96,7 @@ int launch_disc_cfg(const double *x, const double *u, const double *tf, const mp
                     cudaStream_t st)
 {
     auto kern = mpc::discretize_kernel<J2, BLOCK, MAXREG, NDST, GENU>;
-    const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
+    const size_t smem = (size_t)mpc::kDiscSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -121,7 +121,7 @@ int launch_pair_cfg(const double *x, const double *u, const double *tf, const mp
 {
     if (kc < 0) kc = K - 1;   // the whole batch
     auto kern = mpc::discretize_pair_kernel<J2, BLOCK, MAXREG, NDST>;
-    const size_t smem = (size_t)mpc::kAccSlots * BLOCK * sizeof(double);
+    const size_t smem = (size_t)mpc::kDiscSlots * BLOCK * sizeof(double);
     static thread_local int configured_dev = -1;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
