@@ -33,7 +33,7 @@ constexpr int kDfSlots = kDfAcc + 7 * 9;          // + G_s (6), d_s (3) of the 7
 constexpr int kDfSlotsDrag = kDfAcc + 7 * 15;     // + V_s (6): drag branch of the linearisation
 constexpr int kDfPhiA = 0, kDfPhiB = 49;          // the two Phi row blocks inside the output buffer
 constexpr int kDfRow6 = 91;                       // rows 91..98: the row-6 accumulators until the epilogue
-constexpr int kDfEndU = 99;                       // rows 99..104: inputs of the two end nodes (ref_node_input), parked
+constexpr int kDfEndU = 99;                       // rows 99..101: input of the far end node (ref_node_input), parked
 
 #define SM(e) sm[(e) * BLOCK]
 
@@ -95,12 +95,11 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
     double *const row6 = col + (long long)kDfRow6 * pitch;
 #pragma unroll
     for (int q = 0; q < 8; ++q) row6[(long long)q * pitch] = 0.0;
-    if (!GENU) {       // inputs of the two end nodes as the reference looks them up: computed once, parked in the buffer
-        double e[6];
-        ref_node_input(u_in + (long long)sat * 3 * K, K, k, 1.0, e[0], e[1], e[2]);
-        ref_node_input(u_in + (long long)sat * 3 * K, K, k + 1, 1.0, e[3], e[4], e[5]);
+    if (!GENU) {       // input of the far end node as the reference looks it up: computed once, parked in the buffer
+        double e[3];
+        ref_node_input(u_in + (long long)sat * 3 * K, K, k + 1, 1.0, e[0], e[1], e[2]);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) col[(long long)(kDfEndU + q) * pitch] = e[q];
+        for (int q = 0; q < 3; ++q) col[(long long)(kDfEndU + q) * pitch] = e[q];
     }
     int bad = 0, fail = 0, nodes = 1;
     double t = t0;
@@ -188,6 +187,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
 
     // ---- solve_ivp main loop.  One trip per quadrature node: try steps from node j until one is accepted (none when
     // t has reached the end), then add node j with its full trapezoid weight, then move on. ---------------------------
+    ad_end_node_input<GENU>(st0, u_in, sat, K, k);       // the node term of tau_k reads the reference's lookup of u there
     double half_prev = 0.0;       // (t_j - t_{j-1}) / 2
 #pragma unroll 1
     for (;;) {
@@ -344,8 +344,8 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                     pr[c][a] = cur[(long long)(c * 6 + a) * pitch];
                     pv[c][a] = cur[(long long)(c * 6 + 3 + a) * pitch];
                 }
-            if (!GENU && (t == t0 || last)) {       // end node: the node term reads u, 1/|u| (guarded), |u| of the lookup
-                const double *e = col + (long long)(kDfEndU + (last ? 3 : 0)) * pitch;
+            if (!GENU && last) {       // far end node: the node term reads u, 1/|u| (guarded), |u| of the reference's lookup
+                const double *e = col + (long long)kDfEndU * pitch;
                 st0.ux = e[0];
                 st0.uy = e[pitch];
                 st0.uz = e[2 * pitch];

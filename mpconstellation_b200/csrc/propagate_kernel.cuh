@@ -129,8 +129,9 @@ propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_ar
                  int32_t *__restrict__ status, unsigned int *progress = nullptr, int seg_len = 0)
 {
     // progress != nullptr: the kernel publishes how far it has come.  Window b of the discretization covers the intervals
-    // [b seg_len, min((b+1) seg_len, T-1)) and needs the samples up to e_b = min((b+1) seg_len, T-1): once every lane of a
-    // warp has stored sample e_b, the warp adds 1 to progress[b] (stores fenced first).  A stream memory operation on the
+    // [b seg_len, min((b+1) seg_len, T-1)) and needs the samples up to min(e_b + 1, T-1), e_b = min((b+1) seg_len, T-1)
+    // (one past its last interval: see below): once every lane of a warp has stored that sample, the warp adds 1 to
+    // progress[b] (stores fenced first).  A stream memory operation on the
     // discretization's stream waits for progress[b] == number of warps (mpc_propagate_discretize): no kernel ever spins.
     const int s = blockIdx.x * BLOCK + threadIdx.x;
     if (s >= n_sats) return;
@@ -169,10 +170,18 @@ propagate_kernel(const double *__restrict__ y0, const double *__restrict__ tf_ar
                 uo[2 * (long long)T + j] = uz;
             }
         }
-        if (progress && j > 0 && (j == T - 1 || j % seg_len == 0)) {   // j is the last sample some window needs
+        // Window b needs the samples up to e_b + 1 (e_b = min((b+1) seg_len, T-1)): its last interval reads the inputs of
+        // node e_b, and the reference's global-grid lookup of that end node may interpolate towards node e_b + 1
+        // (ref_node_input).  So a window is released one sample later than its last interval ends, the last one at T-1.
+        if (progress && j > 1 && (j - 1) % seg_len == 0 && (j - 1) < T - 1) {
             __threadfence();
             __syncwarp();
-            if ((threadIdx.x & 31) == 0) atomicAdd(progress + ((j == T - 1) ? (T - 2) / seg_len : j / seg_len - 1), 1u);
+            if ((threadIdx.x & 31) == 0) atomicAdd(progress + ((j - 1) / seg_len - 1), 1u);
+        }
+        if (progress && j == T - 1 && j > 0) {
+            __threadfence();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) atomicAdd(progress + (T - 2) / seg_len, 1u);
         }
         if (bad) continue;
         if (j == T - 1) break;

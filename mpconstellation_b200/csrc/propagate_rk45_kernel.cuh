@@ -296,8 +296,16 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                     uo[T + ti] = uy;
                     uo[2 * (long long)T + ti] = uz;
                 }
-                if (progress && ti > 0 && (ti == T - 1 || ti % seg_len == 0)) {   // ti is the last sample some window needs
-                    const int b = (ti == T - 1) ? (T - 2) / seg_len : ti / seg_len - 1;
+                // a window is released one sample after its last interval ends (its end node's input lookup may reach one
+                // node further, see propagate_kernel), the last window at T-1
+                if (progress && ti > 1 && (ti - 1) % seg_len == 0 && (ti - 1) < T - 1) {
+                    const int b = (ti - 1) / seg_len - 1;
+                    __threadfence();
+                    const unsigned peers = __match_any_sync(__activemask(), b);
+                    if (lane == __ffs(peers) - 1) atomicAdd(progress + b, (unsigned)__popc(peers));
+                }
+                if (progress && ti == T - 1 && ti > 0) {
+                    const int b = (T - 2) / seg_len;
                     __threadfence();
                     const unsigned peers = __match_any_sync(__activemask(), b);
                     if (lane == __ffs(peers) - 1) atomicAdd(progress + b, (unsigned)__popc(peers));
@@ -325,9 +333,13 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 uo[T + ti] = qnan;
                 uo[2 * (long long)T + ti] = qnan;
             }
-            if (progress && ti > 0 && (ti == T - 1 || ti % seg_len == 0)) {
+            if (progress && ti > 1 && (ti - 1) % seg_len == 0 && (ti - 1) < T - 1) {
                 __threadfence();
-                atomicAdd(progress + ((ti == T - 1) ? (T - 2) / seg_len : ti / seg_len - 1), 1u);
+                atomicAdd(progress + ((ti - 1) / seg_len - 1), 1u);
+            }
+            if (progress && ti == T - 1 && ti > 0) {
+                __threadfence();
+                atomicAdd(progress + (T - 2) / seg_len, 1u);
             }
         }
     }

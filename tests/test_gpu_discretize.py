@@ -446,3 +446,35 @@ def test_coast_to_thrust_switch_matches_the_unmodified_reference(M, tag):
             for n, a, r in zip(NAMES, got, ref):
                 assert rel_err(a, r) < (1e-7 if uniform else 1e-10), (mode, variant, n)
             assert rel_err(got[1][:, 6], ref[1][:, 6]) < 1e-11 and rel_err(got[2][:, 6], ref[2][:, 6]) < 1e-11
+
+
+def test_reference_test_linearize_many_and_config2_chain_on_the_gpu(M):
+    """the unmodified reference's own test_linearize_many call in its DEFAULT mode (test_discretizer.py:96-105; matching u
+    and the test's malformed (3, 3K) u), through Discretizer.discretize; and BASELINE config 2 -- all 64 satellites x K=100
+    through one batched pass, 4 of them against the reference's own propagation + both quadrature modes"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import make_constellation
+    from oracle.mpc_oracle import OracleConstants
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "discretize_many.npz"))
+    c = OracleConstants(*g["const"])
+    sel = lambda o, ks, n: o[ks] if n in ("A_k", "B_kp", "B_kn") else o[:, ks]
+    d = M.Discretizer(c)
+    assert d.use_uniform_steps is False                       # the reference's default
+    f = M.Simulator.satellite_dynamics
+    for tag, u in (("m0", g["m0_u"]), ("m0q", g["m0_uq"])):
+        got = d.discretize(f, g["m0_x"], u, 1.0)
+        for n, a in zip(NAMES, got):
+            assert rel_err(sel(a, g["m0_ks"], n), g[f"{tag}_def_{n}"]) < 1e-10, (tag, n)
+    Y, const = make_constellation(64)
+    idx, ks = g["m1_idx"], g["m1_ks"]
+    assert np.array_equal(Y[idx], g["m1_y0"])
+    ctrl = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    res, x, u = M.propagate_discretize(Y, 1.0, ctrl, const, T=100)
+    resd = M.discretize_batch(x, u, 1.0, const, adaptive=dict(rtol=1e-3, atol=1e-6, max_step=1e-2))
+    for j, i in enumerate(idx):
+        assert rel_err(x[i], g[f"m1_s{j}_x"]) < 1e-9 and rel_err(u[i], g[f"m1_s{j}_u"]) < 1e-9
+        for n, a, b in zip(NAMES, res.sat(int(i)), resd.sat(int(i))):
+            assert rel_err(sel(a, ks, n), g[f"m1_s{j}_uni_{n}"]) < 1e-8, (j, n)
+            assert rel_err(sel(b, ks, n), g[f"m1_s{j}_def_{n}"]) < 1e-10, (j, n)

@@ -156,6 +156,35 @@ def test_kernels_follow_the_reference_lookup_at_a_coast_to_thrust_switch(tag):
         assert rel_err(got[1][0][:, 6], ref[1][:, 6]) < 1e-12 and rel_err(got[2][0][:, 6], ref[2][:, 6]) < 1e-12, name
 
 
+def _sel_many(o, ks, n):
+    return o[ks] if n in ("A_k", "B_kp", "B_kn") else o[:, ks]
+
+
+def test_reference_test_linearize_many_and_config2_chain():
+    """fixtures generated by the unmodified reference (make_golden.py many): its own test_linearize_many call in the DEFAULT
+    mode (test_discretizer.py:96-105), with the matching u and with the test's malformed (3, 3K) u on its own grid; and the
+    BASELINE config-2 chain (4 of 64 satellites, K=100): replayed propagation -> both quadrature modes"""
+    g = np.load(os.path.join(GOLDEN, "discretize_many.npz"))
+    c = O.OracleConstants(*g["const"])
+    x, u, uq, ks = g["m0_x"], g["m0_u"], g["m0_uq"], g["m0_ks"]
+    K = x.shape[1]
+    got = hostk.stacked(hostk.discretize_adaptive(x[None], u[None], 1.0, c)[0], 1, K)
+    gotq = hostk.stacked(hostk.discretize_ugrid(x[None], uq[None], 1.0, c, adaptive=dict())[0], 1, K)
+    for n, a, q in zip(NAMES, got, gotq):
+        assert rel_err(_sel_many(a[0], ks, n), g[f"m0_def_{n}"]) < 1e-12, n
+        assert rel_err(_sel_many(q[0], ks, n), g[f"m0q_def_{n}"]) < 1e-12, n
+    ks = g["m1_ks"]
+    y, uu, st, _, _ = hostk.propagate_rk45(g["m1_y0"], float(g["m1_tf"]), c, kind=2, thrust=(0.5, 0, 0), T=100)
+    assert st.max() == 0
+    uni = hostk.stacked(hostk.discretize(y, uu, 1.0, c)[0], 4, 100)
+    dfl = hostk.stacked(hostk.discretize_adaptive(y, uu, 1.0, c)[0], 4, 100)
+    for j in range(4):
+        assert rel_err(y[j], g[f"m1_s{j}_x"]) < TOL_RK45 and rel_err(uu[j], g[f"m1_s{j}_u"]) < TOL_RK45
+        for n, a, d in zip(NAMES, uni, dfl):
+            assert rel_err(_sel_many(a[j], ks, n), g[f"m1_s{j}_uni_{n}"]) < TOL_REF, (j, n)
+            assert rel_err(_sel_many(d[j], ks, n), g[f"m1_s{j}_def_{n}"]) < 1e-11, (j, n)
+
+
 def test_k_major_layout_is_a_permutation_of_the_satellite_major_one(const):
     """DstTab.km_ntot / km_soff: column = k n_tot + s_off + s.  Same arithmetic per interval, so the k-major result is the
     satellite-major one permuted, bit for bit -- full launch, ragged k-windows, both kernels, a rank's block inside a
