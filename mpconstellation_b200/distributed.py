@@ -96,7 +96,8 @@ class FusedGather:
         never sent again (6.7 % less NVLink traffic).  stagger: see mpc_set_gather_tuning.
         layout: "satmajor" (column = s (K-1) + k, per-satellite blocks) or "kmajor" (column = k N + s): in the k-major
         layout a k-window of the overlapped pass stores whole runs of consecutive columns, so the propagation can hide
-        behind the discretization at any world size (satellite-major: world <= 2 only).  Default: kmajor for world > 2."""
+        behind the discretization at any world size (satellite-major: world <= 2 only).  Default: kmajor (push modes:
+        satmajor)."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -131,7 +132,9 @@ class FusedGather:
             self.handle.barrier()
         if mode in ("push", "pushk"):
             self.peers = [ptrs[self.rank]] + [ptrs[r] for r in order[1:]]
-        self.layout = layout if layout is not None else ("kmajor" if self.world > 2 else "satmajor")
+        # (measured, profiles/r02_*_multi_gpu_w*: k-major is the faster layout of the overlapped pass at 2, 4 and 8 GPUs;
+        # the push modes copy per-satellite column blocks and keep the satellite-major one)
+        self.layout = layout if layout is not None else ("satmajor" if mode in ("push", "pushk") else "kmajor")
         if self.layout not in ("satmajor", "kmajor"):
             raise ValueError(f"unknown layout {self.layout!r}")
         if self.layout == "kmajor" and mode in ("push", "pushk"):
@@ -170,7 +173,7 @@ class FusedGather:
         satellite -- fine for HBM and for one peer, but with 7 peers the step is NVLink-ingress bound and the fragmented
         peer stores cost more than the hidden propagation buys (8 x B200: 7.77 ms back to back, 13.8 ms windowed;
         profiles/r01_n_overlap.txt) -- so there the overlapped pass is used at world <= 2 only.  In the k-major layout
-        (default for world > 2) a window stores whole runs of consecutive columns and the overlapped pass is used at any
+        (the default) a window stores whole runs of consecutive columns and the overlapped pass is used at any
         world size.  The push modes keep the two-kernel sequence.
         Returns (buf, y, u, status_prop); results are bit-identical to propagate_batch_device + discretize()."""
         from . import batch

@@ -36,7 +36,7 @@ full, _ = M.discretize_batch_device(y_all, u_all, tfd_all, const)
 torch.cuda.synchronize()
 t_local = timed(lambda: M.discretize_batch_device(x, u, tfd, const))
 
-fg = D.FusedGather(N * world, K, device=dev, skip_const=False)
+fg = D.FusedGather(N * world, K, device=dev, skip_const=False, layout="satmajor")
 fg.buf.zero_(); torch.cuda.synchronize(); dist.barrier()
 t_fused = timed(lambda: fg.discretize(x, u, tfd, const))
 variants = {}
@@ -44,7 +44,7 @@ ok_var = 1
 for mode in ("unicast", "multicast"):
     for stag in (0, 4, 8, 16):
         try:
-            fv = D.FusedGather(N * world, K, device=dev, mode=mode, skip_const=True, stagger=stag)
+            fv = D.FusedGather(N * world, K, device=dev, mode=mode, skip_const=True, stagger=stag, layout="satmajor")
         except Exception:
             continue
         fv.buf[:42].zero_(); fv.buf[49:].zero_(); torch.cuda.synchronize(); dist.barrier()
@@ -58,7 +58,7 @@ ok_view = np.array_equal(A, full[:49, -(K - 1):].T.reshape(K - 1, 7, 7).cpu().nu
 
 t_mc, ok_mc = float("nan"), 1
 try:
-    fm = D.FusedGather(N * world, K, device=dev, mode="multicast", skip_const=False)
+    fm = D.FusedGather(N * world, K, device=dev, mode="multicast", skip_const=False, layout="satmajor")
     fm.buf.zero_(); torch.cuda.synchronize(); dist.barrier()
     t_mc = timed(lambda: fm.discretize(x, u, tfd, const))
     ok_mc = int(torch.equal(fm.buf, full))

@@ -43,7 +43,7 @@ def timed(fn, reps=6):
 lines, ok_all = [], 1
 for mode in os.environ.get("MODES", "unicast,multicast").split(","):
     try:
-        fg = D.FusedGather(N * world, K, device=dev, mode=mode)
+        fg = D.FusedGather(N * world, K, device=dev, mode=mode, layout="satmajor")
     except Exception as exc:
         if rank == 0:
             print(f"{mode} unavailable: {exc}")
