@@ -33,6 +33,7 @@ class Simulator:
         # "rk45": the reference's integrator (scipy RK45 + step-size controller + dense-output samples, simulator.py:185-187)
         # replayed step for step on the device; "rk4": fixed-step RK4, ceil(1/(max_time_step (T-1))) steps per sample
         self.integrator = "rk45"
+        self.last_n_steps = None
         self.device = 0
 
     # -- batched core --------------------------------------------------------------------------------
@@ -46,8 +47,12 @@ class Simulator:
             mode = dict(n_sub=batch.default_n_sub(T, self.max_time_step))
         else:
             raise ValueError(f"unknown integrator {self.integrator!r} (rk45 | rk4)")
+        if self.integrator == "rk45":
+            mode["n_steps"] = np.zeros(len(sats), dtype=np.int32)
         y, u, t, _ = batch.propagate_batch(y0, tf, controller, const, include_drag=self.include_drag,
                                            include_J2=self.include_J2, T=T, device=self.device, **mode)
+        # steps attempted per satellite by the replayed integrator (scipy's sol.nfev = 2 + 6 steps)
+        self.last_n_steps = mode.get("n_steps")
         return y, u, t
 
     def run(self, tf=10):
@@ -101,7 +106,9 @@ class Simulator:
     def get_trajectory_ODE(self, sat, tf, u_func):
         """ref: simulator.py:164-189.  Returns an object with .y (7,T) and .t (T,) like solve_ivp's."""
         y, u, t = self._propagate([sat], tf, spec_from(u_func))
-        return SimpleNamespace(y=y[0], t=t, u=u[0], success=True, status=0, message=f"{self.integrator} on sm_100a")
+        nfev = None if self.last_n_steps is None else 2 + 6 * int(self.last_n_steps[0])     # as solve_ivp counts them
+        return SimpleNamespace(y=y[0], t=t, u=u[0], success=True, status=0, nfev=nfev,
+                               message=f"{self.integrator} on sm_100a")
 
     def save_to_csv(self, suffix="", redimensionalize=True, directory="."):
         """ref: simulator.py:192-201 -- one `trajectory_<date>_<sat.id><suffix>.csv` per satellite, rows = samples,

@@ -176,6 +176,7 @@ def test_get_trajectory_ode_signature(M, gold_prop):
     sim.eval_points = 200
     sol = sim.get_trajectory_ODE(sat, 2, c.get_u_func())
     assert sol.y.shape == (7, 200) and sol.t.shape == (200,)
+    assert sol.nfev == 6002                                      # what scipy reports for the reference's call
     assert rel_err(sol.y, gp["p1_y"]) < TOL_STATE
     with pytest.raises(NotImplementedError):
         sim.get_trajectory_ODE(sat, 2, lambda x, tau: np.zeros(3))
