@@ -249,7 +249,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                     double e = st6.k[i] * ew[6];
 #pragma unroll
                     for (int l = 0; l < 6; ++l) e = fma(kx[l][i], ew[l], e);
-                    const double q = e * hs * fast_rcp(atol + fmax(fabs(x[i]), fabs(xn[i])) * rtol);
+                    const double q = e * hs * fast_rcp1(atol + fmax(fabs(x[i]), fabs(xn[i])) * rtol);
                     esum = fma(q, q, esum);
                 }
                 // -- Phi columns: global (L2) -> registers -> global, stage matrices from shared memory ----------------
@@ -266,7 +266,6 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
 #pragma unroll
                         for (int i = 0; i < 6; ++i) pn[i] = cur[(long long)((c + 1) * 6 + i) * pitch];
                     }
-                    const double dflag = (c == 6) ? 1.0 : 0.0;
 #pragma unroll
                     for (int s = 0; s < 7; ++s) {
                         double q[6];
@@ -294,7 +293,13 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                         }
                         const int b = kDfAcc + s * kStage;
                         const double gxx = SM(b), gxy = SM(b + 1), gxz = SM(b + 2), gyy = SM(b + 3), gyz = SM(b + 4), gzz = SM(b + 5);
-                        double dx = SM(b + 6) * dflag, dy_ = SM(b + 7) * dflag, dz = SM(b + 8) * dflag;
+                        // (d = -u/m^2 forces the mass column only: loaded for c == 6, a warp-uniform condition)
+                        double dx = 0.0, dy_ = 0.0, dz = 0.0;
+                        if (c == 6) {
+                            dx = SM(b + 6);
+                            dy_ = SM(b + 7);
+                            dz = SM(b + 8);
+                        }
                         if (DRAG) {   // + V q_v
                             const double vxx = SM(b + 9), vxy = SM(b + 10), vxz = SM(b + 11), vyy = SM(b + 12), vyz = SM(b + 13), vzz = SM(b + 14);
                             dx = fma(vxz, q[5], fma(vxy, q[4], fma(vxx, q[3], dx)));
@@ -313,7 +318,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                                 double e = 0.0;
 #pragma unroll
                                 for (int l = 0; l < 7; ++l) e = fma((i < 3) ? kr[l][i] : kv[l][i - 3], ew[l], e);
-                                const double qq = e * hs * fast_rcp(atol + fmax(fabs(p[i]), fabs(q[i])) * rtol);
+                                const double qq = e * hs * fast_rcp1(atol + fmax(fabs(p[i]), fabs(q[i])) * rtol);
                                 esum = fma(qq, qq, esum);
                             }
                         }

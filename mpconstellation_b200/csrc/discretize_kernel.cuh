@@ -56,6 +56,16 @@ __device__ __forceinline__ double fast_rcp(double a)
     return y;
 }
 
+// reciprocal to ~1e-12 (MUFU seed + ONE Newton step): for the scales of the RK45 error norm, where the controller turns
+// a relative error of 1e-12 into a step-size change of 2e-13
+__device__ __forceinline__ double fast_rcp1(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a, y, 1.0);
+    return fma(y, e, y);
+}
+
 __device__ __forceinline__ double fast_rsqrt(double a)
 {
     // reciprocal square root: MUFU.RSQ64H seed (~20 bits) + 2 Newton steps: relative error

@@ -51,7 +51,7 @@ def _build(SO, force, opt):
             n_sub += n
         assert "asm(" not in text, f"{s}: inline PTX the host build does not know"
         open(os.path.join(BUILD, s), "w").write(text)
-    assert n_sub == 2, "expected exactly the two MUFU seeds to be replaced"
+    assert n_sub == 3, "expected exactly the three MUFU seeds (fast_rcp, fast_rcp1, fast_rsqrt) to be replaced"
     cmd = ["g++"] + opt + ["-std=c++17", "-pthread", "-shared", "-fPIC", "-mfma", "-ffp-contract=fast", "-fno-math-errno", "-w",
            "-I", os.path.join(HERE, "include"), "-I", BUILD, "-o", SO, os.path.join(HERE, "hostk_main.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -108,3 +108,42 @@ def test_chunked_gather_world2_matches_single_process(tmp_path, const):
             assert np.array_equal(got, want), (s, name)
     # the padded columns of the short rank stay zero
     assert not np.any(full[1][:, 2 * (K - 1):])
+
+
+def _worker_kmajor(rank, world, port, n_sats, K, tf, tmp):
+    """every rank discretizes its shard with the HOST BUILD of the kernel sources straight into its place of a k-major
+    gathered buffer (DstTab.km_ntot / km_soff, as FusedGather._opts sets them), the buffers are summed over gloo (disjoint
+    column sets: the stand-in for the peer stores of the fused gather)"""
+    import torch
+    import torch.distributed as dist
+    import hostk
+    from oracle.mpc_oracle import OracleConstants
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "discretize.npz"))
+    const = OracleConstants(*g["const"])
+    _, x, u = synth_batch(n_sats, K, tf, const)
+    s0, s1 = D.shard_range(n_sats, rank, world)
+    buf = np.zeros((105, n_sats * (K - 1)))
+    hostk.discretize(x[s0:s1], u[s0:s1], tf, const, out=buf, pitch=n_sats * (K - 1), km_ntot=n_sats, km_soff=s0)
+    t = torch.from_numpy(buf)
+    dist.all_reduce(t)
+    if rank == 0:
+        np.save(os.path.join(tmp, "kmajor.npy"), t.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_k_major_gathered_layout_world2(tmp_path, const):
+    import torch.multiprocessing as mp
+    import hostk
+    n_sats, K, tf, world = 5, 7, 0.3, 2          # ragged: ranks hold 3 and 2 satellites
+    mp.spawn(_worker_kmajor, args=(world, _free_port(), n_sats, K, tf, str(tmp_path)), nprocs=world, join=True)
+    full = np.load(tmp_path / "kmajor.npy")
+    _, x, u = synth_batch(n_sats, K, tf, const)
+    ref, _ = hostk.discretize(x, u, tf, const)                      # single process, satellite-major
+    vk = D.GatheredView(full, n_sats, K, world, "kmajor")
+    vs = D.GatheredView(ref, n_sats, K, world, "global")
+    for s in range(n_sats):
+        for name, got, want in zip(NAMES, vk.sat(s), vs.sat(s)):
+            assert np.array_equal(got, want), (s, name)
