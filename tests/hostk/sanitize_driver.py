@@ -50,6 +50,30 @@ for N, K in ((1, 2), (3, 5), (33, 4), (7, 13)):         # K = 2, batches that do
                 hostk.propagate(y0, 0.3, const, kind=kind, thrust=(0.1, 0.2, -0.1), table=tab if kind == 3 else None,
                                 end_tau=0.7, include_drag=dj[0], include_J2=dj[1], T=T, n_sub=2, seg_len=seg)
                 n += 1
+    # the replayed RK45 propagator: controller laws, drag / J2, progress words (one count per satellite), T = 1, a step
+    # controller that rejects (max_step 1), fewer satellites per warp
+    for kind in (0, 2, 3):
+        for T, seg, ms, lpw in ((1, 0, 1e-3, 32), (2, 1, 0.05, 32), (K, 2, 1.0, 4), (K + 3, 0, 0.05, 1)):
+            hostk.propagate_rk45(y0, 0.3, const, kind=kind, thrust=(0.1, 0.2, -0.1), table=tab if kind == 3 else None,
+                                 end_tau=0.7, include_drag=(kind == 0), include_J2=(kind == 0), T=T, max_step=ms, lpw=lpw,
+                                 seg_len=seg, spec=(kind != 2))
+            n += 1
+    # the thread-group kernel (8 host threads per interval), with the idle groups of a last partial warp
+    if N <= 3:
+        for n_sub in (2, 7):
+            hostk.discretize_group(x, u, 0.3, const, include_J2=True, n_sub=n_sub, extra_groups=2)
+            n += 1
+    # the k-major gathered layout: this batch as the middle shard of a larger buffer, window by window
+    ntot, soff = N + 5, 2
+    outk = np.full((105, ntot * (K - 1)), np.nan)
+    for k0 in range(0, K - 1, seg_k := max(1, (K - 1) // 2)):
+        hostk.discretize(x, u, 0.3, const, k0=k0, kc=min(seg_k, K - 1 - k0), out=outk, pitch=ntot * (K - 1), status=st,
+                         km_ntot=ntot, km_soff=soff)
+        n += 1
+    assert np.isfinite(outk.reshape(105, K - 1, ntot)[:, :, soff:soff + N]).all()
+    # the round-1 build of the default-mode kernel (kept for A/B)
+    hostk.discretize_adaptive(x, u, 0.3, const, v1=True)
+    n += 1
     # constraint terms with u on its own (longer and shorter) grid, and the sparse Jacobian
     for Ku in (1, K, K + 4):
         hostk.constraint_terms(x, np.ascontiguousarray(np.resize(u, (N, 3, Ku))), const.MU)
