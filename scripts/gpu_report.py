@@ -44,6 +44,40 @@ for tag in ("c0", "c1"):
     worst = max(float(np.max(np.abs(np.asarray(ct[k][0]) - gc[f"{tag}_{k}"])) / max(1.0, float(np.max(np.abs(gc[f"{tag}_{k}"])))))
                 for k in ct if k != "ubar_hat")
     print(f"  {tag} get_constraint_terms: max scaled error over all terms {worst:.1e}")
+# ---- round 2: propagation with the replayed integrator, the coast-to-thrust fixture, the reference's test_linearize_many
+gp = np.load(os.path.join(ROOT, "tests/golden/propagate.npz"))
+x0 = gp["x0_dim"]
+hub = lambda: M.Satellite(x0[0:3].copy(), x0[3:6].copy(), float(x0[6]))
+print("== propagated states vs the unmodified reference (Simulator, default integrator = its solve_ivp call replayed)")
+for tag, tf, kw, ctl in (("p0 5-orbit coast, drag + J2", 5, {}, None),
+                         ("p1 tangential 0.5, tf 2", 2, dict(base_res=100, include_drag=False, include_J2=False), ("tan", 0.5)),
+                         ("p2 constant thrust, drag + J2", 3, {}, ("const", gp["p2_thrust"])),
+                         ("p4 tangential 0.1, drag + J2", 2, {}, ("tan", 0.1)),
+                         ("p5 sequence table ENDING INSIDE the run (end_tau 0.75)", 2, dict(base_res=60, include_drag=False, include_J2=False), ("seq", None))):
+    sat = hub()
+    scale = M.SatelliteScale(sat=sat)
+    c = (M.Controller() if ctl is None else M.ConstantTangentialThrustController([sat], ctl[1]) if ctl[0] == "tan"
+         else M.ConstantThrustController(thrust=ctl[1]) if ctl[0] == "const" else M.SequenceController(u=gp["p5_u_tab"], tf_u=1.5, tf_sim=2.0))
+    errs = []
+    for integ in ("rk45", "rk4"):
+        sim = M.Simulator(sats=[hub()], controller=c, scale=scale, **kw)
+        sim.integrator = integ
+        sim.run(tf=tf)
+        errs.append(norm_rel_err(sim.sim_data[sim.sats[0].id], gp[tag[:2] + "_y"]))
+    print(f"  {tag}: replayed RK45 {errs[0]:.1e} | fixed-step RK4 (round 1) {errs[1]:.1e}")
+gco = np.load(os.path.join(ROOT, "tests/golden/discretize_coast.npz")); cco = OracleConstants(*gco["const"])
+for tag in ("c11", "c24"):
+    for mode, uni in (("uni", True), ("def", False)):
+        d = M.Discretizer(cco); d.use_uniform_steps = uni
+        out = d.discretize(M.Simulator.satellite_dynamics, gco[tag + "_x"], gco[tag + "_u"], float(gco[tag + "_tf"]))
+        print(f"  coast-to-thrust {tag} use_uniform_steps={uni!s:5}: " + "  ".join(f"{n} {norm_rel_err(o, gco[f'{tag}_{mode}_{n}']):.1e}" for n, o in zip(NAMES, out))
+              + f"  | mass rows of B_kp / B_kn {norm_rel_err(out[1][:, 6], gco[f'{tag}_{mode}_B_kp'][:, 6]):.1e} / {norm_rel_err(out[2][:, 6], gco[f'{tag}_{mode}_B_kn'][:, 6]):.1e}")
+gm = np.load(os.path.join(ROOT, "tests/golden/discretize_many.npz")); cm_ = OracleConstants(*gm["const"])
+selm = lambda o, ks: o[ks] if o.ndim == 3 else o[:, ks]
+d = M.Discretizer(cm_)
+for tag, uu in (("m0", gm["m0_u"]), ("m0q", gm["m0_uq"])):
+    out = d.discretize(M.Simulator.satellite_dynamics, gm["m0_x"], uu, 1.0)
+    print(f"  reference test_linearize_many, DEFAULT mode, u {uu.shape}: " + "  ".join(f"{n} {norm_rel_err(selm(o, gm['m0_ks']), gm[f'{tag}_def_{n}']):.1e}" for n, o in zip(NAMES, out)))
 dev = torch.device("cuda:0")
 ctrl = M.ConstantTangentialThrustController(tangential_thrust=0.5)
 print("== kernel times (device-resident, CUDA events, best of 5)")
