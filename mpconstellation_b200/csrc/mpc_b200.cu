@@ -306,9 +306,12 @@ int launch_adaptive_k(const double *x, const double *u, const double *tf, const 
     const long long n_int = (long long)n_sats * (K - 1);
     int block = g_default_block.load(std::memory_order_relaxed);
     if (n_int < 148LL * 256) block = 32;
-    if (!DRAG && !GENU) {
+    if (!DRAG) {
         if (block == 256) return launch_default_b<J2, GENU, DRAG, 256>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
-        if (block == 128) return launch_default_b<J2, GENU, DRAG, 128>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+        if (block == 128 && !GENU) return launch_default_b<J2, GENU, DRAG, 128>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
+    } else if (block != 32) {
+        // the drag branch keeps V_s as well: 153 slots per thread, 5 warps fill the SM's shared memory
+        return launch_default_b<J2, GENU, DRAG, 160>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
     }
     return launch_default_b<J2, GENU, DRAG, 32>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
 }
