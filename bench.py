@@ -568,7 +568,7 @@ def gpu_arm(args):
         barrier()
         t0 = time.perf_counter()
         res, _, _ = M.propagate_discretize(y0_h, tf, ctrl, const, T=K, n_sub_prop=n_prop, n_sub_disc=n_sub, out=out_h,
-                                           y_out=y_h, u_out=u_h, status=st_h, device=local)
+                                           y_out=y_h, u_out=u_h, status=st_h, device=local, layout=args.e2e_layout)
         dt = time.perf_counter() - t0
         if i >= 2:
             e2e_t.append(dt)
@@ -587,7 +587,9 @@ def gpu_arm(args):
                     else fused.buf[:, s0 * (K - 1):(s0 + 1) * (K - 1)])
     else:
         dev_cols = local_out[:, :K - 1]
-    same = bool(np.array_equal(out_h[:, :K - 1], dev_cols.cpu().numpy()))
+    # (the K-1 intervals of the first satellite of this rank, wherever the host layout puts them)
+    host_cols = out_h[:, 0:(K - 1) * N:N] if args.e2e_layout == "kmajor" else out_h[:, :K - 1]
+    same = bool(np.array_equal(host_cols, dev_cols.cpu().numpy()))
     gathered_ok = None
     if fused is not None:
         # every rank must hold every other rank's block: compare a column of each peer block with its owner
@@ -626,7 +628,10 @@ def gpu_arm(args):
         "e2e": {"value": n_int_total / e2e_s, "unit": "intervals/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(y0_h.nbytes + N * 8),
                 "d2h_bytes_per_step": int(out_h.nbytes + y_h.nbytes + u_h.nbytes + n_int * 4),
-                "api": "mpconstellation_b200.propagate_discretize (C-ABI mpc_propagate_discretize_host), pinned host buffers",
+                "api": ("mpconstellation_b200.propagate_discretize(layout='kmajor') (C-ABI mpc_propagate_discretize_host_layout: k-windows "
+                        "gated on the propagation's progress, every window read back while the next one runs), pinned host buffers"
+                        if args.e2e_layout == "kmajor" else
+                        "mpconstellation_b200.propagate_discretize (C-ABI mpc_propagate_discretize_host), pinned host buffers"),
                 "host_cpus_rank0": len(cpus),
                 "matches_device_path": same},
         "gather": {"mode": gather_mode + (":" + args.fused_mode if fused is not None else ""), "verified": gathered_ok,
@@ -720,6 +725,8 @@ def main():
     ap.add_argument("--total-sats", dest="total_sats", type=int, default=0,
                     help="strong scaling: this many satellites in total, sharded over the ranks (5025 = BASELINE configs[3])")
     ap.add_argument("--no-configs", dest="no_configs", action="store_true", help="skip the configs 1/2/5 record (N=1)")
+    ap.add_argument("--e2e-layout", dest="e2e_layout", default="kmajor", choices=["satmajor", "kmajor"],
+                    help="layout of the matrices the end-to-end leg hands back (kmajor: the streamed pass)")
     ap.add_argument("--layout", default=None, choices=["satmajor", "kmajor"], help="gathered layout of the fused all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true",

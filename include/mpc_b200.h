@@ -38,6 +38,11 @@ extern "C" {
 #define MPC_ROW_SIGMA 91 /*  7 rows: Sigma_k                                linearize_discretize.py:74,79 */
 #define MPC_ROW_XI 98    /*  7 rows: xi_k                                   linearize_discretize.py:75,80 */
 
+/* layouts of a [105][n_sats (K-1)] result: column = s (K-1) + k (per-satellite blocks) or k n_sats + s (interval k of all
+ * satellites adjacent; see mpc_discretize_batch_gather / mpc_propagate_discretize_host_layout) */
+#define MPC_LAYOUT_SAT_MAJOR 0
+#define MPC_LAYOUT_K_MAJOR 1
+
 /* return codes */
 #define MPC_SUCCESS 0
 #define MPC_E_INVALID (-1)     /* bad argument */
@@ -238,6 +243,19 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
                                   double *out_host, int32_t *status_host);
 
 /*
+ * mpc_propagate_discretize_host with the result in the K-MAJOR layout (out_host[row][k n_sats + s], see
+ * MPC_LAYOUT_K_MAJOR) and the propagation hidden behind the discretization AND the read-back: the intervals are
+ * discretized window by window along k as the propagation publishes its progress (mpc_propagate_discretize), and the
+ * columns of a finished window -- one contiguous range per row in this layout -- go back over PCIe while the next window
+ * runs.  The first byte leaves the device ~0.3 ms after the call starts instead of after the whole propagation (1.1 ms).
+ * status_host stays [n_sats][T-1].  layout = MPC_LAYOUT_SAT_MAJOR is mpc_propagate_discretize_host.
+ */
+int mpc_propagate_discretize_host_layout(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                         const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                         int n_sub_prop, int n_sub_disc, double *y_host, double *u_host, double *out_host,
+                                         int32_t *status_host, int layout);
+
+/*
  * The same SCP inner step on DEVICE buffers, enqueued on `stream`, with the propagation overlapped with the
  * discretization (control.py:180-188: run_nonlinear -> extract_uk -> Discretizer.discretize, for every satellite).
  * The propagation is sequential in tau and latency-bound; interval k only needs the samples k and k+1.  The intervals
@@ -275,8 +293,6 @@ int mpc_propagate_discretize_multi(mpc_ctx *ctx, const double *y0, const double 
  * (optimizer.py:327-339), so the layout is a stride, not a copy (GatheredView in the Python package).
  * skip_const / stagger_phases: as mpc_set_gather_tuning.  Fixed-step (two-node-step) kernel only.
  */
-#define MPC_LAYOUT_SAT_MAJOR 0
-#define MPC_LAYOUT_K_MAJOR 1
 typedef struct mpc_gather_opts {
     int32_t layout;         /* MPC_LAYOUT_* */
     int32_t skip_const;     /* 0, 1, 2: see mpc_set_gather_tuning */

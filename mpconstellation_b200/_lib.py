@@ -119,6 +119,7 @@ def lib():
     L.mpc_discretize_batch_host.argtypes = [vp, _DP, _DP, _DP, pp, i, i, i, _DP, _DP]
     L.mpc_propagate_batch_host.argtypes = [vp, _DP, _DP, pp, pc, i, i, i, _DP, _DP, _DP]
     L.mpc_propagate_discretize_host.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, _DP]
+    L.mpc_propagate_discretize_host_layout.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, _DP, i]
     L.mpc_propagate_discretize.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, _DP, i64, i64, _DP, _DP, i, vp]
     L.mpc_propagate_discretize_multi.argtypes = [vp, _DP, _DP, pp, pp, pc, i, i, i, i, _DP, _DP, ctypes.POINTER(ctypes.c_void_p), i, i64, i64, _DP, _DP, i, vp]
     pg = ctypes.POINTER(MpcGatherOpts)
@@ -134,7 +135,7 @@ def lib():
     L.mpc_set_gather_tuning.restype = i
     L.mpc_set_tuning.argtypes = [i]
     L.mpc_set_tuning.restype = i
-    for name in ("mpc_discretize_batch_gather", "mpc_propagate_discretize_gather", "mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host", "mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
+    for name in ("mpc_propagate_discretize_host_layout", "mpc_discretize_batch_gather", "mpc_propagate_discretize_gather", "mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host", "mpc_device_info", "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_propagate_batch",
                  "mpc_discretize_batch_adaptive", "mpc_discretize_batch_adaptive_host",
                  "mpc_discretize_batch_ugrid", "mpc_discretize_batch_ugrid_host",
                  "mpc_ctx_create", "mpc_ctx_destroy", "mpc_discretize_batch_host", "mpc_propagate_batch_host",
@@ -149,6 +150,7 @@ EXPORTED_SYMBOLS = [
     "mpc_version", "mpc_last_error", "mpc_device_count", "mpc_device_info", "mpc_launch_count",
     "mpc_discretize_batch", "mpc_discretize_batch_multi", "mpc_discretize_batch_adaptive", "mpc_discretize_batch_ugrid", "mpc_propagate_batch",
     "mpc_propagate_batch_rk45", "mpc_propagate_batch_rk45_host", "mpc_discretize_batch_gather", "mpc_propagate_discretize_gather",
+    "mpc_propagate_discretize_host_layout",
     "mpc_ctx_create", "mpc_ctx_destroy", "mpc_host_alloc", "mpc_host_free",
     "mpc_discretize_batch_host", "mpc_discretize_batch_adaptive_host", "mpc_discretize_batch_ugrid_host", "mpc_propagate_batch_host", "mpc_propagate_discretize_host", "mpc_propagate_discretize", "mpc_propagate_discretize_multi",
     "mpc_constraint_terms", "mpc_constraint_terms_host", "mpc_discretize_batch_push", "mpc_fill_const_rows",

@@ -50,15 +50,18 @@ class DiscretizedBatch:
     """SoA result of a batched discretization plus reference-shaped views.
 
     soa: [105, N*(K-1)] float64 (rows: A 49 | B_kp 21 | B_kn 21 | Sigma 7 | xi 7), status: [N, K-1] int32.
-    sat(s) returns (A_k, B_kp, B_kn, Sigma_k, xi_k) with the shapes and order of
-    Discretizer.discretize (linearize_discretize.py:390); they are views, no copy is made.
+    layout "satmajor": column = s (K-1) + k (per-satellite blocks); "kmajor": column = k N + s (what the streamed host
+    pass propagate_discretize(layout="kmajor") writes).  sat(s) returns (A_k, B_kp, B_kn, Sigma_k, xi_k) with the shapes
+    and order of Discretizer.discretize (linearize_discretize.py:390); they are views in either layout, no copy is made.
     """
 
-    def __init__(self, soa, status, n_sats, K):
-        self.soa, self.status, self.n_sats, self.K = soa, status, n_sats, K
+    def __init__(self, soa, status, n_sats, K, layout="satmajor"):
+        self.soa, self.status, self.n_sats, self.K, self.layout = soa, status, n_sats, K, layout
 
     def _rows(self, r0, nrows, s):
         n = self.K - 1
+        if self.layout == "kmajor":
+            return self.soa[r0:r0 + nrows, s::self.n_sats]
         return self.soa[r0:r0 + nrows, s * n:(s + 1) * n]
 
     def sat(self, s):
@@ -71,7 +74,10 @@ class DiscretizedBatch:
     def stacked(self):
         """(A[N,K-1,7,7], B_kp[N,K-1,7,3], B_kn[N,K-1,7,3], Sigma[N,7,K-1], xi[N,7,K-1]) as views."""
         N, n = self.n_sats, self.K - 1
-        v = self.soa.reshape(_lib.MPC_OUT_ROWS, N, n)
+        if self.layout == "kmajor":
+            v = self.soa.reshape(_lib.MPC_OUT_ROWS, n, N).transpose(0, 2, 1)      # [105, N, n], strided
+        else:
+            v = self.soa.reshape(_lib.MPC_OUT_ROWS, N, n)
         A = v[0:49].transpose(1, 2, 0).reshape(N, n, 7, 7)
         Bp = v[49:70].transpose(1, 2, 0).reshape(N, n, 7, 3)
         Bn = v[70:91].transpose(1, 2, 0).reshape(N, n, 7, 3)
@@ -237,9 +243,11 @@ def propagate_batch(y0, tf, controller, const, include_drag=True, include_J2=Tru
 
 def propagate_discretize(y0, tf, controller, const, T, prop_drag=False, prop_J2=False, disc_J2=False,
                          n_sub_prop=None, n_sub_disc=100, out=None, y_out=None, u_out=None, device=0, check=True,
-                         status=None):
+                         status=None, layout="satmajor"):
     """One SCP linearization pass on the device: propagate -> extract_uk -> discretize, the reference
     trajectory staying in HBM between the kernels (control.py:180-188 pattern).  K = T.
+    layout="kmajor": the matrices come back in the k-major layout (DiscretizedBatch views hide it) through the streamed
+    pass -- windows along k gated on the propagation's progress, every window read back while the next one runs.
     Returns (DiscretizedBatch, y [N,7,T], u [N,3,T])."""
     ctx = _ctx(device)
     y0 = _f64(y0)
@@ -261,12 +269,14 @@ def propagate_discretize(y0, tf, controller, const, T, prop_drag=False, prop_J2=
     pp = _lib.make_params(const, prop_J2, prop_drag)
     pd = _lib.make_params(const, disc_J2, False)
     c, _keep = _ctrl_struct(spec, N)
+    if layout not in ("satmajor", "kmajor"):
+        raise ValueError(f"unknown layout {layout!r}")
     with _lock(device):
-        _lib.check(_lib.lib().mpc_propagate_discretize_host(ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(pp),
-                                                            ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop),
-                                                            int(n_sub_disc), _lib.addr(y), _lib.addr(uo),
-                                                            _lib.addr(out), _lib.addr(status)))
-    res = DiscretizedBatch(out, status.reshape(N, T - 1), N, T)
+        _lib.check(_lib.lib().mpc_propagate_discretize_host_layout(
+            ctx, _lib.addr(y0), _lib.addr(tfv), ctypes.byref(pp), ctypes.byref(pd), ctypes.byref(c), N, T, int(n_sub_prop),
+            int(n_sub_disc), _lib.addr(y), _lib.addr(uo), _lib.addr(out), _lib.addr(status),
+            _lib.LAYOUT_K_MAJOR if layout == "kmajor" else _lib.LAYOUT_SAT_MAJOR))
+    res = DiscretizedBatch(out, status.reshape(N, T - 1), N, T, layout)
     if check:
         res.raise_on_error()
     return res, y, uo

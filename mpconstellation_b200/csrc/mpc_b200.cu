@@ -1273,6 +1273,102 @@ int prop_disc_overlapped(mpc_ctx *ctx, const double *y0, const double *tf, const
 
 }  // namespace
 
+// Host-buffer pass in the k-major layout: windows along k gated on the propagation's progress, every finished window
+// read back while the next one runs (see the header).
+extern "C" int mpc_propagate_discretize_host_layout(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
+                                                    const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
+                                                    int n_sub_prop, int n_sub_disc, double *y_host, double *u_host,
+                                                    double *out_host, int32_t *status_host, int layout)
+{
+    if (layout == MPC_LAYOUT_SAT_MAJOR)
+        return mpc_propagate_discretize_host(ctx, y0, tf, p_prop, p_disc, ctrl, n_sats, T, n_sub_prop, n_sub_disc, y_host, u_host,
+                                             out_host, status_host);
+    if (layout != MPC_LAYOUT_K_MAJOR) return fail(MPC_E_INVALID, "unknown layout %d", layout);
+    if (!ctx || !y0 || !tf || !p_prop || !p_disc || !out_host) return fail(MPC_E_INVALID, "null pointer argument");
+    const int K = T;
+    if (n_sats < 0 || K < 2 || n_sub_prop < 0 || n_sub_disc < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 2, n_sub_prop >= 0, n_sub_disc >= 1");
+    if (p_disc->include_drag || !g_pair.load(std::memory_order_relaxed) || g_tuning.load(std::memory_order_relaxed) != 0)
+        return fail(MPC_E_UNSUPPORTED, "the k-major layout is implemented by the two-node-step kernel only");
+    int rc = check_ctrl(ctrl);
+    if (rc) return rc;
+    if (n_sats == 0) return MPC_SUCCESS;
+    const long long n_int = (long long)n_sats * (K - 1);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if ((rc = ensure(ctx->d_y0, ctx->cap_y0, (size_t)n_sats * 7))) return rc;
+    if ((rc = ensure(ctx->d_tf, ctx->cap_tf, (size_t)n_sats))) return rc;
+    if ((rc = ensure(ctx->d_x, ctx->cap_x, (size_t)n_sats * 7 * K))) return rc;
+    if ((rc = ensure(ctx->d_u, ctx->cap_u, (size_t)n_sats * 3 * K))) return rc;
+    if ((rc = ensure(ctx->d_out, ctx->cap_out, (size_t)n_int * MPC_OUT_ROWS))) return rc;
+    if ((rc = ensure(ctx->d_status, ctx->cap_status, (size_t)n_int))) return rc;
+    if ((rc = ensure(ctx->d_status2, ctx->cap_status2, (size_t)n_sats))) return rc;
+    if ((rc = ensure_overlap(ctx))) return rc;
+    // windows: each at least one wave of the kernel, at most 16 (the read-back of a window is what paces the pipeline)
+    const long long wave = (long long)ctx->sm_count * 2 * kDiscBlock;
+    int nw = (int)std::max<long long>(1, std::min<long long>(16, std::min<long long>(n_int / wave, K - 1)));
+    const bool gated = nw >= 2 && stream_wait_value32() != nullptr;
+    if (!gated) nw = 1;
+    const int seg = (K - 1 + nw - 1) / nw;
+    nw = (K - 1 + seg - 1) / seg;
+    if ((rc = ensure_events(ctx, (size_t)nw + 2))) return rc;
+    cudaStream_t st = ctx->s_compute;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_y0, y0, (size_t)n_sats * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_tf, tf, (size_t)n_sats * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = upload_table(ctx, ctrl, n_sats, st))) return rc;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_progress, 0, kMaxWindows * sizeof(unsigned int), st));
+    CUDA_TRY(cudaEventRecord(ctx->ev_ov[0], st));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_prop, ctx->ev_ov[0], 0));
+    for (cudaStream_t w : ctx->s_win) CUDA_TRY(cudaStreamWaitEvent(w, ctx->ev_ov[0], 0));
+    unsigned int gate = 0;
+    const double *et_dev = ctrl->end_tau_per_sat ? ctx->d_endtau : nullptr;
+    if ((rc = prop_device(ctx->d_y0, ctx->d_tf, p_prop, ctrl, ctx->d_tab, et_dev, n_sats, K, mode_of(n_sub_prop), ctx->d_x, ctx->d_u,
+                          ctx->d_status2, ctx->s_prop, gated ? ctx->d_progress : nullptr, seg, &gate)))
+        return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev_ov[1], ctx->s_prop));
+    const mpc::DiscParams P = disc_params(p_disc);
+    mpc::DstTab tab{};
+    tab.p[0] = ctx->d_out;
+    tab.km_ntot = n_sats;
+    tab.km_soff = 0;
+    for (int b = 0; b < nw; ++b) {
+        cudaStream_t sw = ctx->s_win[b & 1];
+        const int k0 = b * seg, kc = std::min(seg, K - 1 - k0);
+        if (!gated || stream_wait_value32()((CUstream)sw, (CUdeviceptr)(uintptr_t)(ctx->d_progress + b), gate,
+                                            CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            CUDA_TRY(cudaStreamWaitEvent(sw, ctx->ev_ov[1], 0));
+        rc = p_disc->include_j2
+                 ? launch_window<true>(1, ctx->d_x, ctx->d_u, ctx->d_tf, P, n_sats, K, n_sub_disc, tab, n_int, 0, ctx->d_status, sw, k0, kc)
+                 : launch_window<false>(1, ctx->d_x, ctx->d_u, ctx->d_tf, P, n_sats, K, n_sub_disc, tab, n_int, 0, ctx->d_status, sw, k0, kc);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev[b], sw));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev[b], 0));
+        // the window's columns are one contiguous range per row: [k0 n_sats, (k0 + kc) n_sats)
+        if ((rc = copy_out_chunk(out_host, ctx->d_out, n_int, (long long)k0 * n_sats, (long long)kc * n_sats, ctx->s_copy))) return rc;
+    }
+    // trajectory, inputs and status words follow the matrices on the copy stream (the propagation has long finished)
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_ov[1], 0));
+    if (y_host) CUDA_TRY(cudaMemcpyAsync(y_host, ctx->d_x, (size_t)n_sats * 7 * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
+    if (u_host) CUDA_TRY(cudaMemcpyAsync(u_host, ctx->d_u, (size_t)n_sats * 3 * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
+    fill_const_rows(out_host, n_int);
+    if (status_host) {
+        if ((rc = ensure_stage(ctx, (size_t)n_int + n_sats))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(is_pinned(status_host) ? status_host : ctx->h_stage, ctx->d_status, (size_t)n_int * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, ctx->s_copy));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage + n_int, ctx->d_status2, (size_t)n_sats * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_copy));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_prop));
+    for (cudaStream_t w : ctx->s_win) CUDA_TRY(cudaStreamSynchronize(w));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (status_host) {
+        if (!is_pinned(status_host)) memcpy(status_host, ctx->h_stage, (size_t)n_int * sizeof(int32_t));
+        const int32_t *ps = ctx->h_stage + n_int;
+        for (int s = 0; s < n_sats; ++s)
+            if (ps[s])
+                for (int k = 0; k < K - 1; ++k) status_host[(size_t)s * (K - 1) + k] = ps[s];
+    }
+    return MPC_SUCCESS;
+}
+
 extern "C" int mpc_propagate_discretize(mpc_ctx *ctx, const double *y0, const double *tf, const mpc_params *p_prop,
                                         const mpc_params *p_disc, const mpc_controller *ctrl, int n_sats, int T,
                                         int n_sub_prop, int n_sub_disc, double *x, double *u, double *out,

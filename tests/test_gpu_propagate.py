@@ -332,3 +332,36 @@ def test_fused_gather_entry_points_and_layouts_on_one_gpu(M, const, layout):
     small = _lib.MpcGatherOpts(0, 0, 0, 0, N - 1, 0)
     assert _lib.lib().mpc_discretize_batch_gather(y_a.data_ptr(), u_a.data_ptr(), tfd.data_ptr(), ctypes.byref(p), N, T, n_sub,
                                                   arr, 2, ctypes.byref(small), st.data_ptr(), None) == _lib.E_INVALID
+
+
+@pytest.mark.parametrize("case", ["windows", "small", "mass_failure"])
+def test_streamed_host_pass_in_the_k_major_layout(M, const, case):
+    """propagate_discretize(layout="kmajor"): windows along k gated on the propagation's progress, each window read back
+    while the next one runs; the per-satellite views, the trajectory, the inputs and the status words are bit-identical to
+    the satellite-major host pass (same kernels per interval)"""
+    N, T, tf, n_sub = {"windows": (1500, 131, 2.0, 20), "small": (7, 23, 0.7, 100), "mass_failure": (1300, 100, 1.0, 10)}[case]
+    y0, _, _ = synth_batch(N, 2, 1.0, const)
+    rng = np.random.default_rng(4)
+    tfv = tf * (1 + 0.05 * rng.random(N))
+    c = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    if case == "mass_failure":
+        c = M.SequenceController(u=0.3 * rng.standard_normal((N, 3, 9)), tf_u=1.0, tf_sim=1.0)
+        y0 = y0.copy()
+        y0[[3, 700, N - 1], 6] = 1e-4
+    a, ya, ua = M.propagate_discretize(y0, tfv, c, const, T=T, n_sub_disc=n_sub, disc_J2=True, prop_J2=True, check=False)
+    for rep in range(2):
+        b, yb, ub = M.propagate_discretize(y0, tfv, c, const, T=T, n_sub_disc=n_sub, disc_J2=True, prop_J2=True, check=False,
+                                           layout="kmajor")
+        eq = lambda p, q: np.array_equal(p.view(np.int64), q.view(np.int64))       # NaN-aware bit comparison
+        assert b.layout == "kmajor" and eq(np.ascontiguousarray(ya), np.ascontiguousarray(yb)) and eq(np.ascontiguousarray(ua), np.ascontiguousarray(ub))
+        assert np.array_equal(a.status, b.status)
+        for s_ in (0, N // 2, N - 1) + ((3, 700) if case == "mass_failure" else ()):
+            for p, q in zip(a.sat(s_), b.sat(s_)):
+                assert eq(np.ascontiguousarray(p), np.ascontiguousarray(q))
+        assert eq(np.ascontiguousarray(a.soa.reshape(105, N, T - 1).transpose(0, 2, 1)).reshape(105, -1), np.ascontiguousarray(b.soa))
+    if case == "mass_failure":
+        assert a.status[3].max() == 1 and a.status[0].max() == 0
+        with pytest.raises(Exception, match="INVALID SATELLITE MASS"):
+            M.propagate_discretize(y0, tfv, c, const, T=T, n_sub_disc=n_sub, layout="kmajor")
+    else:
+        assert b.status.max() == 0

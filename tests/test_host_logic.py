@@ -222,6 +222,14 @@ def test_discretized_batch_views_have_reference_shapes_and_order():
     assert A.base is not None                                 # views, not copies
     As, Bps, Bns, Ss, Xs = b.stacked()
     assert np.array_equal(As[1], A) and np.array_equal(Ss[1], S) and np.array_equal(Bns[1], Bn)
+    # the k-major layout (column = k N + s, what propagate_discretize(layout="kmajor") returns): same views, still no copy
+    km = np.ascontiguousarray(soa.reshape(105, N, K - 1).transpose(0, 2, 1)).reshape(105, n)
+    bk = batch.DiscretizedBatch(km, np.zeros((N, K - 1), np.int32), N, K, layout="kmajor")
+    for s_ in range(N):
+        for a, c in zip(b.sat(s_), bk.sat(s_)):
+            assert np.array_equal(a, c) and np.shares_memory(c, km)
+    for a, c in zip(b.stacked(), bk.stacked()):
+        assert np.array_equal(a, c) and np.shares_memory(c, km)
 
 
 def test_default_n_sub_matches_reference_max_step():
