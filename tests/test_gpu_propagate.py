@@ -355,6 +355,13 @@ def test_streamed_host_pass_in_the_k_major_layout(M, const, case):
         eq = lambda p, q: np.array_equal(p.view(np.int64), q.view(np.int64))       # NaN-aware bit comparison
         assert b.layout == "kmajor" and eq(np.ascontiguousarray(ya), np.ascontiguousarray(yb)) and eq(np.ascontiguousarray(ua), np.ascontiguousarray(ub))
         assert np.array_equal(a.status, b.status)
+        if case == "small":
+            # (a batch this small runs the thread-group kernel in the satellite-major pass and the one-thread kernel in
+            # the k-major one: equal up to the rounding of the former's cross-lane sums)
+            for s_ in range(N):
+                for p, q in zip(a.sat(s_), b.sat(s_)):
+                    assert rel_err(q, p) < 1e-13
+            continue
         for s_ in (0, N // 2, N - 1) + ((3, 700) if case == "mass_failure" else ()):
             for p, q in zip(a.sat(s_), b.sat(s_)):
                 assert eq(np.ascontiguousarray(p), np.ascontiguousarray(q))
