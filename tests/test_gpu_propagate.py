@@ -365,7 +365,13 @@ def test_streamed_host_pass_in_the_k_major_layout(M, const, case):
         for s_ in (0, N // 2, N - 1) + ((3, 700) if case == "mass_failure" else ()):
             for p, q in zip(a.sat(s_), b.sat(s_)):
                 assert eq(np.ascontiguousarray(p), np.ascontiguousarray(q))
-        assert eq(np.ascontiguousarray(a.soa.reshape(105, N, T - 1).transpose(0, 2, 1)).reshape(105, -1), np.ascontiguousarray(b.soa))
+        # the whole result: the last (short) chunk of the satellite-major pipeline may run the thread-group kernel, so
+        # rounding-level differences are allowed there; NaN patterns (failed satellites) must coincide
+        ak = np.ascontiguousarray(a.soa.reshape(105, N, T - 1).transpose(0, 2, 1)).reshape(105, -1)
+        bk = np.ascontiguousarray(b.soa)
+        assert np.array_equal(np.isnan(ak), np.isnan(bk))
+        fin = ~np.isnan(ak)
+        assert np.max(np.abs(ak[fin] - bk[fin])) <= 1e-13 * np.max(np.abs(ak[fin]))
     if case == "mass_failure":
         assert a.status[3].max() == 1 and a.status[0].max() == 0
         with pytest.raises(Exception, match="INVALID SATELLITE MASS"):
