@@ -139,7 +139,7 @@ int launch_pair_cfg(const double *x, const double *u, const double *tf, const mp
 }
 
 std::atomic<int> g_pair{1};   // mpc_set_tuning(7) switches the two-node steps off (one step per node everywhere)
-std::atomic<int> g_host_windows{16};   // mpc_set_tuning(26..29): k-windows of the streamed host pass 8 / 16 / 24 / 32
+std::atomic<int> g_host_windows{32};   // mpc_set_tuning(26..29): k-windows of the streamed host pass 16 / 32 / 48 / 64
 std::atomic<int> g_group{1};  // mpc_set_tuning(23 / 24): the 8-lanes-per-interval kernel for small batches off / on
 // Below this many intervals the thread-group mapping wins (measured on a B200, profiles/r02_f_small_batches.txt): the
 // one-thread kernel needs 0.118 ms whatever the batch, the group kernel 0.064 ms up to ~1000 intervals, 0.086 ms at
@@ -748,7 +748,7 @@ int mpc_set_tuning(int variant)
         return MPC_SUCCESS;
     }
     if (variant >= 26 && variant <= 29) {  // streamed host pass (k-major): number of k-windows
-        g_host_windows.store(8 * (variant - 25));
+        g_host_windows.store(16 * (variant - 25));
         return MPC_SUCCESS;
     }
     if (variant >= 23 && variant <= 25) {  // small batches: 8-lanes-per-interval kernel off / on / at any size
@@ -1307,10 +1307,11 @@ extern "C" int mpc_propagate_discretize_host_layout(mpc_ctx *ctx, const double *
     if ((rc = ensure(ctx->d_status, ctx->cap_status, (size_t)n_int))) return rc;
     if ((rc = ensure(ctx->d_status2, ctx->cap_status2, (size_t)n_sats))) return rc;
     if ((rc = ensure_overlap(ctx))) return rc;
-    // windows: each at least one wave of the kernel, at most 16 (the read-back of a window is what paces the pipeline)
+    // windows: each at least half a wave of the kernel (they alternate over two streams), at most g_host_windows (the
+    // read-back of a window is what paces the pipeline; measured: profiles/r02_t_probe_e2e.txt)
     const long long wave = (long long)ctx->sm_count * 2 * kDiscBlock;
     int nw = (int)std::max<long long>(1, std::min<long long>(g_host_windows.load(std::memory_order_relaxed),
-                                                           std::min<long long>(n_int / wave, K - 1)));
+                                                           std::min<long long>(2 * n_int / wave, K - 1)));
     const bool gated = nw >= 2 && stream_wait_value32() != nullptr;
     if (!gated) nw = 1;
     const int seg = (K - 1 + nw - 1) / nw;

@@ -1,5 +1,5 @@
 """Round-2 probe: the end-to-end host pass on BASELINE configs[2] -- satellite-major pipeline against the streamed
-k-major pass with 8 / 16 / 24 / 32 k-windows (wall clock per call, pinned buffers)."""
+k-major pass with 16 / 32 / 48 / 64 k-windows (capped at two per kernel wave) (wall clock per call, pinned buffers)."""
 import os
 import sys
 import time
@@ -30,7 +30,7 @@ def run(layout, n=8):
 
 
 print("satellite-major pipeline (chunks of one kernel wave): mean %.3f ms  min %.3f ms" % run("satmajor"))
-for var, nw in ((26, 8), (27, 16), (28, 24), (29, 32)):
+for var, nw in ((26, 16), (27, 32), (28, 48), (29, 64)):
     L.mpc_set_tuning(var)
     print("k-major streamed pass, %2d windows: mean %.3f ms  min %.3f ms" % ((nw,) + run("kmajor")))
 L.mpc_set_tuning(27)
