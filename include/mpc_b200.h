@@ -386,8 +386,9 @@ int64_t mpc_launch_count(void);
  * round-1 build of the default-mode (adaptive) kernel and back (same results to rounding; A/B measurements).  11 / 12: RK45 propagator without / with the speculative first stage
  * of the next step (same results).  13: satellites per warp of the RK45 propagator chosen automatically, 14..19: forced
  * to 32, 16, 8, 4, 2, 1 (same results).  20 / 21 / 22: CTA size of the default-mode kernel 32 / 128 / 256 threads (same
- * results).  23 / 24: the thread-group kernel for small batches (8 lanes per interval) off / on (results equal to
- * rounding). */
+ * results).  23 / 24 / 25: the thread-group kernel for small batches (8 lanes per interval) off / on / at any batch size
+ * (results equal to rounding).  26..29: k-windows of the streamed host pass (mpc_propagate_discretize_host_layout) 16 / 32 /
+ * 48 / 64 (same results). */
 int mpc_set_tuning(int variant);
 
 /* Options of the fused (in-kernel store) all-gather, applied by mpc_discretize_batch / _multi:

@@ -139,6 +139,10 @@ def dynamics_jacobian(matrices):
     Returns a DynamicsJacobian with numpy arrays."""
     import torch
     _lib.require_gpu()
-    soa = torch.from_numpy(np.ascontiguousarray(matrices.soa)).cuda()
+    host = matrices.soa
+    if getattr(matrices, "layout", "satmajor") == "kmajor":        # the assembly kernel reads per-satellite column blocks
+        N, n = matrices.n_sats, matrices.K - 1
+        host = host.reshape(_lib.MPC_OUT_ROWS, n, N).transpose(0, 2, 1).reshape(_lib.MPC_OUT_ROWS, N * n)
+    soa = torch.from_numpy(np.ascontiguousarray(host)).cuda()
     v, c, r = dynamics_jacobian_device(soa, matrices.n_sats, matrices.K)
     return DynamicsJacobian(v.cpu().numpy(), c.cpu().numpy(), r.cpu().numpy(), matrices.n_sats, matrices.K)

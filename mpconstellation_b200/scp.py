@@ -76,8 +76,10 @@ class BatchedSCP:
         tfv = np.ascontiguousarray(np.broadcast_to(np.asarray(tf, dtype=np.float64), (N,)))
         K = int(self.base_res * float(np.max(tfv)))
         if self.use_uniform_steps:
+            # (k-major layout: the streamed host pass; the per-satellite views of the result hide it)
             res, x, u = batch.propagate_discretize(y0, tfv, controller, self.const, T=K, disc_J2=self.include_J2,
-                                                   n_sub_disc=self.integrator_steps - 1, device=self.device)
+                                                   n_sub_disc=self.integrator_steps - 1, device=self.device,
+                                                   layout="kmajor")
         else:
             x, u, _, _ = batch.propagate_batch(y0, tfv, controller, self.const, include_drag=False, include_J2=False,
                                                T=K, device=self.device)

@@ -110,3 +110,9 @@ def test_sparse_dynamics_jacobian_reproduces_the_pyomo_rule(M, const):
     for s in range(N):
         nu0[s, :, :K - 1] = lin.dynamics_residual(s, x[s], u[s], 0.7)
     assert np.max(np.abs(jac.residual(jac.pack(x, u, nu0, 0.7)))) < 1e-13
+    # a k-major result (the streamed host pass) assembles to the same system
+    ctrl = M.ConstantTangentialThrustController(tangential_thrust=0.5)
+    ms, _, _ = M.propagate_discretize(y0, 0.7, ctrl, const, T=K, n_sub_disc=10)
+    mk, _, _ = M.propagate_discretize(y0, 0.7, ctrl, const, T=K, n_sub_disc=10, layout="kmajor")
+    js, jk = dynamics_jacobian(ms), dynamics_jacobian(mk)
+    assert np.array_equal(js.indices, jk.indices) and np.max(np.abs(js.values - jk.values)) < 1e-12 and np.max(np.abs(js.rhs - jk.rhs)) < 1e-12
