@@ -37,26 +37,27 @@ constexpr int kDfEndU = 99;                       // rows 99..101: input of the 
 
 #define SM(e) sm[(e) * BLOCK]
 
+// The stage linearisations are stored in the units of the step: hs^2 G_s, hs^2 d_s (and hs V_s), see the column loop.
 template <int BLOCK, bool DRAG>
-__device__ __forceinline__ void df_store_stage(volatile double *sm, int s, const AdStage &st)
+__device__ __forceinline__ void df_store_stage(volatile double *sm, int s, const AdStage &st, double hs, double hs2)
 {
     const int b = kDfAcc + s * (DRAG ? 15 : 9);
-    SM(b + 0) = st.g.xx;
-    SM(b + 1) = st.g.xy;
-    SM(b + 2) = st.g.xz;
-    SM(b + 3) = st.g.yy;
-    SM(b + 4) = st.g.yz;
-    SM(b + 5) = st.g.zz;
-    SM(b + 6) = st.d[0];
-    SM(b + 7) = st.d[1];
-    SM(b + 8) = st.d[2];
+    SM(b + 0) = hs2 * st.g.xx;
+    SM(b + 1) = hs2 * st.g.xy;
+    SM(b + 2) = hs2 * st.g.xz;
+    SM(b + 3) = hs2 * st.g.yy;
+    SM(b + 4) = hs2 * st.g.yz;
+    SM(b + 5) = hs2 * st.g.zz;
+    SM(b + 6) = hs2 * st.d[0];
+    SM(b + 7) = hs2 * st.d[1];
+    SM(b + 8) = hs2 * st.d[2];
     if (DRAG) {
-        SM(b + 9) = st.v.xx;
-        SM(b + 10) = st.v.xy;
-        SM(b + 11) = st.v.xz;
-        SM(b + 12) = st.v.yy;
-        SM(b + 13) = st.v.yz;
-        SM(b + 14) = st.v.zz;
+        SM(b + 9) = hs * st.v.xx;
+        SM(b + 10) = hs * st.v.xy;
+        SM(b + 11) = hs * st.v.xz;
+        SM(b + 12) = hs * st.v.yy;
+        SM(b + 13) = hs * st.v.yz;
+        SM(b + 14) = hs * st.v.zz;
     }
 }
 
@@ -209,12 +210,12 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                 if (t_new - t1 > 0.0) t_new = t1;
                 const double h = t_new - t;
                 h_abs = fabs(h);
-                const double hs = h * tf;
+                const double hs = h * tf, hs2 = hs * hs, ihs = 1.0 / hs;
                 // -- state stages (registers) ------------------------------------------------------------------------
                 double kx[6][7];
 #pragma unroll
                 for (int i = 0; i < 7; ++i) kx[0][i] = st0.k[i];
-                df_store_stage<BLOCK, DRAG>(sm, 0, st0);
+                df_store_stage<BLOCK, DRAG>(sm, 0, st0, hs, hs2);
                 const double cs[6] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
 #pragma unroll
                 for (int s = 1; s < 6; ++s) {
@@ -230,7 +231,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                     bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
 #pragma unroll
                     for (int i = 0; i < 7; ++i) kx[s][i] = sg.k[i];
-                    df_store_stage<BLOCK, DRAG>(sm, s, sg);
+                    df_store_stage<BLOCK, DRAG>(sm, s, sg, hs, hs2);
                 }
                 const double bw[6] = {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
                 const double ew[7] = {-71.0 / 57600, 0.0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
@@ -242,7 +243,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                     xn[i] = fma(hs, dy, x[i]);
                 }
                 bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xn, (t + h - t0) * ilen, t + h, hold, st6);
-                df_store_stage<BLOCK, DRAG>(sm, 6, st6);
+                df_store_stage<BLOCK, DRAG>(sm, 6, st6, hs, hs2);
                 double esum = 0.0;
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
@@ -253,43 +254,55 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                     esum = fma(q, q, esum);
                 }
                 // -- Phi columns: global (L2) -> registers -> global, stage matrices from shared memory ----------------
+                // Each column (p_r, p_v) obeys p_r' = p_v, p_v' = G p_r (+ V p_v) (+ d): stepped in the units of the
+                // step, P = hs p_v, K_s = hs^2 p_v'(stage s), the Dormand-Prince stages read
+                //     q_r(s) = p_r + c_s P + sum_m (A A)_sm K_m,      hs q_v(s) = P + sum_m A_sm K_m,
+                // the position rows through the squared tableau (the stage derivative of a position row is the stage's
+                // velocity row, itself a combination of the K_m).  Same stages, same result to rounding; every
+                // coefficient is a literal, no product with hs inside the stages and nothing but K to keep per stage.
+                // Error estimate h K^T E of the position rows likewise: sum_m (E A)_m K_m (sum(E) = 0 exactly).
                 // (the next column is requested from L2 while this one is stepped)
+                const double a2[7][5] = {{0, 0, 0, 0, 0},
+                                         {0, 0, 0, 0, 0},
+                                         {9.0 / 200, 0, 0, 0, 0},
+                                         {-12.0 / 25, 4.0 / 5, 0, 0, 0},
+                                         {-12248.0 / 6561, 7208.0 / 2187, -6784.0 / 6561, 0, 0},
+                                         {-533.0 / 264, 91.0 / 22, -56.0 / 33, 7.0 / 88, 0},
+                                         {35.0 / 384, 0.0, 50.0 / 159, 25.0 / 192, -243.0 / 6784}};
+                const double ea[6] = {-611.0 / 230400, 0.0, 514.0 / 83475, -391.0 / 38400, 4617.0 / 1356800, 11.0 / 3360};
                 double pn[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) pn[i] = cur[(long long)i * pitch];
 #pragma unroll 1
                 for (int c = 0; c < 7; ++c) {
-                    double p[6], kr[7][3], kv[7][3];
+                    double pr_[3], pv_[3], Pv[3], kk[7][3];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) p[i] = pn[i];
+                    for (int i = 0; i < 3; ++i) {
+                        pr_[i] = pn[i];
+                        pv_[i] = pn[3 + i];
+                        Pv[i] = hs * pn[3 + i];
+                    }
                     if (c < 6) {
 #pragma unroll
                         for (int i = 0; i < 6; ++i) pn[i] = cur[(long long)((c + 1) * 6 + i) * pitch];
                     }
 #pragma unroll
                     for (int s = 0; s < 7; ++s) {
-                        double q[6];
-                        if (s == 0) {
+                        double qr[3], qv[3];       // q_r(s), hs q_v(s)
 #pragma unroll
-                            for (int i = 0; i < 6; ++i) q[i] = p[i];
-                        } else if (s < 6) {
+                        for (int i = 0; i < 3; ++i) {
+                            if (s == 0) {
+                                qr[i] = pr_[i];
+                                qv[i] = Pv[i];
+                            } else {
+                                double r_ = fma(cs[s == 6 ? 5 : s], Pv[i], pr_[i]), v_ = Pv[i];
 #pragma unroll
-                            for (int i = 0; i < 6; ++i) {
-                                double dy = 0.0;
+                                for (int m = 0; m + 1 < s && m < 5; ++m) r_ = fma(kk[m][i], a2[s][m], r_);
 #pragma unroll
-                                for (int l = 0; l < s; ++l) dy = fma((i < 3) ? kr[l][i] : kv[l][i - 3], kDpA[s][l], dy);
-                                q[i] = fma(dy, hs, p[i]);
+                                for (int m = 0; m < s && m < 6; ++m) v_ = fma(kk[m][i], (s == 6) ? bw[m] : kDpA[s < 6 ? s : 5][m < 5 ? m : 4], v_);
+                                qr[i] = r_;
+                                qv[i] = v_;
                             }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) {
-                                double dy = 0.0;
-#pragma unroll
-                                for (int l = 0; l < 6; ++l) dy = fma((i < 3) ? kr[l][i] : kv[l][i - 3], bw[l], dy);
-                                q[i] = fma(hs, dy, p[i]);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) nxt[(long long)(c * 6 + i) * pitch] = q[i];
                         }
                         const int b = kDfAcc + s * kStage;
                         const double gxx = SM(b), gxy = SM(b + 1), gxz = SM(b + 2), gyy = SM(b + 3), gyz = SM(b + 4), gzz = SM(b + 5);
@@ -300,26 +313,30 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                             dy_ = SM(b + 7);
                             dz = SM(b + 8);
                         }
-                        if (DRAG) {   // + V q_v
+                        if (DRAG) {   // + (hs V) (hs q_v)
                             const double vxx = SM(b + 9), vxy = SM(b + 10), vxz = SM(b + 11), vyy = SM(b + 12), vyz = SM(b + 13), vzz = SM(b + 14);
-                            dx = fma(vxz, q[5], fma(vxy, q[4], fma(vxx, q[3], dx)));
-                            dy_ = fma(vyz, q[5], fma(vyy, q[4], fma(vxy, q[3], dy_)));
-                            dz = fma(vzz, q[5], fma(vyz, q[4], fma(vxz, q[3], dz)));
+                            dx = fma(vxz, qv[2], fma(vxy, qv[1], fma(vxx, qv[0], dx)));
+                            dy_ = fma(vyz, qv[2], fma(vyy, qv[1], fma(vxy, qv[0], dy_)));
+                            dz = fma(vzz, qv[2], fma(vyz, qv[1], fma(vxz, qv[0], dz)));
                         }
-                        kr[s][0] = q[3];
-                        kr[s][1] = q[4];
-                        kr[s][2] = q[5];
-                        kv[s][0] = fma(gxz, q[2], fma(gxy, q[1], fma(gxx, q[0], dx)));
-                        kv[s][1] = fma(gyz, q[2], fma(gyy, q[1], fma(gxy, q[0], dy_)));
-                        kv[s][2] = fma(gzz, q[2], fma(gyz, q[1], fma(gxz, q[0], dz)));
-                        if (s == 6) {
+                        kk[s][0] = fma(gxz, qr[2], fma(gxy, qr[1], fma(gxx, qr[0], dx)));
+                        kk[s][1] = fma(gyz, qr[2], fma(gyy, qr[1], fma(gxy, qr[0], dy_)));
+                        kk[s][2] = fma(gzz, qr[2], fma(gyz, qr[1], fma(gxz, qr[0], dz)));
+                        if (s == 6) {      // (qr, qv / hs) is the new column: store, error estimate
 #pragma unroll
-                            for (int i = 0; i < 6; ++i) {
-                                double e = 0.0;
+                            for (int i = 0; i < 3; ++i) {
+                                const double yv = qv[i] * ihs;
+                                nxt[(long long)(c * 6 + i) * pitch] = qr[i];
+                                nxt[(long long)(c * 6 + 3 + i) * pitch] = yv;
+                                double er = 0.0, ev = 0.0;
 #pragma unroll
-                                for (int l = 0; l < 7; ++l) e = fma((i < 3) ? kr[l][i] : kv[l][i - 3], ew[l], e);
-                                const double qq = e * hs * fast_rcp1(atol + fmax(fabs(p[i]), fabs(q[i])) * rtol);
-                                esum = fma(qq, qq, esum);
+                                for (int m = 0; m < 6; ++m) er = fma(kk[m][i], ea[m], er);
+#pragma unroll
+                                for (int l = 0; l < 7; ++l) ev = fma(kk[l][i], ew[l], ev);
+                                const double q1 = er * fast_rcp1(atol + fmax(fabs(pr_[i]), fabs(qr[i])) * rtol);
+                                const double q2 = ev * ihs * fast_rcp1(atol + fmax(fabs(pv_[i]), fabs(yv)) * rtol);
+                                esum = fma(q1, q1, esum);
+                                esum = fma(q2, q2, esum);
                             }
                         }
                     }

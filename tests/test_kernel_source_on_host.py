@@ -70,14 +70,14 @@ def test_adaptive_kernel_matches_reference_default_mode(gold_disc, const, sc):
 def test_both_builds_of_the_default_mode_kernel_agree(const, j2):
     """discretize_default_kernel (shipped: Phi ping-pongs through the output buffer, every node evaluated once with its
     full trapezoid weight) against discretize_adaptive_kernel (round 1: both ends of every panel): the same steps, the
-    same node counts, results equal up to the association of the panel sums"""
+    same node counts, results equal up to rounding (the panel sums are associated differently, and the shipped build steps
+    the Phi columns in the units of the step, through the squared tableau for the position rows)"""
     _, x, u = synth_batch(5, 23, 1.1, const)
     a, sa, na = hostk.discretize_adaptive(x, u, 1.1, const, include_J2=j2)
     b, sb, nb = hostk.discretize_adaptive(x, u, 1.1, const, include_J2=j2, v1=True)
     assert sa.max() == 0 and np.array_equal(sa, sb) and np.array_equal(na, nb)
     for r0, r1 in ((0, 49), (49, 70), (70, 91), (91, 98), (98, 105)):
         assert rel_err(a[r0:r1], b[r0:r1]) < 1e-13
-    assert np.array_equal(a[0:49], b[0:49])          # A_k = Phi_end: the very same arithmetic
 
 
 @pytest.mark.parametrize("n_sats,K,tf,j2,n_sub", [(16, 60, 1.0, False, 100), (7, 33, 0.7, True, 100), (3, 50, 2.0, True, 16),
