@@ -114,13 +114,17 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
     double h_abs;
     {
         const double interval_length = fabs(t1 - t0);
+        // (the error scales take three kinds of values -- atol, atol + rtol, atol + |x_i| rtol --: nine reciprocals,
+        //  with tf folded in, instead of a division per term)
         const double s1 = atol + rtol, s0 = atol;
-        double d0sq = 7.0 / (s1 * s1), d1sq = 0.0;
+        const double is1 = tf / s1, is0 = tf / s0;
+        double d0sq = 7.0 / (s1 * s1), d1sq = 0.0, isc[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
-            const double sc = atol + fabs(x[i]) * rtol;
-            d0sq += (x[i] / sc) * (x[i] / sc);
-            d1sq += (tf * st0.k[i] / sc) * (tf * st0.k[i] / sc);
+            const double sc = atol + fabs(x[i]) * rtol, r_ = 1.0 / sc;
+            isc[i] = tf * r_;
+            d0sq += (x[i] * r_) * (x[i] * r_);
+            d1sq += (st0.k[i] * isc[i]) * (st0.k[i] * isc[i]);
         }
         const double g[9] = {st0.g.xx, st0.g.xy, st0.g.xz, st0.g.xy, st0.g.yy, st0.g.yz, st0.g.xz, st0.g.yz, st0.g.zz};
         double v0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, vA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -129,15 +133,15 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
                 v0[i] = t_[i];
-                const double sc = (i % 4 == 0) ? s1 : s0;
-                d1sq += (tf * t_[i] / sc) * (tf * t_[i] / sc);
+                const double isc_ = (i % 4 == 0) ? is1 : is0;
+                d1sq += (t_[i] * isc_) * (t_[i] * isc_);
             }
         }
-        d1sq += 3.0 * (tf / s0) * (tf / s0);
+        d1sq += 3.0 * is0 * is0;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) d1sq += (tf * g[i] / s0) * (tf * g[i] / s0);
+        for (int i = 0; i < 9; ++i) d1sq += (g[i] * is0) * (g[i] * is0);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) d1sq += (tf * st0.d[i] / s0) * (tf * st0.d[i] / s0);
+        for (int i = 0; i < 3; ++i) d1sq += (st0.d[i] * is0) * (st0.d[i] * is0);
         const double d0 = sqrt(d0sq / 56.0), d1 = sqrt(d1sq / 56.0);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, interval_length);
@@ -150,8 +154,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
         double d2sq = 0.0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
-            const double sc = atol + fabs(x[i]) * rtol;
-            const double df = tf * (stA.k[i] - st0.k[i]) / sc;
+            const double df = (stA.k[i] - st0.k[i]) * isc[i];
             d2sq += df * df;
         }
         const double g1[9] = {stA.g.xx, stA.g.xy, stA.g.xz, stA.g.xy, stA.g.yy, stA.g.yz, stA.g.xz, stA.g.yz, stA.g.zz};
@@ -176,8 +179,7 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                 double f1v = g1[a * 3 + 0] * p1r[0] + g1[a * 3 + 1] * p1r[1] + g1[a * 3 + 2] * p1r[2];
                 if (DRAG) f1v += vA[a * 3 + 0] * p1v[0] + vA[a * 3 + 1] * p1v[1] + vA[a * 3 + 2] * p1v[2];
                 if (c == 6) f1v += stA.d[a];
-                const double scr = (c == a) ? s1 : s0, scv = (c == a + 3) ? s1 : s0;
-                const double e1 = tf * (f1r - f0r[a]) / scr, e2 = tf * (f1v - f0v[a]) / scv;
+                const double e1 = (f1r - f0r[a]) * ((c == a) ? is1 : is0), e2 = (f1v - f0v[a]) * ((c == a + 3) ? is1 : is0);
                 d2sq += e1 * e1 + e2 * e2;
             }
         }

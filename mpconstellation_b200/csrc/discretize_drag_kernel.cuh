@@ -129,16 +129,16 @@ __device__ __forceinline__ void node_accumulate_general(volatile double *acc, co
         R[a + 3][5] = e.dragv[a] - e.gr[a];
     }
     // Gauss-Jordan without pivoting.  Only the columns of M right of the pivot are touched: the others are already
-    // columns of the identity (and never read again), which saves 40 % of the elimination arithmetic and code; and the
-    // Duf columns of R (0..2) have zeros in rows 0..2, so the first three pivot rows leave them as they are.
+    // columns of the identity (and never read again), which saves 40 % of the elimination arithmetic and code.
+    // (Skipping the Duf columns of R for the first three pivots -- their rows 0..2 are zero -- removes another 54
+    // instructions but measured 3 % slower on the default-mode kernel, same box, r02w: ptxas schedules it worse.)
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
-        const int c0 = (p < 3) ? 3 : 0;
         const double ip = fast_rcp(M[p][p]);
 #pragma unroll
         for (int c = p + 1; c < 6; ++c) M[p][c] *= ip;
 #pragma unroll
-        for (int c = c0; c < 6; ++c) R[p][c] *= ip;
+        for (int c = 0; c < 6; ++c) R[p][c] *= ip;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             if (r == p) continue;
@@ -146,7 +146,7 @@ __device__ __forceinline__ void node_accumulate_general(volatile double *acc, co
 #pragma unroll
             for (int c = p + 1; c < 6; ++c) M[r][c] = fma(-f, M[p][c], M[r][c]);
 #pragma unroll
-            for (int c = c0; c < 6; ++c) R[r][c] = fma(-f, R[p][c], R[r][c]);
+            for (int c = 0; c < 6; ++c) R[r][c] = fma(-f, R[p][c], R[r][c]);
         }
     }
     // (requested after the solve -- 16 registers fewer while it runs -- and used last: the shared-memory updates cover

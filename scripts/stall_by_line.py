@@ -1,5 +1,5 @@
 """Attribute ncu stall samples (SASS level) to CUDA source lines using nvdisasm line info.
-usage: stall_by_line.py rep.ncu-rep kernel-mangled-substring [so]"""
+usage: stall_by_line.py rep.ncu-rep kernel-mangled-substring [so]     (STALL_LINES=n: print the n top lines, default 40; 0 = all)"""
 import csv, io, os, re, subprocess, sys, tempfile, collections
 rep, pat = sys.argv[1], sys.argv[2]
 so = sys.argv[3] if len(sys.argv) > 3 else "mpconstellation_b200/csrc/libmpc_b200.so"
@@ -39,5 +39,5 @@ def text(ln):
         srcfile[f] = open(p).read().splitlines() if os.path.exists(p) else []
     return srcfile[f][n - 1].strip()[:80] if n - 1 < len(srcfile[f]) else ""
 print(f"total samples {tot}")
-for ln, c in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:40]:
+for ln, c in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:(int(os.environ.get("STALL_LINES", "40")) or None)]:
     print(f"{100*c['samples']/tot:5.1f}% inst {c['inst']:>10d} wait {c['stall_wait']:6d} math {c['stall_math']:6d} ssb {c['stall_short_sb']:5d} sel {c['stall_selected']:6d} | {ln} {text(ln)}")
