@@ -232,10 +232,17 @@ __device__ __noinline__ void ref_node_input(const double *__restrict__ us, int K
     const double km1 = (double)(Ku - 1);
     const double dtau = 1.0 / km1;
     const double tau = (double)i * dtau;     // np.linspace: arange(Ku) * step
-    int kq = (int)py_floordiv(tau, dtau);
+    // int(tau // dtau) with Python's float floor division (py_floordiv).  For tau = fl(i * dtau) the quotient is i when the
+    // product was rounded up or is exact and i - 1 when it was rounded down (fmod then returns dtau - |rounding error|),
+    // and the sign of the rounding error is one FMA: checked against CPython for every node of every grid up to 1200
+    // nodes (741 k cases, 351 k of them i - 1).  fmod and the division of py_floordiv cost ~700 instructions a call.
+    int kq = i - (fma((double)i, dtau, -tau) > 0.0 ? 1 : 0);
     kq = min(max(kq, 0), Ku - 2);
     const double tk = (double)kq / km1, tk1 = (double)(kq + 1) / km1;
-    const double ln = (tk1 - tau) / (tk1 - tk), lp = (tau - tk) / (tk1 - tk);
+    // (one division for the two weights: whether a weight is exactly 0 -- the only thing that matters, see above -- is
+    //  decided by its numerator)
+    const double iw = 1.0 / (tk1 - tk);
+    const double ln = (tk1 - tau) * iw, lp = (tau - tk) * iw;
     ux = f * __dadd_rn(__dmul_rn(ln, us[kq]), __dmul_rn(lp, us[kq + 1]));
     uy = f * __dadd_rn(__dmul_rn(ln, us[Ku + kq]), __dmul_rn(lp, us[Ku + kq + 1]));
     uz = f * __dadd_rn(__dmul_rn(ln, us[2 * (long long)Ku + kq]), __dmul_rn(lp, us[2 * (long long)Ku + kq + 1]));
