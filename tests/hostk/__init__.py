@@ -220,6 +220,15 @@ def discretize_ugrid(x, u, tf, const, include_J2=False, n_sub=100, adaptive=None
     return out, status, nodes
 
 
+def ref_node_input(us, f=1.0):
+    """ref_node_input of the kernels at every node of the grid of us [3, Ku] -> [Ku, 3]"""
+    us = np.ascontiguousarray(us, dtype=np.float64)
+    Ku = us.shape[1]
+    out = np.full((Ku, 3), np.nan)
+    lib().hostk_ref_node_input(_p(us), Ku, ctypes.c_double(f), _p(out))
+    return out
+
+
 def constraint_terms(x, u, mu):
     """constraint_terms_kernel on host arrays x [N,7,K], u [N,3,Ku] -> rbar_hat [N,3,K-1], ubar_hat [N,3,Ku], fin [N,32]"""
     x = np.ascontiguousarray(x, dtype=np.float64)

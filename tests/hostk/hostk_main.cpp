@@ -276,3 +276,11 @@ extern "C" int hostk_discretize_ugrid(const double *x, const double *u, int u_co
     });
     return 0;
 }
+
+// the end-node input lookup of the kernels (csrc/discretize_kernel.cuh: ref_node_input) for all nodes of one satellite:
+// us [3][Ku] -> out [Ku][3]
+extern "C" int hostk_ref_node_input(const double *us, int Ku, double f, double *out)
+{
+    for (int i = 0; i < Ku; ++i) mpc::ref_node_input(us, Ku, i, f, out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+    return 0;
+}

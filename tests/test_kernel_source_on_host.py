@@ -620,3 +620,35 @@ def test_u_on_its_own_grid_kernels(gold_disc, const):
     a, _ = hostk.discretize(xs, us, 0.5, const, pair=False)
     b, _, _ = hostk.discretize_ugrid(xs, us, 0.5, const)
     assert rel_err(b, a) < 1e-12
+
+
+def test_end_node_input_lookup_follows_the_reference_on_every_node_of_every_grid():
+    """ref_node_input decides int(tau // dtau) (Python's float floor division, linearize_discretize.py:308-311) with one
+    FMA instead of fmod and a division.  Against the reference's u_FOH restated literally, for every node of every grid of
+    2..600 nodes (and a few large ones): the same interval (the value is compared with both candidates' interpolation),
+    the same exact zeros (what the |u| <= eps guard of B_func, :208, sees) and the value to rounding."""
+    rng = np.random.default_rng(5)
+
+    def u_foh(tau, u):                       # linearize_discretize.py:304-315, verbatim arithmetic
+        if tau == 1:
+            return u[:, -1]
+        K = u.shape[1]
+        dtau = 1 / (K - 1)
+        k = int(tau // dtau)
+        tau_k = k / (K - 1)
+        tau_kp1 = (k + 1) / (K - 1)
+        lambda_kn = (tau_kp1 - tau) / (tau_kp1 - tau_k)
+        lambda_kp = (tau - tau_k) / (tau_kp1 - tau_k)
+        return lambda_kn * u[:, k] + lambda_kp * u[:, k + 1]
+
+    lower = 0
+    for Ku in list(range(2, 600)) + [1000, 2048, 4097]:
+        us = rng.normal(size=(3, Ku))
+        us[:, rng.random(Ku) < 0.3] = 0.0                    # coast arcs: exact zeros next to thrusting nodes
+        got = hostk.ref_node_input(us)
+        tau = np.linspace(0, 1, Ku)                           # :356
+        ref = np.array([u_foh(t, us) for t in tau])
+        assert np.array_equal(got == 0.0, ref == 0.0), Ku
+        assert np.max(np.abs(got - ref)) <= 4e-16 * np.max(np.abs(us)), Ku
+        lower += sum(int(t // (1 / (Ku - 1))) < i for i, t in enumerate(tau[:-1]))
+    assert lower > 50000          # the lookup lands in the interval LEFT of the node in a third of the cases: exercised
