@@ -36,7 +36,7 @@ HUBBLE = np.array([5371.4806e3, -4133.1393e3, 1399.9594e3, 4.6921e3, 4.9848e3, -
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SM x 64 DFMA/clk x 2 flop x 1.965 GHz = 37.2
 
 
-def flops_per_interval(n_sub, include_j2=False):
+def flops_per_interval(n_sub, include_j2=False, em=True):
     """ALGORITHMIC FP64 work of one interval: the arithmetic of the algorithm DESIGN.md section 4 states (42 live Phi
     entries, symmetric G, Nystrom's 3-stage fourth-order Runge-Kutta method in step-normalised variables with steps that
     span two quadrature nodes and a cubic-Hermite midpoint, symplectic inverse, 56 accumulators), FMA = 2 flop,
@@ -44,16 +44,27 @@ def flops_per_interval(n_sub, include_j2=False):
     executed DFMA/DMUL/DADD count: per integrator step (= two quadrature nodes) 754 FMA + 242 mul + 99 add (J2: 798 /
     298 / 116), plus the last node and the Phi_end * [integrals] epilogue (1249 flop; J2 1310).  An odd n_sub runs one
     step per node (532 / 182 / 55; J2 571 / 230 / 69).  Counted from the SASS of the shipped kernel
-    (scripts/sass_reuse.py) and cross-checked against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on."""
+    (scripts/sass_reuse.py) and cross-checked against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on.
+    em (what the library launches for n_sub = 100 unless mpc_set_tuning(37)): see below; em=False prices the same
+    throughput at the work of evaluating all 101 nodes (`all_nodes_alg` in the bench line)."""
     tail = 1310 if include_j2 else 1249
+    if em and n_sub == 100:
+        # the reference's integrator_steps = 101 as shipped: the 101-node trapezoid sums through their Euler-Maclaurin
+        # expansion (kEmW, csrc/discretize_kernel.cuh) -- 20 one-node steps whose ends are the 21 nodes of the rule
+        return EM_STEPS * ((2 * 571 + 230 + 69) if include_j2 else (2 * 532 + 182 + 55)) + tail
     if n_sub % 2 == 0:
         return (n_sub // 2) * ((2 * 798 + 298 + 116) if include_j2 else (2 * 754 + 242 + 99)) + tail
     return n_sub * ((2 * 571 + 230 + 69) if include_j2 else (2 * 532 + 182 + 55)) + tail
 
 
-def fp64_instr_per_interval(n_sub, include_j2=False):
+EM_STEPS = 20
+
+
+def fp64_instr_per_interval(n_sub, include_j2=False, em=True):
     """FP64-pipe instructions (DFMA+DMUL+DADD) per interval: the pipe-occupancy view of the same work."""
     tail = 785 if include_j2 else 742
+    if em and n_sub == 100:
+        return EM_STEPS * ((571 + 230 + 69) if include_j2 else (532 + 182 + 55)) + tail
     if n_sub % 2 == 0:
         return (n_sub // 2) * ((798 + 298 + 116) if include_j2 else (754 + 242 + 99)) + tail
     return n_sub * ((571 + 230 + 69) if include_j2 else (532 + 182 + 55)) + tail
@@ -261,7 +272,7 @@ def workload_config(args):
               "propagate (tangential thrust 0.5, no drag/J2) + discretize, BASELINE configs[2]")
     return {"workload": wl,
             "sats_per_gpu": args.sats, "K": args.nodes, "tf": args.tf, "integrator_steps": args.n_sub + 1,
-            "integrator": "fixed-step fourth-order Runge-Kutta-Nystrom (3 stages), one step per two quadrature nodes with a cubic-Hermite midpoint, trapezoid on all integrator_steps nodes", "l2": "flushed between timed steps (256 MiB write)",
+            "integrator": "fixed-step fourth-order Runge-Kutta-Nystrom (3 stages); the trapezoid sums over the reference's 101 nodes evaluated through their Euler-Maclaurin expansion (21 of the nodes = the ends of 20 integrator steps; agrees with the literal 101-node sums to 1e-13, per-interval fallback to all 101 nodes where the held input is not smooth)", "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": f"satellites sharded over {args.gpus} GPU(s)" + (f", all-gather of the SoA matrices inside the step ({args.gather})" if args.gpus > 1 else "")}
 
 
@@ -612,11 +623,14 @@ def gpu_arm(args):
     except Exception:
         pass
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-    fl = flops_per_interval(n_sub)
-    achieved_tflops = fl * n_int / (disc_ms_avg * 1e-3) / 1e12
     counters = kernel_counters()
     is_cfg3 = (N, K, n_sub, world) == (4096, 200, 100, 1)
     pair_ctr = counters.get("discretize_pair_kernel", {}) if is_cfg3 else {}
+    # executed FP64 work per interval: the ncu count of this very workload where one is committed (profiles/
+    # kernel_counters.json), the count from the SASS of the loop bodies otherwise (within 2 % of each other)
+    fl = pair_ctr.get("flop_per_interval") or flops_per_interval(n_sub)
+    fp64_ipi = pair_ctr.get("fp64_instr_per_interval") or fp64_instr_per_interval(n_sub)
+    achieved_tflops = fl * n_int / (disc_ms_avg * 1e-3) / 1e12
     dflt_ctr = counters.get("discretize_default_kernel", {}) if is_cfg3 else {}
     # the CPU baseline is a rank-0, N=1 measurement (under torchrun OMP_NUM_THREADS=1 would make it a one-core number)
     cpu = cpu_port_baseline(N, K, tf, n_sub) if (world == 1 and not args.no_cpu_baseline) else None
@@ -673,10 +687,16 @@ def gpu_arm(args):
                      # products): 2084 n_sub + 1386 flop per interval.  The kernel executes fewer (Nystrom form,
                      # symplectic inverse, Euler identity), so `achieved`/`frac` above use the EXECUTED count (the
                      # conservative reading); this is the same throughput priced at the survey's count.
+                     # the same throughput priced at the work of evaluating all 101 nodes (the kernel of
+                     # mpc_set_tuning(37): two-node steps with a Hermite midpoint), for comparison with round 1
+                     "all_nodes_alg": {"flop_per_interval": flops_per_interval(n_sub, em=False),
+                                       "achieved": flops_per_interval(n_sub, em=False) * n_int / (disc_ms_avg * 1e-3) / 1e12,
+                                       "frac": flops_per_interval(n_sub, em=False) * n_int / (disc_ms_avg * 1e-3) / 1e12 / peak_tflops},
                      "survey_alg": {"flop_per_interval": 2084 * n_sub + 1386,
                                     "achieved": (2084 * n_sub + 1386) * n_int / (disc_ms_avg * 1e-3) / 1e12,
                                     "frac": (2084 * n_sub + 1386) * n_int / (disc_ms_avg * 1e-3) / 1e12 / peak_tflops},
-                     "fp64_pipe_frac": fp64_instr_per_interval(n_sub) * n_int / (disc_ms_avg * 1e-3) / (peak_tflops * 1e12 / 2),
+                     "fp64_pipe_frac": fp64_ipi * n_int / (disc_ms_avg * 1e-3) / (peak_tflops * 1e12 / 2),
+                     "flop_source": pair_ctr.get("source") or "bench.py: flops_per_interval (SASS count of the loop bodies)",
                      "fp64_pipe_note": "FP64 instructions issued / (measured DFMA issue rate): DMUL/DADD occupy a DFMA slot but count 1 flop",
                      "kernel": "mpc::discretize_pair_kernel",
                      "hbm": {"achieved": bytes_per_interval() * n_int / (disc_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,

@@ -108,7 +108,14 @@ int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc
  *                        integrator (fixed-step fourth-order Runge-Kutta-Nystrom) takes one step per panel, or one
  *                        step per TWO panels with the node in between read off the step's cubic Hermite interpolant
  *                        where that is accurate to ~1e-12 (even n_sub, step short against the orbital rate; decided
- *                        per interval on the device; mpc_set_tuning(7) forces one step per panel everywhere)
+ *                        per interval on the device; mpc_set_tuning(7) forces one step per panel everywhere).
+ *                        n_sub = 100 (the reference's integrator_steps = 101): the 101-node trapezoid sums are evaluated
+ *                        through their Euler-Maclaurin expansion -- T(h) = sum_n w_n T(n h), n = 5, 10, 20, 25: one rule on
+ *                        the 21 nodes 0, 5, ..., 100, which are the ends of 20 integrator steps -- wherever the held
+ *                        input changes by at most a quarter of its size across the interval and the interval is at
+ *                        most ~0.011 orbit; all 101 nodes otherwise, decided per interval on the device.  Same sums to
+ *                        1e-13 (A_k to 1e-11: the integrator at the longer step); mpc_set_tuning(37) evaluates all
+ *                        101 nodes everywhere
  *   out                  SoA, out[row * out_pitch + out_offset + s*(K-1) + k], row in [0,105)
  *   status [n_sats*(K-1)] MPC_ST_* per interval (may be NULL)
  *
@@ -388,7 +395,8 @@ int64_t mpc_launch_count(void);
  * to 32, 16, 8, 4, 2, 1 (same results).  20 / 21 / 22: CTA size of the default-mode kernel 32 / 128 / 256 threads (same
  * results).  23 / 24 / 25: the thread-group kernel for small batches (8 lanes per interval) off / on / at any batch size
  * (results equal to rounding).  26..29: k-windows of the streamed host pass (mpc_propagate_discretize_host_layout) 16 / 32 /
- * 48 / 64 (same results). */
+ * 48 / 64 (same results).  37 / 38: the 21-node Euler-Maclaurin form of the 101-node trapezoid sums (n_sub = 100) off / on
+ * (quadrature equal to 1e-13, A_k to 1e-11). */
 int mpc_set_tuning(int variant);
 
 /* Options of the fused (in-kernel store) all-gather, applied by mpc_discretize_batch / _multi:

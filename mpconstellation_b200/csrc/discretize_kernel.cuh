@@ -338,6 +338,9 @@ struct DstTab {  // destination buffers of the (optionally multi-destination) So
     // the intervals k of all satellites are adjacent, so a window of k (the overlapped pass) writes whole rows of
     // consecutive columns -- whole 256-byte lines per warp, also to the peers -- instead of 13-column fragments.
     long long km_ntot, km_soff;
+    // != 0: the launch may evaluate the 101-node trapezoid sums of an interval through their Euler-Maclaurin expansion
+    // (kEmW below; discretize_pair_kernel decides per interval).  Set by the launcher, mpc_set_tuning(37/38).
+    int em;
 };
 
 // column of interval (s, k) in the SoA output
@@ -571,8 +574,28 @@ __device__ __forceinline__ int epilogue_store(volatile double *acc, const double
 
 // One interval, one integrator step per quadrature node: the whole per-thread computation (the kernel below is a thin
 // wrapper; discretize_pair_kernel falls back to it for intervals whose steps are too long for its midpoint interpolation).
+// The composite trapezoid sum over the reference's 101 uniform nodes (linearize_discretize.py:27-28, 77-80), from 21 of
+// them.  For a smooth integrand g the trapezoid sum with spacing h is, by the Euler-Maclaurin formula,
+//     T(h) = I + c2 h^2 + c4 h^4 + c6 h^6 + O(h^8),
+// with I the integral and c2, c4, c6 fixed by derivatives of g at the two ends of the interval -- the same numbers for every
+// h.  The sums over every 5th, 10th, 20th and 25th node, T(5h), T(10h), T(20h), T(25h), therefore determine T(h): with the
+// weights w solving sum w = 1, sum w n^2 = 1, sum w n^4 = 1, sum w n^6 = 1 for n = (5, 10, 20, 25),
+//     T(h) = sum_n w_n T(n h) + O((25 h)^8 g^(8)) .
+// w = (114114/78125, -7904/15625, 4576/78125, -209/15625); collecting the four sums node by node gives ONE rule on the 21
+// nodes j = 0, 5, ..., 100 with the positive weights below (in units of 5 h; they add up to 20).  On the reference's
+// scenarios the rule reproduces the 101-node sum to 1e-15 (the remainder is 1e-20); what it needs is that the integrand
+// Phi^-1 [B lambda, Sigma, xi'] is smooth across the interval, i.e. that the held input does not come near zero inside it
+// -- discretize_pair_kernel checks that per interval and takes the 101 nodes otherwise.  Nothing is interpolated: the 21
+// nodes are the ends of 20 Nystrom steps, whose own error at this step (5 h) is 6e-12 on 0.01-orbit intervals.
+__device__ __constant__ double kEmW[21] = {
+    48153.0 / 156250, 114114.0 / 78125, 35074.0 / 78125, 114114.0 / 78125, 53378.0 / 78125, 108889.0 / 78125, 35074.0 / 78125,
+    114114.0 / 78125, 53378.0 / 78125,  114114.0 / 78125, 29849.0 / 78125, 114114.0 / 78125, 53378.0 / 78125, 114114.0 / 78125,
+    35074.0 / 78125,  108889.0 / 78125, 53378.0 / 78125,  114114.0 / 78125, 35074.0 / 78125, 114114.0 / 78125, 48153.0 / 156250};
+constexpr int kEmSteps = 20;      // integrator steps of the rule above (n_sub = 100 only)
+
 #define ACC(e) acc[(e) * BLOCK]
-template <bool J2, int BLOCK, int NDST, bool GENU>
+// EM: n_sub is kEmSteps and node n carries the weight kEmW[n] instead of the trapezoid's 1/2, 1, ..., 1, 1/2.
+template <bool J2, int BLOCK, int NDST, bool GENU, bool EM = false>
 __device__ __forceinline__ void discretize_thread(const double *__restrict__ x, const double *__restrict__ u,
                                                   const double *__restrict__ tf_arr, const DiscParams &P, int K, int Ku,
                                                   int n_sub, const DstTab &dst, long long pitch, long long offset,
@@ -666,7 +689,7 @@ __device__ __forceinline__ void discretize_thread(const double *__restrict__ x, 
         const double md1 = -un * Ph.inv_ve;  // hs * mass flow (simulator.py:160)
         {
             const double sfrac = (double)n * inv_n;                     // lambda+   (:61)
-            const double w = (n == 0 || n == n_sub) ? 0.5 : 1.0;        // trapezoid end weights (:77-80)
+            const double w = EM ? kEmW[n] : ((n == 0 || n == n_sub) ? 0.5 : 1.0);   // trapezoid end weights (:77-80)
             const double ws = w * sfrac;
             // D Duf = [0; hs I/m; b^T];  hs D Sigma = [v~; a~; mdot~];  hs D xi' = -[v~; G~ r; mdot~_B]
             node_accumulate<BLOCK>(acc, pr, pv, P, im * hs, ux, uy, uz, iun, md1, vx, vy, vz, a1x, a1y, a1z, grx, gry, grz, w, ws);

@@ -114,6 +114,9 @@ int launch_disc_cfg(const double *x, const double *u, const double *tf, const mp
 }
 
 // discretize_pair_kernel: integrator steps spanning two quadrature nodes (needs an even number of panels)
+// mpc_set_tuning(37 / 38): the 21-node Euler-Maclaurin form of the 101-node trapezoid sums off / on (kEmW)
+std::atomic<int> g_em{1};
+
 template <bool J2, int BLOCK, int MAXREG, int NDST>
 int launch_pair_cfg(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
                     int n_sub, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
@@ -132,7 +135,9 @@ int launch_pair_cfg(const double *x, const double *u, const double *tf, const mp
     }
     const long long n_int = (long long)n_sats * kc;
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status, k0, kc);
+    mpc::DstTab tab = dst;
+    tab.em = g_em.load(std::memory_order_relaxed);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, k0, kc);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
@@ -141,10 +146,11 @@ int launch_pair_cfg(const double *x, const double *u, const double *tf, const mp
 std::atomic<int> g_pair{1};   // mpc_set_tuning(7) switches the two-node steps off (one step per node everywhere)
 std::atomic<int> g_host_windows{32};   // mpc_set_tuning(26..29): k-windows of the streamed host pass 16 / 32 / 48 / 64
 std::atomic<int> g_group{1};  // mpc_set_tuning(23 / 24): the 8-lanes-per-interval kernel for small batches off / on
-// Below this many intervals the thread-group mapping wins (measured on a B200, profiles/r02_f_small_batches.txt): the
-// one-thread kernel needs 0.118 ms whatever the batch, the group kernel 0.064 ms up to ~1000 intervals, 0.086 ms at
-// 2376 and the same 0.12 ms at 6336, where its 8x as many warps queue up on the schedulers.
-constexpr long long kGroupMaxIntervals = 4096;
+// Below this many intervals the thread-group mapping wins (measured on a B200, profiles/r02_x_small_batches.txt, both
+// kernels with the 21-node form of the 101-node sums): the one-thread kernel needs 0.053 ms whatever the batch, the group
+// kernel 0.044 ms up to ~1000 intervals, 0.049 ms at 2376 and 0.065 ms at 6336, where its 8x as many warps queue up on
+// the schedulers.  (With all 101 nodes evaluated the numbers were 0.118 / 0.064 / 0.086 / 0.12 ms, r02_f_small_batches.)
+constexpr long long kGroupMaxIntervals = 2560;
 
 template <bool J2>
 int launch_group(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, int n_sats, int K,
@@ -153,7 +159,9 @@ int launch_group(const double *x, const double *u, const double *tf, const mpc::
     constexpr int BLOCK = 32;                       // 4 intervals per CTA: spreads a small batch over every SM
     const long long n_int = (long long)n_sats * (K - 1);
     const unsigned grid = (unsigned)((n_int * 8 + BLOCK - 1) / BLOCK);
-    mpc::discretize_group_kernel<J2, BLOCK><<<grid, BLOCK, 0, st>>>(x, u, tf, P, n_sats, K, n_sub, dst, pitch, offset, status);
+    mpc::DstTab tab = dst;
+    tab.em = g_em.load(std::memory_order_relaxed);
+    mpc::discretize_group_kernel<J2, BLOCK><<<grid, BLOCK, 0, st>>>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;
@@ -753,6 +761,10 @@ int mpc_set_tuning(int variant)
     }
     if (variant >= 23 && variant <= 25) {  // small batches: 8-lanes-per-interval kernel off / on / at any size
         g_group.store(variant - 23);
+        return MPC_SUCCESS;
+    }
+    if (variant == 37 || variant == 38) {  // 101-node trapezoid sums through their Euler-Maclaurin expansion: off / on
+        g_em.store(variant - 37);
         return MPC_SUCCESS;
     }
     if (variant >= 20 && variant <= 22) {  // default-mode kernel: threads per CTA 32 / 128 / 256

@@ -79,9 +79,10 @@ def _const8(const):
 
 
 def discretize(x, u, tf, const, include_J2=False, n_sub=100, pair=True, k0=0, kc=-1, out=None, pitch=None, offset=0,
-               status=None, km_ntot=0, km_soff=0):
+               status=None, km_ntot=0, km_soff=0, em=True):
     """The fixed-step kernels (discretize_pair_kernel / discretize_kernel) on host arrays x [N,7,K], u [N,3,K] -> SoA
-    [105, pitch] + status, with the launch window (k0, kc) of the overlapped pass."""
+    [105, pitch] + status, with the launch window (k0, kc) of the overlapped pass.  em: what the launcher sets by default
+    (the pair kernel may take the 21-node form of the 101-node sums); em=False: every node evaluated."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
     N, _, K = x.shape
@@ -95,11 +96,11 @@ def discretize(x, u, tf, const, include_J2=False, n_sub=100, pair=True, k0=0, kc
     c8 = _const8(const)
     lib().hostk_discretize(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, int(n_sub), int(pair), int(k0), int(kc),
                            _p(out), ctypes.c_longlong(pitch), ctypes.c_longlong(offset), _p(status),
-                           ctypes.c_longlong(km_ntot), ctypes.c_longlong(km_soff))
+                           ctypes.c_longlong(km_ntot), ctypes.c_longlong(km_soff), int(bool(em)))
     return out, status
 
 
-def discretize_group(x, u, tf, const, include_J2=False, n_sub=100, extra_groups=0):
+def discretize_group(x, u, tf, const, include_J2=False, n_sub=100, extra_groups=0, em=True):
     """discretize_group_kernel (8 lanes per interval, the small-batch mapping) on host arrays -> SoA [105, N*(K-1)], status"""
     x = np.ascontiguousarray(x, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
@@ -110,7 +111,7 @@ def discretize_group(x, u, tf, const, include_J2=False, n_sub=100, extra_groups=
     status = np.full(n_int, -1, dtype=np.int32)
     c8 = _const8(const)
     lib().hostk_discretize_group(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), N, K, int(n_sub), _p(out),
-                                 ctypes.c_longlong(n_int), ctypes.c_longlong(0), _p(status), int(extra_groups))
+                                 ctypes.c_longlong(n_int), ctypes.c_longlong(0), _p(status), int(extra_groups), int(bool(em)))
     return out, status
 
 

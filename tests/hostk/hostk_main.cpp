@@ -49,13 +49,14 @@ mpc::DiscParams disc_params(const double *c, int)
 // const8 = [MU, R_E, J2, G0, ISP, S, R0, RHO] (the order of mpc_params / OracleConstants)
 extern "C" int hostk_discretize(const double *x, const double *u, const double *tf, const double *const8, int include_j2,
                                 int n_sats, int K, int n_sub, int pair, int k0, int kc, double *out, long long pitch,
-                                long long offset, int32_t *status, long long km_ntot, long long km_soff)
+                                long long offset, int32_t *status, long long km_ntot, long long km_soff, int em)
 {
     const mpc::DiscParams P = disc_params(const8, include_j2);
     mpc::DstTab dst{};
     dst.p[0] = out;
     dst.km_ntot = km_ntot;     // > 0: k-major layout, column = k km_ntot + km_soff + s
     dst.km_soff = km_soff;
+    dst.em = em;               // the launcher's default: 1 (21-node form of the 101-node sums where the interval allows it)
     if (kc < 0) kc = K - 1;
     if (pair) {
         run_grid((long long)n_sats * kc, [&] {
@@ -75,11 +76,12 @@ extern "C" int hostk_discretize(const double *x, const double *u, const double *
 // after group; threadIdx / blockIdx are what the 32-thread CTAs of the real launch would give them
 extern "C" int hostk_discretize_group(const double *x, const double *u, const double *tf, const double *const8, int include_j2,
                                       int n_sats, int K, int n_sub, double *out, long long pitch, long long offset,
-                                      int32_t *status, int extra_groups)
+                                      int32_t *status, int extra_groups, int em)
 {
     const mpc::DiscParams P = disc_params(const8, include_j2);
     mpc::DstTab dst{};
     dst.p[0] = out;
+    dst.em = em;
     const long long n_groups = (long long)n_sats * (K - 1) + extra_groups;   // extra: the idle groups of a last partial warp
     for (long long g = 0; g < n_groups; ++g) {
         hostk_group_ctx ctx;

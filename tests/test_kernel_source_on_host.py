@@ -652,3 +652,108 @@ def test_end_node_input_lookup_follows_the_reference_on_every_node_of_every_grid
         assert np.max(np.abs(got - ref)) <= 4e-16 * np.max(np.abs(us)), Ku
         lower += sum(int(t // (1 / (Ku - 1))) < i for i, t in enumerate(tau[:-1]))
     assert lower > 50000          # the lookup lands in the interval LEFT of the node in a third of the cases: exercised
+
+
+# ---- the 101-node trapezoid sums from 21 nodes (Euler-Maclaurin form, kEmW in csrc/discretize_kernel.cuh) -----------------
+
+def _em_rule():
+    """T(h) = sum_n w_n T(n h) for n = 5, 10, 20, 25 with sum w n^(2r) = 1 (r = 0..3), collected node by node: the weight of
+    node j = 5 i in units of 5 h, as exact fractions"""
+    from fractions import Fraction as F
+    ns = [5, 10, 20, 25]
+    A = [[F(n) ** (2 * r) for n in ns] for r in range(4)]
+    b = [F(1)] * 4
+    for c in range(4):
+        for r in range(4):
+            if r != c:
+                f = A[r][c] / A[c][c]
+                A[r] = [a - f * q for a, q in zip(A[r], A[c])]
+                b[r] -= f * b[c]
+    w = [b[i] / A[i][i] for i in range(4)]
+    W = [F(0)] * 21
+    for wn, n in zip(w, ns):
+        p = 100 // n
+        for j in range(p + 1):
+            W[j * n // 5] += wn * n * (F(1, 2) if j in (0, p) else 1) / 5
+    return w, W
+
+
+def test_the_21_node_rule_is_the_euler_maclaurin_combination_of_four_trapezoid_sums():
+    """the literals of kEmW are the exact rational weights; they are positive, symmetric and add up to the 20 coarse panels"""
+    import re
+    from fractions import Fraction as F
+    w, W = _em_rule()
+    assert [str(q) for q in w] == ["114114/78125", "-7904/15625", "4576/78125", "-209/15625"]
+    src = open(os.path.join(os.path.dirname(hostk.CSRC), "csrc", "discretize_kernel.cuh")).read() if hasattr(hostk, "CSRC") else \
+        open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mpconstellation_b200", "csrc",
+                          "discretize_kernel.cuh")).read()
+    body = re.search(r"kEmW\[21\] = \{(.*?)\};", src, re.S).group(1)
+    lits = [F(int(float(a)), int(b)) for a, b in re.findall(r"([0-9.]+) / ([0-9]+)", body)]
+    assert lits == W and sum(W) == 20 and all(q > 0 for q in W) and W == W[::-1]
+    # the rule returns the 101-node trapezoid sum -- not the integral -- exactly for polynomials through degree 7 and to
+    # rounding for functions that vary across the interval the way the integrands do (0.06 ... 0.2 rad); the remainder
+    # grows like the eighth power of the variation (1e-11 at 2 rad)
+    t = np.linspace(0.0, 1.0, 101)
+
+    def both(g):
+        return 0.01 * (g[0] / 2 + g[-1] / 2 + g[1:-1].sum()), 0.05 * sum(float(W[i]) * g[5 * i] for i in range(21))
+
+    for g in (t ** 7 - 0.3 * t ** 5 + t, np.exp(0.05 * t) * np.cos(0.2 * t + 0.4), 1.0 / (1.0 + 0.02 * t) ** 2):
+        full, em = both(g)
+        assert abs(em - full) <= 4e-16 * abs(full)
+        assert abs(full - (0.01 * g[:-1].sum() + 0.005 * (g[-1] - g[0]))) < 1e-15      # (it IS the trapezoid sum)
+    full, em = both(np.cos(2.0 * t + 0.4))
+    assert 1e-13 < abs(em - full) < 1e-10
+
+
+@pytest.mark.parametrize("j2", [False, True])
+def test_21_node_form_of_the_fixed_step_kernels_reproduces_the_101_node_sums(const, j2):
+    """discretize_pair_kernel / discretize_group_kernel as launched (em: 20 steps + the 21-node rule where the interval
+    allows it) against the same kernels with every node evaluated and against the plain-C oracle's literal 101-node sums:
+    the quadrature to 1e-12, A_k (the integrator at step 5 h) to 2e-11"""
+    for n_sats, K, tf in ((5, 23, 0.23), (3, 50, 0.5)):
+        _, x, u = synth_batch(n_sats, K, tf, const)
+        a, sa = hostk.discretize(x, u, tf, const, include_J2=j2)
+        b, sb = hostk.discretize(x, u, tf, const, include_J2=j2, em=False)
+        g, sg = hostk.discretize_group(x, u, tf, const, include_J2=j2)
+        assert sa.max() == 0 and sb.max() == 0 and sg.max() == 0 and not np.array_equal(a, b)
+        assert rel_err(a[0:49], b[0:49]) < 2e-11
+        for r0, r1 in ((49, 70), (70, 91), (91, 98), (98, 105)):
+            assert rel_err(a[r0:r1], b[r0:r1]) < 1e-12, (r0, K)
+        assert rel_err(a, g) < 1e-13 and rel_err(a[0:49], g[0:49]) < 1e-14      # the thread-group kernel takes the same form
+        ref = C.discretize_batch(x, u, tf, const, include_J2=j2)
+        for n, o in zip(NAMES, hostk.stacked(a, n_sats, K)):
+            assert rel_err(o, ref[NAMES.index(n)]) < 2e-11, n
+
+
+def test_21_node_form_is_taken_only_where_the_integrands_are_smooth(const):
+    """per interval: a held input that changes by more than a quarter of its size between the two nodes (a thrust jump, a
+    sign flip through zero, coast-to-thrust) and intervals too long for the step 5 h take the 101 nodes -- bit-identical to
+    the launch without the rule; coast arcs (u = 0 at both nodes) and slowly varying thrust take the rule"""
+    n_sats, K, tf = 4, 23, 0.23
+    _, x, u = synth_batch(n_sats, K, tf, const)
+    u = u.copy()
+    u[0, :, 8:] *= 1.5                    # jump by 50 % between nodes 7 and 8 of satellite 0
+    u[1, :, 5:9] = 0.0                    # coast arc: intervals 5..7 are all-zero, 4 and 8 switch
+    u[2, :, 12:] *= -1.0                  # the hold passes through zero inside interval 11
+    u[3, :, 10] *= 1.2                    # 20 % up and down again: smooth enough on both sides
+    a, sa = hostk.discretize(x, u, tf, const)
+    b, sb = hostk.discretize(x, u, tf, const, em=False)
+    assert sa.max() == 0 and sb.max() == 0
+    same = np.all(a == b, axis=0).reshape(n_sats, K - 1)
+    expect = np.zeros((n_sats, K - 1), dtype=bool)          # True: the 101 nodes were taken
+    expect[0, 7] = expect[1, 4] = expect[1, 8] = expect[2, 11] = True
+    assert np.array_equal(same, expect)
+    assert rel_err(a, b) < 2e-11
+    ref = C.discretize_batch(x, u, tf, const)
+    for n, o in zip(NAMES, hostk.stacked(a, n_sats, K)):
+        assert rel_err(o, ref[NAMES.index(n)]) < 2e-11, n
+    # long intervals (0.034 orbit): the step 5 h would cost 1e-9, every interval takes the 101 nodes
+    _, x2, u2 = synth_batch(2, 16, 0.5, const)
+    a2, _ = hostk.discretize(x2, u2, 0.5, const)
+    b2, _ = hostk.discretize(x2, u2, 0.5, const, em=False)
+    assert np.array_equal(a2, b2)
+    # other node counts than the reference's 101: untouched
+    a3, _ = hostk.discretize(x, u, tf, const, n_sub=50)
+    b3, _ = hostk.discretize(x, u, tf, const, n_sub=50, em=False)
+    assert np.array_equal(a3, b3)
