@@ -19,7 +19,8 @@ out = torch.empty((105, N * (K - 1)), dtype=torch.float64, device=dev)
 sp = torch.empty(N, dtype=torch.int32, device=dev)
 sd = torch.empty(N * (K - 1), dtype=torch.int32, device=dev)
 flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-n_prop = M.batch.default_n_sub(K)
+n_prop = M.batch.default_n_sub(K) if "--rk4" in sys.argv else 0       # 0: the RK45 replay (the default propagator)
+sys.argv = [a for a in sys.argv if a != "--rk4"]
 
 
 def seq():
