@@ -757,3 +757,30 @@ def test_21_node_form_is_taken_only_where_the_integrands_are_smooth(const):
     a3, _ = hostk.discretize(x, u, tf, const, n_sub=50)
     b3, _ = hostk.discretize(x, u, tf, const, n_sub=50, em=False)
     assert np.array_equal(a3, b3)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_21_node_form_on_random_thrust_tables(const, seed):
+    """seeded sweep: inputs whose direction and size change from node to node by random amounts (0 ... 40 % of their size:
+    part of the intervals take the rule right at its smoothness bound, part fall back), J2 on and off, several grids -- the
+    launch with the rule never differs from the launch that evaluates every node by more than the integrator's 2e-11
+    (quadrature: 2e-12)"""
+    rng = np.random.default_rng(seed)
+    n_sats, K, tf = 6, int(rng.integers(12, 40)), None
+    tf = 0.0101 * (K - 1) * float(rng.uniform(0.5, 1.05))          # intervals of 0.005 ... 0.0106 orbit
+    _, x, u = synth_batch(n_sats, K, tf, const)
+    u = u.copy()
+    for s in range(n_sats):
+        for k in range(1, K):
+            d = rng.normal(size=3)
+            d *= rng.uniform(0.0, 0.4) * np.linalg.norm(u[s, :, k - 1]) / np.linalg.norm(d)
+            u[s, :, k] = u[s, :, k - 1] + d
+    j2 = bool(seed % 2)
+    a, sa = hostk.discretize(x, u, tf, const, include_J2=j2)
+    b, sb = hostk.discretize(x, u, tf, const, include_J2=j2, em=False)
+    assert sa.max() == 0 and sb.max() == 0
+    took = ~np.all(a == b, axis=0)
+    assert 0.2 < took.mean() < 0.98                                    # both branches exercised
+    assert rel_err(a[0:49], b[0:49]) < 2e-11
+    for r0, r1 in ((49, 70), (70, 91), (91, 98), (98, 105)):
+        assert rel_err(a[r0:r1], b[r0:r1]) < 2e-12, (r0, seed)
