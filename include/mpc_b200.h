@@ -113,7 +113,8 @@ int mpc_device_info(int device, char *name, int name_len, int *sm_count, int *cc
  *                        through their Euler-Maclaurin expansion -- T(h) = sum_n w_n T(n h), n = 5, 10, 20, 25: one rule on
  *                        the 21 nodes 0, 5, ..., 100, which are the ends of 20 integrator steps -- wherever the held
  *                        input changes by at most a quarter of its size across the interval and the interval is at
- *                        most ~0.011 orbit; all 101 nodes otherwise, decided per interval on the device.  Same sums to
+ *                        most ~0.011 orbit (up to ~0.035 orbit: n = 2, 4, 10, 20, the 51 even nodes, 50 steps); all
+ *                        101 nodes otherwise, decided per interval on the device.  Same sums to
  *                        1e-13 (A_k to 1e-11: the integrator at the longer step); mpc_set_tuning(37) evaluates all
  *                        101 nodes everywhere
  *   out                  SoA, out[row * out_pitch + out_offset + s*(K-1) + k], row in [0,105)

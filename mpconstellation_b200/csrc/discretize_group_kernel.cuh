@@ -109,7 +109,8 @@ discretize_group_kernel(const double *__restrict__ x, const double *__restrict__
     // two-node steps where discretize_pair_kernel takes them (even number of panels, step short against the orbital rate)
     // ... and the 21-node form of the 101-node sums (kEmW, discretize_kernel.cuh) where discretize_pair_kernel takes it:
     // 20 steps of five nodes, the step ends are the nodes of the rule
-    bool pairmode, em = false;
+    bool pairmode;
+    int em = 0;                     // 1: 20 steps + kEmW, 2: 50 steps + kEmW2
     {
         const double r2 = fma(rx, rx, fma(ry, ry, rz * rz));
         const double w2H2 = P.mu * (4.0 * hn * hn) / (r2 * sqrt(r2));
@@ -119,11 +120,11 @@ discretize_group_kernel(const double *__restrict__ x, const double *__restrict__
             const double e0x = hold.u0x + hold.dux, e0y = hold.u0y + hold.duy, e0z = hold.u0z + hold.duz;
             const double a2 = fma(hold.u0x, hold.u0x, fma(hold.u0y, hold.u0y, hold.u0z * hold.u0z));
             const double b2 = fma(e0x, e0x, fma(e0y, e0y, e0z * e0z));
-            em = d2 <= 0.0625 * fmax(a2, b2) && w2H2 * 6.25 <= 1.2e-5;
+            if (d2 <= 0.0625 * fmax(a2, b2)) em = (w2H2 * 6.25 <= 1.2e-5) ? 1 : ((w2H2 <= 1.94e-5) ? 2 : 0);
         }
         if (em) pairmode = false;
     }
-    const int nodes_per_step = em ? 5 : (pairmode ? 2 : 1);
+    const int nodes_per_step = (em == 1) ? 5 : ((em == 2 || pairmode) ? 2 : 1);
     const int n_steps = n_sub / nodes_per_step;
     const double H = hn * (double)nodes_per_step;      // integrator step
     // step-normalised variables as in discretize_kernel, with the step H
@@ -189,7 +190,7 @@ discretize_group_kernel(const double *__restrict__ x, const double *__restrict__
         s1.dz = -tz * im * dflag;
         const double md1 = -un * Ph.inv_ve;
         {
-            const double w = em ? 5.0 * kEmW[j] : ((j == 0 || j == n_steps) ? 0.5 : 1.0);
+            const double w = (em == 1) ? 5.0 * kEmW[j] : ((em == 2) ? 2.0 * kEmW2[j] : ((j == 0 || j == n_steps) ? 0.5 : 1.0));
             const double bs = -P.inv_ve * iun;
             const double b[3] = {bs * ux, bs * uy, bs * uz};
             const double cr[3] = {grp_bcast(pr[0], 6), grp_bcast(pr[1], 6), grp_bcast(pr[2], 6)};

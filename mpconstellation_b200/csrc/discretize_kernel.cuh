@@ -592,10 +592,22 @@ __device__ __constant__ double kEmW[21] = {
     114114.0 / 78125, 53378.0 / 78125,  114114.0 / 78125, 29849.0 / 78125, 114114.0 / 78125, 53378.0 / 78125, 114114.0 / 78125,
     35074.0 / 78125,  108889.0 / 78125, 53378.0 / 78125,  114114.0 / 78125, 35074.0 / 78125, 114114.0 / 78125, 48153.0 / 156250};
 constexpr int kEmSteps = 20;      // integrator steps of the rule above (n_sub = 100 only)
+// The same construction for intervals too long for the step 5 h (up to ~0.035 orbit: BASELINE config 5): the sums over
+// every 2nd, 4th, 10th and 20th node, w = (665/512, -627/2048, 19/2560, -1/10240), one rule on the 51 even nodes = the ends
+// of 50 steps (weights in units of 2 h; they add up to 50).  Half the node terms of the all-nodes path and no midpoint.
+__device__ __constant__ double kEmW2[51] = {
+    185.0 / 512, 665.0 / 512, 703.0 / 1024, 665.0 / 512, 703.0 / 1024, 171.0 / 128, 703.0 / 1024, 665.0 / 512, 703.0 /
+    1024, 665.0 / 512, 185.0 / 256, 665.0 / 512, 703.0 / 1024, 665.0 / 512, 703.0 / 1024, 171.0 / 128, 703.0 / 1024,
+    665.0 / 512, 703.0 / 1024, 665.0 / 512, 185.0 / 256, 665.0 / 512, 703.0 / 1024, 665.0 / 512, 703.0 / 1024, 171.0 /
+    128, 703.0 / 1024, 665.0 / 512, 703.0 / 1024, 665.0 / 512, 185.0 / 256, 665.0 / 512, 703.0 / 1024, 665.0 / 512,
+    703.0 / 1024, 171.0 / 128, 703.0 / 1024, 665.0 / 512, 703.0 / 1024, 665.0 / 512, 185.0 / 256, 665.0 / 512, 703.0 /
+    1024, 665.0 / 512, 703.0 / 1024, 171.0 / 128, 703.0 / 1024, 665.0 / 512, 703.0 / 1024, 665.0 / 512, 185.0 / 512};
+constexpr int kEmSteps2 = 50;
 
 #define ACC(e) acc[(e) * BLOCK]
-// EM: n_sub is kEmSteps and node n carries the weight kEmW[n] instead of the trapezoid's 1/2, 1, ..., 1, 1/2.
-template <bool J2, int BLOCK, int NDST, bool GENU, bool EM = false>
+// EM = 1 / 2: n_sub is kEmSteps / kEmSteps2 and node n carries the weight kEmW[n] / kEmW2[n] instead of the trapezoid's
+// 1/2, 1, ..., 1, 1/2.
+template <bool J2, int BLOCK, int NDST, bool GENU, int EM = 0>
 __device__ __forceinline__ void discretize_thread(const double *__restrict__ x, const double *__restrict__ u,
                                                   const double *__restrict__ tf_arr, const DiscParams &P, int K, int Ku,
                                                   int n_sub, const DstTab &dst, long long pitch, long long offset,
@@ -689,7 +701,7 @@ __device__ __forceinline__ void discretize_thread(const double *__restrict__ x, 
         const double md1 = -un * Ph.inv_ve;  // hs * mass flow (simulator.py:160)
         {
             const double sfrac = (double)n * inv_n;                     // lambda+   (:61)
-            const double w = EM ? kEmW[n] : ((n == 0 || n == n_sub) ? 0.5 : 1.0);   // trapezoid end weights (:77-80)
+            const double w = (EM == 1) ? kEmW[n] : ((EM == 2) ? kEmW2[n] : ((n == 0 || n == n_sub) ? 0.5 : 1.0));   // trapezoid end weights (:77-80)
             const double ws = w * sfrac;
             // D Duf = [0; hs I/m; b^T];  hs D Sigma = [v~; a~; mdot~];  hs D xi' = -[v~; G~ r; mdot~_B]
             node_accumulate<BLOCK>(acc, pr, pv, P, im * hs, ux, uy, uz, iun, md1, vx, vy, vz, a1x, a1y, a1z, grx, gry, grz, w, ws);

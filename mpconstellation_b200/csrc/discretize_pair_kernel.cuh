@@ -179,9 +179,16 @@ discretize_pair_kernel(const double *__restrict__ x, const double *__restrict__ 
             const double e0x = hold.u0x + hold.dux, e0y = hold.u0y + hold.duy, e0z = hold.u0z + hold.duz;
             const double a2 = fma(hold.u0x, hold.u0x, fma(hold.u0y, hold.u0y, hold.u0z * hold.u0z));
             const double b2 = fma(e0x, e0x, fma(e0y, e0y, e0z * e0z));
-            if (d2 <= 0.0625 * fmax(a2, b2) && w2H2 * 6.25 <= 1.2e-5) {
-                discretize_thread<J2, BLOCK, NDST, false, true>(x, u, tf_arr, P, K, K, kEmSteps, dst, pitch, offset, status, gid, acc);
-                return;
+            if (d2 <= 0.0625 * fmax(a2, b2)) {
+                if (w2H2 * 6.25 <= 1.2e-5) {
+                    discretize_thread<J2, BLOCK, NDST, false, 1>(x, u, tf_arr, P, K, K, kEmSteps, dst, pitch, offset, status, gid, acc);
+                    return;
+                }
+                // longer intervals (omega 2h <= 4.4e-3 rad: 0.035-orbit intervals): 50 steps and the 51-node rule kEmW2
+                if (w2H2 <= 1.94e-5) {
+                    discretize_thread<J2, BLOCK, NDST, false, 2>(x, u, tf_arr, P, K, K, kEmSteps2, dst, pitch, offset, status, gid, acc);
+                    return;
+                }
             }
         }
         if ((n_sub & 1) || !(w2H2 <= 1.0e-5)) {

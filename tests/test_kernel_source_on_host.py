@@ -728,8 +728,8 @@ def test_21_node_form_of_the_fixed_step_kernels_reproduces_the_101_node_sums(con
 
 def test_21_node_form_is_taken_only_where_the_integrands_are_smooth(const):
     """per interval: a held input that changes by more than a quarter of its size between the two nodes (a thrust jump, a
-    sign flip through zero, coast-to-thrust) and intervals too long for the step 5 h take the 101 nodes -- bit-identical to
-    the launch without the rule; coast arcs (u = 0 at both nodes) and slowly varying thrust take the rule"""
+    sign flip through zero, coast-to-thrust) and intervals too long for either rule take the 101 nodes -- bit-identical to
+    the launch without the rules; coast arcs (u = 0 at both nodes) and slowly varying thrust take them"""
     n_sats, K, tf = 4, 23, 0.23
     _, x, u = synth_batch(n_sats, K, tf, const)
     u = u.copy()
@@ -748,11 +748,22 @@ def test_21_node_form_is_taken_only_where_the_integrands_are_smooth(const):
     ref = C.discretize_batch(x, u, tf, const)
     for n, o in zip(NAMES, hostk.stacked(a, n_sats, K)):
         assert rel_err(o, ref[NAMES.index(n)]) < 2e-11, n
-    # long intervals (0.034 orbit): the step 5 h would cost 1e-9, every interval takes the 101 nodes
+    # longer intervals (0.033 orbit, BASELINE config 5): the step 5 h would cost 1e-9; they take 50 steps and the 51-node
+    # rule (kEmW2), the thread-group kernel too
     _, x2, u2 = synth_batch(2, 16, 0.5, const)
     a2, _ = hostk.discretize(x2, u2, 0.5, const)
     b2, _ = hostk.discretize(x2, u2, 0.5, const, em=False)
-    assert np.array_equal(a2, b2)
+    g2, _ = hostk.discretize_group(x2, u2, 0.5, const)
+    ref2 = C.discretize_batch(x2, u2, 0.5, const)
+    assert not np.any(np.all(a2 == b2, axis=0)) and rel_err(a2[0:49], b2[0:49]) < 5e-11 and rel_err(a2[49:], b2[49:]) < 2e-12
+    assert rel_err(a2, g2) < 1e-13
+    for n, o in zip(NAMES, hostk.stacked(a2, 2, 16)):
+        assert rel_err(o, ref2[NAMES.index(n)]) < 5e-11, n
+    # still longer ones (0.06 orbit): all 101 nodes, one step per node
+    _, x4, u4 = synth_batch(2, 9, 0.5, const)
+    a4, _ = hostk.discretize(x4, u4, 0.5, const)
+    b4, _ = hostk.discretize(x4, u4, 0.5, const, em=False)
+    assert np.array_equal(a4, b4)
     # other node counts than the reference's 101: untouched
     a3, _ = hostk.discretize(x, u, tf, const, n_sub=50)
     b3, _ = hostk.discretize(x, u, tf, const, n_sub=50, em=False)
