@@ -211,6 +211,28 @@ discretize_drag_kernel(const double *__restrict__ x_in, const double *__restrict
     for (int c = 0; c < 7; ++c) x[c] = xs[(long long)c * K];
     UHold<false> hold;
     hold.init(u_in, s, k, K, K);
+    // The reference's 101 nodes: the trapezoid sums through their Euler-Maclaurin expansion (kEmW / kEmW2 in
+    // discretize_kernel.cuh: 21 nodes = the ends of 20 steps, or 51 nodes / 50 steps on longer intervals), under the same
+    // per-interval conditions as discretize_pair_kernel; drag is smooth in the state, so nothing else changes.
+    const double *wt = nullptr;
+    if (dst.em && n_sub == 100) {
+        const double d2 = fma(hold.dux, hold.dux, fma(hold.duy, hold.duy, hold.duz * hold.duz));
+        const double e0x = hold.u0x + hold.dux, e0y = hold.u0y + hold.duy, e0z = hold.u0z + hold.duz;
+        const double a2 = fma(hold.u0x, hold.u0x, fma(hold.u0y, hold.u0y, hold.u0z * hold.u0z));
+        const double b2 = fma(e0x, e0x, fma(e0y, e0y, e0z * e0z));
+        const double r2 = fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2]));
+        const double hn = tf / (100.0 * (double)(K - 1));
+        const double w2h2 = P.mu * hn * hn / (r2 * sqrt(r2));            // (omega h)^2 for the node spacing h
+        if (d2 <= 0.0625 * fmax(a2, b2)) {
+            if (w2h2 * 25.0 <= 1.2e-5) {
+                wt = kEmW;
+                n_sub = kEmSteps;
+            } else if (w2h2 * 4.0 <= 1.94e-5) {
+                wt = kEmW2;
+                n_sub = kEmSteps2;
+            }
+        }
+    }
     const double inv_n = 1.0 / (double)n_sub;
     const double h = inv_n / (double)(K - 1);
     const double hs = tf * h, hh = 0.5 * hs, h6 = hs * (1.0 / 6.0);
@@ -234,7 +256,7 @@ discretize_drag_kernel(const double *__restrict__ x_in, const double *__restrict
         DragEval e1;
         bad |= drag_eval<J2>(P, kf, ka, x, ux, uy, uz, e1);
         {
-            const double w = (n == 0 || n == n_sub) ? 0.5 : 1.0;
+            const double w = wt ? wt[n] : ((n == 0 || n == n_sub) ? 0.5 : 1.0);
             node_accumulate_general<BLOCK>(acc, pr, pv, P, e1, x, w, w * ((double)n * inv_n));
         }
         if (n == n_sub) break;

@@ -385,7 +385,9 @@ int launch_disc_drag(const double *x, const double *u, const double *tf, const m
     }
     const long long n_int = (long long)n_sats * (K - 1);
     const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, kf, ka, n_sats, K, n_sub, dst, pitch, offset, status);
+    mpc::DstTab tab = dst;
+    tab.em = g_em.load(std::memory_order_relaxed);
+    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, kf, ka, n_sats, K, n_sub, tab, pitch, offset, status);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return MPC_SUCCESS;

@@ -180,7 +180,7 @@ def propagate_rk45(y0, tf, const, kind=0, thrust=(0.0, 0.0, 0.0), table=None, en
     return y, uo, status, steps, progress
 
 
-def discretize_drag(x, u, tf, const, drag, include_J2=False, n_sub=100, adaptive=None, c_d=2.5, rho_atm=9.983e-13):
+def discretize_drag(x, u, tf, const, drag, include_J2=False, n_sub=100, adaptive=None, c_d=2.5, rho_atm=9.983e-13, em=True):
     """The drag kernels (discretize_drag_kernel / the DRAG variant of the adaptive kernel); drag = (const.CD, rho_func
     value), as mpconstellation_b200.discretize_batch(disc_drag=...)."""
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -198,7 +198,8 @@ def discretize_drag(x, u, tf, const, drag, include_J2=False, n_sub=100, adaptive
     D = ctypes.c_double
     lib().hostk_discretize_drag(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), D(kf), D(ka), N, K, int(n_sub),
                                 int(adaptive is not None), D(ad.get("rtol", 1e-3)), D(ad.get("atol", 1e-6)),
-                                D(ad.get("max_step", 1e-2)), _p(out), ctypes.c_longlong(n_int), _p(status), _p(nodes))
+                                D(ad.get("max_step", 1e-2)), _p(out), ctypes.c_longlong(n_int), _p(status), _p(nodes),
+                                int(bool(em)))
     return out, status, nodes
 
 

@@ -223,11 +223,12 @@ extern "C" int hostk_propagate_rk45(const double *y0, const double *tf, const do
 extern "C" int hostk_discretize_drag(const double *x, const double *u, const double *tf, const double *const8,
                                      int include_j2, double kf, double ka, int n_sats, int K, int n_sub, int adaptive,
                                      double rtol, double atol, double max_step, double *out, long long pitch,
-                                     int32_t *status, int32_t *n_nodes)
+                                     int32_t *status, int32_t *n_nodes, int em)
 {
     const mpc::DiscParams P = disc_params(const8, include_j2);
     mpc::DstTab dst{};
     dst.p[0] = out;
+    dst.em = em;
     run_grid((long long)n_sats * (K - 1), [&] {
         if (adaptive) {
             if (include_j2)

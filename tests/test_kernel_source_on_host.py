@@ -795,3 +795,18 @@ def test_21_node_form_on_random_thrust_tables(const, seed):
     assert rel_err(a[0:49], b[0:49]) < 2e-11
     for r0, r1 in ((49, 70), (70, 91), (91, 98), (98, 105)):
         assert rel_err(a[r0:r1], b[r0:r1]) < 2e-12, (r0, seed)
+
+
+def test_21_and_51_node_forms_in_the_drag_kernel(const):
+    """discretize_drag_kernel (classical RK4 on the first-order system, dense 6x6 solve at the nodes) takes the same two
+    rules under the same per-interval conditions: against the launch that evaluates every node and against the oracle"""
+    drag = (2.5, 1.0e4 * 9.983e-13 / 3.6806e-17 * 3.6806e-17)          # const.CD, a density large enough to matter
+    for n_sats, K, tf, tol in ((3, 23, 0.23, 2e-11), (2, 16, 0.5, 1e-10)):
+        _, x, u = synth_batch(n_sats, K, tf, const)
+        a, sa, _ = hostk.discretize_drag(x, u, tf, const, drag, include_J2=True)
+        b, sb, _ = hostk.discretize_drag(x, u, tf, const, drag, include_J2=True, em=False)
+        assert sa.max() == 0 and sb.max() == 0 and not np.array_equal(a, b)
+        assert rel_err(a[0:49], b[0:49]) < tol and rel_err(a[49:], b[49:]) < tol / 10
+        ref = C.discretize_batch(x, u, tf, const, include_J2=True, drag=drag)
+        for n, o in zip(NAMES, hostk.stacked(a, n_sats, K)):
+            assert rel_err(o, ref[NAMES.index(n)]) < tol, n
