@@ -80,14 +80,26 @@ __device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C
     const double m = y[6];
     const double r2 = fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2]));
     const double ir = fast_rsqrt(r2);
-    double ux, uy, uz;
-    ctrl_eval<KIND>(C, tab, end_tau, y, ir, tau, ux, uy, uz);
     const double ir2 = ir * ir;
     const double mu3 = P.mu * ir * ir2;
     const double im = fast_rcp(m);
-    double ax = fma(-mu3, y[0], ux * im);
-    double ay = fma(-mu3, y[1], uy * im);
-    double az = fma(-mu3, y[2], uz * im);
+    double ux = 0.0, uy = 0.0, uz = 0.0, ax, ay, az;
+    if (KIND == 2) {
+        // the tangential law (ctrl_eval<2>) with 1/m folded into its scale: u/m = (mag / (|h| |r| m)) (h x r) -- two
+        // multiplications per evaluation fewer than forming u first (|u| is the constant mag, below)
+        const double hx = fma(y[1], y[5], -y[2] * y[4]);
+        const double hy = fma(y[2], y[3], -y[0] * y[5]);
+        const double hz = fma(y[0], y[4], -y[1] * y[3]);
+        const double scm = C.t0 * ir * fast_rsqrt(fma(hx, hx, fma(hy, hy, hz * hz))) * im;
+        ax = fma(scm, fma(hy, y[2], -hz * y[1]), -mu3 * y[0]);
+        ay = fma(scm, fma(hz, y[0], -hx * y[2]), -mu3 * y[1]);
+        az = fma(scm, fma(hx, y[1], -hy * y[0]), -mu3 * y[2]);
+    } else {
+        ctrl_eval<KIND>(C, tab, end_tau, y, ir, tau, ux, uy, uz);
+        ax = fma(-mu3, y[0], ux * im);
+        ay = fma(-mu3, y[1], uy * im);
+        az = fma(-mu3, y[2], uz * im);
+    }
     if (DRAG) {
         const double v2 = fma(y[3], y[3], fma(y[4], y[4], y[5] * y[5]));
         const double vn = (v2 > 0.0) ? v2 * fast_rsqrt(v2) : 0.0;
