@@ -102,6 +102,6 @@ __attribute__((noinline)) static double __dadd_rn(double a, double b) { return a
 __attribute__((noinline)) static double __ddiv_rn(double a, double b) { return a / b; }
 __attribute__((noinline)) static double __dsqrt_rn(double a) { return sqrt(a); }
 // Stand-ins for the MUFU seeds (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64: ~20 good bits): the exact value rounded to
-// float.  The kernels refine the seed with two Newton steps, so results agree with the device to rounding.
+// float.  The kernels refine the seed with one third-order step, so results agree with the device to rounding.
 static inline double hostk_rcp_seed(double a) { return (double)(float)(1.0 / a); }
 static inline double hostk_rsqrt_seed(double a) { return (double)(float)(1.0 / sqrt(a)); }
