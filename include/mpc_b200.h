@@ -64,11 +64,19 @@ typedef struct mpc_params {
     double s_area, r0, rho;
     double c_d, rho_atm;  /* drag of the DYNAMICS: module-level C_D and density        simulator.py:150-153 */
     double disc_cd;       /* drag of the LINEARISATION: const.CD ...                  linearize_discretize.py:165-168 */
-    double disc_rho;      /* ... and rho_func(r) (constant density, drho_func = 0); 0, 0 = not supplied */
+    double disc_rho;      /* ... and rho_func(r) when the density is constant (drho_func = 0); 0, 0 = not supplied */
     int32_t include_j2;   /* Discretizer(include_J2=...) / Simulator(include_J2=...) */
     int32_t include_drag; /* Simulator(include_drag=...); Discretizer(include_drag=...): needs disc_cd / disc_rho --
                              without them the reference raises (rho_func is None, Constants has no CD) and so do we */
+    /* Altitude-dependent density in the drag LINEARISATION (rho_func(r), drho_func(r) of linearize_discretize.py:164-166,
+     * e.g. the power law of simulator.py:110): Chebyshev series in t = (|r| - disc_r_mid) * disc_r_ihalf over the radii of
+     * the batch, sum_k c_k T_k(t).  disc_n_rho = 0: the constant disc_rho above (and no gradient).  disc_n_drho = 0:
+     * drho_func = 0.  Fitted and verified by the host (mpconstellation_b200/discretizer.py: fit_density). */
+    int32_t disc_n_rho, disc_n_drho; /* 0 .. MPC_RHO_CHEB */
+    double disc_r_mid, disc_r_ihalf;
+    double disc_rho_cheb[32], disc_drho_cheb[32];
 } mpc_params;
+#define MPC_RHO_CHEB 32
 
 /* Controller laws the propagator can evaluate on the device (control.py). */
 #define MPC_CTRL_ZERO 0       /* Controller.get_u_func                      control.py:20-29   */

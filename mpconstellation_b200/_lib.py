@@ -14,8 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libmpc_b200.so")
-SOURCES = ["mpc_b200.cu"]
-HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_default_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "discretize_group_kernel.cuh", "constraint_terms_kernel.cuh", "discretize_drag_kernel.cuh", "discretize_pair_kernel.cuh", os.path.join("..", "..", "include", "mpc_b200.h")]
+SOURCES = ["mpc_b200.cu", "mpc_b200_drag.cu"]    # the drag-branch kernels have a translation unit of their own
+HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_default_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "discretize_group_kernel.cuh", "constraint_terms_kernel.cuh", "discretize_drag_kernel.cuh", "discretize_pair_kernel.cuh", "mpc_b200_drag.h", os.path.join("..", "..", "include", "mpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-split-compile", "0"]
 
@@ -34,7 +34,13 @@ E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4
 class MpcParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double) for n in
                 ("mu", "r_e", "j2", "g0", "isp", "s_area", "r0", "rho", "c_d", "rho_atm", "disc_cd", "disc_rho")] + \
-               [("include_j2", ctypes.c_int32), ("include_drag", ctypes.c_int32)]
+               [("include_j2", ctypes.c_int32), ("include_drag", ctypes.c_int32),
+                ("disc_n_rho", ctypes.c_int32), ("disc_n_drho", ctypes.c_int32),
+                ("disc_r_mid", ctypes.c_double), ("disc_r_ihalf", ctypes.c_double),
+                ("disc_rho_cheb", ctypes.c_double * 32), ("disc_drho_cheb", ctypes.c_double * 32)]
+
+
+RHO_CHEB = 32
 
 
 class MpcController(ctypes.Structure):
@@ -171,11 +177,27 @@ def require_gpu():
 
 def make_params(const, include_J2=False, include_drag=False, c_d=2.5, rho_atm=9.983e-13, disc_drag=None):
     """Pack a reference-style Constants bag (constants.py:11-20) into the C struct.  disc_drag = (CD, rho): what the
-    discretizer's drag branch reads (const.CD, rho_func(r); linearize_discretize.py:162-168)."""
+    discretizer's drag branch reads (const.CD, rho_func(r); linearize_discretize.py:162-168); rho is a number (constant
+    density) or the dict discretizer.fit_density returns for a density that depends on |r|."""
     g = lambda n, d=0.0: float(getattr(const, n, d))
+    model = None
+    if disc_drag is not None and isinstance(disc_drag[1], dict):     # a fitted radial density (discretizer.fit_density)
+        model = disc_drag[1]
+        disc_drag = (disc_drag[0], float(model["rho_c"][0]))
     cd_a, rho_a = (0.0, 0.0) if disc_drag is None else (float(disc_drag[0]), float(disc_drag[1]))
-    return MpcParams(g("MU"), g("R_E"), g("J2"), g("G0"), g("ISP"), g("S"), g("R0", 1.0), g("RHO", 1.0),
-                     float(c_d), float(rho_atm), cd_a, rho_a, int(bool(include_J2)), int(bool(include_drag)))
+    p = MpcParams(g("MU"), g("R_E"), g("J2"), g("G0"), g("ISP"), g("S"), g("R0", 1.0), g("RHO", 1.0),
+                  float(c_d), float(rho_atm), cd_a, rho_a, int(bool(include_J2)), int(bool(include_drag)))
+    if model is not None:
+        rc, dc = list(model["rho_c"]), list(model["drho_c"])
+        if not (1 <= len(rc) <= RHO_CHEB and len(dc) <= RHO_CHEB):
+            raise ValueError(f"density model: 1..{RHO_CHEB} Chebyshev coefficients")
+        p.disc_n_rho, p.disc_n_drho = len(rc), len(dc)
+        p.disc_r_mid, p.disc_r_ihalf = float(model["r_mid"]), float(model["r_ihalf"])
+        for i, v in enumerate(rc):
+            p.disc_rho_cheb[i] = float(v)
+        for i, v in enumerate(dc):
+            p.disc_drho_cheb[i] = float(v)
+    return p
 
 
 # Page-locked buffers are expensive to create (cudaHostAlloc: ~0.1-1 ms plus ~0.2 ms per MiB) and the host API hands out

@@ -36,13 +36,33 @@ __device__ __constant__ double kDpA[6][5] = {{0, 0, 0, 0, 0},
                                              {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
 
 typedef DragEval AdStage;  // one evaluation of the unscaled dynamics and its linearization (v, gr, dragv: DRAG only)
+template <bool DRAG>
+struct AdStageSel {
+    typedef DragEval type;
+};
+template <>
+struct AdStageSel<true> {
+    typedef DragEvalW type;    // + the density gradient's term W (discretize_drag_kernel.cuh)
+};
+// entry (i, j) of d a / d r: G, plus W with drag (then not symmetric)
+template <bool DRAG, int I, int J, typename S>
+__device__ __forceinline__ double g_entry(const S &st)
+{
+    const double gs = (I == 0) ? (J == 0 ? st.g.xx : (J == 1 ? st.g.xy : st.g.xz))
+                               : ((I == 1) ? (J == 0 ? st.g.xy : (J == 1 ? st.g.yy : st.g.yz)) : (J == 0 ? st.g.xz : (J == 1 ? st.g.yz : st.g.zz)));
+    if constexpr (DRAG) return fma(st.gw[I], st.rh[J], gs);
+    else return gs;
+}
+#define MPC_G9(D, st)                                                                                                       \
+    g_entry<D, 0, 0>(st), g_entry<D, 0, 1>(st), g_entry<D, 0, 2>(st), g_entry<D, 1, 0>(st), g_entry<D, 1, 1>(st),            \
+        g_entry<D, 1, 2>(st), g_entry<D, 2, 0>(st), g_entry<D, 2, 1>(st), g_entry<D, 2, 2>(st)
 
 template <bool J2, bool GENU, bool DRAG>
-__device__ __forceinline__ int ad_eval(const DiscParams &P, double kf, double ka, const double (&x)[7], double s,
-                                       double tau, const UHold<GENU> &hold, AdStage &o)
+__device__ __forceinline__ int ad_eval(const DiscParams &P, double kf, const DragLin *L, const double (&x)[7], double s,
+                                       double tau, const UHold<GENU> &hold, typename AdStageSel<DRAG>::type &o)
 {
     hold.at(s, tau, o.ux, o.uy, o.uz);
-    if (DRAG) return drag_eval<J2>(P, kf, ka, x, o.ux, o.uy, o.uz, o);
+    if constexpr (DRAG) return drag_eval<J2>(P, kf, *L, x, o.ux, o.uy, o.uz, o);
     double ax, ay, az;
     gravity<J2>(P, x[0], x[1], x[2], ax, ay, az, o.g, o.gr);
     o.dragv[0] = o.dragv[1] = o.dragv[2] = 0.0;
@@ -136,6 +156,14 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                            int32_t *__restrict__ n_nodes, double kf = 0.0, double ka = 0.0)
 {
     constexpr int kStage = DRAG ? 15 : 9;
+    // (round-1 build, kept for A/B: constant density only -- the launcher refuses it for any other model)
+    DragLin L;
+    L.kc = ka;
+    L.r_mid = 0.0;
+    L.r_ihalf = 0.0;
+    L.n_rho = 1;
+    L.n_drho = 0;
+    L.rho_c[0] = 1.0;
     extern __shared__ double acc_smem[];
     const long long n_int = (long long)n_sats * (K - 1);
     const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
@@ -163,8 +191,8 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
     int bad = 0, fail = 0, nodes = 1;
     double t = t0;
 
-    AdStage st0;
-    bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x, 0.0, t0, hold, st0);
+    typename AdStageSel<DRAG>::type st0;
+    bad |= ad_eval<J2, GENU, DRAG>(P, kf, &L, x, 0.0, t0, hold, st0);
     // ---- select_initial_step (common.py); f = tf * k, y0 = [I, x] ------------------------------------------
     double h_abs;
     {
@@ -205,8 +233,8 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
         double x1[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) x1[i] = fma(hs0, st0.k[i], x[i]);
-        AdStage stA;
-        bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x1, h0 * ilen, t0 + h0, hold, stA);
+        typename AdStageSel<DRAG>::type stA;
+        bad |= ad_eval<J2, GENU, DRAG>(P, kf, &L, x1, h0 * ilen, t0 + h0, hold, stA);
         double d2sq = 0.0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
@@ -256,7 +284,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
         bool accepted = false, rejected = false;
         double t_new = t, h = 0.0;
         double xn[7];
-        AdStage st6;
+        typename AdStageSel<DRAG>::type st6;
         while (!accepted) {
             if (h_abs < min_step) {
                 fail = 1;
@@ -283,8 +311,8 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                     for (int l = 0; l < s; ++l) dy = fma(kx[l][i], kDpA[s][l], dy);
                     xs_[i] = fma(dy, hs, x[i]);
                 }
-                AdStage sg;
-                bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
+                typename AdStageSel<DRAG>::type sg;
+                bad |= ad_eval<J2, GENU, DRAG>(P, kf, &L, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
 #pragma unroll
                 for (int i = 0; i < 7; ++i) kx[s][i] = sg.k[i];
                 ad_store_stage<BLOCK, DRAG>(sm, s, sg);
@@ -298,7 +326,7 @@ discretize_adaptive_kernel(const double *__restrict__ x_in, const double *__rest
                 for (int l = 0; l < 6; ++l) dy = fma(kx[l][i], bw[l], dy);
                 xn[i] = fma(hs, dy, x[i]);
             }
-            bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xn, (t + h - t0) * ilen, t + h, hold, st6);
+            bad |= ad_eval<J2, GENU, DRAG>(P, kf, &L, xn, (t + h - t0) * ilen, t + h, hold, st6);
             ad_store_stage<BLOCK, DRAG>(sm, 6, st6);
             double esum = 0.0;
 #pragma unroll

@@ -30,7 +30,7 @@ namespace mpc {
 constexpr int kDfAcc = 48;                        // accumulators in shared memory: slots 0..47 of the kAccSlots layout; the 8
                                                   // of row 6 (slots 48..55) live in the output buffer (rows kDfRow6..)
 constexpr int kDfSlots = kDfAcc + 7 * 9;          // + G_s (6), d_s (3) of the 7 stages: 111 slots, 8 warps per SM
-constexpr int kDfSlotsDrag = kDfAcc + 7 * 15;     // + V_s (6): drag branch of the linearisation
+constexpr int kDfSlotsDrag = kDfAcc + 7 * 18;     // drag branch of the linearisation: G_s + W_s (9, not symmetric), d_s (3), V_s (6)
 constexpr int kDfPhiA = 0, kDfPhiB = 49;          // the two Phi row blocks inside the output buffer
 constexpr int kDfRow6 = 91;                       // rows 91..98: the row-6 accumulators until the epilogue
 constexpr int kDfEndU = 99;                       // rows 99..101: input of the far end node (ref_node_input), parked
@@ -54,25 +54,39 @@ __device__ __forceinline__ double inv_fifth_root(double x)
 
 // The stage linearisations are stored in the units of the step: hs^2 G_s, hs^2 d_s (and hs V_s), see the column loop.
 template <int BLOCK, bool DRAG>
-__device__ __forceinline__ void df_store_stage(volatile double *sm, int s, const AdStage &st, double hs, double hs2)
+__device__ __forceinline__ void df_store_stage(volatile double *sm, int s, const typename AdStageSel<DRAG>::type &st, double hs, double hs2)
 {
-    const int b = kDfAcc + s * (DRAG ? 15 : 9);
-    SM(b + 0) = hs2 * st.g.xx;
-    SM(b + 1) = hs2 * st.g.xy;
-    SM(b + 2) = hs2 * st.g.xz;
-    SM(b + 3) = hs2 * st.g.yy;
-    SM(b + 4) = hs2 * st.g.yz;
-    SM(b + 5) = hs2 * st.g.zz;
-    SM(b + 6) = hs2 * st.d[0];
-    SM(b + 7) = hs2 * st.d[1];
-    SM(b + 8) = hs2 * st.d[2];
-    if (DRAG) {
-        SM(b + 9) = hs * st.v.xx;
-        SM(b + 10) = hs * st.v.xy;
-        SM(b + 11) = hs * st.v.xz;
-        SM(b + 12) = hs * st.v.yy;
-        SM(b + 13) = hs * st.v.yz;
-        SM(b + 14) = hs * st.v.zz;
+    const int b = kDfAcc + s * (DRAG ? 18 : 9);
+    if constexpr (DRAG) {
+        // hs^2 (G + W), W = gw r_hat^T (the density gradient's term, discretize_drag_kernel.cuh), row-major; d; hs V
+        SM(b + 0) = hs2 * fma(st.gw[0], st.rh[0], st.g.xx);
+        SM(b + 1) = hs2 * fma(st.gw[0], st.rh[1], st.g.xy);
+        SM(b + 2) = hs2 * fma(st.gw[0], st.rh[2], st.g.xz);
+        SM(b + 3) = hs2 * fma(st.gw[1], st.rh[0], st.g.xy);
+        SM(b + 4) = hs2 * fma(st.gw[1], st.rh[1], st.g.yy);
+        SM(b + 5) = hs2 * fma(st.gw[1], st.rh[2], st.g.yz);
+        SM(b + 6) = hs2 * fma(st.gw[2], st.rh[0], st.g.xz);
+        SM(b + 7) = hs2 * fma(st.gw[2], st.rh[1], st.g.yz);
+        SM(b + 8) = hs2 * fma(st.gw[2], st.rh[2], st.g.zz);
+        SM(b + 9) = hs2 * st.d[0];
+        SM(b + 10) = hs2 * st.d[1];
+        SM(b + 11) = hs2 * st.d[2];
+        SM(b + 12) = hs * st.v.xx;
+        SM(b + 13) = hs * st.v.xy;
+        SM(b + 14) = hs * st.v.xz;
+        SM(b + 15) = hs * st.v.yy;
+        SM(b + 16) = hs * st.v.yz;
+        SM(b + 17) = hs * st.v.zz;
+    } else {
+        SM(b + 0) = hs2 * st.g.xx;
+        SM(b + 1) = hs2 * st.g.xy;
+        SM(b + 2) = hs2 * st.g.xz;
+        SM(b + 3) = hs2 * st.g.yy;
+        SM(b + 4) = hs2 * st.g.yz;
+        SM(b + 5) = hs2 * st.g.zz;
+        SM(b + 6) = hs2 * st.d[0];
+        SM(b + 7) = hs2 * st.d[1];
+        SM(b + 8) = hs2 * st.d[2];
     }
 }
 
@@ -81,9 +95,9 @@ __device__ __forceinline__ void
 discretize_default_body(const double *__restrict__ x_in, const double *__restrict__ u_in,
                         const double *__restrict__ tf_arr, const DiscParams &P, int n_sats, int K, int Ku, double rtol, double atol,
                         double max_step, const DstTab &dst, long long pitch, long long offset, int32_t *__restrict__ status,
-                        int32_t *__restrict__ n_nodes, double kf, double ka)
+                        int32_t *__restrict__ n_nodes, double kf, const DragLin *L)
 {
-    constexpr int kStage = DRAG ? 15 : 9;
+    constexpr int kStage = DRAG ? 18 : 9;
     extern __shared__ double acc_smem[];
     const long long n_int = (long long)n_sats * (K - 1);
     const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
@@ -123,8 +137,8 @@ discretize_default_body(const double *__restrict__ x_in, const double *__restric
 #pragma unroll
     for (int e = 0; e < 42; ++e) cur[(long long)e * pitch] = (e % 7 == 0 && e < 36) ? 1.0 : 0.0;
 
-    AdStage st0;
-    bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x, 0.0, t0, hold, st0);
+    typename AdStageSel<DRAG>::type st0;
+    bad |= ad_eval<J2, GENU, DRAG>(P, kf, L, x, 0.0, t0, hold, st0);
     // ---- select_initial_step (common.py); f = tf * k, y0 = [I, x] ----------------------------------------------
     double h_abs;
     {
@@ -141,7 +155,8 @@ discretize_default_body(const double *__restrict__ x_in, const double *__restric
             d0sq += (x[i] * r_) * (x[i] * r_);
             d1sq += (st0.k[i] * isc[i]) * (st0.k[i] * isc[i]);
         }
-        const double g[9] = {st0.g.xx, st0.g.xy, st0.g.xz, st0.g.xy, st0.g.yy, st0.g.yz, st0.g.xz, st0.g.yz, st0.g.zz};
+        // G (+ W = gw r_hat^T with drag: the density gradient's term, not symmetric)
+        const double g[9] = {MPC_G9(DRAG, st0)};
         double v0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, vA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (DRAG) {
             const double t_[9] = {st0.v.xx, st0.v.xy, st0.v.xz, st0.v.xy, st0.v.yy, st0.v.yz, st0.v.xz, st0.v.yz, st0.v.zz};
@@ -164,15 +179,15 @@ discretize_default_body(const double *__restrict__ x_in, const double *__restric
         double x1[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) x1[i] = fma(hs0, st0.k[i], x[i]);
-        AdStage stA;
-        bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, x1, h0 * ilen, t0 + h0, hold, stA);
+        typename AdStageSel<DRAG>::type stA;
+        bad |= ad_eval<J2, GENU, DRAG>(P, kf, L, x1, h0 * ilen, t0 + h0, hold, stA);
         double d2sq = 0.0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             const double df = (stA.k[i] - st0.k[i]) * isc[i];
             d2sq += df * df;
         }
-        const double g1[9] = {stA.g.xx, stA.g.xy, stA.g.xz, stA.g.xy, stA.g.yy, stA.g.yz, stA.g.xz, stA.g.yz, stA.g.zz};
+        const double g1[9] = {MPC_G9(DRAG, stA)};
         if (DRAG) {
             const double t_[9] = {stA.v.xx, stA.v.xy, stA.v.xz, stA.v.xy, stA.v.yy, stA.v.yz, stA.v.xz, stA.v.yz, stA.v.zz};
 #pragma unroll
@@ -212,7 +227,7 @@ discretize_default_body(const double *__restrict__ x_in, const double *__restric
         const bool last = !(t < t1);
         double half_next = 0.0, t_new = t;
         double xn[7];
-        AdStage st6;
+        typename AdStageSel<DRAG>::type st6;
         if (!last) {
             const double min_step = 10.0 * fabs(nextafter(t, CUDART_INF) - t);
             if (h_abs > max_step) h_abs = max_step;
@@ -244,8 +259,8 @@ discretize_default_body(const double *__restrict__ x_in, const double *__restric
                         for (int l = 0; l < s; ++l) dy = fma(kx[l][i], kDpA[s][l], dy);
                         xs_[i] = fma(dy, hs, x[i]);
                     }
-                    AdStage sg;
-                    bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
+                    typename AdStageSel<DRAG>::type sg;
+                    bad |= ad_eval<J2, GENU, DRAG>(P, kf, L, xs_, (t + cs[s] * h - t0) * ilen, t + cs[s] * h, hold, sg);
 #pragma unroll
                     for (int i = 0; i < 7; ++i) kx[s][i] = sg.k[i];
                     df_store_stage<BLOCK, DRAG>(sm, s, sg, hs, hs2);
@@ -259,7 +274,7 @@ discretize_default_body(const double *__restrict__ x_in, const double *__restric
                     for (int l = 0; l < 6; ++l) dy = fma(kx[l][i], bw[l], dy);
                     xn[i] = fma(hs, dy, x[i]);
                 }
-                bad |= ad_eval<J2, GENU, DRAG>(P, kf, ka, xn, (t + h - t0) * ilen, t + h, hold, st6);
+                bad |= ad_eval<J2, GENU, DRAG>(P, kf, L, xn, (t + h - t0) * ilen, t + h, hold, st6);
                 df_store_stage<BLOCK, DRAG>(sm, 6, st6, hs, hs2);
                 double esum = 0.0;
 #pragma unroll
@@ -322,23 +337,34 @@ discretize_default_body(const double *__restrict__ x_in, const double *__restric
                             }
                         }
                         const int b = kDfAcc + s * kStage;
-                        const double gxx = SM(b), gxy = SM(b + 1), gxz = SM(b + 2), gyy = SM(b + 3), gyz = SM(b + 4), gzz = SM(b + 5);
-                        // (d = -u/m^2 forces the mass column only: loaded for c == 6, a warp-uniform condition)
-                        double dx = 0.0, dy_ = 0.0, dz = 0.0;
-                        if (c == 6) {
-                            dx = SM(b + 6);
-                            dy_ = SM(b + 7);
-                            dz = SM(b + 8);
-                        }
-                        if (DRAG) {   // + (hs V) (hs q_v)
-                            const double vxx = SM(b + 9), vxy = SM(b + 10), vxz = SM(b + 11), vyy = SM(b + 12), vyz = SM(b + 13), vzz = SM(b + 14);
+                        if (DRAG) {
+                            // general (G + W): 9 entries, then d (mass column), then (hs V) (hs q_v)
+                            double dx = 0.0, dy_ = 0.0, dz = 0.0;
+                            if (c == 6) {
+                                dx = SM(b + 9);
+                                dy_ = SM(b + 10);
+                                dz = SM(b + 11);
+                            }
+                            const double vxx = SM(b + 12), vxy = SM(b + 13), vxz = SM(b + 14), vyy = SM(b + 15), vyz = SM(b + 16), vzz = SM(b + 17);
                             dx = fma(vxz, qv[2], fma(vxy, qv[1], fma(vxx, qv[0], dx)));
                             dy_ = fma(vyz, qv[2], fma(vyy, qv[1], fma(vxy, qv[0], dy_)));
                             dz = fma(vzz, qv[2], fma(vyz, qv[1], fma(vxz, qv[0], dz)));
+                            kk[s][0] = fma(SM(b + 2), qr[2], fma(SM(b + 1), qr[1], fma(SM(b + 0), qr[0], dx)));
+                            kk[s][1] = fma(SM(b + 5), qr[2], fma(SM(b + 4), qr[1], fma(SM(b + 3), qr[0], dy_)));
+                            kk[s][2] = fma(SM(b + 8), qr[2], fma(SM(b + 7), qr[1], fma(SM(b + 6), qr[0], dz)));
+                        } else {
+                            const double gxx = SM(b), gxy = SM(b + 1), gxz = SM(b + 2), gyy = SM(b + 3), gyz = SM(b + 4), gzz = SM(b + 5);
+                            // (d = -u/m^2 forces the mass column only: loaded for c == 6, a warp-uniform condition)
+                            double dx = 0.0, dy_ = 0.0, dz = 0.0;
+                            if (c == 6) {
+                                dx = SM(b + 6);
+                                dy_ = SM(b + 7);
+                                dz = SM(b + 8);
+                            }
+                            kk[s][0] = fma(gxz, qr[2], fma(gxy, qr[1], fma(gxx, qr[0], dx)));
+                            kk[s][1] = fma(gyz, qr[2], fma(gyy, qr[1], fma(gxy, qr[0], dy_)));
+                            kk[s][2] = fma(gzz, qr[2], fma(gyz, qr[1], fma(gxz, qr[0], dz)));
                         }
-                        kk[s][0] = fma(gxz, qr[2], fma(gxy, qr[1], fma(gxx, qr[0], dx)));
-                        kk[s][1] = fma(gyz, qr[2], fma(gyy, qr[1], fma(gxy, qr[0], dy_)));
-                        kk[s][2] = fma(gzz, qr[2], fma(gyz, qr[1], fma(gxz, qr[0], dz)));
                         if (s == 6) {      // (qr, qv / hs) is the new column: store, error estimate
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
@@ -430,6 +456,9 @@ discretize_default_body(const double *__restrict__ x_in, const double *__restric
 
 // (the body takes the parameter structs by reference: ptxas then reads them from the constant bank where they are used
 //  instead of copying them into registers at entry; 1.47 -> 1.44 ms on config 3, same box)
+// (DRAG is always false here and the two trailing parameters are unused: the drag branch has its own entry below.  They are
+//  kept because ptxas's register allocation of this 254-register kernel turned out to depend on the entry's signature --
+//  the same PTX body with two parameters fewer came out at 255 registers and 240 B more stack, 3-5 % slower on config 3.)
 template <bool J2, int BLOCK, bool GENU, bool DRAG>
 __global__ void __launch_bounds__(BLOCK)
 discretize_default_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in,
@@ -437,8 +466,21 @@ discretize_default_kernel(const double *__restrict__ x_in, const double *__restr
                           double max_step, DstTab dst, long long pitch, long long offset, int32_t *__restrict__ status,
                           int32_t *__restrict__ n_nodes, double kf = 0.0, double ka = 0.0)
 {
-    discretize_default_body<J2, BLOCK, GENU, DRAG>(x_in, u_in, tf_arr, P, n_sats, K, Ku, rtol, atol, max_step, dst, pitch, offset,
-                                                   status, n_nodes, kf, ka);
+    static_assert(!DRAG, "the drag branch is discretize_default_drag_kernel");
+    discretize_default_body<J2, BLOCK, GENU, false>(x_in, u_in, tf_arr, P, n_sats, K, Ku, rtol, atol, max_step, dst, pitch, offset,
+                                                    status, n_nodes, kf, nullptr);
+}
+
+// the drag branch of the linearisation (linearize_discretize.py:160-169): kf for the dynamics, L for the Jacobian
+template <bool J2, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+discretize_default_drag_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in,
+                               const double *__restrict__ tf_arr, DiscParams P, int n_sats, int K, double rtol, double atol,
+                               double max_step, DstTab dst, long long pitch, long long offset, int32_t *__restrict__ status,
+                               int32_t *__restrict__ n_nodes, double kf, const __grid_constant__ DragLin L)
+{
+    discretize_default_body<J2, BLOCK, false, true>(x_in, u_in, tf_arr, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, offset,
+                                                    status, n_nodes, kf, &L);
 }
 
 }  // namespace mpc

@@ -2,11 +2,14 @@
 //
 // Discretizer(include_drag=True) (linearize_discretize.py:160-169) is unreachable with the reference's defaults
 // (rho_func = None, Constants has no CD) but runs once the caller supplies const.CD, rho_func and drho_func.  This
-// kernel covers that case for a CONSTANT density (what Simulator.get_atmo_density returns, simulator.py:112; then
-// drho = 0 and Dr_aD vanishes):
+// kernel covers that case for a density that depends on |r| (constant -- what Simulator.get_atmo_density returns,
+// simulator.py:112 -- or any smooth radial model such as the power law / linear fits of simulator.py:110-111; the host
+// fits rho_func and drho_func with Chebyshev series over the radii of the batch, DragLin):
 //     f   = [v; a_g (+a_J2) + u/m - (kf/m) |v| v; mdot]                 kf = 1/2 C_D S rho_atm/RHO   (simulator.py:152)
-//     Dxf = [[0 I 0],[G, V, d],[0 0 0]],   V = -(ka/m)(|v| I + v v^T/|v|),  d = -u/m^2 + (ka/m^2)|v| v,
-//                                                                       ka = 1/2 const.CD S rho_func  (:166-168)
+//     Dxf = [[0 I 0],[G + W, V, d],[0 0 0]],   V = -(ka/m)(|v| I + v v^T/|v|),  d = -u/m^2 + (ka/m^2)|v| v,
+//                                              W = Dr_aD = -(kc drho/m) |v| v r_hat^T              (:166)
+//                                              ka = kc rho_func(r),  kc = 1/2 const.CD S           (:167-169)
+// (the DYNAMICS keep the simulator's constant density; only the Jacobian reads rho_func / drho_func, as in the reference)
 // The two structural shortcuts of discretize_kernel do not survive drag: the columns of Phi are no longer
 // second-order systems in position only (V multiplies the velocity part) and Phi6 is no longer symplectic.  So this
 // kernel is the plain formulation: classical RK4 on the first-order system in unscaled variables (step hs = tf h),
@@ -19,8 +22,31 @@
 
 namespace mpc {
 
-constexpr int kDragStageSlots = 15;                      // G (6) V (6) d (3)
+constexpr int kDragStageSlots = 18;                      // G + W (9, not symmetric) V (6) d (3)
 constexpr int kDragSlots = kAccSlots + 4 * kDragStageSlots;
+
+// rho_func(|r|) and drho_func(|r|) of the drag linearisation as Chebyshev series in t = (|r| - r_mid) r_ihalf on the
+// radii of the batch (fitted and verified on the host, discretizer.py; n_rho = 1, n_drho = 0: a constant density).
+constexpr int kRhoCheb = 32;
+struct DragLin {
+    double kc;                 // 1/2 const.CD S
+    double r_mid, r_ihalf;
+    int n_rho, n_drho;
+    double rho_c[kRhoCheb], drho_c[kRhoCheb];
+};
+
+__device__ __forceinline__ double cheb_eval(const double *c, int n, double t)
+{
+    // Clenshaw: sum_k c_k T_k(t)
+    double b1 = 0.0, b2 = 0.0;
+    const double t2 = 2.0 * t;
+    for (int k = n - 1; k >= 1; --k) {
+        const double b = fma(t2, b1, c[k]) - b2;
+        b2 = b1;
+        b1 = b;
+    }
+    return fma(t, b1, c[0]) - b2;
+}
 
 struct DragEval {
     double k[7];   // f / tf
@@ -30,9 +56,15 @@ struct DragEval {
     double ux, uy, uz;
 };
 
+// what the drag branch adds to it: W = Dr_aD = gw r_hat^T (zero for a constant density).  A separate type so that the
+// kernels without drag keep the layout (and the register allocation) they were tuned with.
+struct DragEvalW : DragEval {
+    double gw[3], rh[3];
+};
+
 template <bool J2>
-__device__ __forceinline__ int drag_eval(const DiscParams &P, double kf, double ka, const double (&x)[7], double ux,
-                                         double uy, double uz, DragEval &o)
+__device__ __forceinline__ int drag_eval(const DiscParams &P, double kf, const DragLin &L, const double (&x)[7], double ux,
+                                         double uy, double uz, DragEvalW &o)
 {
     double ax, ay, az;
     gravity<J2>(P, x[0], x[1], x[2], ax, ay, az, o.g, o.gr);
@@ -46,6 +78,15 @@ __device__ __forceinline__ int drag_eval(const DiscParams &P, double kf, double 
     o.un = uu * o.iun;
     const double vv = fma(x[3], x[3], fma(x[4], x[4], x[5] * x[5]));
     const double ivn = fast_rsqrt(vv), vn = vv * ivn;          // 1/|v|, |v|
+    // density of the linearisation at this radius
+    const double r2 = fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2]));
+    const double irn = fast_rsqrt(r2), rn = r2 * irn;
+    double ka = L.kc * L.rho_c[0], kw = 0.0;
+    if (L.n_rho > 1 || L.n_drho > 0) {
+        const double t = (rn - L.r_mid) * L.r_ihalf;
+        ka = L.kc * cheb_eval(L.rho_c, L.n_rho, t);
+        if (L.n_drho > 0) kw = L.kc * cheb_eval(L.drho_c, L.n_drho, t);
+    }
     const double cf = -kf * o.im * vn;                         // a_D = cf v
     o.k[0] = x[3];
     o.k[1] = x[4];
@@ -69,18 +110,29 @@ __device__ __forceinline__ int drag_eval(const DiscParams &P, double kf, double 
     o.d[0] = fma(o.dragv[0], o.im, -tx * o.im);
     o.d[1] = fma(o.dragv[1], o.im, -ty * o.im);
     o.d[2] = fma(o.dragv[2], o.im, -tz * o.im);
+    // W = -(kc drho / m) |v| v r_hat^T;  (G + W) r = G r + gw |r|
+    const double cw = -kw * o.im * vn;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        o.gw[a] = cw * x[3 + a];
+        o.rh[a] = x[a] * irn;
+        o.gr[a] = fma(o.gw[a], rn, o.gr[a]);
+    }
     return !(x[6] > 0.0);
 }
 
 #define ACC(e) acc[(e) * BLOCK]
 
 template <int BLOCK>
-__device__ __forceinline__ void drag_store_stage(volatile double *acc, int s, const DragEval &e)
+__device__ __forceinline__ void drag_store_stage(volatile double *acc, int s, const DragEvalW &e)
 {
     const int b = kAccSlots + s * kDragStageSlots;
-    ACC(b + 0) = e.g.xx; ACC(b + 1) = e.g.xy; ACC(b + 2) = e.g.xz; ACC(b + 3) = e.g.yy; ACC(b + 4) = e.g.yz; ACC(b + 5) = e.g.zz;
-    ACC(b + 6) = e.v.xx; ACC(b + 7) = e.v.xy; ACC(b + 8) = e.v.xz; ACC(b + 9) = e.v.yy; ACC(b + 10) = e.v.yz; ACC(b + 11) = e.v.zz;
-    ACC(b + 12) = e.d[0]; ACC(b + 13) = e.d[1]; ACC(b + 14) = e.d[2];
+    // G + W, row-major
+    ACC(b + 0) = fma(e.gw[0], e.rh[0], e.g.xx); ACC(b + 1) = fma(e.gw[0], e.rh[1], e.g.xy); ACC(b + 2) = fma(e.gw[0], e.rh[2], e.g.xz);
+    ACC(b + 3) = fma(e.gw[1], e.rh[0], e.g.xy); ACC(b + 4) = fma(e.gw[1], e.rh[1], e.g.yy); ACC(b + 5) = fma(e.gw[1], e.rh[2], e.g.yz);
+    ACC(b + 6) = fma(e.gw[2], e.rh[0], e.g.xz); ACC(b + 7) = fma(e.gw[2], e.rh[1], e.g.yz); ACC(b + 8) = fma(e.gw[2], e.rh[2], e.g.zz);
+    ACC(b + 9) = e.v.xx; ACC(b + 10) = e.v.xy; ACC(b + 11) = e.v.xz; ACC(b + 12) = e.v.yy; ACC(b + 13) = e.v.yz; ACC(b + 14) = e.v.zz;
+    ACC(b + 15) = e.d[0]; ACC(b + 16) = e.d[1]; ACC(b + 17) = e.d[2];
 }
 
 // derivative of one column y = (pr, pv) under stage s: (pv, G pr + V pv + d * mflag)
@@ -88,13 +140,14 @@ template <int BLOCK>
 __device__ __forceinline__ void drag_col_rhs(volatile double *acc, int s, const double (&y)[6], double mflag, double (&k)[6])
 {
     const int b = kAccSlots + s * kDragStageSlots;
-    const Sym3 g = {ACC(b + 0), ACC(b + 1), ACC(b + 2), ACC(b + 3), ACC(b + 4), ACC(b + 5)};
-    const Sym3 v = {ACC(b + 6), ACC(b + 7), ACC(b + 8), ACC(b + 9), ACC(b + 10), ACC(b + 11)};
+    const Sym3 v = {ACC(b + 9), ACC(b + 10), ACC(b + 11), ACC(b + 12), ACC(b + 13), ACC(b + 14)};
     k[0] = y[3];
     k[1] = y[4];
     k[2] = y[5];
-    double gx, gy, gz;
-    sym_mul_add(g, y[0], y[1], y[2], ACC(b + 12) * mflag, ACC(b + 13) * mflag, ACC(b + 14) * mflag, gx, gy, gz);
+    // (G + W) pr + d mflag
+    const double gx = fma(ACC(b + 2), y[2], fma(ACC(b + 1), y[1], fma(ACC(b + 0), y[0], ACC(b + 15) * mflag)));
+    const double gy = fma(ACC(b + 5), y[2], fma(ACC(b + 4), y[1], fma(ACC(b + 3), y[0], ACC(b + 16) * mflag)));
+    const double gz = fma(ACC(b + 8), y[2], fma(ACC(b + 7), y[1], fma(ACC(b + 6), y[0], ACC(b + 17) * mflag)));
     sym_mul_add(v, y[3], y[4], y[5], gx, gy, gz, k[3], k[4], k[5]);
 }
 
@@ -194,8 +247,8 @@ __device__ __forceinline__ void node_accumulate_general(volatile double *acc, co
 template <bool J2, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 discretize_drag_kernel(const double *__restrict__ x_in, const double *__restrict__ u_in, const double *__restrict__ tf_arr,
-                       DiscParams P, double kf, double ka, int n_sats, int K, int n_sub, DstTab dst, long long pitch,
-                       long long offset, int32_t *__restrict__ status)
+                       DiscParams P, double kf, const __grid_constant__ DragLin L, int n_sats, int K, int n_sub, DstTab dst,
+                       long long pitch, long long offset, int32_t *__restrict__ status)
 {
     extern __shared__ double acc_smem[];
     const long long n_int = (long long)n_sats * (K - 1);
@@ -253,8 +306,8 @@ discretize_drag_kernel(const double *__restrict__ x_in, const double *__restrict
         double ux, uy, uz;
         if (n == 0 || n == n_sub) ref_node_input(u_in + (long long)s * 3 * K, K, k + (n == n_sub), 1.0, ux, uy, uz);   // end nodes
         else hold.at((double)n * inv_n, 0.0, ux, uy, uz);
-        DragEval e1;
-        bad |= drag_eval<J2>(P, kf, ka, x, ux, uy, uz, e1);
+        DragEvalW e1;
+        bad |= drag_eval<J2>(P, kf, L, x, ux, uy, uz, e1);
         {
             const double w = wt ? wt[n] : ((n == 0 || n == n_sub) ? 0.5 : 1.0);
             node_accumulate_general<BLOCK>(acc, pr, pv, P, e1, x, w, w * ((double)n * inv_n));
@@ -266,27 +319,27 @@ discretize_drag_kernel(const double *__restrict__ x_in, const double *__restrict
         double umx, umy, umz, uex, uey, uez;
         hold.at(((double)n + 0.5) * inv_n, 0.0, umx, umy, umz);
         hold.at((double)(n + 1) * inv_n, 0.0, uex, uey, uez);
-        DragEval es;
+        DragEvalW es;
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             ksum[i] = e1.k[i];
             xt[i] = fma(hh, e1.k[i], x[i]);
         }
-        bad |= drag_eval<J2>(P, kf, ka, xt, umx, umy, umz, es);
+        bad |= drag_eval<J2>(P, kf, L, xt, umx, umy, umz, es);
         drag_store_stage<BLOCK>(acc, 1, es);
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             ksum[i] = fma(2.0, es.k[i], ksum[i]);
             xt[i] = fma(hh, es.k[i], x[i]);
         }
-        bad |= drag_eval<J2>(P, kf, ka, xt, umx, umy, umz, es);
+        bad |= drag_eval<J2>(P, kf, L, xt, umx, umy, umz, es);
         drag_store_stage<BLOCK>(acc, 2, es);
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             ksum[i] = fma(2.0, es.k[i], ksum[i]);
             xt[i] = fma(hs, es.k[i], x[i]);
         }
-        bad |= drag_eval<J2>(P, kf, ka, xt, uex, uey, uez, es);
+        bad |= drag_eval<J2>(P, kf, L, xt, uex, uey, uez, es);
         drag_store_stage<BLOCK>(acc, 3, es);
 #pragma unroll
         for (int i = 0; i < 7; ++i) x[i] = fma(h6, ksum[i] + es.k[i], x[i]);

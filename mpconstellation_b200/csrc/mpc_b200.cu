@@ -19,6 +19,7 @@
 #include "discretize_default_kernel.cuh"
 #include "propagate_kernel.cuh"
 #include "propagate_rk45_kernel.cuh"
+#include "mpc_b200_drag.h"
 #include "constraint_terms_kernel.cuh"
 #include "discretize_drag_kernel.cuh"
 #include "discretize_pair_kernel.cuh"
@@ -224,7 +225,8 @@ struct AdaptiveOpts {   // scipy solve_ivp(RK45) controls of the reference's def
     double rtol, atol, max_step;
     int32_t *n_nodes;
     int drag = 0;           // drag branch of the linearisation (set from mpc_params by with_drag)
-    double kf = 0.0, ka = 0.0;
+    double kf = 0.0;
+    mpc::DragLin lin{};     // density model of the Jacobian's drag terms
 };
 
 template <bool J2, bool GENU>
@@ -242,6 +244,44 @@ int launch_adaptive(const double *x, const double *u, const double *tf, const mp
 }
 
 std::atomic<int> g_default_v1{0};   // mpc_set_tuning(9): the round-1 build of the default-mode kernel (A/B measurements)
+
+// The kernels of the drag branch live in mpc_b200_drag.cu (see there for why); this is the call across.
+int launch_drag_unit(bool adaptive, int variant, int block, const double *x, const double *u, const double *tf,
+                     const mpc::DiscParams &P, bool j2, double kf, const mpc::DragLin &L, int n_sats, int K, int n_sub,
+                     double rtol, double atol, double max_step, const mpc::DstTab &dst, long long pitch, long long offset,
+                     int32_t *status, int32_t *n_nodes, cudaStream_t st, bool drag = true, int ucols = 0)
+{
+    if (mpc_drag_sizeof(0) != sizeof(mpc::DiscParams) || mpc_drag_sizeof(1) != sizeof(mpc::DstTab) ||
+        mpc_drag_sizeof(2) != sizeof(mpc::DragLin))
+        return fail(MPC_E_CUDA, "mpc_b200_drag.cu was built against different parameter structs");
+    MpcDragLaunch a{};
+    a.x = x;
+    a.u = u;
+    a.tf = tf;
+    a.disc_params = &P;
+    a.dst_tab = &dst;
+    a.drag_lin = &L;
+    a.kf = kf;
+    a.include_j2 = j2;
+    a.n_sats = n_sats;
+    a.K = K;
+    a.n_sub = n_sub;
+    a.variant = variant;
+    a.block = block;
+    a.drag = drag;
+    a.ucols = ucols;
+    a.rtol = rtol;
+    a.atol = atol;
+    a.max_step = max_step;
+    a.pitch = pitch;
+    a.offset = offset;
+    a.status = status;
+    a.n_nodes = n_nodes;
+    a.stream = st;
+    CUDA_TRY(adaptive ? mpc_drag_launch_adaptive(&a) : mpc_drag_launch_fixed(&a));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return MPC_SUCCESS;
+}
 
 template <typename Kern>
 int configure_smem(Kern kern, size_t smem, int &configured_dev)
@@ -263,18 +303,11 @@ int launch_adaptive_v1(const double *x, const double *u, const double *tf, const
                        cudaStream_t st)
 {
     constexpr int BLOCK = 32;
-    auto kern = mpc::discretize_adaptive_kernel<J2, BLOCK, 1, GENU, DRAG>;
-    const size_t smem = (size_t)(DRAG ? mpc::kAdSlotsDrag : mpc::kAdSlots) * BLOCK * sizeof(double);
-    static thread_local int configured_dev = -1;
-    int rc = configure_smem(kern, smem, configured_dev);
-    if (rc) return rc;
-    const long long n_int = (long long)n_sats * (K - 1);
-    const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, g_ucols, o.rtol, o.atol, o.max_step, dst, pitch, offset,
-                                    status, o.n_nodes, o.kf, o.ka);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CUDA_TRY(cudaGetLastError());
-    return MPC_SUCCESS;
+    if (DRAG && (o.lin.n_rho > 1 || o.lin.n_drho > 0))
+        return fail(MPC_E_UNSUPPORTED, "the round-1 default-mode kernel (mpc_set_tuning(9)) linearizes drag for a constant density only");
+    // (kept for A/B measurements only: compiled in mpc_b200_drag.cu with the other kernels off the default paths)
+    return launch_drag_unit(true, 1, BLOCK, x, u, tf, P, J2, o.kf, o.lin, n_sats, K, 0, o.rtol, o.atol, o.max_step, dst, pitch,
+                            offset, status, o.n_nodes, st, DRAG, GENU ? g_ucols : 0);
 }
 
 // shipped build (discretize_default_kernel): Phi ping-pongs through the output buffer, 30 KiB of shared memory per warp
@@ -285,18 +318,23 @@ int launch_default_b(const double *x, const double *u, const double *tf, const m
                      const AdaptiveOpts &o, const mpc::DstTab &dst, long long pitch, long long offset, int32_t *status,
                      cudaStream_t st)
 {
-    auto kern = mpc::discretize_default_kernel<J2, BLOCK, GENU, DRAG>;
-    const size_t smem = (size_t)(DRAG ? mpc::kDfSlotsDrag : mpc::kDfSlots) * BLOCK * sizeof(double);
-    static thread_local int configured_dev = -1;
-    int rc = configure_smem(kern, smem, configured_dev);
-    if (rc) return rc;
-    const long long n_int = (long long)n_sats * (K - 1);
-    const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, g_ucols, o.rtol, o.atol, o.max_step, dst, pitch, offset,
-                                    status, o.n_nodes, o.kf, o.ka);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CUDA_TRY(cudaGetLastError());
-    return MPC_SUCCESS;
+    if constexpr (DRAG) {
+        return launch_drag_unit(true, 0, BLOCK, x, u, tf, P, J2, o.kf, o.lin, n_sats, K, 0, o.rtol, o.atol, o.max_step, dst,
+                                pitch, offset, status, o.n_nodes, st);
+    } else {
+        const size_t smem = (size_t)mpc::kDfSlots * BLOCK * sizeof(double);
+        static thread_local int configured_dev = -1;
+        const long long n_int = (long long)n_sats * (K - 1);
+        const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
+        auto kern = mpc::discretize_default_kernel<J2, BLOCK, GENU, false>;
+        int rc = configure_smem(kern, smem, configured_dev);
+        if (rc) return rc;
+        kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, n_sats, K, g_ucols, o.rtol, o.atol, o.max_step, dst, pitch, offset,
+                                        status, o.n_nodes, 0.0, 0.0);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+        return MPC_SUCCESS;
+    }
 }
 
 template <bool J2, bool GENU, bool DRAG>
@@ -319,7 +357,7 @@ int launch_adaptive_k(const double *x, const double *u, const double *tf, const 
         if (block == 256) return launch_default_b<J2, GENU, DRAG, 256>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
         if (block == 128 && !GENU) return launch_default_b<J2, GENU, DRAG, 128>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
     } else if (block != 32) {
-        // the drag branch keeps V_s as well: 153 slots per thread, 5 warps fill the SM's shared memory
+        // the drag branch keeps V_s and a general G_s + W_s as well: 174 slots per thread, 5 warps fill the SM's shared memory
         return launch_default_b<J2, GENU, DRAG, 160>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
     }
     return launch_default_b<J2, GENU, DRAG, 32>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
@@ -337,11 +375,40 @@ int launch_adaptive_g(const double *x, const double *u, const double *tf, const 
     return launch_adaptive_k<J2, GENU, false>(x, u, tf, P, n_sats, K, o, dst, pitch, offset, status, st);
 }
 
+// The Jacobian's drag terms read const.CD and rho_func / drho_func (linearize_discretize.py:164-169): a constant
+// (disc_rho) or the Chebyshev series the host fitted over the radii of the batch (mpc_params::disc_*_cheb).
+mpc::DragLin drag_lin(const mpc_params *p)
+{
+    mpc::DragLin L{};
+    L.kc = p->include_drag ? 0.5 * p->disc_cd * p->s_area : 0.0;
+    L.n_rho = 1;
+    L.rho_c[0] = p->disc_rho;
+    if (p->include_drag && p->disc_n_rho > 0) {
+        L.r_mid = p->disc_r_mid;
+        L.r_ihalf = p->disc_r_ihalf;
+        L.n_rho = p->disc_n_rho;
+        L.n_drho = p->disc_n_drho;
+        for (int i = 0; i < mpc::kRhoCheb; ++i) {
+            L.rho_c[i] = i < p->disc_n_rho ? p->disc_rho_cheb[i] : 0.0;
+            L.drho_c[i] = i < p->disc_n_drho ? p->disc_drho_cheb[i] : 0.0;
+        }
+    }
+    return L;
+}
+
+int check_drag_model(const mpc_params *p)
+{
+    if (p->include_drag && (p->disc_n_rho < 0 || p->disc_n_rho > MPC_RHO_CHEB || p->disc_n_drho < 0 || p->disc_n_drho > MPC_RHO_CHEB ||
+                            (p->disc_n_drho > 0 && p->disc_n_rho == 0) || (p->disc_n_rho > 0 && !(p->disc_r_ihalf > 0.0))))
+        return fail(MPC_E_INVALID, "density model of the drag linearisation: need 0 <= disc_n_rho, disc_n_drho <= %d, disc_r_ihalf > 0", MPC_RHO_CHEB);
+    return MPC_SUCCESS;
+}
+
 void with_drag(AdaptiveOpts &o, const mpc_params *p)
 {
     o.drag = p->include_drag;
     o.kf = p->include_drag ? 0.5 * p->c_d * p->s_area * (p->rho_atm / p->rho) : 0.0;
-    o.ka = p->include_drag ? 0.5 * p->disc_cd * p->s_area * p->disc_rho : 0.0;
+    o.lin = drag_lin(p);
 }
 
 int check_adaptive(double rtol, double atol, double max_step)
@@ -360,37 +427,21 @@ int check_disc_args(const void *x, const void *u, const void *tf, const mpc_para
         // the reference's drag linearisation needs const.CD and a rho_func (linearize_discretize.py:162-169); with
         // its defaults (no CD attribute, rho_func = None) it raises; so do we when they are not supplied
         return fail(MPC_E_UNSUPPORTED, "include_drag needs disc_cd / disc_rho (const.CD, rho_func): the reference raises without them too");
-    return MPC_SUCCESS;
+    return check_drag_model(p);
 }
 
 // drag branch of the linearisation: coefficients of the dynamics (kf) and of the Jacobian (ka)
 double drag_kf(const mpc_params *p) { return 0.5 * p->c_d * p->s_area * (p->rho_atm / p->rho); }
-double drag_ka(const mpc_params *p) { return 0.5 * p->disc_cd * p->s_area * p->disc_rho; }
 
 template <bool J2>
-int launch_disc_drag(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, double kf, double ka,
+int launch_disc_drag(const double *x, const double *u, const double *tf, const mpc::DiscParams &P, double kf, const mpc::DragLin &L,
                      int n_sats, int K, int n_sub, const mpc::DstTab &dst, long long pitch, long long offset,
                      int32_t *status, cudaStream_t st)
 {
-    constexpr int BLOCK = 64;
-    auto kern = mpc::discretize_drag_kernel<J2, BLOCK>;
-    const size_t smem = (size_t)mpc::kDragSlots * BLOCK * sizeof(double);
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured_dev = dev;
-    }
-    const long long n_int = (long long)n_sats * (K - 1);
-    const unsigned grid = (unsigned)((n_int + BLOCK - 1) / BLOCK);
     mpc::DstTab tab = dst;
     tab.em = g_em.load(std::memory_order_relaxed);
-    kern<<<grid, BLOCK, smem, st>>>(x, u, tf, P, kf, ka, n_sats, K, n_sub, tab, pitch, offset, status);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CUDA_TRY(cudaGetLastError());
-    return MPC_SUCCESS;
+    return launch_drag_unit(false, 0, 64, x, u, tf, P, J2, kf, L, n_sats, K, n_sub, 0.0, 0.0, 0.0, tab, pitch, offset, status,
+                            nullptr, st);
 }
 
 // one chunk of a fixed-step discretization on stream st: plain or drag kernel
@@ -400,8 +451,9 @@ int launch_fixed(const double *x, const double *u, const double *tf, const mpc_p
 {
     if (p->include_drag) {
         if (g_ucols > 0) return fail(MPC_E_UNSUPPORTED, "include_drag with u on its own grid is not supported");
-        return p->include_j2 ? launch_disc_drag<true>(x, u, tf, P, drag_kf(p), drag_ka(p), n_sats, K, n_sub, tab, pitch, offset, status, st)
-                             : launch_disc_drag<false>(x, u, tf, P, drag_kf(p), drag_ka(p), n_sats, K, n_sub, tab, pitch, offset, status, st);
+        const mpc::DragLin L = drag_lin(p);
+        return p->include_j2 ? launch_disc_drag<true>(x, u, tf, P, drag_kf(p), L, n_sats, K, n_sub, tab, pitch, offset, status, st)
+                             : launch_disc_drag<false>(x, u, tf, P, drag_kf(p), L, n_sats, K, n_sub, tab, pitch, offset, status, st);
     }
     return p->include_j2 ? launch_disc_n<true, 1>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, st)
                          : launch_disc_n<false, 1>(x, u, tf, P, n_sats, K, n_sub, tab, pitch, offset, status, st);
@@ -1084,6 +1136,7 @@ int mpc_propagate_discretize_host(mpc_ctx *ctx, const double *y0, const double *
     if (n_sats < 0 || K < 2 || n_sub_prop < 0 || n_sub_disc < 1) return fail(MPC_E_INVALID, "need n_sats >= 0, T >= 2, n_sub_prop >= 0, n_sub_disc >= 1");
     if (p_disc->include_drag && !(p_disc->disc_cd > 0.0 && p_disc->disc_rho >= 0.0))
         return fail(MPC_E_UNSUPPORTED, "include_drag needs disc_cd / disc_rho (const.CD, rho_func): the reference raises without them too");
+    if (int rcm = check_drag_model(p_disc)) return rcm;
     int rc = check_ctrl(ctrl);
     if (rc) return rc;
     if (n_sats == 0) return MPC_SUCCESS;

@@ -9,6 +9,69 @@ from . import batch
 from .control import spec_from
 
 
+RHO_CHEB = 32          # coefficients per series (include/mpc_b200.h MPC_RHO_CHEB)
+
+
+def _cheb_fit(f, lo, hi, n=RHO_CHEB):
+    """Coefficients c_k of sum_k c_k T_k(t), t = (r - mid) / half, interpolating f at the n Chebyshev points of [lo, hi]."""
+    j = np.arange(n)
+    t = np.cos(np.pi * (j + 0.5) / n)
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    fv = np.array([float(f(mid + half * tj)) for tj in t])
+    c = np.array([2.0 / n * np.sum(fv * np.cos(np.pi * k * (j + 0.5) / n)) for k in range(n)])
+    c[0] *= 0.5
+    return c
+
+
+def _scalar(v):
+    """drho_func returns d rho / d|r| (the factor of r^T/|r| in linearize_discretize.py:166): one number"""
+    v = np.asarray(v, dtype=np.float64)
+    if v.size != 1:
+        raise NotImplementedError("drho_func must return the scalar d rho / d|r| (linearize_discretize.py:166)")
+    return float(v.reshape(-1)[0])
+
+
+def _cheb_val(c, t):
+    return np.polynomial.chebyshev.chebval(t, c)
+
+
+def fit_density(rho_func, drho_func, pos, tol=1e-9):
+    """What the device needs of rho_func / drho_func (linearize_discretize.py:164-165) for a batch whose normalized
+    positions are pos [M,3]: the float rho when the density is constant along the batch and its gradient zero, else
+    {"r_mid", "r_ihalf", "rho_c", "drho_c"}: Chebyshev series in t = (|r| - r_mid) r_ihalf over the radii of the batch
+    (padded by 2 %: the integrator's stages leave the sampled radii by O(h^2)), each fitted along one direction and then
+    CHECKED against the callables at the batch's own positions (all directions): agreement to tol of the largest value,
+    or NotImplementedError -- the density depends on more than |r|, or is not smooth enough for 32 terms."""
+    pos = np.asarray(pos, dtype=np.float64).reshape(-1, 3)
+    if pos.shape[0] == 0:
+        return 0.0
+    if pos.shape[0] > 256:
+        pos = pos[np.linspace(0, pos.shape[0] - 1, 256).astype(int)]
+    rho = np.array([float(rho_func(r)) for r in pos])
+    drho = np.array([_scalar(drho_func(r)) for r in pos])
+    if np.ptp(rho) == 0.0 and not np.any(drho != 0.0):
+        return float(rho[0])
+    if not (np.all(np.isfinite(rho)) and np.all(np.isfinite(drho))):
+        raise NotImplementedError("rho_func / drho_func return non-finite values on this batch")
+    rad = np.linalg.norm(pos, axis=1)
+    lo, hi = float(rad.min()), float(rad.max())
+    pad = 0.02 * (hi - lo) + 1e-9 * hi
+    lo, hi = lo - pad, hi + pad
+    e = pos[0] / rad[0]
+    rho_c = _cheb_fit(lambda r: rho_func(r * e), lo, hi)
+    drho_c = _cheb_fit(lambda r: _scalar(drho_func(r * e)), lo, hi) if np.any(drho != 0.0) else np.zeros(0)
+    mid, ihalf = 0.5 * (lo + hi), 2.0 / (hi - lo)
+    t = (rad - mid) * ihalf
+    err_r = np.max(np.abs(_cheb_val(rho_c, t) - rho)) / max(np.max(np.abs(rho)), 1e-300)
+    err_d = 0.0 if drho_c.size == 0 else np.max(np.abs(_cheb_val(drho_c, t) - drho)) / max(np.max(np.abs(drho)), 1e-300)
+    if not (err_r <= tol and err_d <= tol):
+        raise NotImplementedError(
+            "the GPU discretizer linearizes drag for a density that is a smooth function of |r| over the batch "
+            f"(rho_func / drho_func differ from their radial Chebyshev fit by {err_r:.1e} / {err_d:.1e}); "
+            "there is no CPU fallback")
+    return {"r_mid": mid, "r_ihalf": ihalf, "rho_c": rho_c, "drho_c": drho_c}
+
+
 class Discretizer:
     def __init__(self, const, rho_func=None, drho_func=None, include_drag=False, include_J2=False,
                  use_scipy_ZOH=False):
@@ -55,20 +118,14 @@ class Discretizer:
 
     def _disc_drag(self, x):
         """(CD, rho) for the device, or None.  The drag branch (linearize_discretize.py:160-169) calls rho_func(r) and
-        drho_func(r) at every state; the kernels implement a CONSTANT density (what Simulator.get_atmo_density
-        returns, simulator.py:112), so both callables are sampled on the reference trajectory and anything else is
-        rejected loudly -- there is no CPU fallback."""
+        drho_func(r) at every state.  The kernels take the density as a function of |r|: a constant (what
+        Simulator.get_atmo_density returns, simulator.py:112) or a smooth radial model such as the fits of
+        simulator.py:110-111, handed over as Chebyshev series (fit_density).  Anything else -- a density that depends on the
+        direction of r, or one the series cannot follow -- is rejected loudly: there is no CPU fallback."""
         if not self.include_drag:
             return None
         pos = np.moveaxis(x[:, 0:3, :], 1, 2).reshape(-1, 3)
-        if pos.shape[0] > 64:
-            pos = pos[np.linspace(0, pos.shape[0] - 1, 64).astype(int)]
-        rho = np.array([float(self.rho_func(r)) for r in pos])
-        drho = np.array([float(np.max(np.abs(self.drho_func(r)))) for r in pos])
-        if rho.size and (np.ptp(rho) != 0.0 or np.any(drho != 0.0)):
-            raise NotImplementedError("the GPU discretizer linearizes drag for a constant density only "
-                                      "(rho_func constant, drho_func zero along the trajectory)")
-        return float(self.const.CD), float(rho[0]) if rho.size else 0.0
+        return float(self.const.CD), fit_density(self.rho_func, self.drho_func, pos)
 
     # -- the reference entry point -------------------------------------------------------------------
     def discretize(self, f, x, u, tf):

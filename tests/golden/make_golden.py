@@ -46,11 +46,24 @@ def disc(const, x, u, tf, uniform, J2=False, steps=101, ks=None):
             np.column_stack([r[3] for r in res]), np.column_stack([r[4] for r in res]))
 
 
-def disc_drag(const, x, u, tf, uniform, rho_n, J2=False, ks=None):
+def power_law_density(a, b, r0_m, r_e_m, rho_scale):
+    """rho_func / drho_func for the drag linearisation from the power law the reference's authors tried for 400-600 km
+    (simulator.py:110: `8E26 * altitude**-6.828`): density over rho_scale as a function of the NORMALIZED position, and
+    its derivative with respect to the normalized radius (what linearize_discretize.py:166 multiplies r^T/|r| by)."""
+    def rho(r):
+        return a * (np.linalg.norm(r) * r0_m - r_e_m) ** b / rho_scale
+
+    def drho(r):
+        return a * b * (np.linalg.norm(r) * r0_m - r_e_m) ** (b - 1.0) * r0_m / rho_scale
+    return rho, drho
+
+
+def disc_drag(const, x, u, tf, uniform, rho_n, J2=False, ks=None, funcs_rho=None):
     """Discretizer with the drag branch enabled (linearize_discretize.py:160-169).  The shipped reference cannot
     reach it with its defaults (rho_func=None, Constants has no CD) but runs it once the caller supplies what the
     branch reads: const.CD, rho_func, drho_func.  Constant density, as Simulator.get_atmo_density (simulator.py:112)."""
-    d = R.Discretizer(const, rho_func=lambda r: rho_n, drho_func=lambda r: 0.0, include_drag=True, include_J2=J2)
+    rho_f, drho_f = funcs_rho if funcs_rho is not None else ((lambda r: rho_n), (lambda r: 0.0))
+    d = R.Discretizer(const, rho_func=rho_f, drho_func=drho_f, include_drag=True, include_J2=J2)
     d.use_uniform_steps = uniform
     K = x.shape[1]
     d._Discretizer__tau = np.linspace(0, 1, K)
@@ -97,6 +110,44 @@ def drag_fixtures():
         g.update(pack(f"{tag}_def", disc_drag(const, x, u, 1.0, False, rho_n, J2=J2, ks=ks)))
     np.savez(os.path.join(HERE, "discretize_drag.npz"), **g)
     print("discretize_drag.npz", os.path.getsize(os.path.join(HERE, "discretize_drag.npz")) // 1024, "KiB")
+
+
+def drag_radial_fixtures():
+    """tests/golden/discretize_drag_radial.npz: the g1 scenario of drag_fixtures (S x 1e4, J2, trajectory flown with drag)
+    discretized with an ALTITUDE-DEPENDENT density in the drag branch of the linearisation: rho_func = the power law of
+    simulator.py:110, drho_func = its derivative -- so that Dr_aD (linearize_discretize.py:166) is not zero.  The
+    dynamics keep the simulator's constant density, as in the reference (f is Simulator.satellite_dynamics)."""
+    import constants as ref_constants
+    sat = R.Satellite(R_INIT, V_INIT, M_INIT)
+    scale = R.SatelliteScale(sat=sat)
+    c = R.ConstantTangentialThrustController([sat], 0.5)
+    const = scale.get_normalized_constants()
+    const.S = const.S * 1e4
+    const.CD = ref_constants.C_D
+    a, b = 8e26, -6.828
+    r0_m, r_e_m = float(const.R0), float(ref_constants.R_EARTH)
+    funcs_rho = power_law_density(a, b, r0_m, r_e_m, float(const.RHO))
+    sim = R.Simulator(sats=[R.Satellite(R_INIT, V_INIT, M_INIT)], controller=c, scale=scale, base_res=40,
+                      include_drag=True, include_J2=True)
+    scale_mod = type("ScaleWithS", (), {"get_normalized_constants": lambda self: const,
+                                        "normalize_state": scale.normalize_state, "redim_state": scale.redim_state})()
+    sim.scale = scale_mod
+    sim.run(tf=1)
+    sid = sim.sats[0].id
+    x, t = sim.sim_data[sid], sim.sim_time[sid]
+    u = R.Discretizer.extract_uk(x, t, c)
+    ks = list(range(0, x.shape[1] - 1, 3))
+    g = {"x": x, "u": u, "tf": 1.0, "ks": np.array(ks), "const": const_vec(const), "cd": const.CD, "j2": 1,
+         "law": np.array([a, b, r0_m, r_e_m, float(const.RHO)]),
+         "rho_at_x0": funcs_rho[0](x[0:3, 0]), "drho_at_x0": funcs_rho[1](x[0:3, 0])}
+    g.update(pack("uni", disc_drag(const, x, u, 1.0, True, None, J2=True, ks=ks, funcs_rho=funcs_rho)))
+    g.update(pack("def", disc_drag(const, x, u, 1.0, False, None, J2=True, ks=ks, funcs_rho=funcs_rho)))
+    # the same with drho_func = 0 (what a caller gets who passes the density but forgets its gradient): pins that the
+    # gradient term is what differs
+    g.update(pack("def_nograd", disc_drag(const, x, u, 1.0, False, None, J2=True, ks=ks,
+                                          funcs_rho=(funcs_rho[0], lambda r: 0.0))))
+    np.savez(os.path.join(HERE, "discretize_drag_radial.npz"), **g)
+    print("discretize_drag_radial.npz", os.path.getsize(os.path.join(HERE, "discretize_drag_radial.npz")) // 1024, "KiB")
 
 
 def bench_fixtures():
@@ -371,6 +422,8 @@ elif __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "many":
     many_fixtures()
 elif __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "drag":
     drag_fixtures()
+elif __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "drag_radial":
+    drag_radial_fixtures()
 elif __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bench":
     bench_fixtures()
 elif __name__ == "__main__":

@@ -182,7 +182,8 @@ def propagate_rk45(y0, tf, const, kind=0, thrust=(0.0, 0.0, 0.0), table=None, en
 
 def discretize_drag(x, u, tf, const, drag, include_J2=False, n_sub=100, adaptive=None, c_d=2.5, rho_atm=9.983e-13, em=True):
     """The drag kernels (discretize_drag_kernel / the DRAG variant of the adaptive kernel); drag = (const.CD, rho_func
-    value), as mpconstellation_b200.discretize_batch(disc_drag=...)."""
+    value) or (const.CD, density model: the dict Discretizer fits for a radial rho_func / drho_func), as
+    mpconstellation_b200.discretize_batch(disc_drag=...)."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
     N, _, K = x.shape
@@ -193,13 +194,22 @@ def discretize_drag(x, u, tf, const, drag, include_J2=False, n_sub=100, adaptive
     nodes = np.zeros(n_int, dtype=np.int32)
     c8 = _const8(const)
     kf = 0.5 * c_d * const.S * (rho_atm / const.RHO)
-    ka = 0.5 * drag[0] * const.S * drag[1]
+    model = None
+    if isinstance(drag[1], dict):
+        m = drag[1]
+        ka = 0.5 * drag[0] * const.S
+        model = np.zeros(4 + 64)
+        model[0:4] = m["r_mid"], m["r_ihalf"], len(m["rho_c"]), len(m["drho_c"])
+        model[4:4 + len(m["rho_c"])] = m["rho_c"]
+        model[36:36 + len(m["drho_c"])] = m["drho_c"]
+    else:
+        ka = 0.5 * drag[0] * const.S * drag[1]
     ad = adaptive if adaptive is not None else {}
     D = ctypes.c_double
     lib().hostk_discretize_drag(_p(x), _p(u), _p(tfv), _p(c8), int(include_J2), D(kf), D(ka), N, K, int(n_sub),
                                 int(adaptive is not None), D(ad.get("rtol", 1e-3)), D(ad.get("atol", 1e-6)),
                                 D(ad.get("max_step", 1e-2)), _p(out), ctypes.c_longlong(n_int), _p(status), _p(nodes),
-                                int(bool(em)))
+                                int(bool(em)), _p(model) if model is not None else None)
     return out, status, nodes
 
 

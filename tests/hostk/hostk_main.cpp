@@ -219,25 +219,41 @@ extern "C" int hostk_propagate_rk45(const double *y0, const double *tf, const do
     return 0;
 }
 
-// drag branch of the linearisation: kf = 0.5 C_D S (rho_atm / RHO) (dynamics), ka = 0.5 const.CD S rho_func (Jacobian)
+// drag branch of the linearisation: kf = 0.5 C_D S (rho_atm / RHO) (dynamics), ka = 0.5 const.CD S rho_func (Jacobian).
+// model == nullptr: constant density (ka as given); else [r_mid, r_ihalf, n_rho, n_drho, rho_c[32], drho_c[32]] and
+// ka = 0.5 const.CD S (the density comes from the series)
 extern "C" int hostk_discretize_drag(const double *x, const double *u, const double *tf, const double *const8,
                                      int include_j2, double kf, double ka, int n_sats, int K, int n_sub, int adaptive,
                                      double rtol, double atol, double max_step, double *out, long long pitch,
-                                     int32_t *status, int32_t *n_nodes, int em)
+                                     int32_t *status, int32_t *n_nodes, int em, const double *model)
 {
     const mpc::DiscParams P = disc_params(const8, include_j2);
+    mpc::DragLin L{};
+    L.kc = ka;
+    L.n_rho = 1;
+    L.rho_c[0] = 1.0;
+    if (model) {
+        L.r_mid = model[0];
+        L.r_ihalf = model[1];
+        L.n_rho = (int)model[2];
+        L.n_drho = (int)model[3];
+        for (int i = 0; i < mpc::kRhoCheb; ++i) {
+            L.rho_c[i] = model[4 + i];
+            L.drho_c[i] = model[4 + mpc::kRhoCheb + i];
+        }
+    }
     mpc::DstTab dst{};
     dst.p[0] = out;
     dst.em = em;
     run_grid((long long)n_sats * (K - 1), [&] {
         if (adaptive) {
             if (include_j2)
-                mpc::discretize_default_kernel<true, kBlock, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, ka);
+                mpc::discretize_default_drag_kernel<true, kBlock>(x, u, tf, P, n_sats, K, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, L);
             else
-                mpc::discretize_default_kernel<false, kBlock, false, true>(x, u, tf, P, n_sats, K, 0, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, ka);
+                mpc::discretize_default_drag_kernel<false, kBlock>(x, u, tf, P, n_sats, K, rtol, atol, max_step, dst, pitch, 0, status, n_nodes, kf, L);
         } else {
-            if (include_j2) mpc::discretize_drag_kernel<true, kBlock>(x, u, tf, P, kf, ka, n_sats, K, n_sub, dst, pitch, 0, status);
-            else mpc::discretize_drag_kernel<false, kBlock>(x, u, tf, P, kf, ka, n_sats, K, n_sub, dst, pitch, 0, status);
+            if (include_j2) mpc::discretize_drag_kernel<true, kBlock>(x, u, tf, P, kf, L, n_sats, K, n_sub, dst, pitch, 0, status);
+            else mpc::discretize_drag_kernel<false, kBlock>(x, u, tf, P, kf, L, n_sats, K, n_sub, dst, pitch, 0, status);
         }
     });
     return 0;

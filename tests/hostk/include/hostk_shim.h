@@ -21,6 +21,7 @@
 #define __maxnreg__(...)
 #define __shared__
 #define __constant__
+#define __grid_constant__
 #define CUDART_INF (__builtin_inf())
 
 struct hostk_dim3 {

@@ -53,6 +53,40 @@ def test_drag_discretizer_matches_reference_fixtures(M, tag, uniform):
         assert rel_err(A0[ks], g["g1_uni_A_k"]) > 1e-5
 
 
+@pytest.mark.parametrize("uniform", [True, False])
+def test_drag_discretizer_with_altitude_dependent_density_matches_the_reference(M, uniform):
+    """Discretizer(rho_func = the power law of simulator.py:110, drho_func = its derivative): Dr_aD
+    (linearize_discretize.py:166) is not zero, G + Dr_aD not symmetric.  Through the reference's own signature; the host
+    hands the two callables over as Chebyshev series (discretizer.fit_density).  Fixture from the unmodified reference
+    (make_golden.py drag_radial: radii 1.0 ... 1.2, the density falls by four orders of magnitude along the trajectory)."""
+    g = np.load(os.path.join(GOLDEN, "discretize_drag_radial.npz"))
+    const, _ = _const_with_cd(g["const"], float(g["cd"]))
+    a, b, r0_m, r_e_m, rho_scale = [float(v) for v in g["law"]]
+    rho = lambda r: a * (np.linalg.norm(r) * r0_m - r_e_m) ** b / rho_scale
+    drho = lambda r: a * b * (np.linalg.norm(r) * r0_m - r_e_m) ** (b - 1.0) * r0_m / rho_scale
+    ks = g["ks"]
+    mode = "uni" if uniform else "def"
+    for tag, dfun in ((mode, drho), ("def_nograd", lambda r: 0.0)):
+        if tag == "def_nograd" and uniform:
+            continue
+        d = M.Discretizer(const, rho_func=rho, drho_func=dfun, include_drag=True, include_J2=True)
+        d.use_uniform_steps = uniform
+        out = d.discretize(M.Simulator.satellite_dynamics, g["x"], g["u"], float(g["tf"]))
+        for nm, o in zip(NAMES, out):
+            ref = g[f"{tag}_{nm}"]
+            got = o[ks] if o.ndim == 3 else o[:, ks]
+            assert rel_err(got, ref) < TOL_REF, (tag, nm, rel_err(got, ref))
+    assert rel_err(g["def_A_k"], g["def_nograd_A_k"]) > 1e-3          # the gradient term is what is being tested
+    # a batch: the same satellite three times with the model fitted over all of them == the single call
+    if not uniform:
+        x3, u3 = np.repeat(g["x"][None], 3, axis=0), np.repeat(g["u"][None], 3, axis=0)
+        res = d.discretize_batch(M.Simulator.satellite_dynamics, x3, u3, float(g["tf"]))
+        assert res.status.max() == 0
+        s0, s2 = res.sat(0), res.sat(2)
+        for o0, o2 in zip(s0, s2):
+            assert np.array_equal(o0, o2)
+
+
 @pytest.mark.parametrize("j2", [False, True])
 def test_drag_batch_matches_c_oracle(M, const, j2):
     """37 satellites x K=13 (ragged against the 64-thread CTAs), exaggerated drag, per-satellite tf; both modes"""

@@ -32,7 +32,9 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.MpcParams) == 12 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.MpcParams) == 12 * 8 + 4 * 4 + 2 * 8 + 2 * 32 * 8
+    assert (_lib.MpcParams.disc_n_rho.offset, _lib.MpcParams.disc_r_mid.offset, _lib.MpcParams.disc_rho_cheb.offset,
+            _lib.MpcParams.disc_drho_cheb.offset) == (104, 112, 128, 384)
     assert ctypes.sizeof(_lib.MpcController) == 4 * 4 + 3 * 8 + 8 + 8 + 8
     assert _lib.MpcController.table.offset == 48
     assert ctypes.sizeof(_lib.MpcGatherOpts) == 4 * 4 + 2 * 8 and _lib.MpcGatherOpts.n_sats_total.offset == 16
@@ -178,6 +180,35 @@ def test_run_segment_serves_replanning_controllers_in_the_reference_order(monkey
     assert [c[0] for c in calls] == [3, 3] and sim.sim_data[sats[0].id].shape == (7, 20)
 
 
+def test_fit_density_of_the_drag_linearisation():
+    """rho_func / drho_func (linearize_discretize.py:164-165) as the device takes them: a number when the density is
+    constant along the batch, else Chebyshev series over the batch's radii, checked at the batch's own positions"""
+    from mpconstellation_b200.discretizer import fit_density, _cheb_val
+    rng = np.random.default_rng(5)
+    d = rng.normal(size=(200, 3))
+    pos = d / np.linalg.norm(d, axis=1)[:, None] * rng.uniform(1.0, 1.2, size=(200, 1))
+    assert fit_density(lambda r: 4.0e4, lambda r: 0.0, pos) == 4.0e4
+    a, b, r0, re_, sc = 8e26, -6.828, 6.9e6, 6.371e6, 3.7e-17          # the power law of simulator.py:110
+    rho = lambda r: a * (np.linalg.norm(r) * r0 - re_) ** b / sc
+    drho = lambda r: a * b * (np.linalg.norm(r) * r0 - re_) ** (b - 1) * r0 / sc
+    m = fit_density(rho, drho, pos)
+    rad = np.linalg.norm(pos, axis=1)
+    t = (rad - m["r_mid"]) * m["r_ihalf"]
+    assert np.all(np.abs(t) <= 1.0) and len(m["rho_c"]) == 32 and len(m["drho_c"]) == 32
+    rr = np.array([rho(p) for p in pos])
+    dd = np.array([drho(p) for p in pos])
+    # the density falls by 3.5 orders of magnitude across these radii: 1e-10 of the largest value, 1e-6 of the local one
+    assert np.max(np.abs(_cheb_val(m["rho_c"], t) - rr)) < 1e-10 * rr.max() and np.max(np.abs(_cheb_val(m["rho_c"], t) - rr) / rr) < 1e-6
+    assert np.max(np.abs(_cheb_val(m["drho_c"], t) - dd)) < 1e-10 * np.abs(dd).max()
+    m0 = fit_density(rho, lambda r: 0.0, pos)
+    assert len(m0["drho_c"]) == 0 and np.array_equal(m0["rho_c"], m["rho_c"])
+    with pytest.raises(NotImplementedError, match="smooth function of"):       # a kink inside the batch's radii
+        fit_density(lambda r: abs(np.linalg.norm(r) - 1.1), lambda r: 0.0, pos)
+    p = M._lib.make_params(M.SatelliteScale().get_normalized_constants(), include_drag=True, disc_drag=(2.5, m))
+    assert (p.disc_n_rho, p.disc_n_drho) == (32, 32) and p.disc_rho_cheb[3] == m["rho_c"][3] and p.disc_cd == 2.5
+    assert p.disc_r_ihalf == m["r_ihalf"] and p.disc_rho == m["rho_c"][0]
+
+
 def test_discretizer_option_errors_mirror_reference():
     const = M.SatelliteScale().get_normalized_constants()
     f = M.Simulator.satellite_dynamics
@@ -191,9 +222,14 @@ def test_discretizer_option_errors_mirror_reference():
         d.discretize(f, x, u, 1.0)
     const_cd = M.SatelliteScale().get_normalized_constants()
     const_cd.CD = 2.5
-    d = M.Discretizer(const_cd, rho_func=lambda r: float(np.linalg.norm(r)), drho_func=lambda r: 0.0, include_drag=True)
-    xv = np.ones((7, 3)) * np.array([1.0, 2.0, 3.0])
-    with pytest.raises(NotImplementedError, match="constant density"):      # a density profile cannot run on the device
+    # a density that depends on the DIRECTION of r has no device form (the kernels take rho(|r|), drho(|r|))
+    d = M.Discretizer(const_cd, rho_func=lambda r: float(r[0]), drho_func=lambda r: 0.0, include_drag=True)
+    xv = np.ones((7, 3))
+    xv[0:3] = np.eye(3)
+    with pytest.raises(NotImplementedError, match="smooth function of"):
+        d.discretize(f, xv, u, 1.0)
+    d = M.Discretizer(const_cd, rho_func=lambda r: 1.0, drho_func=lambda r: np.ones(3), include_drag=True)
+    with pytest.raises(NotImplementedError, match="scalar"):                # drho_func is d rho / d|r|
         d.discretize(f, xv, u, 1.0)
     d = M.Discretizer(const)
     with pytest.raises(NotImplementedError):

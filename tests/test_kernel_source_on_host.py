@@ -392,6 +392,50 @@ def test_drag_kernels_match_reference_fixtures(tag, uniform):
         assert rel_err(_sel(o[0], ks), g[f"{tag}_{mode}_{n}"]) < TOL_REF, (tag, mode, n)
 
 
+def _power_law(law):
+    """rho_func / drho_func of the radial fixture (tests/golden/make_golden.py: power_law_density, simulator.py:110)"""
+    a, b, r0_m, r_e_m, rho_scale = [float(v) for v in law]
+
+    def rho(r):
+        return a * (np.linalg.norm(r) * r0_m - r_e_m) ** b / rho_scale
+
+    def drho(r):
+        return a * b * (np.linalg.norm(r) * r0_m - r_e_m) ** (b - 1.0) * r0_m / rho_scale
+    return rho, drho
+
+
+@pytest.mark.parametrize("uniform", [True, False])
+def test_drag_kernels_with_altitude_dependent_density_match_the_reference(uniform):
+    """rho_func = the power law of simulator.py:110, drho_func = its derivative: the reference's Dr_aD
+    (linearize_discretize.py:166) is then not zero and G + Dr_aD is not symmetric.  The host fits both callables with
+    Chebyshev series over the radii of the batch (mpconstellation_b200.discretizer.fit_density) and the kernels evaluate
+    them at every stage; fixture from the unmodified reference (make_golden.py drag_radial; radii 1.0 ... 1.2, density
+    falling by four orders of magnitude along the trajectory)."""
+    from mpconstellation_b200.discretizer import fit_density
+    g = np.load(os.path.join(GOLDEN, "discretize_drag_radial.npz"))
+    cst = _oracle_const(g["const"])
+    rho, drho = _power_law(g["law"])
+    assert rho(g["x"][0:3, 0]) == float(g["rho_at_x0"]) and drho(g["x"][0:3, 0]) == float(g["drho_at_x0"])
+    x, u, tf, ks = g["x"][None], g["u"][None], float(g["tf"]), g["ks"]
+    model = fit_density(rho, drho, np.moveaxis(x[:, 0:3, :], 1, 2).reshape(-1, 3))
+    assert isinstance(model, dict) and len(model["rho_c"]) == 32 and len(model["drho_c"]) == 32
+    soa, st, _ = hostk.discretize_drag(x, u, tf, cst, (float(g["cd"]), model), include_J2=True,
+                                       adaptive=None if uniform else {})
+    assert st.max() == 0
+    mode = "uni" if uniform else "def"
+    for n, o in zip(NAMES, hostk.stacked(soa, 1, x.shape[2])):
+        assert rel_err(_sel(o[0], ks), g[f"{mode}_{n}"]) < TOL_REF, (mode, n)
+    if not uniform:
+        # without the gradient (drho_func = 0) the reference's own answer is 7e-3 away on A_k and xi_k: the term is what is
+        # being tested; and a kernel given that model reproduces THAT answer
+        assert rel_err(g["def_A_k"], g["def_nograd_A_k"]) > 1e-3
+        model0 = fit_density(rho, lambda r: 0.0, np.moveaxis(x[:, 0:3, :], 1, 2).reshape(-1, 3))
+        assert len(model0["drho_c"]) == 0
+        soa0, st0, _ = hostk.discretize_drag(x, u, tf, cst, (float(g["cd"]), model0), include_J2=True, adaptive={})
+        for n, o in zip(NAMES, hostk.stacked(soa0, 1, x.shape[2])):
+            assert rel_err(_sel(o[0], ks), g[f"def_nograd_{n}"]) < TOL_REF, n
+
+
 @pytest.mark.parametrize("j2", [False, True])
 def test_drag_batch_matches_c_oracle(const, j2):
     import copy
