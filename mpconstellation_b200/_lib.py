@@ -16,8 +16,13 @@ CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libmpc_b200.so")
 SOURCES = ["mpc_b200.cu", "mpc_b200_drag.cu"]    # the drag-branch kernels have a translation unit of their own
 HEADERS = ["discretize_kernel.cuh", "discretize_adaptive_kernel.cuh", "discretize_default_kernel.cuh", "propagate_kernel.cuh", "propagate_rk45_kernel.cuh", "discretize_group_kernel.cuh", "constraint_terms_kernel.cuh", "discretize_drag_kernel.cuh", "discretize_pair_kernel.cuh", "mpc_b200_drag.h", os.path.join("..", "..", "include", "mpc_b200.h")]
+# No -split-compile: with it nvcc partitions the module for parallel compilation and the register allocation of the
+# 250-register kernels comes out differently from build to build (the same source gave discretize_default_kernel 253
+# registers / 296 B of stack in one build and 255 / 536 B in the next: 1.366 vs 1.390 ms on BASELINE configs[2];
+# profiles/r02_zz_ab_default_*.log).  Unsplit, every kernel compiles as it does on its own: 1.327 ms.  The two
+# translation units are compiled side by side instead (build()).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-split-compile", "0"]
+              "-Xcompiler", "-fPIC"]
 
 MPC_OUT_ROWS = 105
 ROW_A, ROW_BP, ROW_BN, ROW_SIGMA, ROW_XI = 0, 49, 70, 91, 98
@@ -75,13 +80,25 @@ def build(force=False, verbose=False):
     """Compile csrc/*.cu into csrc/libmpc_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     if not force and not needs_build():
         return SO_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", SO_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    import concurrent.futures
+    objs = [os.path.join(CSRC, os.path.splitext(src)[0] + ".o") for src in SOURCES]
+
+    def compile_one(src, obj):
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        return subprocess.run(cmd, capture_output=True, text=True)
+
+    with concurrent.futures.ThreadPoolExecutor(len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES, objs))
+    for res in results:
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            sys.stderr.write(res.stderr)
+    res = subprocess.run(["nvcc", "-shared", "-o", SO_PATH] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc (link) failed:\n" + res.stdout + res.stderr)
+    for obj in objs:
+        os.remove(obj)
     return SO_PATH
 
 

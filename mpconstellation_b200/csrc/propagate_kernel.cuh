@@ -72,10 +72,55 @@ __device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__r
     }
 }
 
-// f(y,u) without the tf factor (simulator.py:130-160); returns nonzero on non-positive mass
+// The FOH table law (KIND 3) evaluated through a one-entry cache of its knot interval.  The integrator's steps (0.001) are
+// short against the knot spacing (end_tau / (Ku - 1)), so consecutive stage times almost always fall between the same
+// two knots: the three divisions that place the interval (k / (Ku-1), (k+1) / (Ku-1), 1 / (hi - lo)) and the six table
+// loads are then the previous evaluation's.  Same operations on the same values as ctrl_eval<3>: bit-identical results.
+struct FohCache {
+    int k;
+    double lo, hi, iw, a[3], b[3];
+};
+
+__device__ __forceinline__ void ctrl_eval_foh_cached(const CtrlParams &C, const double *__restrict__ tab, double end_tau,
+                                                     double tau, FohCache &fc, double &ux, double &uy, double &uz)
+{
+    ux = uy = uz = 0.0;
+    if (tau <= end_tau) {
+        const int Ku = C.table_len;
+        const double t = tau / end_tau;
+        if (t == 1.0) {
+            ux = tab[Ku - 1];
+            uy = tab[2 * Ku - 1];
+            uz = tab[3 * Ku - 1];
+        } else {
+            const double km1 = (double)(Ku - 1);
+            int k = (int)floor(t * km1);
+            k = min(max(k, 0), Ku - 2);
+            if (k != fc.k) {
+                fc.k = k;
+                fc.lo = (double)k / km1;
+                fc.hi = (double)(k + 1) / km1;
+                fc.iw = 1.0 / (fc.hi - fc.lo);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    fc.a[i] = tab[i * Ku + k];
+                    fc.b[i] = tab[i * Ku + k + 1];
+                }
+            }
+            const double ln = (fc.hi - t) * fc.iw, lp = (t - fc.lo) * fc.iw;
+            ux = fma(ln, fc.a[0], lp * fc.b[0]);
+            uy = fma(ln, fc.a[1], lp * fc.b[1]);
+            uz = fma(ln, fc.a[2], lp * fc.b[2]);
+        }
+    }
+}
+
+// f(y,u) without the tf factor (simulator.py:130-160); returns nonzero on non-positive mass.  fc: the knot-interval cache
+// of the table law (KIND 3 only; nullptr = evaluate the law from scratch)
 template <int KIND, bool DRAG, bool J2>
 __device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C, const double *__restrict__ tab,
-                                        double end_tau, const double (&y)[7], double tau, double (&dy)[7])
+                                        double end_tau, const double (&y)[7], double tau, double (&dy)[7],
+                                        FohCache *fc = nullptr)
 {
     const double m = y[6];
     const double r2 = fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2]));
@@ -95,7 +140,8 @@ __device__ __forceinline__ int prop_rhs(const PropParams &P, const CtrlParams &C
         ay = fma(scm, fma(hz, y[0], -hx * y[2]), -mu3 * y[1]);
         az = fma(scm, fma(hx, y[1], -hy * y[0]), -mu3 * y[2]);
     } else {
-        ctrl_eval<KIND>(C, tab, end_tau, y, ir, tau, ux, uy, uz);
+        if (KIND == 3 && fc) ctrl_eval_foh_cached(C, tab, end_tau, tau, *fc, ux, uy, uz);
+        else ctrl_eval<KIND>(C, tab, end_tau, y, ir, tau, ux, uy, uz);
         ax = fma(-mu3, y[0], ux * im);
         ay = fma(-mu3, y[1], uy * im);
         az = fma(-mu3, y[2], uz * im);

@@ -80,6 +80,9 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
     int bad = 0, fail = 0, steps = 0;
     double t = 0.0;
 
+    FohCache foh;                 // KIND 3: knot interval of the table law shared by consecutive stage evaluations
+    foh.k = -1;
+    FohCache *const fc = (KIND == 3) ? &foh : nullptr;
     bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, y, 0.0, K[0]);
     // ---- select_initial_step (common.py), f = tf * k ------------------------------------------------------------
     double h_abs;
@@ -135,7 +138,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
 #pragma unroll
                 for (int i = 0; i < NC; ++i) ys[i] = fma(K[0][i], a10, y[i]);
                 if (CM) ys[6] = fma(K[0][6], hs * (1.0 / 5), y[6]);
-                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (1.0 / 5) * h, K[1]);
+                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (1.0 / 5) * h, K[1], fc);
             }
             have_k1 = false;
             {
@@ -144,7 +147,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
 #pragma unroll
                 for (int i = 0; i < NC; ++i) ys[i] = fma(K[1][i], a1, fma(K[0][i], a0, y[i]));
                 if (CM) ys[6] = fma(K[0][6], hs * (3.0 / 10), y[6]);
-                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (3.0 / 10) * h, K[2]);
+                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (3.0 / 10) * h, K[2], fc);
             }
             {
                 double ys[7];
@@ -152,7 +155,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
 #pragma unroll
                 for (int i = 0; i < NC; ++i) ys[i] = fma(K[2][i], a2, fma(K[1][i], a1, fma(K[0][i], a0, y[i])));
                 if (CM) ys[6] = fma(K[0][6], hs * (4.0 / 5), y[6]);
-                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (4.0 / 5) * h, K[3]);
+                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (4.0 / 5) * h, K[3], fc);
             }
             {
                 double ys[7];
@@ -162,7 +165,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 for (int i = 0; i < NC; ++i)
                     ys[i] = fma(K[3][i], a3, fma(K[2][i], a2, fma(K[1][i], a1, fma(K[0][i], a0, y[i]))));
                 if (CM) ys[6] = fma(K[0][6], hs * (8.0 / 9), y[6]);
-                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (8.0 / 9) * h, K[4]);
+                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + (8.0 / 9) * h, K[4], fc);
             }
             {
                 double ys[7];
@@ -172,7 +175,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 for (int i = 0; i < NC; ++i)
                     ys[i] = fma(K[4][i], a4, fma(K[3][i], a3, fma(K[2][i], a2, fma(K[1][i], a1, fma(K[0][i], a0, y[i])))));
                 if (CM) ys[6] = fma(K[0][6], hs, y[6]);
-                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + h, K[5]);
+                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t + h, K[5], fc);
             }
             {
                 const double b0 = hs * (35.0 / 384), b2 = hs * (500.0 / 1113), b3 = hs * (125.0 / 192),
@@ -181,7 +184,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
                 for (int i = 0; i < NC; ++i)
                     yn[i] = fma(K[5][i], b5, fma(K[4][i], b4, fma(K[3][i], b3, fma(K[2][i], b2, fma(K[0][i], b0, y[i])))));
                 if (CM) yn[6] = fma(K[0][6], hs, y[6]);
-                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, yn, t + h, K[6]);
+                bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, yn, t + h, K[6], fc);
             }
             double k1n[7];
             int bad_n = 0;
@@ -196,7 +199,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
 #pragma unroll
                 for (int i = 0; i < NC; ++i) ys[i] = fma(K[6][i], a10, yn[i]);
                 if (CM) ys[6] = fma(K[0][6], a10, yn[6]);
-                bad_n = prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t_new + (1.0 / 5) * h_pred, k1n);
+                bad_n = prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, ys, t_new + (1.0 / 5) * h_pred, k1n, fc);
             }
             // -- error norm (rk.py _estimate_error_norm) ---------------------------------------------------------------
             double eh[NC], esum0 = 0.0;
