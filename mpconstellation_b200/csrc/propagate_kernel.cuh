@@ -81,6 +81,24 @@ struct FohCache {
     double lo, hi, iw, a[3], b[3];
 };
 
+// The refill is a real call (the result comes back by value, so the cache itself stays in registers): inlined into the
+// seven stage evaluations of a step it made the hot loop 28 KB of code, most of it never executed.
+__device__ __noinline__ FohCache foh_cache_fill(const double *__restrict__ tab, int Ku, int k)
+{
+    FohCache fc;
+    const double km1 = (double)(Ku - 1);
+    fc.k = k;
+    fc.lo = (double)k / km1;
+    fc.hi = (double)(k + 1) / km1;
+    fc.iw = 1.0 / (fc.hi - fc.lo);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        fc.a[i] = tab[i * Ku + k];
+        fc.b[i] = tab[i * Ku + k + 1];
+    }
+    return fc;
+}
+
 __device__ __forceinline__ void ctrl_eval_foh_cached(const CtrlParams &C, const double *__restrict__ tab, double end_tau,
                                                      double tau, FohCache &fc, double &ux, double &uy, double &uz)
 {
@@ -96,17 +114,7 @@ __device__ __forceinline__ void ctrl_eval_foh_cached(const CtrlParams &C, const 
             const double km1 = (double)(Ku - 1);
             int k = (int)floor(t * km1);
             k = min(max(k, 0), Ku - 2);
-            if (k != fc.k) {
-                fc.k = k;
-                fc.lo = (double)k / km1;
-                fc.hi = (double)(k + 1) / km1;
-                fc.iw = 1.0 / (fc.hi - fc.lo);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    fc.a[i] = tab[i * Ku + k];
-                    fc.b[i] = tab[i * Ku + k + 1];
-                }
-            }
+            if (k != fc.k) fc = foh_cache_fill(tab, Ku, k);
             const double ln = (fc.hi - t) * fc.iw, lp = (t - fc.lo) * fc.iw;
             ux = fma(ln, fc.a[0], lp * fc.b[0]);
             uy = fma(ln, fc.a[1], lp * fc.b[1]);
