@@ -75,19 +75,29 @@ __device__ __forceinline__ void ctrl_eval(const CtrlParams &C, const double *__r
 // The FOH table law (KIND 3) evaluated through a one-entry cache of its knot interval.  The integrator's steps (0.001) are
 // short against the knot spacing (end_tau / (Ku - 1)), so consecutive stage times almost always fall between the same
 // two knots: the three divisions that place the interval (k / (Ku-1), (k+1) / (Ku-1), 1 / (hi - lo)) and the six table
-// loads are then the previous evaluation's.  Same operations on the same values as ctrl_eval<3>: bit-identical results.
+// loads are then the previous evaluation's (same values as ctrl_eval<3>; see ctrl_eval_foh_cached for the two places where
+// the arithmetic differs from it by a rounding).
 struct FohCache {
     int k;
     double lo, hi, iw, a[3], b[3];
+    double km1, inv_et;          // Ku - 1 and 1 / end_tau (set once, foh_cache_init)
 };
+
+__device__ __forceinline__ void foh_cache_init(FohCache &fc, int Ku, double end_tau)
+{
+    fc.k = -1;
+    fc.km1 = (double)(Ku - 1);
+    fc.inv_et = 1.0 / end_tau;
+}
 
 // The refill is a real call (the result comes back by value, so the cache itself stays in registers): inlined into the
 // seven stage evaluations of a step it made the hot loop 28 KB of code, most of it never executed.
-__device__ __noinline__ FohCache foh_cache_fill(const double *__restrict__ tab, int Ku, int k)
+__device__ __noinline__ FohCache foh_cache_fill(const double *__restrict__ tab, int Ku, int k, double km1, double inv_et)
 {
     FohCache fc;
-    const double km1 = (double)(Ku - 1);
     fc.k = k;
+    fc.km1 = km1;
+    fc.inv_et = inv_et;
     fc.lo = (double)k / km1;
     fc.hi = (double)(k + 1) / km1;
     fc.iw = 1.0 / (fc.hi - fc.lo);
@@ -99,28 +109,25 @@ __device__ __noinline__ FohCache foh_cache_fill(const double *__restrict__ tab, 
     return fc;
 }
 
+// Straight-line on the common path (the only branch is the refill): the quotient tau / end_tau from the stored reciprocal
+// and one correction step (q = tau y; q += (tau - q end_tau) y: the correctly rounded quotient but for rare last-bit
+// cases), the end point t = 1 through the last interval (lambda- = 0 there) and the cut-off after end_tau by a select --
+// the branches and slow-path guards of the literal form kept ptxas from scheduling across the seven stage evaluations.
 __device__ __forceinline__ void ctrl_eval_foh_cached(const CtrlParams &C, const double *__restrict__ tab, double end_tau,
                                                      double tau, FohCache &fc, double &ux, double &uy, double &uz)
 {
-    ux = uy = uz = 0.0;
-    if (tau <= end_tau) {
-        const int Ku = C.table_len;
-        const double t = tau / end_tau;
-        if (t == 1.0) {
-            ux = tab[Ku - 1];
-            uy = tab[2 * Ku - 1];
-            uz = tab[3 * Ku - 1];
-        } else {
-            const double km1 = (double)(Ku - 1);
-            int k = (int)floor(t * km1);
-            k = min(max(k, 0), Ku - 2);
-            if (k != fc.k) fc = foh_cache_fill(tab, Ku, k);
-            const double ln = (fc.hi - t) * fc.iw, lp = (t - fc.lo) * fc.iw;
-            ux = fma(ln, fc.a[0], lp * fc.b[0]);
-            uy = fma(ln, fc.a[1], lp * fc.b[1]);
-            uz = fma(ln, fc.a[2], lp * fc.b[2]);
-        }
-    }
+    const int Ku = C.table_len;
+    double t = tau * fc.inv_et;
+    t = fma(fma(-t, end_tau, tau), fc.inv_et, t);
+    int k = (int)(t * fc.km1);
+    k = min(max(k, 0), Ku - 2);
+    if (k != fc.k) fc = foh_cache_fill(tab, Ku, k, fc.km1, fc.inv_et);
+    const double ln = (fc.hi - t) * fc.iw, lp = (t - fc.lo) * fc.iw;
+    const bool on = tau <= end_tau;
+    const double vx = fma(ln, fc.a[0], lp * fc.b[0]), vy = fma(ln, fc.a[1], lp * fc.b[1]), vz = fma(ln, fc.a[2], lp * fc.b[2]);
+    ux = on ? vx : 0.0;
+    uy = on ? vy : 0.0;
+    uz = on ? vz : 0.0;
 }
 
 // f(y,u) without the tf factor (simulator.py:130-160); returns nonzero on non-positive mass.  fc: the knot-interval cache

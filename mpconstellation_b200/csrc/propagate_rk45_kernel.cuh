@@ -81,7 +81,7 @@ propagate_rk45_kernel(const double *__restrict__ y0, const double *__restrict__ 
     double t = 0.0;
 
     FohCache foh;                 // KIND 3: knot interval of the table law shared by consecutive stage evaluations
-    foh.k = -1;
+    foh_cache_init(foh, C.table_len, end_tau);
     FohCache *const fc = (KIND == 3) ? &foh : nullptr;
     bad |= prop_rhs<KIND, DRAG, J2>(P, C, tab, end_tau, y, 0.0, K[0]);
     // ---- select_initial_step (common.py), f = tf * k ------------------------------------------------------------
