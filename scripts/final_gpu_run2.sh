@@ -21,4 +21,4 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:disc
 python scripts/ncu_summary.py gpurun_out/prof_default_$tag.ncu-rep gpurun_out/prof_default_$tag.txt > /dev/null 2>&1; rm -f gpurun_out/prof_default_$tag.ncu-rep
 python scripts/r02_probe_default_quick.py 2>&1 | tail -1 | tee gpurun_out/probe_default_$tag.txt
 python scripts/r02_probe_prop_quick.py 2>&1 | tee gpurun_out/probe_prop_$tag.txt | tail -3
-python scripts/r02_probe_sequence_quick.py 2>&1 | tee gpurun_out/probe_seq_$tag.txt | tail -2
+python scripts/r02_probe_sequence_quick.py 2>&1 | tee gpurun_out/probe_seq_$tag.txt | tail -4

@@ -30,7 +30,7 @@ def timed(fn, n=10):
 
 
 res = {}
-for N, K, tf in ((256, 60, 2.0), (4096, 200, 2.0)):
+for N, K, tf in ((256, 60, 2.0), (256, 200, 2.0), (4096, 60, 2.0), (4096, 200, 2.0)):
     Y, const = make_constellation(N)
     y0 = torch.from_numpy(Y).to(dev)
     tfd = torch.full((N,), tf, dtype=torch.float64, device=dev)
